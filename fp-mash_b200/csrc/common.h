@@ -1,0 +1,47 @@
+// common.h -- context, error handling and scratch memory shared by the C-ABI translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "../../include/fpmash_b200.h"
+
+namespace fpm {
+
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define FPM_CUDA(call)                                                          \
+    do {                                                                        \
+        cudaError_t e__ = (call);                                               \
+        if (e__ != cudaSuccess) return fpm::cuda_fail(e__, #call, __FILE__, __LINE__); \
+    } while (0)
+
+// Grow-only device scratch buffer.
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes);
+    void release();
+    template <typename T> T* as() const { return (T*)p; }
+};
+
+}  // namespace fpm
+
+struct fpm_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    uint64_t launches = 0;
+    int sm_count = 0;
+    // sketch scratch
+    fpm::DevBuf seq, goff, thresh, active, toff, tmask, tkeys, tcnt, tpos, maxcnt, maxpos, overflow,
+        stat, tiles, args, outh, outc, outn, outk, firstpos, tr_off, tr_cursor, tr_pos, glist;
+    // dist scratch
+    fpm::DevBuf d_ref, d_qry, d_rs, d_qs, d_rl, d_ql, d_out, d_misc;
+    // pinned staging for small host<->device exchanges
+    void* h_pinned = nullptr;
+    size_t h_pinned_cap = 0;
+    int ensure_pinned(size_t bytes);
+};

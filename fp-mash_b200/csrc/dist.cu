@@ -1,0 +1,359 @@
+// dist.cu -- all-vs-all sketch comparison on sm_100a.
+//
+// Replaces compare() -> compareSketches() -> pValue() (CommandDistance.cpp:335-450).
+//
+// Two kernels:
+//   dist_literal_kernel   one thread per pair, the reference loop executed literally from
+//                         row-major panels in global memory.  Defines the result for ANY
+//                         input (fp-mode lists are unsorted and may repeat) and
+//                         is the fallback when the fast path's preconditions do not hold.
+//   dist_tile_kernel      the fast path for ascending duplicate-free lists.  One CTA owns a
+//                         16-query x 32-reference tile (512 pairs, one thread each).  The 48
+//                         sketches are staged in shared memory as lane-private COLUMNS
+//                         (element p of sketch c at [p][c]), so the data-dependent reads of a
+//                         sequential merge are bank-conflict free whatever position each lane
+//                         has reached.  Sketches are streamed in phases of DT_ROWS rows
+//                         bounded by value: V = min over the 48 columns of the first element
+//                         that did not fit, so every element < V of every column is resident
+//                         and each pair can merge up to V independently; elements >= V are
+//                         masked to the +inf sentinel, which makes "phase exhausted" and
+//                         "list exhausted" the same cheap test.  Pairs that reach denom == s
+//                         stop early (for unrelated same-size genomes one phase suffices).
+//
+// This is set intersection, not a contraction: no tensor cores.  The bound is integer
+// compare / shared-memory throughput.
+#include <algorithm>
+#include <string.h>
+#include "common.h"
+#include "dist_math.h"
+
+namespace fpm {
+
+constexpr uint64_t DT_INF = ~0ULL;
+constexpr int DT_Q = 16;            // query columns per CTA
+constexpr int DT_R = 32;            // reference columns per CTA (two 16-column planes)
+constexpr int DT_COLS = DT_Q + DT_R;
+constexpr int DT_ROWS = 576;        // rows resident per phase
+constexpr int DT_THREADS = DT_Q * DT_R;   // 512
+
+struct DistArgs {
+    uint32_t s;
+    int kmer_size;
+    double kmer_space, max_distance, max_pvalue;
+};
+
+__device__ __forceinline__ void finish_pair(const DistArgs& a, uint64_t common, uint64_t denom, uint64_t len_ref, uint64_t len_qry, fpm_pair* out)
+{
+    double d = mash_distance(common, denom, a.kmer_size);
+    fpm_pair o;
+    o.numer = (uint32_t)common;
+    o.denom = (uint32_t)denom;
+    o.distance = d;
+    o.pvalue = 0.;
+    bool pass = !(a.max_distance >= 0 && d > a.max_distance);          // CommandDistance.cpp:416-419
+    if (pass) {
+        o.pvalue = mash_pvalue(common, len_ref, len_qry, a.kmer_space, denom);
+        if (a.max_pvalue >= 0 && o.pvalue > a.max_pvalue) pass = false; // :425-428
+    }
+    if (pass) o.denom |= FPM_PAIR_PASS;
+    *out = o;
+}
+
+__global__ void __launch_bounds__(256) dist_literal_kernel(fpm_panel ref, fpm_panel qry, DistArgs a, fpm_pair* out, unsigned long long* steps)
+{
+    uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t total = ref.n * qry.n;
+    unsigned long long my_steps = 0;
+    if (p < total) {
+        uint64_t q = p / ref.n, r = p % ref.n;
+        const uint64_t* A = ref.hashes + r * ref.stride;
+        const uint64_t* B = qry.hashes + q * qry.stride;
+        uint64_t na = ref.sizes[r], nb = qry.sizes[q];
+        uint64_t i = 0, j = 0, common = 0, denom = 0;
+        while (denom < a.s && i < na && j < nb) {                       // CommandDistance.cpp:376-387
+            uint64_t x = A[i], y = B[j];
+            if (x < y) i++;
+            else if (y < x) j++;
+            else { i++; j++; common++; }
+            denom++;
+        }
+        my_steps = denom;
+        if (denom < a.s) {                                              // :389-400
+            if (i < na) denom += na - i;
+            if (j < nb) denom += nb - j;
+            if (denom > a.s) denom = a.s;
+        }
+        finish_pair(a, common, denom, ref.lengths[r], qry.lengths[q], out + p);
+    }
+    if (steps) {
+        for (int o = 16; o; o >>= 1) my_steps += __shfl_down_sync(0xffffffffu, my_steps, o);
+        if ((threadIdx.x & 31) == 0 && my_steps) atomicAdd(steps, my_steps);
+    }
+}
+
+// Row-major [n][stride] -> column tiles [ceil(n/16)][rows][16], +inf beyond each sketch's size.
+// flags[0] |= 1 if a real hash equals the sentinel or a row is not strictly ascending (the
+// host then falls back to the literal kernel).
+__global__ void __launch_bounds__(256) dist_pack_kernel(fpm_panel pn, uint64_t rows, uint64_t* packed, uint32_t* flags)
+{
+    uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;     // over n16*16 x rows, column fastest
+    uint64_t n16 = (pn.n + 15) / 16;
+    if (idx >= n16 * 16 * rows) return;
+    uint64_t c = idx & 15, row = (idx >> 4) % rows, tile = (idx >> 4) / rows;
+    uint64_t sk = tile * 16 + c;
+    uint64_t v = DT_INF;
+    if (sk < pn.n && row < pn.sizes[sk]) {
+        v = pn.hashes[sk * pn.stride + row];
+        bool bad = v == DT_INF;
+        if (row > 0 && pn.hashes[sk * pn.stride + row - 1] >= v) bad = true;
+        if (bad) atomicOr(flags, 1u);
+    }
+    packed[idx] = v;
+}
+
+__global__ void __launch_bounds__(DT_THREADS, 1)
+dist_tile_kernel(const uint64_t* __restrict__ pref, const uint64_t* __restrict__ pqry, uint64_t rows_ref, uint64_t rows_qry,
+                 uint64_t n_ref, uint64_t n_qry, const uint64_t* __restrict__ len_ref, const uint64_t* __restrict__ len_qry,
+                 DistArgs a, fpm_pair* __restrict__ out, unsigned long long* steps)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* colQ = reinterpret_cast<uint64_t*>(smem_raw);                 // [(DT_ROWS+1)][16]
+    uint64_t* colR = colQ + (DT_ROWS + 1) * 16;                             // 2 planes of [(DT_ROWS+1)][16]
+    __shared__ uint32_t s_cursor[DT_COLS];
+    __shared__ unsigned long long s_V;
+
+    const int t = threadIdx.x;
+    const int w = t >> 5, l = t & 31, h = l >> 4, i16 = l & 15;
+    const int qc = i16;                              // my query column
+    const int rc = ((i16 + w) & 15);                 // my reference column within plane h
+    const uint64_t q_tile = blockIdx.y, r_tile2 = blockIdx.x;               // r_tile2 indexes pairs of 16-col tiles
+    const uint64_t* gQ = pqry + q_tile * rows_qry * 16;
+    const uint64_t* gR[2] = {pref + (2 * r_tile2) * rows_ref * 16, pref + (2 * r_tile2 + 1) * rows_ref * 16};
+    const uint64_t n_rtiles16 = (n_ref + 15) / 16;
+    const bool plane1_exists = 2 * r_tile2 + 1 < n_rtiles16;
+
+    if (t < DT_COLS) s_cursor[t] = 0;
+    uint32_t common = 0, denom = 0;
+    bool done = false;
+    __syncthreads();
+
+    for (;;) {
+        // ---- V = smallest element that does not fit this phase ------------------------
+        if (t == 0) s_V = DT_INF;
+        __syncthreads();
+        if (t < DT_COLS) {
+            uint64_t row = (uint64_t)s_cursor[t] + DT_ROWS;
+            uint64_t v = DT_INF;
+            if (t < DT_Q) { if (row < rows_qry) v = gQ[row * 16 + t]; }
+            else {
+                int pl = (t - DT_Q) >> 4, c = (t - DT_Q) & 15;
+                if ((pl == 0 || plane1_exists) && row < rows_ref) v = gR[pl][row * 16 + c];
+            }
+            if (v != DT_INF) atomicMin(&s_V, (unsigned long long)v);
+        }
+        __syncthreads();
+        const uint64_t V = s_V;
+        // ---- stage rows [cursor, cursor+DT_ROWS) of every column, masking >= V --------
+        for (int idx = t; idx < DT_ROWS * 16; idx += DT_THREADS) {
+            int c = idx & 15, r = idx >> 4;
+            uint64_t row = (uint64_t)s_cursor[c] + r;
+            uint64_t v = row < rows_qry ? gQ[row * 16 + c] : DT_INF;
+            colQ[r * 16 + c] = v < V ? v : DT_INF;
+        }
+#pragma unroll
+        for (int pl = 0; pl < 2; pl++) {
+            uint64_t* dst = colR + pl * (DT_ROWS + 1) * 16;
+            bool exists = pl == 0 || plane1_exists;
+            for (int idx = t; idx < DT_ROWS * 16; idx += DT_THREADS) {
+                int c = idx & 15, r = idx >> 4;
+                uint64_t row = (uint64_t)s_cursor[DT_Q + 16 * pl + c] + r;
+                uint64_t v = (exists && row < rows_ref) ? gR[pl][row * 16 + c] : DT_INF;
+                dst[r * 16 + c] = v < V ? v : DT_INF;
+            }
+        }
+        if (t < 16) { colQ[DT_ROWS * 16 + t] = DT_INF; colR[DT_ROWS * 16 + t] = DT_INF; colR[(DT_ROWS + 1) * 16 + DT_ROWS * 16 + t] = DT_INF; }
+        __syncthreads();
+
+        // ---- merge up to V ------------------------------------------------------------
+        if (!done) {
+            const uint64_t* pa = colQ + qc;
+            const uint64_t* pb = colR + h * (DT_ROWS + 1) * 16 + rc;
+            uint64_t x = *pa, y = *pb;
+            // reference loop with one simplification: an exhausted list reads +inf, and the
+            // "complete the union" tail (CommandDistance.cpp:389-400) is the same loop running
+            // on the surviving list one element per step.
+            while (denom < a.s && (x & y) != DT_INF) {
+                bool le = x <= y, ge = y <= x;
+                common += le & ge;
+                denom++;
+                if (le) { pa += 16; x = *pa; }
+                if (ge) { pb += 16; y = *pb; }
+            }
+            if (denom >= a.s || V == DT_INF) done = true;
+        }
+        // ---- anyone left?  then advance every column past its elements < V ------------
+        if (!__syncthreads_or(done ? 0 : 1)) break;
+        if (t < DT_COLS) {
+            const uint64_t* col = t < DT_Q ? colQ + t : colR + ((t - DT_Q) >> 4) * (DT_ROWS + 1) * 16 + ((t - DT_Q) & 15);
+            uint32_t lo = 0, hi = DT_ROWS;   // first row holding +inf (masked or exhausted)
+            while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (col[mid * 16] != DT_INF) lo = mid + 1; else hi = mid; }
+            s_cursor[t] += lo;
+        }
+        // (the barrier at the top of the next phase orders these writes before their readers)
+    }
+
+    // ---- results: stage in shared memory, then coalesced row writes ---------------------
+    __syncthreads();
+    fpm_pair* res = reinterpret_cast<fpm_pair*>(smem_raw);                  // [16][32]
+    const uint64_t qg = q_tile * 16 + qc, rg = r_tile2 * 32 + 16 * h + rc;
+    unsigned long long my_steps = denom;
+    if (qg < n_qry && rg < n_ref) {
+        finish_pair(a, common, denom, len_ref[rg], len_qry[qg], &res[qc * 32 + 16 * h + rc]);
+    }
+    __syncthreads();
+    {
+        // 16 rows of 32 pairs = 768 bytes each, written as 8-byte words
+        const uint64_t* src = reinterpret_cast<const uint64_t*>(res);
+        for (int idx = t; idx < 16 * 32 * 3; idx += DT_THREADS) {
+            int row = idx / 96, wd = idx % 96, pr = wd / 3;
+            uint64_t qg2 = q_tile * 16 + row, rg2 = r_tile2 * 32 + pr;
+            if (qg2 < n_qry && rg2 < n_ref)
+                reinterpret_cast<uint64_t*>(out + qg2 * n_ref + rg2)[wd % 3] = src[idx];
+        }
+    }
+    if (steps) {
+        for (int o = 16; o; o >>= 1) my_steps += __shfl_down_sync(0xffffffffu, my_steps, o);
+        if (l == 0 && my_steps) atomicAdd(steps, my_steps);
+    }
+}
+
+static int run_dist(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* d_ref, const fpm_panel* d_qry, fpm_pair* d_out,
+                    uint64_t* d_steps, uint32_t max_size_ref, uint32_t max_size_qry)
+{
+    DistArgs a;
+    a.s = p->sketch_size; a.kmer_size = p->kmer_size; a.kmer_space = p->kmer_space;
+    a.max_distance = p->max_distance; a.max_pvalue = p->max_pvalue;
+    cudaStream_t st = ctx->stream;
+    uint64_t total = d_ref->n * d_qry->n;
+    if (total == 0) return FPM_OK;
+    bool fast = p->sorted_unique != 0;
+    if (fast) {
+        int rc;
+        uint64_t rows_r = (uint64_t)max_size_ref + 1, rows_q = (uint64_t)max_size_qry + 1;
+        uint64_t nr16 = (d_ref->n + 15) / 16, nq16 = (d_qry->n + 15) / 16;
+        if ((rc = ctx->d_ref.ensure(nr16 * 16 * rows_r * 8))) return rc;
+        if ((rc = ctx->d_qry.ensure(nq16 * 16 * rows_q * 8))) return rc;
+        if ((rc = ctx->d_misc.ensure(64))) return rc;
+        FPM_CUDA(cudaMemsetAsync(ctx->d_misc.p, 0, 64, st));
+        uint64_t n1 = nr16 * 16 * rows_r, n2 = nq16 * 16 * rows_q;
+        dist_pack_kernel<<<(uint32_t)((n1 + 255) / 256), 256, 0, st>>>(*d_ref, rows_r, ctx->d_ref.as<uint64_t>(), ctx->d_misc.as<uint32_t>());
+        dist_pack_kernel<<<(uint32_t)((n2 + 255) / 256), 256, 0, st>>>(*d_qry, rows_q, ctx->d_qry.as<uint64_t>(), ctx->d_misc.as<uint32_t>());
+        ctx->launches += 2;
+        FPM_CUDA(cudaGetLastError());
+        uint32_t flag = 0;
+        FPM_CUDA(cudaMemcpyAsync(&flag, ctx->d_misc.p, 4, cudaMemcpyDeviceToHost, st));
+        FPM_CUDA(cudaStreamSynchronize(st));
+        if (flag) fast = false;   // sentinel collision or unsorted input: literal loop defines the result
+        else {
+            size_t smem = (size_t)DT_COLS * (DT_ROWS + 1) * 8;
+            FPM_CUDA(cudaFuncSetAttribute(dist_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            dim3 grid((uint32_t)((d_ref->n + 31) / 32), (uint32_t)nq16);
+            if (grid.y > 65535) { set_error("query panel too tall for one launch (%llu sketches): split it", (unsigned long long)d_qry->n); return FPM_ERR_ARG; }
+            dist_tile_kernel<<<grid, DT_THREADS, smem, st>>>(ctx->d_ref.as<uint64_t>(), ctx->d_qry.as<uint64_t>(), rows_r, rows_q, d_ref->n,
+                                                             d_qry->n, d_ref->lengths, d_qry->lengths, a, d_out, (unsigned long long*)d_steps);
+            ctx->launches++;
+            FPM_CUDA(cudaGetLastError());
+        }
+    }
+    if (!fast) {
+        uint64_t blocks = (total + 255) / 256;
+        if (blocks > 0x7fffffffull) { set_error("too many pairs for one launch"); return FPM_ERR_ARG; }
+        dist_literal_kernel<<<(uint32_t)blocks, 256, 0, st>>>(*d_ref, *d_qry, a, d_out, (unsigned long long*)d_steps);
+        ctx->launches++;
+        FPM_CUDA(cudaGetLastError());
+    }
+    return FPM_OK;
+}
+
+static int max_size_dev(fpm_ctx* ctx, const fpm_panel* d, uint32_t* out)
+{
+    std::vector<uint32_t> h(d->n);
+    if (d->n) {
+        FPM_CUDA(cudaMemcpyAsync(h.data(), d->sizes, sizeof(uint32_t) * d->n, cudaMemcpyDeviceToHost, ctx->stream));
+        FPM_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    uint32_t m = 0;
+    for (uint32_t v : h) m = std::max(m, v);
+    *out = m;
+    return FPM_OK;
+}
+
+static int check_dist(const fpm_dist_params* p, const fpm_panel* ref, const fpm_panel* qry)
+{
+    if (!p || !ref || !qry) { set_error("NULL argument"); return FPM_ERR_ARG; }
+    if (p->sketch_size >= 0x7fffffffu) { set_error("sketch size too large"); return FPM_ERR_ARG; }
+    if (p->kmer_size < 1) { set_error("kmer size must be >= 1"); return FPM_ERR_ARG; }
+    return FPM_OK;
+}
+
+}  // namespace fpm
+
+using namespace fpm;
+
+extern "C" {
+
+int fpm_dist_tile_dev(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* d_ref, const fpm_panel* d_qry, fpm_pair* d_out, uint64_t* d_merge_steps)
+{
+    if (!ctx) { set_error("ctx is NULL"); return FPM_ERR_ARG; }
+    int rc = check_dist(p, d_ref, d_qry);
+    if (rc) return rc;
+    FPM_CUDA(cudaSetDevice(ctx->device));
+    uint32_t mr = 0, mq = 0;
+    if ((rc = max_size_dev(ctx, d_ref, &mr))) return rc;
+    if ((rc = max_size_dev(ctx, d_qry, &mq))) return rc;
+    if (mr > d_ref->stride || mq > d_qry->stride) { set_error("a sketch size exceeds the panel stride"); return FPM_ERR_ARG; }
+    return run_dist(ctx, p, d_ref, d_qry, d_out, d_merge_steps, mr, mq);
+}
+
+int fpm_dist_tile(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* ref, const fpm_panel* qry, fpm_pair* out)
+{
+    if (!ctx) { set_error("ctx is NULL"); return FPM_ERR_ARG; }
+    int rc = check_dist(p, ref, qry);
+    if (rc) return rc;
+    if (ref->n == 0 || qry->n == 0) return FPM_OK;
+    FPM_CUDA(cudaSetDevice(ctx->device));
+    uint32_t mr = 0, mq = 0;
+    for (uint64_t i = 0; i < ref->n; i++) mr = std::max(mr, ref->sizes[i]);
+    for (uint64_t i = 0; i < qry->n; i++) mq = std::max(mq, qry->sizes[i]);
+    if (mr > ref->stride || mq > qry->stride) { set_error("a sketch size exceeds the panel stride"); return FPM_ERR_ARG; }
+    cudaStream_t st = ctx->stream;
+    // inputs: hashes | sizes | lengths for both panels
+    size_t rh = ref->n * ref->stride * 8, qh = qry->n * qry->stride * 8;
+    if ((rc = ctx->d_rs.ensure(rh + ref->n * 12 + 64))) return rc;
+    if ((rc = ctx->d_qs.ensure(qh + qry->n * 12 + 64))) return rc;
+    if ((rc = ctx->d_out.ensure(ref->n * qry->n * sizeof(fpm_pair)))) return rc;
+    unsigned char* br = ctx->d_rs.as<unsigned char>();
+    unsigned char* bq = ctx->d_qs.as<unsigned char>();
+    fpm_panel dr = *ref, dq = *qry;
+    dr.hashes = (const uint64_t*)br; dr.lengths = (const uint64_t*)(br + rh); dr.sizes = (const uint32_t*)(br + rh + ref->n * 8);
+    dq.hashes = (const uint64_t*)bq; dq.lengths = (const uint64_t*)(bq + qh); dq.sizes = (const uint32_t*)(bq + qh + qry->n * 8);
+    if (rh) FPM_CUDA(cudaMemcpyAsync((void*)dr.hashes, ref->hashes, rh, cudaMemcpyHostToDevice, st));
+    FPM_CUDA(cudaMemcpyAsync((void*)dr.lengths, ref->lengths, ref->n * 8, cudaMemcpyHostToDevice, st));
+    FPM_CUDA(cudaMemcpyAsync((void*)dr.sizes, ref->sizes, ref->n * 4, cudaMemcpyHostToDevice, st));
+    if (qh) FPM_CUDA(cudaMemcpyAsync((void*)dq.hashes, qry->hashes, qh, cudaMemcpyHostToDevice, st));
+    FPM_CUDA(cudaMemcpyAsync((void*)dq.lengths, qry->lengths, qry->n * 8, cudaMemcpyHostToDevice, st));
+    FPM_CUDA(cudaMemcpyAsync((void*)dq.sizes, qry->sizes, qry->n * 4, cudaMemcpyHostToDevice, st));
+    if ((rc = run_dist(ctx, p, &dr, &dq, ctx->d_out.as<fpm_pair>(), nullptr, mr, mq))) return rc;
+    FPM_CUDA(cudaMemcpyAsync(out, ctx->d_out.p, ref->n * qry->n * sizeof(fpm_pair), cudaMemcpyDeviceToHost, st));
+    FPM_CUDA(cudaStreamSynchronize(st));
+    return FPM_OK;
+}
+
+double fpm_pvalue(uint64_t x, uint64_t len_ref, uint64_t len_qry, double kmer_space, uint64_t n)
+{
+    return mash_pvalue(x, len_ref, len_qry, kmer_space, n);
+}
+
+double fpm_distance(uint64_t common, uint64_t denom, int kmer_size) { return mash_distance(common, denom, kmer_size); }
+
+}  // extern "C"

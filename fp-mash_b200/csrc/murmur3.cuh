@@ -1,0 +1,82 @@
+// murmur3.cuh -- MurmurHash3_x64_128 on device, h1 only.
+//
+// Replaces MurmurHash3_x64_128 (MurmurHash3.cpp:255-331) + getHash (hash.cpp:12-40).
+// Only out[0] (h1) is ever consumed by the reference, so the final "h2 += h1" is dropped.
+// All arithmetic is 64-bit integer (IMAD / SHF / LOP3 / IADD3 on sm_100a): the kernel
+// built on this is integer-ALU bound, not HBM bound.
+#pragma once
+#include <stdint.h>
+
+namespace fpm {
+
+__device__ __forceinline__ uint64_t rotl64(uint64_t x, int r)
+{
+    uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+    uint32_t nlo, nhi;
+    if (r == 32) { nlo = hi; nhi = lo; }
+    else if (r < 32) { nhi = __funnelshift_l(lo, hi, r); nlo = __funnelshift_l(hi, lo, r); }
+    else { nhi = __funnelshift_l(hi, lo, r - 32); nlo = __funnelshift_l(lo, hi, r - 32); }
+    return ((uint64_t)nhi << 32) | nlo;
+}
+
+__device__ __forceinline__ uint64_t fmix64(uint64_t k)
+{
+    k ^= k >> 33;
+    k *= 0xff51afd7ed558ccdULL;
+    k ^= k >> 33;
+    k *= 0xc4ceb9fe1a85ec53ULL;
+    k ^= k >> 33;
+    return k;
+}
+
+#define FPM_MC1 0x87c37b91114253d5ULL
+#define FPM_MC2 0x4cf5ad432745937fULL
+
+__device__ __forceinline__ uint64_t mm_k1(uint64_t k) { k *= FPM_MC1; k = rotl64(k, 31); k *= FPM_MC2; return k; }
+__device__ __forceinline__ uint64_t mm_k2(uint64_t k) { k *= FPM_MC2; k = rotl64(k, 33); k *= FPM_MC1; return k; }
+
+__device__ __forceinline__ void mm_block(uint64_t& h1, uint64_t& h2, uint64_t k1, uint64_t k2)
+{
+    h1 ^= mm_k1(k1);
+    h1 = rotl64(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729ULL;
+    h2 ^= mm_k2(k2);
+    h2 = rotl64(h2, 31); h2 += h1; h2 = h2 * 5 + 0x38495ab5ULL;
+}
+
+__device__ __forceinline__ uint64_t mm_finish(uint64_t h1, uint64_t h2, uint64_t len)
+{
+    h1 ^= len; h2 ^= len;
+    h1 += h2; h2 += h1;
+    h1 = fmix64(h1); h2 = fmix64(h2);
+    return h1 + h2;
+}
+
+// Hash of a LEN-byte key given as zero-padded little-endian 64-bit words w[0..3]
+// (bytes >= LEN are zero).  LEN is a compile-time constant in 1..32, so the block/tail
+// structure of MurmurHash3.cpp:270-314 resolves statically.
+template <int LEN>
+__device__ __forceinline__ uint64_t murmur3_h1_fixed(const uint64_t (&w)[4], uint32_t seed)
+{
+    uint64_t h1 = seed, h2 = seed;
+    constexpr int nblocks = LEN / 16;
+    constexpr int rem = LEN & 15;
+    if (nblocks >= 1) mm_block(h1, h2, w[0], w[1]);
+    if (nblocks >= 2) mm_block(h1, h2, w[2], w[3]);
+    if (rem > 8) h2 ^= mm_k2(w[2 * nblocks + 1]);
+    if (rem > 0) h1 ^= mm_k1(w[2 * nblocks]);
+    return mm_finish(h1, h2, (uint64_t)LEN);
+}
+
+// Generic length, key read as little-endian u64 words from memory (fingerprint token rows:
+// the key IS an array of uint64, so every block is two tokens and the tail is 0 or 8 bytes).
+__device__ __forceinline__ uint64_t murmur3_h1_tokens(const uint64_t* tok, uint64_t n_tok, uint32_t seed)
+{
+    uint64_t h1 = seed, h2 = seed;
+    uint64_t i = 0;
+    for (; i + 2 <= n_tok; i += 2) mm_block(h1, h2, tok[i], tok[i + 1]);
+    if (i < n_tok) h1 ^= mm_k1(tok[i]);          // 8-byte tail -> lane 1 only (case 8)
+    // len is an int in the reference; n_tok*8 stays far below 2^31 for any real line
+    return mm_finish(h1, h2, (uint64_t)(int64_t)(int32_t)(uint32_t)(n_tok * 8));
+}
+
+}  // namespace fpm

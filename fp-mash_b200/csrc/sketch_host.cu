@@ -1,0 +1,411 @@
+// sketch_host.cu -- C-ABI entry points for sketching: pass orchestration around the kernels.
+//
+// Exactness does not depend on the threshold guess: a sketch is accepted only when the
+// table held at least s qualifying hashes (then the s smallest of them ARE the bottom-s) or
+// when the threshold admitted every hash; otherwise that sketch is re-run with a threshold
+// scaled from the density just measured.
+#include <algorithm>
+#include <string.h>
+#include "common.h"
+#include "sketch_kernels.cuh"
+#include "sketch_launch.h"
+#include "sketch_select.h"
+
+namespace fpm {
+
+#define FPM_TAB(K) launch_sketch_hash_k##K,
+static const sketch_hash_launcher g_hash_launch[32] = {FPM_FOR_ALL_K(FPM_TAB)};
+#undef FPM_TAB
+#define FPM_TAB(K) launch_hash_stream_k##K,
+static const hash_stream_launcher g_stream_launch[32] = {FPM_FOR_ALL_K(FPM_TAB)};
+#undef FPM_TAB
+#define FPM_TAB(K) launch_count_windows_k##K,
+static const count_windows_launcher g_count_launch[32] = {FPM_FOR_ALL_K(FPM_TAB)};
+#undef FPM_TAB
+
+static uint32_t pow2ceil(uint64_t v)
+{
+    uint64_t p = 64;
+    while (p < v) p <<= 1;
+    return (uint32_t)std::min<uint64_t>(p, 1ull << 31);
+}
+
+static int check_params(const fpm_sketch_params* p)
+{
+    if (!p) { set_error("sketch params are NULL"); return FPM_ERR_ARG; }
+    if (p->kmer_size < 1 || p->kmer_size > 32) { set_error("k-mer size %d outside 1..32", p->kmer_size); return FPM_ERR_ARG; }
+    if (p->sketch_size < 1) { set_error("sketch size must be >= 1"); return FPM_ERR_ARG; }
+    if (p->min_cov < 1) { set_error("min_cov must be >= 1"); return FPM_ERR_ARG; }
+    // The accelerated path is the nucleotide alphabet (alphabetNucleotide, Sketch.h:25).
+    for (int c = 0; c < 256; c++) {
+        bool want = c == 'A' || c == 'C' || c == 'G' || c == 'T';
+        if ((p->alphabet[c] != 0) != want) {
+            set_error("only the nucleotide alphabet ACGT is accelerated (alphabet differs at byte %d)", c);
+            return FPM_ERR_UNSUPPORTED;
+        }
+    }
+    bool use64 = p->kmer_size > 16;   // 4^k > 2^32  (Sketch.cpp:1288)
+    if ((p->use64 != 0) != use64) { set_error("use64=%d inconsistent with k=%d for a 4-letter alphabet", p->use64, p->kmer_size); return FPM_ERR_ARG; }
+    uint64_t s = p->sketch_size;
+    uint64_t target = s <= 4096 ? 2 * s + 64 : s + s / 4 + 256;
+    if (target > SK_SORT_CAP) { set_error("sketch size %u exceeds the shared-memory selection limit (12900)", p->sketch_size); return FPM_ERR_UNSUPPORTED; }
+    return FPM_OK;
+}
+
+struct GroupPlan {
+    uint64_t thresh;     // accept h <= thresh
+    bool all;            // thresh admits every hash
+    uint32_t cap;        // table capacity (power of two)
+};
+
+static const uint64_t kAll64 = ~0ULL;
+
+static uint64_t scale_threshold(uint64_t bits_full /*2^bits - 1*/, double frac)
+{
+    if (frac >= 1.0) return bits_full;
+    long double v = (long double)bits_full * (long double)frac;
+    if (v < 1) v = 1;
+    return (uint64_t)v;
+}
+
+int sketch_batch_dev_impl(fpm_ctx* ctx, const fpm_sketch_params* p, const uint8_t* d_seq, uint64_t n_bytes,
+                          const uint64_t* h_goff, uint32_t n_groups, uint64_t* d_out_hashes, uint32_t* d_out_counts,
+                          uint32_t* d_out_n, uint64_t* d_out_kmers)
+{
+    int rc = check_params(p);
+    if (rc) return rc;
+    if (n_groups == 0) return FPM_OK;
+    if (!d_seq || !h_goff || !d_out_hashes || !d_out_n) { set_error("NULL buffer"); return FPM_ERR_ARG; }
+    if (h_goff[0] != 0 || h_goff[n_groups] != n_bytes) { set_error("group_offsets must start at 0 and end at seq_bytes"); return FPM_ERR_ARG; }
+    for (uint32_t g = 0; g < n_groups; g++)
+        if (h_goff[g + 1] < h_goff[g]) { set_error("group_offsets not ascending at %u", g); return FPM_ERR_ARG; }
+    if (((uintptr_t)d_seq & 15) != 0) { set_error("d_seq must be 16-byte aligned"); return FPM_ERR_ARG; }
+    if (n_bytes == 0) {
+        FPM_CUDA(cudaMemsetAsync(d_out_n, 0, sizeof(uint32_t) * n_groups, ctx->stream));
+        if (d_out_kmers) FPM_CUDA(cudaMemsetAsync(d_out_kmers, 0, sizeof(uint64_t) * n_groups, ctx->stream));
+        return FPM_OK;
+    }
+    const uint64_t n_tiles64 = (n_bytes + SK_TILE_WINDOWS - 1) / SK_TILE_WINDOWS;
+    if (n_tiles64 > 0x7fffffffull) { set_error("batch too large (%llu bytes)", (unsigned long long)n_bytes); return FPM_ERR_ARG; }
+    const uint32_t n_tiles = (uint32_t)n_tiles64;
+
+    const int K = p->kmer_size;
+    const uint32_t s = p->sketch_size;
+    const bool canon = !p->noncanonical;
+    const uint64_t full = p->use64 ? kAll64 : 0xffffffffULL;
+    const uint64_t target = s <= 4096 ? 2ull * s + 64 : (uint64_t)s + s / 4 + 256;
+    const bool want_counts = p->want_counts && d_out_counts;
+    cudaStream_t st = ctx->stream;
+
+    // ---- plan ---------------------------------------------------------------------------
+    std::vector<GroupPlan> plan(n_groups);
+    for (uint32_t g = 0; g < n_groups; g++) {
+        uint64_t n = h_goff[g + 1] - h_goff[g];
+        GroupPlan& pl = plan[g];
+        if (n <= 2 * target && n <= SK_SORT_CAP) {
+            pl.all = true; pl.thresh = full; pl.cap = pow2ceil(2 * n);
+        } else {
+            pl.all = false;
+            pl.thresh = scale_threshold(full, (double)target / (double)n);
+            pl.cap = pow2ceil(4 * target);
+        }
+    }
+
+    // persistent per-call device arrays
+    if ((rc = ctx->goff.ensure(sizeof(uint64_t) * (n_groups + 1)))) return rc;
+    if ((rc = ctx->thresh.ensure(sizeof(uint64_t) * n_groups))) return rc;
+    if ((rc = ctx->active.ensure(n_groups))) return rc;
+    if ((rc = ctx->toff.ensure(sizeof(uint64_t) * n_groups))) return rc;
+    if ((rc = ctx->tmask.ensure(sizeof(uint32_t) * n_groups))) return rc;
+    if ((rc = ctx->maxcnt.ensure(sizeof(uint32_t) * n_groups))) return rc;
+    if ((rc = ctx->maxpos.ensure(sizeof(uint64_t) * n_groups))) return rc;
+    if ((rc = ctx->overflow.ensure(sizeof(uint32_t) * n_groups))) return rc;
+    if ((rc = ctx->stat.ensure(sizeof(uint32_t) * 4 * n_groups))) return rc;
+    if ((rc = ctx->args.ensure(sizeof(SketchArgs)))) return rc;
+    if ((rc = ctx->firstpos.ensure(want_counts ? sizeof(uint64_t) * (uint64_t)n_groups * s : 8))) return rc;
+    FPM_CUDA(cudaMemcpyAsync(ctx->goff.p, h_goff, sizeof(uint64_t) * (n_groups + 1), cudaMemcpyHostToDevice, st));
+
+    std::vector<uint8_t> active(n_groups, 1);
+    std::vector<uint64_t> h_thresh(n_groups), h_toff(n_groups);
+    std::vector<uint32_t> h_tmask(n_groups), h_stat(4 * (size_t)n_groups), h_over(n_groups), h_outn(n_groups, 0), h_topcnt(n_groups, 0);
+    std::vector<uint32_t> tiles;
+
+    uint32_t* d_stat_nq = ctx->stat.as<uint32_t>();
+    uint32_t* d_stat_nd = d_stat_nq + n_groups;
+    uint32_t* d_stat_top = d_stat_nd + n_groups;
+
+    int max_smem = 0;
+    FPM_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+    if ((size_t)max_smem < (size_t)SK_SORT_CAP * 8) { set_error("device offers only %d bytes of opt-in shared memory", max_smem); return FPM_ERR_UNSUPPORTED; }
+    if (configure_sketch_select((size_t)SK_SORT_CAP * 8) != 0) { set_error("cudaFuncSetAttribute(select) failed"); return FPM_ERR_CUDA; }
+
+    for (int pass = 0; pass < 12; pass++) {
+        // tables for the active groups
+        uint64_t slots = 0;
+        uint32_t max_cap = 64;
+        uint32_t n_active = 0;
+        for (uint32_t g = 0; g < n_groups; g++) {
+            h_thresh[g] = plan[g].thresh;
+            if (active[g]) {
+                h_toff[g] = slots; h_tmask[g] = plan[g].cap - 1; slots += plan[g].cap;
+                max_cap = std::max(max_cap, plan[g].cap); n_active++;
+            } else { h_toff[g] = 0; h_tmask[g] = 0; }
+        }
+        if (n_active == 0) break;
+        if ((rc = ctx->tkeys.ensure(slots * 8))) return rc;
+        if ((rc = ctx->tcnt.ensure(slots * 4))) return rc;
+        if ((rc = ctx->tpos.ensure(slots * 8))) return rc;
+        FPM_CUDA(cudaMemsetAsync(ctx->tkeys.p, 0xff, slots * 8, st));
+        FPM_CUDA(cudaMemsetAsync(ctx->tcnt.p, 0, slots * 4, st));
+        FPM_CUDA(cudaMemsetAsync(ctx->tpos.p, 0xff, slots * 8, st));
+        FPM_CUDA(cudaMemsetAsync(ctx->maxcnt.p, 0, sizeof(uint32_t) * n_groups, st));
+        FPM_CUDA(cudaMemsetAsync(ctx->maxpos.p, 0xff, sizeof(uint64_t) * n_groups, st));
+        FPM_CUDA(cudaMemsetAsync(ctx->overflow.p, 0, sizeof(uint32_t) * n_groups, st));
+        FPM_CUDA(cudaMemcpyAsync(ctx->thresh.p, h_thresh.data(), sizeof(uint64_t) * n_groups, cudaMemcpyHostToDevice, st));
+        FPM_CUDA(cudaMemcpyAsync(ctx->active.p, active.data(), n_groups, cudaMemcpyHostToDevice, st));
+        FPM_CUDA(cudaMemcpyAsync(ctx->toff.p, h_toff.data(), sizeof(uint64_t) * n_groups, cudaMemcpyHostToDevice, st));
+        FPM_CUDA(cudaMemcpyAsync(ctx->tmask.p, h_tmask.data(), sizeof(uint32_t) * n_groups, cudaMemcpyHostToDevice, st));
+
+        // tile list: identity on the first pass, tiles of the active groups afterwards
+        const uint32_t* d_tiles = nullptr;
+        uint32_t grid = n_tiles;
+        if (pass > 0) {
+            tiles.clear();
+            for (uint32_t g = 0; g < n_groups; g++) {
+                if (!active[g] || h_goff[g + 1] == h_goff[g]) continue;
+                uint32_t t0 = (uint32_t)(h_goff[g] / SK_TILE_WINDOWS), t1 = (uint32_t)((h_goff[g + 1] - 1) / SK_TILE_WINDOWS);
+                if (!tiles.empty() && tiles.back() >= t0) t0 = tiles.back() + 1;
+                for (uint32_t t = t0; t <= t1; t++) tiles.push_back(t);
+            }
+            if ((rc = ctx->tiles.ensure(sizeof(uint32_t) * std::max<size_t>(tiles.size(), 1)))) return rc;
+            FPM_CUDA(cudaMemcpyAsync(ctx->tiles.p, tiles.data(), sizeof(uint32_t) * tiles.size(), cudaMemcpyHostToDevice, st));
+            d_tiles = ctx->tiles.as<uint32_t>();
+            grid = (uint32_t)tiles.size();
+        }
+
+        SketchArgs a;
+        memset(&a, 0, sizeof a);
+        a.seq = d_seq; a.n_bytes = n_bytes; a.group_off = ctx->goff.as<uint64_t>(); a.n_groups = n_groups;
+        a.tile_list = d_tiles; a.thresh = ctx->thresh.as<uint64_t>(); a.active = ctx->active.as<uint8_t>();
+        a.tkeys = ctx->tkeys.as<uint64_t>(); a.tcnt = ctx->tcnt.as<uint32_t>(); a.tpos = ctx->tpos.as<uint64_t>();
+        a.toff = ctx->toff.as<uint64_t>(); a.tmask = ctx->tmask.as<uint32_t>();
+        a.maxkey_cnt = ctx->maxcnt.as<uint32_t>(); a.maxkey_pos = ctx->maxpos.as<uint64_t>();
+        a.overflow = ctx->overflow.as<uint32_t>();
+        a.sketch_size = s; a.seed = p->seed; a.fold_case = !p->preserve_case; a.hash32 = !p->use64;
+        FPM_CUDA(cudaMemcpyAsync(ctx->args.p, &a, sizeof a, cudaMemcpyHostToDevice, st));
+        if (grid) {
+            g_hash_launch[K - 1](canon, grid, st, ctx->args.as<SketchArgs>(), 0);
+            ctx->launches++;
+            FPM_CUDA(cudaGetLastError());
+        }
+
+        SelectArgs sa;
+        sa.tkeys = a.tkeys; sa.tcnt = a.tcnt; sa.tpos = a.tpos; sa.toff = a.toff; sa.tmask = a.tmask;
+        sa.maxkey_cnt = a.maxkey_cnt; sa.maxkey_pos = a.maxkey_pos; sa.active = a.active;
+        sa.sketch_size = s; sa.min_cov = p->min_cov;
+        sa.sort_cap = std::min<uint32_t>(SK_SORT_CAP, max_cap);
+        sa.out_hashes = d_out_hashes; sa.out_counts = want_counts ? d_out_counts : nullptr;
+        sa.out_firstpos = nullptr;
+        sa.out_n = d_out_n; sa.stat_nq = d_stat_nq; sa.stat_nd = d_stat_nd; sa.stat_topcnt = d_stat_top;
+        launch_sketch_select(n_groups, (size_t)sa.sort_cap * 8, st, sa);
+        ctx->launches++;
+        FPM_CUDA(cudaGetLastError());
+
+        FPM_CUDA(cudaMemcpyAsync(h_stat.data(), ctx->stat.p, sizeof(uint32_t) * 3 * n_groups, cudaMemcpyDeviceToHost, st));
+        FPM_CUDA(cudaMemcpyAsync(h_over.data(), ctx->overflow.p, sizeof(uint32_t) * n_groups, cudaMemcpyDeviceToHost, st));
+        FPM_CUDA(cudaStreamSynchronize(st));
+
+        // ---- decide ---------------------------------------------------------------------
+        bool again = false;
+        for (uint32_t g = 0; g < n_groups; g++) {
+            if (!active[g]) continue;
+            uint32_t nq = h_stat[g], nd = h_stat[n_groups + g];
+            GroupPlan& pl = plan[g];
+            uint64_t n = h_goff[g + 1] - h_goff[g];
+            bool too_many = h_over[g] || nq > sa.sort_cap;
+            bool too_few = !pl.all && nq < s;
+            if (!too_many && !too_few) {
+                active[g] = 0;
+                h_outn[g] = std::min<uint32_t>(nq, s);
+                h_topcnt[g] = h_stat[2 * (size_t)n_groups + g];
+                continue;
+            }
+            again = true;
+            double cur = pl.all ? 1.0 : ((double)pl.thresh + 1.0) / ((double)full + 1.0);
+            double next;
+            if (too_many) next = (nq > sa.sort_cap && nq > 0) ? cur * (double)target / (double)nq : cur / 4;
+            else next = nq >= 16 ? cur * 1.15 * (double)target / (double)nq : cur * 16;
+            if (next >= 1.0) { pl.all = true; pl.thresh = full; next = 1.0; }
+            else { pl.all = false; pl.thresh = scale_threshold(full, next); }
+            double nd_next = ((double)nd + 16) * (next / cur) * 1.3 + 256;
+            if (nd_next > (double)n) nd_next = (double)n;
+            pl.cap = std::max(pow2ceil((uint64_t)(2 * nd_next)), pow2ceil(4 * target));
+        }
+        if (!again) break;
+        if (pass == 11) { set_error("bottom-s selection did not converge"); return FPM_ERR_CUDA; }
+    }
+
+    // ---- order-dependent multiplicity of the largest element (full sketches only) -------
+    if (want_counts) {
+        std::vector<uint32_t> tg;
+        for (uint32_t g = 0; g < n_groups; g++)
+            if (h_outn[g] == s && h_topcnt[g] > p->min_cov) tg.push_back(g);
+        if (!tg.empty()) {
+            // bucket layout from the counts just written
+            std::vector<uint32_t> row(s);
+            std::vector<uint64_t> h_troff((size_t)n_groups * s, 0);
+            uint64_t total = 0;
+            for (uint32_t g : tg) {
+                FPM_CUDA(cudaMemcpyAsync(row.data(), d_out_counts + (uint64_t)g * s, sizeof(uint32_t) * s, cudaMemcpyDeviceToHost, st));
+                FPM_CUDA(cudaStreamSynchronize(st));
+                for (uint32_t r = 0; r < s; r++) { h_troff[(uint64_t)g * s + r] = total; total += row[r]; }
+            }
+            if ((rc = ctx->tr_off.ensure(sizeof(uint64_t) * (uint64_t)n_groups * s))) return rc;
+            if ((rc = ctx->tr_cursor.ensure(sizeof(uint32_t) * (uint64_t)n_groups * s))) return rc;
+            if ((rc = ctx->tr_pos.ensure(sizeof(uint64_t) * std::max<uint64_t>(total, 1)))) return rc;
+            if ((rc = ctx->glist.ensure(sizeof(uint32_t) * tg.size()))) return rc;
+            FPM_CUDA(cudaMemcpyAsync(ctx->tr_off.p, h_troff.data(), sizeof(uint64_t) * (uint64_t)n_groups * s, cudaMemcpyHostToDevice, st));
+            FPM_CUDA(cudaMemsetAsync(ctx->tr_cursor.p, 0, sizeof(uint32_t) * (uint64_t)n_groups * s, st));
+            FPM_CUDA(cudaMemcpyAsync(ctx->glist.p, tg.data(), sizeof(uint32_t) * tg.size(), cudaMemcpyHostToDevice, st));
+            std::fill(active.begin(), active.end(), 0);
+            for (uint32_t g : tg) active[g] = 1;
+            FPM_CUDA(cudaMemcpyAsync(ctx->active.p, active.data(), n_groups, cudaMemcpyHostToDevice, st));
+            for (uint32_t g = 0; g < n_groups; g++) h_thresh[g] = plan[g].thresh;
+            FPM_CUDA(cudaMemcpyAsync(ctx->thresh.p, h_thresh.data(), sizeof(uint64_t) * n_groups, cudaMemcpyHostToDevice, st));
+            tiles.clear();
+            for (uint32_t g : tg) {
+                uint32_t t0 = (uint32_t)(h_goff[g] / SK_TILE_WINDOWS), t1 = (uint32_t)((h_goff[g + 1] - 1) / SK_TILE_WINDOWS);
+                if (!tiles.empty() && tiles.back() >= t0) t0 = tiles.back() + 1;
+                for (uint32_t t = t0; t <= t1; t++) tiles.push_back(t);
+            }
+            if ((rc = ctx->tiles.ensure(sizeof(uint32_t) * tiles.size()))) return rc;
+            FPM_CUDA(cudaMemcpyAsync(ctx->tiles.p, tiles.data(), sizeof(uint32_t) * tiles.size(), cudaMemcpyHostToDevice, st));
+            SketchArgs a;
+            memset(&a, 0, sizeof a);
+            a.seq = d_seq; a.n_bytes = n_bytes; a.group_off = ctx->goff.as<uint64_t>(); a.n_groups = n_groups;
+            a.tile_list = ctx->tiles.as<uint32_t>(); a.thresh = ctx->thresh.as<uint64_t>(); a.active = ctx->active.as<uint8_t>();
+            a.fin_hashes = d_out_hashes; a.fin_n = d_out_n; a.tr_off = ctx->tr_off.as<uint64_t>(); a.tr_cap = d_out_counts;
+            a.tr_cursor = ctx->tr_cursor.as<uint32_t>(); a.tr_pos = ctx->tr_pos.as<uint64_t>();
+            a.sketch_size = s; a.seed = p->seed; a.fold_case = !p->preserve_case; a.hash32 = !p->use64;
+            FPM_CUDA(cudaMemcpyAsync(ctx->args.p, &a, sizeof a, cudaMemcpyHostToDevice, st));
+            g_hash_launch[K - 1](canon, (uint32_t)tiles.size(), st, ctx->args.as<SketchArgs>(), 1);
+            ctx->launches++;
+            FPM_CUDA(cudaGetLastError());
+            launch_sketch_topcount((uint32_t)tg.size(), st, ctx->glist.as<uint32_t>(), s, p->min_cov, a.tr_off, a.tr_cap, a.tr_pos, d_out_counts);
+            ctx->launches++;
+            FPM_CUDA(cudaGetLastError());
+        }
+    }
+
+    if (d_out_kmers) {
+        FPM_CUDA(cudaMemsetAsync(d_out_kmers, 0, sizeof(uint64_t) * n_groups, st));
+        SketchArgs a;
+        memset(&a, 0, sizeof a);
+        a.seq = d_seq; a.n_bytes = n_bytes; a.group_off = ctx->goff.as<uint64_t>(); a.n_groups = n_groups;
+        a.fold_case = !p->preserve_case;
+        FPM_CUDA(cudaMemcpyAsync(ctx->args.p, &a, sizeof a, cudaMemcpyHostToDevice, st));
+        g_count_launch[K - 1](n_tiles, st, ctx->args.as<SketchArgs>(), (unsigned long long*)d_out_kmers);
+        ctx->launches++;
+        FPM_CUDA(cudaGetLastError());
+    }
+    FPM_CUDA(cudaStreamSynchronize(st));
+    return FPM_OK;
+}
+
+}  // namespace fpm
+
+using namespace fpm;
+
+extern "C" {
+
+int fpm_sketch_batch_dev(fpm_ctx* ctx, const fpm_sketch_params* p, const uint8_t* d_seq, uint64_t seq_bytes,
+                         const uint64_t* h_group_offsets, uint32_t n_groups, uint64_t* d_out_hashes, uint32_t* d_out_counts,
+                         uint32_t* d_out_n, uint64_t* d_out_kmers)
+{
+    if (!ctx) { set_error("ctx is NULL"); return FPM_ERR_ARG; }
+    FPM_CUDA(cudaSetDevice(ctx->device));
+    return sketch_batch_dev_impl(ctx, p, d_seq, seq_bytes, h_group_offsets, n_groups, d_out_hashes, d_out_counts, d_out_n, d_out_kmers);
+}
+
+int fpm_sketch_batch(fpm_ctx* ctx, const fpm_sketch_params* p, const uint8_t* seq, uint64_t seq_bytes,
+                     const uint64_t* group_offsets, uint32_t n_groups, uint64_t* out_hashes, uint32_t* out_counts,
+                     uint32_t* out_n, uint64_t* out_kmers)
+{
+    if (!ctx) { set_error("ctx is NULL"); return FPM_ERR_ARG; }
+    int rc = check_params(p);
+    if (rc) return rc;
+    if (n_groups == 0) return FPM_OK;
+    if (!seq && seq_bytes) { set_error("seq is NULL"); return FPM_ERR_ARG; }
+    FPM_CUDA(cudaSetDevice(ctx->device));
+    const uint64_t s = p->sketch_size;
+    if ((rc = ctx->seq.ensure(seq_bytes + 64))) return rc;
+    if ((rc = ctx->outh.ensure(sizeof(uint64_t) * n_groups * s))) return rc;
+    if ((rc = ctx->outc.ensure(sizeof(uint32_t) * n_groups * s))) return rc;
+    if ((rc = ctx->outn.ensure(sizeof(uint32_t) * n_groups))) return rc;
+    if ((rc = ctx->outk.ensure(sizeof(uint64_t) * n_groups))) return rc;
+    FPM_CUDA(cudaMemcpyAsync(ctx->seq.p, seq, seq_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    bool counts = p->want_counts && out_counts;
+    rc = sketch_batch_dev_impl(ctx, p, ctx->seq.as<uint8_t>(), seq_bytes, group_offsets, n_groups, ctx->outh.as<uint64_t>(),
+                               counts ? ctx->outc.as<uint32_t>() : nullptr, ctx->outn.as<uint32_t>(),
+                               out_kmers ? ctx->outk.as<uint64_t>() : nullptr);
+    if (rc) return rc;
+    FPM_CUDA(cudaMemcpyAsync(out_hashes, ctx->outh.p, sizeof(uint64_t) * n_groups * s, cudaMemcpyDeviceToHost, ctx->stream));
+    if (counts) FPM_CUDA(cudaMemcpyAsync(out_counts, ctx->outc.p, sizeof(uint32_t) * n_groups * s, cudaMemcpyDeviceToHost, ctx->stream));
+    FPM_CUDA(cudaMemcpyAsync(out_n, ctx->outn.p, sizeof(uint32_t) * n_groups, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_kmers) FPM_CUDA(cudaMemcpyAsync(out_kmers, ctx->outk.p, sizeof(uint64_t) * n_groups, cudaMemcpyDeviceToHost, ctx->stream));
+    FPM_CUDA(cudaStreamSynchronize(ctx->stream));
+    return FPM_OK;
+}
+
+int fpm_kmer_hashes(fpm_ctx* ctx, const fpm_sketch_params* p, const uint8_t* seq, uint64_t seq_bytes, uint64_t* out_hashes, uint64_t* out_count)
+{
+    if (!ctx) { set_error("ctx is NULL"); return FPM_ERR_ARG; }
+    int rc = check_params(p);
+    if (rc) return rc;
+    if (out_count) *out_count = 0;
+    if (seq_bytes == 0) return FPM_OK;
+    FPM_CUDA(cudaSetDevice(ctx->device));
+    if ((rc = ctx->seq.ensure(seq_bytes + 64))) return rc;
+    if ((rc = ctx->outh.ensure(sizeof(uint64_t) * seq_bytes))) return rc;
+    if ((rc = ctx->outc.ensure(seq_bytes))) return rc;
+    FPM_CUDA(cudaMemcpyAsync(ctx->seq.p, seq, seq_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    uint32_t grid = (uint32_t)((seq_bytes + SK_TILE_WINDOWS - 1) / SK_TILE_WINDOWS);
+    g_stream_launch[p->kmer_size - 1](!p->noncanonical, grid, ctx->stream, ctx->seq.as<uint8_t>(), seq_bytes, p->seed,
+                                      !p->preserve_case, !p->use64, ctx->outh.as<uint64_t>(), ctx->outc.as<uint8_t>());
+    ctx->launches++;
+    FPM_CUDA(cudaGetLastError());
+    std::vector<uint64_t> h(seq_bytes);
+    std::vector<uint8_t> v(seq_bytes);
+    FPM_CUDA(cudaMemcpyAsync(h.data(), ctx->outh.p, sizeof(uint64_t) * seq_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    FPM_CUDA(cudaMemcpyAsync(v.data(), ctx->outc.p, seq_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    FPM_CUDA(cudaStreamSynchronize(ctx->stream));
+    uint64_t n = 0;
+    for (uint64_t i = 0; i < seq_bytes; i++)
+        if (v[i]) out_hashes[n++] = h[i];
+    if (out_count) *out_count = n;
+    return FPM_OK;
+}
+
+int fpm_fp_hash_batch(fpm_ctx* ctx, const uint64_t* tokens, const uint64_t* line_offsets, uint64_t n_lines, uint32_t seed,
+                      int use64, uint64_t* out_hashes)
+{
+    if (!ctx) { set_error("ctx is NULL"); return FPM_ERR_ARG; }
+    if (n_lines == 0) return FPM_OK;
+    if (!line_offsets || !out_hashes) { set_error("NULL buffer"); return FPM_ERR_ARG; }
+    FPM_CUDA(cudaSetDevice(ctx->device));
+    uint64_t n_tok = line_offsets[n_lines];
+    int rc;
+    if ((rc = ctx->seq.ensure(sizeof(uint64_t) * std::max<uint64_t>(n_tok, 1)))) return rc;
+    if ((rc = ctx->goff.ensure(sizeof(uint64_t) * (n_lines + 1)))) return rc;
+    if ((rc = ctx->outh.ensure(sizeof(uint64_t) * n_lines))) return rc;
+    if (n_tok) FPM_CUDA(cudaMemcpyAsync(ctx->seq.p, tokens, sizeof(uint64_t) * n_tok, cudaMemcpyHostToDevice, ctx->stream));
+    FPM_CUDA(cudaMemcpyAsync(ctx->goff.p, line_offsets, sizeof(uint64_t) * (n_lines + 1), cudaMemcpyHostToDevice, ctx->stream));
+    launch_fp_hash(n_lines, ctx->stream, ctx->seq.as<uint64_t>(), ctx->goff.as<uint64_t>(), seed, use64, ctx->outh.as<uint64_t>());
+    ctx->launches++;
+    FPM_CUDA(cudaGetLastError());
+    FPM_CUDA(cudaMemcpyAsync(out_hashes, ctx->outh.p, sizeof(uint64_t) * n_lines, cudaMemcpyDeviceToHost, ctx->stream));
+    FPM_CUDA(cudaStreamSynchronize(ctx->stream));
+    return FPM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,157 @@
+// sketch_select.cu -- bottom-s selection, the order-dependent top count, and the -fp line hash.
+#include "sketch_kernels.cuh"
+#include "sketch_select.h"
+
+namespace fpm {
+
+// ---------------------------------------------------------------------------------------
+// Selection: one CTA per sketch.
+// ---------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256) sketch_select_kernel(const SelectArgs a)
+{
+    extern __shared__ uint64_t s_keys[];
+    __shared__ uint32_t s_nq, s_nd;
+    const uint32_t g = blockIdx.x;
+    if (!a.active[g]) return;
+    const uint64_t base = a.toff[g];
+    const uint32_t mask = a.tmask[g];
+    if (threadIdx.x == 0) { s_nq = 0; s_nd = 0; }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i <= mask; i += blockDim.x) {
+        uint64_t key = a.tkeys[base + i];
+        if (key != SK_EMPTY) {
+            atomicAdd(&s_nd, 1u);
+            if (a.tcnt[base + i] >= a.min_cov) {
+                uint32_t idx = atomicAdd(&s_nq, 1u);
+                if (idx < a.sort_cap) s_keys[idx] = key;
+            }
+        }
+    }
+    if (threadIdx.x == 0 && a.maxkey_cnt[g]) {
+        atomicAdd(&s_nd, 1u);
+        if (a.maxkey_cnt[g] >= a.min_cov) {
+            uint32_t idx = atomicAdd(&s_nq, 1u);
+            if (idx < a.sort_cap) s_keys[idx] = SK_EMPTY;
+        }
+    }
+    __syncthreads();
+    const uint32_t nq = s_nq;
+    if (threadIdx.x == 0) { a.stat_nq[g] = nq; a.stat_nd[g] = s_nd; a.stat_topcnt[g] = 0; }
+    __syncthreads();
+    if (nq > a.sort_cap) { if (threadIdx.x == 0) a.out_n[g] = 0; return; }
+    uint32_t P = 1;
+    while (P < nq) P <<= 1;
+    for (uint32_t i = nq + threadIdx.x; i < P; i += blockDim.x) s_keys[i] = SK_EMPTY;
+    __syncthreads();
+    // bitonic sort, ascending
+    for (uint32_t k = 2; k <= P; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) {
+                uint32_t ixj = i ^ j;
+                if (ixj > i) {
+                    uint64_t x = s_keys[i], y = s_keys[ixj];
+                    bool up = (i & k) == 0;
+                    if ((x > y) == up) { s_keys[i] = y; s_keys[ixj] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    const uint32_t n_out = nq < a.sketch_size ? nq : a.sketch_size;
+    if (threadIdx.x == 0) a.out_n[g] = n_out;
+    for (uint32_t i = threadIdx.x; i < n_out; i += blockDim.x) {
+        uint64_t key = s_keys[i];
+        uint64_t o = (uint64_t)g * a.sketch_size + i;
+        a.out_hashes[o] = key;
+        {
+            uint32_t cnt; uint64_t fp;
+            if (key == SK_EMPTY) { cnt = a.maxkey_cnt[g]; fp = a.maxkey_pos[g]; }
+            else {
+                uint32_t slot = table_slot(key, mask);
+                while (a.tkeys[base + slot] != key) slot = (slot + 1) & mask;
+                cnt = a.tcnt[base + slot]; fp = a.tpos[base + slot];
+            }
+            if (a.out_counts) a.out_counts[o] = cnt;
+            if (i == n_out - 1) a.stat_topcnt[g] = cnt;
+            if (a.out_firstpos) a.out_firstpos[o] = fp;
+        }
+    }
+}
+
+// Order-dependent multiplicity of the largest element of a FULL sketch:
+// counts(T) = #occurrences of T at stream position <= t*, t* = max over the sketch of the
+// position of each hash's min_cov-th occurrence.  One CTA per listed group; positions of
+// every occurrence of the sketch's hashes were bucketed by the trace pass.
+__global__ void __launch_bounds__(256) sketch_topcount_kernel(const uint32_t* groups, uint32_t sketch_size, uint32_t min_cov,
+                                                              const uint64_t* tr_off, const uint32_t* tr_cap,
+                                                              const uint64_t* tr_pos, uint32_t* out_counts)
+{
+    __shared__ unsigned long long s_tstar;
+    __shared__ uint32_t s_cnt;
+    const uint32_t g = groups[blockIdx.x];
+    if (threadIdx.x == 0) { s_tstar = 0; s_cnt = 0; }
+    __syncthreads();
+    for (uint32_t r = threadIdx.x; r < sketch_size; r += blockDim.x) {
+        uint64_t b = (uint64_t)g * sketch_size + r;
+        const uint64_t* p = tr_pos + tr_off[b];
+        uint32_t n = tr_cap[b];
+        // min_cov-th smallest position (min_cov is tiny: repeated minimum extraction)
+        uint64_t prev = 0; bool first = true; uint64_t kth = 0;
+        uint32_t need = min_cov;
+        while (need) {
+            uint64_t best = ~0ULL; uint32_t mult = 0;
+            for (uint32_t i = 0; i < n; i++) {
+                uint64_t v = p[i];
+                if (!first && v <= prev) continue;
+                if (v < best) { best = v; mult = 1; } else if (v == best) mult++;
+            }
+            kth = best; prev = best; first = false;
+            need = mult >= need ? 0 : need - mult;
+        }
+        atomicMax(&s_tstar, (unsigned long long)kth);
+    }
+    __syncthreads();
+    const uint64_t tstar = s_tstar;
+    uint64_t b = (uint64_t)g * sketch_size + (sketch_size - 1);
+    const uint64_t* p = tr_pos + tr_off[b];
+    uint32_t n = tr_cap[b], c = 0;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) c += p[i] <= tstar;
+    atomicAdd(&s_cnt, c);
+    __syncthreads();
+    if (threadIdx.x == 0) out_counts[b] = s_cnt;
+}
+
+// -fp mode: one thread per fingerprint line.
+__global__ void fp_hash_kernel(const uint64_t* tokens, const uint64_t* line_off, uint64_t n_lines, uint32_t seed, int use64, uint64_t* out)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_lines) return;
+    uint64_t h = murmur3_h1_tokens(tokens + line_off[i], line_off[i + 1] - line_off[i], seed);
+    out[i] = use64 ? h : (h & 0xffffffffULL);
+}
+
+
+void launch_sketch_select(uint32_t n_groups, size_t smem_bytes, cudaStream_t st, const SelectArgs& a)
+{
+    sketch_select_kernel<<<n_groups, 256, smem_bytes, st>>>(a);
+}
+
+int configure_sketch_select(size_t max_smem_bytes)
+{
+    return (int)cudaFuncSetAttribute(sketch_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem_bytes);
+}
+
+void launch_sketch_topcount(uint32_t n_list, cudaStream_t st, const uint32_t* d_groups, uint32_t sketch_size, uint32_t min_cov,
+                            const uint64_t* tr_off, const uint32_t* tr_cap, const uint64_t* tr_pos, uint32_t* out_counts)
+{
+    sketch_topcount_kernel<<<n_list, 256, 0, st>>>(d_groups, sketch_size, min_cov, tr_off, tr_cap, tr_pos, out_counts);
+}
+
+void launch_fp_hash(uint64_t n_lines, cudaStream_t st, const uint64_t* tokens, const uint64_t* line_off, uint32_t seed, int use64, uint64_t* out)
+{
+    uint32_t grid = (uint32_t)((n_lines + 255) / 256);
+    fp_hash_kernel<<<grid, 256, 0, st>>>(tokens, line_off, n_lines, seed, use64, out);
+}
+
+}  // namespace fpm

@@ -1,0 +1,297 @@
+"""fpmash_b200 -- ctypes binding of the C ABI in include/fpmash_b200.h.
+
+This is plumbing for tests and bench.py: it loads fp-mash_b200/lib/libfpmash_b200.so (the
+hand-written sm_100a kernels) and exposes the reference's hot-path operations with the
+reference's own argument names.  There is NO CPU fallback: if the library is missing the
+import fails, and if no CUDA device is present every compute call raises FpmError.
+
+Reference interfaces mirrored (mash/src/mash/ of UmbertoDellaMonica/fp-mash):
+    sketch_batch    <- sketchFile / sketchSequence / addMinHashes   (Sketch.cpp:1299-1517, 664-735)
+    fp_hash_batch   <- getHashFingerPrint via initFromFingerprints   (hash.cpp:45-73, Sketch.cpp:132)
+    dist_tile       <- compare / compareSketches / pValue            (CommandDistance.cpp:335-450)
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "..", "lib", "libfpmash_b200.so"))
+HEADER_PATH = os.path.normpath(os.path.join(_HERE, "..", "..", "..", "include", "fpmash_b200.h"))
+
+FPM_OK = 0
+FPM_ERR_NO_DEVICE = -1
+FPM_ERR_CUDA = -2
+FPM_ERR_ARG = -3
+FPM_ERR_UNSUPPORTED = -4
+FPM_ERR_NOMEM = -5
+FPM_PAIR_PASS = 0x80000000
+
+u8p = C.POINTER(C.c_uint8)
+u32p = C.POINTER(C.c_uint32)
+u64p = C.POINTER(C.c_uint64)
+
+
+class FpmError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("fpmash_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class SketchParams(C.Structure):
+    _fields_ = [("kmer_size", C.c_int32), ("sketch_size", C.c_uint32), ("seed", C.c_uint32),
+                ("min_cov", C.c_uint32), ("noncanonical", C.c_uint8), ("preserve_case", C.c_uint8),
+                ("use64", C.c_uint8), ("want_counts", C.c_uint8), ("alphabet", C.c_uint8 * 256)]
+
+
+class Pair(C.Structure):
+    _fields_ = [("numer", C.c_uint32), ("denom", C.c_uint32), ("distance", C.c_double), ("pvalue", C.c_double)]
+
+
+PAIR_DTYPE = np.dtype([("numer", "<u4"), ("denom", "<u4"), ("distance", "<f8"), ("pvalue", "<f8")])
+
+
+class DistParams(C.Structure):
+    _fields_ = [("sketch_size", C.c_uint32), ("kmer_size", C.c_int32), ("kmer_space", C.c_double),
+                ("max_distance", C.c_double), ("max_pvalue", C.c_double), ("sorted_unique", C.c_uint8)]
+
+
+class Panel(C.Structure):
+    _fields_ = [("hashes", C.c_void_p), ("sizes", C.c_void_p), ("lengths", C.c_void_p),
+                ("n", C.c_uint64), ("stride", C.c_uint64)]
+
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError("fpmash_b200: %s is missing -- build it with `make -C fp-mash_b200` "
+                      "(or __graft_entry__.build()); there is no CPU fallback" % LIB_PATH)
+
+lib = C.CDLL(LIB_PATH)
+
+_VP = C.c_void_p
+lib.fpm_abi_version.restype = C.c_int
+lib.fpm_device_count.restype = C.c_int
+lib.fpm_ctx_create.argtypes = [C.c_int, C.POINTER(_VP)]
+lib.fpm_ctx_destroy.argtypes = [_VP]
+lib.fpm_last_error.restype = C.c_char_p
+lib.fpm_ctx_sync.argtypes = [_VP]
+lib.fpm_ctx_stream.restype = _VP
+lib.fpm_ctx_stream.argtypes = [_VP]
+lib.fpm_ctx_set_stream.argtypes = [_VP, _VP]
+lib.fpm_host_alloc.argtypes = [C.c_size_t, C.POINTER(_VP)]
+lib.fpm_host_free.argtypes = [_VP]
+lib.fpm_ctx_launch_count.restype = C.c_uint64
+lib.fpm_ctx_launch_count.argtypes = [_VP]
+lib.fpm_sketch_batch.argtypes = [_VP, C.POINTER(SketchParams), _VP, C.c_uint64, _VP, C.c_uint32, _VP, _VP, _VP, _VP]
+lib.fpm_sketch_batch_dev.argtypes = [_VP, C.POINTER(SketchParams), _VP, C.c_uint64, _VP, C.c_uint32, _VP, _VP, _VP, _VP]
+lib.fpm_kmer_hashes.argtypes = [_VP, C.POINTER(SketchParams), _VP, C.c_uint64, _VP, u64p]
+lib.fpm_fp_hash_batch.argtypes = [_VP, _VP, _VP, C.c_uint64, C.c_uint32, C.c_int, _VP]
+lib.fpm_dist_tile.argtypes = [_VP, C.POINTER(DistParams), C.POINTER(Panel), C.POINTER(Panel), _VP]
+lib.fpm_dist_tile_dev.argtypes = [_VP, C.POINTER(DistParams), C.POINTER(Panel), C.POINTER(Panel), _VP, _VP]
+lib.fpm_pvalue.restype = C.c_double
+lib.fpm_pvalue.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_double, C.c_uint64]
+lib.fpm_distance.restype = C.c_double
+lib.fpm_distance.argtypes = [C.c_uint64, C.c_uint64, C.c_int]
+lib.fpm_measure_int32_peak.argtypes = [_VP, C.POINTER(C.c_double)]
+
+EXPORTED = ["fpm_abi_version", "fpm_device_count", "fpm_ctx_create", "fpm_ctx_destroy", "fpm_last_error",
+            "fpm_ctx_sync", "fpm_ctx_stream", "fpm_ctx_set_stream", "fpm_host_alloc", "fpm_host_free",
+            "fpm_ctx_launch_count", "fpm_sketch_batch", "fpm_sketch_batch_dev", "fpm_kmer_hashes",
+            "fpm_fp_hash_batch", "fpm_dist_tile", "fpm_dist_tile_dev", "fpm_pvalue", "fpm_distance",
+            "fpm_measure_int32_peak"]
+
+
+def _check(rc):
+    if rc != FPM_OK:
+        raise FpmError(rc, lib.fpm_last_error().decode("utf-8", "replace"))
+
+
+def device_count():
+    return lib.fpm_device_count()
+
+
+def nucleotide_alphabet(chars="ACGT", preserve_case=False):
+    """setAlphabetFromString (Sketch.cpp:1260-1289)."""
+    a = np.zeros(256, dtype=np.uint8)
+    for ch in chars:
+        c = ord(ch)
+        if not preserve_case and 96 < c < 123:
+            c -= 32
+        a[c] = 1
+    return a
+
+
+def make_sketch_params(k=21, s=1000, seed=42, min_cov=1, noncanonical=False, preserve_case=False,
+                       alphabet="ACGT", want_counts=False, use64=None):
+    """Sketch::Parameters as resolved by sketchParameterSetup (sketchParameterSetup.cpp:9-106)."""
+    p = SketchParams()
+    table = nucleotide_alphabet(alphabet, preserve_case)
+    p.kmer_size, p.sketch_size, p.seed, p.min_cov = k, s, seed, min_cov
+    p.noncanonical, p.preserve_case, p.want_counts = int(noncanonical), int(preserve_case), int(want_counts)
+    if use64 is None:
+        use64 = float(int(table.sum())) ** k > 2.0 ** 32   # Sketch.cpp:1288
+    p.use64 = int(use64)
+    C.memmove(p.alphabet, table.ctypes.data, 256)
+    return p
+
+
+def pack_records(groups):
+    """groups: list of sketches, each a list of records (bytes).  Returns (seq u8 array,
+    group_offsets u64 array) in the layout fpm_sketch_batch wants: records back to back,
+    each followed by one 0x00 byte."""
+    total = sum(len(r) + 1 for g in groups for r in g)
+    seq = np.zeros(total, dtype=np.uint8)
+    off = np.zeros(len(groups) + 1, dtype=np.uint64)
+    pos = 0
+    for gi, g in enumerate(groups):
+        for r in g:
+            n = len(r)
+            seq[pos:pos + n] = np.frombuffer(bytes(r), dtype=np.uint8)
+            pos += n + 1
+        off[gi + 1] = pos
+    return seq, off
+
+
+class Context:
+    """One CUDA device + stream (fpm_ctx)."""
+
+    def __init__(self, device=0):
+        self._h = _VP()
+        _check(lib.fpm_ctx_create(device, C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib.fpm_ctx_destroy(self._h)
+            self._h = _VP()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def sync(self):
+        _check(lib.fpm_ctx_sync(self._h))
+
+    def stream(self):
+        return lib.fpm_ctx_stream(self._h)
+
+    def set_stream(self, cuda_stream):
+        _check(lib.fpm_ctx_set_stream(self._h, _VP(cuda_stream)))
+
+    def launch_count(self):
+        return int(lib.fpm_ctx_launch_count(self._h))
+
+    def int32_peak(self):
+        v = C.c_double()
+        _check(lib.fpm_measure_int32_peak(self._h, C.byref(v)))
+        return v.value
+
+    # -- sketch ---------------------------------------------------------------------------
+    def sketch_batch(self, seq, group_offsets, params, want_kmers=False):
+        """Host buffers in, host arrays out (H2D + kernels + D2H)."""
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        off = np.ascontiguousarray(group_offsets, dtype=np.uint64)
+        ng = len(off) - 1
+        s = params.sketch_size
+        hashes = np.zeros((ng, s), dtype=np.uint64)
+        counts = np.zeros((ng, s), dtype=np.uint32) if params.want_counts else None
+        n = np.zeros(ng, dtype=np.uint32)
+        kmers = np.zeros(ng, dtype=np.uint64) if want_kmers else None
+        _check(lib.fpm_sketch_batch(self._h, C.byref(params), seq.ctypes.data, seq.size, off.ctypes.data, ng,
+                                    hashes.ctypes.data, counts.ctypes.data if counts is not None else None,
+                                    n.ctypes.data, kmers.ctypes.data if kmers is not None else None))
+        return dict(hashes=hashes, counts=counts, n=n, kmers=kmers)
+
+    def sketch_batch_dev(self, d_seq_ptr, seq_bytes, group_offsets, params, d_hashes_ptr, d_counts_ptr, d_n_ptr,
+                         d_kmers_ptr=None):
+        """Device pointers (ints) for sequence and outputs; group offsets stay on the host."""
+        off = np.ascontiguousarray(group_offsets, dtype=np.uint64)
+        _check(lib.fpm_sketch_batch_dev(self._h, C.byref(params), _VP(d_seq_ptr), seq_bytes, off.ctypes.data,
+                                        len(off) - 1, _VP(d_hashes_ptr), _VP(d_counts_ptr) if d_counts_ptr else None,
+                                        _VP(d_n_ptr), _VP(d_kmers_ptr) if d_kmers_ptr else None))
+
+    def sketch_records(self, groups, **kw):
+        """Convenience: groups = list of lists of record bytes -> list of dict per sketch."""
+        want_kmers = kw.pop("want_kmers", False)
+        params = make_sketch_params(**kw)
+        seq, off = pack_records(groups)
+        r = self.sketch_batch(seq, off, params, want_kmers=want_kmers)
+        out = []
+        for g in range(len(groups)):
+            n = int(r["n"][g])
+            d = dict(hashes=r["hashes"][g, :n].copy())
+            if r["counts"] is not None:
+                d["counts"] = r["counts"][g, :n].copy()
+            if r["kmers"] is not None:
+                d["kmers"] = int(r["kmers"][g])
+            out.append(d)
+        return out
+
+    def kmer_hashes(self, record: bytes, **kw):
+        """Hash of every valid window of one record, in order (getHash parity)."""
+        params = make_sketch_params(**kw)
+        seq = np.frombuffer(bytes(record) + b"\0", dtype=np.uint8).copy()
+        out = np.zeros(max(seq.size, 1), dtype=np.uint64)
+        cnt = C.c_uint64()
+        _check(lib.fpm_kmer_hashes(self._h, C.byref(params), seq.ctypes.data, seq.size, out.ctypes.data, C.byref(cnt)))
+        return out[:cnt.value].copy()
+
+    # -- fingerprints ---------------------------------------------------------------------
+    def fp_hash_batch(self, lines, seed=42, use64=False):
+        """lines: list of token lists (one fingerprint line each) -> u64 array of hashes."""
+        off = np.zeros(len(lines) + 1, dtype=np.uint64)
+        for i, t in enumerate(lines):
+            off[i + 1] = off[i] + len(t)
+        tok = np.zeros(max(int(off[-1]), 1), dtype=np.uint64)
+        p = 0
+        for t in lines:
+            tok[p:p + len(t)] = np.asarray(t, dtype=np.uint64)
+            p += len(t)
+        out = np.zeros(len(lines), dtype=np.uint64)
+        _check(lib.fpm_fp_hash_batch(self._h, tok.ctypes.data, off.ctypes.data, len(lines), seed, int(use64), out.ctypes.data))
+        return out
+
+    # -- dist -----------------------------------------------------------------------------
+    @staticmethod
+    def _panel(hashes, sizes, lengths):
+        h = np.ascontiguousarray(hashes, dtype=np.uint64)
+        if h.ndim != 2:
+            raise ValueError("panel hashes must be [n][stride]")
+        sz = np.ascontiguousarray(sizes, dtype=np.uint32)
+        ln = np.ascontiguousarray(lengths, dtype=np.uint64)
+        p = Panel(h.ctypes.data, sz.ctypes.data, ln.ctypes.data, h.shape[0], h.shape[1])
+        return p, (h, sz, ln)
+
+    def dist_tile(self, ref, qry, sketch_size, kmer_size, kmer_space, max_distance=1.0, max_pvalue=1.0,
+                  sorted_unique=True):
+        """ref / qry: (hashes [n][stride], sizes [n], lengths [n]).  Returns a structured array
+        [n_qry][n_ref] of (numer, denom, distance, pvalue) plus a bool `pass` matrix."""
+        pr, keep_r = self._panel(*ref)
+        pq, keep_q = self._panel(*qry)
+        dp = DistParams(sketch_size, kmer_size, kmer_space, max_distance, max_pvalue, int(sorted_unique))
+        out = np.zeros((pq.n, pr.n), dtype=PAIR_DTYPE)
+        _check(lib.fpm_dist_tile(self._h, C.byref(dp), C.byref(pr), C.byref(pq), out.ctypes.data))
+        passed = (out["denom"] & FPM_PAIR_PASS) != 0
+        out["denom"] &= 0x7fffffff
+        return out, passed
+
+    def dist_tile_dev(self, ref_ptrs, qry_ptrs, sketch_size, kmer_size, kmer_space, d_out_ptr, d_steps_ptr=None,
+                      max_distance=1.0, max_pvalue=1.0, sorted_unique=True):
+        """ref_ptrs / qry_ptrs: (hashes_ptr, sizes_ptr, lengths_ptr, n, stride) device pointers."""
+        pr = Panel(*ref_ptrs)
+        pq = Panel(*qry_ptrs)
+        dp = DistParams(sketch_size, kmer_size, kmer_space, max_distance, max_pvalue, int(sorted_unique))
+        _check(lib.fpm_dist_tile_dev(self._h, C.byref(dp), C.byref(pr), C.byref(pq), _VP(d_out_ptr),
+                                     _VP(d_steps_ptr) if d_steps_ptr else None))
+
+
+def pvalue(x, len_ref, len_qry, kmer_space, n):
+    return lib.fpm_pvalue(x, len_ref, len_qry, kmer_space, n)
+
+
+def distance(common, denom, kmer_size):
+    return lib.fpm_distance(common, denom, kmer_size)

@@ -1,0 +1,172 @@
+/* fpmash_b200.h -- C ABI of the B200-native fp-mash hot path (mash sketch / mash dist).
+ *
+ * The reference (UmbertoDellaMonica/fp-mash, Mash 2.3 fork) has no FFI layer; the seam this
+ * library sits behind is the worker-function contract of its ThreadPool plus the free
+ * functions of libmash.a.  Each entry point below names the
+ * reference interface it replaces (paths relative to mash/src/mash/).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every function returns FPM_OK (0) or a negative
+ *     fpm_status, and fpm_last_error() gives the message for the calling thread;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails
+ *     with FPM_ERR_NO_DEVICE;
+ *   - "_dev" variants take device pointers (inputs already resident in HBM, outputs left
+ *     in HBM) and are asynchronous on the context's stream; the plain variants take host
+ *     pointers and include the H2D/D2H copies;
+ *   - a context is bound to one device and one stream; use one context per host thread
+ *     (the reference calls its workers from -p pthreads: ThreadPool.hxx:182-230).
+ */
+#ifndef FPMASH_B200_H
+#define FPMASH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FPM_ABI_VERSION 1
+
+typedef enum fpm_status {
+    FPM_OK = 0,
+    FPM_ERR_NO_DEVICE = -1,   /* no CUDA device / driver: the product path refuses to run   */
+    FPM_ERR_CUDA = -2,        /* a CUDA runtime call failed (message has the CUDA error)    */
+    FPM_ERR_ARG = -3,         /* invalid argument                                            */
+    FPM_ERR_UNSUPPORTED = -4, /* valid in the reference but outside the accelerated path     */
+    FPM_ERR_NOMEM = -5
+} fpm_status;
+
+typedef struct fpm_ctx fpm_ctx;
+
+/* ---- context ------------------------------------------------------------------------- */
+
+int fpm_abi_version(void);
+int fpm_device_count(void);                          /* 0 when no usable CUDA device        */
+int fpm_ctx_create(int device, fpm_ctx** out);
+void fpm_ctx_destroy(fpm_ctx* ctx);
+const char* fpm_last_error(void);                    /* thread-local, never NULL            */
+int fpm_ctx_sync(fpm_ctx* ctx);                      /* cudaStreamSynchronize(ctx stream)   */
+void* fpm_ctx_stream(fpm_ctx* ctx);                  /* the cudaStream_t, for event timing  */
+/* Adopt an external stream (e.g. torch's current stream) for all later launches.          */
+int fpm_ctx_set_stream(fpm_ctx* ctx, void* cuda_stream);
+
+/* Pinned host memory for zero-staging H2D/D2H (cudaHostAlloc / cudaFreeHost).             */
+int fpm_host_alloc(size_t bytes, void** out);
+void fpm_host_free(void* p);
+
+/* Kernel launches issued by this context so far (all of them are this library's own).     */
+uint64_t fpm_ctx_launch_count(const fpm_ctx* ctx);
+
+/* ---- sketch: nucleotide k-mers -> bottom-s MinHash sketch ---------------------------- */
+
+/* Mirrors the fields of Sketch::Parameters (Sketch.h:40-113) that reach the hot loop.     */
+typedef struct fpm_sketch_params {
+    int32_t kmer_size;        /* -k, 1..32                                                  */
+    uint32_t sketch_size;     /* -s  (minHashesPerWindow)                                   */
+    uint32_t seed;            /* -S                                                         */
+    uint32_t min_cov;         /* -m  (1 unless read mode; MinHashHeap multiplicityMinimum)  */
+    uint8_t noncanonical;     /* -n                                                         */
+    uint8_t preserve_case;    /* -Z                                                         */
+    uint8_t use64;            /* alphabetSize^k > 2^32 (Sketch.cpp:1288)                    */
+    uint8_t want_counts;      /* fill out_counts (parameters.counts / read mode)            */
+    uint8_t alphabet[256];    /* Sketch::Parameters::alphabet                               */
+} fpm_sketch_params;
+
+/* Replaces sketchFile / sketchSequence -> addMinHashes -> MinHashHeap::tryInsert ->
+ * setMinHashesForReference (Sketch.cpp:1299-1517, 664-735, 1291-1297; MinHashHeap.cpp:68-146)
+ * for a whole batch of sketches ("groups") at once.
+ *
+ * seq          : sequence bytes as kseq delivers them (any case, IUPAC codes allowed).
+ *                Records are laid out back to back, EACH FOLLOWED BY ONE 0x00 BYTE, in the
+ *                order the reference would feed them to addMinHashes; records shorter than k
+ *                may be present (they produce no window, like Sketch.cpp:1374-1378).
+ * group_offsets: n_groups+1 byte offsets into seq; group g = one output sketch = bytes
+ *                [group_offsets[g], group_offsets[g+1]) (a whole number of records).
+ * out_hashes   : [n_groups][sketch_size] ascending hashes (u64; 32-bit hashes zero-extended)
+ * out_counts   : [n_groups][sketch_size] multiplicities, or NULL (HashSet::toHashList counts,
+ *                including the reference's order-dependent count of the largest element)
+ * out_n        : [n_groups] number of hashes in each sketch (<= sketch_size)
+ * out_kmers    : [n_groups] number of valid k-mer windows hashed, or NULL
+ */
+int fpm_sketch_batch(fpm_ctx* ctx, const fpm_sketch_params* p,
+                     const uint8_t* seq, uint64_t seq_bytes,
+                     const uint64_t* group_offsets, uint32_t n_groups,
+                     uint64_t* out_hashes, uint32_t* out_counts, uint32_t* out_n, uint64_t* out_kmers);
+
+/* Same, device pointers.  d_seq must be 16-byte aligned.  Synchronises internally (the
+ * exact bottom-s needs a host decision between passes) but leaves results in HBM.          */
+int fpm_sketch_batch_dev(fpm_ctx* ctx, const fpm_sketch_params* p,
+                         const uint8_t* d_seq, uint64_t seq_bytes,
+                         const uint64_t* h_group_offsets, uint32_t n_groups,
+                         uint64_t* d_out_hashes, uint32_t* d_out_counts, uint32_t* d_out_n, uint64_t* d_out_kmers);
+
+/* Raw hash stream of one record (every valid window in order), for parity tests of the
+ * rolling + MurmurHash3 kernel against getHash (hash.cpp:12-40).  out_hashes needs
+ * seq_bytes entries; *out_count receives the number written.                               */
+int fpm_kmer_hashes(fpm_ctx* ctx, const fpm_sketch_params* p, const uint8_t* seq, uint64_t seq_bytes,
+                    uint64_t* out_hashes, uint64_t* out_count);
+
+/* ---- sketch: -fp fingerprint mode ---------------------------------------------------- */
+
+/* Replaces getHashFingerPrint (hash.cpp:45-73) as called per line by
+ * Sketch::initFromFingerprints (Sketch.cpp:132): MurmurHash3_x64_128 over the raw
+ * little-endian bytes of each line's uint64 tokens.  line_offsets has n_lines+1 entries
+ * (token indices).  out_hashes[i] = (use64 ? h1 : low 32 bits of h1) of line i.            */
+int fpm_fp_hash_batch(fpm_ctx* ctx, const uint64_t* tokens, const uint64_t* line_offsets, uint64_t n_lines,
+                      uint32_t seed, int use64, uint64_t* out_hashes);
+
+/* ---- dist ---------------------------------------------------------------------------- */
+
+/* PairOutput (CommandDistance.h:57-64) as a 24-byte POD.                                   */
+typedef struct fpm_pair {
+    uint32_t numer;           /* shared hashes (common)                                     */
+    uint32_t denom;           /* bits 0..30 union size compared; bit 31 = pass              */
+    double distance;
+    double pvalue;
+} fpm_pair;
+#define FPM_PAIR_PASS 0x80000000u
+#define FPM_PAIR_DENOM(p) ((p).denom & 0x7fffffffu)
+
+typedef struct fpm_dist_params {
+    uint32_t sketch_size;     /* min(ref, query minHashesPerWindow), CommandDistance.cpp:342 */
+    int32_t kmer_size;
+    double kmer_space;        /* alphabetSize^k (Sketch.cpp:661)                             */
+    double max_distance;      /* -d                                                          */
+    double max_pvalue;        /* -v                                                          */
+    uint8_t sorted_unique;    /* 1: lists are ascending and duplicate-free (every nucleotide
+                                 sketch); 0: run the reference loop literally (fp-mode lists
+                                 are unsorted and may repeat)               */
+} fpm_dist_params;
+
+/* A panel is a dense [n][stride] u64 array of hashes plus per-sketch sizes and lengths.   */
+typedef struct fpm_panel {
+    const uint64_t* hashes;   /* [n][stride]                                                */
+    const uint32_t* sizes;    /* [n] hashes used in each row                                */
+    const uint64_t* lengths;  /* [n] Reference::length (for the p-value)                    */
+    uint64_t n;
+    uint64_t stride;
+} fpm_panel;
+
+/* Replaces compare() -> compareSketches() -> pValue() (CommandDistance.cpp:335-450) for the
+ * whole tile query x ref.  out[q * ref.n + r] (query-major, reference-minor: the order of
+ * CommandDistance.cpp:355-359).                                                            */
+int fpm_dist_tile(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* ref, const fpm_panel* qry, fpm_pair* out);
+int fpm_dist_tile_dev(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* d_ref, const fpm_panel* d_qry,
+                      fpm_pair* d_out, uint64_t* d_merge_steps /* nullable: += loop iterations */);
+
+/* Scalar helpers exported for host code and tests (same code the kernels run).             */
+double fpm_pvalue(uint64_t x, uint64_t len_ref, uint64_t len_qry, double kmer_space, uint64_t n);
+double fpm_distance(uint64_t common, uint64_t denom, int kmer_size);
+
+/* ---- measurement helpers ------------------------------------------------------------- */
+
+/* Integer-pipe microbenchmark: sustained 32-bit integer ops/s of this GPU (a dependent
+ * IMAD+LOP3+SHF mix on every SM), the denominator of the sketch kernel's integer roofline
+ * (INT32 peak is not in MEASURED_PEAKS.json and must be measured).           */
+int fpm_measure_int32_peak(fpm_ctx* ctx, double* out_ops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FPMASH_B200_H */

@@ -1,0 +1,97 @@
+"""GPU parity: all-vs-all sketch comparison vs the oracle's literal compareSketches loop.
+Shared-hash counts and denominators bit-exact; distance and p-value within 1e-12 relative."""
+import numpy as np
+import pytest
+
+from util import sorted_sketch_panel
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12
+
+
+def _oracle_matrix(oracle, ref, qry, s, k, kmer_space, max_d=1.0, max_p=1.0):
+    rh, rs, rl = ref
+    qh, qs, ql = qry
+    out = []
+    for q in range(len(qs)):
+        row = []
+        for r in range(len(rs)):
+            row.append(oracle.compare(rh[r, :rs[r]], qh[q, :qs[q]], int(rl[r]), int(ql[q]), s, k, kmer_space, max_d, max_p))
+        out.append(row)
+    return out
+
+
+def _compare(got, passed, want):
+    for q, row in enumerate(want):
+        for r, w in enumerate(row):
+            g = got[q, r]
+            assert bool(passed[q, r]) == w["passed"], (q, r)
+            assert int(g["numer"]) == w["numer"] and int(g["denom"]) == w["denom"], (q, r, g, w)
+            assert g["distance"] == pytest.approx(w["distance"], rel=RTOL, abs=0), (q, r)
+            if w["passed"] or w["pvalue"] != 0:
+                if w["pvalue"] == 0:
+                    assert g["pvalue"] == 0
+                else:
+                    assert g["pvalue"] == pytest.approx(w["pvalue"], rel=RTOL, abs=1e-300), (q, r, g, w)
+
+
+@pytest.mark.parametrize("s,n_ref,n_qry", [(1000, 37, 21), (1000, 64, 16), (100, 33, 50), (2500, 20, 9)])
+def test_dist_sorted_panels(ctx, oracle, s, n_ref, n_qry):
+    rng = np.random.default_rng(s + n_ref)
+    rh, rs = sorted_sketch_panel(rng, n_ref, s)
+    qh, qs = sorted_sketch_panel(rng, n_qry, s)
+    qh[:3] = rh[:3]; qs[:3] = rs[:3]          # identical sketches: distance 0, 1000/1000
+    rl = rng.integers(1000, 6_000_000, size=n_ref).astype(np.uint64)
+    ql = rng.integers(1000, 6_000_000, size=n_qry).astype(np.uint64)
+    got, passed = ctx.dist_tile((rh, rs, rl), (qh, qs, ql), s, 21, 4.0 ** 21)
+    _compare(got, passed, _oracle_matrix(oracle, (rh, rs, rl), (qh, qs, ql), s, 21, 4.0 ** 21))
+
+
+def test_dist_thresholds_and_sketch_size_mismatch(ctx, oracle):
+    rng = np.random.default_rng(77)
+    rh, rs = sorted_sketch_panel(rng, 40, 1000, shared=0.8)
+    qh, qs = sorted_sketch_panel(rng, 24, 1000, shared=0.8)
+    rl = np.full(40, 4_600_000, dtype=np.uint64)
+    ql = np.full(24, 5_100_000, dtype=np.uint64)
+    # compare at s=400 although the lists hold up to 1000 hashes (CommandDistance.cpp:342-344)
+    got, passed = ctx.dist_tile((rh, rs, rl), (qh, qs, ql), 400, 21, 4.0 ** 21, max_distance=0.2, max_pvalue=1e-5)
+    _compare(got, passed, _oracle_matrix(oracle, (rh, rs, rl), (qh, qs, ql), 400, 21, 4.0 ** 21, 0.2, 1e-5))
+
+
+def test_dist_heterogeneous_densities_multi_phase(ctx, oracle):
+    # sketches whose hash densities differ 50x force several value-bounded phases
+    rng = np.random.default_rng(5)
+    s = 1500
+    rows = []
+    for i in range(48):
+        scale = (1 << 60) // (1 + 49 * (i % 3 == 0))
+        rows.append(np.unique(rng.integers(0, scale, size=s, dtype=np.uint64))[:s])
+    h = np.zeros((48, s), dtype=np.uint64); sz = np.zeros(48, dtype=np.uint32)
+    for i, r in enumerate(rows):
+        h[i, :len(r)] = r; sz[i] = len(r)
+    ln = np.full(48, 3_000_000, dtype=np.uint64)
+    got, passed = ctx.dist_tile((h, sz, ln), (h[:20], sz[:20], ln[:20]), s, 21, 4.0 ** 21)
+    _compare(got, passed, _oracle_matrix(oracle, (h, sz, ln), (h[:20], sz[:20], ln[:20]), s, 21, 4.0 ** 21))
+
+
+def test_dist_literal_unsorted_fp_lists(ctx, oracle):
+    # fp mode: unsorted, repeating 32-bit lists, k=1, kmerSpace=10
+    rng = np.random.default_rng(6)
+    n, s = 7, 2000
+    h = rng.integers(0, 3000, size=(n, s)).astype(np.uint64)
+    sz = np.full(n, s, dtype=np.uint32)
+    ln = rng.integers(9000, 11000, size=n).astype(np.uint64)
+    got, passed = ctx.dist_tile((h, sz, ln), (h, sz, ln), 1000, 1, 10.0, sorted_unique=False)
+    _compare(got, passed, _oracle_matrix(oracle, (h, sz, ln), (h, sz, ln), 1000, 1, 10.0))
+    # declared sorted but is not: the library must notice and still return the literal result
+    got2, passed2 = ctx.dist_tile((h, sz, ln), (h, sz, ln), 1000, 1, 10.0, sorted_unique=True)
+    assert np.array_equal(got2, got) and np.array_equal(passed2, passed)
+
+
+def test_dist_empty_sketches(ctx, oracle):
+    h = np.zeros((3, 10), dtype=np.uint64); h[1, :4] = [5, 9, 11, 40]; h[2, :2] = [9, 40]
+    sz = np.array([0, 4, 2], dtype=np.uint32)
+    ln = np.array([100, 200, 300], dtype=np.uint64)
+    got, passed = ctx.dist_tile((h, sz, ln), (h, sz, ln), 10, 21, 4.0 ** 21)
+    _compare(got, passed, _oracle_matrix(oracle, (h, sz, ln), (h, sz, ln), 10, 21, 4.0 ** 21))

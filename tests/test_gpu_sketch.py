@@ -1,0 +1,108 @@
+"""GPU parity: rolling canonical k-mer + MurmurHash3 + bottom-s selection vs the oracle.
+Every call goes through the C ABI (fpmash_b200 ctypes binding).  Bit-exact."""
+import numpy as np
+import pytest
+
+from util import dirty_dna, mutate, random_dna
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 7, 8, 9, 15, 16, 17, 21, 24, 25, 31, 32])
+@pytest.mark.parametrize("noncanonical", [False, True])
+def test_kmer_hash_stream_matches_getHash(ctx, oracle, k, noncanonical):
+    rng = np.random.default_rng(1000 + k)
+    rec = dirty_dna(rng, 20011)
+    want = oracle.sketch([rec], k=k, s=10, noncanonical=noncanonical, trace=True)["trace"]
+    got = ctx.kmer_hashes(rec, k=k, s=10, noncanonical=noncanonical)
+    assert len(got) == len(want)
+    assert np.array_equal(got, want)
+
+
+def test_kmer_hash_preserve_case_and_seed(ctx, oracle):
+    rng = np.random.default_rng(7)
+    rec = dirty_dna(rng, 5000, lower_rate=0.3)
+    for seed in (0, 42, 12345):
+        want = oracle.sketch([rec], k=21, s=10, seed=seed, preserve_case=True, trace=True)["trace"]
+        got = ctx.kmer_hashes(rec, k=21, s=10, seed=seed, preserve_case=True)
+        assert np.array_equal(got, want)
+
+
+def test_pocket_known_answers(ctx):
+    # SURVEY.md Appendix C (computed with the reference's own hash.cpp)
+    kat = {b"ATGCATGCATGCATGCATGCA": 14844149108877162497, b"CATGCATGCATGCATGCATGC": 10703850894209713636,
+           b"GCATGCATGCATGCATGCATG": 17987483124073101136, b"TGCATGCATGCATGCATGCAT": 11471179132836535170}
+    for kmer, h in kat.items():
+        assert int(ctx.kmer_hashes(kmer, k=21, s=1, noncanonical=True)[0]) == h
+    assert int(ctx.kmer_hashes(b"AAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAA", k=32, s=1, noncanonical=True)[0]) == 7775287419336189913
+    assert int(ctx.kmer_hashes(b"ACGTACGTACGTACGT", k=16, s=1, noncanonical=True)[0]) == 2886031495
+    assert int(ctx.kmer_hashes(b"A", k=1, s=1, noncanonical=True)[0]) == 969040168
+
+
+def _check_groups(ctx, oracle, groups, **kw):
+    got = ctx.sketch_records(groups, want_counts=True, want_kmers=True, **kw)
+    okw = {k: v for k, v in kw.items()}
+    for g, recs in enumerate(groups):
+        want = oracle.sketch(recs, trace=True, **okw)
+        assert np.array_equal(got[g]["hashes"], want["hashes"]), "group %d hashes" % g
+        assert np.array_equal(got[g]["counts"], want["counts"]), "group %d counts" % g
+        assert got[g]["kmers"] == len(want["trace"]), "group %d window count" % g
+
+
+@pytest.mark.parametrize("k,s", [(21, 1000), (16, 1000), (32, 10000), (11, 500), (21, 50)])
+def test_sketch_genomes(ctx, oracle, k, s):
+    rng = np.random.default_rng(k * 100 + s)
+    base = random_dna(rng, 300000)
+    groups = [[base], [mutate(rng, base, 0.01)], [dirty_dna(rng, 150000)],
+              [random_dna(rng, 70000), random_dna(rng, 5), random_dna(rng, 90000)]]
+    _check_groups(ctx, oracle, groups, k=k, s=s)
+
+
+def test_sketch_small_and_empty_groups(ctx, oracle):
+    rng = np.random.default_rng(5)
+    groups = [[b"ACGT"], [random_dna(rng, 21)], [random_dna(rng, 20)], [b"N" * 100], [random_dna(rng, 1500)],
+              [b"ACGTACGTACGTACGTACGTACGTACGT" * 50], [b"A" * 3000], [random_dna(rng, 40000)]]
+    _check_groups(ctx, oracle, groups, k=21, s=1000)
+
+
+@pytest.mark.parametrize("min_cov", [1, 2, 3])
+def test_sketch_reads_min_cov_and_counts(ctx, oracle, min_cov):
+    rng = np.random.default_rng(40 + min_cov)
+    genome = random_dna(rng, 20000)
+    reads = []
+    for _ in range(4000):   # ~30x of 150 bp reads with errors, both strands
+        p = int(rng.integers(0, len(genome) - 150))
+        r = mutate(rng, genome[p:p + 150], 0.01)
+        if rng.random() < 0.5:
+            r = r[::-1].translate(bytes.maketrans(b"ACGT", b"TGCA"))
+        if rng.random() < 0.02:
+            r = r[:70] + b"N" + r[71:]
+        reads.append(r)
+    _check_groups(ctx, oracle, [reads], k=21, s=1000, min_cov=min_cov)
+    _check_groups(ctx, oracle, [reads], k=21, s=100, min_cov=min_cov)   # full sketch: top-count rule
+
+
+def test_sketch_repeats_trigger_rerun(ctx, oracle):
+    # few distinct k-mers: the first threshold admits < s distinct hashes, forcing re-runs
+    rng = np.random.default_rng(9)
+    unit = random_dna(rng, 3000)
+    groups = [[unit * 100], [random_dna(rng, 200000)]]
+    _check_groups(ctx, oracle, groups, k=21, s=1000)
+
+
+def test_noncanonical_sketch(ctx, oracle):
+    rng = np.random.default_rng(11)
+    _check_groups(ctx, oracle, [[random_dna(rng, 120000)]], k=21, s=1000, noncanonical=True)
+
+
+def test_fp_hash_batch(ctx, oracle):
+    rng = np.random.default_rng(3)
+    lines = [list(rng.integers(1, 200, size=int(rng.integers(0, 25)))) for _ in range(3000)]
+    lines[0] = [8, 34, 57, 1]
+    lines[1] = [1, 1, 1, 1, 2, 34, 60]
+    got = ctx.fp_hash_batch(lines, seed=42, use64=False)
+    assert int(got[0]) == 819737709 and int(got[1]) == 2641509094   # DNA1-sketch.json
+    for use64 in (False, True):
+        got = ctx.fp_hash_batch(lines, seed=42, use64=use64)
+        want = np.array([oracle.fp_hash(t, 42, use64) for t in lines], dtype=np.uint64)
+        assert np.array_equal(got, want)
