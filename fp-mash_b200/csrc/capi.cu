@@ -78,7 +78,56 @@ int fpm_ctx::ensure_pinned(size_t bytes)
     return FPM_OK;
 }
 
+void fpm_ctx::time_begin(int id)
+{
+    if (!timing) return;
+    Timed t;
+    t.id = id;
+    cudaEventCreate(&t.e0);
+    cudaEventCreate(&t.e1);
+    cudaEventRecord(t.e0, stream);
+    pending.push_back(t);
+}
+
+void fpm_ctx::time_end()
+{
+    if (!timing || pending.empty()) return;
+    cudaEventRecord(pending.back().e1, stream);
+}
+
+void fpm_ctx::time_resolve()
+{
+    for (auto& t : pending) {
+        float ms = 0;
+        if (cudaEventSynchronize(t.e1) == cudaSuccess && cudaEventElapsedTime(&ms, t.e0, t.e1) == cudaSuccess) {
+            kernel_ms[t.id] += ms;
+            kernel_launches[t.id]++;
+        }
+        cudaEventDestroy(t.e0);
+        cudaEventDestroy(t.e1);
+    }
+    pending.clear();
+}
+
 extern "C" {
+
+int fpm_ctx_set_timing(fpm_ctx* c, int enable)
+{
+    if (!c) { set_error("ctx is NULL"); return FPM_ERR_ARG; }
+    c->time_resolve();
+    c->timing = enable != 0;
+    for (int i = 0; i < 8; i++) { c->kernel_ms[i] = 0; c->kernel_launches[i] = 0; }
+    return FPM_OK;
+}
+
+int fpm_ctx_get_timing(fpm_ctx* c, int kernel_id, double* out_ms_total, uint64_t* out_launches)
+{
+    if (!c || kernel_id < 0 || kernel_id >= 8) { set_error("bad argument"); return FPM_ERR_ARG; }
+    c->time_resolve();
+    if (out_ms_total) *out_ms_total = c->kernel_ms[kernel_id];
+    if (out_launches) *out_launches = c->kernel_launches[kernel_id];
+    return FPM_OK;
+}
 
 int fpm_abi_version(void) { return FPM_ABI_VERSION; }
 

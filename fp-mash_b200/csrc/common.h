@@ -40,6 +40,15 @@ struct fpm_ctx {
         stat, tiles, args, outh, outc, outn, outk, firstpos, tr_off, tr_cursor, tr_pos, glist;
     // dist scratch
     fpm::DevBuf d_ref, d_qry, d_rs, d_qs, d_rl, d_ql, d_out, d_misc;
+    // optional per-kernel event timing (bench roofline): pairs of events around each launch
+    bool timing = false;
+    struct Timed { int id; cudaEvent_t e0, e1; };
+    std::vector<Timed> pending;
+    double kernel_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint64_t kernel_launches[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    void time_begin(int id);
+    void time_end();
+    void time_resolve();
     // pinned staging for small host<->device exchanges
     void* h_pinned = nullptr;
     size_t h_pinned_cap = 0;

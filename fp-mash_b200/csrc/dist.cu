@@ -246,8 +246,10 @@ static int run_dist(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* d_r
         if ((rc = ctx->d_misc.ensure(64))) return rc;
         FPM_CUDA(cudaMemsetAsync(ctx->d_misc.p, 0, 64, st));
         uint64_t n1 = nr16 * 16 * rows_r, n2 = nq16 * 16 * rows_q;
+        ctx->time_begin(FPM_KERNEL_DIST_PACK);
         dist_pack_kernel<<<(uint32_t)((n1 + 255) / 256), 256, 0, st>>>(*d_ref, rows_r, ctx->d_ref.as<uint64_t>(), ctx->d_misc.as<uint32_t>());
         dist_pack_kernel<<<(uint32_t)((n2 + 255) / 256), 256, 0, st>>>(*d_qry, rows_q, ctx->d_qry.as<uint64_t>(), ctx->d_misc.as<uint32_t>());
+        ctx->time_end();
         ctx->launches += 2;
         FPM_CUDA(cudaGetLastError());
         uint32_t flag = 0;
@@ -259,8 +261,10 @@ static int run_dist(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* d_r
             FPM_CUDA(cudaFuncSetAttribute(dist_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             dim3 grid((uint32_t)((d_ref->n + 31) / 32), (uint32_t)nq16);
             if (grid.y > 65535) { set_error("query panel too tall for one launch (%llu sketches): split it", (unsigned long long)d_qry->n); return FPM_ERR_ARG; }
+            ctx->time_begin(FPM_KERNEL_DIST_TILE);
             dist_tile_kernel<<<grid, DT_THREADS, smem, st>>>(ctx->d_ref.as<uint64_t>(), ctx->d_qry.as<uint64_t>(), rows_r, rows_q, d_ref->n,
                                                              d_qry->n, d_ref->lengths, d_qry->lengths, a, d_out, (unsigned long long*)d_steps);
+            ctx->time_end();
             ctx->launches++;
             FPM_CUDA(cudaGetLastError());
         }
@@ -268,7 +272,9 @@ static int run_dist(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* d_r
     if (!fast) {
         uint64_t blocks = (total + 255) / 256;
         if (blocks > 0x7fffffffull) { set_error("too many pairs for one launch"); return FPM_ERR_ARG; }
+        ctx->time_begin(FPM_KERNEL_DIST_LITERAL);
         dist_literal_kernel<<<(uint32_t)blocks, 256, 0, st>>>(*d_ref, *d_qry, a, d_out, (unsigned long long*)d_steps);
+        ctx->time_end();
         ctx->launches++;
         FPM_CUDA(cudaGetLastError());
     }

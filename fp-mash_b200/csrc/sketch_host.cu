@@ -194,7 +194,9 @@ int sketch_batch_dev_impl(fpm_ctx* ctx, const fpm_sketch_params* p, const uint8_
         a.sketch_size = s; a.seed = p->seed; a.fold_case = !p->preserve_case; a.hash32 = !p->use64;
         FPM_CUDA(cudaMemcpyAsync(ctx->args.p, &a, sizeof a, cudaMemcpyHostToDevice, st));
         if (grid) {
+            ctx->time_begin(FPM_KERNEL_SKETCH_HASH);
             g_hash_launch[K - 1](canon, grid, st, ctx->args.as<SketchArgs>(), 0);
+            ctx->time_end();
             ctx->launches++;
             FPM_CUDA(cudaGetLastError());
         }
@@ -207,7 +209,9 @@ int sketch_batch_dev_impl(fpm_ctx* ctx, const fpm_sketch_params* p, const uint8_
         sa.out_hashes = d_out_hashes; sa.out_counts = want_counts ? d_out_counts : nullptr;
         sa.out_firstpos = nullptr;
         sa.out_n = d_out_n; sa.stat_nq = d_stat_nq; sa.stat_nd = d_stat_nd; sa.stat_topcnt = d_stat_top;
+        ctx->time_begin(FPM_KERNEL_SKETCH_SELECT);
         launch_sketch_select(n_groups, (size_t)sa.sort_cap * 8, st, sa);
+        ctx->time_end();
         ctx->launches++;
         FPM_CUDA(cudaGetLastError());
 
@@ -288,7 +292,9 @@ int sketch_batch_dev_impl(fpm_ctx* ctx, const fpm_sketch_params* p, const uint8_
             a.tr_cursor = ctx->tr_cursor.as<uint32_t>(); a.tr_pos = ctx->tr_pos.as<uint64_t>();
             a.sketch_size = s; a.seed = p->seed; a.fold_case = !p->preserve_case; a.hash32 = !p->use64;
             FPM_CUDA(cudaMemcpyAsync(ctx->args.p, &a, sizeof a, cudaMemcpyHostToDevice, st));
+            ctx->time_begin(FPM_KERNEL_SKETCH_HASH);
             g_hash_launch[K - 1](canon, (uint32_t)tiles.size(), st, ctx->args.as<SketchArgs>(), 1);
+            ctx->time_end();
             ctx->launches++;
             FPM_CUDA(cudaGetLastError());
             launch_sketch_topcount((uint32_t)tg.size(), st, ctx->glist.as<uint32_t>(), s, p->min_cov, a.tr_off, a.tr_cap, a.tr_pos, d_out_counts);

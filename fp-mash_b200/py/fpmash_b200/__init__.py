@@ -92,12 +92,16 @@ lib.fpm_pvalue.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_double, C.c_u
 lib.fpm_distance.restype = C.c_double
 lib.fpm_distance.argtypes = [C.c_uint64, C.c_uint64, C.c_int]
 lib.fpm_measure_int32_peak.argtypes = [_VP, C.POINTER(C.c_double)]
+lib.fpm_ctx_set_timing.argtypes = [_VP, C.c_int]
+lib.fpm_ctx_get_timing.argtypes = [_VP, C.c_int, C.POINTER(C.c_double), u64p]
+
+KERNEL_SKETCH_HASH, KERNEL_SKETCH_SELECT, KERNEL_DIST_TILE, KERNEL_DIST_LITERAL, KERNEL_DIST_PACK = range(5)
 
 EXPORTED = ["fpm_abi_version", "fpm_device_count", "fpm_ctx_create", "fpm_ctx_destroy", "fpm_last_error",
             "fpm_ctx_sync", "fpm_ctx_stream", "fpm_ctx_set_stream", "fpm_host_alloc", "fpm_host_free",
             "fpm_ctx_launch_count", "fpm_sketch_batch", "fpm_sketch_batch_dev", "fpm_kmer_hashes",
             "fpm_fp_hash_batch", "fpm_dist_tile", "fpm_dist_tile_dev", "fpm_pvalue", "fpm_distance",
-            "fpm_measure_int32_peak"]
+            "fpm_measure_int32_peak", "fpm_ctx_set_timing", "fpm_ctx_get_timing"]
 
 
 def _check(rc):
@@ -184,6 +188,16 @@ class Context:
 
     def launch_count(self):
         return int(lib.fpm_ctx_launch_count(self._h))
+
+    def set_timing(self, enable=True):
+        _check(lib.fpm_ctx_set_timing(self._h, int(enable)))
+
+    def get_timing(self, kernel_id):
+        """(total ms, launches) of one kernel since set_timing(True)."""
+        ms = C.c_double()
+        n = C.c_uint64()
+        _check(lib.fpm_ctx_get_timing(self._h, kernel_id, C.byref(ms), C.byref(n)))
+        return ms.value, int(n.value)
 
     def int32_peak(self):
         v = C.c_double()

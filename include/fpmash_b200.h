@@ -161,6 +161,16 @@ double fpm_distance(uint64_t common, uint64_t denom, int kmer_size);
 
 /* ---- measurement helpers ------------------------------------------------------------- */
 
+/* Per-kernel device timing (CUDA events recorded on the context's stream around each launch of
+ * the named kernel).  Off by default; enabling resets the accumulators.                        */
+#define FPM_KERNEL_SKETCH_HASH 0   /* sketch_hash_kernel (pack + canonical roll + Murmur + filter) */
+#define FPM_KERNEL_SKETCH_SELECT 1 /* sketch_select_kernel                                         */
+#define FPM_KERNEL_DIST_TILE 2     /* dist_tile_kernel                                             */
+#define FPM_KERNEL_DIST_LITERAL 3  /* dist_literal_kernel                                          */
+#define FPM_KERNEL_DIST_PACK 4     /* dist_pack_kernel                                             */
+int fpm_ctx_set_timing(fpm_ctx* ctx, int enable);
+int fpm_ctx_get_timing(fpm_ctx* ctx, int kernel_id, double* out_ms_total, uint64_t* out_launches);
+
 /* Integer-pipe microbenchmark: sustained 32-bit integer ops/s of this GPU (a dependent
  * IMAD+LOP3+SHF mix on every SM), the denominator of the sketch kernel's integer roofline
  * (INT32 peak is not in MEASURED_PEAKS.json and must be measured).           */
