@@ -1,0 +1,545 @@
+// Sketch.cpp -- host mirror of mash/src/mash/Sketch.cpp for the sketch/dist hot path.
+// File parsing, naming rules and the .msh container live here; every hash, every bottom-s
+// selection and every comparison is done by the CUDA library behind include/fpmash_b200.h.
+#include "Sketch.h"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <unistd.h>
+#include <zlib.h>
+#include <fstream>
+#include <iostream>
+#include <memory>
+#include <sstream>
+
+#include "fastx.h"
+#include "fpmash_b200.h"
+#include "msh.h"
+
+using namespace std;
+
+static const uint64_t kLimitReadFingerprint = 1000000;   // LIMIT_READ_FINGERPRINT, Sketch.cpp:37
+static const uint64_t kFlushBytes = 1ull << 30;          // sequence bytes per GPU batch
+
+fpm_ctx* gpuContext()
+{
+    static fpm_ctx* ctx = nullptr;
+    if (!ctx) {
+        const char* dev = getenv("FPMASH_DEVICE");
+        int rc = fpm_ctx_create(dev ? atoi(dev) : 0, &ctx);
+        if (rc != FPM_OK) {
+            cerr << "ERROR: " << fpm_last_error() << endl;
+            exit(1);
+        }
+    }
+    return ctx;
+}
+
+static void gpuCheck(int rc)
+{
+    if (rc != FPM_OK) {
+        cerr << "ERROR: " << fpm_last_error() << endl;
+        exit(1);
+    }
+}
+
+bool hasSuffix(string const& whole, string const& suffix)
+{
+    return whole.length() >= suffix.length() && 0 == whole.compare(whole.length() - suffix.length(), suffix.length(), suffix);
+}
+
+// Sketch.cpp:1260-1289
+void setAlphabetFromString(Sketch::Parameters& parameters, const char* characters)
+{
+    parameters.alphabetSize = 0;
+    memset(parameters.alphabet, 0, 256);
+    for (const char* c = characters; *c != 0; c++) {
+        char upper = *c;
+        if (!parameters.preserveCase && upper > 96 && upper < 123) upper -= 32;
+        parameters.alphabet[(unsigned char)upper] = true;
+    }
+    for (int i = 0; i < 256; i++)
+        if (parameters.alphabet[i]) parameters.alphabetSize++;
+    parameters.use64 = pow(parameters.alphabetSize, parameters.kmerSize) > pow(2, 32);
+}
+
+// ------------------------------------------------------------------------------------------
+// a batch of sketches on its way to the GPU: sequence bytes (records each followed by 0x00,
+// the layout fpm_sketch_batch defines) + per-sketch metadata
+// ------------------------------------------------------------------------------------------
+struct Sketch::Batch {
+    uint8_t* seq = nullptr;      // pinned
+    uint64_t used = 0, cap = 0;
+    vector<uint64_t> goff{0};
+    vector<Reference> metas;
+
+    ~Batch() { if (seq) fpm_host_free(seq); }
+
+    void reserve(uint64_t extra)
+    {
+        if (used + extra <= cap) return;
+        uint64_t ncap = max<uint64_t>(cap ? cap * 2 : (64ull << 20), used + extra);
+        void* p = nullptr;
+        gpuCheck(fpm_host_alloc(ncap, &p));
+        if (used) memcpy(p, seq, used);
+        if (seq) fpm_host_free(seq);
+        seq = (uint8_t*)p;
+        cap = ncap;
+    }
+    void addRecord(const char* s, uint64_t l)
+    {
+        reserve(l + 1);
+        memcpy(seq + used, s, l);
+        seq[used + l] = 0;
+        used += l + 1;
+    }
+    void closeGroup(const Reference& meta)
+    {
+        goff.push_back(used);
+        metas.push_back(meta);
+    }
+    void clear()
+    {
+        used = 0;
+        goff.assign(1, 0);
+        metas.clear();
+    }
+};
+
+static void fillSketchParams(const Sketch::Parameters& p, fpm_sketch_params& sp, bool readsGroup)
+{
+    memset(&sp, 0, sizeof sp);
+    sp.kmer_size = p.kmerSize;
+    sp.sketch_size = (uint32_t)p.minHashesPerWindow;
+    sp.seed = p.seed;
+    sp.min_cov = readsGroup ? p.minCov : 1;                    // Sketch.cpp:1308, 1513
+    sp.noncanonical = p.noncanonical;
+    sp.preserve_case = p.preserveCase;
+    sp.use64 = p.use64;
+    sp.want_counts = p.counts;
+    for (int i = 0; i < 256; i++) sp.alphabet[i] = p.alphabet[i];
+}
+
+void Sketch::flushBatch(Batch& b)
+{
+    if (b.metas.empty()) return;
+    const uint32_t n = (uint32_t)b.metas.size();
+    const uint64_t s = parameters.minHashesPerWindow;
+    fpm_sketch_params sp;
+    fillSketchParams(parameters, sp, parameters.reads);
+    vector<uint64_t> hashes((size_t)n * s);
+    vector<uint32_t> counts(parameters.counts ? (size_t)n * s : 0);
+    vector<uint32_t> outn(n);
+    gpuCheck(fpm_sketch_batch(gpuContext(), &sp, b.seq, b.used, b.goff.data(), n, hashes.data(),
+                              parameters.counts ? counts.data() : nullptr, outn.data(), nullptr));
+    for (uint32_t g = 0; g < n; g++) {
+        Reference& r = b.metas[g];
+        r.hashesSorted.setUse64(parameters.use64);
+        r.hashesSorted.values.assign(hashes.begin() + (size_t)g * s, hashes.begin() + (size_t)g * s + outn[g]);
+        if (parameters.counts) r.counts.assign(counts.begin() + (size_t)g * s, counts.begin() + (size_t)g * s + outn[g]);
+        r.countsSorted = true;                                  // setMinHashesForReference, Sketch.cpp:1296
+        references.push_back(r);
+    }
+    b.clear();
+}
+
+// sketchFile's reading loop (Sketch.cpp:1318-1422) for one sketch made of one or more files:
+// records are taken one per file in rotation, a record shorter than k is skipped WITHOUT
+// advancing the rotation, name/comment come from the first valid record.
+static void readGroup(const vector<string>& fileNames, const Sketch::Parameters& parameters, Sketch::Reference& reference,
+                      uint64_t& count, bool& skipped, Sketch::Batch* batchPtr,
+                      void (*addRecord)(Sketch::Batch*, const char*, uint64_t))
+{
+    int fileCount = (int)fileNames.size();
+    vector<gzFile> fps(fileCount);
+    vector<unique_ptr<FastxReader>> readers;
+    reference.length = 0;
+    for (int f = 0; f < fileCount; f++) {
+        if (fileNames[f] == "-") {
+            if (f > 1) {
+                cerr << "ERROR: '-' for stdin must be first input" << endl;
+                exit(1);
+            }
+            fps[f] = gzdopen(fileno(stdin), "r");
+        } else {
+            if (reference.name == "" && fileNames[f] != "-") reference.name = fileNames[f];
+            fps[f] = gzopen(fileNames[f].c_str(), "r");
+            if (fps[f] == 0) {
+                cerr << "ERROR: could not open " << fileNames[f] << endl;
+                exit(1);
+            }
+        }
+        gzbuffer(fps[f], 1 << 20);
+        readers.emplace_back(new FastxReader(fps[f]));
+    }
+    int64_t l = -1;
+    size_t it = 0;
+    count = 0;
+    skipped = false;
+    while (!readers.empty()) {
+        FastxReader& rd = *readers[it];
+        l = rd.next();
+        if (l < -1) break;                                       // error
+        if (l == -1) {                                           // eof
+            readers.erase(readers.begin() + it);
+            if (it == readers.size()) it = 0;
+            continue;
+        }
+        if (l < parameters.kmerSize) {
+            skipped = true;
+            continue;
+        }
+        if (count == 0) {
+            if (fileNames[0] == "-") {
+                reference.name = rd.name;
+                reference.comment = rd.comment_cstr;
+            } else {
+                reference.comment = rd.name;
+                reference.comment.append(" ");
+                reference.comment.append(rd.comment_cstr);
+            }
+        }
+        count++;
+        if (!parameters.reads) reference.length += l;
+        addRecord(batchPtr, rd.seq.data(), (uint64_t)l);
+        it++;
+        if (it == readers.size()) it = 0;
+    }
+    for (int i = 0; i < fileCount; i++) gzclose(fps[i]);
+    if (count > 1) {                                             // Sketch.cpp:1436-1444
+        reference.comment.insert(0, " seqs] ");
+        reference.comment.insert(0, to_string(count));
+        reference.comment.insert(0, "[");
+        reference.comment.append(" [...]");
+    }
+    if (l != -1) {
+        cerr << "\nERROR: reading input files." << endl;
+        exit(1);
+    }
+}
+
+static void batchAdd(Sketch::Batch* b, const char* s, uint64_t l);
+
+static void checkUnsupported(const Sketch::Parameters& p)
+{
+    if (p.windowed) { cerr << "ERROR: windowed sketching is not part of the accelerated path." << endl; exit(1); }
+    if (p.memoryBound > 0) { cerr << "ERROR: the Bloom-filter option (-b) is not part of the accelerated path; use -m for exact filtering." << endl; exit(1); }
+    if (p.targetCov > 0) { cerr << "ERROR: target coverage (-c) is inherently sequential and not part of the accelerated path." << endl; exit(1); }
+}
+
+// ------------------------------------------------------------------------------------------
+
+void Sketch::getAlphabetAsString(string& alphabet) const
+{
+    for (int i = 0; i < 256; i++)
+        if (parameters.alphabet[i]) alphabet.append(1, (char)i);
+}
+
+int Sketch::getMinKmerSize(uint64_t reference) const
+{
+    return ceil(log(references[reference].length * (1 - parameters.warning) / parameters.warning) / log(parameters.alphabetSize));
+}
+
+double Sketch::getRandomKmerChance(uint64_t reference) const
+{
+    return 1. / (kmerSpace / references[reference].length + 1.);
+}
+
+void Sketch::getReferenceHistogram(uint64_t index, map<uint32_t, uint64_t>& histogram) const
+{
+    const Reference& reference = references.at(index);
+    histogram.clear();
+    for (uint64_t i = 0; i < reference.counts.size(); i++) histogram[reference.counts.at(i)]++;
+}
+
+uint64_t Sketch::getReferenceIndex(string id) const
+{
+    auto it = referenceIndecesById.find(id);
+    return it == referenceIndecesById.end() ? (uint64_t)-1 : (uint64_t)it->second;
+}
+
+void Sketch::createIndex()   // Sketch.cpp:644-662
+{
+    for (size_t i = 0; i < references.size(); i++) referenceIndecesById[references[i].id] = (int)i;
+    kmerSpace = pow(parameters.alphabetSize, parameters.kmerSize);
+}
+
+// Sketch::initFromFingerprints (Sketch.cpp:56-151): one hash per line, appended in line order
+// (never sorted, truncated or deduplicated); consecutive equal ids form one Reference.
+void Sketch::initFromFingerprints(const vector<string>& files, const Parameters& parametersNew)
+{
+    parameters = parametersNew;
+    uint64_t counterLine = 0;
+    string lastID = "";
+    vector<uint64_t> tokens, lineOff{0};
+    vector<size_t> lineRef;                 // reference index of every hashed line
+
+    cout << "Initializing from fingerprints..." << endl;
+    for (const string& file : files) {
+        cout << "Processing file: " << file << endl;
+        ifstream inputFile(file);
+        if (!inputFile) {
+            cerr << "ERROR: Could not open fingerprint file " << file << " for reading." << endl;
+            exit(1);
+        }
+        string line;
+        bool haveCurrent = false;           // the reference code keeps a per-file current pointer
+        while (getline(inputFile, line) && counterLine < kLimitReadFingerprint) {
+            counterLine++;
+            istringstream ss(line);
+            uint64_t number;
+            string id;
+            ss >> id;
+            size_t first = tokens.size();
+            while (ss >> number) {
+                tokens.push_back(number);
+                if (ss.peek() == ' ') ss.ignore();
+            }
+            size_t n = tokens.size() - first;
+            if (id != lastID) {
+                Reference r;
+                r.id = id;
+                r.length = n;
+                r.name = "" + id;
+                r.comment = "FingerPrint : " + r.id;
+                r.hashesSorted.setUse64(parameters.use64);
+                references.push_back(r);
+                lastID = id;
+                haveCurrent = true;
+            } else if (!haveCurrent) {
+                // The reference dereferences a null pointer here (a file that starts with an empty
+                // line or with the id the previous file ended on).
+                cerr << "ERROR: fingerprint file " << file << " starts with an empty id or with the id that ended the previous file." << endl;
+                exit(1);
+            }
+            references.back().length += n;
+            lineOff.push_back(tokens.size());
+            lineRef.push_back(references.size() - 1);
+        }
+    }
+    const uint64_t nLines = lineRef.size();
+    if (nLines) {
+        vector<uint64_t> hashes(nLines);
+        gpuCheck(fpm_fp_hash_batch(gpuContext(), tokens.data(), lineOff.data(), nLines, parameters.seed, parameters.use64, hashes.data()));
+        for (uint64_t i = 0; i < nLines; i++) references[lineRef[i]].hashesSorted.add(hashes[i]);
+    }
+    createIndex();
+    cout << "Initialization complete." << endl;
+}
+
+void Sketch::initFromReads(const vector<string>& files, const Parameters& parametersNew)   // Sketch.cpp:203-210
+{
+    parameters = parametersNew;
+    checkUnsupported(parameters);
+    Batch batch;
+    Reference reference;
+    uint64_t count;
+    bool skipped;
+    readGroup(files, parameters, reference, count, skipped, &batch, batchAdd);
+    batch.closeGroup(reference);
+    size_t at = references.size();
+    flushBatch(batch);
+    Reference& ref = references[at];
+    // estimateSetSize / estimateMultiplicity (MinHashHeap.h:44-45)
+    double setSize = 0, multiplicity = 0;
+    size_t n = ref.hashesSorted.size();
+    if (n) {
+        setSize = pow(2.0, parameters.use64 ? 64.0 : 32.0) * (double)n / (double)ref.hashesSorted.at(n - 1);
+        uint64_t sum = 0;
+        for (uint32_t c : ref.counts) sum += c;
+        multiplicity = (double)sum / n;
+    }
+    if (parameters.reads) ref.length = parameters.genomeSize != 0 ? parameters.genomeSize : (uint64_t)setSize;   // Sketch.cpp:1424-1434
+    if (ref.length == 0) {
+        if (skipped) cerr << "\nWARNING: All fasta records in input files were shorter than the k-mer size (" << parameters.kmerSize << ")." << endl;
+        else cerr << "\nERROR: Did not find fasta records in \"input files\"." << endl;
+        exit(1);
+    }
+    if (parameters.reads) {
+        cerr << "Estimated genome size: " << setSize << endl;
+        cerr << "Estimated coverage:    " << multiplicity << endl;
+    }
+    createIndex();
+}
+
+void Sketch::loadSketchFile(const string& file)   // loadCapnp, Sketch.cpp:1059-1219
+{
+    vector<uint8_t> bytes;
+    if (!msh::read_file(file, bytes)) return;
+    msh::File mf;
+    string err;
+    if (!msh::decode(bytes.data(), bytes.size(), parameters.use64, parameters.minHashesPerWindow, mf, err)) {
+        cerr << "ERROR: " << file << " is not a valid sketch file (" << err << ")." << endl;
+        exit(1);
+    }
+    for (msh::RefRecord& r : mf.refs) {
+        Reference ref;
+        ref.name = r.name;
+        ref.comment = r.comment;
+        ref.length = r.length;
+        ref.hashesSorted.setUse64(parameters.use64);
+        ref.hashesSorted.values.swap(r.hashes);
+        if (r.has_counts) ref.counts.swap(r.counts);
+        ref.countsSorted = r.counts_sorted;
+        references.push_back(ref);
+    }
+}
+
+uint64_t Sketch::initParametersFromCapnp(const char* file)   // Sketch.cpp:401-470
+{
+    vector<uint8_t> bytes;
+    if (!msh::read_file(file, bytes)) {
+        cerr << "ERROR: could not open \"" << file << "\" for reading." << endl;
+        exit(1);
+    }
+    msh::Header h;
+    uint64_t referenceCount = 0;
+    bool firstHasCounts = false;
+    string err;
+    if (!msh::decode_header(bytes.data(), bytes.size(), h, referenceCount, firstHasCounts, err)) {
+        cerr << "ERROR: \"" << file << "\" is not a valid sketch file (" << err << ")." << endl;
+        exit(1);
+    }
+    parameters.kmerSize = h.kmer_size;
+    parameters.error = h.error;
+    parameters.minHashesPerWindow = h.min_hashes_per_window;
+    parameters.windowSize = h.window_size;
+    parameters.concatenated = h.concatenated;
+    parameters.noncanonical = h.noncanonical;
+    parameters.preserveCase = h.preserve_case;
+    parameters.counts = firstHasCounts;
+    parameters.seed = h.hash_seed;
+    setAlphabetFromString(parameters, h.has_alphabet ? h.alphabet.c_str() : alphabetNucleotide);
+    return referenceCount;
+}
+
+static void batchAdd(Sketch::Batch* b, const char* s, uint64_t l) { b->addRecord(s, l); }
+
+int Sketch::initFromFiles(const vector<string>& files, const Parameters& parametersNew, int verbosity, bool enforceParameters, bool contain)
+{
+    parameters = parametersNew;
+    Batch batch;
+
+    for (size_t i = 0; i < files.size(); i++) {
+        bool isSketch = hasSuffix(files[i], suffixSketch);
+        if (isSketch) {
+            flushBatch(batch);                                   // keep submission order (ThreadPool output queue)
+            Sketch sketchTest;
+            sketchTest.initParametersFromCapnp(files[i].c_str());
+            if (i == 0 && !enforceParameters) initParametersFromCapnp(files[i].c_str());
+            string alphabet, alphabetTest;
+            getAlphabetAsString(alphabet);
+            sketchTest.getAlphabetAsString(alphabetTest);
+            if (alphabet != alphabetTest) {
+                cerr << "\nWARNING: The sketch file " << files[i] << " has different alphabet (" << alphabetTest << ") than the current alphabet (" << alphabet << "). This file will be skipped." << endl << endl;
+                continue;
+            }
+            if (sketchTest.getHashSeed() != parameters.seed) {
+                cerr << "\nWARNING: The sketch " << files[i] << " has a seed size (" << sketchTest.getHashSeed() << ") that does not match the current seed (" << parameters.seed << "). This file will be skipped." << endl << endl;
+                continue;
+            }
+            if (sketchTest.getKmerSize() != parameters.kmerSize) {
+                cerr << "\nWARNING: The sketch " << files[i] << " has a kmer size (" << sketchTest.getKmerSize() << ") that does not match the current kmer size (" << parameters.kmerSize << "). This file will be skipped." << endl << endl;
+                continue;
+            }
+            if (!contain && sketchTest.getMinHashesPerWindow() < parameters.minHashesPerWindow) {
+                cerr << "\nWARNING: The sketch file " << files[i] << " has a target sketch size (" << sketchTest.getMinHashesPerWindow() << ") that is smaller than the current sketch size (" << parameters.minHashesPerWindow << "). This file will be skipped." << endl << endl;
+                continue;
+            }
+            if (sketchTest.getNoncanonical() != parameters.noncanonical) {
+                cerr << "\nWARNING: The sketch file " << files[i] << " is " << (sketchTest.getNoncanonical() ? "noncanonical" : "canonical") << ", which is incompatible with the current setting. This file will be skipped." << endl << endl;
+                continue;
+            }
+            if (sketchTest.getMinHashesPerWindow() > parameters.minHashesPerWindow) {
+                cerr << "\nWARNING: The sketch file " << files[i] << " has a target sketch size (" << sketchTest.getMinHashesPerWindow() << ") that is larger than the current sketch size (" << parameters.minHashesPerWindow << "). Its sketches will be reduced." << endl << endl;
+            }
+            loadSketchFile(files[i]);
+            continue;
+        }
+
+        checkUnsupported(parameters);
+        if (files[i] == "-") {
+            if (verbosity > 0) cerr << "Sketching from stdin..." << endl;
+        } else {
+            if (verbosity > 0) cerr << "Sketching " << files[i] << "..." << endl;
+            FILE* probe = fopen(files[i].c_str(), "r");
+            if (probe == NULL) {
+                cerr << "ERROR: could not open " << files[i] << " for reading." << endl;
+                exit(1);
+            }
+            fclose(probe);
+        }
+        if (parameters.concatenated) {
+            // one sketch per file: sketchFile (Sketch.cpp:1299-1488)
+            Reference reference;
+            uint64_t count;
+            bool skipped;
+            readGroup(vector<string>(1, files[i]), parameters, reference, count, skipped, &batch, batchAdd);
+            if (reference.length == 0) {
+                if (skipped) cerr << "\nWARNING: All fasta records in input files were shorter than the k-mer size (" << parameters.kmerSize << ")." << endl;
+                else cerr << "\nERROR: Did not find fasta records in \"input files\"." << endl;
+                exit(1);
+            }
+            batch.closeGroup(reference);
+        } else {
+            // one sketch per record: sketchFileBySequence + sketchSequence (Sketch.cpp:478-522, 1490-1517)
+            gzFile fp = files[i] == "-" ? gzdopen(fileno(stdin), "r") : gzopen(files[i].c_str(), "r");
+            if (!fp) {
+                cerr << "ERROR: could not open " << files[i] << " for reading." << endl;
+                exit(1);
+            }
+            gzbuffer(fp, 1 << 20);
+            FastxReader rd(fp);
+            int64_t l;
+            while ((l = rd.next()) >= 0) {
+                if (l < parameters.kmerSize) continue;
+                Reference reference;
+                reference.length = l;
+                reference.name = rd.name;
+                reference.comment = rd.comment;
+                batch.addRecord(rd.seq.data(), (uint64_t)l);
+                batch.closeGroup(reference);
+                if (batch.used >= kFlushBytes) flushBatch(batch);
+            }
+            gzclose(fp);
+            if (l != -1) {
+                cerr << "\nERROR: reading " << files[i] << "." << endl;
+                exit(1);
+            }
+        }
+        if (batch.used >= kFlushBytes) flushBatch(batch);
+    }
+    flushBatch(batch);
+    createIndex();
+    return 0;
+}
+
+int Sketch::writeToCapnp(const char* file) const   // Sketch.cpp:536-642
+{
+    msh::File mf;
+    mf.use64 = parameters.use64;
+    mf.header.kmer_size = parameters.kmerSize;
+    mf.header.hash_seed = parameters.seed;
+    mf.header.error = (float)parameters.error;
+    mf.header.min_hashes_per_window = (uint32_t)parameters.minHashesPerWindow;
+    mf.header.window_size = (uint32_t)parameters.windowSize;
+    mf.header.concatenated = parameters.concatenated;
+    mf.header.noncanonical = parameters.noncanonical;
+    mf.header.preserve_case = parameters.preserveCase;
+    getAlphabetAsString(mf.header.alphabet);
+    mf.refs.resize(references.size());
+    for (size_t i = 0; i < references.size(); i++) {
+        msh::RefRecord& r = mf.refs[i];
+        r.name = references[i].name;
+        r.comment = references[i].comment;
+        r.length = references[i].length;
+        r.hashes = references[i].hashesSorted.values;
+        r.counts = references[i].counts;
+    }
+    vector<uint8_t> bytes = msh::encode(mf, parameters.counts);
+    if (!msh::write_file(file, bytes)) {
+        cerr << "ERROR: could not open " << file << " for writing.\n";
+        exit(1);
+    }
+    return 0;
+}

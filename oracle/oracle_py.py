@@ -252,8 +252,9 @@ class RefLib:
         recs = []
 
         def cb(_u, name, comment, clen, seq, l):
+            # (name, comment by length, sequence, comment as the C string kseq exposes -- stale when absent)
             recs.append((name.decode("latin1"), C.string_at(comment, clen).decode("latin1"),
-                         C.string_at(seq, l)))
+                         C.string_at(seq, l), C.string_at(comment).decode("latin1")))
         code = self.L.ref_parse_file(path.encode(), REF_CB(cb), None)
         return recs, code
 

@@ -1,0 +1,153 @@
+"""GPU, end to end through the C++ host binary (`mash sketch`, `mash dist`): the reference's own
+recipes (Makefile.in:95-115, README.md:34-98) reproduce its fixtures -- .msh files byte for
+byte, dist rows character for character."""
+import gzip
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+import mshpy
+from conftest import GOLDEN, ROOT
+
+pytestmark = pytest.mark.gpu
+MASH = os.path.join(ROOT, "fp-mash_b200", "bin", "mash")
+
+
+def run(args, cwd=None):
+    r = subprocess.run([MASH] + args, capture_output=True, text=True, cwd=cwd)
+    assert r.returncode == 0, r.stderr
+    return r
+
+
+def gunzip_to(name, dst, crlf=False):
+    data = gzip.open(os.path.join(GOLDEN, name), "rb").read()
+    if crlf:
+        data = data.replace(b"\n", b"\r\n")
+    with open(dst, "wb") as f:
+        f.write(data)
+
+
+def same_bytes(a, b):
+    return open(a, "rb").read() == open(b, "rb").read()
+
+
+def test_sketch_test_sequence_byte_identical(tmp_path):
+    os.makedirs(tmp_path / "new_data")
+    shutil.copy(os.path.join(GOLDEN, "test_sequence.fasta"), tmp_path / "new_data" / "test_sequence.fasta")
+    r = run(["sketch", "new_data/test_sequence.fasta"], cwd=tmp_path)
+    assert "Sketching new_data/test_sequence.fasta..." in r.stderr and "Writing to new_data/test_sequence.fasta.msh..." in r.stderr
+    assert same_bytes(tmp_path / "new_data" / "test_sequence.fasta.msh", os.path.join(GOLDEN, "test_sequence.msh"))
+
+
+@pytest.mark.parametrize("n", [1, 2, 3])
+def test_sketch_fingerprints_byte_identical(tmp_path, n):
+    """README recipe: mash sketch -fp DNAn-CFL.txt -o DNAn-sketch.msh (4 capnp segments, 5 far pointers)."""
+    gunzip_to("DNA%d-CFL.txt.gz" % n, tmp_path / ("DNA%d-CFL.txt" % n))
+    r = run(["sketch", "-fp", "DNA%d-CFL.txt" % n, "-o", "DNA%d-sketch.msh" % n], cwd=tmp_path)
+    assert "Initializing from fingerprints..." in r.stdout and "Initialization complete." in r.stdout
+    assert same_bytes(tmp_path / ("DNA%d-sketch.msh" % n), os.path.join(GOLDEN, "DNA%d-sketch.msh" % n))
+
+
+def test_sketch_reads_byte_identical(tmp_path):
+    """Makefile.in:106-107: mash sketch -r -I reads reads1.fastq reads2.fastq -o reads.msh.  The
+    fixture was made from CRLF files (its comment holds a '\\r'), so the inputs are converted."""
+    gunzip_to("reads1.fastq.gz", tmp_path / "reads1.fastq", crlf=True)
+    gunzip_to("reads2.fastq.gz", tmp_path / "reads2.fastq", crlf=True)
+    r = run(["sketch", "-r", "-I", "reads", "reads1.fastq", "reads2.fastq", "-o", "reads.msh"], cwd=tmp_path)
+    assert "Estimated genome size: 502359" in r.stderr and "Estimated coverage:    1.115" in r.stderr
+    assert same_bytes(tmp_path / "reads.msh", os.path.join(GOLDEN, "reads.msh"))
+
+
+def test_sketch_then_paste_byte_identical(tmp_path):
+    """paste_example/read1_2.msh = the two read files sketched as genomes, then pasted."""
+    os.makedirs(tmp_path / "test")
+    gunzip_to("reads1.fastq.gz", tmp_path / "test" / "reads1.fastq", crlf=True)
+    gunzip_to("reads2.fastq.gz", tmp_path / "test" / "reads2.fastq", crlf=True)
+    run(["sketch", "./test/reads1.fastq"], cwd=tmp_path)
+    run(["sketch", "./test/reads2.fastq"], cwd=tmp_path)
+    run(["paste", "read1_2", "./test/reads1.fastq.msh", "./test/reads2.fastq.msh"], cwd=tmp_path)
+    assert same_bytes(tmp_path / "read1_2.msh", os.path.join(GOLDEN, "read1_2.msh"))
+    # one invocation over both files gives the same two sketches
+    run(["sketch", "-o", "both", "./test/reads1.fastq", "./test/reads2.fastq"], cwd=tmp_path)
+    assert same_bytes(tmp_path / "both.msh", os.path.join(GOLDEN, "read1_2.msh"))
+
+
+def test_dist_reproduces_genomes_dist(tmp_path):
+    """Makefile.in:109-111: mash dist genomes.msh reads.msh == test/ref/genomes.dist."""
+    files = [os.path.join(GOLDEN, "genome%d.fna.msh" % i) for i in (1, 2, 3)]
+    run(["paste", "genomes"] + files, cwd=tmp_path)
+    r = run(["dist", "genomes.msh", os.path.join(GOLDEN, "reads.msh")], cwd=tmp_path)
+    want = [l.split("\t") for l in open(os.path.join(GOLDEN, "genomes.dist")).read().splitlines()]
+    got = [l.split("\t") for l in r.stdout.splitlines()]
+    assert len(got) == 3
+    for g, w in zip(got, want):
+        assert g[0] == "data/" + w[0] and g[1:] == w[1:]
+    # tutorials.rst:24,56-57
+    r = run(["dist", files[0], files[1], files[2]], cwd=tmp_path)
+    rows = [l.split("\t") for l in r.stdout.splitlines()]
+    assert rows[0][2:] == ["0.0222766", "0", "456/1000"] and rows[1][2:] == ["0", "0", "1000/1000"]
+    # table output and thresholds
+    t = run(["dist", "-t", "genomes.msh", files[0]], cwd=tmp_path).stdout.splitlines()
+    assert t[0].split("\t") == ["#query", "data/genome1.fna", "data/genome2.fna", "data/genome3.fna"]
+    assert t[1].split("\t") == ["data/genome1.fna", "0", "0.0222766", "0"]
+    d = run(["dist", "-d", "0.01", "genomes.msh", files[0]], cwd=tmp_path).stdout.splitlines()
+    assert [l.split("\t")[0] for l in d] == ["data/genome1.fna", "data/genome3.fna"]
+
+
+def test_dist_fingerprint_mode_matches_oracle(tmp_path, oracle):
+    """mash dist -fp a.txt b.txt: unsorted untruncated 32-bit lists, k=1, kmerSpace=10 -- the literal
+    loop defines the result (no golden output exists in the reference: SURVEY.md Appendix A.18)."""
+    for n in (1, 2):
+        gunzip_to("DNA%d-CFL.txt.gz" % n, tmp_path / ("DNA%d-CFL.txt" % n))
+    r = run(["dist", "-fp", "DNA1-CFL.txt", "DNA2-CFL.txt"], cwd=tmp_path)
+    rows = [l.split("\t") for l in r.stdout.splitlines() if "\t" in l]
+    assert len(rows) == 25
+    a = mshpy.load(os.path.join(GOLDEN, "DNA1-sketch.msh")).refs
+    b = mshpy.load(os.path.join(GOLDEN, "DNA2-sketch.msh")).refs
+    k = 0
+    for q in b:
+        for ref in a:
+            w = oracle.compare(ref["hashes32"], q["hashes32"], ref["length"], q["length"], 1000, 1, 10.0)
+            g = rows[k]
+            k += 1
+            assert g[0] == ref["name"] and g[1] == q["name"]
+            assert g[2] == "%g" % w["distance"] and g[3] == "%g" % w["pvalue"] and g[4] == "%d/%d" % (w["numer"], w["denom"])
+    # the same comparison from the .msh files truncates each list to its first 1000 hashes (Appendix A.9)
+    run(["sketch", "-fp", "DNA1-CFL.txt", "-o", "a"], cwd=tmp_path)
+    run(["sketch", "-fp", "DNA2-CFL.txt", "-o", "b"], cwd=tmp_path)
+    r = run(["dist", "-fp", "a.msh", "b.msh"], cwd=tmp_path)
+    rows = [l.split("\t") for l in r.stdout.splitlines() if "\t" in l]
+    w = oracle.compare(a[0]["hashes32"][:1000], b[0]["hashes32"][:1000], a[0]["length"], b[0]["length"], 1000, 1, 10.0)
+    assert rows[0][4] == "%d/%d" % (w["numer"], w["denom"]) and rows[0][2] == "%g" % w["distance"]
+
+
+def test_sketch_individual_and_options(tmp_path, oracle):
+    from util import dirty_dna
+    rng = np.random.default_rng(8)
+    recs = [dirty_dna(rng, n) for n in (5000, 12, 30000, 800)]
+    with open(tmp_path / "multi.fa", "wb") as f:
+        for i, r in enumerate(recs):
+            f.write(b">rec%d some comment %d\n" % (i, i))
+            for p in range(0, len(r), 70):
+                f.write(r[p:p + 70] + b"\n")
+    run(["sketch", "-i", "-k", "16", "-s", "400", "-S", "7", "-M", "multi.fa"], cwd=tmp_path)
+    m = mshpy.load(tmp_path / "multi.fa.msh")
+    assert (m.kmer_size, m.sketch_size, m.hash_seed, m.concatenated, m.used_old_list) == (16, 400, 7, False, False)
+    keep = [(i, r) for i, r in enumerate(recs) if len(r) >= 16]
+    assert [x["name"] for x in m.refs] == ["rec%d" % i for i, _ in keep]
+    for x, (i, r) in zip(m.refs, keep):
+        w = oracle.sketch([r], k=16, s=400, seed=7)
+        assert x["hashes32"] == [int(v) for v in w["hashes"]] and x["counts32"] == [int(v) for v in w["counts"]]
+        assert x["length"] == len(r) and x["comment"] == "some comment %d" % i
+    # whole-file mode, gzipped input, noncanonical
+    with open(tmp_path / "multi.fa", "rb") as f, gzip.open(tmp_path / "multi.fa.gz", "wb") as g:
+        g.write(f.read())
+    run(["sketch", "-n", "-o", "whole", "multi.fa.gz"], cwd=tmp_path)
+    m = mshpy.load(tmp_path / "whole.msh")
+    w = oracle.sketch(recs, k=21, s=1000, noncanonical=True)
+    assert m.refs[0]["hashes64"] == [int(v) for v in w["hashes"]] and m.noncanonical
+    assert m.refs[0]["length"] == sum(len(r) for _, r in [(i, r) for i, r in enumerate(recs) if len(r) >= 21])
+    assert m.refs[0]["comment"] == "[3 seqs] rec0 some comment 0 [...]" and m.refs[0]["name"] == "multi.fa.gz"
