@@ -1,0 +1,170 @@
+// sketch_hash_v2.cuh -- the production sketching kernel (round-1 second version).
+//
+// Changes against the first version (kept in sketch_kernels.cuh for the test/count kernels), each
+// motivated by the ncu capture in profiles/r01_sketch_hash.txt:
+//   * warp-autonomous: a warp loads 64 bases per lane, converts them in registers and gets its
+//     right-hand halo from the next lane with three shuffles -- no shared memory, no
+//     __syncthreads (the "barrier" stall was 1.6 warps/issue);
+//   * 4-window unrolling with byte-wise shifting of the forward / reverse-complement registers
+//     between sub-blocks instead of 16 fully unrolled windows: ~10 KB of code instead of 55 KB
+//     (the top stall was "no_instruction", i.e. instruction-cache misses);
+//   * validity computed four bases at a time (re-expand the 2-bit code with PRMT and compare with
+//     the input bytes) instead of a per-byte test;
+//   * each warp walks a contiguous run of tiles and caches the sketch it is in, so the per-tile
+//     group lookup is a register compare except at sketch boundaries.
+//
+// Work decomposition: warp tile = 63 chunks of 32 windows (2016 windows).  Lane l converts
+// chunks 2l and 2l+1; lanes 0..30 hash both, lane 31 hashes only its first chunk -- its second
+// chunk is the halo of lane 30 and the first chunk of the next warp tile.
+#pragma once
+#include "sketch_kernels.cuh"
+
+namespace fpm {
+
+constexpr int WT_WINDOWS = 63 * 32;        // windows per warp tile
+constexpr int WT_TILES_PER_WARP = 12;      // contiguous warp tiles walked by one warp
+
+// 4 ASCII bytes -> 4 validity bits (bit j = byte j is one of ACGT after optional case fold).
+// valid  <=>  the byte equals the ASCII letter its own 2-bit code expands to.
+__device__ __forceinline__ uint32_t nt_valid4_simd(uint32_t x, uint32_t fold_mask)
+{
+    const uint32_t TBL = 0x54474341u;                       // 'A','C','G','T'
+    uint32_t f = x & fold_mask;
+    uint32_t c = ((x >> 1) ^ (x >> 2)) & 0x03030303u;       // per-byte code
+    uint32_t t = c | (c >> 4);                              // byte0 = c0|c1<<4, byte2 = c2|c3<<4
+    uint32_t sel = prmt(t, 0u, 0x4420u);                    // selector nibbles c0,c1,c2,c3
+    uint32_t e = prmt(TBL, 0u, sel);                        // expected ASCII per byte
+    uint32_t d = e ^ f;                                     // zero byte <=> valid
+    uint32_t nz = (((d & 0x7f7f7f7fu) + 0x7f7f7f7fu) | d) & 0x80808080u;   // bit 7 of each non-zero byte
+    uint32_t ok = (nz ^ 0x80808080u) >> 7;                  // bits 0,8,16,24
+    return (ok * 0x00204081u) >> 21 & 0xfu;                 // gather to bits 0..3
+}
+
+// 32 ASCII bases (8 words) -> two big-endian 2-bit code words + 32 validity bits
+__device__ __forceinline__ void convert32(const uint32_t (&w)[8], uint32_t fold_mask, uint32_t& c0, uint32_t& c1, uint32_t& v)
+{
+    c0 = 0; c1 = 0; v = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        c0 |= nt_codes4(w[i]) << (24 - 8 * i);
+        c1 |= nt_codes4(w[i + 4]) << (24 - 8 * i);
+        v |= nt_valid4_simd(w[i], fold_mask) << (4 * i);
+        v |= nt_valid4_simd(w[i + 4], fold_mask) << (16 + 4 * i);
+    }
+}
+
+template <int K, bool CANON>
+__global__ void __launch_bounds__(SK_THREADS) sketch_hash_kernel_v2(const SketchArgs* __restrict__ ga, uint64_t range_lo, uint64_t range_hi,
+                                                                   uint64_t range_base, int trace)
+{
+    const SketchArgs& a = *ga;
+    const uint8_t* __restrict__ seq = a.seq;
+    const uint64_t n_bytes = a.n_bytes;
+    const uint32_t seed = a.seed;
+    const int hash32 = a.hash32;
+    const uint32_t fold_mask = a.fold_case ? 0xdfdfdfdfu : 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = (uint64_t)blockIdx.x * (SK_THREADS / 32) + (threadIdx.x >> 5);
+    const uint64_t n_tiles = (range_hi - range_base + WT_WINDOWS - 1) / WT_WINDOWS;
+    uint64_t t0 = warp * WT_TILES_PER_WARP, t1 = t0 + WT_TILES_PER_WARP;
+    if (t1 > n_tiles) t1 = n_tiles;
+
+    // the sketch ("group") this warp is currently inside; [g_begin, g_end) in bytes
+    uint32_t g_lo = 0, g_hi = 0;
+    uint64_t g_begin = 1, g_end = 0, tmax = 0;   // empty interval: forces a lookup on the first tile
+    bool uniform_ok = false;
+
+    for (uint64_t t = t0; t < t1; t++) {
+        const uint64_t tile_base = range_base + t * WT_WINDOWS;
+        uint64_t last = tile_base + WT_WINDOWS - 1;
+        if (last >= n_bytes) last = n_bytes - 1;
+        if (!(uniform_ok && tile_base >= g_begin && last < g_end)) {
+            // leaving the cached sketch: lane 0 looks the tile's sketches up, all lanes take the answer
+            uint32_t lo = 0, hi = 0;
+            uint64_t tm = 0, gb = 1, ge = 0;
+            int uni = 0;
+            if (lane == 0) {
+                lo = find_group(a.group_off, 0, a.n_groups - 1, tile_base);
+                hi = find_group(a.group_off, lo, a.n_groups - 1, last);
+                for (uint32_t g = lo; g <= hi; g++)
+                    if (a.active[g] && a.thresh[g] > tm) tm = a.thresh[g];
+                bool any = false;
+                for (uint32_t g = lo; g <= hi; g++) any |= a.active[g] != 0;
+                if (!any) tm = 0;
+                if (lo == hi) { uni = 1; gb = a.group_off[lo]; ge = a.group_off[lo + 1]; }
+                if (!any) uni |= 2;
+            }
+            g_lo = __shfl_sync(0xffffffffu, lo, 0);
+            g_hi = __shfl_sync(0xffffffffu, hi, 0);
+            tmax = __shfl_sync(0xffffffffu, tm, 0);
+            g_begin = __shfl_sync(0xffffffffu, gb, 0);
+            g_end = __shfl_sync(0xffffffffu, ge, 0);
+            uni = __shfl_sync(0xffffffffu, uni, 0);
+            uniform_ok = (uni & 1) != 0;
+            if (uni & 2) { if (!uniform_ok) continue; tmax = 0; }
+        }
+        const bool idle_tile = uniform_ok && tmax == 0 && !a.active[g_lo];
+        if (idle_tile) continue;
+
+        // ---- load + convert 64 bases per lane -------------------------------------------------
+        const uint64_t lane_pos = tile_base + 64ull * lane;
+        uint32_t q0, q1, q2, q3, q4, q5, v0, v1, v2;
+        {
+            uint4 l0 = load16_guarded(seq, lane_pos, n_bytes), l1 = load16_guarded(seq, lane_pos + 16, n_bytes);
+            uint4 l2 = load16_guarded(seq, lane_pos + 32, n_bytes), l3 = load16_guarded(seq, lane_pos + 48, n_bytes);
+            const uint32_t wa[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+            const uint32_t wb[8] = {l2.x, l2.y, l2.z, l2.w, l3.x, l3.y, l3.z, l3.w};
+            convert32(wa, fold_mask, q0, q1, v0);
+            convert32(wb, fold_mask, q2, q3, v1);
+        }
+        q4 = __shfl_down_sync(0xffffffffu, q0, 1);
+        q5 = __shfl_down_sync(0xffffffffu, q1, 1);
+        v2 = __shfl_down_sync(0xffffffffu, v0, 1);
+        const int nblk = lane == 31 ? 2 : 4;
+        if (lane_pos >= n_bytes) continue;            // (after the shuffles: no lane skips them)
+
+#pragma unroll 1
+        for (int blk = 0; blk < nblk; blk++) {
+            uint32_t fw0 = q0, fw1 = q1, fw2 = q2;
+            uint32_t x[5];
+            if (CANON) { x[0] = revcomp16(fw2); x[1] = revcomp16(fw1); x[2] = revcomp16(fw0); x[3] = 0; x[4] = 0; }
+#pragma unroll 1
+            for (int sub = 0; sub < 4; sub++) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    uint32_t fhi = j ? __funnelshift_l(fw1, fw0, 2 * j) : fw0;
+                    uint32_t flo = j ? __funnelshift_l(fw2, fw1, 2 * j) : fw1;
+                    uint32_t chi = fhi, clo = flo;
+                    if (CANON) {
+                        const int start = 48 - K - j;                 // constant: the rc registers move instead
+                        const int ia = start >> 4, sh = 2 * (start & 15);
+                        uint32_t rhi = sh ? __funnelshift_l(x[ia + 1], x[ia], sh) : x[ia];
+                        uint32_t rlo = sh ? __funnelshift_l(x[ia + 2], x[ia + 1], sh) : x[ia + 1];
+                        // bits below the k-mer only matter for palindromes, where both strands hash alike
+                        bool use_r = (rhi < fhi) || (rhi == fhi && rlo < flo);
+                        chi = use_r ? rhi : fhi;
+                        clo = use_r ? rlo : flo;
+                    }
+                    uint64_t w[4];
+                    expand_ascii<K>(chi, clo, w);
+                    uint64_t h = murmur3_h1_fixed<K>(w, seed);
+                    if (hash32) h &= 0xffffffffULL;
+                    if (h <= tmax) {
+                        const int b = 16 * blk + 4 * sub + j;                    // window index within the lane's 64
+                        const uint64_t vlo = ((uint64_t)v1 << 32) | v0;
+                        const uint64_t vw = b ? ((vlo >> b) | ((uint64_t)v2 << (64 - b))) : vlo;
+                        constexpr uint64_t km = (1ULL << K) - 1;
+                        const uint64_t pos = lane_pos + b;
+                        if ((vw & km) == km && pos >= range_lo && pos < range_hi) sketch_emit(a, h, pos, g_lo, g_hi, trace);
+                    }
+                }
+                // next four windows: forward registers one byte left, reverse-complement one byte right
+                fw0 = __funnelshift_l(fw1, fw0, 8); fw1 = __funnelshift_l(fw2, fw1, 8); fw2 <<= 8;
+                if (CANON) { x[2] = __funnelshift_r(x[2], x[1], 8); x[1] = __funnelshift_r(x[1], x[0], 8); x[0] >>= 8; }
+            }
+            q0 = q1; q1 = q2; q2 = q3; q3 = q4; q4 = q5;
+        }
+    }
+}
+
+}  // namespace fpm

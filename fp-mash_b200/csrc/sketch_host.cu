@@ -60,6 +60,17 @@ struct GroupPlan {
 
 static const uint64_t kAll64 = ~0ULL;
 
+// [lo, hi) byte ranges covering the active sketches, adjacent active sketches merged into one range
+static void active_ranges(const std::vector<uint8_t>& active, const uint64_t* goff, uint32_t n_groups,
+                          std::vector<std::pair<uint64_t, uint64_t>>& out)
+{
+    for (uint32_t g = 0; g < n_groups; g++) {
+        if (!active[g] || goff[g + 1] == goff[g]) continue;
+        if (!out.empty() && out.back().second == goff[g]) out.back().second = goff[g + 1];
+        else out.push_back({goff[g], goff[g + 1]});
+    }
+}
+
 static uint64_t scale_threshold(uint64_t bits_full /*2^bits - 1*/, double frac)
 {
     if (frac >= 1.0) return bits_full;
@@ -128,7 +139,7 @@ int sketch_batch_dev_impl(fpm_ctx* ctx, const fpm_sketch_params* p, const uint8_
     std::vector<uint8_t> active(n_groups, 1);
     std::vector<uint64_t> h_thresh(n_groups), h_toff(n_groups);
     std::vector<uint32_t> h_tmask(n_groups), h_stat(4 * (size_t)n_groups), h_over(n_groups), h_outn(n_groups, 0), h_topcnt(n_groups, 0);
-    std::vector<uint32_t> tiles;
+    std::vector<std::pair<uint64_t, uint64_t>> ranges;
 
     uint32_t* d_stat_nq = ctx->stat.as<uint32_t>();
     uint32_t* d_stat_nd = d_stat_nq + n_groups;
@@ -166,36 +177,24 @@ int sketch_batch_dev_impl(fpm_ctx* ctx, const fpm_sketch_params* p, const uint8_
         FPM_CUDA(cudaMemcpyAsync(ctx->toff.p, h_toff.data(), sizeof(uint64_t) * n_groups, cudaMemcpyHostToDevice, st));
         FPM_CUDA(cudaMemcpyAsync(ctx->tmask.p, h_tmask.data(), sizeof(uint32_t) * n_groups, cudaMemcpyHostToDevice, st));
 
-        // tile list: identity on the first pass, tiles of the active groups afterwards
-        const uint32_t* d_tiles = nullptr;
-        uint32_t grid = n_tiles;
-        if (pass > 0) {
-            tiles.clear();
-            for (uint32_t g = 0; g < n_groups; g++) {
-                if (!active[g] || h_goff[g + 1] == h_goff[g]) continue;
-                uint32_t t0 = (uint32_t)(h_goff[g] / SK_TILE_WINDOWS), t1 = (uint32_t)((h_goff[g + 1] - 1) / SK_TILE_WINDOWS);
-                if (!tiles.empty() && tiles.back() >= t0) t0 = tiles.back() + 1;
-                for (uint32_t t = t0; t <= t1; t++) tiles.push_back(t);
-            }
-            if ((rc = ctx->tiles.ensure(sizeof(uint32_t) * std::max<size_t>(tiles.size(), 1)))) return rc;
-            FPM_CUDA(cudaMemcpyAsync(ctx->tiles.p, tiles.data(), sizeof(uint32_t) * tiles.size(), cudaMemcpyHostToDevice, st));
-            d_tiles = ctx->tiles.as<uint32_t>();
-            grid = (uint32_t)tiles.size();
-        }
+        // byte ranges to hash: everything on the first pass, afterwards the runs of adjacent active sketches
+        ranges.clear();
+        if (pass == 0) ranges.push_back({0, n_bytes});
+        else active_ranges(active, h_goff, n_groups, ranges);
 
         SketchArgs a;
         memset(&a, 0, sizeof a);
         a.seq = d_seq; a.n_bytes = n_bytes; a.group_off = ctx->goff.as<uint64_t>(); a.n_groups = n_groups;
-        a.tile_list = d_tiles; a.thresh = ctx->thresh.as<uint64_t>(); a.active = ctx->active.as<uint8_t>();
+        a.tile_list = nullptr; a.thresh = ctx->thresh.as<uint64_t>(); a.active = ctx->active.as<uint8_t>();
         a.tkeys = ctx->tkeys.as<uint64_t>(); a.tcnt = ctx->tcnt.as<uint32_t>(); a.tpos = ctx->tpos.as<uint64_t>();
         a.toff = ctx->toff.as<uint64_t>(); a.tmask = ctx->tmask.as<uint32_t>();
         a.maxkey_cnt = ctx->maxcnt.as<uint32_t>(); a.maxkey_pos = ctx->maxpos.as<uint64_t>();
         a.overflow = ctx->overflow.as<uint32_t>();
         a.sketch_size = s; a.seed = p->seed; a.fold_case = !p->preserve_case; a.hash32 = !p->use64;
         FPM_CUDA(cudaMemcpyAsync(ctx->args.p, &a, sizeof a, cudaMemcpyHostToDevice, st));
-        if (grid) {
+        for (const auto& r : ranges) {
             ctx->time_begin(FPM_KERNEL_SKETCH_HASH);
-            g_hash_launch[K - 1](canon, grid, st, ctx->args.as<SketchArgs>(), 0);
+            g_hash_launch[K - 1](canon, st, ctx->args.as<SketchArgs>(), r.first, r.second, 0);
             ctx->time_end();
             ctx->launches++;
             FPM_CUDA(cudaGetLastError());
@@ -276,27 +275,23 @@ int sketch_batch_dev_impl(fpm_ctx* ctx, const fpm_sketch_params* p, const uint8_
             FPM_CUDA(cudaMemcpyAsync(ctx->active.p, active.data(), n_groups, cudaMemcpyHostToDevice, st));
             for (uint32_t g = 0; g < n_groups; g++) h_thresh[g] = plan[g].thresh;
             FPM_CUDA(cudaMemcpyAsync(ctx->thresh.p, h_thresh.data(), sizeof(uint64_t) * n_groups, cudaMemcpyHostToDevice, st));
-            tiles.clear();
-            for (uint32_t g : tg) {
-                uint32_t t0 = (uint32_t)(h_goff[g] / SK_TILE_WINDOWS), t1 = (uint32_t)((h_goff[g + 1] - 1) / SK_TILE_WINDOWS);
-                if (!tiles.empty() && tiles.back() >= t0) t0 = tiles.back() + 1;
-                for (uint32_t t = t0; t <= t1; t++) tiles.push_back(t);
-            }
-            if ((rc = ctx->tiles.ensure(sizeof(uint32_t) * tiles.size()))) return rc;
-            FPM_CUDA(cudaMemcpyAsync(ctx->tiles.p, tiles.data(), sizeof(uint32_t) * tiles.size(), cudaMemcpyHostToDevice, st));
+            ranges.clear();
+            active_ranges(active, h_goff, n_groups, ranges);
             SketchArgs a;
             memset(&a, 0, sizeof a);
             a.seq = d_seq; a.n_bytes = n_bytes; a.group_off = ctx->goff.as<uint64_t>(); a.n_groups = n_groups;
-            a.tile_list = ctx->tiles.as<uint32_t>(); a.thresh = ctx->thresh.as<uint64_t>(); a.active = ctx->active.as<uint8_t>();
+            a.tile_list = nullptr; a.thresh = ctx->thresh.as<uint64_t>(); a.active = ctx->active.as<uint8_t>();
             a.fin_hashes = d_out_hashes; a.fin_n = d_out_n; a.tr_off = ctx->tr_off.as<uint64_t>(); a.tr_cap = d_out_counts;
             a.tr_cursor = ctx->tr_cursor.as<uint32_t>(); a.tr_pos = ctx->tr_pos.as<uint64_t>();
             a.sketch_size = s; a.seed = p->seed; a.fold_case = !p->preserve_case; a.hash32 = !p->use64;
             FPM_CUDA(cudaMemcpyAsync(ctx->args.p, &a, sizeof a, cudaMemcpyHostToDevice, st));
-            ctx->time_begin(FPM_KERNEL_SKETCH_HASH);
-            g_hash_launch[K - 1](canon, (uint32_t)tiles.size(), st, ctx->args.as<SketchArgs>(), 1);
-            ctx->time_end();
-            ctx->launches++;
-            FPM_CUDA(cudaGetLastError());
+            for (const auto& r : ranges) {
+                ctx->time_begin(FPM_KERNEL_SKETCH_HASH);
+                g_hash_launch[K - 1](canon, st, ctx->args.as<SketchArgs>(), r.first, r.second, 1);
+                ctx->time_end();
+                ctx->launches++;
+                FPM_CUDA(cudaGetLastError());
+            }
             launch_sketch_topcount((uint32_t)tg.size(), st, ctx->glist.as<uint32_t>(), s, p->min_cov, a.tr_off, a.tr_cap, a.tr_pos, d_out_counts);
             ctx->launches++;
             FPM_CUDA(cudaGetLastError());

@@ -95,13 +95,19 @@ __device__ __forceinline__ uint32_t nt_valid4(uint32_t x, uint32_t fold_mask)
     return v;
 }
 
-__device__ __forceinline__ uint4 load16_guarded(const uint8_t* base, uint64_t off, uint64_t n)
+static __device__ __noinline__ uint4 load16_tail(const uint8_t* base, uint64_t off, uint64_t n)
 {
-    if (off + 16 <= n) return *reinterpret_cast<const uint4*>(base + off);
     uint32_t w[4] = {0, 0, 0, 0};
     for (int i = 0; i < 16; i++)
         if (off + i < n) w[i >> 2] |= (uint32_t)base[off + i] << (8 * (i & 3));
     return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// 16 bytes at `off`; bytes at or beyond n read as 0x00 (never in an alphabet)
+__device__ __forceinline__ uint4 load16_guarded(const uint8_t* base, uint64_t off, uint64_t n)
+{
+    if (off + 16 <= n) return *reinterpret_cast<const uint4*>(base + off);
+    return load16_tail(base, off, n);
 }
 
 // Convert one tile (SK_TILE_CHUNKS x 32 bases starting at byte tile_base) into shared memory:
