@@ -41,7 +41,7 @@ W_INT32_OPS = {21: 74, 32: 96, 16: 64}   # int32-op equivalents 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--genomes", type=int, default=1000, help="genomes per GPU (config: 1000)")
@@ -124,7 +124,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -289,7 +289,6 @@ def main():
     e1.record()
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
-    clocks = sampler.stop() if rank == 0 else None
     launches = ctx.launch_count() - launches0
     hash_ms, hash_n = ctx.get_timing(fpm.KERNEL_SKETCH_HASH)
     sel_ms, sel_n = ctx.get_timing(fpm.KERNEL_SKETCH_SELECT)
@@ -313,6 +312,7 @@ def main():
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * windows_per_step * args.steps / e2e_s / 1e9
+    clocks = sampler.stop() if rank == 0 else None   # sampled across the resident and the end-to-end timed regions
     assert np.array_equal(e2e_res["hashes"], out_h.cpu().numpy().view(np.uint64)), "e2e and resident sketches differ"
     h2d = int(seq.numel() + offsets.nbytes)
     d2h = int(n * S * 8 + n * 4)

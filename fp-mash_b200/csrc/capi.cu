@@ -172,6 +172,7 @@ void fpm_ctx_destroy(fpm_ctx* c)
                            &c->d_out, &c->d_misc};
     for (auto* b : bufs) b->release();
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    if (c->copy_stream) { cudaStreamDestroy(c->copy_stream); cudaEventDestroy(c->copy_done[0]); cudaEventDestroy(c->copy_done[1]); }
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }

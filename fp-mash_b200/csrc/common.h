@@ -33,6 +33,8 @@ struct fpm_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = true;
+    cudaStream_t copy_stream = nullptr;          // H2D of the next chunk while the current one is hashed
+    cudaEvent_t copy_done[2] = {nullptr, nullptr};
     uint64_t launches = 0;
     int sm_count = 0;
     // sketch scratch

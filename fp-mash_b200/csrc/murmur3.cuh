@@ -35,12 +35,15 @@ __device__ __forceinline__ uint64_t fmix64(uint64_t k)
 __device__ __forceinline__ uint64_t mm_k1(uint64_t k) { k *= FPM_MC1; k = rotl64(k, 31); k *= FPM_MC2; return k; }
 __device__ __forceinline__ uint64_t mm_k2(uint64_t k) { k *= FPM_MC2; k = rotl64(k, 33); k *= FPM_MC1; return k; }
 
-__device__ __forceinline__ void mm_block(uint64_t& h1, uint64_t& h2, uint64_t k1, uint64_t k2)
+// add1/add2 are the two additive constants of the block mix; callers in hot loops pass them in
+// registers (an immediate would be re-materialised with two moves per use).
+__device__ __forceinline__ void mm_block(uint64_t& h1, uint64_t& h2, uint64_t k1, uint64_t k2,
+                                         uint64_t add1 = 0x52dce729ULL, uint64_t add2 = 0x38495ab5ULL)
 {
     h1 ^= mm_k1(k1);
-    h1 = rotl64(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729ULL;
+    h1 = rotl64(h1, 27); h1 += h2; h1 = h1 * 5 + add1;
     h2 ^= mm_k2(k2);
-    h2 = rotl64(h2, 31); h2 += h1; h2 = h2 * 5 + 0x38495ab5ULL;
+    h2 = rotl64(h2, 31); h2 += h1; h2 = h2 * 5 + add2;
 }
 
 __device__ __forceinline__ uint64_t mm_finish(uint64_t h1, uint64_t h2, uint64_t len)
@@ -55,13 +58,14 @@ __device__ __forceinline__ uint64_t mm_finish(uint64_t h1, uint64_t h2, uint64_t
 // (bytes >= LEN are zero).  LEN is a compile-time constant in 1..32, so the block/tail
 // structure of MurmurHash3.cpp:270-314 resolves statically.
 template <int LEN>
-__device__ __forceinline__ uint64_t murmur3_h1_fixed(const uint64_t (&w)[4], uint32_t seed)
+__device__ __forceinline__ uint64_t murmur3_h1_fixed(const uint64_t (&w)[4], uint32_t seed,
+                                                     uint64_t add1 = 0x52dce729ULL, uint64_t add2 = 0x38495ab5ULL)
 {
     uint64_t h1 = seed, h2 = seed;
     constexpr int nblocks = LEN / 16;
     constexpr int rem = LEN & 15;
-    if (nblocks >= 1) mm_block(h1, h2, w[0], w[1]);
-    if (nblocks >= 2) mm_block(h1, h2, w[2], w[3]);
+    if (nblocks >= 1) mm_block(h1, h2, w[0], w[1], add1, add2);
+    if (nblocks >= 2) mm_block(h1, h2, w[2], w[3], add1, add2);
     if (rem > 8) h2 ^= mm_k2(w[2 * nblocks + 1]);
     if (rem > 0) h1 ^= mm_k1(w[2 * nblocks]);
     return mm_finish(h1, h2, (uint64_t)LEN);

@@ -61,8 +61,12 @@ __global__ void __launch_bounds__(SK_THREADS) sketch_hash_kernel_v2(const Sketch
     const uint8_t* __restrict__ seq = a.seq;
     const uint64_t n_bytes = a.n_bytes;
     const uint32_t seed = a.seed;
-    const int hash32 = a.hash32;
+    constexpr bool hash32 = K <= 16;               // 4^K <= 2^32 (Sketch.cpp:1288); the host checks a.hash32 agrees
     const uint32_t fold_mask = a.fold_case ? 0xdfdfdfdfu : 0xffffffffu;
+    // constants kept in registers for the whole kernel: as immediates they cost moves per window
+    // (read from the argument block so that ptxas cannot fold them back into immediates)
+    const uint32_t tbl = a.c_tbl;
+    const uint64_t add1 = a.c_add1, add2 = a.c_add2;
     const int lane = threadIdx.x & 31;
     const uint64_t warp = (uint64_t)blockIdx.x * (SK_THREADS / 32) + (threadIdx.x >> 5);
     const uint64_t n_tiles = (range_hi - range_base + WT_WINDOWS - 1) / WT_WINDOWS;
@@ -141,13 +145,13 @@ __global__ void __launch_bounds__(SK_THREADS) sketch_hash_kernel_v2(const Sketch
                         uint32_t rhi = sh ? __funnelshift_l(x[ia + 1], x[ia], sh) : x[ia];
                         uint32_t rlo = sh ? __funnelshift_l(x[ia + 2], x[ia + 1], sh) : x[ia + 1];
                         // bits below the k-mer only matter for palindromes, where both strands hash alike
-                        bool use_r = (rhi < fhi) || (rhi == fhi && rlo < flo);
+                        bool use_r = (((uint64_t)rhi << 32) | rlo) < (((uint64_t)fhi << 32) | flo);
                         chi = use_r ? rhi : fhi;
                         clo = use_r ? rlo : flo;
                     }
                     uint64_t w[4];
-                    expand_ascii<K>(chi, clo, w);
-                    uint64_t h = murmur3_h1_fixed<K>(w, seed);
+                    expand_ascii<K>(chi, clo, w, tbl);
+                    uint64_t h = murmur3_h1_fixed<K>(w, seed, add1, add2);
                     if (hash32) h &= 0xffffffffULL;
                     if (h <= tmax) {
                         const int b = 16 * blk + 4 * sub + j;                    // window index within the lane's 64

@@ -191,6 +191,7 @@ int sketch_batch_dev_impl(fpm_ctx* ctx, const fpm_sketch_params* p, const uint8_
         a.maxkey_cnt = ctx->maxcnt.as<uint32_t>(); a.maxkey_pos = ctx->maxpos.as<uint64_t>();
         a.overflow = ctx->overflow.as<uint32_t>();
         a.sketch_size = s; a.seed = p->seed; a.fold_case = !p->preserve_case; a.hash32 = !p->use64;
+            a.c_tbl = 0x54474341u; a.c_add1 = 0x52dce729ULL; a.c_add2 = 0x38495ab5ULL;
         FPM_CUDA(cudaMemcpyAsync(ctx->args.p, &a, sizeof a, cudaMemcpyHostToDevice, st));
         for (const auto& r : ranges) {
             ctx->time_begin(FPM_KERNEL_SKETCH_HASH);
@@ -284,6 +285,7 @@ int sketch_batch_dev_impl(fpm_ctx* ctx, const fpm_sketch_params* p, const uint8_
             a.fin_hashes = d_out_hashes; a.fin_n = d_out_n; a.tr_off = ctx->tr_off.as<uint64_t>(); a.tr_cap = d_out_counts;
             a.tr_cursor = ctx->tr_cursor.as<uint32_t>(); a.tr_pos = ctx->tr_pos.as<uint64_t>();
             a.sketch_size = s; a.seed = p->seed; a.fold_case = !p->preserve_case; a.hash32 = !p->use64;
+            a.c_tbl = 0x54474341u; a.c_add1 = 0x52dce729ULL; a.c_add2 = 0x38495ab5ULL;
             FPM_CUDA(cudaMemcpyAsync(ctx->args.p, &a, sizeof a, cudaMemcpyHostToDevice, st));
             for (const auto& r : ranges) {
                 ctx->time_begin(FPM_KERNEL_SKETCH_HASH);
@@ -339,16 +341,56 @@ int fpm_sketch_batch(fpm_ctx* ctx, const fpm_sketch_params* p, const uint8_t* se
     if (!seq && seq_bytes) { set_error("seq is NULL"); return FPM_ERR_ARG; }
     FPM_CUDA(cudaSetDevice(ctx->device));
     const uint64_t s = p->sketch_size;
-    if ((rc = ctx->seq.ensure(seq_bytes + 64))) return rc;
     if ((rc = ctx->outh.ensure(sizeof(uint64_t) * n_groups * s))) return rc;
     if ((rc = ctx->outc.ensure(sizeof(uint32_t) * n_groups * s))) return rc;
     if ((rc = ctx->outn.ensure(sizeof(uint32_t) * n_groups))) return rc;
     if ((rc = ctx->outk.ensure(sizeof(uint64_t) * n_groups))) return rc;
-    FPM_CUDA(cudaMemcpyAsync(ctx->seq.p, seq, seq_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (!group_offsets || group_offsets[0] != 0 || group_offsets[n_groups] != seq_bytes) { set_error("group_offsets must start at 0 and end at seq_bytes"); return FPM_ERR_ARG; }
     bool counts = p->want_counts && out_counts;
-    rc = sketch_batch_dev_impl(ctx, p, ctx->seq.as<uint8_t>(), seq_bytes, group_offsets, n_groups, ctx->outh.as<uint64_t>(),
-                               counts ? ctx->outc.as<uint32_t>() : nullptr, ctx->outn.as<uint32_t>(),
-                               out_kmers ? ctx->outk.as<uint64_t>() : nullptr);
+
+    // Chunks of whole sketches, ~kChunkBytes each.  Chunk c+1 is copied on a second stream while
+    // chunk c is being hashed, so with pinned host memory the call costs max(H2D, kernels), not
+    // their sum.  Each chunk is placed 256-byte aligned on the device and sketched as a batch of
+    // its own (positions only need to be ordered within a sketch).
+    const uint64_t kChunkBytes = 256ull << 20;
+    std::vector<uint32_t> cut{0};
+    for (uint32_t g = 0; g < n_groups; g++)
+        if (group_offsets[g + 1] - group_offsets[cut.back()] >= kChunkBytes && g + 1 < n_groups) cut.push_back(g + 1);
+    cut.push_back(n_groups);
+    const size_t n_chunks = cut.size() - 1;
+    std::vector<uint64_t> dev_off(n_chunks);
+    uint64_t dev_total = 0;
+    for (size_t c = 0; c < n_chunks; c++) {
+        dev_off[c] = dev_total;
+        dev_total += ((group_offsets[cut[c + 1]] - group_offsets[cut[c]]) + 64 + 255) & ~255ull;
+    }
+    if ((rc = ctx->seq.ensure(dev_total + 64))) return rc;
+    if (n_chunks > 1 && !ctx->copy_stream) {
+        FPM_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        FPM_CUDA(cudaEventCreateWithFlags(&ctx->copy_done[0], cudaEventDisableTiming));
+        FPM_CUDA(cudaEventCreateWithFlags(&ctx->copy_done[1], cudaEventDisableTiming));
+    }
+    auto enqueue_copy = [&](size_t c) -> int {
+        uint64_t h0 = group_offsets[cut[c]], len = group_offsets[cut[c + 1]] - h0;
+        cudaStream_t cs = n_chunks > 1 ? ctx->copy_stream : ctx->stream;
+        if (len) FPM_CUDA(cudaMemcpyAsync(ctx->seq.as<uint8_t>() + dev_off[c], seq + h0, len, cudaMemcpyHostToDevice, cs));
+        if (n_chunks > 1) FPM_CUDA(cudaEventRecord(ctx->copy_done[c & 1], cs));
+        return FPM_OK;
+    };
+    if ((rc = enqueue_copy(0))) return rc;
+    std::vector<uint64_t> goff;
+    rc = FPM_OK;
+    for (size_t c = 0; c < n_chunks && rc == FPM_OK; c++) {
+        const uint32_t g0 = cut[c], ng = cut[c + 1] - cut[c];
+        if (n_chunks > 1) FPM_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->copy_done[c & 1], 0));
+        // the event of chunk c+1 reuses slot (c+1)&1, last used by chunk c-1 whose wait was already enqueued
+        if (c + 1 < n_chunks && (rc = enqueue_copy(c + 1))) return rc;
+        goff.resize(ng + 1);
+        for (uint32_t g = 0; g <= ng; g++) goff[g] = group_offsets[g0 + g] - group_offsets[g0];
+        rc = sketch_batch_dev_impl(ctx, p, ctx->seq.as<uint8_t>() + dev_off[c], goff[ng], goff.data(), ng,
+                                   ctx->outh.as<uint64_t>() + (uint64_t)g0 * s, counts ? ctx->outc.as<uint32_t>() + (uint64_t)g0 * s : nullptr,
+                                   ctx->outn.as<uint32_t>() + g0, out_kmers ? ctx->outk.as<uint64_t>() + g0 : nullptr);
+    }
     if (rc) return rc;
     FPM_CUDA(cudaMemcpyAsync(out_hashes, ctx->outh.p, sizeof(uint64_t) * n_groups * s, cudaMemcpyDeviceToHost, ctx->stream));
     if (counts) FPM_CUDA(cudaMemcpyAsync(out_counts, ctx->outc.p, sizeof(uint32_t) * n_groups * s, cudaMemcpyDeviceToHost, ctx->stream));

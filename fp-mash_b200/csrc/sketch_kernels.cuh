@@ -67,6 +67,9 @@ struct SketchArgs {
     uint32_t seed;
     int fold_case;               // !preserveCase
     int hash32;                  // !use64
+    // hot-loop constants handed over as data ('ACGT' table for PRMT, Murmur block addends)
+    uint32_t c_tbl;
+    uint64_t c_add1, c_add2;
 };
 
 // ---------------------------------------------------------------------------------------
@@ -159,9 +162,8 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
 // ("ACGT") four bases at a time; a selector nibble with bit 3 set replicates the sign bit
 // of an ASCII byte, i.e. yields 0x00, which zero-pads bytes >= K for free.
 template <int K>
-__device__ __forceinline__ void expand_ascii(uint32_t hi, uint32_t lo, uint64_t (&w)[4])
+__device__ __forceinline__ void expand_ascii(uint32_t hi, uint32_t lo, uint64_t (&w)[4], uint32_t TBL = 0x54474341u /* 'A','C','G','T' */)
 {
-    const uint32_t TBL = 0x54474341u;   // 'A','C','G','T'
     uint32_t e[4], o[4];
     uint32_t ehi = hi & 0x33333333u, ohi = (hi >> 2) & 0x33333333u;
     uint32_t elo = lo & 0x33333333u, olo = (lo >> 2) & 0x33333333u;
