@@ -42,26 +42,33 @@ void DevBuf::release()
     cap = 0;
 }
 
-// Four independent chains per thread of IMAD / LOP3 / SHF / IADD3 in the 1:2 FMA-pipe:ALU-pipe
-// proportion of the Murmur inner loop.  6 integer instructions per chain per iteration.
+// Integer-pipe microbenchmark.  Eight independent register chains per thread, instructions pinned
+// with inline PTX so ptxas keeps them 1:1.  MODE 0: ALU pipe only (LOP3 / SHF / IADD3-class),
+// MODE 1: FMA pipe only (IMAD), MODE 2: alternating.  Every asm statement is one counted op.
+template <int MODE>
 __global__ void __launch_bounds__(256) int32_peak_kernel(uint32_t iters, uint32_t seed, uint32_t* sink)
 {
-    uint32_t a0 = seed + threadIdx.x, a1 = a0 * 3 + 1, a2 = a0 * 5 + 2, a3 = a0 * 7 + 3;
-    uint32_t b0 = blockIdx.x + 11, b1 = b0 + 1, b2 = b0 + 2, b3 = b0 + 3;
-#pragma unroll 4
+    uint32_t r[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) r[c] = seed * (2 * c + 1) + threadIdx.x + blockIdx.x;
+    const uint32_t k1 = seed | 0x9e3779b1u, k2 = seed ^ 0x7f4a7c15u;
+#pragma unroll 1
     for (uint32_t i = 0; i < iters; i++) {
-#define FPM_STEP(a, b)                                \
-        a = a * 0x9e3779b1u + b;           /* IMAD  */ \
-        b = __funnelshift_l(a, b, 7);      /* SHF   */ \
-        b = (b ^ a) & 0x7fffff7fu;         /* LOP3  */ \
-        a = a * 0x85ebca6bu + i;           /* IMAD  */ \
-        b = b + a + 0x1234567u;            /* IADD3 */ \
-        a = __funnelshift_r(b, a, 11);     /* SHF   */
-        FPM_STEP(a0, b0) FPM_STEP(a1, b1) FPM_STEP(a2, b2) FPM_STEP(a3, b3)
-#undef FPM_STEP
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                if (MODE == 0 || (MODE == 2 && ((c + u) & 1)))
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(r[c]) : "r"(k1), "r"(k2));
+                else
+                    asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(r[c]) : "r"(k1), "r"(k2));
+            }
+        }
     }
-    uint32_t r = a0 ^ a1 ^ a2 ^ a3 ^ b0 ^ b1 ^ b2 ^ b3;
-    if (r == 0x12345u) sink[0] = r;   // never true in practice; keeps the chains alive
+    uint32_t x = 0;
+#pragma unroll
+    for (int c = 0; c < 8; c++) x ^= r[c];
+    if (x == 0x12345u) sink[0] = x;   // practically never; keeps the chains alive
 }
 
 }  // namespace fpm
@@ -210,28 +217,42 @@ void fpm_host_free(void* p)
     if (p) cudaFreeHost(p);
 }
 
+int fpm_get_int32_peaks(fpm_ctx* c, double* out3)
+{
+    if (!c || !out3) { set_error("NULL argument"); return FPM_ERR_ARG; }
+    for (int i = 0; i < 3; i++) out3[i] = c->int_peak[i];
+    return FPM_OK;
+}
+
 int fpm_measure_int32_peak(fpm_ctx* c, double* out_ops_per_s)
 {
     if (!c || !out_ops_per_s) { set_error("NULL argument"); return FPM_ERR_ARG; }
     FPM_CUDA(cudaSetDevice(c->device));
     int rc = c->d_misc.ensure(64);
     if (rc) return rc;
-    const uint32_t iters = 1 << 14;
+    const uint32_t iters = 1 << 11;
     const uint32_t grid = (uint32_t)c->sm_count * 8;
     cudaEvent_t e0, e1;
     FPM_CUDA(cudaEventCreate(&e0));
     FPM_CUDA(cudaEventCreate(&e1));
     double best = 0;
-    for (int rep = 0; rep < 5; rep++) {
-        FPM_CUDA(cudaEventRecord(e0, c->stream));
-        int32_peak_kernel<<<grid, 256, 0, c->stream>>>(iters, (uint32_t)rep, c->d_misc.as<uint32_t>());
-        c->launches++;
-        FPM_CUDA(cudaEventRecord(e1, c->stream));
-        FPM_CUDA(cudaEventSynchronize(e1));
-        float ms = 0;
-        FPM_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-        double ops = (double)grid * 256.0 * iters * 24.0;   // 4 chains x 6 instructions
-        if (rep > 0 && ms > 0) best = std::max(best, ops / (ms * 1e-3));
+    for (int mode = 0; mode < 3; mode++) {
+        double best_mode = 0;
+        for (int rep = 0; rep < 4; rep++) {
+            FPM_CUDA(cudaEventRecord(e0, c->stream));
+            if (mode == 0) int32_peak_kernel<0><<<grid, 256, 0, c->stream>>>(iters, (uint32_t)rep + 3, c->d_misc.as<uint32_t>());
+            else if (mode == 1) int32_peak_kernel<1><<<grid, 256, 0, c->stream>>>(iters, (uint32_t)rep + 3, c->d_misc.as<uint32_t>());
+            else int32_peak_kernel<2><<<grid, 256, 0, c->stream>>>(iters, (uint32_t)rep + 3, c->d_misc.as<uint32_t>());
+            c->launches++;
+            FPM_CUDA(cudaEventRecord(e1, c->stream));
+            FPM_CUDA(cudaEventSynchronize(e1));
+            float ms = 0;
+            FPM_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+            double ops = (double)grid * 256.0 * iters * 32.0;   // 4 x 8 counted instructions per iteration
+            if (rep > 0 && ms > 0) best_mode = std::max(best_mode, ops / (ms * 1e-3));
+        }
+        c->int_peak[mode] = best_mode;
+        best = std::max(best, best_mode);
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);

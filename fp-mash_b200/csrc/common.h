@@ -37,6 +37,7 @@ struct fpm_ctx {
     cudaEvent_t copy_done[2] = {nullptr, nullptr};
     uint64_t launches = 0;
     int sm_count = 0;
+    double int_peak[3] = {0, 0, 0};              // last fpm_measure_int32_peak: ALU-only, IMAD-only, alternating
     // sketch scratch
     fpm::DevBuf seq, goff, thresh, active, toff, tmask, tkeys, tcnt, tpos, maxcnt, maxpos, overflow,
         stat, tiles, args, outh, outc, outn, outk, firstpos, tr_off, tr_cursor, tr_pos, glist;

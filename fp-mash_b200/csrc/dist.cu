@@ -33,7 +33,7 @@ constexpr uint64_t DT_INF = ~0ULL;
 constexpr int DT_Q = 16;            // query columns per CTA
 constexpr int DT_R = 32;            // reference columns per CTA (two 16-column planes)
 constexpr int DT_COLS = DT_Q + DT_R;
-constexpr int DT_ROWS = 576;        // rows resident per phase
+constexpr int DT_ROWS = 280;        // rows resident per phase (108 KB: two CTAs per SM)
 constexpr int DT_THREADS = DT_Q * DT_R;   // 512
 
 struct DistArgs {
@@ -41,6 +41,11 @@ struct DistArgs {
     int kmer_size;
     double kmer_space, max_distance, max_pvalue;
 };
+
+__device__ __forceinline__ void lds64(uint32_t addr, uint32_t& lo, uint32_t& hi)
+{
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(addr));
+}
 
 __device__ __forceinline__ void finish_pair(const DistArgs& a, uint64_t common, uint64_t denom, uint64_t len_ref, uint64_t len_qry, fpm_pair* out)
 {
@@ -92,7 +97,7 @@ __global__ void __launch_bounds__(256) dist_literal_kernel(fpm_panel ref, fpm_pa
 }
 
 // Row-major [n][stride] -> column tiles [ceil(n/16)][rows][16], +inf beyond each sketch's size.
-// flags[0] |= 1 if a real hash equals the sentinel or a row is not strictly ascending (the
+// flags[0] |= 1 if a real hash collides with the sentinel's high word or a row is not strictly ascending (the
 // host then falls back to the literal kernel).
 __global__ void __launch_bounds__(256) dist_pack_kernel(fpm_panel pn, uint64_t rows, uint64_t* packed, uint32_t* flags)
 {
@@ -104,14 +109,14 @@ __global__ void __launch_bounds__(256) dist_pack_kernel(fpm_panel pn, uint64_t r
     uint64_t v = DT_INF;
     if (sk < pn.n && row < pn.sizes[sk]) {
         v = pn.hashes[sk * pn.stride + row];
-        bool bad = v == DT_INF;
+        bool bad = (v >> 32) == 0xffffffffULL;   // high word all ones is reserved for the +inf sentinel
         if (row > 0 && pn.hashes[sk * pn.stride + row - 1] >= v) bad = true;
         if (bad) atomicOr(flags, 1u);
     }
     packed[idx] = v;
 }
 
-__global__ void __launch_bounds__(DT_THREADS, 1)
+__global__ void __launch_bounds__(DT_THREADS, 2)
 dist_tile_kernel(const uint64_t* __restrict__ pref, const uint64_t* __restrict__ pqry, uint64_t rows_ref, uint64_t rows_qry,
                  uint64_t n_ref, uint64_t n_qry, const uint64_t* __restrict__ len_ref, const uint64_t* __restrict__ len_qry,
                  DistArgs a, fpm_pair* __restrict__ out, unsigned long long* steps)
@@ -176,19 +181,29 @@ dist_tile_kernel(const uint64_t* __restrict__ pref, const uint64_t* __restrict__
 
         // ---- merge up to V ------------------------------------------------------------
         if (!done) {
-            const uint64_t* pa = colQ + qc;
-            const uint64_t* pb = colR + h * (DT_ROWS + 1) * 16 + rc;
-            uint64_t x = *pa, y = *pb;
-            // reference loop with one simplification: an exhausted list reads +inf, and the
-            // "complete the union" tail (CommandDistance.cpp:389-400) is the same loop running
-            // on the surviving list one element per step.
-            while (denom < a.s && (x & y) != DT_INF) {
-                bool le = x <= y, ge = y <= x;
-                common += le & ge;
-                denom++;
-                if (le) { pa += 16; x = *pa; }
-                if (ge) { pb += 16; y = *pb; }
+            // The reference loop (CommandDistance.cpp:376-387) with two simplifications: an exhausted
+            // (or phase-masked) list reads +inf, and the "complete the union" tail (:389-400) is the
+            // same loop running on the surviving list one element per step.  Values are handled as
+            // 32-bit halves and shared-space byte addresses so one step is ~13 instructions.  The
+            // common count is recovered from the pointers: advances(a) + advances(b) = steps + matches.
+            const uint32_t pa0 = (uint32_t)__cvta_generic_to_shared(colQ + qc);
+            const uint32_t pb0 = (uint32_t)__cvta_generic_to_shared(colR + h * (DT_ROWS + 1) * 16 + rc);
+            uint32_t pa = pa0, pb = pb0, alo, ahi, blo, bhi;
+            lds64(pa, alo, ahi);
+            lds64(pb, blo, bhi);
+            const uint32_t budget = a.s - denom;
+            uint32_t rem = budget;
+            // (pack flagged any real hash whose high word is all ones, so hi == ~0 <=> +inf)
+            while (rem != 0 && (ahi & bhi) != 0xffffffffu) {
+                const uint64_t x = ((uint64_t)ahi << 32) | alo, y = ((uint64_t)bhi << 32) | blo;
+                const bool lt = x < y, gt = y < x;
+                if (!gt) { pa += 128; lds64(pa, alo, ahi); }
+                if (!lt) { pb += 128; lds64(pb, blo, bhi); }
+                rem--;
             }
+            const uint32_t steps = budget - rem;
+            denom += steps;
+            common += ((pa - pa0) >> 7) + ((pb - pb0) >> 7) - steps;
             if (denom >= a.s || V == DT_INF) done = true;
         }
         // ---- anyone left?  then advance every column past its elements < V ------------

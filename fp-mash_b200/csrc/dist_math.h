@@ -79,6 +79,10 @@ FPM_HD double binom_tail_ge(uint64_t x, uint64_t n, double r)
     double m;
     long long e;
     if (double(x) >= mean) {
+        // Cheap exit for hopeless tails (the common case between related genomes: hundreds of shared
+        // hashes, p far below the smallest double).  tail <= (n+1) * C(n,x) r^x <= (n+1) * (e*n*r/x)^x;
+        // below 2^-1200 the full evaluation returns 0 as well (ldexp_clamped), so results are identical.
+        if (double(x) * log2(2.718281828459045 * double(n) * r / double(x)) + log2(double(n) + 1.) < -1200.) return 0.;
         binom_pmf_scaled(n, x, r, m, e);
         double sum = m, term = m;
         for (uint64_t i = x; i < n; i++) {

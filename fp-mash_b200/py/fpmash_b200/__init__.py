@@ -92,6 +92,7 @@ lib.fpm_pvalue.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_double, C.c_u
 lib.fpm_distance.restype = C.c_double
 lib.fpm_distance.argtypes = [C.c_uint64, C.c_uint64, C.c_int]
 lib.fpm_measure_int32_peak.argtypes = [_VP, C.POINTER(C.c_double)]
+lib.fpm_get_int32_peaks.argtypes = [_VP, C.POINTER(C.c_double)]
 lib.fpm_ctx_set_timing.argtypes = [_VP, C.c_int]
 lib.fpm_ctx_get_timing.argtypes = [_VP, C.c_int, C.POINTER(C.c_double), u64p]
 
@@ -101,7 +102,7 @@ EXPORTED = ["fpm_abi_version", "fpm_device_count", "fpm_ctx_create", "fpm_ctx_de
             "fpm_ctx_sync", "fpm_ctx_stream", "fpm_ctx_set_stream", "fpm_host_alloc", "fpm_host_free",
             "fpm_ctx_launch_count", "fpm_sketch_batch", "fpm_sketch_batch_dev", "fpm_kmer_hashes",
             "fpm_fp_hash_batch", "fpm_dist_tile", "fpm_dist_tile_dev", "fpm_pvalue", "fpm_distance",
-            "fpm_measure_int32_peak", "fpm_ctx_set_timing", "fpm_ctx_get_timing"]
+            "fpm_measure_int32_peak", "fpm_get_int32_peaks", "fpm_ctx_set_timing", "fpm_ctx_get_timing"]
 
 
 def _check(rc):
@@ -204,6 +205,12 @@ class Context:
         _check(lib.fpm_measure_int32_peak(self._h, C.byref(v)))
         return v.value
 
+    def int32_peaks(self):
+        """(ALU-only, IMAD-only, alternating) thread-instructions/s from the last int32_peak()."""
+        a = (C.c_double * 3)()
+        _check(lib.fpm_get_int32_peaks(self._h, a))
+        return tuple(a)
+
     # -- sketch ---------------------------------------------------------------------------
     def sketch_batch(self, seq, group_offsets, params, want_kmers=False):
         """Host buffers in, host arrays out (H2D + kernels + D2H)."""
@@ -281,13 +288,16 @@ class Context:
         return p, (h, sz, ln)
 
     def dist_tile(self, ref, qry, sketch_size, kmer_size, kmer_space, max_distance=1.0, max_pvalue=1.0,
-                  sorted_unique=True):
+                  sorted_unique=True, out=None):
         """ref / qry: (hashes [n][stride], sizes [n], lengths [n]).  Returns a structured array
-        [n_qry][n_ref] of (numer, denom, distance, pvalue) plus a bool `pass` matrix."""
+        [n_qry][n_ref] of (numer, denom, distance, pvalue) plus a bool `pass` matrix.  `out` may be a
+        caller-owned (e.g. pinned) PAIR_DTYPE array of that shape."""
         pr, keep_r = self._panel(*ref)
         pq, keep_q = self._panel(*qry)
         dp = DistParams(sketch_size, kmer_size, kmer_space, max_distance, max_pvalue, int(sorted_unique))
-        out = np.zeros((pq.n, pr.n), dtype=PAIR_DTYPE)
+        if out is None:
+            out = np.zeros((pq.n, pr.n), dtype=PAIR_DTYPE)
+        assert out.dtype == PAIR_DTYPE and out.shape == (pq.n, pr.n) and out.flags["C_CONTIGUOUS"]
         _check(lib.fpm_dist_tile(self._h, C.byref(dp), C.byref(pr), C.byref(pq), out.ctypes.data))
         passed = (out["denom"] & FPM_PAIR_PASS) != 0
         out["denom"] &= 0x7fffffff

@@ -175,6 +175,9 @@ int fpm_ctx_get_timing(fpm_ctx* ctx, int kernel_id, double* out_ms_total, uint64
  * IMAD+LOP3+SHF mix on every SM), the denominator of the sketch kernel's integer roofline
  * (INT32 peak is not in MEASURED_PEAKS.json and must be measured).           */
 int fpm_measure_int32_peak(fpm_ctx* ctx, double* out_ops_per_s);
+/* The three figures behind the last fpm_measure_int32_peak: [0] ALU pipe only (LOP3), [1] FMA pipe only
+ * (IMAD), [2] alternating; the value returned above is their maximum.                              */
+int fpm_get_int32_peaks(fpm_ctx* ctx, double* out3);
 
 #ifdef __cplusplus
 }
