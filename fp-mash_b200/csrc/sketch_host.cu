@@ -10,6 +10,7 @@
 #include "sketch_kernels.cuh"
 #include "sketch_launch.h"
 #include "sketch_select.h"
+#include <math.h>
 
 namespace fpm {
 
@@ -30,22 +31,30 @@ static uint32_t pow2ceil(uint64_t v)
     return (uint32_t)std::min<uint64_t>(p, 1ull << 31);
 }
 
+static bool is_nucleotide(const fpm_sketch_params* p)
+{
+    for (int c = 0; c < 256; c++)
+        if ((p->alphabet[c] != 0) != (c == 'A' || c == 'C' || c == 'G' || c == 'T')) return false;
+    return true;
+}
+
 static int check_params(const fpm_sketch_params* p)
 {
     if (!p) { set_error("sketch params are NULL"); return FPM_ERR_ARG; }
     if (p->kmer_size < 1 || p->kmer_size > 32) { set_error("k-mer size %d outside 1..32", p->kmer_size); return FPM_ERR_ARG; }
     if (p->sketch_size < 1) { set_error("sketch size must be >= 1"); return FPM_ERR_ARG; }
     if (p->min_cov < 1) { set_error("min_cov must be >= 1"); return FPM_ERR_ARG; }
-    // The accelerated path is the nucleotide alphabet (alphabetNucleotide, Sketch.h:25).
-    for (int c = 0; c < 256; c++) {
-        bool want = c == 'A' || c == 'C' || c == 'G' || c == 'T';
-        if ((p->alphabet[c] != 0) != want) {
-            set_error("only the nucleotide alphabet ACGT is accelerated (alphabet differs at byte %d)", c);
-            return FPM_ERR_UNSUPPORTED;
-        }
+    // ACGT (alphabetNucleotide, Sketch.h:25) takes the 2-bit kernel; any other alphabet the generic
+    // byte kernel, which -- like the reference with -a / -z -- is noncanonical only.
+    int asize = 0;
+    for (int c = 0; c < 256; c++) asize += p->alphabet[c] != 0;
+    if (asize == 0 || p->alphabet[0]) { set_error("alphabet is empty or contains NUL"); return FPM_ERR_ARG; }
+    if (!is_nucleotide(p) && !p->noncanonical) {
+        set_error("canonical k-mers are only defined for the nucleotide alphabet ACGT; custom alphabets imply -n");
+        return FPM_ERR_UNSUPPORTED;
     }
-    bool use64 = p->kmer_size > 16;   // 4^k > 2^32  (Sketch.cpp:1288)
-    if ((p->use64 != 0) != use64) { set_error("use64=%d inconsistent with k=%d for a 4-letter alphabet", p->use64, p->kmer_size); return FPM_ERR_ARG; }
+    bool use64 = pow((double)asize, (double)p->kmer_size) > pow(2.0, 32.0);   // Sketch.cpp:1288
+    if ((p->use64 != 0) != use64) { set_error("use64=%d inconsistent with k=%d for a %d-letter alphabet", p->use64, p->kmer_size, asize); return FPM_ERR_ARG; }
     uint64_t s = p->sketch_size;
     uint64_t target = s <= 4096 ? 2 * s + 64 : s + s / 4 + 256;
     if (target > SK_SORT_CAP) { set_error("sketch size %u exceeds the shared-memory selection limit (12900)", p->sketch_size); return FPM_ERR_UNSUPPORTED; }
@@ -103,6 +112,11 @@ int sketch_batch_dev_impl(fpm_ctx* ctx, const fpm_sketch_params* p, const uint8_
     const int K = p->kmer_size;
     const uint32_t s = p->sketch_size;
     const bool canon = !p->noncanonical;
+    const bool nucleotide = is_nucleotide(p);
+    if (!nucleotide) {
+        if ((rc = ctx->alpha.ensure(256))) return rc;
+        FPM_CUDA(cudaMemcpyAsync(ctx->alpha.p, p->alphabet, 256, cudaMemcpyHostToDevice, ctx->stream));
+    }
     const uint64_t full = p->use64 ? kAll64 : 0xffffffffULL;
     const uint64_t target = s <= 4096 ? 2ull * s + 64 : (uint64_t)s + s / 4 + 256;
     const bool want_counts = p->want_counts && d_out_counts;
@@ -195,7 +209,8 @@ int sketch_batch_dev_impl(fpm_ctx* ctx, const fpm_sketch_params* p, const uint8_
         FPM_CUDA(cudaMemcpyAsync(ctx->args.p, &a, sizeof a, cudaMemcpyHostToDevice, st));
         for (const auto& r : ranges) {
             ctx->time_begin(FPM_KERNEL_SKETCH_HASH);
-            g_hash_launch[K - 1](canon, st, ctx->args.as<SketchArgs>(), r.first, r.second, 0);
+            if (nucleotide) g_hash_launch[K - 1](canon, st, ctx->args.as<SketchArgs>(), r.first, r.second, 0);
+            else launch_sketch_generic(st, ctx->args.as<SketchArgs>(), ctx->alpha.as<uint8_t>(), K, r.first, r.second, 0, nullptr);
             ctx->time_end();
             ctx->launches++;
             FPM_CUDA(cudaGetLastError());
@@ -289,7 +304,8 @@ int sketch_batch_dev_impl(fpm_ctx* ctx, const fpm_sketch_params* p, const uint8_
             FPM_CUDA(cudaMemcpyAsync(ctx->args.p, &a, sizeof a, cudaMemcpyHostToDevice, st));
             for (const auto& r : ranges) {
                 ctx->time_begin(FPM_KERNEL_SKETCH_HASH);
-                g_hash_launch[K - 1](canon, st, ctx->args.as<SketchArgs>(), r.first, r.second, 1);
+                if (nucleotide) g_hash_launch[K - 1](canon, st, ctx->args.as<SketchArgs>(), r.first, r.second, 1);
+                else launch_sketch_generic(st, ctx->args.as<SketchArgs>(), ctx->alpha.as<uint8_t>(), K, r.first, r.second, 1, nullptr);
                 ctx->time_end();
                 ctx->launches++;
                 FPM_CUDA(cudaGetLastError());
@@ -307,7 +323,8 @@ int sketch_batch_dev_impl(fpm_ctx* ctx, const fpm_sketch_params* p, const uint8_
         a.seq = d_seq; a.n_bytes = n_bytes; a.group_off = ctx->goff.as<uint64_t>(); a.n_groups = n_groups;
         a.fold_case = !p->preserve_case;
         FPM_CUDA(cudaMemcpyAsync(ctx->args.p, &a, sizeof a, cudaMemcpyHostToDevice, st));
-        g_count_launch[K - 1](n_tiles, st, ctx->args.as<SketchArgs>(), (unsigned long long*)d_out_kmers);
+        if (nucleotide) g_count_launch[K - 1](n_tiles, st, ctx->args.as<SketchArgs>(), (unsigned long long*)d_out_kmers);
+        else launch_sketch_generic(st, ctx->args.as<SketchArgs>(), ctx->alpha.as<uint8_t>(), K, 0, n_bytes, 2, (unsigned long long*)d_out_kmers);
         ctx->launches++;
         FPM_CUDA(cudaGetLastError());
     }
@@ -406,6 +423,7 @@ int fpm_kmer_hashes(fpm_ctx* ctx, const fpm_sketch_params* p, const uint8_t* seq
     int rc = check_params(p);
     if (rc) return rc;
     if (out_count) *out_count = 0;
+    if (!is_nucleotide(p)) { set_error("fpm_kmer_hashes covers the nucleotide kernel only"); return FPM_ERR_UNSUPPORTED; }
     if (seq_bytes == 0) return FPM_OK;
     FPM_CUDA(cudaSetDevice(ctx->device));
     if ((rc = ctx->seq.ensure(seq_bytes + 64))) return rc;

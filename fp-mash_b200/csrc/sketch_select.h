@@ -30,6 +30,9 @@ void launch_sketch_select(uint32_t n_groups, size_t smem_bytes, cudaStream_t st,
 int configure_sketch_select(size_t max_smem_bytes);
 void launch_sketch_topcount(uint32_t n_list, cudaStream_t st, const uint32_t* d_groups, uint32_t sketch_size, uint32_t min_cov,
                             const uint64_t* tr_off, const uint32_t* tr_cap, const uint64_t* tr_pos, uint32_t* out_counts);
+struct SketchArgs;
+void launch_sketch_generic(cudaStream_t st, const SketchArgs* d_args, const uint8_t* d_alphabet, int K, uint64_t range_lo,
+                           uint64_t range_hi, int mode, unsigned long long* out_kmers);
 void launch_fp_hash(uint64_t n_lines, cudaStream_t st, const uint64_t* tokens, const uint64_t* line_off, uint32_t seed, int use64, uint64_t* out);
 
 }  // namespace fpm

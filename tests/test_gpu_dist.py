@@ -95,3 +95,30 @@ def test_dist_empty_sketches(ctx, oracle):
     ln = np.array([100, 200, 300], dtype=np.uint64)
     got, passed = ctx.dist_tile((h, sz, ln), (h, sz, ln), 10, 21, 4.0 ** 21)
     _compare(got, passed, _oracle_matrix(oracle, (h, sz, ln), (h, sz, ln), 10, 21, 4.0 ** 21))
+
+
+def test_dist_large_sketches_many_phases(ctx, oracle):
+    """s = 10000 (config 5's shape): every pair needs dozens of value-bounded phases."""
+    rng = np.random.default_rng(10)
+    s = 10000
+    rh, rs = sorted_sketch_panel(rng, 20, s, n_clusters=3, shared=0.7)
+    qh, qs = sorted_sketch_panel(rng, 9, s, n_clusters=3, shared=0.7)
+    qh[0] = rh[0]; qs[0] = rs[0]
+    rl = np.full(20, 5_000_000, dtype=np.uint64); ql = np.full(9, 4_000_000, dtype=np.uint64)
+    got, passed = ctx.dist_tile((rh, rs, rl), (qh, qs, ql), s, 32, 4.0 ** 32)
+    _compare(got, passed, _oracle_matrix(oracle, (rh, rs, rl), (qh, qs, ql), s, 32, 4.0 ** 32))
+
+
+def test_dist_full_size_properties(ctx):
+    """4000 x 4000 all-vs-all at s=1000: symmetry, identity diagonal, bounds -- properties that need no oracle."""
+    rng = np.random.default_rng(11)
+    n, s = 4000, 1000
+    h, sz = sorted_sketch_panel(rng, n, s, n_clusters=20, shared=0.6, ragged=False)
+    ln = np.full(n, 5_000_000, dtype=np.uint64)
+    got, passed = ctx.dist_tile((h, sz, ln), (h, sz, ln), s, 21, 4.0 ** 21)
+    assert np.array_equal(got["numer"], got["numer"].T) and np.array_equal(got["denom"], got["denom"].T)
+    assert np.array_equal(got["distance"], got["distance"].T) and np.array_equal(got["pvalue"], got["pvalue"].T)
+    assert (np.diag(got["numer"]) == s).all() and (np.diag(got["distance"]) == 0).all() and (got["denom"] == s).all()
+    assert (got["numer"] <= got["denom"]).all() and passed.all()
+    same = (np.arange(n)[:, None] % 20) == (np.arange(n)[None, :] % 20)
+    assert got["numer"][same].min() > 100 and got["numer"][~same].max() < 10

@@ -106,3 +106,42 @@ def test_fp_hash_batch(ctx, oracle):
         got = ctx.fp_hash_batch(lines, seed=42, use64=use64)
         want = np.array([oracle.fp_hash(t, 42, use64) for t in lines], dtype=np.uint64)
         assert np.array_equal(got, want)
+
+
+PROTEIN = "ACDEFGHIKLMNPQRSTVWY"
+
+
+@pytest.mark.parametrize("alphabet,k,s", [(PROTEIN, 9, 1000), (PROTEIN, 5, 400), ("ACGTN", 21, 500), ("01", 32, 300), ("acgu", 16, 200)])
+def test_sketch_custom_alphabets(ctx, oracle, fpm, alphabet, k, s):
+    """-a / -z: noncanonical, every window whose k bytes are all in the alphabet (case folded)."""
+    rng = np.random.default_rng(len(alphabet) * 100 + k)
+    letters = np.frombuffer((alphabet.upper() + alphabet.lower() + "XZ*-").encode(), dtype=np.uint8)
+    p = np.r_[np.full(2 * len(alphabet), 0.97 / (2 * len(alphabet))), np.full(4, 0.03 / 4)]
+    groups = [[letters[rng.choice(len(letters), size=n, p=p)].tobytes() for n in sizes] for sizes in ([60000], [3000, 7, 12000], [k], [k - 1])]
+    table = fpm.nucleotide_alphabet(alphabet)
+    got = ctx.sketch_records(groups, k=k, s=s, alphabet=alphabet, noncanonical=True, want_counts=True, want_kmers=True)
+    for g, recs in enumerate(groups):
+        want = oracle.sketch(recs, k=k, s=s, alphabet=table, noncanonical=True, trace=True)
+        assert np.array_equal(got[g]["hashes"], want["hashes"]) and np.array_equal(got[g]["counts"], want["counts"]), g
+        assert got[g]["kmers"] == len(want["trace"])
+    # reads-style multiplicity filter on the generic path
+    recs = groups[0] * 2 + groups[1]
+    got = ctx.sketch_records([recs], k=k, s=50, alphabet=alphabet, noncanonical=True, min_cov=2, want_counts=True)[0]
+    want = oracle.sketch(recs, k=k, s=50, alphabet=table, noncanonical=True, min_cov=2)
+    assert np.array_equal(got["hashes"], want["hashes"]) and np.array_equal(got["counts"], want["counts"])
+
+
+def test_custom_alphabet_requires_noncanonical(ctx, fpm):
+    with pytest.raises(fpm.FpmError) as e:
+        ctx.sketch_records([[b"ACDEFGHIK" * 10]], k=9, s=10, alphabet=PROTEIN)
+    assert e.value.code == fpm.FPM_ERR_UNSUPPORTED
+
+
+def test_full_size_genome_and_large_sketch(ctx, oracle):
+    """One 5 Mbp genome at the headline parameters, and k=32 s=10000 (config 5's sketch shape)."""
+    rng = np.random.default_rng(2026)
+    g = random_dna(rng, 5_000_000)
+    for k, s in ((21, 1000), (32, 10000)):
+        got = ctx.sketch_records([[g]], k=k, s=s, want_counts=True)[0]
+        want = oracle.sketch([g], k=k, s=s)
+        assert np.array_equal(got["hashes"], want["hashes"]) and np.array_equal(got["counts"], want["counts"])
