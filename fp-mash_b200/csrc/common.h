@@ -40,7 +40,7 @@ struct fpm_ctx {
     double int_peak[3] = {0, 0, 0};              // last fpm_measure_int32_peak: ALU-only, IMAD-only, alternating
     // sketch scratch
     fpm::DevBuf seq, goff, thresh, active, toff, tmask, tkeys, tcnt, tpos, maxcnt, maxpos, overflow,
-        stat, tiles, args, alpha, outh, outc, outn, outk, firstpos, tr_off, tr_cursor, tr_pos, glist;
+        stat, tiles, args, alpha, scratch, outh, outc, outn, outk, firstpos, tr_off, tr_cursor, tr_pos, glist;
     // dist scratch
     fpm::DevBuf d_ref, d_qry, d_rs, d_qs, d_rl, d_ql, d_out, d_misc;
     // optional per-kernel event timing (bench roofline): pairs of events around each launch

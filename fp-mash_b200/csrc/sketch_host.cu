@@ -55,9 +55,7 @@ static int check_params(const fpm_sketch_params* p)
     }
     bool use64 = pow((double)asize, (double)p->kmer_size) > pow(2.0, 32.0);   // Sketch.cpp:1288
     if ((p->use64 != 0) != use64) { set_error("use64=%d inconsistent with k=%d for a %d-letter alphabet", p->use64, p->kmer_size, asize); return FPM_ERR_ARG; }
-    uint64_t s = p->sketch_size;
-    uint64_t target = s <= 4096 ? 2 * s + 64 : s + s / 4 + 256;
-    if (target > SK_SORT_CAP) { set_error("sketch size %u exceeds the shared-memory selection limit (12900)", p->sketch_size); return FPM_ERR_UNSUPPORTED; }
+    if (p->sketch_size > (1u << 24)) { set_error("sketch size %u too large (the reference stores it in a float: exact only up to 2^24)", p->sketch_size); return FPM_ERR_ARG; }
     return FPM_OK;
 }
 
@@ -127,7 +125,7 @@ int sketch_batch_dev_impl(fpm_ctx* ctx, const fpm_sketch_params* p, const uint8_
     for (uint32_t g = 0; g < n_groups; g++) {
         uint64_t n = h_goff[g + 1] - h_goff[g];
         GroupPlan& pl = plan[g];
-        if (n <= 2 * target && n <= SK_SORT_CAP) {
+        if (n <= 2 * target) {
             pl.all = true; pl.thresh = full; pl.cap = pow2ceil(2 * n);
         } else {
             pl.all = false;
@@ -221,6 +219,11 @@ int sketch_batch_dev_impl(fpm_ctx* ctx, const fpm_sketch_params* p, const uint8_
         sa.maxkey_cnt = a.maxkey_cnt; sa.maxkey_pos = a.maxkey_pos; sa.active = a.active;
         sa.sketch_size = s; sa.min_cov = p->min_cov;
         sa.sort_cap = std::min<uint32_t>(SK_SORT_CAP, max_cap);
+        sa.scratch = nullptr;
+        if (max_cap > SK_SORT_CAP) {   // large sketches: sort qualifying keys in global memory
+            if ((rc = ctx->scratch.ensure(slots * 8))) return rc;
+            sa.scratch = ctx->scratch.as<uint64_t>();
+        }
         sa.out_hashes = d_out_hashes; sa.out_counts = want_counts ? d_out_counts : nullptr;
         sa.out_firstpos = nullptr;
         sa.out_n = d_out_n; sa.stat_nq = d_stat_nq; sa.stat_nd = d_stat_nd; sa.stat_topcnt = d_stat_top;
@@ -241,7 +244,7 @@ int sketch_batch_dev_impl(fpm_ctx* ctx, const fpm_sketch_params* p, const uint8_
             uint32_t nq = h_stat[g], nd = h_stat[n_groups + g];
             GroupPlan& pl = plan[g];
             uint64_t n = h_goff[g + 1] - h_goff[g];
-            bool too_many = h_over[g] || nq > sa.sort_cap;
+            bool too_many = h_over[g] != 0;
             bool too_few = !pl.all && nq < s;
             if (!too_many && !too_few) {
                 active[g] = 0;
@@ -252,7 +255,7 @@ int sketch_batch_dev_impl(fpm_ctx* ctx, const fpm_sketch_params* p, const uint8_
             again = true;
             double cur = pl.all ? 1.0 : ((double)pl.thresh + 1.0) / ((double)full + 1.0);
             double next;
-            if (too_many) next = (nq > sa.sort_cap && nq > 0) ? cur * (double)target / (double)nq : cur / 4;
+            if (too_many) next = cur / 4;
             else next = nq >= 16 ? cur * 1.15 * (double)target / (double)nq : cur * 16;
             if (next >= 1.0) { pl.all = true; pl.thresh = full; next = 1.0; }
             else { pl.all = false; pl.thresh = scale_threshold(full, next); }

@@ -16,33 +16,36 @@ __global__ void __launch_bounds__(256) sketch_select_kernel(const SelectArgs a)
     if (!a.active[g]) return;
     const uint64_t base = a.toff[g];
     const uint32_t mask = a.tmask[g];
+    // pass 1: how many distinct hashes, how many qualify (count >= min_cov)
     if (threadIdx.x == 0) { s_nq = 0; s_nd = 0; }
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i <= mask; i += blockDim.x) {
-        uint64_t key = a.tkeys[base + i];
-        if (key != SK_EMPTY) {
-            atomicAdd(&s_nd, 1u);
-            if (a.tcnt[base + i] >= a.min_cov) {
-                uint32_t idx = atomicAdd(&s_nq, 1u);
-                if (idx < a.sort_cap) s_keys[idx] = key;
-            }
+    {
+        uint32_t nd = 0, nq1 = 0;
+        for (uint32_t i = threadIdx.x; i <= mask; i += blockDim.x) {
+            if (a.tkeys[base + i] != SK_EMPTY) { nd++; nq1 += a.tcnt[base + i] >= a.min_cov; }
         }
-    }
-    if (threadIdx.x == 0 && a.maxkey_cnt[g]) {
-        atomicAdd(&s_nd, 1u);
-        if (a.maxkey_cnt[g] >= a.min_cov) {
-            uint32_t idx = atomicAdd(&s_nq, 1u);
-            if (idx < a.sort_cap) s_keys[idx] = SK_EMPTY;
-        }
+        if (threadIdx.x == 0 && a.maxkey_cnt[g]) { nd++; nq1 += a.maxkey_cnt[g] >= a.min_cov; }
+        if (nd) atomicAdd(&s_nd, nd);
+        if (nq1) atomicAdd(&s_nq, nq1);
     }
     __syncthreads();
     const uint32_t nq = s_nq;
     if (threadIdx.x == 0) { a.stat_nq[g] = nq; a.stat_nd[g] = s_nd; a.stat_topcnt[g] = 0; }
     __syncthreads();
-    if (nq > a.sort_cap) { if (threadIdx.x == 0) a.out_n[g] = 0; return; }
+    // keys are sorted in shared memory when they fit, else in this sketch's slice of the global scratch
+    // (same capacity as its table, so P = pow2ceil(nq) always fits)
+    uint64_t* keys = nq <= a.sort_cap ? s_keys : (a.scratch ? a.scratch + base : nullptr);
+    if (!keys) { if (threadIdx.x == 0) a.out_n[g] = 0; return; }
+    if (threadIdx.x == 0) s_nq = 0;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i <= mask; i += blockDim.x) {
+        uint64_t key = a.tkeys[base + i];
+        if (key != SK_EMPTY && a.tcnt[base + i] >= a.min_cov) keys[atomicAdd(&s_nq, 1u)] = key;
+    }
+    if (threadIdx.x == 0 && a.maxkey_cnt[g] >= a.min_cov && a.maxkey_cnt[g]) keys[atomicAdd(&s_nq, 1u)] = SK_EMPTY;
     uint32_t P = 1;
     while (P < nq) P <<= 1;
-    for (uint32_t i = nq + threadIdx.x; i < P; i += blockDim.x) s_keys[i] = SK_EMPTY;
+    for (uint32_t i = nq + threadIdx.x; i < P; i += blockDim.x) keys[i] = SK_EMPTY;
     __syncthreads();
     // bitonic sort, ascending
     for (uint32_t k = 2; k <= P; k <<= 1) {
@@ -50,9 +53,9 @@ __global__ void __launch_bounds__(256) sketch_select_kernel(const SelectArgs a)
             for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) {
                 uint32_t ixj = i ^ j;
                 if (ixj > i) {
-                    uint64_t x = s_keys[i], y = s_keys[ixj];
+                    uint64_t x = keys[i], y = keys[ixj];
                     bool up = (i & k) == 0;
-                    if ((x > y) == up) { s_keys[i] = y; s_keys[ixj] = x; }
+                    if ((x > y) == up) { keys[i] = y; keys[ixj] = x; }
                 }
             }
             __syncthreads();
@@ -61,7 +64,7 @@ __global__ void __launch_bounds__(256) sketch_select_kernel(const SelectArgs a)
     const uint32_t n_out = nq < a.sketch_size ? nq : a.sketch_size;
     if (threadIdx.x == 0) a.out_n[g] = n_out;
     for (uint32_t i = threadIdx.x; i < n_out; i += blockDim.x) {
-        uint64_t key = s_keys[i];
+        uint64_t key = keys[i];
         uint64_t o = (uint64_t)g * a.sketch_size + i;
         a.out_hashes[o] = key;
         {

@@ -17,6 +17,7 @@ struct SelectArgs {
     uint32_t sketch_size;
     uint32_t min_cov;
     uint32_t sort_cap;       // u64 keys that fit the dynamic shared memory of this launch
+    uint64_t* scratch;       // table-shaped global scratch for sketches with more qualifying keys (nullable)
     uint64_t* out_hashes;    // [n_groups][s]
     uint32_t* out_counts;    // [n_groups][s] (nullable)
     uint64_t* out_firstpos;  // [n_groups][s] (nullable)

@@ -145,3 +145,14 @@ def test_full_size_genome_and_large_sketch(ctx, oracle):
         got = ctx.sketch_records([[g]], k=k, s=s, want_counts=True)[0]
         want = oracle.sketch([g], k=k, s=s)
         assert np.array_equal(got["hashes"], want["hashes"]) and np.array_equal(got["counts"], want["counts"])
+
+
+@pytest.mark.parametrize("s,n", [(20000, 400000), (50000, 90000), (30000, 2000000)])
+def test_sketch_sizes_beyond_shared_memory(ctx, oracle, s, n):
+    """-s above ~12900: qualifying hashes no longer fit the shared-memory sort; the global-memory path takes over."""
+    rng = np.random.default_rng(s)
+    g = dirty_dna(rng, n, n_rate=0.001)
+    got = ctx.sketch_records([[g], [g[: n // 3]]], k=21, s=s, want_counts=True)
+    for rec, out in zip(([g], [g[: n // 3]]), got):
+        want = oracle.sketch(rec, k=21, s=s)
+        assert np.array_equal(out["hashes"], want["hashes"]) and np.array_equal(out["counts"], want["counts"])
