@@ -96,6 +96,27 @@ __global__ void __launch_bounds__(256) dist_literal_kernel(fpm_panel ref, fpm_pa
     }
 }
 
+// The fork's positional fingerprint comparison (CommandTriangle.cpp:265-302, `mash triangle -fp`):
+// matches = #{i < min(|A|,|B|) : A[i] == B[i]}, distance = 1 - matches/min, p = chi-square upper tail
+// with one degree of freedom at `matches` (gsl_cdf_chisq_Q(matches, 1) = erfc(sqrt(matches/2))).
+__global__ void __launch_bounds__(256) fp_positional_kernel(fpm_panel ref, fpm_panel qry, double max_distance, double max_pvalue, fpm_pair* out)
+{
+    uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= ref.n * qry.n) return;
+    uint64_t q = p / ref.n, r = p % ref.n;
+    const uint64_t* A = ref.hashes + r * ref.stride;
+    const uint64_t* B = qry.hashes + q * qry.stride;
+    uint32_t na = ref.sizes[r], nb = qry.sizes[q], m = na < nb ? na : nb, matches = 0;
+    for (uint32_t i = 0; i < m; i++) matches += A[i] == B[i];
+    fpm_pair o;
+    o.numer = matches;
+    o.denom = m;
+    o.distance = 1.0 - (double(matches) / double(m));
+    o.pvalue = erfc(sqrt(double(matches) * 0.5));
+    if (o.distance <= max_distance && o.pvalue <= max_pvalue) o.denom |= FPM_PAIR_PASS;
+    out[p] = o;
+}
+
 // Row-major [n][stride] -> column tiles [ceil(n/16)][rows][16], +inf beyond each sketch's size.
 // flags[0] |= 1 if a real hash collides with the sentinel's high word or a row is not strictly ascending (the
 // host then falls back to the literal kernel).
@@ -336,7 +357,7 @@ int fpm_dist_tile_dev(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* d
     return run_dist(ctx, p, d_ref, d_qry, d_out, d_merge_steps, mr, mq);
 }
 
-int fpm_dist_tile(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* ref, const fpm_panel* qry, fpm_pair* out)
+static int dist_tile_host(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* ref, const fpm_panel* qry, fpm_pair* out, bool positional)
 {
     if (!ctx) { set_error("ctx is NULL"); return FPM_ERR_ARG; }
     int rc = check_dist(p, ref, qry);
@@ -364,10 +385,25 @@ int fpm_dist_tile(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* ref, 
     if (qh) FPM_CUDA(cudaMemcpyAsync((void*)dq.hashes, qry->hashes, qh, cudaMemcpyHostToDevice, st));
     FPM_CUDA(cudaMemcpyAsync((void*)dq.lengths, qry->lengths, qry->n * 8, cudaMemcpyHostToDevice, st));
     FPM_CUDA(cudaMemcpyAsync((void*)dq.sizes, qry->sizes, qry->n * 4, cudaMemcpyHostToDevice, st));
-    if ((rc = run_dist(ctx, p, &dr, &dq, ctx->d_out.as<fpm_pair>(), nullptr, mr, mq))) return rc;
+    if (positional) {
+        uint64_t total = ref->n * qry->n;
+        fp_positional_kernel<<<(uint32_t)((total + 255) / 256), 256, 0, st>>>(dr, dq, p->max_distance, p->max_pvalue, ctx->d_out.as<fpm_pair>());
+        ctx->launches++;
+        FPM_CUDA(cudaGetLastError());
+    } else if ((rc = run_dist(ctx, p, &dr, &dq, ctx->d_out.as<fpm_pair>(), nullptr, mr, mq))) return rc;
     FPM_CUDA(cudaMemcpyAsync(out, ctx->d_out.p, ref->n * qry->n * sizeof(fpm_pair), cudaMemcpyDeviceToHost, st));
     FPM_CUDA(cudaStreamSynchronize(st));
     return FPM_OK;
+}
+
+int fpm_dist_tile(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* ref, const fpm_panel* qry, fpm_pair* out)
+{
+    return dist_tile_host(ctx, p, ref, qry, out, false);
+}
+
+int fpm_fp_positional_tile(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* ref, const fpm_panel* qry, fpm_pair* out)
+{
+    return dist_tile_host(ctx, p, ref, qry, out, true);
 }
 
 double fpm_pvalue(uint64_t x, uint64_t len_ref, uint64_t len_qry, double kmer_space, uint64_t n)

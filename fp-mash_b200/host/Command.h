@@ -48,5 +48,6 @@ class CommandSketch : public Command { public: CommandSketch(); int run() const;
 class CommandDistance : public Command { public: CommandDistance(); int run() const; };
 class CommandPaste : public Command { public: CommandPaste(); int run() const; };
 class CommandInfo : public Command { public: CommandInfo(); int run() const; };
+class CommandTriangle : public Command { public: CommandTriangle(); int run() const; };
 
 }  // namespace mash

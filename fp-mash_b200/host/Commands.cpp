@@ -645,4 +645,126 @@ int CommandInfo::run() const
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// mash triangle (CommandTriangle.cpp:38-263): lower-triangular all-vs-all over one sketch set with
+// the same comparison kernel as `dist`; `-fp` uses the fork's positional compareFingerprints.
+// ------------------------------------------------------------------------------------------
+CommandTriangle::CommandTriangle() : Command()
+{
+    name = "triangle";
+    summary = "Estimate a lower-triangular distance matrix.";
+    description = "Estimate the distance of each input sequence or fingerprint to every other input. Outputs a lower-triangular distance matrix in relaxed Phylip format. The input sequences can be fasta or fastq, gzipped or not, or Mash sketch files (.msh) with matching k-mer sizes. Input files can also be files of file names (see -l). If more than one input file is provided, whole files are compared by default (see -i).";
+    argumentString = "<seq1> [<seq2>] ...";
+    useOption("help");
+    addOption("list", Option(Option::Boolean, "l", "Input", "List input. Lines in each <query> specify paths to sequence files, one per line. The reference file is not affected.", ""));
+    addOption("comment", Option(Option::Boolean, "C", "Output", "Use comment fields for sequence names instead of IDs.", ""));
+    addOption("edge", Option(Option::Boolean, "E", "Output", "Output edge list instead of Phylip matrix, with fields [seq1, seq2, dist, p-val, shared-hashes].", ""));
+    addOption("pvalue", Option(Option::Number, "v", "Output", "Maximum p-value to report in edge list. Implies -E.", "1.0", 0., 1.));
+    addOption("distance", Option(Option::Number, "d", "Output", "Maximum distance to report in edge list. Implies -E.", "1.0", 0., 1.));
+    addOption("fingerprint", Option(Option::Boolean, "fp", "Input", "Indicates that the input files are fingerprints instead of sequences.", ""));
+    useSketchOptions();
+}
+
+int CommandTriangle::run() const
+{
+    if (arguments.size() < 1 || options.at("help").active) {
+        print();
+        return 0;
+    }
+    bool list = options.at("list").active;
+    bool comment = options.at("comment").active;
+    bool edge = options.at("edge").active;
+    bool fingerprint = options.at("fingerprint").active;
+    double pValueMax = options.at("pvalue").getArgumentAsNumber();
+    double distanceMax = options.at("distance").getArgumentAsNumber();
+    double pValuePeak = 0;
+    if (options.at("pvalue").active || options.at("distance").active) edge = true;
+
+    Sketch::Parameters parameters;
+    if (sketchParameterSetup(parameters, *this)) return 1;
+    if (arguments.size() == 1 && !list) parameters.concatenated = false;
+
+    vector<string> queryFiles;
+    for (size_t i = 0; i < arguments.size(); i++) {
+        if (list) splitFile(arguments[i], queryFiles);
+        else queryFiles.push_back(arguments[i]);
+    }
+    Sketch sketch;
+    if (fingerprint && containsTag(queryFiles, ".msh")) sketch.initFromFiles(queryFiles, parameters);
+    else if (fingerprint) sketch.initFromFingerprints(queryFiles, parameters);
+    else sketch.initFromFiles(queryFiles, parameters);
+
+    uint64_t lengthMax = 0;
+    double randomChance = 0;
+    int kMin = 0;
+    string lengthMaxName;
+    int warningCount = 0;
+    double lengthThreshold = (parameters.warning * sketch.getKmerSpace()) / (1. - parameters.warning);
+    for (uint64_t i = 0; i < sketch.getReferenceCount(); i++) {
+        uint64_t length = sketch.getReference(i).length;
+        if (length > lengthThreshold) {
+            if (warningCount == 0 || length > lengthMax) {
+                lengthMax = length;
+                lengthMaxName = sketch.getReference(i).name;
+                randomChance = sketch.getRandomKmerChance(i);
+                kMin = sketch.getMinKmerSize(i);
+            }
+            warningCount++;
+        }
+    }
+    const uint64_t n = sketch.getReferenceCount();
+    if (n == 0) return 0;
+    if (!edge) {
+        cout << '\t' << n << endl;
+        cout << (comment ? sketch.getReference(0).comment : sketch.getReference(0).name) << endl;
+    }
+    HostPanel panel;
+    buildPanel(sketch, panel);
+    fpm_dist_params dp;
+    dp.sketch_size = (uint32_t)sketch.getMinHashesPerWindow();
+    dp.kmer_size = sketch.getKmerSize();
+    dp.kmer_space = sketch.getKmerSpace();
+    dp.max_distance = distanceMax;
+    dp.max_pvalue = pValueMax;
+    dp.sorted_unique = 1;
+    // row blocks [i0, i1) against columns [0, i1-1): only the lower triangle (plus block padding) is computed
+    vector<fpm_pair> out;
+    for (uint64_t i0 = 1; i0 < n;) {
+        uint64_t i1 = i0 + 1;
+        while (i1 < n && (i1 - i0 + 1) * i1 <= (32ull << 20)) i1++;
+        const uint64_t nq = i1 - i0, nr = i1 - 1;
+        out.resize(nq * nr);
+        fpm_panel vr = panel.view(0, nr), vq = panel.view(i0, nq);
+        int rc = fingerprint ? fpm_fp_positional_tile(gpuContext(), &dp, &vr, &vq, out.data())
+                             : fpm_dist_tile(gpuContext(), &dp, &vr, &vq, out.data());
+        if (rc != FPM_OK) {
+            cerr << "ERROR: " << fpm_last_error() << endl;
+            return 1;
+        }
+        for (uint64_t i = i0; i < i1; i++) {                        // writeOutput, CommandTriangle.cpp:202-236
+            const Sketch::Reference& ref = sketch.getReference(i);
+            if (!edge) cout << (comment ? ref.comment : ref.name);
+            for (uint64_t j = 0; j < i; j++) {
+                const fpm_pair& pair = out[(i - i0) * nr + j];
+                if (edge) {
+                    if (pair.denom & FPM_PAIR_PASS) {
+                        const Sketch::Reference& qry = sketch.getReference(j);
+                        cout << (comment ? ref.comment : ref.name) << '\t' << (comment ? qry.comment : qry.name) << '\t' << pair.distance
+                             << '\t' << pair.pvalue << '\t' << pair.numer << '/' << FPM_PAIR_DENOM(pair) << '\n';
+                    }
+                } else {
+                    cout << '\t' << pair.distance;
+                }
+                if (pair.pvalue > pValuePeak) pValuePeak = pair.pvalue;
+            }
+            if (!edge) cout << '\n';
+        }
+        i0 = i1;
+    }
+    cout.flush();
+    if (!edge) cerr << "Max p-value: " << pValuePeak << endl;
+    if (warningCount > 0 && !parameters.reads) warnKmerSize(parameters, *this, lengthMax, lengthMaxName, randomChance, kMin, warningCount);
+    return 0;
+}
+
 }  // namespace mash

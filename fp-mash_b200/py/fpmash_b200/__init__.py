@@ -86,6 +86,7 @@ lib.fpm_sketch_batch_dev.argtypes = [_VP, C.POINTER(SketchParams), _VP, C.c_uint
 lib.fpm_kmer_hashes.argtypes = [_VP, C.POINTER(SketchParams), _VP, C.c_uint64, _VP, u64p]
 lib.fpm_fp_hash_batch.argtypes = [_VP, _VP, _VP, C.c_uint64, C.c_uint32, C.c_int, _VP]
 lib.fpm_dist_tile.argtypes = [_VP, C.POINTER(DistParams), C.POINTER(Panel), C.POINTER(Panel), _VP]
+lib.fpm_fp_positional_tile.argtypes = [_VP, C.POINTER(DistParams), C.POINTER(Panel), C.POINTER(Panel), _VP]
 lib.fpm_dist_tile_dev.argtypes = [_VP, C.POINTER(DistParams), C.POINTER(Panel), C.POINTER(Panel), _VP, _VP]
 lib.fpm_pvalue.restype = C.c_double
 lib.fpm_pvalue.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_double, C.c_uint64]
@@ -101,7 +102,7 @@ KERNEL_SKETCH_HASH, KERNEL_SKETCH_SELECT, KERNEL_DIST_TILE, KERNEL_DIST_LITERAL,
 EXPORTED = ["fpm_abi_version", "fpm_device_count", "fpm_ctx_create", "fpm_ctx_destroy", "fpm_last_error",
             "fpm_ctx_sync", "fpm_ctx_stream", "fpm_ctx_set_stream", "fpm_host_alloc", "fpm_host_free",
             "fpm_ctx_launch_count", "fpm_sketch_batch", "fpm_sketch_batch_dev", "fpm_kmer_hashes",
-            "fpm_fp_hash_batch", "fpm_dist_tile", "fpm_dist_tile_dev", "fpm_pvalue", "fpm_distance",
+            "fpm_fp_hash_batch", "fpm_dist_tile", "fpm_dist_tile_dev", "fpm_fp_positional_tile", "fpm_pvalue", "fpm_distance",
             "fpm_measure_int32_peak", "fpm_get_int32_peaks", "fpm_ctx_set_timing", "fpm_ctx_get_timing"]
 
 
@@ -299,6 +300,17 @@ class Context:
             out = np.zeros((pq.n, pr.n), dtype=PAIR_DTYPE)
         assert out.dtype == PAIR_DTYPE and out.shape == (pq.n, pr.n) and out.flags["C_CONTIGUOUS"]
         _check(lib.fpm_dist_tile(self._h, C.byref(dp), C.byref(pr), C.byref(pq), out.ctypes.data))
+        passed = (out["denom"] & FPM_PAIR_PASS) != 0
+        out["denom"] &= 0x7fffffff
+        return out, passed
+
+    def fp_positional_tile(self, ref, qry, max_distance=1.0, max_pvalue=1.0):
+        """compareFingerprints (mash triangle -fp): positional matches, chi-square p-value."""
+        pr, keep_r = self._panel(*ref)
+        pq, keep_q = self._panel(*qry)
+        dp = DistParams(0, 1, 10.0, max_distance, max_pvalue, 0)
+        out = np.zeros((pq.n, pr.n), dtype=PAIR_DTYPE)
+        _check(lib.fpm_fp_positional_tile(self._h, C.byref(dp), C.byref(pr), C.byref(pq), out.ctypes.data))
         passed = (out["denom"] & FPM_PAIR_PASS) != 0
         out["denom"] &= 0x7fffffff
         return out, passed

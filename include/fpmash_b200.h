@@ -155,6 +155,11 @@ int fpm_dist_tile(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* ref, 
 int fpm_dist_tile_dev(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* d_ref, const fpm_panel* d_qry,
                       fpm_pair* d_out, uint64_t* d_merge_steps /* nullable: += loop iterations */);
 
+/* Replaces the fork's compareFingerprints (CommandTriangle.cpp:265-302, `mash triangle -fp`): positional
+ * matches over the first min(|ref|,|qry|) hashes, distance = 1 - matches/min, p = chi-square(1 dof) upper
+ * tail at `matches`.  Only max_distance / max_pvalue of *p are used.  Same output layout as fpm_dist_tile. */
+int fpm_fp_positional_tile(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* ref, const fpm_panel* qry, fpm_pair* out);
+
 /* Scalar helpers exported for host code and tests (same code the kernels run).             */
 double fpm_pvalue(uint64_t x, uint64_t len_ref, uint64_t len_qry, double kmer_space, uint64_t n);
 double fpm_distance(uint64_t common, uint64_t denom, int kmer_size);

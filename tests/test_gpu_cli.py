@@ -152,3 +152,50 @@ def test_sketch_individual_and_options(tmp_path, oracle):
     assert m.refs[0]["hashes64"] == [int(v) for v in w["hashes"]] and m.noncanonical
     assert m.refs[0]["length"] == sum(len(r) for _, r in [(i, r) for i, r in enumerate(recs) if len(r) >= 21])
     assert m.refs[0]["comment"] == "[3 seqs] rec0 some comment 0 [...]" and m.refs[0]["name"] == "multi.fa.gz"
+
+
+def test_triangle_matches_dist_and_positional_fp(tmp_path, oracle):
+    """mash triangle (CommandTriangle.cpp): Phylip lower triangle from the dist kernel; -fp uses the
+    fork's positional compareFingerprints with a chi-square(1) p-value."""
+    import math
+    files = [os.path.join(GOLDEN, "genome%d.fna.msh" % i) for i in (1, 2, 3)]
+    r = run(["triangle"] + files, cwd=tmp_path)
+    lines = r.stdout.splitlines()
+    assert lines[0] == "\t3" and lines[1] == "data/genome1.fna"
+    assert lines[2].split("\t") == ["data/genome2.fna", "0.0222766"]
+    assert lines[3].split("\t") == ["data/genome3.fna", "0", "0.0222766"]
+    assert "Max p-value: 0" in r.stderr
+    e = run(["triangle", "-E"] + files, cwd=tmp_path).stdout.splitlines()
+    assert e[0].split("\t") == ["data/genome2.fna", "data/genome1.fna", "0.0222766", "0", "456/1000"]
+    assert len(e) == 3 and e[2].split("\t")[4] == "456/1000"
+    # fingerprints: 5 references of 2000 unsorted 32-bit hashes each
+    gunzip_to("DNA1-CFL.txt.gz", tmp_path / "DNA1-CFL.txt")
+    t = run(["triangle", "-fp", "-E", "DNA1-CFL.txt"], cwd=tmp_path).stdout.splitlines()
+    rows = [l.split("\t") for l in t if l.count("\t") == 4]
+    refs = mshpy.load(os.path.join(GOLDEN, "DNA1-sketch.msh")).refs
+    want = []
+    for i in range(1, 5):
+        for j in range(i):
+            a, b = refs[i]["hashes32"], refs[j]["hashes32"]
+            m = min(len(a), len(b))
+            matches = sum(1 for x, y in zip(a[:m], b[:m]) if x == y)
+            p = math.erfc(math.sqrt(matches / 2.0))
+            if 1.0 - matches / m <= 1.0 and p <= 1.0:
+                want.append([refs[i]["name"], refs[j]["name"], "%g" % (1.0 - matches / m), "%g" % p, "%d/%d" % (matches, m)])
+    assert rows == want
+
+
+def test_sketch_protein_cli(tmp_path, oracle, fpm):
+    rng = np.random.default_rng(4)
+    aa = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWYXB", dtype=np.uint8)
+    seqs = [aa[rng.integers(0, len(aa), size=n)].tobytes() for n in (4000, 300)]
+    with open(tmp_path / "p.faa", "wb") as f:
+        for i, s in enumerate(seqs):
+            f.write(b">p%d\n" % i + s + b"\n")
+    run(["sketch", "-a", "-i", "-s", "300", "p.faa"], cwd=tmp_path)
+    m = mshpy.load(tmp_path / "p.faa.msh")
+    assert (m.kmer_size, m.alphabet, m.noncanonical) == (9, "ACDEFGHIKLMNPQRSTVWY", True)
+    table = fpm.nucleotide_alphabet("ACDEFGHIKLMNPQRSTVWY")
+    for x, s in zip(m.refs, seqs):
+        w = oracle.sketch([s], k=9, s=300, alphabet=table, noncanonical=True)
+        assert x["hashes64"] == [int(v) for v in w["hashes"]]
