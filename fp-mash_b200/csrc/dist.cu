@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(256) dist_pack_kernel(fpm_panel pn, uint64_t r
 __global__ void __launch_bounds__(DT_THREADS, 2)
 dist_tile_kernel(const uint64_t* __restrict__ pref, const uint64_t* __restrict__ pqry, uint64_t rows_ref, uint64_t rows_qry,
                  uint64_t n_ref, uint64_t n_qry, const uint64_t* __restrict__ len_ref, const uint64_t* __restrict__ len_qry,
-                 DistArgs a, fpm_pair* __restrict__ out, unsigned long long* steps)
+                 DistArgs a, fpm_pair* __restrict__ out, unsigned long long* steps, uint32_t q_tile0)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* colQ = reinterpret_cast<uint64_t*>(smem_raw);                 // [(DT_ROWS+1)][16]
@@ -152,7 +152,7 @@ dist_tile_kernel(const uint64_t* __restrict__ pref, const uint64_t* __restrict__
     const int w = t >> 5, l = t & 31, h = l >> 4, i16 = l & 15;
     const int qc = i16;                              // my query column
     const int rc = ((i16 + w) & 15);                 // my reference column within plane h
-    const uint64_t q_tile = blockIdx.y, r_tile2 = blockIdx.x;               // r_tile2 indexes pairs of 16-col tiles
+    const uint64_t q_tile = blockIdx.y + q_tile0, r_tile2 = blockIdx.x;               // r_tile2 indexes pairs of 16-col tiles
     const uint64_t* gQ = pqry + q_tile * rows_qry * 16;
     const uint64_t* gR[2] = {pref + (2 * r_tile2) * rows_ref * 16, pref + (2 * r_tile2 + 1) * rows_ref * 16};
     const uint64_t n_rtiles16 = (n_ref + 15) / 16;
@@ -263,8 +263,10 @@ dist_tile_kernel(const uint64_t* __restrict__ pref, const uint64_t* __restrict__
     }
 }
 
+// h_out (nullable): host destination.  When given, the fast path runs in query-row chunks and copies chunk c
+// back on a second stream while chunk c+1 is being compared, then waits for all copies.
 static int run_dist(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* d_ref, const fpm_panel* d_qry, fpm_pair* d_out,
-                    uint64_t* d_steps, uint32_t max_size_ref, uint32_t max_size_qry)
+                    uint64_t* d_steps, uint32_t max_size_ref, uint32_t max_size_qry, fpm_pair* h_out = nullptr)
 {
     DistArgs a;
     a.s = p->sketch_size; a.kmer_size = p->kmer_size; a.kmer_space = p->kmer_space;
@@ -295,14 +297,33 @@ static int run_dist(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* d_r
         else {
             size_t smem = (size_t)DT_COLS * (DT_ROWS + 1) * 8;
             FPM_CUDA(cudaFuncSetAttribute(dist_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            dim3 grid((uint32_t)((d_ref->n + 31) / 32), (uint32_t)nq16);
-            if (grid.y > 65535) { set_error("query panel too tall for one launch (%llu sketches): split it", (unsigned long long)d_qry->n); return FPM_ERR_ARG; }
-            ctx->time_begin(FPM_KERNEL_DIST_TILE);
-            dist_tile_kernel<<<grid, DT_THREADS, smem, st>>>(ctx->d_ref.as<uint64_t>(), ctx->d_qry.as<uint64_t>(), rows_r, rows_q, d_ref->n,
-                                                             d_qry->n, d_ref->lengths, d_qry->lengths, a, d_out, (unsigned long long*)d_steps);
-            ctx->time_end();
-            ctx->launches++;
-            FPM_CUDA(cudaGetLastError());
+            // query-row chunks: at most 65535 tiles per launch, and ~16M pairs per chunk when streaming to the host
+            uint64_t tiles_per_chunk = 65535;
+            if (h_out) tiles_per_chunk = std::max<uint64_t>(1, std::min<uint64_t>(65535, (16ull << 20) / (16 * std::max<uint64_t>(d_ref->n, 1))));
+            if (h_out && !ctx->copy_stream) {
+                FPM_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+                FPM_CUDA(cudaEventCreateWithFlags(&ctx->copy_done[0], cudaEventDisableTiming));
+                FPM_CUDA(cudaEventCreateWithFlags(&ctx->copy_done[1], cudaEventDisableTiming));
+            }
+            uint64_t c = 0;
+            for (uint64_t t0 = 0; t0 < nq16; t0 += tiles_per_chunk, c++) {
+                const uint64_t nt = std::min(tiles_per_chunk, nq16 - t0);
+                dim3 grid((uint32_t)((d_ref->n + 31) / 32), (uint32_t)nt);
+                ctx->time_begin(FPM_KERNEL_DIST_TILE);
+                dist_tile_kernel<<<grid, DT_THREADS, smem, st>>>(ctx->d_ref.as<uint64_t>(), ctx->d_qry.as<uint64_t>(), rows_r, rows_q, d_ref->n,
+                                                                 d_qry->n, d_ref->lengths, d_qry->lengths, a, d_out, (unsigned long long*)d_steps, (uint32_t)t0);
+                ctx->time_end();
+                ctx->launches++;
+                FPM_CUDA(cudaGetLastError());
+                if (h_out) {
+                    const uint64_t q0 = t0 * 16, q1 = std::min<uint64_t>(d_qry->n, (t0 + nt) * 16);
+                    FPM_CUDA(cudaEventRecord(ctx->copy_done[c & 1], st));
+                    FPM_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_done[c & 1], 0));
+                    FPM_CUDA(cudaMemcpyAsync(h_out + q0 * d_ref->n, d_out + q0 * d_ref->n, (q1 - q0) * d_ref->n * sizeof(fpm_pair),
+                                             cudaMemcpyDeviceToHost, ctx->copy_stream));
+                }
+            }
+            if (h_out) FPM_CUDA(cudaStreamSynchronize(ctx->copy_stream));
         }
     }
     if (!fast) {
@@ -313,6 +334,10 @@ static int run_dist(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* d_r
         ctx->time_end();
         ctx->launches++;
         FPM_CUDA(cudaGetLastError());
+        if (h_out) {
+            FPM_CUDA(cudaMemcpyAsync(h_out, d_out, total * sizeof(fpm_pair), cudaMemcpyDeviceToHost, st));
+            FPM_CUDA(cudaStreamSynchronize(st));
+        }
     }
     return FPM_OK;
 }
@@ -390,8 +415,8 @@ static int dist_tile_host(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_pane
         fp_positional_kernel<<<(uint32_t)((total + 255) / 256), 256, 0, st>>>(dr, dq, p->max_distance, p->max_pvalue, ctx->d_out.as<fpm_pair>());
         ctx->launches++;
         FPM_CUDA(cudaGetLastError());
-    } else if ((rc = run_dist(ctx, p, &dr, &dq, ctx->d_out.as<fpm_pair>(), nullptr, mr, mq))) return rc;
-    FPM_CUDA(cudaMemcpyAsync(out, ctx->d_out.p, ref->n * qry->n * sizeof(fpm_pair), cudaMemcpyDeviceToHost, st));
+        FPM_CUDA(cudaMemcpyAsync(out, ctx->d_out.p, ref->n * qry->n * sizeof(fpm_pair), cudaMemcpyDeviceToHost, st));
+    } else if ((rc = run_dist(ctx, p, &dr, &dq, ctx->d_out.as<fpm_pair>(), nullptr, mr, mq, out))) return rc;
     FPM_CUDA(cudaStreamSynchronize(st));
     return FPM_OK;
 }

@@ -289,7 +289,7 @@ class Context:
         return p, (h, sz, ln)
 
     def dist_tile(self, ref, qry, sketch_size, kmer_size, kmer_space, max_distance=1.0, max_pvalue=1.0,
-                  sorted_unique=True, out=None):
+                  sorted_unique=True, out=None, raw=False):
         """ref / qry: (hashes [n][stride], sizes [n], lengths [n]).  Returns a structured array
         [n_qry][n_ref] of (numer, denom, distance, pvalue) plus a bool `pass` matrix.  `out` may be a
         caller-owned (e.g. pinned) PAIR_DTYPE array of that shape."""
@@ -300,6 +300,8 @@ class Context:
             out = np.zeros((pq.n, pr.n), dtype=PAIR_DTYPE)
         assert out.dtype == PAIR_DTYPE and out.shape == (pq.n, pr.n) and out.flags["C_CONTIGUOUS"]
         _check(lib.fpm_dist_tile(self._h, C.byref(dp), C.byref(pr), C.byref(pq), out.ctypes.data))
+        if raw:   # the records exactly as the C ABI wrote them (pass flag still in bit 31 of denom)
+            return out, None
         passed = (out["denom"] & FPM_PAIR_PASS) != 0
         out["denom"] &= 0x7fffffff
         return out, passed
