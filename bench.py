@@ -36,6 +36,7 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 K = 21
 S = 1000
 W_INT32_OPS = {21: 74, 32: 96, 16: 64}   # int32-op equivalents of Murmur per k-mer
+NCU_SKETCH_TRAFFIC_RATIO = (315.58 + 9.75) / 300.0   # DRAM bytes per algorithmic byte, ncu capture of sketch_hash_kernel_v2
 
 
 def parse_args():
@@ -441,7 +442,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": "Gk-mers/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
-                         "traffic": None, "kernel": "sketch_hash_kernel<21,true>", "launch_ms": hash_ms_avg,
+                         "traffic": alg_bytes * NCU_SKETCH_TRAFFIC_RATIO, "kernel": "sketch_hash_kernel_v2<21,true>", "launch_ms": hash_ms_avg,
+                         "traffic_note": "dram__bytes_read+write of one ncu --set full capture (profiles/r01_sketch_hash_v2.txt: 325.3 MB for a 300.0 MB launch) scaled to this launch size",
                          "share_of_step": hash_ms / ms_total if ms_total else None,
                          "peak_source": hbm_src,
                          "note": "algorithmic bytes = 1 B per base read once; this kernel is integer-ALU bound, see roofline_int"},
