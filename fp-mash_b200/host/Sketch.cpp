@@ -5,11 +5,15 @@
 
 #include <stdio.h>
 #include <stdlib.h>
+#include <sys/stat.h>
 #include <unistd.h>
 #include <zlib.h>
 #include <fstream>
 #include <iostream>
+#include <condition_variable>
 #include <memory>
+#include <mutex>
+#include <thread>
 #include <sstream>
 
 #include "fastx.h"
@@ -19,7 +23,7 @@
 using namespace std;
 
 static const uint64_t kLimitReadFingerprint = 1000000;   // LIMIT_READ_FINGERPRINT, Sketch.cpp:37
-static const uint64_t kFlushBytes = 1ull << 30;          // sequence bytes per GPU batch
+static const uint64_t kFlushBytes = 256ull << 20;        // sequence bytes per GPU batch (the pinned staging buffer is sized for it)
 
 fpm_ctx* gpuContext()
 {
@@ -67,7 +71,15 @@ void setAlphabetFromString(Sketch::Parameters& parameters, const char* character
 // a batch of sketches on its way to the GPU: sequence bytes (records each followed by 0x00,
 // the layout fpm_sketch_batch defines) + per-sketch metadata
 // ------------------------------------------------------------------------------------------
-struct Sketch::Batch {
+// where parsed records go: the pinned GPU batch, or a per-file buffer filled by a parser thread
+struct SeqSink {
+    virtual void addRecord(const char* s, uint64_t l) = 0;
+    virtual void closeGroup(const Sketch::Reference& meta) = 0;
+    virtual void expect(uint64_t /*bytes*/) {}   // size hint before a file is parsed
+    virtual ~SeqSink() {}
+};
+
+struct Sketch::Batch : SeqSink {
     uint8_t* seq = nullptr;      // pinned
     uint64_t used = 0, cap = 0;
     vector<uint64_t> goff{0};
@@ -78,7 +90,7 @@ struct Sketch::Batch {
     void reserve(uint64_t extra)
     {
         if (used + extra <= cap) return;
-        uint64_t ncap = max<uint64_t>(cap ? cap * 2 : (64ull << 20), used + extra);
+        uint64_t ncap = max<uint64_t>(cap ? cap * 2 : (kFlushBytes + (64ull << 20)), used + extra);
         void* p = nullptr;
         gpuCheck(fpm_host_alloc(ncap, &p));
         if (used) memcpy(p, seq, used);
@@ -86,17 +98,25 @@ struct Sketch::Batch {
         seq = (uint8_t*)p;
         cap = ncap;
     }
-    void addRecord(const char* s, uint64_t l)
+    void addRecord(const char* s, uint64_t l) override
     {
         reserve(l + 1);
         memcpy(seq + used, s, l);
         seq[used + l] = 0;
         used += l + 1;
     }
-    void closeGroup(const Reference& meta)
+    void closeGroup(const Reference& meta) override
     {
         goff.push_back(used);
         metas.push_back(meta);
+    }
+    // append a whole parsed file (records already followed by their separators)
+    void append(const uint8_t* bytes, uint64_t n, const vector<uint64_t>& offs, const vector<Reference>& ms)
+    {
+        reserve(n);
+        if (n) memcpy(seq + used, bytes, n);
+        for (size_t g = 0; g < ms.size(); g++) { goff.push_back(used + offs[g + 1]); metas.push_back(ms[g]); }
+        used += n;
     }
     void clear()
     {
@@ -147,8 +167,7 @@ void Sketch::flushBatch(Batch& b)
 // records are taken one per file in rotation, a record shorter than k is skipped WITHOUT
 // advancing the rotation, name/comment come from the first valid record.
 static void readGroup(const vector<string>& fileNames, const Sketch::Parameters& parameters, Sketch::Reference& reference,
-                      uint64_t& count, bool& skipped, Sketch::Batch* batchPtr,
-                      void (*addRecord)(Sketch::Batch*, const char*, uint64_t))
+                      uint64_t& count, bool& skipped, SeqSink& sink)
 {
     int fileCount = (int)fileNames.size();
     vector<gzFile> fps(fileCount);
@@ -169,7 +188,7 @@ static void readGroup(const vector<string>& fileNames, const Sketch::Parameters&
                 exit(1);
             }
         }
-        gzbuffer(fps[f], 1 << 20);
+        gzbuffer(fps[f], 1 << 17);   // smaller than the reader's 1 MB requests: plain files are then read directly
         readers.emplace_back(new FastxReader(fps[f]));
     }
     int64_t l = -1;
@@ -201,7 +220,7 @@ static void readGroup(const vector<string>& fileNames, const Sketch::Parameters&
         }
         count++;
         if (!parameters.reads) reference.length += l;
-        addRecord(batchPtr, rd.seq.data(), (uint64_t)l);
+        sink.addRecord(rd.seq.data(), (uint64_t)l);
         it++;
         if (it == readers.size()) it = 0;
     }
@@ -218,7 +237,129 @@ static void readGroup(const vector<string>& fileNames, const Sketch::Parameters&
     }
 }
 
-static void batchAdd(Sketch::Batch* b, const char* s, uint64_t l);
+
+// One input file -> records in `sink`: one sketch per file (sketchFile, Sketch.cpp:1299-1488) or, with -i, one
+// per record (sketchFileBySequence + sketchSequence, Sketch.cpp:478-522, 1490-1517).  Errors print and exit
+// like the reference's workers do.
+static void parseSequenceFile(const string& file, const Sketch::Parameters& parameters, SeqSink& sink)
+{
+    struct stat st;
+    if (file != "-" && stat(file.c_str(), &st) == 0 && !hasSuffix(file, ".gz")) sink.expect((uint64_t)st.st_size);
+    if (parameters.concatenated) {
+        Sketch::Reference reference;
+        uint64_t count;
+        bool skipped;
+        readGroup(vector<string>(1, file), parameters, reference, count, skipped, sink);
+        if (reference.length == 0) {
+            if (skipped) cerr << "\nWARNING: All fasta records in input files were shorter than the k-mer size (" << parameters.kmerSize << ")." << endl;
+            else cerr << "\nERROR: Did not find fasta records in \"input files\"." << endl;
+            exit(1);
+        }
+        sink.closeGroup(reference);
+        return;
+    }
+    gzFile fp = file == "-" ? gzdopen(fileno(stdin), "r") : gzopen(file.c_str(), "r");
+    if (!fp) {
+        cerr << "ERROR: could not open " << file << " for reading." << endl;
+        exit(1);
+    }
+    gzbuffer(fp, 1 << 17);
+    FastxReader rd(fp);
+    int64_t l;
+    while ((l = rd.next()) >= 0) {
+        if (l < parameters.kmerSize) continue;
+        Sketch::Reference reference;
+        reference.length = l;
+        reference.name = rd.name;
+        reference.comment = rd.comment;
+        sink.addRecord(rd.seq.data(), (uint64_t)l);
+        sink.closeGroup(reference);
+    }
+    gzclose(fp);
+    if (l != -1) {
+        cerr << "\nERROR: reading " << file << "." << endl;
+        exit(1);
+    }
+}
+
+// A parsed file held in ordinary memory until the main thread splices it into the GPU batch.
+struct FileBuffer : SeqSink {
+    vector<uint8_t> seq;
+    vector<uint64_t> goff{0};
+    vector<Sketch::Reference> metas;
+    void expect(uint64_t bytes) override { seq.reserve(seq.size() + bytes + 16); }
+    void addRecord(const char* s, uint64_t l) override
+    {
+        seq.insert(seq.end(), (const uint8_t*)s, (const uint8_t*)s + l);
+        seq.push_back(0);
+    }
+    void closeGroup(const Sketch::Reference& meta) override
+    {
+        goff.push_back(seq.size());
+        metas.push_back(meta);
+    }
+};
+
+// -p: files are parsed by a pool of threads (the reference's ThreadPool fans out whole files the same way,
+// Sketch.cpp:353-355) with a bounded look-ahead; results are consumed strictly in submission order.
+class ParsePool {
+public:
+    ParsePool(const vector<string>& jobFiles, const Sketch::Parameters& p, int nThreads)
+        : files(jobFiles), parameters(p), slots(jobFiles.size()), ready(jobFiles.size(), 0), window((size_t)nThreads * 4)
+    {
+        for (int t = 0; t < nThreads; t++) threads.emplace_back([this] { work(); });
+    }
+    ~ParsePool()
+    {
+        {
+            lock_guard<mutex> lk(m);
+            stop = true;
+        }
+        cvWork.notify_all();
+        for (auto& t : threads) t.join();
+    }
+    unique_ptr<FileBuffer> take(size_t j)
+    {
+        unique_lock<mutex> lk(m);
+        cvDone.wait(lk, [&] { return ready[j] != 0; });
+        unique_ptr<FileBuffer> r = move(slots[j]);
+        consumed = j + 1;
+        lk.unlock();
+        cvWork.notify_all();
+        return r;
+    }
+
+private:
+    void work()
+    {
+        for (;;) {
+            size_t j;
+            {
+                unique_lock<mutex> lk(m);
+                cvWork.wait(lk, [&] { return stop || (next < files.size() && next < consumed + window); });
+                if (stop || next >= files.size()) return;
+                j = next++;
+            }
+            unique_ptr<FileBuffer> fb(new FileBuffer());
+            parseSequenceFile(files[j], parameters, *fb);
+            {
+                lock_guard<mutex> lk(m);
+                slots[j] = move(fb);
+                ready[j] = 1;
+            }
+            cvDone.notify_all();
+        }
+    }
+    const vector<string>& files;
+    const Sketch::Parameters& parameters;
+    vector<unique_ptr<FileBuffer>> slots;
+    vector<char> ready;
+    size_t window, next = 0, consumed = 0;
+    bool stop = false;
+    mutex m;
+    condition_variable cvWork, cvDone;
+    vector<thread> threads;
+};
 
 static void checkUnsupported(const Sketch::Parameters& p)
 {
@@ -335,7 +476,7 @@ void Sketch::initFromReads(const vector<string>& files, const Parameters& parame
     Reference reference;
     uint64_t count;
     bool skipped;
-    readGroup(files, parameters, reference, count, skipped, &batch, batchAdd);
+    readGroup(files, parameters, reference, count, skipped, batch);
     batch.closeGroup(reference);
     size_t at = references.size();
     flushBatch(batch);
@@ -413,12 +554,35 @@ uint64_t Sketch::initParametersFromCapnp(const char* file)   // Sketch.cpp:401-4
     return referenceCount;
 }
 
-static void batchAdd(Sketch::Batch* b, const char* s, uint64_t l) { b->addRecord(s, l); }
 
 int Sketch::initFromFiles(const vector<string>& files, const Parameters& parametersNew, int verbosity, bool enforceParameters, bool contain)
 {
     parameters = parametersNew;
     Batch batch;
+
+    // sequence files (not sketches, not stdin) can be parsed ahead by -p threads
+    vector<string> jobFiles;
+    vector<size_t> jobOf(files.size(), 0);
+    for (size_t i = 0; i < files.size(); i++) {
+        if (!hasSuffix(files[i], suffixSketch) && files[i] != "-") { jobOf[i] = jobFiles.size(); jobFiles.push_back(files[i]); }
+    }
+    bool anyStdin = false;
+    for (const string& f : files) anyStdin |= f == "-";
+    unique_ptr<ParsePool> pool;
+    const Parameters poolParameters = parameters;   // sketch files given first may still change `parameters`
+    bool sketchFirst = !files.empty() && hasSuffix(files[0], suffixSketch) && !enforceParameters;
+    if (parameters.parallelism > 1 && jobFiles.size() > 1 && !anyStdin && !sketchFirst) {
+        for (const string& f : jobFiles) {
+            FILE* probe = fopen(f.c_str(), "r");
+            if (probe == NULL) {
+                cerr << "ERROR: could not open " << f << " for reading." << endl;
+                exit(1);
+            }
+            fclose(probe);
+        }
+        checkUnsupported(parameters);
+        pool.reset(new ParsePool(jobFiles, poolParameters, min<int>(parameters.parallelism, (int)jobFiles.size())));
+    }
 
     for (size_t i = 0; i < files.size(); i++) {
         bool isSketch = hasSuffix(files[i], suffixSketch);
@@ -469,43 +633,11 @@ int Sketch::initFromFiles(const vector<string>& files, const Parameters& paramet
             }
             fclose(probe);
         }
-        if (parameters.concatenated) {
-            // one sketch per file: sketchFile (Sketch.cpp:1299-1488)
-            Reference reference;
-            uint64_t count;
-            bool skipped;
-            readGroup(vector<string>(1, files[i]), parameters, reference, count, skipped, &batch, batchAdd);
-            if (reference.length == 0) {
-                if (skipped) cerr << "\nWARNING: All fasta records in input files were shorter than the k-mer size (" << parameters.kmerSize << ")." << endl;
-                else cerr << "\nERROR: Did not find fasta records in \"input files\"." << endl;
-                exit(1);
-            }
-            batch.closeGroup(reference);
+        if (pool) {
+            unique_ptr<FileBuffer> fb = pool->take(jobOf[i]);
+            batch.append(fb->seq.data(), fb->seq.size(), fb->goff, fb->metas);
         } else {
-            // one sketch per record: sketchFileBySequence + sketchSequence (Sketch.cpp:478-522, 1490-1517)
-            gzFile fp = files[i] == "-" ? gzdopen(fileno(stdin), "r") : gzopen(files[i].c_str(), "r");
-            if (!fp) {
-                cerr << "ERROR: could not open " << files[i] << " for reading." << endl;
-                exit(1);
-            }
-            gzbuffer(fp, 1 << 20);
-            FastxReader rd(fp);
-            int64_t l;
-            while ((l = rd.next()) >= 0) {
-                if (l < parameters.kmerSize) continue;
-                Reference reference;
-                reference.length = l;
-                reference.name = rd.name;
-                reference.comment = rd.comment;
-                batch.addRecord(rd.seq.data(), (uint64_t)l);
-                batch.closeGroup(reference);
-                if (batch.used >= kFlushBytes) flushBatch(batch);
-            }
-            gzclose(fp);
-            if (l != -1) {
-                cerr << "\nERROR: reading " << files[i] << "." << endl;
-                exit(1);
-            }
+            parseSequenceFile(files[i], parameters, batch);
         }
         if (batch.used >= kFlushBytes) flushBatch(batch);
     }

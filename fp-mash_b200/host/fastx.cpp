@@ -3,6 +3,9 @@
 
 #include <ctype.h>
 #include <string.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 namespace {
 // byte classes while reading sequence lines: 0 keep (isgraph), 1 drop, 2 terminator ('>', '+', '@')
@@ -68,17 +71,35 @@ int64_t FastxReader::next()
         }
         const unsigned char* p = buf.data() + begin;
         const unsigned char* e = buf.data() + end;
-        size_t old = seq.size();
-        seq.resize(old + (size_t)(e - p));
-        char* out = seq.data() + old;
+        seq.reserve_more((size_t)(e - p));
+        char* out = seq.data() + seq.size();
         bool stop = false;
         while (p < e) {
+#if defined(__SSE2__)
+            // 16 bytes at a time while they are all plain sequence characters (33..126, none of > + @)
+            while (p + 16 <= e) {
+                __m128i x = _mm_loadu_si128((const __m128i*)p);
+                __m128i bad = _mm_or_si128(_mm_cmpgt_epi8(_mm_set1_epi8(33), x), _mm_cmpgt_epi8(x, _mm_set1_epi8(126)));
+                bad = _mm_or_si128(bad, _mm_cmpeq_epi8(x, _mm_set1_epi8('>')));
+                bad = _mm_or_si128(bad, _mm_cmpeq_epi8(x, _mm_set1_epi8('+')));
+                bad = _mm_or_si128(bad, _mm_cmpeq_epi8(x, _mm_set1_epi8('@')));
+                int mask = _mm_movemask_epi8(bad);
+                _mm_storeu_si128((__m128i*)out, x);        // harmless over-write: the buffer has room for e - p bytes
+                if (mask) {
+                    int good = __builtin_ctz(mask);          // bytes before the first special one
+                    p += good; out += good;
+                    break;
+                }
+                p += 16; out += 16;
+            }
+            if (p >= e) break;
+#endif
             unsigned char ch = *p++;
             unsigned char cls = kClass.t[ch];
             if (cls == 0) *out++ = (char)ch;
             else if (cls == 2) { c = ch; stop = true; break; }
         }
-        seq.resize((size_t)(out - seq.data()));
+        seq.n = (size_t)(out - seq.data());
         begin = (size_t)(p - buf.data());
         if (stop) break;
     }
@@ -86,9 +107,28 @@ int64_t FastxReader::next()
     if (c != '+') return (int64_t)seq.size();
     while ((c = getc()) != -1 && c != '\n') {}
     if (c == -1) return -2;
+    // quality: skip bytes until as many printable ones (33..127) as bases were seen, then one more byte
     size_t qual = 0;
-    while ((c = getc()) != -1 && qual < seq.size())
-        if (c >= 33 && c <= 127) qual++;
+    for (;;) {
+        if (begin >= end) {
+            c = getc();
+            if (c == -1) break;
+            begin--;
+        }
+        if (qual >= seq.size()) { c = buf[begin++]; break; }     // the byte consumed after the last quality byte
+        const unsigned char* p = buf.data() + begin;
+        const unsigned char* e = buf.data() + end;
+        const size_t need = seq.size() - qual;
+        // fast path: the next `need` bytes are one clean quality line
+        if ((size_t)(e - p) > need && memchr(p, '\n', need) == nullptr && memchr(p, '\r', need) == nullptr &&
+            memchr(p, ' ', need) == nullptr && memchr(p, '\t', need) == nullptr) {
+            bool clean = true;
+            for (size_t i = 0; i < need; i++) clean &= (p[i] >= 33) & (p[i] <= 127);
+            if (clean) { qual += need; begin += need; continue; }
+        }
+        unsigned char ch = buf[begin++];
+        if (ch >= 33 && ch <= 127) qual++;
+    }
     last_char = 0;
     if (qual != seq.size()) return -2;
     return (int64_t)seq.size();

@@ -12,6 +12,7 @@
 //     stale text is observable and is mirrored here as `comment_cstr`.
 #pragma once
 #include <stdint.h>
+#include <stdlib.h>
 #include <zlib.h>
 #include <string>
 #include <vector>
@@ -25,7 +26,26 @@ public:
     std::string name;
     std::string comment;        // this record's comment (empty if none)
     std::string comment_cstr;   // what kseq's comment.s would hold (stale when no comment)
-    std::vector<char> seq;      // sequence bytes (not NUL-terminated)
+    // sequence bytes (not NUL-terminated); a plain growable buffer (no zero fill on growth)
+    struct CharBuf {
+        char* p = nullptr;
+        size_t n = 0, cap = 0;
+        ~CharBuf() { free(p); }
+        char* data() { return p; }
+        const char* data() const { return p; }
+        size_t size() const { return n; }
+        void clear() { n = 0; }
+        void reserve_more(size_t extra)
+        {
+            if (n + extra <= cap) return;
+            size_t nc = cap ? cap * 2 : (1 << 16);
+            while (nc < n + extra) nc *= 2;
+            p = (char*)realloc(p, nc);
+            cap = nc;
+        }
+        const char* begin() const { return p; }
+        const char* end() const { return p + n; }
+    } seq;
 private:
     int getc();
     gzFile fp;

@@ -199,3 +199,25 @@ def test_sketch_protein_cli(tmp_path, oracle, fpm):
     for x, s in zip(m.refs, seqs):
         w = oracle.sketch([s], k=9, s=300, alphabet=table, noncanonical=True)
         assert x["hashes64"] == [int(v) for v in w["hashes"]]
+
+
+def test_parallel_parsing_keeps_submission_order(tmp_path):
+    """-p N parses files on N threads; the .msh must be byte-identical to the single-threaded run
+    (the reference's ThreadPool returns outputs in submission order, ThreadPool.hxx:127-167)."""
+    from util import random_dna
+    rng = np.random.default_rng(21)
+    names = []
+    for i in range(23):
+        nm = "g%02d.fa" % i
+        with open(tmp_path / nm, "wb") as f:
+            for r in range(1 + i % 3):
+                f.write(b">g%d_%d c\n" % (i, r) + random_dna(rng, int(rng.integers(30, 60000))) + b"\n")
+        names.append(nm)
+    (tmp_path / "list.txt").write_text("\n".join(names) + "\n")
+    run(["sketch", "-l", "-o", "one", "list.txt"], cwd=tmp_path)
+    run(["sketch", "-l", "-p", "6", "-o", "six", "list.txt"], cwd=tmp_path)
+    assert same_bytes(tmp_path / "one.msh", tmp_path / "six.msh")
+    run(["sketch", "-i", "-p", "4", "-o", "ind4"] + names, cwd=tmp_path)
+    run(["sketch", "-i", "-o", "ind1"] + names, cwd=tmp_path)
+    assert same_bytes(tmp_path / "ind1.msh", tmp_path / "ind4.msh")
+    assert len(mshpy.load(tmp_path / "ind4.msh").refs) == sum(1 + i % 3 for i in range(23))

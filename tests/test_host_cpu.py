@@ -112,6 +112,12 @@ NASTY = {
     "no_newline.fa": b">x\nACGTAC",
     "empty.fa": b"",
     "garbage_head.fa": b"junk\nmore junk\n>ok 1\nACGT\n",
+    "long_lines.fa": b">a x\n" + b"ACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTAC\n" * 40
+                     + b">b\n" + b"ACGTNNNNACGT ACGTACGTACGTACGTAC\tGTACGTACGTACGTACG\r\nTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTT>c inner\nAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAA+\n",
+    "fastq_tricky_quality.fq": b"@r1\nACGTACGTACGTACGTACGTACGTACGTACGTAC\n+\n@@>>++IIIIIIIIIIIIIIIIIIIIIIIIIIII\n"
+                               b"@r2 c\r\nACGTACGTACGTACGTACGTAC\r\n+\r\nIIIIIIIIIIIIIIIIIIIIII\r\n"
+                               b"@r3\nACGTACGTACGTACGTACGTACGTACGTACGTACGTACGT\n+\nIIIIIIIIII IIIIIIIIII\nIIIIIIIIIIIIIIIIIIII\n@r4\nAC\n+\nII",
+    "fastq_multiline.fq": b"@m1\nACGTACGTAC\nGGGGGTTTTT\n+m1\nIIIIIIIIII\nJJJJJJJJJJ\n@m2\nAAAA\n+\nIIII\n",
 }
 
 
