@@ -1,0 +1,105 @@
+// cfl.cu -- lyn2vec's "basic" CFL fingerprints on the GPU (the producer of `-fp` inputs).
+//
+// Replaces, for --type basic --type_factorization CFL --shift shift (the README recipe, README.md:34-52):
+//   shift_string      (lyn2vec/fingerprint_utils.py:95-110)  every circular window of `window` (=100) characters
+//   CFL               (lyn2vec/factorizations.py:102-126)    Duval's Lyndon factorisation of each window
+//   the line writer   (fingerprint_utils.py:443-476)         one row of factor LENGTHS per window
+// and fuses getHashFingerPrint (hash.cpp:45-73) over each row, so a FASTA record can go straight to the
+// `-fp` sketch (one 32-bit hash per window) without the text file -- which can still be written from
+// the token rows, byte-identical with lyn2vec's.
+//
+// One thread per window: Duval is sequential within a word (O(window) steps) and the windows are
+// independent.  Characters compare by byte value, as Python compares single characters.
+#include "common.h"
+#include "murmur3.cuh"
+
+namespace fpm {
+
+constexpr int CFL_MAX_WINDOW = 256;
+
+__global__ void __launch_bounds__(128) cfl_window_kernel(const uint8_t* __restrict__ seq, const uint64_t* __restrict__ rec_off,
+                                                         const uint64_t* __restrict__ win_off, uint32_t n_rec, uint32_t window,
+                                                         uint32_t seed, int use64, uint64_t* __restrict__ out_hash,
+                                                         uint16_t* __restrict__ out_tok, uint16_t* __restrict__ out_ntok)
+{
+    const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= win_off[n_rec]) return;
+    uint32_t lo = 0, hi = n_rec - 1;                       // record holding window w
+    while (lo < hi) { uint32_t mid = (lo + hi + 1) >> 1; if (win_off[mid] <= w) lo = mid; else hi = mid - 1; }
+    const uint64_t base = rec_off[lo], n = rec_off[lo + 1] - base, shift = w - win_off[lo];
+    const uint32_t len = n < window ? (uint32_t)n : window;   // shorter records give one window: the record itself
+    uint8_t word[CFL_MAX_WINDOW];
+    for (uint32_t j = 0; j < len; j++) {
+        uint64_t p = shift + j;
+        if (p >= n) p -= n;                                 // circular wrap (fingerprint_utils.py:104-108)
+        word[j] = seq[base + p];
+    }
+    // Duval (factorizations.py:102-126), factor lengths streamed into MurmurHash3 two tokens per block
+    uint64_t h1 = seed, h2 = seed, pending = 0;
+    uint32_t ntok = 0, i = 0;
+    uint16_t* row = out_tok ? out_tok + w * window : nullptr;
+    while (i < len) {
+        uint32_t j = i + 1, k = i;
+        while (j < len && word[k] <= word[j]) {
+            k = word[k] < word[j] ? i : k + 1;
+            j++;
+        }
+        const uint32_t flen = j - k;
+        while (i <= k) {
+            if (row) row[ntok] = (uint16_t)flen;
+            if (ntok & 1) mm_block(h1, h2, pending, (uint64_t)flen); else pending = flen;
+            ntok++;
+            i += flen;
+        }
+    }
+    if (ntok & 1) h1 ^= mm_k1(pending);                     // 8-byte tail
+    const uint64_t h = mm_finish(h1, h2, (uint64_t)ntok * 8);
+    if (out_hash) out_hash[w] = use64 ? h : (h & 0xffffffffULL);
+    if (out_ntok) out_ntok[w] = (uint16_t)ntok;
+}
+
+}  // namespace fpm
+
+using namespace fpm;
+
+extern "C" int fpm_cfl_fingerprint_batch(fpm_ctx* ctx, const uint8_t* seq, const uint64_t* rec_offsets, uint32_t n_records, uint32_t window,
+                                         uint32_t seed, int use64, uint64_t* out_hashes, uint16_t* out_tokens, uint16_t* out_ntokens,
+                                         uint64_t* out_window_offsets)
+{
+    if (!ctx) { set_error("ctx is NULL"); return FPM_ERR_ARG; }
+    if (!rec_offsets || !out_window_offsets) { set_error("NULL buffer"); return FPM_ERR_ARG; }
+    if (window < 1 || window > CFL_MAX_WINDOW) { set_error("window %u outside 1..%d", window, CFL_MAX_WINDOW); return FPM_ERR_ARG; }
+    FPM_CUDA(cudaSetDevice(ctx->device));
+    // windows per record: len(record) circular shifts, or one window when the record is shorter (shift_string)
+    std::vector<uint64_t> woff(n_records + 1, 0);
+    for (uint32_t r = 0; r < n_records; r++) {
+        if (rec_offsets[r + 1] < rec_offsets[r]) { set_error("record offsets not ascending"); return FPM_ERR_ARG; }
+        uint64_t n = rec_offsets[r + 1] - rec_offsets[r];
+        woff[r + 1] = woff[r] + (n == 0 ? 0 : (n < window ? 1 : n));
+    }
+    memcpy(out_window_offsets, woff.data(), sizeof(uint64_t) * (n_records + 1));
+    const uint64_t n_win = woff[n_records], n_bytes = rec_offsets[n_records];
+    if (n_win == 0 || (!out_hashes && !out_tokens && !out_ntokens)) return FPM_OK;
+    int rc;
+    cudaStream_t st = ctx->stream;
+    if ((rc = ctx->seq.ensure(n_bytes + 64))) return rc;
+    if ((rc = ctx->goff.ensure(sizeof(uint64_t) * 2 * (n_records + 1)))) return rc;
+    if ((rc = ctx->outh.ensure(sizeof(uint64_t) * n_win))) return rc;
+    if ((rc = ctx->outc.ensure(out_tokens ? sizeof(uint16_t) * n_win * window : 8))) return rc;
+    if ((rc = ctx->outn.ensure(sizeof(uint16_t) * n_win))) return rc;
+    uint64_t* d_rec = ctx->goff.as<uint64_t>();
+    uint64_t* d_win = d_rec + (n_records + 1);
+    FPM_CUDA(cudaMemcpyAsync(ctx->seq.p, seq, n_bytes, cudaMemcpyHostToDevice, st));
+    FPM_CUDA(cudaMemcpyAsync(d_rec, rec_offsets, sizeof(uint64_t) * (n_records + 1), cudaMemcpyHostToDevice, st));
+    FPM_CUDA(cudaMemcpyAsync(d_win, woff.data(), sizeof(uint64_t) * (n_records + 1), cudaMemcpyHostToDevice, st));
+    cfl_window_kernel<<<(uint32_t)((n_win + 127) / 128), 128, 0, st>>>(ctx->seq.as<uint8_t>(), d_rec, d_win, n_records, window, seed, use64,
+                                                                       ctx->outh.as<uint64_t>(), out_tokens ? ctx->outc.as<uint16_t>() : nullptr,
+                                                                       ctx->outn.as<uint16_t>());
+    ctx->launches++;
+    FPM_CUDA(cudaGetLastError());
+    if (out_hashes) FPM_CUDA(cudaMemcpyAsync(out_hashes, ctx->outh.p, sizeof(uint64_t) * n_win, cudaMemcpyDeviceToHost, st));
+    if (out_tokens) FPM_CUDA(cudaMemcpyAsync(out_tokens, ctx->outc.p, sizeof(uint16_t) * n_win * window, cudaMemcpyDeviceToHost, st));
+    if (out_ntokens) FPM_CUDA(cudaMemcpyAsync(out_ntokens, ctx->outn.p, sizeof(uint16_t) * n_win, cudaMemcpyDeviceToHost, st));
+    FPM_CUDA(cudaStreamSynchronize(st));
+    return FPM_OK;
+}

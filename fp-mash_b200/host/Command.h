@@ -49,5 +49,6 @@ class CommandDistance : public Command { public: CommandDistance(); int run() co
 class CommandPaste : public Command { public: CommandPaste(); int run() const; };
 class CommandInfo : public Command { public: CommandInfo(); int run() const; };
 class CommandTriangle : public Command { public: CommandTriangle(); int run() const; };
+class CommandFingerprint : public Command { public: CommandFingerprint(); int run() const; };
 
 }  // namespace mash

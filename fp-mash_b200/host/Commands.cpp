@@ -767,4 +767,95 @@ int CommandTriangle::run() const
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// mash fingerprint: lyn2vec's `--type basic --type_factorization CFL --shift shift --rev_comb true`
+// (README.md:34-52; lyn2vec/fingerprint_utils.py:256-308,312-376,443-476) with the factorisation on the
+// GPU, so the producer of `-fp` inputs no longer needs Python.  Output rows: "<id> n1 n2 ...".
+// ------------------------------------------------------------------------------------------
+CommandFingerprint::CommandFingerprint() : Command()
+{
+    name = "fingerprint";
+    summary = "Lyndon (CFL) fingerprints of sequences, the input of `sketch -fp` (lyn2vec basic mode).";
+    description = "For every record of each FASTA input, factorise every circular window of -w characters with Duval's algorithm and write one line of factor lengths per window, in the format of lyn2vec's fingerprint_CFL.txt. The row id is the second word of the record header followed by _0, as lyn2vec writes it with --rev_comb true.";
+    argumentString = "<fasta> [<fasta>] ...";
+    useOption("help");
+    addOption("window", Option(Option::Integer, "w", "", "Window length of the circular shifts.", "100", 1, 256));
+    addOption("prefix", Option(Option::File, "o", "Output", "Output file.", "fingerprint_CFL.txt"));
+}
+
+int CommandFingerprint::run() const
+{
+    if (arguments.size() == 0 || options.at("help").active) {
+        print();
+        return 0;
+    }
+    const uint32_t window = (uint32_t)options.at("window").getArgumentAsNumber();
+    vector<string> ids;
+    vector<uint8_t> seq;
+    vector<uint64_t> off{0};
+    for (const string& file : arguments) {
+        ifstream in(file);
+        if (!in) {
+            cerr << "ERROR: could not open " << file << " for reading." << endl;
+            return 1;
+        }
+        // read_fasta (fingerprint_utils.py:256-308): id = 2nd word of the header; sequence lines joined, upper-cased
+        string line;
+        bool open = false;
+        while (getline(in, line)) {
+            if (!line.empty() && line[0] == '>') {
+                if (open) off.push_back(seq.size());
+                size_t a = line.find_first_not_of(" \t\r", line.find_first_of(" \t\r"));
+                string id = a == string::npos ? line.substr(1) : line.substr(a, line.find_first_of(" \t\r", a) - a);
+                ids.push_back(id + "_0");
+                open = true;
+            } else if (open) {
+                for (char ch : line) {
+                    if (ch == '\r' || ch == '\n') continue;
+                    seq.push_back((uint8_t)((ch > 96 && ch < 123) ? ch - 32 : ch));
+                }
+            }
+        }
+        if (open) off.push_back(seq.size());
+    }
+    const uint32_t n = (uint32_t)ids.size();
+    if (n == 0) {
+        cerr << "ERROR: no FASTA records found." << endl;
+        return 1;
+    }
+    seq.push_back(0);
+    vector<uint64_t> woff(n + 1);
+    if (fpm_cfl_fingerprint_batch(gpuContext(), seq.data(), off.data(), n, window, 42, 0, nullptr, nullptr, nullptr, woff.data()) != FPM_OK) {
+        cerr << "ERROR: " << fpm_last_error() << endl;
+        return 1;
+    }
+    const uint64_t nWin = woff[n];
+    vector<uint16_t> tok(nWin * window), ntok(nWin);
+    if (fpm_cfl_fingerprint_batch(gpuContext(), seq.data(), off.data(), n, window, 42, 0, nullptr, tok.data(), ntok.data(), woff.data()) != FPM_OK) {
+        cerr << "ERROR: " << fpm_last_error() << endl;
+        return 1;
+    }
+    const string outName = options.at("prefix").argument;
+    ofstream out(outName);
+    if (!out) {
+        cerr << "ERROR: could not open " << outName << " for writing." << endl;
+        return 1;
+    }
+    string row;
+    for (uint32_t r = 0; r < n; r++) {
+        for (uint64_t w = woff[r]; w < woff[r + 1]; w++) {
+            row = ids[r];
+            row += ' ';                                      // lbl_id_gene = id + ' '; lengths joined by ' '
+            for (uint16_t t = 0; t < ntok[w]; t++) {
+                if (t) row += ' ';
+                row += to_string(tok[w * window + t]);
+            }
+            row += '\n';
+            out << row;
+        }
+    }
+    cerr << "Writing to " << outName << "..." << endl;
+    return 0;
+}
+
 }  // namespace mash

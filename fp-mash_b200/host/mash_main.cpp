@@ -16,6 +16,7 @@ int main(int argc, const char** argv)
     commands["paste"].reset(new mash::CommandPaste());
     commands["info"].reset(new mash::CommandInfo());
     commands["triangle"].reset(new mash::CommandTriangle());
+    commands["fingerprint"].reset(new mash::CommandFingerprint());
     if (argc >= 2 && (strcmp(argv[1], "--version") == 0)) {
         std::cout << "2.3 (fp-mash hot path, B200-native)" << std::endl;
         return 0;

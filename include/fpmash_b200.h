@@ -116,6 +116,18 @@ int fpm_kmer_hashes(fpm_ctx* ctx, const fpm_sketch_params* p, const uint8_t* seq
 int fpm_fp_hash_batch(fpm_ctx* ctx, const uint64_t* tokens, const uint64_t* line_offsets, uint64_t n_lines,
                       uint32_t seed, int use64, uint64_t* out_hashes);
 
+/* Upstream of -fp: lyn2vec's `--type basic --type_factorization CFL --shift shift` on the GPU.
+ * Replaces shift_string + CFL (Duval) + the row writer (lyn2vec/fingerprint_utils.py:95-110,443-476,
+ * lyn2vec/factorizations.py:102-126): for every record, every circular window of `window` characters (one
+ * window = the record itself when it is shorter) is Lyndon-factorised; the row of factor LENGTHS is hashed
+ * like getHashFingerPrint.  Records are raw bytes back to back (no separators); rec_offsets has n_records+1
+ * entries.  out_window_offsets[n_records+1] (required) receives the first window index of each record;
+ * out_hashes[n_windows], out_tokens[n_windows][window] (lengths, row-padded) and out_ntokens[n_windows] are
+ * optional.  Call once with all three NULL to learn n_windows = out_window_offsets[n_records].             */
+int fpm_cfl_fingerprint_batch(fpm_ctx* ctx, const uint8_t* seq, const uint64_t* rec_offsets, uint32_t n_records, uint32_t window,
+                              uint32_t seed, int use64, uint64_t* out_hashes, uint16_t* out_tokens, uint16_t* out_ntokens,
+                              uint64_t* out_window_offsets);
+
 /* ---- dist ---------------------------------------------------------------------------- */
 
 /* PairOutput (CommandDistance.h:57-64) as a 24-byte POD.                                   */
