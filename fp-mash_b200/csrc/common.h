@@ -41,6 +41,10 @@ struct fpm_ctx {
     // sketch scratch
     fpm::DevBuf seq, goff, thresh, active, toff, tmask, tkeys, tcnt, tpos, maxcnt, maxpos, overflow,
         stat, tiles, args, alpha, scratch, outh, outc, outn, outk, firstpos, tr_off, tr_cursor, tr_pos, glist;
+    // streaming sketch input (fpm_sketch_stream_*): sequence accumulated in HBM + group ends
+    fpm::DevBuf stream_buf;
+    uint64_t stream_used = 0;
+    std::vector<uint64_t> stream_goff;
     // dist scratch
     fpm::DevBuf d_ref, d_qry, d_rs, d_qs, d_rl, d_ql, d_out, d_misc;
     // optional per-kernel event timing (bench roofline): pairs of events around each launch

@@ -53,8 +53,11 @@ __device__ __forceinline__ void convert32(const uint32_t (&w)[8], uint32_t fold_
     }
 }
 
+#ifndef FPM_SK_MIN_CTAS
+#define FPM_SK_MIN_CTAS 4   // 64 registers: four 256-thread CTAs (32 warps) per SM; measured best (3 -> 79 regs, 1 -> 100 regs are slower)
+#endif
 template <int K, bool CANON>
-__global__ void __launch_bounds__(SK_THREADS) sketch_hash_kernel_v2(const SketchArgs* __restrict__ ga, uint64_t range_lo, uint64_t range_hi,
+__global__ void __launch_bounds__(SK_THREADS, FPM_SK_MIN_CTAS) sketch_hash_kernel_v2(const SketchArgs* __restrict__ ga, uint64_t range_lo, uint64_t range_hi,
                                                                    uint64_t range_base, int trace)
 {
     const SketchArgs& a = *ga;
@@ -110,6 +113,8 @@ __global__ void __launch_bounds__(SK_THREADS) sketch_hash_kernel_v2(const Sketch
         const bool idle_tile = uniform_ok && tmax == 0 && !a.active[g_lo];
         if (idle_tile) continue;
 
+        const uint32_t tcut = hash32 ? (uint32_t)tmax : (uint32_t)(tmax >> 32);
+
         // ---- load + convert 64 bases per lane -------------------------------------------------
         const uint64_t lane_pos = tile_base + 64ull * lane;
         uint32_t q0, q1, q2, q3, q4, q5, v0, v1, v2;
@@ -153,7 +158,9 @@ __global__ void __launch_bounds__(SK_THREADS) sketch_hash_kernel_v2(const Sketch
                     expand_ascii<K>(chi, clo, w, tbl);
                     uint64_t h = murmur3_h1_fixed<K>(w, seed, add1, add2);
                     if (hash32) h &= 0xffffffffULL;
-                    if (h <= tmax) {
+                    // one-instruction reject on the deciding word; the exact 64-bit test only for the survivors
+                    const uint32_t hcut = hash32 ? (uint32_t)h : (uint32_t)(h >> 32);
+                    if (hcut <= tcut && h <= tmax) {
                         const int b = 16 * blk + 4 * sub + j;                    // window index within the lane's 64
                         const uint64_t vlo = ((uint64_t)v1 << 32) | v0;
                         const uint64_t vw = b ? ((vlo >> b) | ((uint64_t)v2 << (64 - b))) : vlo;

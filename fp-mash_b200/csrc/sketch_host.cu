@@ -145,7 +145,6 @@ int sketch_batch_dev_impl(fpm_ctx* ctx, const fpm_sketch_params* p, const uint8_
     if ((rc = ctx->overflow.ensure(sizeof(uint32_t) * n_groups))) return rc;
     if ((rc = ctx->stat.ensure(sizeof(uint32_t) * 4 * n_groups))) return rc;
     if ((rc = ctx->args.ensure(sizeof(SketchArgs)))) return rc;
-    if ((rc = ctx->firstpos.ensure(want_counts ? sizeof(uint64_t) * (uint64_t)n_groups * s : 8))) return rc;
     FPM_CUDA(cudaMemcpyAsync(ctx->goff.p, h_goff, sizeof(uint64_t) * (n_groups + 1), cudaMemcpyHostToDevice, st));
 
     std::vector<uint8_t> active(n_groups, 1);
@@ -197,7 +196,7 @@ int sketch_batch_dev_impl(fpm_ctx* ctx, const fpm_sketch_params* p, const uint8_
         SketchArgs a;
         memset(&a, 0, sizeof a);
         a.seq = d_seq; a.n_bytes = n_bytes; a.group_off = ctx->goff.as<uint64_t>(); a.n_groups = n_groups;
-        a.tile_list = nullptr; a.thresh = ctx->thresh.as<uint64_t>(); a.active = ctx->active.as<uint8_t>();
+        a.thresh = ctx->thresh.as<uint64_t>(); a.active = ctx->active.as<uint8_t>();
         a.tkeys = ctx->tkeys.as<uint64_t>(); a.tcnt = ctx->tcnt.as<uint32_t>(); a.tpos = ctx->tpos.as<uint64_t>();
         a.toff = ctx->toff.as<uint64_t>(); a.tmask = ctx->tmask.as<uint32_t>();
         a.maxkey_cnt = ctx->maxcnt.as<uint32_t>(); a.maxkey_pos = ctx->maxpos.as<uint64_t>();
@@ -299,7 +298,7 @@ int sketch_batch_dev_impl(fpm_ctx* ctx, const fpm_sketch_params* p, const uint8_
             SketchArgs a;
             memset(&a, 0, sizeof a);
             a.seq = d_seq; a.n_bytes = n_bytes; a.group_off = ctx->goff.as<uint64_t>(); a.n_groups = n_groups;
-            a.tile_list = nullptr; a.thresh = ctx->thresh.as<uint64_t>(); a.active = ctx->active.as<uint8_t>();
+            a.thresh = ctx->thresh.as<uint64_t>(); a.active = ctx->active.as<uint8_t>();
             a.fin_hashes = d_out_hashes; a.fin_n = d_out_n; a.tr_off = ctx->tr_off.as<uint64_t>(); a.tr_cap = d_out_counts;
             a.tr_cursor = ctx->tr_cursor.as<uint32_t>(); a.tr_pos = ctx->tr_pos.as<uint64_t>();
             a.sketch_size = s; a.seed = p->seed; a.fold_case = !p->preserve_case; a.hash32 = !p->use64;
@@ -417,6 +416,79 @@ int fpm_sketch_batch(fpm_ctx* ctx, const fpm_sketch_params* p, const uint8_t* se
     FPM_CUDA(cudaMemcpyAsync(out_n, ctx->outn.p, sizeof(uint32_t) * n_groups, cudaMemcpyDeviceToHost, ctx->stream));
     if (out_kmers) FPM_CUDA(cudaMemcpyAsync(out_kmers, ctx->outk.p, sizeof(uint64_t) * n_groups, cudaMemcpyDeviceToHost, ctx->stream));
     FPM_CUDA(cudaStreamSynchronize(ctx->stream));
+    return FPM_OK;
+}
+
+// ---- streaming input: sequence arrives in pieces, is accumulated in HBM, sketched once at the end -------
+// (read sets far larger than any pinned staging buffer: `mash sketch -r` reads everything into ONE sketch)
+
+int fpm_sketch_stream_begin(fpm_ctx* ctx)
+{
+    if (!ctx) { set_error("ctx is NULL"); return FPM_ERR_ARG; }
+    ctx->stream_used = 0;
+    ctx->stream_goff.assign(1, 0);
+    return FPM_OK;
+}
+
+int fpm_sketch_stream_append(fpm_ctx* ctx, const uint8_t* seq, uint64_t bytes)
+{
+    if (!ctx) { set_error("ctx is NULL"); return FPM_ERR_ARG; }
+    if (ctx->stream_goff.empty()) { set_error("fpm_sketch_stream_begin was not called"); return FPM_ERR_ARG; }
+    if (bytes == 0) return FPM_OK;
+    FPM_CUDA(cudaSetDevice(ctx->device));
+    if (ctx->stream_used + bytes + 64 > ctx->stream_buf.cap) {
+        // grow by doubling, keeping what is already resident
+        size_t want = std::max<size_t>(ctx->stream_buf.cap * 2, ctx->stream_used + bytes + 64);
+        want = std::max<size_t>(want, (size_t)256 << 20);
+        void* np = nullptr;
+        cudaError_t e = cudaMalloc(&np, want);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(stream buffer)", __FILE__, __LINE__);
+        if (ctx->stream_used) FPM_CUDA(cudaMemcpyAsync(np, ctx->stream_buf.p, ctx->stream_used, cudaMemcpyDeviceToDevice, ctx->stream));
+        FPM_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->stream_buf.p) cudaFree(ctx->stream_buf.p);
+        ctx->stream_buf.p = np;
+        ctx->stream_buf.cap = want;
+    }
+    FPM_CUDA(cudaMemcpyAsync((uint8_t*)ctx->stream_buf.p + ctx->stream_used, seq, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    FPM_CUDA(cudaStreamSynchronize(ctx->stream));   // the caller may reuse its staging buffer right away
+    ctx->stream_used += bytes;
+    return FPM_OK;
+}
+
+int fpm_sketch_stream_end_group(fpm_ctx* ctx)
+{
+    if (!ctx) { set_error("ctx is NULL"); return FPM_ERR_ARG; }
+    if (ctx->stream_goff.empty()) { set_error("fpm_sketch_stream_begin was not called"); return FPM_ERR_ARG; }
+    ctx->stream_goff.push_back(ctx->stream_used);
+    return FPM_OK;
+}
+
+int fpm_sketch_stream_finish(fpm_ctx* ctx, const fpm_sketch_params* p, uint64_t* out_hashes, uint32_t* out_counts, uint32_t* out_n, uint64_t* out_kmers)
+{
+    if (!ctx) { set_error("ctx is NULL"); return FPM_ERR_ARG; }
+    int rc = check_params(p);
+    if (rc) return rc;
+    if (ctx->stream_goff.empty()) { set_error("fpm_sketch_stream_begin was not called"); return FPM_ERR_ARG; }
+    if (ctx->stream_goff.back() != ctx->stream_used) { set_error("the last group was not closed with fpm_sketch_stream_end_group"); return FPM_ERR_ARG; }
+    const uint32_t n_groups = (uint32_t)ctx->stream_goff.size() - 1;
+    if (n_groups == 0) return FPM_OK;
+    FPM_CUDA(cudaSetDevice(ctx->device));
+    const uint64_t s = p->sketch_size;
+    if ((rc = ctx->outh.ensure(sizeof(uint64_t) * n_groups * s))) return rc;
+    if ((rc = ctx->outc.ensure(sizeof(uint32_t) * n_groups * s))) return rc;
+    if ((rc = ctx->outn.ensure(sizeof(uint32_t) * n_groups))) return rc;
+    if ((rc = ctx->outk.ensure(sizeof(uint64_t) * n_groups))) return rc;
+    const bool counts = p->want_counts && out_counts;
+    rc = sketch_batch_dev_impl(ctx, p, (const uint8_t*)ctx->stream_buf.p, ctx->stream_used, ctx->stream_goff.data(), n_groups,
+                               ctx->outh.as<uint64_t>(), counts ? ctx->outc.as<uint32_t>() : nullptr, ctx->outn.as<uint32_t>(),
+                               out_kmers ? ctx->outk.as<uint64_t>() : nullptr);
+    if (rc) return rc;
+    FPM_CUDA(cudaMemcpyAsync(out_hashes, ctx->outh.p, sizeof(uint64_t) * n_groups * s, cudaMemcpyDeviceToHost, ctx->stream));
+    if (counts) FPM_CUDA(cudaMemcpyAsync(out_counts, ctx->outc.p, sizeof(uint32_t) * n_groups * s, cudaMemcpyDeviceToHost, ctx->stream));
+    FPM_CUDA(cudaMemcpyAsync(out_n, ctx->outn.p, sizeof(uint32_t) * n_groups, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_kmers) FPM_CUDA(cudaMemcpyAsync(out_kmers, ctx->outk.p, sizeof(uint64_t) * n_groups, cudaMemcpyDeviceToHost, ctx->stream));
+    FPM_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->stream_goff.clear();
     return FPM_OK;
 }
 

@@ -1,6 +1,7 @@
 // sketch_kernels.cuh -- the sm_100a sketching kernels.
 //
-//   sketch_hash_kernel<K,CANON>  fused: ASCII -> 2-bit pack (+validity) -> canonical k-mer
+//   sketch_hash_kernel_v2<K,CANON> (sketch_hash_v2.cuh; this header holds its building blocks)
+//                                fused: ASCII -> 2-bit pack (+validity) -> canonical k-mer
 //                                (reverse-complement min) -> 2-bit -> ASCII re-expansion
 //                                (PRMT) -> MurmurHash3_x64_128 -> threshold filter ->
 //                                per-sketch counting hash table (global atomics).
@@ -44,7 +45,6 @@ struct SketchArgs {
     uint64_t n_bytes;
     const uint64_t* group_off;   // [n_groups+1] byte offsets
     uint32_t n_groups;
-    const uint32_t* tile_list;   // optional list of tile ids (rerun passes); NULL = identity
     // filter + tables
     const uint64_t* thresh;      // [n_groups] accept h <= thresh
     const uint8_t* active;       // [n_groups] group takes part in this pass
@@ -275,57 +275,6 @@ static __device__ __noinline__ void sketch_emit(const SketchArgs& a, uint64_t h,
         slot = (slot + 1) & mask;
     }
     atomicExch(&a.overflow[g], 1u);
-}
-
-template <int K, bool CANON>
-__global__ void __launch_bounds__(SK_THREADS) sketch_hash_kernel(const SketchArgs* __restrict__ ga, int trace)
-{
-    const SketchArgs& a = *ga;   // lives in global memory: its address is handed to the rare path
-    __shared__ uint32_t s_code[2 * SK_TILE_CHUNKS + 2];
-    __shared__ uint32_t s_valid[SK_TILE_CHUNKS + 1];
-    __shared__ uint32_t s_g[2];
-    __shared__ uint64_t s_tmax;
-
-    const uint32_t tile = a.tile_list ? a.tile_list[blockIdx.x] : blockIdx.x;
-    const uint64_t tile_base = (uint64_t)tile * SK_TILE_WINDOWS;
-
-    convert_tile(a.seq, a.n_bytes, tile_base, a.fold_case, s_code, s_valid);
-    if (threadIdx.x == 0) {
-        // groups touched by window starts of this tile, and the loosest threshold among them
-        uint64_t last = tile_base + SK_TILE_WINDOWS - 1;
-        if (last >= a.n_bytes) last = a.n_bytes - 1;
-        uint32_t g0 = find_group(a.group_off, 0, a.n_groups - 1, tile_base);
-        uint32_t g1 = find_group(a.group_off, g0, a.n_groups - 1, last);
-        uint64_t tmax = 0;
-        bool any = false;
-        for (uint32_t g = g0; g <= g1; g++)
-            if (a.active[g]) { any = true; if (a.thresh[g] > tmax) tmax = a.thresh[g]; }
-        s_g[0] = g0; s_g[1] = g1;
-        s_tmax = any ? tmax : 0;
-        if (!any) s_g[1] = 0xffffffffu;   // nothing to do in this tile
-        s_code[2 * SK_TILE_CHUNKS] = 0; s_code[2 * SK_TILE_CHUNKS + 1] = 0; s_valid[SK_TILE_CHUNKS] = 0;
-    }
-    __syncthreads();
-    const uint32_t g_lo = s_g[0], g_hi = s_g[1];
-    if (g_hi == 0xffffffffu) return;
-    const uint64_t tmax = s_tmax;
-
-#pragma unroll 1
-    for (int it = 0; it < SK_BLOCKS_PER_THREAD; it++) {
-        const int b = it * SK_THREADS + threadIdx.x;            // 16-window block within the tile
-        const uint64_t block_pos = tile_base + 16ull * b;
-        if (block_pos >= a.n_bytes) break;
-        const uint32_t fw0 = s_code[b], fw1 = s_code[b + 1], fw2 = s_code[b + 2];
-        hash_block16<K, CANON>(fw0, fw1, fw2, a.seed, a.hash32, [&](int i, uint64_t h) {
-            if (h <= tmax) {
-                // validity of window i: bases [16b+i, 16b+i+K) all in the alphabet
-                uint64_t v = ((uint64_t)s_valid[(b >> 1) + 1] << 32) | s_valid[b >> 1];
-                v >>= (16 * (b & 1) + i);
-                constexpr uint64_t km = (K == 64) ? ~0ULL : ((1ULL << K) - 1);
-                if ((v & km) == km) sketch_emit(a, h, block_pos + i, g_lo, g_hi, trace);
-            }
-        });
-    }
 }
 
 // ---------------------------------------------------------------------------------------

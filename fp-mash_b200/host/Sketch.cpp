@@ -472,15 +472,48 @@ void Sketch::initFromReads(const vector<string>& files, const Parameters& parame
 {
     parameters = parametersNew;
     checkUnsupported(parameters);
-    Batch batch;
+    // A read set becomes ONE sketch and can be far larger than a staging buffer: records are streamed to the
+    // GPU in pinned pieces (fpm_sketch_stream_*), accumulate in HBM and are sketched once at the end.
+    struct StreamSink : SeqSink {
+        uint8_t* stage = nullptr;
+        uint64_t used = 0;
+        const uint64_t kStage = 64ull << 20;
+        StreamSink() { void* p = nullptr; gpuCheck(fpm_host_alloc(kStage, &p)); stage = (uint8_t*)p; gpuCheck(fpm_sketch_stream_begin(gpuContext())); }
+        ~StreamSink() { fpm_host_free(stage); }
+        void push() { if (used) gpuCheck(fpm_sketch_stream_append(gpuContext(), stage, used)); used = 0; }
+        void addRecord(const char* s, uint64_t l) override
+        {
+            uint64_t done = 0;                                // records longer than the stage go through in pieces
+            while (done < l) {
+                if (used == kStage) push();
+                uint64_t n = min<uint64_t>(l - done, kStage - used);
+                memcpy(stage + used, s + done, n);
+                used += n; done += n;
+            }
+            if (used == kStage) push();
+            stage[used++] = 0;
+        }
+        void closeGroup(const Sketch::Reference&) override { push(); gpuCheck(fpm_sketch_stream_end_group(gpuContext())); }
+    } sink;
     Reference reference;
     uint64_t count;
     bool skipped;
-    readGroup(files, parameters, reference, count, skipped, batch);
-    batch.closeGroup(reference);
-    size_t at = references.size();
-    flushBatch(batch);
-    Reference& ref = references[at];
+    readGroup(files, parameters, reference, count, skipped, sink);
+    sink.closeGroup(reference);
+    {
+        const uint64_t s = parameters.minHashesPerWindow;
+        fpm_sketch_params sp;
+        fillSketchParams(parameters, sp, parameters.reads);
+        vector<uint64_t> hashes(s);
+        vector<uint32_t> counts(s), outn(1);
+        gpuCheck(fpm_sketch_stream_finish(gpuContext(), &sp, hashes.data(), parameters.counts ? counts.data() : nullptr, outn.data(), nullptr));
+        reference.hashesSorted.setUse64(parameters.use64);
+        reference.hashesSorted.values.assign(hashes.begin(), hashes.begin() + outn[0]);
+        if (parameters.counts) reference.counts.assign(counts.begin(), counts.begin() + outn[0]);
+        reference.countsSorted = true;
+        references.push_back(reference);
+    }
+    Reference& ref = references.back();
     // estimateSetSize / estimateMultiplicity (MinHashHeap.h:44-45)
     double setSize = 0, multiplicity = 0;
     size_t n = ref.hashesSorted.size();

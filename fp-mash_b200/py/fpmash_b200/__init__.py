@@ -16,7 +16,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "..", "lib", "libfpmash_b200.so"))
+LIB_PATH = os.environ.get("FPMASH_B200_LIB") or os.path.normpath(os.path.join(_HERE, "..", "..", "lib", "libfpmash_b200.so"))
 HEADER_PATH = os.path.normpath(os.path.join(_HERE, "..", "..", "..", "include", "fpmash_b200.h"))
 
 FPM_OK = 0
@@ -83,6 +83,10 @@ lib.fpm_ctx_launch_count.restype = C.c_uint64
 lib.fpm_ctx_launch_count.argtypes = [_VP]
 lib.fpm_sketch_batch.argtypes = [_VP, C.POINTER(SketchParams), _VP, C.c_uint64, _VP, C.c_uint32, _VP, _VP, _VP, _VP]
 lib.fpm_sketch_batch_dev.argtypes = [_VP, C.POINTER(SketchParams), _VP, C.c_uint64, _VP, C.c_uint32, _VP, _VP, _VP, _VP]
+lib.fpm_sketch_stream_begin.argtypes = [_VP]
+lib.fpm_sketch_stream_append.argtypes = [_VP, _VP, C.c_uint64]
+lib.fpm_sketch_stream_end_group.argtypes = [_VP]
+lib.fpm_sketch_stream_finish.argtypes = [_VP, C.POINTER(SketchParams), _VP, _VP, _VP, _VP]
 lib.fpm_kmer_hashes.argtypes = [_VP, C.POINTER(SketchParams), _VP, C.c_uint64, _VP, u64p]
 lib.fpm_fp_hash_batch.argtypes = [_VP, _VP, _VP, C.c_uint64, C.c_uint32, C.c_int, _VP]
 lib.fpm_cfl_fingerprint_batch.argtypes = [_VP, _VP, _VP, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, _VP, _VP, _VP, _VP]
@@ -103,6 +107,7 @@ KERNEL_SKETCH_HASH, KERNEL_SKETCH_SELECT, KERNEL_DIST_TILE, KERNEL_DIST_LITERAL,
 EXPORTED = ["fpm_abi_version", "fpm_device_count", "fpm_ctx_create", "fpm_ctx_destroy", "fpm_last_error",
             "fpm_ctx_sync", "fpm_ctx_stream", "fpm_ctx_set_stream", "fpm_host_alloc", "fpm_host_free",
             "fpm_ctx_launch_count", "fpm_sketch_batch", "fpm_sketch_batch_dev", "fpm_kmer_hashes",
+            "fpm_sketch_stream_begin", "fpm_sketch_stream_append", "fpm_sketch_stream_end_group", "fpm_sketch_stream_finish",
             "fpm_fp_hash_batch", "fpm_cfl_fingerprint_batch", "fpm_dist_tile", "fpm_dist_tile_dev", "fpm_fp_positional_tile", "fpm_pvalue", "fpm_distance",
             "fpm_measure_int32_peak", "fpm_get_int32_peaks", "fpm_ctx_set_timing", "fpm_ctx_get_timing"]
 
@@ -253,6 +258,24 @@ class Context:
                 d["kmers"] = int(r["kmers"][g])
             out.append(d)
         return out
+
+    def sketch_stream(self, groups, piece=1 << 16, **kw):
+        """Like sketch_records but through the streaming entry points, in pieces of `piece` bytes."""
+        params = make_sketch_params(**kw)
+        _check(lib.fpm_sketch_stream_begin(self._h))
+        for g in groups:
+            buf = np.frombuffer(b"".join(bytes(r) + b"\0" for r in g), dtype=np.uint8).copy() if g else np.zeros(0, dtype=np.uint8)
+            for p0 in range(0, buf.size, piece):
+                chunk = np.ascontiguousarray(buf[p0:p0 + piece])
+                _check(lib.fpm_sketch_stream_append(self._h, chunk.ctypes.data, chunk.size))
+            _check(lib.fpm_sketch_stream_end_group(self._h))
+        ng, s = len(groups), params.sketch_size
+        hashes = np.zeros((ng, s), dtype=np.uint64)
+        counts = np.zeros((ng, s), dtype=np.uint32)
+        n = np.zeros(ng, dtype=np.uint32)
+        _check(lib.fpm_sketch_stream_finish(self._h, C.byref(params), hashes.ctypes.data,
+                                            counts.ctypes.data if params.want_counts else None, n.ctypes.data, None))
+        return [dict(hashes=hashes[g, :n[g]].copy(), counts=counts[g, :n[g]].copy()) for g in range(ng)]
 
     def kmer_hashes(self, record: bytes, **kw):
         """Hash of every valid window of one record, in order (getHash parity)."""

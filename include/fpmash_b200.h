@@ -101,6 +101,16 @@ int fpm_sketch_batch_dev(fpm_ctx* ctx, const fpm_sketch_params* p,
                          const uint64_t* h_group_offsets, uint32_t n_groups,
                          uint64_t* d_out_hashes, uint32_t* d_out_counts, uint32_t* d_out_n, uint64_t* d_out_kmers);
 
+/* Streaming variant for inputs larger than any host staging buffer (`mash sketch -r` turns a whole read set
+ * into ONE sketch): begin, then append sequence pieces (same layout: records each followed by 0x00, a piece
+ * may end anywhere between records) and close each sketch with end_group; the bytes accumulate in HBM and
+ * finish() sketches all groups exactly like fpm_sketch_batch.  append() returns after its copy completed. */
+int fpm_sketch_stream_begin(fpm_ctx* ctx);
+int fpm_sketch_stream_append(fpm_ctx* ctx, const uint8_t* seq, uint64_t bytes);
+int fpm_sketch_stream_end_group(fpm_ctx* ctx);
+int fpm_sketch_stream_finish(fpm_ctx* ctx, const fpm_sketch_params* p, uint64_t* out_hashes, uint32_t* out_counts,
+                             uint32_t* out_n, uint64_t* out_kmers);
+
 /* Raw hash stream of one record (every valid window in order), for parity tests of the
  * rolling + MurmurHash3 kernel against getHash (hash.cpp:12-40).  out_hashes needs
  * seq_bytes entries; *out_count receives the number written.                               */

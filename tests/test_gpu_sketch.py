@@ -156,3 +156,16 @@ def test_sketch_sizes_beyond_shared_memory(ctx, oracle, s, n):
     for rec, out in zip(([g], [g[: n // 3]]), got):
         want = oracle.sketch(rec, k=21, s=s)
         assert np.array_equal(out["hashes"], want["hashes"]) and np.array_equal(out["counts"], want["counts"])
+
+
+def test_streaming_entry_points_match_batch(ctx, oracle):
+    """fpm_sketch_stream_*: pieces of arbitrary size (cutting records anywhere) give the batch result."""
+    rng = np.random.default_rng(77)
+    genome = random_dna(rng, 30000)
+    reads = [mutate(rng, genome[p:p + 150], 0.01) for p in rng.integers(0, len(genome) - 150, size=5000)]
+    groups = [reads, [dirty_dna(rng, 200000)], [b"ACGT"], []]
+    for piece in (1000, 1 << 16, 1 << 22):
+        got = ctx.sketch_stream(groups, piece=piece, k=21, s=500, min_cov=2, want_counts=True)
+        for g, recs in zip(got, groups):
+            want = oracle.sketch(recs, k=21, s=500, min_cov=2)
+            assert np.array_equal(g["hashes"], want["hashes"]) and np.array_equal(g["counts"], want["counts"])
