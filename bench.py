@@ -216,8 +216,9 @@ def run_reference(args):
         "unit": "Gk-mers/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total_t / len(vals), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic",
-        "config": {"workload": "mash sketch -k 21 -s 1000 over synthetic 5 Mbp genomes (BASELINE configs[1]), CPU sample",
-                   "genomes_per_step": n, "genome_len": args.genome_len, "k": K, "sketch_size": S},
+        "config": {"workload": "mash sketch -k 21 -s 1000 canonical over %d synthetic %.1f Mbp genomes per GPU (BASELINE configs[1])" % (args.genomes, args.genome_len / 1e6),
+                   "genomes_per_gpu": args.genomes, "genome_len": args.genome_len, "k": K, "sketch_size": S, "seed": 42,
+                   "cpu_sample_genomes_per_step": n},
         "cpu_baseline": {"value": value, "unit": "Gk-mers/s", "cores": threads, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": "Gk-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }

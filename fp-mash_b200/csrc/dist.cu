@@ -33,7 +33,9 @@ constexpr uint64_t DT_INF = ~0ULL;
 constexpr int DT_Q = 16;            // query columns per CTA
 constexpr int DT_R = 32;            // reference columns per CTA (two 16-column planes)
 constexpr int DT_COLS = DT_Q + DT_R;
-constexpr int DT_ROWS = 280;        // rows resident per phase (108 KB: two CTAs per SM)
+constexpr int DT_ROWS = 288;        // rows resident per phase
+constexpr int DT_PAD = 9;           // +inf rows after them: a pointer rests at most on row DT_ROWS and the unchecked blocks look 8 rows ahead
+constexpr int DT_COLROWS = DT_ROWS + DT_PAD;   // 297 rows x 48 columns x 8 B = 114.0 KB: two CTAs per SM
 constexpr int DT_THREADS = DT_Q * DT_R;   // 512
 
 struct DistArgs {
@@ -45,6 +47,11 @@ struct DistArgs {
 __device__ __forceinline__ void lds64(uint32_t addr, uint32_t& lo, uint32_t& hi)
 {
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(addr));
+}
+
+__device__ __forceinline__ void lds32(uint32_t addr, uint32_t& v)
+{
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
 }
 
 __device__ __forceinline__ void finish_pair(const DistArgs& a, uint64_t common, uint64_t denom, uint64_t len_ref, uint64_t len_qry, fpm_pair* out)
@@ -144,9 +151,10 @@ dist_tile_kernel(const uint64_t* __restrict__ pref, const uint64_t* __restrict__
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* colQ = reinterpret_cast<uint64_t*>(smem_raw);                 // [(DT_ROWS+1)][16]
-    uint64_t* colR = colQ + (DT_ROWS + 1) * 16;                             // 2 planes of [(DT_ROWS+1)][16]
+    uint64_t* colR = colQ + DT_COLROWS * 16;                             // 2 planes of [(DT_ROWS+1)][16]
     __shared__ uint32_t s_cursor[DT_COLS];
     __shared__ unsigned long long s_V;
+    __shared__ uint32_t s_need;
 
     const int t = threadIdx.x;
     const int w = t >> 5, l = t & 31, h = l >> 4, i16 = l & 15;
@@ -161,14 +169,18 @@ dist_tile_kernel(const uint64_t* __restrict__ pref, const uint64_t* __restrict__
     if (t < DT_COLS) s_cursor[t] = 0;
     uint32_t common = 0, denom = 0;
     bool done = false;
+    // rows staged per phase: no pair consumes more elements of a list than it has union steps left, so later
+    // phases (a few dozen steps for the stragglers) stage only what can still be needed
+    int R = (int)(a.s < (uint32_t)DT_ROWS ? (a.s < 32u ? 32u : a.s) : (uint32_t)DT_ROWS);
     __syncthreads();
 
     for (;;) {
         // ---- V = smallest element that does not fit this phase ------------------------
-        if (t == 0) s_V = DT_INF;
+        __syncthreads();                   // everyone has read s_need / written its cursor for this phase
+        if (t == 0) { s_V = DT_INF; s_need = 0; }
         __syncthreads();
         if (t < DT_COLS) {
-            uint64_t row = (uint64_t)s_cursor[t] + DT_ROWS;
+            uint64_t row = (uint64_t)s_cursor[t] + R;
             uint64_t v = DT_INF;
             if (t < DT_Q) { if (row < rows_qry) v = gQ[row * 16 + t]; }
             else {
@@ -179,8 +191,8 @@ dist_tile_kernel(const uint64_t* __restrict__ pref, const uint64_t* __restrict__
         }
         __syncthreads();
         const uint64_t V = s_V;
-        // ---- stage rows [cursor, cursor+DT_ROWS) of every column, masking >= V --------
-        for (int idx = t; idx < DT_ROWS * 16; idx += DT_THREADS) {
+        // ---- stage rows [cursor, cursor+R) of every column, masking >= V ----------------
+        for (int idx = t; idx < R * 16; idx += DT_THREADS) {
             int c = idx & 15, r = idx >> 4;
             uint64_t row = (uint64_t)s_cursor[c] + r;
             uint64_t v = row < rows_qry ? gQ[row * 16 + c] : DT_INF;
@@ -188,16 +200,18 @@ dist_tile_kernel(const uint64_t* __restrict__ pref, const uint64_t* __restrict__
         }
 #pragma unroll
         for (int pl = 0; pl < 2; pl++) {
-            uint64_t* dst = colR + pl * (DT_ROWS + 1) * 16;
+            uint64_t* dst = colR + pl * DT_COLROWS * 16;
             bool exists = pl == 0 || plane1_exists;
-            for (int idx = t; idx < DT_ROWS * 16; idx += DT_THREADS) {
+            for (int idx = t; idx < R * 16; idx += DT_THREADS) {
                 int c = idx & 15, r = idx >> 4;
                 uint64_t row = (uint64_t)s_cursor[DT_Q + 16 * pl + c] + r;
                 uint64_t v = (exists && row < rows_ref) ? gR[pl][row * 16 + c] : DT_INF;
                 dst[r * 16 + c] = v < V ? v : DT_INF;
             }
         }
-        if (t < 16) { colQ[DT_ROWS * 16 + t] = DT_INF; colR[DT_ROWS * 16 + t] = DT_INF; colR[(DT_ROWS + 1) * 16 + DT_ROWS * 16 + t] = DT_INF; }
+        for (int idx = t; idx < DT_PAD * 16; idx += DT_THREADS) {
+            colQ[R * 16 + idx] = DT_INF; colR[R * 16 + idx] = DT_INF; colR[DT_COLROWS * 16 + R * 16 + idx] = DT_INF;
+        }
         __syncthreads();
 
         // ---- merge up to V ------------------------------------------------------------
@@ -208,14 +222,33 @@ dist_tile_kernel(const uint64_t* __restrict__ pref, const uint64_t* __restrict__
             // 32-bit halves and shared-space byte addresses so one step is ~13 instructions.  The
             // common count is recovered from the pointers: advances(a) + advances(b) = steps + matches.
             const uint32_t pa0 = (uint32_t)__cvta_generic_to_shared(colQ + qc);
-            const uint32_t pb0 = (uint32_t)__cvta_generic_to_shared(colR + h * (DT_ROWS + 1) * 16 + rc);
+            const uint32_t pb0 = (uint32_t)__cvta_generic_to_shared(colR + h * DT_COLROWS * 16 + rc);
             uint32_t pa = pa0, pb = pb0, alo, ahi, blo, bhi;
             lds64(pa, alo, ahi);
             lds64(pb, blo, bhi);
             const uint32_t budget = a.s - denom;
             uint32_t rem = budget;
             // (pack flagged any real hash whose high word is all ones, so hi == ~0 <=> +inf)
-            while (rem != 0 && (ahi & bhi) != 0xffffffffu) {
+            for (;;) {
+                // fast block: when at least 8 steps of budget remain and neither list can run out within them
+                // (row +8 of both columns is still a real value), run 8 steps without any exit test
+                if (rem >= 8) {
+                    uint32_t a8, b8;
+                    lds32(pa + 8 * 128 + 4, a8);
+                    lds32(pb + 8 * 128 + 4, b8);
+                    if (a8 != 0xffffffffu && b8 != 0xffffffffu) {
+#pragma unroll
+                        for (int u = 0; u < 8; u++) {
+                            const uint64_t x = ((uint64_t)ahi << 32) | alo, y = ((uint64_t)bhi << 32) | blo;
+                            const bool lt = x < y, gt = y < x;
+                            if (!gt) { pa += 128; lds64(pa, alo, ahi); }
+                            if (!lt) { pb += 128; lds64(pb, blo, bhi); }
+                        }
+                        rem -= 8;
+                        continue;
+                    }
+                }
+                if (rem == 0 || (ahi & bhi) == 0xffffffffu) break;
                 const uint64_t x = ((uint64_t)ahi << 32) | alo, y = ((uint64_t)bhi << 32) | blo;
                 const bool lt = x < y, gt = y < x;
                 if (!gt) { pa += 128; lds64(pa, alo, ahi); }
@@ -226,15 +259,17 @@ dist_tile_kernel(const uint64_t* __restrict__ pref, const uint64_t* __restrict__
             denom += steps;
             common += ((pa - pa0) >> 7) + ((pb - pb0) >> 7) - steps;
             if (denom >= a.s || V == DT_INF) done = true;
+            else atomicMax(&s_need, a.s - denom);
         }
         // ---- anyone left?  then advance every column past its elements < V ------------
         if (!__syncthreads_or(done ? 0 : 1)) break;
         if (t < DT_COLS) {
-            const uint64_t* col = t < DT_Q ? colQ + t : colR + ((t - DT_Q) >> 4) * (DT_ROWS + 1) * 16 + ((t - DT_Q) & 15);
-            uint32_t lo = 0, hi = DT_ROWS;   // first row holding +inf (masked or exhausted)
+            const uint64_t* col = t < DT_Q ? colQ + t : colR + ((t - DT_Q) >> 4) * DT_COLROWS * 16 + ((t - DT_Q) & 15);
+            uint32_t lo = 0, hi = R;         // first row holding +inf (masked or exhausted)
             while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (col[mid * 16] != DT_INF) lo = mid + 1; else hi = mid; }
             s_cursor[t] += lo;
         }
+        R = (int)min((uint32_t)DT_ROWS, max(32u, s_need));
         // (the barrier at the top of the next phase orders these writes before their readers)
     }
 
@@ -295,7 +330,7 @@ static int run_dist(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* d_r
         FPM_CUDA(cudaStreamSynchronize(st));
         if (flag) fast = false;   // sentinel collision or unsorted input: literal loop defines the result
         else {
-            size_t smem = (size_t)DT_COLS * (DT_ROWS + 1) * 8;
+            size_t smem = (size_t)DT_COLS * DT_COLROWS * 8;
             FPM_CUDA(cudaFuncSetAttribute(dist_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             // query-row chunks: at most 65535 tiles per launch, and ~16M pairs per chunk when streaming to the host
             uint64_t tiles_per_chunk = 65535;
