@@ -53,6 +53,21 @@ __device__ __forceinline__ void convert32(const uint32_t (&w)[8], uint32_t fold_
     }
 }
 
+constexpr uint32_t SQ_CAP = 128;     // per-warp survivor queue (hash, position)
+constexpr uint32_t SQ_FLUSH = 24;    // flush at a tile boundary once this many are waiting
+
+// All 32 lanes insert queued survivors in parallel (one table round trip per 32 hashes).  Entries may stem
+// from earlier tiles, so the sketch is looked up over the whole group table.
+__device__ __forceinline__ void flush_survivors(const SketchArgs& a, const uint64_t* qh, const uint64_t* qp, uint32_t* qn, int lane, int trace)
+{
+    uint32_t n = *qn;
+    if (n > SQ_CAP) n = SQ_CAP;
+    for (uint32_t i = lane; i < n; i += 32) sketch_emit(a, qh[i], qp[i], 0, a.n_groups - 1, trace);
+    __syncwarp();
+    if (lane == 0) *qn = 0;
+    __syncwarp();
+}
+
 #ifndef FPM_SK_MIN_CTAS
 #define FPM_SK_MIN_CTAS 4   // 64 registers: four 256-thread CTAs (32 warps) per SM; measured best (3 -> 79 regs, 1 -> 100 regs are slower)
 #endif
@@ -70,7 +85,11 @@ __global__ void __launch_bounds__(SK_THREADS, FPM_SK_MIN_CTAS) sketch_hash_kerne
     // (read from the argument block so that ptxas cannot fold them back into immediates)
     const uint32_t tbl = a.c_tbl;
     const uint64_t add1 = a.c_add1, add2 = a.c_add2;
-    const int lane = threadIdx.x & 31;
+    __shared__ uint64_t s_qh[SK_THREADS / 32][SQ_CAP], s_qp[SK_THREADS / 32][SQ_CAP];
+    __shared__ uint32_t s_qn[SK_THREADS / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) s_qn[wid] = 0;
+    __syncwarp();
     const uint64_t warp = (uint64_t)blockIdx.x * (SK_THREADS / 32) + (threadIdx.x >> 5);
     const uint64_t n_tiles = (range_hi - range_base + WT_WINDOWS - 1) / WT_WINDOWS;
     uint64_t t0 = warp * WT_TILES_PER_WARP, t1 = t0 + WT_TILES_PER_WARP;
@@ -129,8 +148,8 @@ __global__ void __launch_bounds__(SK_THREADS, FPM_SK_MIN_CTAS) sketch_hash_kerne
         q4 = __shfl_down_sync(0xffffffffu, q0, 1);
         q5 = __shfl_down_sync(0xffffffffu, q1, 1);
         v2 = __shfl_down_sync(0xffffffffu, v0, 1);
-        const int nblk = lane == 31 ? 2 : 4;
-        if (lane_pos >= n_bytes) continue;            // (after the shuffles: no lane skips them)
+        // (no lane leaves the tile early: the survivor queue below is flushed by the whole warp)
+        const int nblk = lane_pos >= n_bytes ? 0 : (lane == 31 ? 2 : 4);
 
 #pragma unroll 1
         for (int blk = 0; blk < nblk; blk++) {
@@ -166,7 +185,13 @@ __global__ void __launch_bounds__(SK_THREADS, FPM_SK_MIN_CTAS) sketch_hash_kerne
                         const uint64_t vw = b ? ((vlo >> b) | ((uint64_t)v2 << (64 - b))) : vlo;
                         constexpr uint64_t km = (1ULL << K) - 1;
                         const uint64_t pos = lane_pos + b;
-                        if ((vw & km) == km && pos >= range_lo && pos < range_hi) sketch_emit(a, h, pos, g_lo, g_hi, trace);
+                        if ((vw & km) == km && pos >= range_lo && pos < range_hi) {
+                            // survivors are queued per warp and inserted 32 at a time: the table atomics cost a
+                            // ~1 us round trip that would otherwise stall the whole warp for one lane's hash
+                            const uint32_t qi = atomicAdd(&s_qn[wid], 1u);
+                            if (qi < SQ_CAP) { s_qh[wid][qi] = h; s_qp[wid][qi] = pos; }
+                            else sketch_emit(a, h, pos, g_lo, g_hi, trace);      // queue full (accept-all sketches)
+                        }
                     }
                 }
                 // next four windows: forward registers one byte left, reverse-complement one byte right
@@ -175,7 +200,11 @@ __global__ void __launch_bounds__(SK_THREADS, FPM_SK_MIN_CTAS) sketch_hash_kerne
             }
             q0 = q1; q1 = q2; q2 = q3; q3 = q4; q4 = q5;
         }
+        __syncwarp();
+        if (s_qn[wid] >= SQ_FLUSH) flush_survivors(a, s_qh[wid], s_qp[wid], &s_qn[wid], lane, trace);
     }
+    __syncwarp();
+    if (s_qn[wid]) flush_survivors(a, s_qh[wid], s_qp[wid], &s_qn[wid], lane, trace);
 }
 
 }  // namespace fpm

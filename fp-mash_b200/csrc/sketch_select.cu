@@ -8,7 +8,7 @@ namespace fpm {
 // Selection: one CTA per sketch.
 // ---------------------------------------------------------------------------------------
 
-__global__ void __launch_bounds__(256) sketch_select_kernel(const SelectArgs a)
+__global__ void __launch_bounds__(1024) sketch_select_kernel(const SelectArgs a)
 {
     extern __shared__ uint64_t s_keys[];
     __shared__ uint32_t s_nq, s_nd;
@@ -137,7 +137,8 @@ __global__ void fp_hash_kernel(const uint64_t* tokens, const uint64_t* line_off,
 
 void launch_sketch_select(uint32_t n_groups, size_t smem_bytes, cudaStream_t st, const SelectArgs& a)
 {
-    sketch_select_kernel<<<n_groups, 256, smem_bytes, st>>>(a);
+    // large tables (big sketch sizes) get a full 1024-thread CTA for the scan and the bitonic passes
+    sketch_select_kernel<<<n_groups, smem_bytes > 32768 ? 1024 : 256, smem_bytes, st>>>(a);
 }
 
 int configure_sketch_select(size_t max_smem_bytes)
