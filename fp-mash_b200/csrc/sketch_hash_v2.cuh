@@ -152,7 +152,8 @@ __global__ void __launch_bounds__(SK_THREADS, FPM_SK_MIN_CTAS) sketch_hash_kerne
         const int nblk = lane_pos >= n_bytes ? 0 : (lane == 31 ? 2 : 4);
 
 #pragma unroll 1
-        for (int blk = 0; blk < nblk; blk++) {
+        for (int blk = 0; blk < 4; blk++) {           // uniform trip count: the warp meets at the flush points
+            const bool live = blk < nblk;
             uint32_t fw0 = q0, fw1 = q1, fw2 = q2;
             uint32_t x[5];
             if (CANON) { x[0] = revcomp16(fw2); x[1] = revcomp16(fw1); x[2] = revcomp16(fw0); x[3] = 0; x[4] = 0; }
@@ -160,6 +161,7 @@ __global__ void __launch_bounds__(SK_THREADS, FPM_SK_MIN_CTAS) sketch_hash_kerne
             for (int sub = 0; sub < 4; sub++) {
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
+                    if (!live) break;
                     uint32_t fhi = j ? __funnelshift_l(fw1, fw0, 2 * j) : fw0;
                     uint32_t flo = j ? __funnelshift_l(fw2, fw1, 2 * j) : fw1;
                     uint32_t chi = fhi, clo = flo;
@@ -197,6 +199,9 @@ __global__ void __launch_bounds__(SK_THREADS, FPM_SK_MIN_CTAS) sketch_hash_kerne
                 // next four windows: forward registers one byte left, reverse-complement one byte right
                 fw0 = __funnelshift_l(fw1, fw0, 8); fw1 = __funnelshift_l(fw2, fw1, 8); fw2 <<= 8;
                 if (CANON) { x[2] = __funnelshift_r(x[2], x[1], 8); x[1] = __funnelshift_r(x[1], x[0], 8); x[0] >>= 8; }
+                // dense survivors (accept-all sketches of short records): insert as soon as a warp-load is waiting
+                __syncwarp();
+                if (s_qn[wid] >= 32) flush_survivors(a, s_qh[wid], s_qp[wid], &s_qn[wid], lane, trace);
             }
             q0 = q1; q1 = q2; q2 = q3; q3 = q4; q4 = q5;
         }
