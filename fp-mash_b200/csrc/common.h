@@ -46,7 +46,8 @@ struct fpm_ctx {
     uint64_t stream_used = 0;
     std::vector<uint64_t> stream_goff;
     // dist scratch
-    fpm::DevBuf d_ref, d_qry, d_rs, d_qs, d_rl, d_ql, d_out, d_misc;
+    fpm::DevBuf d_ref, d_qry, d_rs, d_qs, d_rl, d_ql, d_out, d_misc, d_p32, d_rank;
+    bool force_dist64 = false;                   // tests: run the 64-bit tile kernel although the 32-bit rank path applies
     // optional per-kernel event timing (bench roofline): pairs of events around each launch
     bool timing = false;
     struct Timed { int id; cudaEvent_t e0, e1; };

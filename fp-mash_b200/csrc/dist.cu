@@ -26,6 +26,7 @@
 #include <string.h>
 #include "common.h"
 #include "dist_math.h"
+#include "dist_rank.h"
 
 namespace fpm {
 
@@ -52,6 +53,21 @@ __device__ __forceinline__ void lds64(uint32_t addr, uint32_t& lo, uint32_t& hi)
 __device__ __forceinline__ void lds32(uint32_t addr, uint32_t& v)
 {
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+}
+
+// One step of the reference's merge loop (CommandDistance.cpp:378-386) on 32-bit ranks held in shared-memory
+// columns of 128-byte row pitch: the list(s) holding the smaller-or-equal head advance and reload.  Pinned as
+// six instructions (two compares, two predicated pointer bumps, two predicated LDS.32).
+__device__ __forceinline__ void merge_step32(uint32_t& pa, uint32_t& pb, uint32_t& av, uint32_t& bv)
+{
+    asm volatile("{\n\t.reg .pred pa_le, pb_le;\n\t"
+                 "setp.le.u32 pa_le, %2, %3;\n\t"
+                 "setp.ge.u32 pb_le, %2, %3;\n\t"
+                 "@pa_le add.u32 %0, %0, 128;\n\t"
+                 "@pb_le add.u32 %1, %1, 128;\n\t"
+                 "@pa_le ld.shared.u32 %2, [%0];\n\t"
+                 "@pb_le ld.shared.u32 %3, [%1];\n\t}"
+                 : "+r"(pa), "+r"(pb), "+r"(av), "+r"(bv));
 }
 
 __device__ __forceinline__ void finish_pair(const DistArgs& a, uint64_t common, uint64_t denom, uint64_t len_ref, uint64_t len_qry, fpm_pair* out)
@@ -298,6 +314,170 @@ dist_tile_kernel(const uint64_t* __restrict__ pref, const uint64_t* __restrict__
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// dist_tile32_kernel: the same tile algorithm on 32-bit dense ranks (dist_rank.cu).  What changes against the
+// 64-bit kernel above, each from its ncu capture (profiles/r01_dist_tile_v3.txt: shared-memory pipe 80 % busy,
+// every step two LDS.64 of two wavefronts each):
+//   * elements are 4 bytes: a step's loads are LDS.32; the 16 query columns are stored twice side by side so the
+//     32 lanes of a warp read 32 different banks (lanes l and l+16 share a query) -- one wavefront per load;
+//   * the order test is one ISETP per direction instead of a two-instruction 64-bit compare;
+//   * 432 rows per phase fit at two CTAs per SM (was 288), so same-size genomes usually finish in two phases.
+// ---------------------------------------------------------------------------------------------------------
+constexpr uint32_t D4_INF = 0xffffffffu;
+constexpr int D4_ROWS = 432;          // rows resident per phase
+constexpr int D4_UNROLL = 8;          // unchecked steps per fast block
+constexpr int D4_PAD = D4_UNROLL + 1; // +inf rows after them (a pointer rests at most on row R; the fast block looks D4_UNROLL rows ahead)
+constexpr int D4_COLROWS = D4_ROWS + D4_PAD;   // 441 rows x (32 + 32) columns x 4 B = 110.25 KB: two CTAs per SM
+
+__global__ void __launch_bounds__(DT_THREADS, 2)
+dist_tile32_kernel(const uint32_t* __restrict__ pref, const uint32_t* __restrict__ pqry, uint64_t rows_ref, uint64_t rows_qry,
+                   uint64_t n_ref, uint64_t n_qry, const uint64_t* __restrict__ len_ref, const uint64_t* __restrict__ len_qry,
+                   DistArgs a, fpm_pair* __restrict__ out, unsigned long long* steps, uint32_t q_tile0)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t* colQ = reinterpret_cast<uint32_t*>(smem_raw);               // [D4_COLROWS][32]: query columns, two copies
+    uint32_t* colR = colQ + D4_COLROWS * 32;                              // [D4_COLROWS][32]: reference columns
+    __shared__ uint32_t s_cursor[DT_COLS];
+    __shared__ uint32_t s_V;
+    __shared__ uint32_t s_need;
+
+    const int t = threadIdx.x;
+    const int w = t >> 5, l = t & 31, h = l >> 4, i16 = l & 15;
+    const int qc = i16;                              // my query column
+    const int rc = 16 * h + ((i16 + w) & 15);        // my reference column (0..31)
+    const uint64_t q_tile = blockIdx.y + q_tile0, r_tile2 = blockIdx.x;
+    const uint32_t* gQ = pqry + q_tile * rows_qry * 16;
+    const uint32_t* gR0 = pref + (2 * r_tile2) * rows_ref * 16;          // plane 1 follows at + rows_ref * 16
+    const uint64_t n_rtiles16 = (n_ref + 15) / 16;
+    const bool plane1_exists = 2 * r_tile2 + 1 < n_rtiles16;
+
+    if (t < DT_COLS) s_cursor[t] = 0;
+    uint32_t common = 0, denom = 0;
+    bool done = false;
+    int R = (int)(a.s < (uint32_t)D4_ROWS ? (a.s < 32u ? 32u : a.s) : (uint32_t)D4_ROWS);
+    __syncthreads();
+
+    for (int phase = 0;; phase++) {
+        // ---- V = smallest element that does not fit this phase ------------------------
+        __syncthreads();
+        if (t == 0) { s_V = D4_INF; s_need = 0; }
+        __syncthreads();
+        if (t < DT_COLS) {
+            uint64_t row = (uint64_t)s_cursor[t] + R;
+            uint32_t v = D4_INF;
+            if (t < DT_Q) { if (row < rows_qry) v = gQ[row * 16 + t]; }
+            else {
+                int pl = (t - DT_Q) >> 4, c = (t - DT_Q) & 15;
+                if ((pl == 0 || plane1_exists) && row < rows_ref) v = gR0[(pl * rows_ref + row) * 16 + c];
+            }
+            if (v != D4_INF) atomicMin(&s_V, v);
+        }
+        __syncthreads();
+        const uint32_t V = s_V;
+        // ---- stage rows [cursor, cursor+R) of every column, masking >= V ----------------
+        if (phase == 0) {
+            // all cursors are 0: rows are contiguous 64-byte lines, moved as 16-byte vectors
+            for (int idx = t; idx < R * 4; idx += DT_THREADS) {
+                const int r = idx >> 2, c4 = (idx & 3) * 4;
+                uint4 v = make_uint4(D4_INF, D4_INF, D4_INF, D4_INF);
+                if ((uint64_t)r < rows_qry) v = *reinterpret_cast<const uint4*>(gQ + r * 16 + c4);
+                v.x = v.x < V ? v.x : D4_INF; v.y = v.y < V ? v.y : D4_INF; v.z = v.z < V ? v.z : D4_INF; v.w = v.w < V ? v.w : D4_INF;
+                *reinterpret_cast<uint4*>(colQ + r * 32 + c4) = v;
+                *reinterpret_cast<uint4*>(colQ + r * 32 + 16 + c4) = v;
+            }
+            for (int idx = t; idx < R * 8; idx += DT_THREADS) {
+                const int r = idx >> 3, c4 = (idx & 7) * 4, pl = c4 >> 4;
+                uint4 v = make_uint4(D4_INF, D4_INF, D4_INF, D4_INF);
+                if ((pl == 0 || plane1_exists) && (uint64_t)r < rows_ref) v = *reinterpret_cast<const uint4*>(gR0 + (pl * rows_ref + r) * 16 + (c4 & 15));
+                v.x = v.x < V ? v.x : D4_INF; v.y = v.y < V ? v.y : D4_INF; v.z = v.z < V ? v.z : D4_INF; v.w = v.w < V ? v.w : D4_INF;
+                *reinterpret_cast<uint4*>(colR + r * 32 + c4) = v;
+            }
+        } else {
+            for (int idx = t; idx < R * 16; idx += DT_THREADS) {
+                int c = idx & 15, r = idx >> 4;
+                uint64_t row = (uint64_t)s_cursor[c] + r;
+                uint32_t v = row < rows_qry ? gQ[row * 16 + c] : D4_INF;
+                v = v < V ? v : D4_INF;
+                colQ[r * 32 + c] = v;
+                colQ[r * 32 + 16 + c] = v;
+            }
+            for (int idx = t; idx < R * 32; idx += DT_THREADS) {
+                int c = idx & 31, r = idx >> 5, pl = c >> 4;
+                bool exists = pl == 0 || plane1_exists;
+                uint64_t row = (uint64_t)s_cursor[DT_Q + c] + r;
+                uint32_t v = (exists && row < rows_ref) ? gR0[(pl * rows_ref + row) * 16 + (c & 15)] : D4_INF;
+                colR[r * 32 + c] = v < V ? v : D4_INF;
+            }
+        }
+        for (int idx = t; idx < D4_PAD * 32; idx += DT_THREADS) { colQ[R * 32 + idx] = D4_INF; colR[R * 32 + idx] = D4_INF; }
+        __syncthreads();
+
+        // ---- merge up to V ------------------------------------------------------------
+        if (!done) {
+            // the reference loop (CommandDistance.cpp:376-400) exactly as in the 64-bit kernel: an exhausted or
+            // phase-masked list reads +inf; matches are recovered from the pointer advances
+            const uint32_t pa0 = (uint32_t)__cvta_generic_to_shared(colQ + l);
+            const uint32_t pb0 = (uint32_t)__cvta_generic_to_shared(colR + rc);
+            uint32_t pa = pa0, pb = pb0, av, bv;
+            lds32(pa, av);
+            lds32(pb, bv);
+            const uint32_t budget = a.s - denom;
+            uint32_t rem = budget;
+            for (;;) {
+                if (rem >= (uint32_t)D4_UNROLL) {
+                    uint32_t a8, b8;
+                    lds32(pa + D4_UNROLL * 128, a8);
+                    lds32(pb + D4_UNROLL * 128, b8);
+                    if (a8 != D4_INF && b8 != D4_INF) {
+#pragma unroll
+                        for (int u = 0; u < D4_UNROLL; u++) merge_step32(pa, pb, av, bv);
+                        rem -= D4_UNROLL;
+                        continue;
+                    }
+                }
+                if (rem == 0 || (av & bv) == D4_INF) break;
+                merge_step32(pa, pb, av, bv);
+                rem--;
+            }
+            const uint32_t nsteps = budget - rem;
+            denom += nsteps;
+            common += ((pa - pa0) >> 7) + ((pb - pb0) >> 7) - nsteps;
+            if (denom >= a.s || V == D4_INF) done = true;
+            else atomicMax(&s_need, a.s - denom);
+        }
+        // ---- anyone left?  then advance every column past its elements < V ------------
+        if (!__syncthreads_or(done ? 0 : 1)) break;
+        if (t < DT_COLS) {
+            const uint32_t* col = t < DT_Q ? colQ + t : colR + (t - DT_Q);
+            uint32_t lo = 0, hi = R;         // first row holding +inf (masked or exhausted)
+            while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (col[mid * 32] != D4_INF) lo = mid + 1; else hi = mid; }
+            s_cursor[t] += lo;
+        }
+        R = (int)min((uint32_t)D4_ROWS, max(32u, s_need));
+    }
+
+    // ---- results: stage in shared memory, then coalesced row writes ---------------------
+    __syncthreads();
+    fpm_pair* res = reinterpret_cast<fpm_pair*>(smem_raw);                  // [16][32]
+    const uint64_t qg = q_tile * 16 + qc, rg = r_tile2 * 32 + rc;
+    unsigned long long my_steps = denom;
+    if (qg < n_qry && rg < n_ref) finish_pair(a, common, denom, len_ref[rg], len_qry[qg], &res[qc * 32 + rc]);
+    __syncthreads();
+    {
+        const uint64_t* src = reinterpret_cast<const uint64_t*>(res);
+        for (int idx = t; idx < 16 * 32 * 3; idx += DT_THREADS) {
+            int row = idx / 96, wd = idx % 96, pr = wd / 3;
+            uint64_t qg2 = q_tile * 16 + row, rg2 = r_tile2 * 32 + pr;
+            if (qg2 < n_qry && rg2 < n_ref)
+                reinterpret_cast<uint64_t*>(out + qg2 * n_ref + rg2)[wd % 3] = src[idx];
+        }
+    }
+    if (steps) {
+        for (int o = 16; o; o >>= 1) my_steps += __shfl_down_sync(0xffffffffu, my_steps, o);
+        if (l == 0 && my_steps) atomicAdd(steps, my_steps);
+    }
+}
+
 // h_out (nullable): host destination.  When given, the fast path runs in query-row chunks and copies chunk c
 // back on a second stream while chunk c+1 is being compared, then waits for all copies.
 static int run_dist(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* d_ref, const fpm_panel* d_qry, fpm_pair* d_out,
@@ -312,26 +492,35 @@ static int run_dist(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* d_r
     bool fast = p->sorted_unique != 0;
     if (fast) {
         int rc;
-        uint64_t rows_r = (uint64_t)max_size_ref + 1, rows_q = (uint64_t)max_size_qry + 1;
-        uint64_t nr16 = (d_ref->n + 15) / 16, nq16 = (d_qry->n + 15) / 16;
-        if ((rc = ctx->d_ref.ensure(nr16 * 16 * rows_r * 8))) return rc;
-        if ((rc = ctx->d_qry.ensure(nq16 * 16 * rows_q * 8))) return rc;
-        if ((rc = ctx->d_misc.ensure(64))) return rc;
-        FPM_CUDA(cudaMemsetAsync(ctx->d_misc.p, 0, 64, st));
-        uint64_t n1 = nr16 * 16 * rows_r, n2 = nq16 * 16 * rows_q;
-        ctx->time_begin(FPM_KERNEL_DIST_PACK);
-        dist_pack_kernel<<<(uint32_t)((n1 + 255) / 256), 256, 0, st>>>(*d_ref, rows_r, ctx->d_ref.as<uint64_t>(), ctx->d_misc.as<uint32_t>());
-        dist_pack_kernel<<<(uint32_t)((n2 + 255) / 256), 256, 0, st>>>(*d_qry, rows_q, ctx->d_qry.as<uint64_t>(), ctx->d_misc.as<uint32_t>());
-        ctx->time_end();
-        ctx->launches += 2;
-        FPM_CUDA(cudaGetLastError());
-        uint32_t flag = 0;
-        FPM_CUDA(cudaMemcpyAsync(&flag, ctx->d_misc.p, 4, cudaMemcpyDeviceToHost, st));
-        FPM_CUDA(cudaStreamSynchronize(st));
-        if (flag) fast = false;   // sentinel collision or unsorted input: literal loop defines the result
-        else {
-            size_t smem = (size_t)DT_COLS * DT_COLROWS * 8;
-            FPM_CUDA(cudaFuncSetAttribute(dist_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const uint64_t rows_r = (uint64_t)max_size_ref + 1, rows_q = (uint64_t)max_size_qry + 1;
+        const uint64_t nr16 = (d_ref->n + 15) / 16, nq16 = (d_qry->n + 15) / 16;
+        // preferred: 32-bit dense ranks (dist_rank.cu); panels too large for 32-bit indices keep the 64-bit kernel
+        uint32_t *p32r = nullptr, *p32q = nullptr;
+        int mode = DIST_RANK_TOO_BIG;
+        if (!ctx->force_dist64 && (rc = dist_rank_panels(ctx, d_ref, d_qry, max_size_ref, max_size_qry, rows_r, rows_q, &p32r, &p32q, &mode))) return rc;
+        if (mode == DIST_RANK_UNSORTED) fast = false;
+        if (mode == DIST_RANK_TOO_BIG) {
+            if ((rc = ctx->d_ref.ensure(nr16 * 16 * rows_r * 8))) return rc;
+            if ((rc = ctx->d_qry.ensure(nq16 * 16 * rows_q * 8))) return rc;
+            if ((rc = ctx->d_misc.ensure(64))) return rc;
+            FPM_CUDA(cudaMemsetAsync(ctx->d_misc.p, 0, 64, st));
+            uint64_t n1 = nr16 * 16 * rows_r, n2 = nq16 * 16 * rows_q;
+            ctx->time_begin(FPM_KERNEL_DIST_PACK);
+            dist_pack_kernel<<<(uint32_t)((n1 + 255) / 256), 256, 0, st>>>(*d_ref, rows_r, ctx->d_ref.as<uint64_t>(), ctx->d_misc.as<uint32_t>());
+            dist_pack_kernel<<<(uint32_t)((n2 + 255) / 256), 256, 0, st>>>(*d_qry, rows_q, ctx->d_qry.as<uint64_t>(), ctx->d_misc.as<uint32_t>());
+            ctx->time_end();
+            ctx->launches += 2;
+            FPM_CUDA(cudaGetLastError());
+            uint32_t flag = 0;
+            FPM_CUDA(cudaMemcpyAsync(&flag, ctx->d_misc.p, 4, cudaMemcpyDeviceToHost, st));
+            FPM_CUDA(cudaStreamSynchronize(st));
+            if (flag) fast = false;   // sentinel collision or unsorted input: literal loop defines the result
+        }
+        if (fast) {
+            const bool k32 = mode == DIST_RANK_OK;
+            const size_t smem = k32 ? (size_t)64 * D4_COLROWS * 4 : (size_t)DT_COLS * DT_COLROWS * 8;
+            if (k32) FPM_CUDA(cudaFuncSetAttribute(dist_tile32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            else FPM_CUDA(cudaFuncSetAttribute(dist_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             // query-row chunks: at most 65535 tiles per launch, and ~16M pairs per chunk when streaming to the host
             uint64_t tiles_per_chunk = 65535;
             if (h_out) tiles_per_chunk = std::max<uint64_t>(1, std::min<uint64_t>(65535, (16ull << 20) / (16 * std::max<uint64_t>(d_ref->n, 1))));
@@ -345,8 +534,12 @@ static int run_dist(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* d_r
                 const uint64_t nt = std::min(tiles_per_chunk, nq16 - t0);
                 dim3 grid((uint32_t)((d_ref->n + 31) / 32), (uint32_t)nt);
                 ctx->time_begin(FPM_KERNEL_DIST_TILE);
-                dist_tile_kernel<<<grid, DT_THREADS, smem, st>>>(ctx->d_ref.as<uint64_t>(), ctx->d_qry.as<uint64_t>(), rows_r, rows_q, d_ref->n,
-                                                                 d_qry->n, d_ref->lengths, d_qry->lengths, a, d_out, (unsigned long long*)d_steps, (uint32_t)t0);
+                if (k32)
+                    dist_tile32_kernel<<<grid, DT_THREADS, smem, st>>>(p32r, p32q, rows_r, rows_q, d_ref->n, d_qry->n, d_ref->lengths, d_qry->lengths, a,
+                                                                       d_out, (unsigned long long*)d_steps, (uint32_t)t0);
+                else
+                    dist_tile_kernel<<<grid, DT_THREADS, smem, st>>>(ctx->d_ref.as<uint64_t>(), ctx->d_qry.as<uint64_t>(), rows_r, rows_q, d_ref->n,
+                                                                     d_qry->n, d_ref->lengths, d_qry->lengths, a, d_out, (unsigned long long*)d_steps, (uint32_t)t0);
                 ctx->time_end();
                 ctx->launches++;
                 FPM_CUDA(cudaGetLastError());

@@ -1,0 +1,111 @@
+// dist_rank.cu -- order-preserving 32-bit compression of the sketch panels for dist_tile32_kernel.
+//
+// compareSketches (CommandDistance.cpp:365-400) looks only at the ORDER and EQUALITY of the hashes of the two
+// lists, never at their values.  So the 64-bit hashes of both panels are replaced by their dense rank in the
+// sorted set of all distinct hashes of the call (equal hashes -> equal rank, h1 < h2 -> rank1 < rank2): exact,
+// and a merge step then costs one 32-bit shared-memory load and one 32-bit compare per list instead of a 64-bit
+// load (two shared-memory wavefronts) and a two-instruction compare.  0xffffffff is the +inf sentinel.
+//
+// Steps (all on the caller's stream):
+//   dist_keys_kernel     every valid element -> (hash, destination index in the packed 32-bit tile layout);
+//                        also validates "strictly ascending" (the fast path's precondition)
+//   cub radix sort       by hash (library call, like the scan below: preprocessing, ~5 % of a dist step)
+//   cub inclusive scan   of "differs from predecessor" = dense rank
+//   dist_scatter_kernel  rank -> packed[destination]
+#include <cub/cub.cuh>
+#include "common.h"
+#include "dist_rank.h"
+
+namespace fpm {
+
+// keys/dst are indexed by out_base + idx, idx over n * max_size (sketch-major)
+__global__ void __launch_bounds__(256) dist_keys_kernel(fpm_panel pn, uint32_t max_size, uint64_t rows, uint32_t dst_base, uint64_t out_base,
+                                                        uint64_t* __restrict__ keys, uint32_t* __restrict__ dst, uint32_t* flags)
+{
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= pn.n * max_size) return;
+    const uint64_t sk = idx / max_size, row = idx % max_size;
+    uint64_t v = ~0ULL;
+    if (row < pn.sizes[sk]) {
+        v = pn.hashes[sk * pn.stride + row];
+        bool bad = v == ~0ULL;                                            // reserved: sorts with the invalid slots
+        if (row > 0 && pn.hashes[sk * pn.stride + row - 1] >= v) bad = true;   // not strictly ascending
+        if (bad) atomicOr(flags, 1u);
+    }
+    keys[out_base + idx] = v;
+    dst[out_base + idx] = dst_base + (uint32_t)(((sk >> 4) * rows + row) * 16 + (sk & 15));
+}
+
+struct HeadFlag {
+    const uint64_t* keys;
+    __host__ __device__ uint32_t operator()(uint64_t i) const { return i > 0 && keys[i] != keys[i - 1] ? 1u : 0u; }
+};
+
+__global__ void __launch_bounds__(256) dist_scatter_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ dst,
+                                                           const uint32_t* __restrict__ rank, uint64_t m, uint32_t* __restrict__ packed)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    if (keys[i] != ~0ULL) packed[dst[i]] = rank[i];
+}
+
+int dist_rank_panels(fpm_ctx* ctx, const fpm_panel* d_ref, const fpm_panel* d_qry, uint32_t max_size_ref, uint32_t max_size_qry,
+                     uint64_t rows_r, uint64_t rows_q, uint32_t** packed_ref, uint32_t** packed_qry, int* mode)
+{
+    cudaStream_t st = ctx->stream;
+    *mode = DIST_RANK_TOO_BIG;
+    const uint64_t nr16 = (d_ref->n + 15) / 16, nq16 = (d_qry->n + 15) / 16;
+    const uint64_t pr = nr16 * 16 * rows_r, pq = nq16 * 16 * rows_q;      // packed elements
+    const uint64_t mr = d_ref->n * (uint64_t)max_size_ref, mq = d_qry->n * (uint64_t)max_size_qry, m = mr + mq;
+    if (pr + pq >= 0xffffffffull || m >= 0x7fffffffull) return FPM_OK;    // ranks / indices would not fit: 64-bit path
+    int rc;
+    if ((rc = ctx->d_p32.ensure((pr + pq) * 4))) return rc;
+    if ((rc = ctx->d_misc.ensure(64))) return rc;
+    uint32_t* packed = ctx->d_p32.as<uint32_t>();
+    *packed_ref = packed;
+    *packed_qry = packed + pr;
+    FPM_CUDA(cudaMemsetAsync(packed, 0xff, (pr + pq) * 4, st));
+    FPM_CUDA(cudaMemsetAsync(ctx->d_misc.p, 0, 64, st));
+    if (m == 0) { *mode = DIST_RANK_OK; return FPM_OK; }
+
+    size_t sort_tmp = 0, scan_tmp = 0;
+    cub::DoubleBuffer<uint64_t> kb(nullptr, nullptr);
+    cub::DoubleBuffer<uint32_t> vb(nullptr, nullptr);
+    FPM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, kb, vb, (int64_t)m, 0, 64, st));
+    HeadFlag hf{nullptr};
+    cub::CountingInputIterator<uint64_t> cnt(0);
+    cub::TransformInputIterator<uint32_t, HeadFlag, cub::CountingInputIterator<uint64_t>> it0(cnt, hf);
+    FPM_CUDA(cub::DeviceScan::InclusiveSum(nullptr, scan_tmp, it0, (uint32_t*)nullptr, (int64_t)m, st));
+    const size_t tmp = std::max(sort_tmp, scan_tmp);
+    // one scratch block: keys x2 | dst x2 | cub temp (the rank array reuses the spare key buffer)
+    const size_t ka = (m * 8 + 255) & ~(size_t)255, va = (m * 4 + 255) & ~(size_t)255;
+    if ((rc = ctx->d_rank.ensure(2 * ka + 2 * va + tmp + 256))) return rc;
+    unsigned char* base = ctx->d_rank.as<unsigned char>();
+    uint64_t* k0 = (uint64_t*)base; uint64_t* k1 = (uint64_t*)(base + ka);
+    uint32_t* v0 = (uint32_t*)(base + 2 * ka); uint32_t* v1 = (uint32_t*)(base + 2 * ka + va);
+    void* d_tmp = base + 2 * ka + 2 * va;
+
+    ctx->time_begin(FPM_KERNEL_DIST_PACK);
+    if (mr) dist_keys_kernel<<<(uint32_t)((mr + 255) / 256), 256, 0, st>>>(*d_ref, max_size_ref, rows_r, 0u, 0, k0, v0, ctx->d_misc.as<uint32_t>());
+    if (mq) dist_keys_kernel<<<(uint32_t)((mq + 255) / 256), 256, 0, st>>>(*d_qry, max_size_qry, rows_q, (uint32_t)pr, mr, k0, v0, ctx->d_misc.as<uint32_t>());
+    FPM_CUDA(cudaGetLastError());
+    kb = cub::DoubleBuffer<uint64_t>(k0, k1);
+    vb = cub::DoubleBuffer<uint32_t>(v0, v1);
+    FPM_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, sort_tmp, kb, vb, (int64_t)m, 0, 64, st));
+    const uint64_t* ks = kb.Current();
+    uint32_t* rank = (uint32_t*)kb.Alternate();
+    hf.keys = ks;
+    cub::TransformInputIterator<uint32_t, HeadFlag, cub::CountingInputIterator<uint64_t>> it(cnt, hf);
+    FPM_CUDA(cub::DeviceScan::InclusiveSum(d_tmp, scan_tmp, it, rank, (int64_t)m, st));
+    dist_scatter_kernel<<<(uint32_t)((m + 255) / 256), 256, 0, st>>>(ks, vb.Current(), rank, m, packed);
+    ctx->time_end();
+    ctx->launches += 3 + (mr ? 1 : 0) + (mq ? 1 : 0);
+    FPM_CUDA(cudaGetLastError());
+    uint32_t flag = 0;
+    FPM_CUDA(cudaMemcpyAsync(&flag, ctx->d_misc.p, 4, cudaMemcpyDeviceToHost, st));
+    FPM_CUDA(cudaStreamSynchronize(st));
+    *mode = flag == 0 ? DIST_RANK_OK : DIST_RANK_UNSORTED;     // unsorted input or a hash equal to 2^64-1: the literal kernel defines the result
+    return FPM_OK;
+}
+
+}  // namespace fpm

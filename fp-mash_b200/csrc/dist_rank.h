@@ -1,0 +1,14 @@
+// dist_rank.h -- see dist_rank.cu
+#pragma once
+#include "common.h"
+
+namespace fpm {
+
+// Fills ctx->d_p32 with both panels as column tiles [ceil(n/16)][rows][16] of 32-bit dense ranks (0xffffffff
+// beyond each sketch's size).  *mode says whether the rank path can be used: not with more than 2^31 elements (the
+// caller then runs the 64-bit tile kernel) or with input that is not strictly ascending (literal kernel).
+enum { DIST_RANK_OK = 0, DIST_RANK_TOO_BIG = 1, DIST_RANK_UNSORTED = 2 };
+int dist_rank_panels(fpm_ctx* ctx, const fpm_panel* d_ref, const fpm_panel* d_qry, uint32_t max_size_ref, uint32_t max_size_qry,
+                     uint64_t rows_r, uint64_t rows_q, uint32_t** packed_ref, uint32_t** packed_qry, int* mode);
+
+}  // namespace fpm

@@ -100,6 +100,7 @@ lib.fpm_distance.argtypes = [C.c_uint64, C.c_uint64, C.c_int]
 lib.fpm_measure_int32_peak.argtypes = [_VP, C.POINTER(C.c_double)]
 lib.fpm_get_int32_peaks.argtypes = [_VP, C.POINTER(C.c_double)]
 lib.fpm_ctx_set_timing.argtypes = [_VP, C.c_int]
+lib.fpm_ctx_set_dist_mode.argtypes = [_VP, C.c_int]
 lib.fpm_ctx_get_timing.argtypes = [_VP, C.c_int, C.POINTER(C.c_double), u64p]
 
 KERNEL_SKETCH_HASH, KERNEL_SKETCH_SELECT, KERNEL_DIST_TILE, KERNEL_DIST_LITERAL, KERNEL_DIST_PACK = range(5)
@@ -109,7 +110,7 @@ EXPORTED = ["fpm_abi_version", "fpm_device_count", "fpm_ctx_create", "fpm_ctx_de
             "fpm_ctx_launch_count", "fpm_sketch_batch", "fpm_sketch_batch_dev", "fpm_kmer_hashes",
             "fpm_sketch_stream_begin", "fpm_sketch_stream_append", "fpm_sketch_stream_end_group", "fpm_sketch_stream_finish",
             "fpm_fp_hash_batch", "fpm_cfl_fingerprint_batch", "fpm_dist_tile", "fpm_dist_tile_dev", "fpm_fp_positional_tile", "fpm_pvalue", "fpm_distance",
-            "fpm_measure_int32_peak", "fpm_get_int32_peaks", "fpm_ctx_set_timing", "fpm_ctx_get_timing"]
+            "fpm_measure_int32_peak", "fpm_get_int32_peaks", "fpm_ctx_set_timing", "fpm_ctx_get_timing", "fpm_ctx_set_dist_mode"]
 
 
 def _check(rc):
@@ -196,6 +197,10 @@ class Context:
 
     def launch_count(self):
         return int(lib.fpm_ctx_launch_count(self._h))
+
+    def set_dist_mode(self, force64=False):
+        """force64=True: run the 64-bit tile kernel even where the 32-bit rank kernel applies."""
+        _check(lib.fpm_ctx_set_dist_mode(self._h, 1 if force64 else 0))
 
     def set_timing(self, enable=True):
         _check(lib.fpm_ctx_set_timing(self._h, int(enable)))

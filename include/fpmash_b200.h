@@ -182,6 +182,13 @@ int fpm_dist_tile_dev(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* d
  * tail at `matches`.  Only max_distance / max_pvalue of *p are used.  Same output layout as fpm_dist_tile. */
 int fpm_fp_positional_tile(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* ref, const fpm_panel* qry, fpm_pair* out);
 
+/* Which tile kernel fpm_dist_tile[_dev] uses for ascending duplicate-free panels.
+ * FPM_DIST_AUTO (default): 32-bit dense-rank kernel whenever both panels together hold fewer than 2^31
+ * hashes, else the 64-bit kernel.  FPM_DIST_FORCE64: always the 64-bit kernel (tests compare the two). */
+#define FPM_DIST_AUTO 0
+#define FPM_DIST_FORCE64 1
+int fpm_ctx_set_dist_mode(fpm_ctx* ctx, int mode);
+
 /* Scalar helpers exported for host code and tests (same code the kernels run).             */
 double fpm_pvalue(uint64_t x, uint64_t len_ref, uint64_t len_qry, double kmer_space, uint64_t n);
 double fpm_distance(uint64_t common, uint64_t denom, int kmer_size);
@@ -192,9 +199,9 @@ double fpm_distance(uint64_t common, uint64_t denom, int kmer_size);
  * the named kernel).  Off by default; enabling resets the accumulators.                        */
 #define FPM_KERNEL_SKETCH_HASH 0   /* sketch_hash_kernel (pack + canonical roll + Murmur + filter) */
 #define FPM_KERNEL_SKETCH_SELECT 1 /* sketch_select_kernel                                         */
-#define FPM_KERNEL_DIST_TILE 2     /* dist_tile_kernel                                             */
+#define FPM_KERNEL_DIST_TILE 2     /* dist_tile32_kernel / dist_tile_kernel                        */
 #define FPM_KERNEL_DIST_LITERAL 3  /* dist_literal_kernel                                          */
-#define FPM_KERNEL_DIST_PACK 4     /* dist_pack_kernel                                             */
+#define FPM_KERNEL_DIST_PACK 4     /* dist_pack_kernel, or the rank pre-pass (keys, sort, scan, scatter) */
 int fpm_ctx_set_timing(fpm_ctx* ctx, int enable);
 int fpm_ctx_get_timing(fpm_ctx* ctx, int kernel_id, double* out_ms_total, uint64_t* out_launches);
 

@@ -10,6 +10,14 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-12
 
 
+@pytest.fixture(params=["rank32", "u64"])
+def dctx(ctx, request):
+    """The context with the tile kernel pinned: 32-bit dense ranks (default) or the 64-bit kernel."""
+    ctx.set_dist_mode(force64=request.param == "u64")
+    yield ctx
+    ctx.set_dist_mode(force64=False)
+
+
 def _oracle_matrix(oracle, ref, qry, s, k, kmer_space, max_d=1.0, max_p=1.0):
     rh, rs, rl = ref
     qh, qs, ql = qry
@@ -37,29 +45,29 @@ def _compare(got, passed, want):
 
 
 @pytest.mark.parametrize("s,n_ref,n_qry", [(1000, 37, 21), (1000, 64, 16), (100, 33, 50), (2500, 20, 9)])
-def test_dist_sorted_panels(ctx, oracle, s, n_ref, n_qry):
+def test_dist_sorted_panels(dctx, oracle, s, n_ref, n_qry):
     rng = np.random.default_rng(s + n_ref)
     rh, rs = sorted_sketch_panel(rng, n_ref, s)
     qh, qs = sorted_sketch_panel(rng, n_qry, s)
     qh[:3] = rh[:3]; qs[:3] = rs[:3]          # identical sketches: distance 0, 1000/1000
     rl = rng.integers(1000, 6_000_000, size=n_ref).astype(np.uint64)
     ql = rng.integers(1000, 6_000_000, size=n_qry).astype(np.uint64)
-    got, passed = ctx.dist_tile((rh, rs, rl), (qh, qs, ql), s, 21, 4.0 ** 21)
+    got, passed = dctx.dist_tile((rh, rs, rl), (qh, qs, ql), s, 21, 4.0 ** 21)
     _compare(got, passed, _oracle_matrix(oracle, (rh, rs, rl), (qh, qs, ql), s, 21, 4.0 ** 21))
 
 
-def test_dist_thresholds_and_sketch_size_mismatch(ctx, oracle):
+def test_dist_thresholds_and_sketch_size_mismatch(dctx, oracle):
     rng = np.random.default_rng(77)
     rh, rs = sorted_sketch_panel(rng, 40, 1000, shared=0.8)
     qh, qs = sorted_sketch_panel(rng, 24, 1000, shared=0.8)
     rl = np.full(40, 4_600_000, dtype=np.uint64)
     ql = np.full(24, 5_100_000, dtype=np.uint64)
     # compare at s=400 although the lists hold up to 1000 hashes (CommandDistance.cpp:342-344)
-    got, passed = ctx.dist_tile((rh, rs, rl), (qh, qs, ql), 400, 21, 4.0 ** 21, max_distance=0.2, max_pvalue=1e-5)
+    got, passed = dctx.dist_tile((rh, rs, rl), (qh, qs, ql), 400, 21, 4.0 ** 21, max_distance=0.2, max_pvalue=1e-5)
     _compare(got, passed, _oracle_matrix(oracle, (rh, rs, rl), (qh, qs, ql), 400, 21, 4.0 ** 21, 0.2, 1e-5))
 
 
-def test_dist_heterogeneous_densities_multi_phase(ctx, oracle):
+def test_dist_heterogeneous_densities_multi_phase(dctx, oracle):
     # sketches whose hash densities differ 50x force several value-bounded phases
     rng = np.random.default_rng(5)
     s = 1500
@@ -71,7 +79,7 @@ def test_dist_heterogeneous_densities_multi_phase(ctx, oracle):
     for i, r in enumerate(rows):
         h[i, :len(r)] = r; sz[i] = len(r)
     ln = np.full(48, 3_000_000, dtype=np.uint64)
-    got, passed = ctx.dist_tile((h, sz, ln), (h[:20], sz[:20], ln[:20]), s, 21, 4.0 ** 21)
+    got, passed = dctx.dist_tile((h, sz, ln), (h[:20], sz[:20], ln[:20]), s, 21, 4.0 ** 21)
     _compare(got, passed, _oracle_matrix(oracle, (h, sz, ln), (h[:20], sz[:20], ln[:20]), s, 21, 4.0 ** 21))
 
 
@@ -89,15 +97,15 @@ def test_dist_literal_unsorted_fp_lists(ctx, oracle):
     assert np.array_equal(got2, got) and np.array_equal(passed2, passed)
 
 
-def test_dist_empty_sketches(ctx, oracle):
+def test_dist_empty_sketches(dctx, oracle):
     h = np.zeros((3, 10), dtype=np.uint64); h[1, :4] = [5, 9, 11, 40]; h[2, :2] = [9, 40]
     sz = np.array([0, 4, 2], dtype=np.uint32)
     ln = np.array([100, 200, 300], dtype=np.uint64)
-    got, passed = ctx.dist_tile((h, sz, ln), (h, sz, ln), 10, 21, 4.0 ** 21)
+    got, passed = dctx.dist_tile((h, sz, ln), (h, sz, ln), 10, 21, 4.0 ** 21)
     _compare(got, passed, _oracle_matrix(oracle, (h, sz, ln), (h, sz, ln), 10, 21, 4.0 ** 21))
 
 
-def test_dist_large_sketches_many_phases(ctx, oracle):
+def test_dist_large_sketches_many_phases(dctx, oracle):
     """s = 10000 (config 5's shape): every pair needs dozens of value-bounded phases."""
     rng = np.random.default_rng(10)
     s = 10000
@@ -105,7 +113,7 @@ def test_dist_large_sketches_many_phases(ctx, oracle):
     qh, qs = sorted_sketch_panel(rng, 9, s, n_clusters=3, shared=0.7)
     qh[0] = rh[0]; qs[0] = rs[0]
     rl = np.full(20, 5_000_000, dtype=np.uint64); ql = np.full(9, 4_000_000, dtype=np.uint64)
-    got, passed = ctx.dist_tile((rh, rs, rl), (qh, qs, ql), s, 32, 4.0 ** 32)
+    got, passed = dctx.dist_tile((rh, rs, rl), (qh, qs, ql), s, 32, 4.0 ** 32)
     _compare(got, passed, _oracle_matrix(oracle, (rh, rs, rl), (qh, qs, ql), s, 32, 4.0 ** 32))
 
 
@@ -122,3 +130,23 @@ def test_dist_full_size_properties(ctx):
     assert (got["numer"] <= got["denom"]).all() and passed.all()
     same = (np.arange(n)[:, None] % 20) == (np.arange(n)[None, :] % 20)
     assert got["numer"][same].min() > 100 and got["numer"][~same].max() < 10
+
+
+def test_dist_rank32_equals_u64_kernel(ctx):
+    """600 x 900 ragged panels incl. values near 2^64 and equal hashes across panels: both tile kernels byte-identical."""
+    rng = np.random.default_rng(12)
+    s = 1000
+    rh, rs = sorted_sketch_panel(rng, 900, s, n_clusters=7, shared=0.7)
+    qh, qs = sorted_sketch_panel(rng, 600, s, n_clusters=7, shared=0.7)
+    qh[:40] = rh[100:140]; qs[:40] = rs[100:140]
+    top = np.unique(rng.integers((1 << 64) - 5000, (1 << 64) - 2, size=700, dtype=np.uint64))   # high words all ones: the
+    rh[5, :len(top)] = top; rs[5] = len(top)                                                     # u64 path must fall back
+    rl = rng.integers(1000, 6_000_000, size=900).astype(np.uint64)
+    ql = rng.integers(1000, 6_000_000, size=600).astype(np.uint64)
+    got32, pass32 = ctx.dist_tile((rh, rs, rl), (qh, qs, ql), s, 21, 4.0 ** 21, max_distance=0.3)
+    ctx.set_dist_mode(force64=True)
+    try:
+        got64, pass64 = ctx.dist_tile((rh, rs, rl), (qh, qs, ql), s, 21, 4.0 ** 21, max_distance=0.3)
+    finally:
+        ctx.set_dist_mode(force64=False)
+    assert np.array_equal(got32, got64) and np.array_equal(pass32, pass64)
