@@ -45,14 +45,16 @@ struct DistArgs {
     double kmer_space, max_distance, max_pvalue;
 };
 
+// (the "memory" clobbers matter: these loads read what other threads staged, so they must stay behind the
+// __syncthreads() that publishes it -- without the clobber the compiler is free to move them)
 __device__ __forceinline__ void lds64(uint32_t addr, uint32_t& lo, uint32_t& hi)
 {
-    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(addr));
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(addr) : "memory");
 }
 
 __device__ __forceinline__ void lds32(uint32_t addr, uint32_t& v)
 {
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
 }
 
 // One step of the reference's merge loop (CommandDistance.cpp:378-386) on 32-bit ranks held in shared-memory
@@ -67,7 +69,9 @@ __device__ __forceinline__ void merge_step32(uint32_t& pa, uint32_t& pb, uint32_
                  "@pb_le add.u32 %1, %1, 128;\n\t"
                  "@pa_le ld.shared.u32 %2, [%0];\n\t"
                  "@pb_le ld.shared.u32 %3, [%1];\n\t}"
-                 : "+r"(pa), "+r"(pb), "+r"(av), "+r"(bv));
+                 : "+r"(pa), "+r"(pb), "+r"(av), "+r"(bv)
+                 :
+                 : "memory");
 }
 
 __device__ __forceinline__ void finish_pair(const DistArgs& a, uint64_t common, uint64_t denom, uint64_t len_ref, uint64_t len_qry, fpm_pair* out)
@@ -278,14 +282,16 @@ dist_tile_kernel(const uint64_t* __restrict__ pref, const uint64_t* __restrict__
             else atomicMax(&s_need, a.s - denom);
         }
         // ---- anyone left?  then advance every column past its elements < V ------------
-        if (!__syncthreads_or(done ? 0 : 1)) break;
+        __syncthreads();
+        const uint32_t need_all = s_need;    // max over the unfinished pairs of the union steps still missing (see dist_tile32_kernel)
+        if (need_all == 0) break;
         if (t < DT_COLS) {
             const uint64_t* col = t < DT_Q ? colQ + t : colR + ((t - DT_Q) >> 4) * DT_COLROWS * 16 + ((t - DT_Q) & 15);
             uint32_t lo = 0, hi = R;         // first row holding +inf (masked or exhausted)
             while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (col[mid * 16] != DT_INF) lo = mid + 1; else hi = mid; }
             s_cursor[t] += lo;
         }
-        R = (int)min((uint32_t)DT_ROWS, max(32u, s_need));
+        R = (int)min((uint32_t)DT_ROWS, max(32u, need_all));
         // (the barrier at the top of the next phase orders these writes before their readers)
     }
 
@@ -315,19 +321,58 @@ dist_tile_kernel(const uint64_t* __restrict__ pref, const uint64_t* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// dist_tile32_kernel: the same tile algorithm on 32-bit dense ranks (dist_rank.cu).  What changes against the
-// 64-bit kernel above, each from its ncu capture (profiles/r01_dist_tile_v3.txt: shared-memory pipe 80 % busy,
-// every step two LDS.64 of two wavefronts each):
-//   * elements are 4 bytes: a step's loads are LDS.32; the 16 query columns are stored twice side by side so the
-//     32 lanes of a warp read 32 different banks (lanes l and l+16 share a query) -- one wavefront per load;
+// dist_tile32_kernel: the tile algorithm on 32-bit dense ranks (dist_rank.cu).  What changes against the 64-bit
+// kernel above, each from an ncu capture (profiles/r01_dist_tile_v3.txt: shared-memory pipe 80 % busy, every step
+// two LDS.64 of two wavefronts each; profiles/r01_dist_tile32_v1.txt: latency bound at 8 warps per scheduler):
+//   * elements are 4 bytes: a step's loads are LDS.32, one wavefront each (32 lanes, 32 different columns);
 //   * the order test is one ISETP per direction instead of a two-instruction 64-bit compare;
-//   * 432 rows per phase fit at two CTAs per SM (was 288), so same-size genomes usually finish in two phases.
+//   * the tile is 32 queries x 32 references and every thread merges TWO pairs (same query, references 16
+//     columns apart) in one interleaved instruction stream: twice the loads in flight per warp;
+//   * the first +inf row of every column is found once per phase, so a thread knows how many steps it can run
+//     without an end test; a list that is through lets the other one jump to its end in O(1);
+//   * 432 rows per phase at two CTAs per SM (was 288); phase 0 is staged with 16-byte vectors.
 // ---------------------------------------------------------------------------------------------------------
 constexpr uint32_t D4_INF = 0xffffffffu;
 constexpr int D4_ROWS = 432;          // rows resident per phase
 constexpr int D4_UNROLL = 8;          // unchecked steps per fast block
-constexpr int D4_PAD = D4_UNROLL + 1; // +inf rows after them (a pointer rests at most on row R; the fast block looks D4_UNROLL rows ahead)
-constexpr int D4_COLROWS = D4_ROWS + D4_PAD;   // 441 rows x (32 + 32) columns x 4 B = 110.25 KB: two CTAs per SM
+constexpr int D4_PAD = 1;             // one +inf row after them (a pointer rests at most on row R)
+constexpr int D4_COLROWS = D4_ROWS + D4_PAD;   // 433 rows x (32 + 32) columns x 4 B = 108.25 KB: two CTAs per SM
+constexpr int D4_COLS = 64;           // 32 query + 32 reference columns
+
+struct Merge32 {
+    uint32_t pa, pb, av, bv, ea, eb, rem;
+    __device__ __forceinline__ uint32_t safe() const { return min(min((ea - pa) >> 7, (eb - pb) >> 7), rem); }
+    __device__ __forceinline__ bool finished() const { return rem == 0 || (av & bv) == D4_INF; }
+    // one end-tested action; call only while !finished()
+    __device__ __forceinline__ void slow()
+    {
+        if (av == D4_INF) { const uint32_t k = min((eb - pb) >> 7, rem); pb += k * 128; rem -= k; lds32(pb, bv); }        // a is through:
+        else if (bv == D4_INF) { const uint32_t k = min((ea - pa) >> 7, rem); pa += k * 128; rem -= k; lds32(pa, av); }   // "complete the union",
+        else { merge_step32(pa, pb, av, bv); rem--; }                                                                     // CommandDistance.cpp:389-400
+    }
+};
+
+// One pair to the end of the phase.  Deliberately NOT inlined: with this loop nest inlined twice behind the
+// two-pair loop of the kernel, nvcc 12.9 -O3 produced code for sm_100a that ran pointers past their column
+// ends (hangs / illegal addresses from n = 288 sketches on; -G and -Xptxas -O0 builds of the same source
+// were correct).  tests/test_gpu_dist.py::test_dist_rank32_sizes_sweep pins the shapes that exposed it.
+__device__ __noinline__ Merge32 merge32_alone(Merge32 m)
+{
+    for (;;) {
+        uint32_t blocks = m.safe() / D4_UNROLL;
+        if (blocks) {
+            m.rem -= blocks * D4_UNROLL;
+            do {
+#pragma unroll
+                for (int u = 0; u < D4_UNROLL; u++) merge_step32(m.pa, m.pb, m.av, m.bv);
+            } while (--blocks);
+            continue;
+        }
+        if (m.finished()) break;
+        m.slow();
+    }
+    return m;
+}
 
 __global__ void __launch_bounds__(DT_THREADS, 2)
 dist_tile32_kernel(const uint32_t* __restrict__ pref, const uint32_t* __restrict__ pqry, uint64_t rows_ref, uint64_t rows_qry,
@@ -335,25 +380,34 @@ dist_tile32_kernel(const uint32_t* __restrict__ pref, const uint32_t* __restrict
                    DistArgs a, fpm_pair* __restrict__ out, unsigned long long* steps, uint32_t q_tile0)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint32_t* colQ = reinterpret_cast<uint32_t*>(smem_raw);               // [D4_COLROWS][32]: query columns, two copies
-    uint32_t* colR = colQ + D4_COLROWS * 32;                              // [D4_COLROWS][32]: reference columns
-    __shared__ uint32_t s_cursor[DT_COLS];
+    uint32_t* colQ = reinterpret_cast<uint32_t*>(smem_raw);               // [D4_COLROWS][32] query columns
+    uint32_t* colR = colQ + D4_COLROWS * 32;                              // [D4_COLROWS][32] reference columns
+    __shared__ uint32_t s_cursor[D4_COLS], s_end[D4_COLS], s_exh[D4_COLS];
     __shared__ uint32_t s_V;
     __shared__ uint32_t s_need;
 
     const int t = threadIdx.x;
-    const int w = t >> 5, l = t & 31, h = l >> 4, i16 = l & 15;
-    const int qc = i16;                              // my query column
-    const int rc = 16 * h + ((i16 + w) & 15);        // my reference column (0..31)
-    const uint64_t q_tile = blockIdx.y + q_tile0, r_tile2 = blockIdx.x;
-    const uint32_t* gQ = pqry + q_tile * rows_qry * 16;
-    const uint32_t* gR0 = pref + (2 * r_tile2) * rows_ref * 16;          // plane 1 follows at + rows_ref * 16
-    const uint64_t n_rtiles16 = (n_ref + 15) / 16;
-    const bool plane1_exists = 2 * r_tile2 + 1 < n_rtiles16;
+    const int w = t >> 5, l = t & 31;
+    const int rc0 = (l + w) & 31, rc1 = (l + w + 16) & 31;     // my two reference columns; my query column is l
+    const uint64_t q_tile2 = blockIdx.y + q_tile0, r_tile2 = blockIdx.x;   // both index pairs of 16-column tiles
+    const uint32_t* gQ0 = pqry + (2 * q_tile2) * rows_qry * 16;           // plane 1 follows at + rows * 16
+    const uint32_t* gR0 = pref + (2 * r_tile2) * rows_ref * 16;
+    const bool q1_exists = 2 * q_tile2 + 1 < (n_qry + 15) / 16, r1_exists = 2 * r_tile2 + 1 < (n_ref + 15) / 16;
 
-    if (t < DT_COLS) s_cursor[t] = 0;
-    uint32_t common = 0, denom = 0;
-    bool done = false;
+    // column t of the 64 (0..31 query, 32..63 reference): its global base, row count and whether it exists
+    const uint32_t* my_col = nullptr;
+    uint64_t my_rows = 0;
+    if (t < D4_COLS) {
+        const int c = t & 31, pl = c >> 4;
+        const bool isq = t < 32;
+        if (pl == 0 || (isq ? q1_exists : r1_exists)) {
+            my_rows = isq ? rows_qry : rows_ref;
+            my_col = (isq ? gQ0 : gR0) + (uint64_t)pl * my_rows * 16 + (c & 15);
+        }
+        s_cursor[t] = 0;
+    }
+    uint32_t common0 = 0, common1 = 0, denom0 = 0, denom1 = 0;
+    bool done0 = false, done1 = false;
     int R = (int)(a.s < (uint32_t)D4_ROWS ? (a.s < 32u ? 32u : a.s) : (uint32_t)D4_ROWS);
     __syncthreads();
 
@@ -362,112 +416,122 @@ dist_tile32_kernel(const uint32_t* __restrict__ pref, const uint32_t* __restrict
         __syncthreads();
         if (t == 0) { s_V = D4_INF; s_need = 0; }
         __syncthreads();
-        if (t < DT_COLS) {
-            uint64_t row = (uint64_t)s_cursor[t] + R;
-            uint32_t v = D4_INF;
-            if (t < DT_Q) { if (row < rows_qry) v = gQ[row * 16 + t]; }
-            else {
-                int pl = (t - DT_Q) >> 4, c = (t - DT_Q) & 15;
-                if ((pl == 0 || plane1_exists) && row < rows_ref) v = gR0[(pl * rows_ref + row) * 16 + c];
-            }
-            if (v != D4_INF) atomicMin(&s_V, v);
+        if (t < D4_COLS) {
+            const uint64_t row = (uint64_t)s_cursor[t] + R;
+            if (row < my_rows) { const uint32_t v = my_col[row * 16]; if (v != D4_INF) atomicMin(&s_V, v); }
         }
         __syncthreads();
         const uint32_t V = s_V;
         // ---- stage rows [cursor, cursor+R) of every column, masking >= V ----------------
         if (phase == 0) {
             // all cursors are 0: rows are contiguous 64-byte lines, moved as 16-byte vectors
-            for (int idx = t; idx < R * 4; idx += DT_THREADS) {
-                const int r = idx >> 2, c4 = (idx & 3) * 4;
+            for (int idx = t; idx < R * 16; idx += DT_THREADS) {
+                const int r = idx >> 4, c4 = (idx & 7) * 4, pl = c4 >> 4;
+                const bool isq = (idx & 8) == 0;
+                const uint64_t rows = isq ? rows_qry : rows_ref;
                 uint4 v = make_uint4(D4_INF, D4_INF, D4_INF, D4_INF);
-                if ((uint64_t)r < rows_qry) v = *reinterpret_cast<const uint4*>(gQ + r * 16 + c4);
+                if ((pl == 0 || (isq ? q1_exists : r1_exists)) && (uint64_t)r < rows)
+                    v = *reinterpret_cast<const uint4*>((isq ? gQ0 : gR0) + ((uint64_t)pl * rows + r) * 16 + (c4 & 15));
                 v.x = v.x < V ? v.x : D4_INF; v.y = v.y < V ? v.y : D4_INF; v.z = v.z < V ? v.z : D4_INF; v.w = v.w < V ? v.w : D4_INF;
-                *reinterpret_cast<uint4*>(colQ + r * 32 + c4) = v;
-                *reinterpret_cast<uint4*>(colQ + r * 32 + 16 + c4) = v;
-            }
-            for (int idx = t; idx < R * 8; idx += DT_THREADS) {
-                const int r = idx >> 3, c4 = (idx & 7) * 4, pl = c4 >> 4;
-                uint4 v = make_uint4(D4_INF, D4_INF, D4_INF, D4_INF);
-                if ((pl == 0 || plane1_exists) && (uint64_t)r < rows_ref) v = *reinterpret_cast<const uint4*>(gR0 + (pl * rows_ref + r) * 16 + (c4 & 15));
-                v.x = v.x < V ? v.x : D4_INF; v.y = v.y < V ? v.y : D4_INF; v.z = v.z < V ? v.z : D4_INF; v.w = v.w < V ? v.w : D4_INF;
-                *reinterpret_cast<uint4*>(colR + r * 32 + c4) = v;
+                *reinterpret_cast<uint4*>((isq ? colQ : colR) + r * 32 + c4) = v;
             }
         } else {
-            for (int idx = t; idx < R * 16; idx += DT_THREADS) {
-                int c = idx & 15, r = idx >> 4;
-                uint64_t row = (uint64_t)s_cursor[c] + r;
-                uint32_t v = row < rows_qry ? gQ[row * 16 + c] : D4_INF;
-                v = v < V ? v : D4_INF;
-                colQ[r * 32 + c] = v;
-                colQ[r * 32 + 16 + c] = v;
-            }
-            for (int idx = t; idx < R * 32; idx += DT_THREADS) {
-                int c = idx & 31, r = idx >> 5, pl = c >> 4;
-                bool exists = pl == 0 || plane1_exists;
-                uint64_t row = (uint64_t)s_cursor[DT_Q + c] + r;
-                uint32_t v = (exists && row < rows_ref) ? gR0[(pl * rows_ref + row) * 16 + (c & 15)] : D4_INF;
-                colR[r * 32 + c] = v < V ? v : D4_INF;
+            for (int idx = t; idx < R * 64; idx += DT_THREADS) {
+                const int c = idx & 63, r = idx >> 6, pl = (c & 31) >> 4;
+                const bool isq = c < 32;
+                const uint64_t rows = isq ? rows_qry : rows_ref;
+                const uint64_t row = (uint64_t)s_cursor[c] + r;
+                uint32_t v = D4_INF;
+                if ((pl == 0 || (isq ? q1_exists : r1_exists)) && row < rows) v = (isq ? gQ0 : gR0)[((uint64_t)pl * rows + row) * 16 + (c & 15)];
+                (isq ? colQ : colR)[r * 32 + (c & 31)] = v < V ? v : D4_INF;
             }
         }
-        for (int idx = t; idx < D4_PAD * 32; idx += DT_THREADS) { colQ[R * 32 + idx] = D4_INF; colR[R * 32 + idx] = D4_INF; }
+        for (int idx = t; idx < D4_PAD * 64; idx += DT_THREADS) (idx < D4_PAD * 32 ? colQ + R * 32 : colR + R * 32 - D4_PAD * 32)[idx] = D4_INF;
+        __syncthreads();
+        if (t < D4_COLS) {
+            const uint32_t* col = t < 32 ? colQ + t : colR + (t - 32);
+            uint32_t lo = 0, hi = R;         // first row holding +inf (masked or exhausted)
+            while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (col[mid * 32] != D4_INF) lo = mid + 1; else hi = mid; }
+            s_end[t] = lo;
+            const uint64_t nxt = (uint64_t)s_cursor[t] + lo;          // nothing at or beyond V either: the list is through for good
+            s_exh[t] = !(nxt < my_rows && my_col[nxt * 16] != D4_INF);
+        }
         __syncthreads();
 
         // ---- merge up to V ------------------------------------------------------------
-        if (!done) {
-            // the reference loop (CommandDistance.cpp:376-400) exactly as in the 64-bit kernel: an exhausted or
-            // phase-masked list reads +inf; matches are recovered from the pointer advances
+        // the reference loop (CommandDistance.cpp:376-400): an exhausted or phase-masked list reads +inf; matches
+        // are recovered from the pointer advances: advances(a) + advances(b) = steps + matches
+        {
             const uint32_t pa0 = (uint32_t)__cvta_generic_to_shared(colQ + l);
-            const uint32_t pb0 = (uint32_t)__cvta_generic_to_shared(colR + rc);
-            uint32_t pa = pa0, pb = pb0, av, bv;
-            lds32(pa, av);
-            lds32(pb, bv);
-            const uint32_t budget = a.s - denom;
-            uint32_t rem = budget;
+            const uint32_t pb00 = (uint32_t)__cvta_generic_to_shared(colR + rc0), pb01 = (uint32_t)__cvta_generic_to_shared(colR + rc1);
+            const uint32_t ea = pa0 + s_end[l] * 128;
+            Merge32 m0, m1;
+            m0.pa = pa0; m0.pb = pb00; m0.ea = ea; m0.eb = pb00 + s_end[32 + rc0] * 128; m0.rem = done0 ? 0u : a.s - denom0;
+            m1.pa = pa0; m1.pb = pb01; m1.ea = ea; m1.eb = pb01 + s_end[32 + rc1] * 128; m1.rem = done1 ? 0u : a.s - denom1;
+            const uint32_t budget0 = m0.rem, budget1 = m1.rem;
+            lds32(pa0, m0.av); m1.av = m0.av;
+            lds32(pb00, m0.bv);
+            lds32(pb01, m1.bv);
+            // both pairs together while both have unchecked steps left; then each one alone
             for (;;) {
-                if (rem >= (uint32_t)D4_UNROLL) {
-                    uint32_t a8, b8;
-                    lds32(pa + D4_UNROLL * 128, a8);
-                    lds32(pb + D4_UNROLL * 128, b8);
-                    if (a8 != D4_INF && b8 != D4_INF) {
+                uint32_t blocks = min(m0.safe(), m1.safe()) / D4_UNROLL;
+                if (!blocks) break;
+                m0.rem -= blocks * D4_UNROLL; m1.rem -= blocks * D4_UNROLL;
+                do {
 #pragma unroll
-                        for (int u = 0; u < D4_UNROLL; u++) merge_step32(pa, pb, av, bv);
-                        rem -= D4_UNROLL;
-                        continue;
-                    }
-                }
-                if (rem == 0 || (av & bv) == D4_INF) break;
-                merge_step32(pa, pb, av, bv);
-                rem--;
+                    for (int u = 0; u < D4_UNROLL; u++) { merge_step32(m0.pa, m0.pb, m0.av, m0.bv); merge_step32(m1.pa, m1.pb, m1.av, m1.bv); }
+                } while (--blocks);
             }
-            const uint32_t nsteps = budget - rem;
-            denom += nsteps;
-            common += ((pa - pa0) >> 7) + ((pb - pb0) >> 7) - nsteps;
-            if (denom >= a.s || V == D4_INF) done = true;
-            else atomicMax(&s_need, a.s - denom);
+            m0 = merge32_alone(m0);
+            m1 = merge32_alone(m1);
+            // a pair is finished when its union reached s, or when both lists are through for good (nothing at or
+            // beyond V either); everything else goes on in the next phase with the rows it can still need
+            const uint32_t exh_a = s_exh[l], exh_b0 = s_exh[32 + rc0], exh_b1 = s_exh[32 + rc1];
+            {
+                const uint32_t n = budget0 - m0.rem;
+                denom0 += n;
+                common0 += ((m0.pa - pa0) >> 7) + ((m0.pb - pb00) >> 7) - n;
+                const bool through = (exh_a & exh_b0) != 0 & (m0.pa == m0.ea) & (m0.pb == m0.eb);
+                done0 = done0 | (denom0 >= a.s) | through;
+            }
+            {
+                const uint32_t n = budget1 - m1.rem;
+                denom1 += n;
+                common1 += ((m1.pa - pa0) >> 7) + ((m1.pb - pb01) >> 7) - n;
+                const bool through = (exh_a & exh_b1) != 0 & (m1.pa == m1.ea) & (m1.pb == m1.eb);
+                done1 = done1 | (denom1 >= a.s) | through;
+            }
+            const uint32_t need = max(done0 ? 0u : a.s - denom0, done1 ? 0u : a.s - denom1);
+            if (need) atomicMax(&s_need, need);
         }
         // ---- anyone left?  then advance every column past its elements < V ------------
-        if (!__syncthreads_or(done ? 0 : 1)) break;
-        if (t < DT_COLS) {
-            const uint32_t* col = t < DT_Q ? colQ + t : colR + (t - DT_Q);
-            uint32_t lo = 0, hi = R;         // first row holding +inf (masked or exhausted)
-            while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (col[mid * 32] != D4_INF) lo = mid + 1; else hi = mid; }
-            s_cursor[t] += lo;
-        }
-        R = (int)min((uint32_t)D4_ROWS, max(32u, s_need));
+        // (a plain barrier and the shared maximum: the BAR.RED form of this test, __syncthreads_or, faulted with
+        // "illegal instruction" on sm_100a in this kernel)
+        __syncthreads();
+        const uint32_t need_all = s_need;                      // max over the CTA's unfinished pairs of the union steps still missing
+        if (need_all == 0) break;
+        if (t < D4_COLS) s_cursor[t] += s_end[t];
+        R = (int)min((uint32_t)D4_ROWS, max(32u, need_all));
     }
 
     // ---- results: stage in shared memory, then coalesced row writes ---------------------
     __syncthreads();
-    fpm_pair* res = reinterpret_cast<fpm_pair*>(smem_raw);                  // [16][32]
-    const uint64_t qg = q_tile * 16 + qc, rg = r_tile2 * 32 + rc;
-    unsigned long long my_steps = denom;
-    if (qg < n_qry && rg < n_ref) finish_pair(a, common, denom, len_ref[rg], len_qry[qg], &res[qc * 32 + rc]);
+    fpm_pair* res = reinterpret_cast<fpm_pair*>(smem_raw);                  // [32][32]
+    const uint64_t qg = q_tile2 * 32 + l;
+    unsigned long long my_steps = (unsigned long long)denom0 + denom1;
+    if (qg < n_qry) {
+        const uint64_t lq = len_qry[qg];
+        const uint64_t rg0 = r_tile2 * 32 + rc0, rg1 = r_tile2 * 32 + rc1;
+        if (rg0 < n_ref) finish_pair(a, common0, denom0, len_ref[rg0], lq, &res[l * 32 + rc0]);
+        if (rg1 < n_ref) finish_pair(a, common1, denom1, len_ref[rg1], lq, &res[l * 32 + rc1]);
+    }
     __syncthreads();
     {
+        // 32 rows of 32 pairs = 768 bytes each, written as 8-byte words
         const uint64_t* src = reinterpret_cast<const uint64_t*>(res);
-        for (int idx = t; idx < 16 * 32 * 3; idx += DT_THREADS) {
+        for (int idx = t; idx < 32 * 32 * 3; idx += DT_THREADS) {
             int row = idx / 96, wd = idx % 96, pr = wd / 3;
-            uint64_t qg2 = q_tile * 16 + row, rg2 = r_tile2 * 32 + pr;
+            uint64_t qg2 = q_tile2 * 32 + row, rg2 = r_tile2 * 32 + pr;
             if (qg2 < n_qry && rg2 < n_ref)
                 reinterpret_cast<uint64_t*>(out + qg2 * n_ref + rg2)[wd % 3] = src[idx];
         }
@@ -518,20 +582,22 @@ static int run_dist(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* d_r
         }
         if (fast) {
             const bool k32 = mode == DIST_RANK_OK;
-            const size_t smem = k32 ? (size_t)64 * D4_COLROWS * 4 : (size_t)DT_COLS * DT_COLROWS * 8;
+            const size_t smem = k32 ? (size_t)D4_COLS * D4_COLROWS * 4 : (size_t)DT_COLS * DT_COLROWS * 8;
             if (k32) FPM_CUDA(cudaFuncSetAttribute(dist_tile32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             else FPM_CUDA(cudaFuncSetAttribute(dist_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             // query-row chunks: at most 65535 tiles per launch, and ~16M pairs per chunk when streaming to the host
+            const uint64_t qt = k32 ? 32 : 16;                        // query rows per tile
+            const uint64_t nqt = (d_qry->n + qt - 1) / qt;
             uint64_t tiles_per_chunk = 65535;
-            if (h_out) tiles_per_chunk = std::max<uint64_t>(1, std::min<uint64_t>(65535, (16ull << 20) / (16 * std::max<uint64_t>(d_ref->n, 1))));
+            if (h_out) tiles_per_chunk = std::max<uint64_t>(1, std::min<uint64_t>(65535, (16ull << 20) / (qt * std::max<uint64_t>(d_ref->n, 1))));
             if (h_out && !ctx->copy_stream) {
                 FPM_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
                 FPM_CUDA(cudaEventCreateWithFlags(&ctx->copy_done[0], cudaEventDisableTiming));
                 FPM_CUDA(cudaEventCreateWithFlags(&ctx->copy_done[1], cudaEventDisableTiming));
             }
             uint64_t c = 0;
-            for (uint64_t t0 = 0; t0 < nq16; t0 += tiles_per_chunk, c++) {
-                const uint64_t nt = std::min(tiles_per_chunk, nq16 - t0);
+            for (uint64_t t0 = 0; t0 < nqt; t0 += tiles_per_chunk, c++) {
+                const uint64_t nt = std::min(tiles_per_chunk, nqt - t0);
                 dim3 grid((uint32_t)((d_ref->n + 31) / 32), (uint32_t)nt);
                 ctx->time_begin(FPM_KERNEL_DIST_TILE);
                 if (k32)
@@ -544,7 +610,7 @@ static int run_dist(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* d_r
                 ctx->launches++;
                 FPM_CUDA(cudaGetLastError());
                 if (h_out) {
-                    const uint64_t q0 = t0 * 16, q1 = std::min<uint64_t>(d_qry->n, (t0 + nt) * 16);
+                    const uint64_t q0 = t0 * qt, q1 = std::min<uint64_t>(d_qry->n, (t0 + nt) * qt);
                     FPM_CUDA(cudaEventRecord(ctx->copy_done[c & 1], st));
                     FPM_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_done[c & 1], 0));
                     FPM_CUDA(cudaMemcpyAsync(h_out + q0 * d_ref->n, d_out + q0 * d_ref->n, (q1 - q0) * d_ref->n * sizeof(fpm_pair),

@@ -150,3 +150,22 @@ def test_dist_rank32_equals_u64_kernel(ctx):
     finally:
         ctx.set_dist_mode(force64=False)
     assert np.array_equal(got32, got64) and np.array_equal(pass32, pass64)
+
+
+@pytest.mark.parametrize("n,ragged", [(64, False), (288, False), (300, True), (500, False), (1111, True)])
+def test_dist_rank32_sizes_sweep(ctx, n, ragged):
+    """All-vs-all at the panel sizes that exposed a miscompiled merge loop in the 32-bit kernel (hang / illegal
+    address from 288 same-size sketches on): the 32-bit kernel must equal the 64-bit one bit for bit."""
+    rng = np.random.default_rng(11)
+    s = 1000
+    h, sz = sorted_sketch_panel(rng, n, s, n_clusters=20, shared=0.6, ragged=ragged)
+    ln = np.full(n, 5_000_000, dtype=np.uint64)
+    got32, pass32 = ctx.dist_tile((h, sz, ln), (h, sz, ln), s, 21, 4.0 ** 21)
+    ctx.set_dist_mode(force64=True)
+    try:
+        got64, pass64 = ctx.dist_tile((h, sz, ln), (h, sz, ln), s, 21, 4.0 ** 21)
+    finally:
+        ctx.set_dist_mode(force64=False)
+    assert np.array_equal(got32, got64) and np.array_equal(pass32, pass64)
+    full = sz == s
+    assert (np.diag(got32["numer"])[full] == s).all()
