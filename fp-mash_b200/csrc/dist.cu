@@ -343,12 +343,12 @@ struct Merge32 {
     uint32_t pa, pb, av, bv, ea, eb, rem;
     __device__ __forceinline__ uint32_t safe() const { return min(min((ea - pa) >> 7, (eb - pb) >> 7), rem); }
     __device__ __forceinline__ bool finished() const { return rem == 0 || (av & bv) == D4_INF; }
-    // one end-tested action; call only while !finished()
-    __device__ __forceinline__ void slow()
+    // no unchecked step is possible (safe() == 0) although the pair is not finished: one list rests on its first
+    // +inf row, so the other one advances alone -- "complete the union" (CommandDistance.cpp:389-400) -- in O(1)
+    __device__ __forceinline__ void one_sided()
     {
-        if (av == D4_INF) { const uint32_t k = min((eb - pb) >> 7, rem); pb += k * 128; rem -= k; lds32(pb, bv); }        // a is through:
-        else if (bv == D4_INF) { const uint32_t k = min((ea - pa) >> 7, rem); pa += k * 128; rem -= k; lds32(pa, av); }   // "complete the union",
-        else { merge_step32(pa, pb, av, bv); rem--; }                                                                     // CommandDistance.cpp:389-400
+        if (pa == ea) { const uint32_t k = min((eb - pb) >> 7, rem); pb += k * 128; rem -= k; lds32(pb, bv); }
+        else { const uint32_t k = min((ea - pa) >> 7, rem); pa += k * 128; rem -= k; lds32(pa, av); }
     }
 };
 
@@ -359,8 +359,9 @@ struct Merge32 {
 __device__ __noinline__ Merge32 merge32_alone(Merge32 m)
 {
     for (;;) {
-        uint32_t blocks = m.safe() / D4_UNROLL;
-        if (blocks) {
+        uint32_t n = m.safe();
+        if (n >= (uint32_t)D4_UNROLL) {
+            uint32_t blocks = n / D4_UNROLL;
             m.rem -= blocks * D4_UNROLL;
             do {
 #pragma unroll
@@ -368,8 +369,14 @@ __device__ __noinline__ Merge32 merge32_alone(Merge32 m)
             } while (--blocks);
             continue;
         }
+        if (n) {                     // fewer than a block: still no end test needed for these n steps
+            m.rem -= n;
+#pragma unroll 1
+            do merge_step32(m.pa, m.pb, m.av, m.bv); while (--n);
+            continue;
+        }
         if (m.finished()) break;
-        m.slow();
+        m.one_sided();
     }
     return m;
 }
