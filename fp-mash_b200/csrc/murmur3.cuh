@@ -19,12 +19,26 @@ __device__ __forceinline__ uint64_t rotl64(uint64_t x, int r)
     return ((uint64_t)nhi << 32) | nlo;
 }
 
+// x * C mod 2^64 for a compile-time C, pinned as three FMA-pipe instructions (IMAD.WIDE for lo*lo, then two
+// dependent IMADs folding hi*lo and lo*hi into the high word); left to itself nvcc emits four (two independent
+// IMADs, the IMAD.WIDE and an add).  The longer dependency chain is hidden by the other warps.
+template <uint64_t C>
+__device__ __forceinline__ uint64_t mul64c(uint64_t x)
+{
+    const uint32_t xl = (uint32_t)x, xh = (uint32_t)(x >> 32);
+    uint32_t lo, hi;
+    asm("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %2, %4;\n\tmov.b64 {%0, %1}, t;\n\tmad.lo.u32 %1, %3, %4, %1;\n\tmad.lo.u32 %1, %2, %5, %1;\n\t}"
+        : "=r"(lo), "=&r"(hi)
+        : "r"(xl), "r"(xh), "n"((uint32_t)C), "n"((uint32_t)(C >> 32)));
+    return ((uint64_t)hi << 32) | lo;
+}
+
 __device__ __forceinline__ uint64_t fmix64(uint64_t k)
 {
     k ^= k >> 33;
-    k *= 0xff51afd7ed558ccdULL;
+    k = mul64c<0xff51afd7ed558ccdULL>(k);
     k ^= k >> 33;
-    k *= 0xc4ceb9fe1a85ec53ULL;
+    k = mul64c<0xc4ceb9fe1a85ec53ULL>(k);
     k ^= k >> 33;
     return k;
 }
@@ -32,8 +46,8 @@ __device__ __forceinline__ uint64_t fmix64(uint64_t k)
 #define FPM_MC1 0x87c37b91114253d5ULL
 #define FPM_MC2 0x4cf5ad432745937fULL
 
-__device__ __forceinline__ uint64_t mm_k1(uint64_t k) { k *= FPM_MC1; k = rotl64(k, 31); k *= FPM_MC2; return k; }
-__device__ __forceinline__ uint64_t mm_k2(uint64_t k) { k *= FPM_MC2; k = rotl64(k, 33); k *= FPM_MC1; return k; }
+__device__ __forceinline__ uint64_t mm_k1(uint64_t k) { k = mul64c<FPM_MC1>(k); k = rotl64(k, 31); k = mul64c<FPM_MC2>(k); return k; }
+__device__ __forceinline__ uint64_t mm_k2(uint64_t k) { k = mul64c<FPM_MC2>(k); k = rotl64(k, 33); k = mul64c<FPM_MC1>(k); return k; }
 
 // add1/add2 are the two additive constants of the block mix; callers in hot loops pass them in
 // registers (an immediate would be re-materialised with two moves per use).

@@ -12,6 +12,15 @@
 //     the input bytes) instead of a per-byte test;
 //   * each warp walks a contiguous run of tiles and caches the sketch it is in, so the per-tile
 //     group lookup is a register compare except at sketch boundaries.
+// Third pass (profiles/r01_sketch_hash_v3.txt; the kernel is bound by the ALU pipe -- SHF/LOP3/PRMT -- while the
+// LSU pipe idles and the FMA pipe has slots left; an experiment with a free expansion ran 18 % faster):
+//   * the 2-bit -> ASCII expansion reads a 512-entry shared-memory table, one byte of packed codes = four
+//     letters per LDS.32 (expand_lut): 6 ALU + 6 FMA + 6 LSU instructions instead of ~24 ALU per window;
+//   * 64-bit constant multiplies are pinned at three IMADs (mul64c);
+//   * the per-window threshold reject is ONE compare (the exact 64-bit test sits behind a volatile shared load
+//     the compiler cannot hoist), and the survivor-queue check runs only when a vote says a lane queued something.
+//   Tried and dropped: right shifts as IMAD.HI (the FMA pipe runs it at a fraction of IMAD's rate: 169 vs 188
+//   Gk-mers/s), x*5+c as mad.wide asm (blocks the fold with the preceding add: +3 instructions).
 //
 // Work decomposition: warp tile = 63 chunks of 32 windows (2016 windows).  Lane l converts
 // chunks 2l and 2l+1; lanes 0..30 hash both, lane 31 hashes only its first chunk -- its second
@@ -87,7 +96,13 @@ __global__ void __launch_bounds__(SK_THREADS, FPM_SK_MIN_CTAS) sketch_hash_kerne
     const uint64_t add1 = a.c_add1, add2 = a.c_add2;
     __shared__ uint64_t s_qh[SK_THREADS / 32][SQ_CAP], s_qp[SK_THREADS / 32][SQ_CAP];
     __shared__ uint32_t s_qn[SK_THREADS / 32];
+    __shared__ uint64_t s_tm[SK_THREADS / 32];      // the warp's current threshold bound (see the filter below)
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __shared__ uint32_t s_lut[512];
+    build_expand_lut(s_lut, K, threadIdx.x, SK_THREADS);
+    uint32_t lut_addr = (uint32_t)__cvta_generic_to_shared(s_lut);
+    asm volatile("" : "+r"(lut_addr));     // keep the table address in a register: re-deriving it costs ~4 instructions per window
+    __syncthreads();
     if (lane == 0) s_qn[wid] = 0;
     __syncwarp();
     const uint64_t warp = (uint64_t)blockIdx.x * (SK_THREADS / 32) + (threadIdx.x >> 5);
@@ -133,6 +148,8 @@ __global__ void __launch_bounds__(SK_THREADS, FPM_SK_MIN_CTAS) sketch_hash_kerne
         if (idle_tile) continue;
 
         const uint32_t tcut = hash32 ? (uint32_t)tmax : (uint32_t)(tmax >> 32);
+        if (lane == 0) s_tm[wid] = tmax;
+        __syncwarp();
 
         // ---- load + convert 64 bases per lane -------------------------------------------------
         const uint64_t lane_pos = tile_base + 64ull * lane;
@@ -151,6 +168,7 @@ __global__ void __launch_bounds__(SK_THREADS, FPM_SK_MIN_CTAS) sketch_hash_kerne
         // (no lane leaves the tile early: the survivor queue below is flushed by the whole warp)
         const int nblk = lane_pos >= n_bytes ? 0 : (lane == 31 ? 2 : 4);
 
+        bool queued = false;
 #pragma unroll 1
         for (int blk = 0; blk < 4; blk++) {           // uniform trip count: the warp meets at the flush points
             const bool live = blk < nblk;
@@ -176,12 +194,15 @@ __global__ void __launch_bounds__(SK_THREADS, FPM_SK_MIN_CTAS) sketch_hash_kerne
                         clo = use_r ? rlo : flo;
                     }
                     uint64_t w[4];
-                    expand_ascii<K>(chi, clo, w, tbl);
+                    expand_lut<K>(chi, clo, w, lut_addr);
                     uint64_t h = murmur3_h1_fixed<K>(w, seed, add1, add2);
                     if (hash32) h &= 0xffffffffULL;
                     // one-instruction reject on the deciding word; the exact 64-bit test only for the survivors
                     const uint32_t hcut = hash32 ? (uint32_t)h : (uint32_t)(h >> 32);
-                    if (hcut <= tcut && h <= tmax) {
+                    if (hcut <= tcut) {
+                        // the exact 64-bit test reads its bound back through a volatile shared load, which the compiler
+                        // cannot speculate above the branch: the per-window path keeps ONE compare
+                        if (h > *(volatile uint64_t*)&s_tm[wid]) continue;
                         const int b = 16 * blk + 4 * sub + j;                    // window index within the lane's 64
                         const uint64_t vlo = ((uint64_t)v1 << 32) | v0;
                         const uint64_t vw = b ? ((vlo >> b) | ((uint64_t)v2 << (64 - b))) : vlo;
@@ -190,6 +211,7 @@ __global__ void __launch_bounds__(SK_THREADS, FPM_SK_MIN_CTAS) sketch_hash_kerne
                         if ((vw & km) == km && pos >= range_lo && pos < range_hi) {
                             // survivors are queued per warp and inserted 32 at a time: the table atomics cost a
                             // ~1 us round trip that would otherwise stall the whole warp for one lane's hash
+                            queued = true;
                             const uint32_t qi = atomicAdd(&s_qn[wid], 1u);
                             if (qi < SQ_CAP) { s_qh[wid][qi] = h; s_qp[wid][qi] = pos; }
                             else sketch_emit(a, h, pos, g_lo, g_hi, trace);      // queue full (accept-all sketches)
@@ -200,8 +222,11 @@ __global__ void __launch_bounds__(SK_THREADS, FPM_SK_MIN_CTAS) sketch_hash_kerne
                 fw0 = __funnelshift_l(fw1, fw0, 8); fw1 = __funnelshift_l(fw2, fw1, 8); fw2 <<= 8;
                 if (CANON) { x[2] = __funnelshift_r(x[2], x[1], 8); x[1] = __funnelshift_r(x[1], x[0], 8); x[0] >>= 8; }
                 // dense survivors (accept-all sketches of short records): insert as soon as a warp-load is waiting
-                __syncwarp();
-                if (s_qn[wid] >= 32) flush_survivors(a, s_qh[wid], s_qp[wid], &s_qn[wid], lane, trace);
+                // the queue can only have grown if some lane queued a survivor in these four windows (~5 % of the time)
+                if (__any_sync(0xffffffffu, queued)) {
+                    queued = false;
+                    if (s_qn[wid] >= 32) flush_survivors(a, s_qh[wid], s_qp[wid], &s_qn[wid], lane, trace);
+                }
             }
             q0 = q1; q1 = q2; q2 = q3; q3 = q4; q4 = q5;
         }

@@ -190,6 +190,39 @@ __device__ __forceinline__ void expand_ascii(uint32_t hi, uint32_t lo, uint64_t 
     }
 }
 
+// The same expansion through a shared-memory table: the canonical k-mer is left-aligned in hi:lo, so every group of
+// four bases is one BYTE of hi/lo; lut[v] holds the four ASCII letters of byte value v (first base in the low
+// byte), lut[256 + v] only the first K % 4 of them (zero-padded: the Murmur tail).  Per group: one PRMT (byte
+// extract, ALU pipe), one IMAD (table address, FMA pipe) and one LDS.32 -- against ~4 ALU-pipe instructions per
+// group for expand_ascii.  The sketch kernel is bound by the ALU pipe and leaves the LSU pipe idle.
+__device__ __forceinline__ void build_expand_lut(uint32_t* lut, int K, int tid, int nthreads)
+{
+    for (int v = tid; v < 512; v += nthreads) {
+        const int nb = v < 256 ? 4 : (K & 3);
+        uint32_t e = 0;
+        for (int i = 0; i < nb; i++) e |= (uint32_t)"ACGT"[((v & 255) >> (6 - 2 * i)) & 3] << (8 * i);
+        lut[v] = e;
+    }
+}
+
+template <int K>
+__device__ __forceinline__ void expand_lut(uint32_t hi, uint32_t lo, uint64_t (&w)[4], uint32_t lut_addr /* shared-space byte address */)
+{
+    uint32_t v[8];
+#pragma unroll
+    for (int g = 0; g < 8; g++) {
+        if (4 * g >= K) { v[g] = 0; continue; }
+        const uint32_t src = g < 4 ? hi : lo;
+        const uint32_t idx = prmt(src, 0u, 0x4440u | (3 - (g & 3)));           // byte 3 holds the first four bases
+        const bool partial = 4 * g + 4 > K;
+        uint32_t addr;
+        asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(addr) : "r"(idx), "r"(lut_addr + (partial ? 1024u : 0u)));
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v[g]) : "r"(addr));
+    }
+#pragma unroll
+    for (int c = 0; c < 4; c++) w[c] = ((uint64_t)v[2 * c + 1] << 32) | v[2 * c];
+}
+
 // The 16 windows of one block.  fw0..2: 48 forward bases; window i starts at base i.
 // CANON: pick min(forward, reverse complement) (ties are palindromes: identical bytes).
 // F is called as F(i, hash) for every window, valid or not (validity is checked only for the
