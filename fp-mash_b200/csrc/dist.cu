@@ -525,12 +525,12 @@ dist_tile32_kernel(const uint32_t* __restrict__ pref, const uint32_t* __restrict
     __syncthreads();
     fpm_pair* res = reinterpret_cast<fpm_pair*>(smem_raw);                  // [32][32]
     const uint64_t qg = q_tile2 * 32 + l;
-    unsigned long long my_steps = (unsigned long long)denom0 + denom1;
+    unsigned long long my_steps = 0;       // union steps of real pairs only (tile padding merges against empty lists)
     if (qg < n_qry) {
         const uint64_t lq = len_qry[qg];
         const uint64_t rg0 = r_tile2 * 32 + rc0, rg1 = r_tile2 * 32 + rc1;
-        if (rg0 < n_ref) finish_pair(a, common0, denom0, len_ref[rg0], lq, &res[l * 32 + rc0]);
-        if (rg1 < n_ref) finish_pair(a, common1, denom1, len_ref[rg1], lq, &res[l * 32 + rc1]);
+        if (rg0 < n_ref) { finish_pair(a, common0, denom0, len_ref[rg0], lq, &res[l * 32 + rc0]); my_steps += denom0; }
+        if (rg1 < n_ref) { finish_pair(a, common1, denom1, len_ref[rg1], lq, &res[l * 32 + rc1]); my_steps += denom1; }
     }
     __syncthreads();
     {

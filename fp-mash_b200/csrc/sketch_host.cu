@@ -125,12 +125,17 @@ int sketch_batch_dev_impl(fpm_ctx* ctx, const fpm_sketch_params* p, const uint8_
     for (uint32_t g = 0; g < n_groups; g++) {
         uint64_t n = h_goff[g + 1] - h_goff[g];
         GroupPlan& pl = plan[g];
-        if (n <= 2 * target) {
+        // -m > 1 (read sets): only hashes seen min_cov times qualify, so the first bound must admit about
+        // coverage x more hash OCCURRENCES than sketch slots.  The coverage is not known yet; a guess of 32x costs a
+        // larger table and a few thousand more atomics, and saves the whole second pass whenever the real coverage
+        // is below it (bounded so that many-sketch batches do not multiply their table memory by 32).
+        const uint64_t cov_guess = p->min_cov > 1 ? std::max<uint64_t>(1, std::min<uint64_t>(32, (64ull << 20) / (4 * target * n_groups))) : 1;
+        if (n <= 2 * target * cov_guess) {
             pl.all = true; pl.thresh = full; pl.cap = pow2ceil(2 * n);
         } else {
             pl.all = false;
-            pl.thresh = scale_threshold(full, (double)target / (double)n);
-            pl.cap = pow2ceil(4 * target);
+            pl.thresh = scale_threshold(full, (double)(target * cov_guess) / (double)n);
+            pl.cap = pow2ceil(4 * target * cov_guess);
         }
     }
 

@@ -64,7 +64,7 @@ ctx.set_timing(False)
 out["C4_read_sketch_m2"] = {"reads": n_reads, "read_len": rl, "valid_windows": windows, "sketch_full": int(on.item()) == 1000,
                             "coverage_estimate": float(oc.sum().item()) / 1000.0, "ms": dt * 1e3, "Gk-mers/s": windows / dt / 1e9,
                             "hash_passes_per_call": hn / 4, "hash_kernel_ms_per_pass": hm / max(hn, 1),
-                            "note": "threshold pass + re-run at the measured density + trace pass for the order-dependent top count"}
+                            "note": "one threshold pass (coverage guess 32x for -m) + trace pass for the order-dependent top count"}
 del buf, reads, codes, idx
 
 # ---- C5: k=32, s=10000 sketches of 5 Mbp genomes -------------------------------------------------------------------
