@@ -17,6 +17,7 @@
 #include <sstream>
 
 #include "fastx.h"
+#include <chrono>
 #include "fpmash_b200.h"
 #include "msh.h"
 
@@ -25,12 +26,26 @@ using namespace std;
 static const uint64_t kLimitReadFingerprint = 1000000;   // LIMIT_READ_FINGERPRINT, Sketch.cpp:37
 static const uint64_t kFlushBytes = 256ull << 20;        // sequence bytes per GPU batch (the pinned staging buffer is sized for it)
 
+void fpmTick(const char* label)
+{
+    static const bool on = getenv("FPMASH_TIMING") != nullptr;
+    if (!on) return;
+    static const auto t0 = std::chrono::steady_clock::now();
+    static auto last = t0;
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[timing] %8.1f ms (+%7.1f)  %s\n", std::chrono::duration<double, std::milli>(now - t0).count(),
+            std::chrono::duration<double, std::milli>(now - last).count(), label);
+    last = now;
+}
+
 fpm_ctx* gpuContext()
 {
     static fpm_ctx* ctx = nullptr;
     if (!ctx) {
         const char* dev = getenv("FPMASH_DEVICE");
+        fpmTick("before fpm_ctx_create");
         int rc = fpm_ctx_create(dev ? atoi(dev) : 0, &ctx);
+        fpmTick("fpm_ctx_create done");
         if (rc != FPM_OK) {
             cerr << "ERROR: " << fpm_last_error() << endl;
             exit(1);
@@ -93,6 +108,7 @@ struct Sketch::Batch : SeqSink {
         uint64_t ncap = max<uint64_t>(cap ? cap * 2 : (kFlushBytes + (64ull << 20)), used + extra);
         void* p = nullptr;
         gpuCheck(fpm_host_alloc(ncap, &p));
+        fpmTick("pinned batch allocated");
         if (used) memcpy(p, seq, used);
         if (seq) fpm_host_free(seq);
         seq = (uint8_t*)p;
@@ -150,8 +166,10 @@ void Sketch::flushBatch(Batch& b)
     vector<uint64_t> hashes((size_t)n * s);
     vector<uint32_t> counts(parameters.counts ? (size_t)n * s : 0);
     vector<uint32_t> outn(n);
+    fpmTick("batch parsed");
     gpuCheck(fpm_sketch_batch(gpuContext(), &sp, b.seq, b.used, b.goff.data(), n, hashes.data(),
                               parameters.counts ? counts.data() : nullptr, outn.data(), nullptr));
+    fpmTick("fpm_sketch_batch done");
     for (uint32_t g = 0; g < n; g++) {
         Reference& r = b.metas[g];
         r.hashesSorted.setUse64(parameters.use64);

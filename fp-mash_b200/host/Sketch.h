@@ -113,3 +113,5 @@ void setAlphabetFromString(Sketch::Parameters& parameters, const char* character
 // The process-wide CUDA context (created on first use; failure is fatal: no CPU fallback).
 struct fpm_ctx;
 fpm_ctx* gpuContext();
+// FPMASH_TIMING=1: print elapsed wall-clock milestones to stderr (where does a CLI run spend its time?)
+void fpmTick(const char* label);

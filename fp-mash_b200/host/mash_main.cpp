@@ -6,6 +6,7 @@
 #include <memory>
 
 #include "Command.h"
+#include "Sketch.h"
 #include "fastx.h"
 
 int main(int argc, const char** argv)
@@ -43,5 +44,8 @@ int main(int argc, const char** argv)
         std::cout << std::endl;
         return argc < 2 ? 0 : 1;
     }
-    return commands[argv[1]]->run(argc - 2, argv + 2);
+    fpmTick("main");
+    int rc = commands[argv[1]]->run(argc - 2, argv + 2);
+    fpmTick("command done");
+    return rc;
 }
