@@ -1,8 +1,11 @@
-// cfl.cu -- lyn2vec's "basic" CFL fingerprints on the GPU (the producer of `-fp` inputs).
+// cfl.cu -- lyn2vec's "basic" fingerprints on the GPU (the producer of `-fp` inputs):
+// --type_factorization CFL, ICFL and CFL_ICFL-<C>.
 //
-// Replaces, for --type basic --type_factorization CFL --shift shift (the README recipe, README.md:34-52):
+// Replaces, for --type basic --shift shift (the README recipe, README.md:34-52, uses CFL):
 //   shift_string      (lyn2vec/fingerprint_utils.py:95-110)  every circular window of `window` (=100) characters
 //   CFL               (lyn2vec/factorizations.py:102-126)    Duval's Lyndon factorisation of each window
+//   ICFL_recursive    (factorizations.py:143-248)            the inverse Lyndon factorisation
+//   CFL_icfl          (factorizations.py:265-300)            CFL with long factors sub-factorised by ICFL
 //   the line writer   (fingerprint_utils.py:443-476)         one row of factor LENGTHS per window
 // and fuses getHashFingerPrint (hash.cpp:45-73) over each row, so a FASTA record can go straight to the
 // `-fp` sketch (one 32-bit hash per window) without the text file -- which can still be written from
@@ -17,9 +20,82 @@ namespace fpm {
 
 constexpr int CFL_MAX_WINDOW = 256;
 
+// Rows of factor lengths go to the optional token buffer and, two tokens per block, into MurmurHash3
+// (getHashFingerPrint, hash.cpp:45-73, hashes the row as an array of uint64).
+struct RowSink {
+    uint64_t h1, h2, pending;
+    uint32_t ntok;
+    uint16_t* row;
+    __device__ __forceinline__ void emit(uint32_t flen)
+    {
+        if (row) row[ntok] = (uint16_t)flen;
+        if (ntok & 1) mm_block(h1, h2, pending, (uint64_t)flen); else pending = flen;
+        ntok++;
+    }
+    __device__ __forceinline__ uint64_t finish()
+    {
+        if (ntok & 1) h1 ^= mm_k1(pending);                 // 8-byte tail
+        return mm_finish(h1, h2, (uint64_t)ntok * 8);
+    }
+};
+
+// ICFL, the inverse Lyndon factorisation (lyn2vec/factorizations.py:143-248, ICFL_recursive), without recursion.
+// The reference recurses on a suffix: find_pre (:172-189) scans the longest prefix x[0..j) on which
+// x[j'] <= x[i'] keeps holding (a non-increasing "anti-Lyndon" run) up to the first character x[j] that breaks
+// it; find_bre (:212-232) walks the border chain of x[0..j) (KMP failure function, border(), :235-248) for the
+// shortest border b with x[b] < x[j] (`last`), cuts p = x[0 .. j-last) off and recurses on the rest.  On the way
+// back (compute_icfl_recursive, :152-169) p becomes a factor of its own iff the first factor found so far is
+// longer than `last`, else it is glued to it.  Here: a forward pass records (|p|, last) per level, a backward
+// pass decides the cuts, a second forward pass emits the lengths in order.
+// scratch: plen/aux/f hold n bytes each (n <= 256, so every value fits a byte: |p| <= j <= 255).
+__device__ void icfl_lengths(const uint8_t* w, int n, uint8_t* plen, uint8_t* aux, uint8_t* f, RowSink& sink)
+{
+    int pos = 0, levels = 0, tail_len = 0;
+    for (;;) {
+        const int m = n - pos;
+        const uint8_t* x = w + pos;
+        int j = m;
+        if (m > 1) {                                         // find_pre
+            int i = 0;
+            j = 1;
+            while (j < m && x[j] <= x[i]) { i = x[j] < x[i] ? 0 : i + 1; j++; }
+        }
+        if (j >= m) { tail_len = m; break; }                 // the rest is one factor (the "$" case, :158-161)
+        f[0] = 0;                                            // border() of x[0..j)
+        for (int i = 1, k = 0; i < j; i++) {
+            while (k > 0 && x[k] != x[i]) k = f[k - 1];
+            if (x[k] == x[i]) k++;
+            f[i] = (uint8_t)k;
+        }
+        int i = j, last = f[j - 1];                          // find_bre
+        while (i > 0) {
+            if (x[f[i - 1]] < x[j]) last = f[i - 1];
+            i = f[i - 1];
+        }
+        plen[levels] = (uint8_t)(j - last);
+        aux[levels] = (uint8_t)last;
+        levels++;
+        pos += j - last;
+    }
+    int first = tail_len;                                    // length of the current first factor, unwinding
+    for (int t = levels - 1; t >= 0; t--) {
+        const bool cut = first > (int)aux[t];                // :165-168
+        first = cut ? (int)plen[t] : first + (int)plen[t];
+        aux[t] = cut;
+    }
+    uint32_t acc = 0;
+    for (int t = 0; t < levels; t++) {
+        acc += plen[t];
+        if (aux[t]) { sink.emit(acc); acc = 0; }
+    }
+    sink.emit(acc + tail_len);
+}
+
+// mode: FPM_FACT_CFL, FPM_FACT_ICFL, FPM_FACT_CFL_ICFL (CFL factors longer than `sub_len` are sub-factorised with
+// ICFL, CFL_icfl, factorizations.py:265-300; the "<<" ">>" markers are dropped from the rows, fingerprint_utils.py:459-463)
 __global__ void __launch_bounds__(128) cfl_window_kernel(const uint8_t* __restrict__ seq, const uint64_t* __restrict__ rec_off,
-                                                         const uint64_t* __restrict__ win_off, uint32_t n_rec, uint32_t window,
-                                                         uint32_t seed, int use64, uint64_t* __restrict__ out_hash,
+                                                         const uint64_t* __restrict__ win_off, uint32_t n_rec, uint32_t window, int mode,
+                                                         uint32_t sub_len, uint32_t seed, int use64, uint64_t* __restrict__ out_hash,
                                                          uint16_t* __restrict__ out_tok, uint16_t* __restrict__ out_ntok)
 {
     const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -29,44 +105,52 @@ __global__ void __launch_bounds__(128) cfl_window_kernel(const uint8_t* __restri
     const uint64_t base = rec_off[lo], n = rec_off[lo + 1] - base, shift = w - win_off[lo];
     const uint32_t len = n < window ? (uint32_t)n : window;   // shorter records give one window: the record itself
     uint8_t word[CFL_MAX_WINDOW];
+    uint8_t s_plen[CFL_MAX_WINDOW], s_aux[CFL_MAX_WINDOW], s_f[CFL_MAX_WINDOW];   // ICFL scratch (local memory; unused for CFL)
     for (uint32_t j = 0; j < len; j++) {
         uint64_t p = shift + j;
         if (p >= n) p -= n;                                 // circular wrap (fingerprint_utils.py:104-108)
         word[j] = seq[base + p];
     }
-    // Duval (factorizations.py:102-126), factor lengths streamed into MurmurHash3 two tokens per block
-    uint64_t h1 = seed, h2 = seed, pending = 0;
-    uint32_t ntok = 0, i = 0;
-    uint16_t* row = out_tok ? out_tok + w * window : nullptr;
-    while (i < len) {
-        uint32_t j = i + 1, k = i;
-        while (j < len && word[k] <= word[j]) {
-            k = word[k] < word[j] ? i : k + 1;
-            j++;
-        }
-        const uint32_t flen = j - k;
-        while (i <= k) {
-            if (row) row[ntok] = (uint16_t)flen;
-            if (ntok & 1) mm_block(h1, h2, pending, (uint64_t)flen); else pending = flen;
-            ntok++;
-            i += flen;
+    RowSink sink;
+    sink.h1 = seed; sink.h2 = seed; sink.pending = 0; sink.ntok = 0;
+    sink.row = out_tok ? out_tok + w * window : nullptr;
+    if (mode == FPM_FACT_ICFL) {
+        icfl_lengths(word, (int)len, s_plen, s_aux, s_f, sink);
+    } else {
+        // Duval (factorizations.py:102-126)
+        uint32_t i = 0;
+        while (i < len) {
+            uint32_t j = i + 1, k = i;
+            while (j < len && word[k] <= word[j]) {
+                k = word[k] < word[j] ? i : k + 1;
+                j++;
+            }
+            const uint32_t flen = j - k;
+            while (i <= k) {
+                if (mode == FPM_FACT_CFL_ICFL && flen > sub_len) icfl_lengths(word + i, (int)flen, s_plen, s_aux, s_f, sink);
+                else sink.emit(flen);
+                i += flen;
+            }
         }
     }
-    if (ntok & 1) h1 ^= mm_k1(pending);                     // 8-byte tail
-    const uint64_t h = mm_finish(h1, h2, (uint64_t)ntok * 8);
+    const uint64_t h = sink.finish();
     if (out_hash) out_hash[w] = use64 ? h : (h & 0xffffffffULL);
-    if (out_ntok) out_ntok[w] = (uint16_t)ntok;
+    if (out_ntok) out_ntok[w] = (uint16_t)sink.ntok;
 }
 
 }  // namespace fpm
 
 using namespace fpm;
 
-extern "C" int fpm_cfl_fingerprint_batch(fpm_ctx* ctx, const uint8_t* seq, const uint64_t* rec_offsets, uint32_t n_records, uint32_t window,
-                                         uint32_t seed, int use64, uint64_t* out_hashes, uint16_t* out_tokens, uint16_t* out_ntokens,
-                                         uint64_t* out_window_offsets)
+extern "C" int fpm_fingerprint_batch(fpm_ctx* ctx, const uint8_t* seq, const uint64_t* rec_offsets, uint32_t n_records, uint32_t window,
+                                     int factorization, uint32_t sub_len, uint32_t seed, int use64, uint64_t* out_hashes,
+                                     uint16_t* out_tokens, uint16_t* out_ntokens, uint64_t* out_window_offsets)
 {
     if (!ctx) { set_error("ctx is NULL"); return FPM_ERR_ARG; }
+    if (factorization != FPM_FACT_CFL && factorization != FPM_FACT_ICFL && factorization != FPM_FACT_CFL_ICFL) {
+        set_error("unknown factorization %d", factorization);
+        return FPM_ERR_ARG;
+    }
     if (!rec_offsets || !out_window_offsets) { set_error("NULL buffer"); return FPM_ERR_ARG; }
     if (window < 1 || window > CFL_MAX_WINDOW) { set_error("window %u outside 1..%d", window, CFL_MAX_WINDOW); return FPM_ERR_ARG; }
     FPM_CUDA(cudaSetDevice(ctx->device));
@@ -92,7 +176,7 @@ extern "C" int fpm_cfl_fingerprint_batch(fpm_ctx* ctx, const uint8_t* seq, const
     FPM_CUDA(cudaMemcpyAsync(ctx->seq.p, seq, n_bytes, cudaMemcpyHostToDevice, st));
     FPM_CUDA(cudaMemcpyAsync(d_rec, rec_offsets, sizeof(uint64_t) * (n_records + 1), cudaMemcpyHostToDevice, st));
     FPM_CUDA(cudaMemcpyAsync(d_win, woff.data(), sizeof(uint64_t) * (n_records + 1), cudaMemcpyHostToDevice, st));
-    cfl_window_kernel<<<(uint32_t)((n_win + 127) / 128), 128, 0, st>>>(ctx->seq.as<uint8_t>(), d_rec, d_win, n_records, window, seed, use64,
+    cfl_window_kernel<<<(uint32_t)((n_win + 127) / 128), 128, 0, st>>>(ctx->seq.as<uint8_t>(), d_rec, d_win, n_records, window, factorization, sub_len, seed, use64,
                                                                        ctx->outh.as<uint64_t>(), out_tokens ? ctx->outc.as<uint16_t>() : nullptr,
                                                                        ctx->outn.as<uint16_t>());
     ctx->launches++;
@@ -102,4 +186,12 @@ extern "C" int fpm_cfl_fingerprint_batch(fpm_ctx* ctx, const uint8_t* seq, const
     if (out_ntokens) FPM_CUDA(cudaMemcpyAsync(out_ntokens, ctx->outn.p, sizeof(uint16_t) * n_win, cudaMemcpyDeviceToHost, st));
     FPM_CUDA(cudaStreamSynchronize(st));
     return FPM_OK;
+}
+
+extern "C" int fpm_cfl_fingerprint_batch(fpm_ctx* ctx, const uint8_t* seq, const uint64_t* rec_offsets, uint32_t n_records, uint32_t window,
+                                         uint32_t seed, int use64, uint64_t* out_hashes, uint16_t* out_tokens, uint16_t* out_ntokens,
+                                         uint64_t* out_window_offsets)
+{
+    return fpm_fingerprint_batch(ctx, seq, rec_offsets, n_records, window, FPM_FACT_CFL, 0, seed, use64, out_hashes, out_tokens, out_ntokens,
+                                 out_window_offsets);
 }

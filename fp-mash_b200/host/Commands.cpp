@@ -775,12 +775,13 @@ int CommandTriangle::run() const
 CommandFingerprint::CommandFingerprint() : Command()
 {
     name = "fingerprint";
-    summary = "Lyndon (CFL) fingerprints of sequences, the input of `sketch -fp` (lyn2vec basic mode).";
-    description = "For every record of each FASTA input, factorise every circular window of -w characters with Duval's algorithm and write one line of factor lengths per window, in the format of lyn2vec's fingerprint_CFL.txt. The row id is the second word of the record header followed by _0, as lyn2vec writes it with --rev_comb true.";
+    summary = "Lyndon (CFL / ICFL) fingerprints of sequences, the input of `sketch -fp` (lyn2vec basic mode).";
+    description = "For every record of each FASTA input, factorise every circular window of -w characters (-t CFL: Duval's algorithm; ICFL: inverse Lyndon factorisation; CFL_ICFL-<C>: CFL with factors longer than C sub-factorised by ICFL) and write one line of factor lengths per window, in the format of lyn2vec's fingerprint_<type>.txt. The row id is the second word of the record header followed by _0, as lyn2vec writes it with --rev_comb true.";
     argumentString = "<fasta> [<fasta>] ...";
     useOption("help");
     addOption("window", Option(Option::Integer, "w", "", "Window length of the circular shifts.", "100", 1, 256));
-    addOption("prefix", Option(Option::File, "o", "Output", "Output file.", "fingerprint_CFL.txt"));
+    addOption("type", Option(Option::File, "t", "", "Factorisation (lyn2vec --type_factorization): CFL, ICFL or CFL_ICFL-<C> (lyn2vec offers C = 10, 20, 30).", "CFL"));
+    addOption("prefix", Option(Option::File, "o", "Output", "Output file (default: fingerprint_<type>.txt).", ""));
 }
 
 int CommandFingerprint::run() const
@@ -790,6 +791,18 @@ int CommandFingerprint::run() const
         return 0;
     }
     const uint32_t window = (uint32_t)options.at("window").getArgumentAsNumber();
+    const string type = options.at("type").argument;
+    int factorization = FPM_FACT_CFL;
+    uint32_t subLen = 0;
+    if (type == "CFL") factorization = FPM_FACT_CFL;
+    else if (type == "ICFL") factorization = FPM_FACT_ICFL;
+    else if (type.compare(0, 9, "CFL_ICFL-") == 0 && type.size() > 9 && type.find_first_not_of("0123456789", 9) == string::npos) {
+        factorization = FPM_FACT_CFL_ICFL;
+        subLen = (uint32_t)atoi(type.c_str() + 9);
+    } else {
+        cerr << "ERROR: unknown factorisation \"" << type << "\" (CFL, ICFL, CFL_ICFL-<C>)." << endl;
+        return 1;
+    }
     vector<string> ids;
     vector<uint8_t> seq;
     vector<uint64_t> off{0};
@@ -825,17 +838,17 @@ int CommandFingerprint::run() const
     }
     seq.push_back(0);
     vector<uint64_t> woff(n + 1);
-    if (fpm_cfl_fingerprint_batch(gpuContext(), seq.data(), off.data(), n, window, 42, 0, nullptr, nullptr, nullptr, woff.data()) != FPM_OK) {
+    if (fpm_fingerprint_batch(gpuContext(), seq.data(), off.data(), n, window, factorization, subLen, 42, 0, nullptr, nullptr, nullptr, woff.data()) != FPM_OK) {
         cerr << "ERROR: " << fpm_last_error() << endl;
         return 1;
     }
     const uint64_t nWin = woff[n];
     vector<uint16_t> tok(nWin * window), ntok(nWin);
-    if (fpm_cfl_fingerprint_batch(gpuContext(), seq.data(), off.data(), n, window, 42, 0, nullptr, tok.data(), ntok.data(), woff.data()) != FPM_OK) {
+    if (fpm_fingerprint_batch(gpuContext(), seq.data(), off.data(), n, window, factorization, subLen, 42, 0, nullptr, tok.data(), ntok.data(), woff.data()) != FPM_OK) {
         cerr << "ERROR: " << fpm_last_error() << endl;
         return 1;
     }
-    const string outName = options.at("prefix").argument;
+    const string outName = options.at("prefix").argument != "" ? options.at("prefix").argument : "fingerprint_" + type + ".txt";
     ofstream out(outName);
     if (!out) {
         cerr << "ERROR: could not open " << outName << " for writing." << endl;

@@ -90,6 +90,8 @@ lib.fpm_sketch_stream_finish.argtypes = [_VP, C.POINTER(SketchParams), _VP, _VP,
 lib.fpm_kmer_hashes.argtypes = [_VP, C.POINTER(SketchParams), _VP, C.c_uint64, _VP, u64p]
 lib.fpm_fp_hash_batch.argtypes = [_VP, _VP, _VP, C.c_uint64, C.c_uint32, C.c_int, _VP]
 lib.fpm_cfl_fingerprint_batch.argtypes = [_VP, _VP, _VP, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, _VP, _VP, _VP, _VP]
+lib.fpm_fingerprint_batch.argtypes = [_VP, _VP, _VP, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, C.c_int, _VP, _VP, _VP, _VP]
+FACT_CFL, FACT_ICFL, FACT_CFL_ICFL = 0, 1, 2
 lib.fpm_dist_tile.argtypes = [_VP, C.POINTER(DistParams), C.POINTER(Panel), C.POINTER(Panel), _VP]
 lib.fpm_fp_positional_tile.argtypes = [_VP, C.POINTER(DistParams), C.POINTER(Panel), C.POINTER(Panel), _VP]
 lib.fpm_dist_tile_dev.argtypes = [_VP, C.POINTER(DistParams), C.POINTER(Panel), C.POINTER(Panel), _VP, _VP]
@@ -109,7 +111,7 @@ EXPORTED = ["fpm_abi_version", "fpm_device_count", "fpm_ctx_create", "fpm_ctx_de
             "fpm_ctx_sync", "fpm_ctx_stream", "fpm_ctx_set_stream", "fpm_host_alloc", "fpm_host_free",
             "fpm_ctx_launch_count", "fpm_sketch_batch", "fpm_sketch_batch_dev", "fpm_kmer_hashes",
             "fpm_sketch_stream_begin", "fpm_sketch_stream_append", "fpm_sketch_stream_end_group", "fpm_sketch_stream_finish",
-            "fpm_fp_hash_batch", "fpm_cfl_fingerprint_batch", "fpm_dist_tile", "fpm_dist_tile_dev", "fpm_fp_positional_tile", "fpm_pvalue", "fpm_distance",
+            "fpm_fp_hash_batch", "fpm_cfl_fingerprint_batch", "fpm_fingerprint_batch", "fpm_dist_tile", "fpm_dist_tile_dev", "fpm_fp_positional_tile", "fpm_pvalue", "fpm_distance",
             "fpm_measure_int32_peak", "fpm_get_int32_peaks", "fpm_ctx_set_timing", "fpm_ctx_get_timing", "fpm_ctx_set_dist_mode"]
 
 
@@ -306,24 +308,36 @@ class Context:
         _check(lib.fpm_fp_hash_batch(self._h, tok.ctypes.data, off.ctypes.data, len(lines), seed, int(use64), out.ctypes.data))
         return out
 
-    def cfl_fingerprint_batch(self, records, window=100, seed=42, use64=False):
-        """lyn2vec basic/CFL/shift on the GPU: records = list of bytes.  Returns (rows, hashes, window_offsets):
-        rows[w] = list of Lyndon factor lengths of window w, hashes[w] = getHashFingerPrint(rows[w])."""
+    def fingerprint_batch(self, records, window=100, factorization="CFL", seed=42, use64=False):
+        """lyn2vec basic/shift on the GPU: records = list of bytes; factorization = "CFL", "ICFL" or "CFL_ICFL-<C>"
+        (lyn2vec's --type_factorization).  Returns (rows, hashes, window_offsets): rows[w] = list of factor lengths
+        of window w, hashes[w] = getHashFingerPrint(rows[w])."""
+        if factorization == "CFL":
+            mode, sub = FACT_CFL, 0
+        elif factorization == "ICFL":
+            mode, sub = FACT_ICFL, 0
+        elif factorization.startswith("CFL_ICFL-"):
+            mode, sub = FACT_CFL_ICFL, int(factorization.split("-")[1])
+        else:
+            raise ValueError("unknown factorization " + factorization)
         off = np.zeros(len(records) + 1, dtype=np.uint64)
         for i, r in enumerate(records):
             off[i + 1] = off[i] + len(r)
         seq = np.frombuffer(b"".join(bytes(r) for r in records) + b"\0", dtype=np.uint8).copy()
         woff = np.zeros(len(records) + 1, dtype=np.uint64)
-        _check(lib.fpm_cfl_fingerprint_batch(self._h, seq.ctypes.data, off.ctypes.data, len(records), window, seed, int(use64),
-                                             None, None, None, woff.ctypes.data))
+        _check(lib.fpm_fingerprint_batch(self._h, seq.ctypes.data, off.ctypes.data, len(records), window, mode, sub, seed, int(use64),
+                                         None, None, None, woff.ctypes.data))
         nw = int(woff[-1])
         hashes = np.zeros(nw, dtype=np.uint64)
         tok = np.zeros((nw, window), dtype=np.uint16)
         ntok = np.zeros(nw, dtype=np.uint16)
-        _check(lib.fpm_cfl_fingerprint_batch(self._h, seq.ctypes.data, off.ctypes.data, len(records), window, seed, int(use64),
-                                             hashes.ctypes.data, tok.ctypes.data, ntok.ctypes.data, woff.ctypes.data))
+        _check(lib.fpm_fingerprint_batch(self._h, seq.ctypes.data, off.ctypes.data, len(records), window, mode, sub, seed, int(use64),
+                                         hashes.ctypes.data, tok.ctypes.data, ntok.ctypes.data, woff.ctypes.data))
         rows = [tok[w, :ntok[w]].tolist() for w in range(nw)]
         return rows, hashes, woff
+
+    def cfl_fingerprint_batch(self, records, window=100, seed=42, use64=False):
+        return self.fingerprint_batch(records, window, "CFL", seed, use64)
 
     # -- dist -----------------------------------------------------------------------------
     @staticmethod

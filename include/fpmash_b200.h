@@ -137,6 +137,16 @@ int fpm_fp_hash_batch(fpm_ctx* ctx, const uint64_t* tokens, const uint64_t* line
 int fpm_cfl_fingerprint_batch(fpm_ctx* ctx, const uint8_t* seq, const uint64_t* rec_offsets, uint32_t n_records, uint32_t window,
                               uint32_t seed, int use64, uint64_t* out_hashes, uint16_t* out_tokens, uint16_t* out_ntokens,
                               uint64_t* out_window_offsets);
+/* The same with the factorisation chosen (lyn2vec --type_factorization): FPM_FACT_CFL (Duval,
+ * factorizations.py:102-126), FPM_FACT_ICFL (inverse Lyndon factorisation, ICFL_recursive, :143-248) or
+ * FPM_FACT_CFL_ICFL (CFL_icfl, :265-300: CFL factors longer than sub_len are sub-factorised with ICFL; lyn2vec's
+ * CFL_ICFL-10/-20/-30 are sub_len = 10/20/30).  sub_len is ignored by the other two.                           */
+#define FPM_FACT_CFL 0
+#define FPM_FACT_ICFL 1
+#define FPM_FACT_CFL_ICFL 2
+int fpm_fingerprint_batch(fpm_ctx* ctx, const uint8_t* seq, const uint64_t* rec_offsets, uint32_t n_records, uint32_t window,
+                          int factorization, uint32_t sub_len, uint32_t seed, int use64, uint64_t* out_hashes,
+                          uint16_t* out_tokens, uint16_t* out_ntokens, uint64_t* out_window_offsets);
 
 /* ---- dist ---------------------------------------------------------------------------- */
 

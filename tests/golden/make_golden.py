@@ -5,13 +5,18 @@
 1. copies the reference's own fixtures for the sketch/dist path (data files, not sources);
    large text inputs are gzipped with mtime 0 so the bytes are reproducible;
 2. generates known-answer vectors by calling the reference's own hash.cpp / MinHashHeap.cpp
-   (oracle/_ref/libmashref.so) on seeded inputs -> ref_vectors.json.
+   (oracle/_ref/libmashref.so) on seeded inputs -> ref_vectors.json;
+3. runs the reference's own lyn2vec (README.md:34-52 recipe) on DNA1.fasta with --type_factorization ICFL and
+   CFL_ICFL-30 -> DNA1-ICFL.txt.gz, DNA1-CFL_ICFL-30.txt.gz (the CFL run reproduces the shipped DNA1-CFL.txt
+   byte for byte, which is checked here).
 """
 import gzip
 import json
 import os
 import shutil
+import subprocess
 import sys
+import tempfile
 
 import numpy as np
 
@@ -54,6 +59,20 @@ def main():
         with open(os.path.join(REF, src), "rb") as f, open(os.path.join(HERE, dst), "wb") as raw:
             with gzip.GzipFile(filename="", mode="wb", fileobj=raw, mtime=0, compresslevel=9) as g:
                 g.write(f.read())
+
+    # lyn2vec, run as the README runs it (it writes fingerprint_<type>.txt next to the FASTA file)
+    with tempfile.TemporaryDirectory() as d:
+        shutil.copyfile(os.path.join(REF, "training/Umberto/CFL/DNA1.fasta"), os.path.join(d, "DNA1.fasta"))
+        for fact in ("CFL", "ICFL", "CFL_ICFL-30"):
+            subprocess.run([sys.executable, "lyn2vec.py", "--type", "basic", "--path", d + "/", "--fasta", "DNA1.fasta", "--type_factorization", fact,
+                            "--rev_comb", "true", "-n", "4"], cwd=os.path.join(REF, "lyn2vec"), check=True, stdout=subprocess.DEVNULL)
+            data = open(os.path.join(d, "fingerprint_%s.txt" % fact), "rb").read()
+            if fact == "CFL":
+                assert data == open(os.path.join(REF, "training/Umberto/CFL/DNA1-CFL.txt"), "rb").read(), "lyn2vec no longer reproduces DNA1-CFL.txt"
+                continue
+            with open(os.path.join(HERE, "DNA1-%s.txt.gz" % fact), "wb") as raw:
+                with gzip.GzipFile(filename="", mode="wb", fileobj=raw, mtime=0, compresslevel=9) as g:
+                    g.write(data)
 
     from oracle_py import RefLib, build
     build(ref=True)

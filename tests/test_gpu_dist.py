@@ -169,3 +169,30 @@ def test_dist_rank32_sizes_sweep(ctx, n, ragged):
     assert np.array_equal(got32, got64) and np.array_equal(pass32, pass64)
     full = sz == s
     assert (np.diag(got32["numer"])[full] == s).all()
+
+
+def test_dist_structured_edge_cases(dctx, oracle):
+    """Hand-built list shapes around the loop's exits (CommandDistance.cpp:376-400): sizes 0/1/s-1/s/s+1, identical,
+    disjoint-interleaved, one list a prefix / suffix / subset of the other, all matches after the cut-off."""
+    s = 64
+    base = np.arange(1, 4 * s + 1, dtype=np.uint64) * np.uint64(1 << 40)
+    lists = [
+        base[:0], base[:1], base[:s - 1], base[:s], base[:s + 1],      # sizes around s
+        base[::2][:s], base[1::2][:s],                                  # disjoint, perfectly interleaved
+        base[s:2 * s], base[s // 2:s // 2 + s],                         # shifted windows (suffix/prefix overlaps)
+        base[:2 * s:3], base[2 * s:3 * s],                              # sparse subset; entirely beyond the others
+        np.concatenate([base[1:s:2], base[3 * s:3 * s + s // 2]]),      # shares only early elements
+        np.concatenate([base[:3], base[3 * s + 5:3 * s + 5 + s - 3]]),  # three early matches, the rest far away
+        base[s - 1:s], base[4 * s - 1:],                                # single elements at the cut-off / at the very end
+    ]
+    n = len(lists)
+    width = max(len(x) for x in lists)
+    h = np.zeros((n, max(width, 1)), dtype=np.uint64)
+    sz = np.zeros(n, dtype=np.uint32)
+    for i, x in enumerate(lists):
+        h[i, :len(x)] = x
+        sz[i] = len(x)
+    ln = np.arange(1000, 1000 + n, dtype=np.uint64) * np.uint64(977)
+    for s_cmp in (s, s - 1, 1, 3 * s):
+        got, passed = dctx.dist_tile((h, sz, ln), (h, sz, ln), s_cmp, 21, 4.0 ** 21)
+        _compare(got, passed, _oracle_matrix(oracle, (h, sz, ln), (h, sz, ln), s_cmp, 21, 4.0 ** 21))
