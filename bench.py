@@ -302,10 +302,10 @@ def main():
     assert int(out_n.min().item()) == S, "sketches are not full"
 
     # ---- sketch: e2e (pinned host buffers through the host-pointer C-ABI call) ----------------
-    host_seq_t = torch.empty(seq.numel(), dtype=torch.uint8, pin_memory=True)
-    host_seq_t.copy_(seq)
+    pinned_seq = fpm.PinnedBuffer(seq.numel())      # page-locked, on the NUMA node of this rank's GPU
+    host_seq = pinned_seq.array
+    torch.from_numpy(host_seq).copy_(seq)
     torch.cuda.synchronize()
-    host_seq = host_seq_t.numpy()
     e2e_res = None
     for _ in range(max(1, args.warmup)):
         e2e_res = ctx.sketch_batch(host_seq, offsets, params)

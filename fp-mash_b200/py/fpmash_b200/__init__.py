@@ -120,6 +120,28 @@ def _check(rc):
         raise FpmError(rc, lib.fpm_last_error().decode("utf-8", "replace"))
 
 
+class PinnedBuffer:
+    """Page-locked host memory from fpm_host_alloc (placed on the current device's NUMA node) as a numpy uint8 array."""
+
+    def __init__(self, nbytes):
+        p = _VP()
+        _check(lib.fpm_host_alloc(int(nbytes), C.byref(p)))
+        self._p = p
+        self.array = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(int(nbytes),))
+
+    def close(self):
+        if self._p:
+            self.array = None
+            lib.fpm_host_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def device_count():
     return lib.fpm_device_count()
 
