@@ -47,6 +47,9 @@ struct fpm_ctx {
     std::vector<uint64_t> stream_goff;
     // dist scratch
     fpm::DevBuf d_ref, d_qry, d_rs, d_qs, d_rl, d_ql, d_out, d_misc, d_p32, d_rank;
+    // FASTA ingestion (fpm_fasta_parse): raw bytes, compacted sequence, per-chunk scan arrays, record table
+    fpm::DevBuf fa_raw, fa_seq, fa_chunk, fa_recs;
+    uint64_t fa_records = 0, fa_seq_bytes = 0;
     bool force_dist64 = false;                   // tests: run the 64-bit tile kernel although the 32-bit rank path applies
     // optional per-kernel event timing (bench roofline): pairs of events around each launch
     bool timing = false;

@@ -1,0 +1,328 @@
+// fasta_parse.cu -- FASTA ingestion on the GPU (first half): raw file bytes in, the sketch
+// kernel's batch layout out (records back to back, each followed by one 0x00), plus a record table.
+//
+// Replaces, for plain FASTA, the byte loop of the reference's kseq.h reader (2009 version, kseq.h:170-208) as
+// mirrored by host/fastx.cpp:
+//   * a record starts at the next '>'; its header runs to the next '\n';
+//   * the sequence is every isgraph() byte (33..126) up to the next '>' -- ANYWHERE, not only at a line start --
+//     everything else ('\n', '\r', blanks) is dropped; bytes before the first '>' of a file are skipped.
+// '+' and '@' also end a record there (FASTQ); this parser does not follow them: it reports FPM_FASTA_NOT_PLAIN
+// and the caller uses the host reader for that input.  Several files go into one call separated by a 0x00 byte
+// (which resets the state machine; a file that itself contains 0x00 must take the host reader).
+//
+// The reader is a three-state automaton (PRE: before the first header of a file, SEQ, HDR) whose transitions
+// are functions on three states, so "state before byte i" is a prefix scan under function composition:
+//   fasta_chunk_fn_kernel   one warp per 4 KB chunk: the chunk's transition function from its last reset / '>' / '\n'
+//   fasta_scan_kernel       one CTA: exclusive scan of the chunk functions (-> state at every chunk start), and
+//                           later of the per-chunk output / record counts
+//   fasta_emit_kernel<0|1>  one warp per chunk, 128 bytes per step: a lane composes its 4 bytes, a warp scan gives
+//                           every lane its start state; pass 0 counts kept bytes and records, pass 1 writes them
+#include "common.h"
+
+namespace fpm {
+
+constexpr int FA_CHUNK = 4096;
+constexpr uint32_t ST_PRE = 0, ST_SEQ = 1, ST_HDR = 2;
+constexpr uint32_t FN_ID = 0u | (1u << 2) | (2u << 4);         // f(s) in bits [2s+1 : 2s]
+
+__device__ __forceinline__ uint32_t fn_apply(uint32_t f, uint32_t s) { return (f >> (2 * s)) & 3u; }
+// first f, then g
+__device__ __forceinline__ uint32_t fn_then(uint32_t f, uint32_t g)
+{
+    return fn_apply(g, f & 3u) | (fn_apply(g, (f >> 2) & 3u) << 2) | (fn_apply(g, (f >> 4) & 3u) << 4);
+}
+__device__ __forceinline__ uint32_t fn_of_byte(uint32_t b)
+{
+    if (b == 0) return 0u;                                        // reset: everything -> PRE
+    if (b == '>') return ST_HDR | (ST_HDR << 2) | (ST_HDR << 4);
+    if (b == '\n') return ST_PRE | (ST_SEQ << 2) | (ST_SEQ << 4);
+    return FN_ID;
+}
+__device__ __forceinline__ uint32_t step_state(uint32_t s, uint32_t b)
+{
+    if (b == 0) return ST_PRE;
+    if (b == '>') return ST_HDR;
+    if (b == '\n' && s == ST_HDR) return ST_SEQ;
+    return s;
+}
+
+// 4 bytes at raw[pos .. pos+4) as a little-endian word; bytes at or beyond n read as ' ' (dropped, no state change)
+__device__ __forceinline__ uint32_t load4(const uint8_t* __restrict__ raw, uint64_t pos, uint64_t n)
+{
+    if (pos + 4 <= n) return *reinterpret_cast<const uint32_t*>(raw + pos);
+    uint32_t w = 0x20202020u;
+    for (int j = 0; j < 4; j++)
+        if (pos + j < n) w = (w & ~(0xffu << (8 * j))) | ((uint32_t)raw[pos + j] << (8 * j));
+    return w;
+}
+
+__global__ void __launch_bounds__(256) fasta_chunk_fn_kernel(const uint8_t* __restrict__ raw, uint64_t n, uint64_t n_chunks, uint8_t* __restrict__ chunk_fn)
+{
+    const uint64_t chunk = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (chunk >= n_chunks) return;
+    const uint64_t base = chunk * FA_CHUNK;
+    int lastR = -1, lastG = -1, lastN = -1;                       // chunk-relative positions of the last reset / '>' / '\n'
+    for (int off = 4 * lane; off < FA_CHUNK; off += 128) {
+        if (base + off >= n) break;
+        const uint32_t w = load4(raw, base + off, n);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t b = (w >> (8 * j)) & 0xffu;
+            if (b == 0) lastR = off + j;
+            else if (b == '>') lastG = off + j;
+            else if (b == '\n') lastN = off + j;
+        }
+    }
+    for (int o = 16; o; o >>= 1) {
+        lastR = max(lastR, __shfl_xor_sync(0xffffffffu, lastR, o));
+        lastG = max(lastG, __shfl_xor_sync(0xffffffffu, lastG, o));
+        lastN = max(lastN, __shfl_xor_sync(0xffffffffu, lastN, o));
+    }
+    if (lane == 0) {
+        uint32_t f = 0;
+        for (uint32_t s = 0; s < 3; s++) {
+            uint32_t t = lastR >= 0 ? ST_PRE : s;
+            if (lastG > lastR) t = lastN > lastG ? ST_SEQ : ST_HDR;
+            else if (t == ST_HDR && lastN > lastR) t = ST_SEQ;
+            f |= t << (2 * s);
+        }
+        chunk_fn[chunk] = (uint8_t)f;
+    }
+}
+
+// One CTA.  mode 0: chunk_fn -> start_state (exclusive scan under composition, applied to PRE).
+//           mode 1: counts (bytes | records) -> exclusive prefix sums, totals in totals[0..1].
+__global__ void __launch_bounds__(1024) fasta_scan_kernel(int mode, uint64_t n_chunks, const uint8_t* __restrict__ chunk_fn, uint8_t* __restrict__ start_state,
+                                                           const uint32_t* __restrict__ cnt_bytes, const uint32_t* __restrict__ cnt_recs,
+                                                           uint64_t* __restrict__ off_bytes, uint64_t* __restrict__ off_recs, uint64_t* __restrict__ totals)
+{
+    __shared__ uint32_t s_fn[32];
+    __shared__ uint64_t s_a[32], s_b[32];
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    uint32_t carry_fn = FN_ID;
+    uint64_t carry_a = 0, carry_b = 0;
+    for (uint64_t tile = 0; tile < n_chunks; tile += 1024) {
+        const uint64_t c = tile + t;
+        if (mode == 0) {
+            uint32_t f = c < n_chunks ? chunk_fn[c] : FN_ID;
+            uint32_t inc = f;                                      // inclusive scan within the warp
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t up = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc = fn_then(up, inc);
+            }
+            if (lane == 31) s_fn[wid] = inc;
+            __syncthreads();
+            if (wid == 0) {
+                uint32_t w = s_fn[lane], winc = w;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t up = __shfl_up_sync(0xffffffffu, winc, o);
+                    if (lane >= o) winc = fn_then(up, winc);
+                }
+                s_fn[lane] = winc;                                  // inclusive over warps
+            }
+            __syncthreads();
+            uint32_t excl = __shfl_up_sync(0xffffffffu, inc, 1);    // exclusive within the warp
+            if (lane == 0) excl = FN_ID;
+            uint32_t before = wid ? fn_then(s_fn[wid - 1], excl) : excl;
+            before = fn_then(carry_fn, before);
+            if (c < n_chunks) start_state[c] = (uint8_t)fn_apply(before, ST_PRE);
+            carry_fn = fn_then(carry_fn, s_fn[31]);
+            __syncthreads();
+        } else {
+            uint64_t a = c < n_chunks ? cnt_bytes[c] : 0, b = c < n_chunks ? cnt_recs[c] : 0;
+            uint64_t ia = a, ib = b;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint64_t ua = __shfl_up_sync(0xffffffffu, ia, o), ub = __shfl_up_sync(0xffffffffu, ib, o);
+                if (lane >= o) { ia += ua; ib += ub; }
+            }
+            if (lane == 31) { s_a[wid] = ia; s_b[wid] = ib; }
+            __syncthreads();
+            if (wid == 0) {
+                uint64_t wa = s_a[lane], wb = s_b[lane];
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint64_t ua = __shfl_up_sync(0xffffffffu, wa, o), ub = __shfl_up_sync(0xffffffffu, wb, o);
+                    if (lane >= o) { wa += ua; wb += ub; }
+                }
+                s_a[lane] = wa; s_b[lane] = wb;
+            }
+            __syncthreads();
+            const uint64_t pa = carry_a + (wid ? s_a[wid - 1] : 0) + ia - a, pb = carry_b + (wid ? s_b[wid - 1] : 0) + ib - b;
+            if (c < n_chunks) { off_bytes[c] = pa; off_recs[c] = pb; }
+            carry_a += s_a[31]; carry_b += s_b[31];
+            __syncthreads();
+        }
+    }
+    if (mode == 1 && t == 0) { totals[0] = carry_a; totals[1] = carry_b; }
+}
+
+// WRITE = false: count kept bytes (sequence + separators) and record starts per chunk.
+// WRITE = true:  write them at the scanned offsets and fill the record table.
+template <bool WRITE>
+__global__ void __launch_bounds__(256) fasta_emit_kernel(const uint8_t* __restrict__ raw, uint64_t n, uint64_t n_chunks, const uint8_t* __restrict__ start_state,
+                                                         uint32_t* __restrict__ cnt_bytes, uint32_t* __restrict__ cnt_recs,
+                                                         const uint64_t* __restrict__ off_bytes, const uint64_t* __restrict__ off_recs,
+                                                         uint8_t* __restrict__ out, fpm_fasta_record* __restrict__ recs, uint32_t* __restrict__ flags)
+{
+    const uint64_t chunk = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (chunk >= n_chunks) return;
+    const uint64_t base = chunk * FA_CHUNK;
+    uint32_t state = start_state[chunk];                          // warp-uniform: state before the current 128-byte slice
+    uint64_t out_pos = WRITE ? off_bytes[chunk] : 0, rec_idx = WRITE ? off_recs[chunk] : 0;
+    uint32_t tot_bytes = 0, tot_recs = 0, bad = 0;
+    for (int off = 0; off < FA_CHUNK; off += 128) {
+        if (base + off >= n) break;
+        const uint64_t pos = base + off + 4 * lane;
+        const uint32_t w = pos < n ? load4(raw, pos, n) : 0x20202020u;
+        // my four bytes as a transition function, then the state before my first byte
+        uint32_t f = FN_ID;
+#pragma unroll
+        for (int j = 0; j < 4; j++) f = fn_then(f, fn_of_byte((w >> (8 * j)) & 0xffu));
+        uint32_t inc = f;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc = fn_then(up, inc);
+        }
+        uint32_t excl = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane == 0) excl = FN_ID;
+        uint32_t s = fn_apply(excl, state);
+        const uint32_t slice_fn = __shfl_sync(0xffffffffu, inc, 31);
+        // walk my four bytes: what do they emit?
+        uint32_t nb = 0, nr = 0;
+        uint8_t ob[8];                                              // at most a separator + a byte per input byte
+        uint32_t rec_at[4], rec_sep[4], hdr_end_at[4];
+        uint32_t n_rec_local = 0, n_hend = 0;
+        uint32_t hend_before[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t b = (w >> (8 * j)) & 0xffu;
+            if (pos + j < n) {
+                if (b == '>' && s != ST_HDR) {                      // a record starts; the previous one (if any) gets its separator
+                    const uint32_t sep = s == ST_SEQ;
+                    if (sep) ob[nb++] = 0;
+                    rec_at[n_rec_local] = j; rec_sep[n_rec_local] = nb; n_rec_local++;
+                    nr++;
+                } else if (b == 0) {                                // end of a file
+                    if (s == ST_HDR) { hdr_end_at[n_hend] = j; hend_before[n_hend] = nr; n_hend++; }
+                    if (s != ST_PRE) ob[nb++] = 0;
+                } else if (s == ST_HDR) {
+                    if (b == '\n') { hdr_end_at[n_hend] = j; hend_before[n_hend] = nr; n_hend++; }
+                } else if (b == '+' || b == '@') {
+                    if (s == ST_SEQ || b == '@') bad = 1;           // FASTQ: not this parser's job
+                } else if (s == ST_SEQ && b >= 33 && b <= 126) {
+                    ob[nb++] = (uint8_t)b;
+                }
+            }
+            s = step_state(s, b);
+        }
+        // exclusive prefix of (bytes, records) over the lanes
+        uint32_t packed = nb | (nr << 16), pinc = packed;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, pinc, o);
+            if (lane >= o) pinc += up;
+        }
+        const uint32_t pex = pinc - packed, slice_tot = __shfl_sync(0xffffffffu, pinc, 31);
+        if (WRITE) {
+            const uint64_t my_out = out_pos + (pex & 0xffffu), my_rec = rec_idx + (pex >> 16);
+            for (uint32_t i = 0; i < nb; i++) out[my_out + i] = ob[i];
+            for (uint32_t r = 0; r < n_rec_local; r++) {
+                recs[my_rec + r].hdr_begin = pos + rec_at[r];
+                recs[my_rec + r].seq_begin = my_out + rec_sep[r];
+            }
+            for (uint32_t h = 0; h < n_hend; h++) recs[my_rec + hend_before[h] - 1].hdr_end = pos + hdr_end_at[h];
+        }
+        out_pos += slice_tot & 0xffffu;
+        rec_idx += slice_tot >> 16;
+        tot_bytes += slice_tot & 0xffffu;
+        tot_recs += slice_tot >> 16;
+        state = fn_apply(slice_fn, state);
+    }
+    if (!WRITE) {
+        bad = __any_sync(0xffffffffu, bad);
+        if (lane == 0) {
+            cnt_bytes[chunk] = tot_bytes;
+            cnt_recs[chunk] = tot_recs;
+            if (bad) atomicOr(flags, 1u);
+        }
+    }
+}
+
+}  // namespace fpm
+
+using namespace fpm;
+
+extern "C" {
+
+int fpm_fasta_parse(fpm_ctx* ctx, const uint8_t* raw, uint64_t n_bytes, uint64_t* out_n_records, uint64_t* out_seq_bytes, int* out_status)
+{
+    if (!ctx) { set_error("ctx is NULL"); return FPM_ERR_ARG; }
+    if (!out_n_records || !out_seq_bytes || !out_status) { set_error("NULL output"); return FPM_ERR_ARG; }
+    if (!raw && n_bytes) { set_error("raw is NULL"); return FPM_ERR_ARG; }
+    *out_n_records = 0; *out_seq_bytes = 0; *out_status = FPM_FASTA_OK;
+    ctx->fa_records = 0; ctx->fa_seq_bytes = 0;
+    if (n_bytes == 0) return FPM_OK;
+    FPM_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const uint64_t n_chunks = (n_bytes + FA_CHUNK - 1) / FA_CHUNK;
+    if (n_chunks * 32 > 0x7fffffffull * 256) { set_error("FASTA batch too large"); return FPM_ERR_ARG; }
+    int rc;
+    if ((rc = ctx->fa_raw.ensure(n_bytes + 64))) return rc;
+    if ((rc = ctx->fa_seq.ensure(n_bytes + 64))) return rc;          // kept bytes + separators never exceed the input
+    if ((rc = ctx->fa_chunk.ensure(n_chunks * (1 + 1 + 4 + 4 + 8 + 8) + 256))) return rc;
+    if ((rc = ctx->d_misc.ensure(64))) return rc;
+    unsigned char* cb = ctx->fa_chunk.as<unsigned char>();
+    uint64_t* off_bytes = (uint64_t*)cb;                             // 8-byte fields first (alignment)
+    uint64_t* off_recs = off_bytes + n_chunks;
+    uint32_t* cnt_bytes = (uint32_t*)(off_recs + n_chunks);
+    uint32_t* cnt_recs = cnt_bytes + n_chunks;
+    uint8_t* chunk_fn = (uint8_t*)(cnt_recs + n_chunks);
+    uint8_t* start_state = chunk_fn + n_chunks;
+    uint64_t* totals = ctx->d_misc.as<uint64_t>() + 2;               // d_misc: [flags | pad | totals[2]]
+    FPM_CUDA(cudaMemsetAsync(ctx->d_misc.p, 0, 64, st));
+    FPM_CUDA(cudaMemcpyAsync(ctx->fa_raw.p, raw, n_bytes, cudaMemcpyHostToDevice, st));
+    const uint32_t grid = (uint32_t)((n_chunks * 32 + 255) / 256);
+    const uint8_t* d_raw = ctx->fa_raw.as<uint8_t>();
+    fasta_chunk_fn_kernel<<<grid, 256, 0, st>>>(d_raw, n_bytes, n_chunks, chunk_fn);
+    fasta_scan_kernel<<<1, 1024, 0, st>>>(0, n_chunks, chunk_fn, start_state, nullptr, nullptr, nullptr, nullptr, nullptr);
+    fasta_emit_kernel<false><<<grid, 256, 0, st>>>(d_raw, n_bytes, n_chunks, start_state, cnt_bytes, cnt_recs, nullptr, nullptr, nullptr, nullptr,
+                                                   ctx->d_misc.as<uint32_t>());
+    fasta_scan_kernel<<<1, 1024, 0, st>>>(1, n_chunks, nullptr, nullptr, cnt_bytes, cnt_recs, off_bytes, off_recs, totals);
+    ctx->launches += 4;
+    FPM_CUDA(cudaGetLastError());
+    uint64_t h[4] = {0, 0, 0, 0};
+    FPM_CUDA(cudaMemcpyAsync(h, ctx->d_misc.p, 32, cudaMemcpyDeviceToHost, st));
+    FPM_CUDA(cudaStreamSynchronize(st));
+    if ((uint32_t)h[0] & 1u) { *out_status = FPM_FASTA_NOT_PLAIN; return FPM_OK; }
+    const uint64_t seq_bytes = h[2], n_rec = h[3];
+    if ((rc = ctx->fa_recs.ensure(sizeof(fpm_fasta_record) * std::max<uint64_t>(n_rec, 1)))) return rc;
+    fasta_emit_kernel<true><<<grid, 256, 0, st>>>(d_raw, n_bytes, n_chunks, start_state, nullptr, nullptr, off_bytes, off_recs, ctx->fa_seq.as<uint8_t>(),
+                                                  ctx->fa_recs.as<fpm_fasta_record>(), nullptr);
+    ctx->launches++;
+    FPM_CUDA(cudaGetLastError());
+    ctx->fa_records = n_rec;
+    ctx->fa_seq_bytes = seq_bytes;
+    *out_n_records = n_rec;
+    *out_seq_bytes = seq_bytes;
+    return FPM_OK;
+}
+
+int fpm_fasta_records(fpm_ctx* ctx, fpm_fasta_record* out)
+{
+    if (!ctx || !out) { set_error("NULL argument"); return FPM_ERR_ARG; }
+    FPM_CUDA(cudaSetDevice(ctx->device));
+    if (ctx->fa_records) FPM_CUDA(cudaMemcpyAsync(out, ctx->fa_recs.p, sizeof(fpm_fasta_record) * ctx->fa_records, cudaMemcpyDeviceToHost, ctx->stream));
+    FPM_CUDA(cudaStreamSynchronize(ctx->stream));
+    return FPM_OK;
+}
+
+int fpm_fasta_sequence(fpm_ctx* ctx, uint8_t* out)
+{
+    if (!ctx || !out) { set_error("NULL argument"); return FPM_ERR_ARG; }
+    FPM_CUDA(cudaSetDevice(ctx->device));
+    if (ctx->fa_seq_bytes) FPM_CUDA(cudaMemcpyAsync(out, ctx->fa_seq.p, ctx->fa_seq_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    FPM_CUDA(cudaStreamSynchronize(ctx->stream));
+    return FPM_OK;
+}
+
+}  // extern "C"

@@ -424,6 +424,33 @@ int fpm_sketch_batch(fpm_ctx* ctx, const fpm_sketch_params* p, const uint8_t* se
     return FPM_OK;
 }
 
+int fpm_sketch_parsed(fpm_ctx* ctx, const fpm_sketch_params* p, const uint64_t* group_offsets, uint32_t n_groups, uint64_t* out_hashes,
+                      uint32_t* out_counts, uint32_t* out_n)
+{
+    if (!ctx) { set_error("ctx is NULL"); return FPM_ERR_ARG; }
+    int rc = check_params(p);
+    if (rc) return rc;
+    if (n_groups == 0) return FPM_OK;
+    if (!group_offsets || group_offsets[0] != 0 || group_offsets[n_groups] != ctx->fa_seq_bytes) {
+        set_error("group_offsets must start at 0 and end at the parsed sequence's size");
+        return FPM_ERR_ARG;
+    }
+    FPM_CUDA(cudaSetDevice(ctx->device));
+    const uint64_t s = p->sketch_size;
+    if ((rc = ctx->outh.ensure(sizeof(uint64_t) * n_groups * s))) return rc;
+    if ((rc = ctx->outc.ensure(sizeof(uint32_t) * n_groups * s))) return rc;
+    if ((rc = ctx->outn.ensure(sizeof(uint32_t) * n_groups))) return rc;
+    const bool counts = p->want_counts && out_counts;
+    rc = sketch_batch_dev_impl(ctx, p, ctx->fa_seq.as<uint8_t>(), ctx->fa_seq_bytes, group_offsets, n_groups, ctx->outh.as<uint64_t>(),
+                               counts ? ctx->outc.as<uint32_t>() : nullptr, ctx->outn.as<uint32_t>(), nullptr);
+    if (rc) return rc;
+    FPM_CUDA(cudaMemcpyAsync(out_hashes, ctx->outh.p, sizeof(uint64_t) * n_groups * s, cudaMemcpyDeviceToHost, ctx->stream));
+    if (counts) FPM_CUDA(cudaMemcpyAsync(out_counts, ctx->outc.p, sizeof(uint32_t) * n_groups * s, cudaMemcpyDeviceToHost, ctx->stream));
+    FPM_CUDA(cudaMemcpyAsync(out_n, ctx->outn.p, sizeof(uint32_t) * n_groups, cudaMemcpyDeviceToHost, ctx->stream));
+    FPM_CUDA(cudaStreamSynchronize(ctx->stream));
+    return FPM_OK;
+}
+
 // ---- streaming input: sequence arrives in pieces, is accumulated in HBM, sketched once at the end -------
 // (read sets far larger than any pinned staging buffer: `mash sketch -r` reads everything into ONE sketch)
 

@@ -101,6 +101,11 @@ lib.fpm_distance.restype = C.c_double
 lib.fpm_distance.argtypes = [C.c_uint64, C.c_uint64, C.c_int]
 lib.fpm_measure_int32_peak.argtypes = [_VP, C.POINTER(C.c_double)]
 lib.fpm_get_int32_peaks.argtypes = [_VP, C.POINTER(C.c_double)]
+lib.fpm_fasta_parse.argtypes = [_VP, _VP, C.c_uint64, u64p, u64p, C.POINTER(C.c_int)]
+lib.fpm_fasta_records.argtypes = [_VP, _VP]
+lib.fpm_fasta_sequence.argtypes = [_VP, _VP]
+lib.fpm_sketch_parsed.argtypes = [_VP, C.POINTER(SketchParams), _VP, C.c_uint32, _VP, _VP, _VP]
+FASTA_RECORD_DTYPE = np.dtype([("hdr_begin", "<u8"), ("hdr_end", "<u8"), ("seq_begin", "<u8")])
 lib.fpm_ctx_set_timing.argtypes = [_VP, C.c_int]
 lib.fpm_ctx_set_dist_mode.argtypes = [_VP, C.c_int]
 lib.fpm_ctx_get_timing.argtypes = [_VP, C.c_int, C.POINTER(C.c_double), u64p]
@@ -112,7 +117,8 @@ EXPORTED = ["fpm_abi_version", "fpm_device_count", "fpm_ctx_create", "fpm_ctx_de
             "fpm_ctx_launch_count", "fpm_sketch_batch", "fpm_sketch_batch_dev", "fpm_kmer_hashes",
             "fpm_sketch_stream_begin", "fpm_sketch_stream_append", "fpm_sketch_stream_end_group", "fpm_sketch_stream_finish",
             "fpm_fp_hash_batch", "fpm_cfl_fingerprint_batch", "fpm_fingerprint_batch", "fpm_dist_tile", "fpm_dist_tile_dev", "fpm_fp_positional_tile", "fpm_pvalue", "fpm_distance",
-            "fpm_measure_int32_peak", "fpm_get_int32_peaks", "fpm_ctx_set_timing", "fpm_ctx_get_timing", "fpm_ctx_set_dist_mode"]
+            "fpm_measure_int32_peak", "fpm_get_int32_peaks", "fpm_ctx_set_timing", "fpm_ctx_get_timing", "fpm_ctx_set_dist_mode",
+            "fpm_fasta_parse", "fpm_fasta_records", "fpm_fasta_sequence", "fpm_sketch_parsed"]
 
 
 def _check(rc):
@@ -360,6 +366,41 @@ class Context:
 
     def cfl_fingerprint_batch(self, records, window=100, seed=42, use64=False):
         return self.fingerprint_batch(records, window, "CFL", seed, use64)
+
+    # -- FASTA ingestion ------------------------------------------------------------------
+    def fasta_parse(self, files, fetch_sequence=True):
+        """files: list of bytes (raw FASTA file contents, without 0x00).  Returns None when the input is not plain
+        FASTA, else (records, lengths, sequence): records = FASTA_RECORD_DTYPE array, lengths[i] = sequence length
+        of record i, sequence = the compacted batch (records each followed by 0x00) or None."""
+        raw = np.frombuffer(b"".join(bytes(f) + b"\0" for f in files), dtype=np.uint8).copy()
+        nrec, nseq, status = C.c_uint64(0), C.c_uint64(0), C.c_int(0)
+        _check(lib.fpm_fasta_parse(self._h, raw.ctypes.data, raw.size, C.byref(nrec), C.byref(nseq), C.byref(status)))
+        if status.value != 0:
+            return None
+        recs = np.zeros(nrec.value, dtype=FASTA_RECORD_DTYPE)
+        if nrec.value:
+            _check(lib.fpm_fasta_records(self._h, recs.ctypes.data))
+        nxt = np.append(recs["seq_begin"][1:], np.uint64(nseq.value)) if nrec.value else np.zeros(0, dtype=np.uint64)
+        lengths = (nxt - recs["seq_begin"] - np.uint64(1)).astype(np.uint64) if nrec.value else nxt
+        seq = None
+        if fetch_sequence:
+            seq = np.zeros(max(nseq.value, 1), dtype=np.uint8)
+            if nseq.value:
+                _check(lib.fpm_fasta_sequence(self._h, seq.ctypes.data))
+            seq = seq[:nseq.value]
+        return recs, lengths, seq
+
+    def sketch_parsed(self, group_offsets, params):
+        """Sketch the sequence the last fasta_parse left on the device."""
+        goff = np.ascontiguousarray(group_offsets, dtype=np.uint64)
+        n = len(goff) - 1
+        s = params.sketch_size
+        hashes = np.zeros((n, s), dtype=np.uint64)
+        counts = np.zeros((n, s), dtype=np.uint32)
+        out_n = np.zeros(n, dtype=np.uint32)
+        _check(lib.fpm_sketch_parsed(self._h, C.byref(params), goff.ctypes.data, n, hashes.ctypes.data,
+                                     counts.ctypes.data if params.want_counts else None, out_n.ctypes.data))
+        return {"hashes": hashes, "counts": counts, "n": out_n}
 
     # -- dist -----------------------------------------------------------------------------
     @staticmethod

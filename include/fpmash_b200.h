@@ -148,6 +148,31 @@ int fpm_fingerprint_batch(fpm_ctx* ctx, const uint8_t* seq, const uint64_t* rec_
                           int factorization, uint32_t sub_len, uint32_t seed, int use64, uint64_t* out_hashes,
                           uint16_t* out_tokens, uint16_t* out_ntokens, uint64_t* out_window_offsets);
 
+/* ---- FASTA ingestion on the GPU -------------------------------------- */
+
+/* Replaces the byte loop of the reference's reader (kseq.h:170-208, called from sketchFile, Sketch.cpp:1340-1422)
+ * for plain FASTA: `raw` holds the bytes of one or more files, EACH FOLLOWED BY ONE 0x00 BYTE (a file that itself
+ * contains 0x00 must be read on the host).  On the device the sequence bytes are compacted into the batch layout
+ * of fpm_sketch_batch (records back to back, each followed by 0x00) and stay resident in the context; a record
+ * table comes back.  Semantics as kseq: a record starts at '>', its header runs to the next '\n', its sequence is
+ * every byte 33..126 up to the next '>' (anywhere in a line); bytes before a file's first '>' are skipped.
+ * *out_status = FPM_FASTA_NOT_PLAIN when a '+' or '@' ends a record (FASTQ): nothing is produced, use the host
+ * reader.  Record i's sequence length = (seq_begin of record i+1, or *out_seq_bytes for the last) - seq_begin - 1. */
+typedef struct fpm_fasta_record {
+    uint64_t hdr_begin;   /* offset in raw of the '>'                                              */
+    uint64_t hdr_end;     /* offset in raw of the '\n' (or the file's 0x00) that ends the header   */
+    uint64_t seq_begin;   /* offset of the record's first base in the compacted sequence          */
+} fpm_fasta_record;
+#define FPM_FASTA_OK 0
+#define FPM_FASTA_NOT_PLAIN 1
+int fpm_fasta_parse(fpm_ctx* ctx, const uint8_t* raw, uint64_t n_bytes, uint64_t* out_n_records, uint64_t* out_seq_bytes, int* out_status);
+int fpm_fasta_records(fpm_ctx* ctx, fpm_fasta_record* out /* [n_records] */);
+int fpm_fasta_sequence(fpm_ctx* ctx, uint8_t* out /* [seq_bytes], tests */);
+/* fpm_sketch_batch over the sequence the last fpm_fasta_parse left on the device (group_offsets in compacted
+ * coordinates, from 0 to seq_bytes).                                                                        */
+int fpm_sketch_parsed(fpm_ctx* ctx, const fpm_sketch_params* p, const uint64_t* group_offsets, uint32_t n_groups, uint64_t* out_hashes,
+                      uint32_t* out_counts, uint32_t* out_n);
+
 /* ---- dist ---------------------------------------------------------------------------- */
 
 /* PairOutput (CommandDistance.h:57-64) as a 24-byte POD.                                   */

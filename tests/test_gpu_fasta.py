@@ -1,0 +1,118 @@
+"""GPU FASTA ingestion against the host reader that mirrors the reference's kseq.h
+(`mash debug-parse`, itself pinned to kseq.h by tests/test_host_cpu.py): same records, same lengths, same bytes."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+MASH = os.path.join(ROOT, "fp-mash_b200", "bin", "mash")
+
+
+def host_records(path):
+    """(name+comment text is checked by the CLI tests) -> list of (length, fnv1a of the sequence bytes)."""
+    out = subprocess.run([MASH, "debug-parse", path], capture_output=True, check=True).stdout.split(b"\n")
+    while out and out[-1] == b"":
+        out.pop()
+    assert out[-1].startswith(b"END\t-1"), out[-1]
+    recs = []
+    for line in out[:-1]:
+        f = line.split(b"\t")
+        recs.append((int(f[-2]), int(f[-1])))
+    return recs
+
+
+def fnv(b):
+    h = 1469598103934665603
+    for c in bytes(b):
+        h = ((h ^ c) * 1099511628211) & 0xffffffffffffffff
+    return h
+
+
+def fasta_cases(rng):
+    lut = np.frombuffer(b"ACGTacgtNRYKM", dtype=np.uint8)
+    def seq(n):
+        return lut[rng.integers(0, len(lut), size=n)].tobytes()
+    def wrap(s, w, eol=b"\n"):
+        return eol.join(s[i:i + w] for i in range(0, len(s), w)) + eol
+    cases = {
+        "plain": b">r1 first record\n" + wrap(seq(1000), 70) + b">r2\n" + wrap(seq(333), 70),
+        "crlf": b">r1 c\r\n" + wrap(seq(500), 60, b"\r\n") + b">r2\r\n" + wrap(seq(61), 60, b"\r\n"),
+        "no_final_newline": b">a\n" + seq(200),
+        "header_only_at_eof": b">a\n" + seq(50) + b"\n>b",
+        "header_line_at_eof": b">a\n" + seq(50) + b"\n>b comment\n",
+        "empty_records": b">a\n>b\n\n>c\n" + seq(10) + b"\n",
+        "junk_before_first": b"junk line\n; comment\n>a x\n" + wrap(seq(100), 50),
+        "blank_and_spaces": b">a\n" + seq(30) + b"\n\n  " + seq(20) + b" \t" + seq(7) + b"\n\n",
+        "gt_mid_line": b">a\nACGT" + seq(40) + b">b glued header\n" + seq(25) + b"\n",
+        "gt_inside_header": b">a has > inside > twice\n" + seq(33) + b"\n",
+        "long_single_line": b">chr one line\n" + seq(300_000) + b"\n>tail\n" + seq(5000) + b"\n",
+        "many_short": b"".join(b">r%d\n" % i + seq(int(rng.integers(0, 90))) + b"\n" for i in range(3000)),
+        "control_bytes": b">a\n" + seq(20) + bytes([1, 2, 127, 128, 200, 255]) + seq(20) + b"\n",
+        "empty_file": b"",
+        "no_records": b"just text\nno headers here\n",
+    }
+    # boundaries of the 4 KB chunks and of the 128-byte slices: headers and newlines straddling them
+    for pad in (4095, 4096, 4097, 127, 128, 129, 8191):
+        cases["straddle_%d" % pad] = b">x\n" + seq(pad - 3) + b">boundary header that is long enough to cross\n" + seq(200) + b"\n"
+    return cases
+
+
+def test_fasta_parse_matches_host_reader(ctx, tmp_path):
+    rng = np.random.default_rng(3)
+    cases = fasta_cases(rng)
+    names = sorted(cases)
+    want = []
+    for nm in names:
+        p = tmp_path / (nm + ".fa")
+        p.write_bytes(cases[nm])
+        want.append(host_records(str(p)))
+    # every file alone, then all of them in one call (0x00-separated)
+    for group in [[nm] for nm in names] + [names]:
+        got = ctx.fasta_parse([cases[nm] for nm in group])
+        assert got is not None, group
+        recs, lengths, seq = got
+        exp = [r for nm in group for r in want[names.index(nm)]]
+        assert len(recs) == len(exp), (group, len(recs), len(exp))
+        for i, (l, h) in enumerate(exp):
+            assert int(lengths[i]) == l, (group, i)
+            b = int(recs["seq_begin"][i])
+            assert fnv(seq[b:b + l]) == h, (group, i)
+            assert seq[b + l] == 0
+        assert int(seq.size) == sum(l + 1 for l, _ in exp)
+    # headers: the table points at them in the raw bytes
+    raw = b"".join(cases[nm] + b"\0" for nm in names)
+    recs, _, _ = ctx.fasta_parse([cases[nm] for nm in names], fetch_sequence=False)
+    for r in recs:
+        assert raw[int(r["hdr_begin"])] == ord(">")
+        assert raw[int(r["hdr_end"])] in (ord("\n"), 0)
+        assert b"\n" not in raw[int(r["hdr_begin"]):int(r["hdr_end"])]
+
+
+def test_fasta_parse_rejects_fastq(ctx):
+    assert ctx.fasta_parse([b"@r1\nACGT\n+\nIIII\n"]) is None
+    assert ctx.fasta_parse([b">r1\nACGT\n+\nIIII\n"]) is None
+    assert ctx.fasta_parse([b">ok\nACGT\n", b">r\nAC@GT\n"]) is None
+    assert ctx.fasta_parse([b">plus + and @ in the header are fine\nACGT\n"]) is not None
+
+
+def test_sketch_parsed_equals_sketch_batch(ctx, fpm):
+    rng = np.random.default_rng(4)
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    files, batch, goff = [], bytearray(), [0]
+    for f in range(6):
+        recs = [lut[rng.integers(0, 4, size=int(rng.integers(500, 40000)))].tobytes() for _ in range(int(rng.integers(1, 4)))]
+        text = b"".join(b">f%d_r%d\n" % (f, i) + b"\n".join(r[j:j + 80] for j in range(0, len(r), 80)) + b"\n" for i, r in enumerate(recs))
+        files.append(text)
+        for r in recs:
+            batch += r + b"\0"
+        goff.append(len(batch))
+    recs, lengths, seq = ctx.fasta_parse(files)
+    assert bytes(seq) == bytes(batch)
+    p = fpm.make_sketch_params(k=21, s=400)
+    a = ctx.sketch_parsed(np.array(goff, dtype=np.uint64), p)
+    b = ctx.sketch_batch(np.frombuffer(bytes(batch), dtype=np.uint8), np.array(goff, dtype=np.uint64), p)
+    assert np.array_equal(a["hashes"], b["hashes"]) and np.array_equal(a["n"], b["n"])
