@@ -10,6 +10,7 @@
 #include <zlib.h>
 #include <fstream>
 #include <iostream>
+#include <atomic>
 #include <condition_variable>
 #include <memory>
 #include <mutex>
@@ -179,6 +180,205 @@ void Sketch::flushBatch(Batch& b)
         references.push_back(r);
     }
     b.clear();
+}
+
+static void parseSequenceFile(const string& file, const Sketch::Parameters& parameters, SeqSink& sink);
+
+// ------------------------------------------------------------------------------------------
+// GPU ingestion of plain FASTA files: the raw bytes of whole files go to the device, the
+// parser there (csrc/fasta_parse.cu) does what FastxReader::next does byte by byte, and only the record table
+// comes back.  The metadata rules of sketchFile (Sketch.cpp:1318-1422,1436-1444) are applied to that table.
+// ------------------------------------------------------------------------------------------
+struct Sketch::RawBatch {
+    uint8_t* raw = nullptr;      // pinned: file bytes, each file followed by one 0x00
+    uint64_t used = 0, cap = 0;
+    vector<string> files;
+    vector<uint64_t> fileEnd;    // offset of each file's 0x00
+
+    ~RawBatch() { if (raw) fpm_host_free(raw); }
+    void reserve(uint64_t extra)
+    {
+        if (used + extra <= cap) return;
+        uint64_t ncap = max<uint64_t>(cap ? cap * 2 : (kFlushBytes + (64ull << 20)), used + extra);
+        void* p = nullptr;
+        gpuCheck(fpm_host_alloc(ncap, &p));
+        fpmTick("pinned raw batch allocated");
+        if (used) memcpy(p, raw, used);
+        if (raw) fpm_host_free(raw);
+        raw = (uint8_t*)p;
+        cap = ncap;
+    }
+    // Whole files -> batch, read by up to `threads` threads straight into the pinned buffer.  Returns how many of
+    // them (a prefix of `names`) were appended: it stops before the first file that cannot go to the GPU parser
+    // (gzip behind a plain name, unreadable, not a regular file, contains 0x00, changed size while being read).
+    size_t addFiles(const vector<string>& names, int threads)
+    {
+        const size_t n = names.size();
+        vector<uint64_t> size(n, 0), off(n, 0);
+        vector<char> ok(n, 1);
+        uint64_t total = 0;
+        for (size_t i = 0; i < n; i++) {
+            struct stat st;
+            if (stat(names[i].c_str(), &st) != 0 || !S_ISREG(st.st_mode)) { ok[i] = 0; continue; }
+            size[i] = (uint64_t)st.st_size;
+            off[i] = used + total;
+            total += size[i] + 1;
+        }
+        reserve(total);
+        auto readOne = [&](size_t i) {
+            if (!ok[i]) return;
+            FILE* f = fopen(names[i].c_str(), "rb");
+            if (!f) { ok[i] = 0; return; }
+            uint8_t* dst = raw + off[i];
+            const uint64_t got = size[i] ? fread(dst, 1, size[i], f) : 0;
+            const bool more = fgetc(f) != EOF;
+            fclose(f);
+            if (got != size[i] || more) { ok[i] = 0; return; }
+            if (size[i] >= 2 && dst[0] == 0x1f && dst[1] == 0x8b) { ok[i] = 0; return; }       // gzip
+            if (size[i] && memchr(dst, 0, size[i]) != nullptr) { ok[i] = 0; return; }
+            dst[size[i]] = 0;
+        };
+        const int nt = (int)min<size_t>((size_t)max(threads, 1), n);
+        if (nt <= 1) {
+            for (size_t i = 0; i < n; i++) readOne(i);
+        } else {
+            atomic<size_t> next(0);
+            vector<thread> pool;
+            for (int t = 0; t < nt; t++)
+                pool.emplace_back([&] { for (size_t i; (i = next.fetch_add(1)) < n;) readOne(i); });
+            for (auto& t : pool) t.join();
+        }
+        size_t good = 0;
+        while (good < n && ok[good]) good++;
+        for (size_t i = 0; i < good; i++) {
+            files.push_back(names[i]);
+            fileEnd.push_back(off[i] + size[i]);
+            used = off[i] + size[i] + 1;
+        }
+        return good;
+    }
+    void clear() { used = 0; files.clear(); fileEnd.clear(); }
+};
+
+namespace {
+// name / comment of one header, as FastxReader::next reads them (kseq.h:175-182): [p, e) is the text after '>',
+// up to but excluding the '\n' that ended it (or up to the end of the file when atEof).
+void parseHeader(const uint8_t* p, const uint8_t* e, bool atEof, string& name, string& comment, string& commentCstr)
+{
+    name.clear();
+    comment.clear();
+    const uint8_t* q = p;
+    while (q < e && !isspace(*q)) q++;
+    name.assign((const char*)p, (size_t)(q - p));
+    if (q == e) return;                                    // delimiter was the '\n' (or the end of the file): no comment, buffer untouched
+    q++;                                                   // the delimiter
+    if (q == e && atEof) return;                           // nothing after it before the end of the file: kseq leaves the buffer untouched
+    comment.assign((const char*)q, (size_t)(e - q));
+    commentCstr = comment;
+}
+}  // namespace
+
+void Sketch::flushRawBatch(RawBatch& rb, Batch& hostBatch)
+{
+    if (rb.files.empty()) return;
+    fpmTick("raw batch read");
+    uint64_t nRec = 0, seqBytes = 0;
+    int status = 0;
+    gpuCheck(fpm_fasta_parse(gpuContext(), rb.raw, rb.used, &nRec, &seqBytes, &status));
+    if (status != FPM_FASTA_OK) {
+        // not plain FASTA somewhere in this batch (FASTQ records): the host reader defines the result
+        for (const string& f : rb.files) parseSequenceFile(f, parameters, hostBatch);
+        flushBatch(hostBatch);
+        rb.clear();
+        return;
+    }
+    vector<fpm_fasta_record> recs(nRec);
+    if (nRec) gpuCheck(fpm_fasta_records(gpuContext(), recs.data()));
+    fpmTick("fasta parsed on the GPU");
+    vector<uint64_t> goff{0};
+    vector<Reference> metas;
+    vector<char> keep;                                     // -i: groups of records shorter than k are dropped after sketching
+    string name, comment, commentCstr;
+    size_t r = 0;
+    for (size_t f = 0; f < rb.files.size(); f++) {
+        const uint64_t fEnd = rb.fileEnd[f];
+        commentCstr.clear();                               // one reader (one kseq_t) per file
+        Reference reference;
+        reference.length = 0;
+        reference.name = rb.files[f];
+        uint64_t count = 0;
+        bool skipped = false;
+        for (; r < nRec && recs[r].hdr_begin < fEnd; r++) {
+            const uint64_t seqEnd = r + 1 < nRec ? recs[r + 1].seq_begin : seqBytes;
+            const uint64_t l = seqEnd - recs[r].seq_begin - 1;
+            const bool atEof = recs[r].hdr_end == fEnd;
+            if (atEof && recs[r].hdr_end == recs[r].hdr_begin + 1) {          // a lone '>' as the file's last byte: no record for kseq
+                if (!parameters.concatenated) { goff.push_back(seqEnd); keep.push_back(0); metas.emplace_back(); }
+                continue;
+            }
+            parseHeader(rb.raw + recs[r].hdr_begin + 1, rb.raw + recs[r].hdr_end, atEof, name, comment, commentCstr);
+            if (parameters.concatenated) {
+                if (l < (uint64_t)parameters.kmerSize) { skipped = true; continue; }
+                if (count == 0) {
+                    reference.comment = name;
+                    reference.comment.append(" ");
+                    reference.comment.append(commentCstr.c_str());            // read as a C string (Sketch.cpp:1383-1392)
+                }
+                count++;
+                reference.length += l;
+            } else {
+                Reference one;
+                one.length = l;
+                one.name = name;
+                one.comment = comment;
+                goff.push_back(seqEnd);
+                keep.push_back(l >= (uint64_t)parameters.kmerSize);
+                metas.push_back(one);
+            }
+        }
+        if (parameters.concatenated) {
+            if (count > 1) {                                                  // Sketch.cpp:1436-1444
+                reference.comment.insert(0, " seqs] ");
+                reference.comment.insert(0, to_string(count));
+                reference.comment.insert(0, "[");
+                reference.comment.append(" [...]");
+            }
+            if (reference.length == 0) {
+                if (skipped) cerr << "\nWARNING: All fasta records in input files were shorter than the k-mer size (" << parameters.kmerSize << ")." << endl;
+                else cerr << "\nERROR: Did not find fasta records in \"input files\"." << endl;
+                exit(1);
+            }
+            const uint64_t gEnd = r < nRec ? recs[r].seq_begin : seqBytes;   // this file's records end where the next file's begin
+            goff.push_back(gEnd);
+            keep.push_back(1);
+            metas.push_back(reference);
+        }
+    }
+    if (goff.back() != seqBytes) {                          // files without any record leave no bytes: cannot happen, but never trust a table
+        cerr << "ERROR: inconsistent FASTA record table." << endl;
+        exit(1);
+    }
+    const uint32_t n = (uint32_t)metas.size();
+    if (n) {
+        const uint64_t s = parameters.minHashesPerWindow;
+        fpm_sketch_params sp;
+        fillSketchParams(parameters, sp, false);
+        vector<uint64_t> hashes((size_t)n * s);
+        vector<uint32_t> counts(parameters.counts ? (size_t)n * s : 0);
+        vector<uint32_t> outn(n);
+        gpuCheck(fpm_sketch_parsed(gpuContext(), &sp, goff.data(), n, hashes.data(), parameters.counts ? counts.data() : nullptr, outn.data()));
+        fpmTick("fpm_sketch_parsed done");
+        for (uint32_t g = 0; g < n; g++) {
+            if (!keep[g]) continue;
+            Reference& ref = metas[g];
+            ref.hashesSorted.setUse64(parameters.use64);
+            ref.hashesSorted.values.assign(hashes.begin() + (size_t)g * s, hashes.begin() + (size_t)g * s + outn[g]);
+            if (parameters.counts) ref.counts.assign(counts.begin() + (size_t)g * s, counts.begin() + (size_t)g * s + outn[g]);
+            ref.countsSorted = true;
+            references.push_back(ref);
+        }
+    }
+    rb.clear();
 }
 
 // sketchFile's reading loop (Sketch.cpp:1318-1422) for one sketch made of one or more files:
@@ -610,12 +810,22 @@ int Sketch::initFromFiles(const vector<string>& files, const Parameters& paramet
 {
     parameters = parametersNew;
     Batch batch;
+    RawBatch rawBatch;
 
-    // sequence files (not sketches, not stdin) can be parsed ahead by -p threads
+    // Plain FASTA files are parsed on the GPU (FPMASH_GPU_PARSE=0 turns that off): not read sets (-r: FASTQ, and
+    // several files may feed one sketch), not .gz, not stdin.  The content checks happen when the file is read.
+    const char* gpuParseEnv = getenv("FPMASH_GPU_PARSE");
+    const bool gpuParse = !(gpuParseEnv && gpuParseEnv[0] == '0') && !parametersNew.reads && !contain;
+    vector<char> rawCandidate(files.size(), 0);
+    size_t rawDone = 0;                                          // candidates below this index are already in rawBatch
+    for (size_t i = 0; i < files.size(); i++)
+        rawCandidate[i] = gpuParse && !hasSuffix(files[i], suffixSketch) && files[i] != "-" && !hasSuffix(files[i], ".gz");
+
+    // the other sequence files (not sketches, not stdin) can be parsed ahead by -p threads
     vector<string> jobFiles;
     vector<size_t> jobOf(files.size(), 0);
     for (size_t i = 0; i < files.size(); i++) {
-        if (!hasSuffix(files[i], suffixSketch) && files[i] != "-") { jobOf[i] = jobFiles.size(); jobFiles.push_back(files[i]); }
+        if (!hasSuffix(files[i], suffixSketch) && files[i] != "-" && !rawCandidate[i]) { jobOf[i] = jobFiles.size(); jobFiles.push_back(files[i]); }
     }
     bool anyStdin = false;
     for (const string& f : files) anyStdin |= f == "-";
@@ -638,6 +848,7 @@ int Sketch::initFromFiles(const vector<string>& files, const Parameters& paramet
     for (size_t i = 0; i < files.size(); i++) {
         bool isSketch = hasSuffix(files[i], suffixSketch);
         if (isSketch) {
+            flushRawBatch(rawBatch, batch);
             flushBatch(batch);                                   // keep submission order (ThreadPool output queue)
             Sketch sketchTest;
             sketchTest.initParametersFromCapnp(files[i].c_str());
@@ -684,14 +895,36 @@ int Sketch::initFromFiles(const vector<string>& files, const Parameters& paramet
             }
             fclose(probe);
         }
-        if (pool) {
-            unique_ptr<FileBuffer> fb = pool->take(jobOf[i]);
-            batch.append(fb->seq.data(), fb->seq.size(), fb->goff, fb->metas);
-        } else {
+        if (rawCandidate[i]) {
+            flushBatch(batch);                                   // references keep the order of the inputs
+            if (rawDone > i) continue;                           // already read with an earlier file of its run
+            // the run of GPU-parse candidates starting here, up to one batch of bytes, read by the -p threads
+            vector<string> run;
+            uint64_t runBytes = 0;
+            for (size_t j = i; j < files.size() && rawCandidate[j] && (run.empty() || rawBatch.used + runBytes < kFlushBytes); j++) {
+                struct stat st;
+                run.push_back(files[j]);
+                runBytes += stat(files[j].c_str(), &st) == 0 ? (uint64_t)st.st_size + 1 : 1;
+            }
+            const size_t good = rawBatch.addFiles(run, parameters.parallelism);
+            rawDone = i + good;
+            if (rawBatch.used >= kFlushBytes) flushRawBatch(rawBatch, batch);
+            if (good > 0) continue;
+            flushRawBatch(rawBatch, batch);                      // gzip behind a plain name, 0x00 inside, ...: host reader
             parseSequenceFile(files[i], parameters, batch);
+            rawDone = i + 1;
+        } else {
+            flushRawBatch(rawBatch, batch);
+            if (pool && !rawCandidate[i]) {
+                unique_ptr<FileBuffer> fb = pool->take(jobOf[i]);
+                batch.append(fb->seq.data(), fb->seq.size(), fb->goff, fb->metas);
+            } else {
+                parseSequenceFile(files[i], parameters, batch);
+            }
         }
         if (batch.used >= kFlushBytes) flushBatch(batch);
     }
+    flushRawBatch(rawBatch, batch);
     flushBatch(batch);
     createIndex();
     return 0;

@@ -99,6 +99,8 @@ public:
 private:
     void createIndex();
     void flushBatch(Batch& b);
+    struct RawBatch;   // raw FASTA files on their way to the GPU parser (Sketch.cpp)
+    void flushRawBatch(RawBatch& rb, Batch& hostBatch);
     void loadSketchFile(const std::string& file);
 
     std::vector<Reference> references;

@@ -1,3 +1,4 @@
+# FPMASH_TIMING milestones of the CLI: tiny input (fixed costs), 100 x 5 Mbp FASTA with the GPU parser and with the host reader, dist
 M=fp-mash_b200/bin/mash
 D=$(mktemp -d)
 python - "$D" <<'PY'
@@ -14,6 +15,8 @@ open(os.path.join(d, "list.txt"), "w").write("\n".join(names) + "\n")
 PY
 export FPMASH_TIMING=1
 echo "== tiny"; $M sketch -o $D/tiny $D/tiny.fna 2>&1 | grep timing
-echo "== 100 x 5 Mbp -p 16"; $M sketch -l -p 16 -o $D/all $D/list.txt 2>&1 | grep timing
+echo "== 100 x 5 Mbp -p 16, GPU FASTA parser"; $M sketch -l -p 16 -o $D/all $D/list.txt 2>&1 | grep timing
+echo "== 100 x 5 Mbp -p 16, host reader (FPMASH_GPU_PARSE=0)"; FPMASH_GPU_PARSE=0 $M sketch -l -p 16 -o $D/all0 $D/list.txt 2>&1 | grep timing
+cmp $D/all.msh $D/all0.msh && echo "identical .msh"
 echo "== dist 100x100"; $M dist $D/all.msh $D/all.msh 2>&1 | grep timing
 rm -rf $D
