@@ -116,3 +116,37 @@ def test_sketch_parsed_equals_sketch_batch(ctx, fpm):
     a = ctx.sketch_parsed(np.array(goff, dtype=np.uint64), p)
     b = ctx.sketch_batch(np.frombuffer(bytes(batch), dtype=np.uint8), np.array(goff, dtype=np.uint64), p)
     assert np.array_equal(a["hashes"], b["hashes"]) and np.array_equal(a["n"], b["n"])
+
+
+@pytest.mark.parametrize("individual", [False, True])
+def test_cli_gpu_parser_route_equals_host_reader_route(tmp_path, individual):
+    """`mash sketch` through the GPU parser and through the host reader (FPMASH_GPU_PARSE=0): same .msh bytes, or
+    the same failure, for every tricky input -- names, comments, [N seqs], lengths, short-record rules, -i."""
+    rng = np.random.default_rng(5)
+    cases = fasta_cases(rng)
+    cases["two_comments_then_none"] = b">a first comment\n" + b"ACGT" * 20 + b"\n>b\n" + b"GATTACA" * 12 + b"\n>c  spaced  comment \n" + b"TTGCA" * 15 + b"\n"
+    cases["lone_gt_at_eof"] = b">a\n" + b"ACGT" * 20 + b"\n>"
+    cases["name_then_eof"] = b">a\n" + b"ACGT" * 20 + b"\n>b "
+    for nm, data in sorted(cases.items()):
+        (tmp_path / (nm + ".fa")).write_bytes(data)
+    opts = ["-k", "15", "-s", "50"] + (["-i"] if individual else [])
+    env0 = dict(os.environ, FPMASH_GPU_PARSE="0")
+    failing = ("empty_file", "no_records", "empty_records")     # the reference exits with an error on these (every CLI start costs
+    for nm in failing:                                            # seconds of CUDA initialisation, so only they run one by one)
+        a = subprocess.run([MASH, "sketch"] + opts + ["-o", "gpu_" + nm, nm + ".fa"], cwd=tmp_path, capture_output=True, text=True)
+        b = subprocess.run([MASH, "sketch"] + opts + ["-o", "host_" + nm, nm + ".fa"], cwd=tmp_path, capture_output=True, text=True, env=env0)
+        assert a.returncode == b.returncode, (nm, a.stderr, b.stderr)
+        if a.returncode == 0:
+            assert (tmp_path / ("gpu_%s.msh" % nm)).read_bytes() == (tmp_path / ("host_%s.msh" % nm)).read_bytes(), nm
+        else:
+            assert a.stderr.replace("gpu_", "") == b.stderr.replace("host_", ""), nm
+    # all other files in one command (one raw batch, several files), then with a FASTQ file in the middle (the whole
+    # batch falls back to the host reader)
+    good = [nm + ".fa" for nm in sorted(cases) if nm not in failing]
+    (tmp_path / "reads.fq").write_bytes(b"@r1\n" + b"ACGTTGCA" * 10 + b"\n+\n" + b"I" * 80 + b"\n")
+    for extra in ([], ["reads.fq"]):
+        files = good[:5] + extra + good[5:]
+        a = subprocess.run([MASH, "sketch"] + opts + ["-o", "gpu_all"] + files, cwd=tmp_path, capture_output=True, text=True)
+        b = subprocess.run([MASH, "sketch"] + opts + ["-o", "host_all"] + files, cwd=tmp_path, capture_output=True, text=True, env=env0)
+        assert a.returncode == 0 and b.returncode == 0, (a.stderr, b.stderr)
+        assert (tmp_path / "gpu_all.msh").read_bytes() == (tmp_path / "host_all.msh").read_bytes()
