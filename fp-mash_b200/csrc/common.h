@@ -29,6 +29,11 @@ struct DevBuf {
 
 }  // namespace fpm
 
+struct fpm_ctx;
+namespace fpm {
+int stream_reserve(fpm_ctx* ctx, uint64_t bytes);   // sketch_host.cu
+}
+
 struct fpm_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;

@@ -248,6 +248,139 @@ __global__ void __launch_bounds__(256) fasta_emit_kernel(const uint8_t* __restri
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// FASTQ, four lines per record ("clean" FASTQ: what sequencers write).  For such input the reference's reader
+// (kseq.h:170-208) reduces to: line 4r is the header, line 4r+1 the sequence, line 4r+2 starts with '+', line
+// 4r+3 holds as many quality bytes as there are bases.  The role of a byte is then its line number mod 4, and the
+// line number is a prefix sum of newlines.  Everything the general reader would treat differently is detected and
+// reported as FPM_FASTA_NOT_PLAIN (the caller restarts with the host reader): a header not starting with '@', a
+// third line not starting with '+', a sequence byte outside 33..126 or one of '>' '+' '@', a quality byte outside
+// 33..127, '\r' or 0x00 anywhere, sequence and quality of different lengths, a line count not divisible by four.
+// The buffer must start at a record boundary and end with '\n'.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fastq_newline_kernel(const uint8_t* __restrict__ raw, uint64_t n, uint64_t n_chunks, uint32_t* __restrict__ cnt_nl,
+                                                            uint32_t* __restrict__ flags)
+{
+    const uint64_t chunk = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (chunk >= n_chunks) return;
+    const uint64_t base = chunk * FA_CHUNK;
+    uint32_t c = 0, bad = 0;
+    for (int off = 4 * lane; off < FA_CHUNK; off += 128) {
+        if (base + off >= n) break;
+        const uint32_t w = load4(raw, base + off, n);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t b = (w >> (8 * j)) & 0xffu;
+            c += b == '\n';
+            bad |= (b == '\r') | (b == 0);
+        }
+    }
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0) {
+        cnt_nl[chunk] = c;
+        if (bad) atomicOr(flags, 1u);
+    }
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(256) fastq_emit_kernel(const uint8_t* __restrict__ raw, uint64_t n, uint64_t n_chunks, const uint64_t* __restrict__ line_base,
+                                                         uint32_t* __restrict__ cnt_bytes, const uint64_t* __restrict__ off_bytes, uint8_t* __restrict__ out,
+                                                         uint64_t* __restrict__ nlpos, uint32_t* __restrict__ flags)
+{
+    const uint64_t chunk = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (chunk >= n_chunks) return;
+    const uint64_t base = chunk * FA_CHUNK;
+    uint64_t line = line_base[chunk];                              // warp-uniform: lines completed before the current slice
+    uint64_t out_pos = WRITE ? off_bytes[chunk] : 0;
+    uint32_t prev_last = base ? raw[base - 1] : '\n';             // the byte before the current slice (line-start test)
+    uint32_t tot = 0, bad = 0;
+    for (int off = 0; off < FA_CHUNK; off += 128) {
+        if (base + off >= n) break;
+        const uint64_t pos = base + off + 4 * lane;
+        const uint32_t w = pos < n ? load4(raw, pos, n) : 0x20202020u;
+        uint32_t nl = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) nl += (pos + j < n) && ((w >> (8 * j)) & 0xffu) == '\n';
+        uint32_t inc = nl;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += up;
+        }
+        uint64_t my_line = line + (inc - nl);
+        uint32_t before = __shfl_up_sync(0xffffffffu, w >> 24, 1);  // last byte of the previous lane
+        if (lane == 0) before = prev_last;
+        uint8_t ob[4];
+        uint32_t nb = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t b = (w >> (8 * j)) & 0xffu;
+            if (pos + j < n) {
+                const uint32_t role = (uint32_t)my_line & 3u;
+                const bool first = before == '\n';
+                if (b == '\n') {
+                    if (role == 1) ob[nb++] = 0;                    // end of a read
+                    if (first && role != 1 && role != 3) bad = 1;   // empty header or '+' line
+                    if (WRITE) nlpos[my_line] = pos + j;
+                    my_line++;
+                } else if (role == 0) {
+                    if (first && b != '@') bad = 1;
+                } else if (role == 1) {
+                    if (b < 33 || b > 126 || b == '>' || b == '+' || b == '@') bad = 1;
+                    ob[nb++] = (uint8_t)b;
+                } else if (role == 2) {
+                    if (first && b != '+') bad = 1;
+                } else {
+                    if (b < 33 || b > 127) bad = 1;
+                }
+            }
+            before = b;
+        }
+        uint32_t pinc = nb;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, pinc, o);
+            if (lane >= o) pinc += up;
+        }
+        const uint32_t slice_tot = __shfl_sync(0xffffffffu, pinc, 31);
+        if (WRITE) {
+            const uint64_t my_out = out_pos + (pinc - nb);
+            for (uint32_t i = 0; i < nb; i++) out[my_out + i] = ob[i];
+        }
+        out_pos += slice_tot;
+        tot += slice_tot;
+        line += __shfl_sync(0xffffffffu, inc, 31);
+        prev_last = __shfl_sync(0xffffffffu, w >> 24, 31);
+    }
+    if (!WRITE) {
+        bad = __any_sync(0xffffffffu, bad);
+        if (lane == 0) {
+            cnt_bytes[chunk] = tot;
+            if (bad) atomicOr(flags, 1u);
+        }
+    }
+}
+
+// per record: sequence and quality lengths must agree; count the reads of at least min_len bases and find the first one
+__global__ void __launch_bounds__(256) fastq_check_kernel(const uint64_t* __restrict__ nlpos, uint64_t n_reads, uint32_t min_len, uint32_t* __restrict__ flags,
+                                                          unsigned long long* __restrict__ n_valid, unsigned long long* __restrict__ first_valid)
+{
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = false, bad = false;
+    if (r < n_reads) {
+        const uint64_t len1 = nlpos[4 * r + 1] - nlpos[4 * r] - 1, len3 = nlpos[4 * r + 3] - nlpos[4 * r + 2] - 1;
+        bad = len1 != len3;
+        valid = len1 >= min_len;
+    }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flags, 1u);
+    const uint32_t m = __ballot_sync(0xffffffffu, valid);
+    if (m && (threadIdx.x & 31) == 0) {
+        atomicAdd(n_valid, (unsigned long long)__popc(m));
+        atomicMin(first_valid, (unsigned long long)(r + (__ffs(m) - 1)));
+    }
+}
+
 }  // namespace fpm
 
 using namespace fpm;
@@ -321,6 +454,79 @@ int fpm_fasta_sequence(fpm_ctx* ctx, uint8_t* out)
     if (!ctx || !out) { set_error("NULL argument"); return FPM_ERR_ARG; }
     FPM_CUDA(cudaSetDevice(ctx->device));
     if (ctx->fa_seq_bytes) FPM_CUDA(cudaMemcpyAsync(out, ctx->fa_seq.p, ctx->fa_seq_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    FPM_CUDA(cudaStreamSynchronize(ctx->stream));
+    return FPM_OK;
+}
+
+int fpm_fastq_stream_append(fpm_ctx* ctx, const uint8_t* raw, uint64_t n_bytes, uint32_t min_len, int* out_status, uint64_t* out_info)
+{
+    if (!ctx) { set_error("ctx is NULL"); return FPM_ERR_ARG; }
+    if (!out_status || !out_info) { set_error("NULL output"); return FPM_ERR_ARG; }
+    if (ctx->stream_goff.empty()) { set_error("fpm_sketch_stream_begin was not called"); return FPM_ERR_ARG; }
+    *out_status = FPM_FASTA_OK;
+    for (int i = 0; i < FPM_FASTQ_INFO_WORDS; i++) out_info[i] = 0;
+    if (n_bytes == 0) return FPM_OK;
+    if (!raw || raw[n_bytes - 1] != '\n') { set_error("a FASTQ piece must end with a newline"); return FPM_ERR_ARG; }
+    FPM_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const uint64_t n_chunks = (n_bytes + FA_CHUNK - 1) / FA_CHUNK;
+    int rc;
+    if ((rc = ctx->fa_raw.ensure(n_bytes + 64))) return rc;
+    if ((rc = ctx->fa_chunk.ensure(n_chunks * (8 + 8 + 8 + 4 + 4) + 256))) return rc;
+    if ((rc = ctx->d_misc.ensure(64))) return rc;
+    if ((rc = stream_reserve(ctx, n_bytes))) return rc;                 // kept bytes + separators never exceed the input
+    uint64_t* line_base = ctx->fa_chunk.as<uint64_t>();
+    uint64_t* out_off = line_base + n_chunks;
+    uint64_t* scratch = out_off + n_chunks;                             // the scan kernel's second output (unused here)
+    uint32_t* cnt_nl = (uint32_t*)(scratch + n_chunks);
+    uint32_t* cnt_bytes = cnt_nl + n_chunks;
+    uint32_t* d_flags = ctx->d_misc.as<uint32_t>();
+    uint64_t* totals = ctx->d_misc.as<uint64_t>() + 2;                  // d_misc (u64 words): flags, pad, totals[2], n_valid, first_valid
+    unsigned long long* d_valid = (unsigned long long*)(ctx->d_misc.as<uint64_t>() + 4);
+    unsigned long long* d_first = d_valid + 1;
+    FPM_CUDA(cudaMemsetAsync(ctx->d_misc.p, 0, 40, st));
+    FPM_CUDA(cudaMemsetAsync(d_first, 0xff, 8, st));
+    FPM_CUDA(cudaMemcpyAsync(ctx->fa_raw.p, raw, n_bytes, cudaMemcpyHostToDevice, st));
+    const uint32_t grid = (uint32_t)((n_chunks * 32 + 255) / 256);
+    const uint8_t* d_raw = ctx->fa_raw.as<uint8_t>();
+    fastq_newline_kernel<<<grid, 256, 0, st>>>(d_raw, n_bytes, n_chunks, cnt_nl, d_flags);
+    fasta_scan_kernel<<<1, 1024, 0, st>>>(1, n_chunks, nullptr, nullptr, cnt_nl, cnt_nl, line_base, scratch, totals);
+    fastq_emit_kernel<false><<<grid, 256, 0, st>>>(d_raw, n_bytes, n_chunks, line_base, cnt_bytes, nullptr, nullptr, nullptr, d_flags);
+    ctx->launches += 3;
+    FPM_CUDA(cudaGetLastError());
+    uint64_t h[6];
+    FPM_CUDA(cudaMemcpyAsync(h, ctx->d_misc.p, 32, cudaMemcpyDeviceToHost, st));
+    FPM_CUDA(cudaStreamSynchronize(st));
+    const uint64_t n_lines = h[2];
+    if (((uint32_t)h[0] & 1u) || (n_lines & 3)) { *out_status = FPM_FASTA_NOT_PLAIN; return FPM_OK; }
+    const uint64_t n_reads = n_lines / 4;
+    if ((rc = ctx->fa_recs.ensure(sizeof(uint64_t) * std::max<uint64_t>(n_lines, 1)))) return rc;
+    uint64_t* nlpos = ctx->fa_recs.as<uint64_t>();
+    uint8_t* dst = (uint8_t*)ctx->stream_buf.p + ctx->stream_used;
+    fasta_scan_kernel<<<1, 1024, 0, st>>>(1, n_chunks, nullptr, nullptr, cnt_bytes, cnt_bytes, out_off, scratch, totals);
+    fastq_emit_kernel<true><<<grid, 256, 0, st>>>(d_raw, n_bytes, n_chunks, line_base, nullptr, out_off, dst, nlpos, nullptr);
+    if (n_reads) fastq_check_kernel<<<(uint32_t)((n_reads + 255) / 256), 256, 0, st>>>(nlpos, n_reads, min_len, d_flags, d_valid, d_first);
+    ctx->launches += 3;
+    FPM_CUDA(cudaGetLastError());
+    FPM_CUDA(cudaMemcpyAsync(h, ctx->d_misc.p, 48, cudaMemcpyDeviceToHost, st));
+    FPM_CUDA(cudaStreamSynchronize(st));
+    if ((uint32_t)h[0] & 1u) { *out_status = FPM_FASTA_NOT_PLAIN; return FPM_OK; }      // nothing was committed to the stream
+    const uint64_t seq_bytes = h[2], n_valid = h[4], first_valid = h[5];
+    out_info[0] = n_reads;
+    out_info[1] = n_valid;
+    out_info[2] = seq_bytes;
+    out_info[3] = n_valid ? first_valid : n_reads;                       // index of the first read of at least min_len bases
+    ctx->fa_records = n_lines;                                           // fpm_fastq_line_ends serves the newline table
+    ctx->stream_used += seq_bytes;
+    return FPM_OK;
+}
+
+int fpm_fastq_line_ends(fpm_ctx* ctx, uint64_t first_line, uint64_t n_lines, uint64_t* out)
+{
+    if (!ctx || !out) { set_error("NULL argument"); return FPM_ERR_ARG; }
+    if (first_line + n_lines > ctx->fa_records) { set_error("line range outside the last FASTQ piece"); return FPM_ERR_ARG; }
+    FPM_CUDA(cudaSetDevice(ctx->device));
+    if (n_lines) FPM_CUDA(cudaMemcpyAsync(out, ctx->fa_recs.as<uint64_t>() + first_line, sizeof(uint64_t) * n_lines, cudaMemcpyDeviceToHost, ctx->stream));
     FPM_CUDA(cudaStreamSynchronize(ctx->stream));
     return FPM_OK;
 }

@@ -86,6 +86,23 @@ static uint64_t scale_threshold(uint64_t bits_full /*2^bits - 1*/, double frac)
     return (uint64_t)v;
 }
 
+// room for `bytes` more in the HBM-resident read stream: grows by doubling, keeping what is already there
+int stream_reserve(fpm_ctx* ctx, uint64_t bytes)
+{
+    if (ctx->stream_used + bytes + 64 <= ctx->stream_buf.cap) return FPM_OK;
+    size_t want = std::max<size_t>(ctx->stream_buf.cap * 2, ctx->stream_used + bytes + 64);
+    want = std::max<size_t>(want, (size_t)256 << 20);
+    void* np = nullptr;
+    cudaError_t e = cudaMalloc(&np, want);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(stream buffer)", __FILE__, __LINE__);
+    if (ctx->stream_used) FPM_CUDA(cudaMemcpyAsync(np, ctx->stream_buf.p, ctx->stream_used, cudaMemcpyDeviceToDevice, ctx->stream));
+    FPM_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->stream_buf.p) cudaFree(ctx->stream_buf.p);
+    ctx->stream_buf.p = np;
+    ctx->stream_buf.cap = want;
+    return FPM_OK;
+}
+
 int sketch_batch_dev_impl(fpm_ctx* ctx, const fpm_sketch_params* p, const uint8_t* d_seq, uint64_t n_bytes,
                           const uint64_t* h_goff, uint32_t n_groups, uint64_t* d_out_hashes, uint32_t* d_out_counts,
                           uint32_t* d_out_n, uint64_t* d_out_kmers)
@@ -468,19 +485,8 @@ int fpm_sketch_stream_append(fpm_ctx* ctx, const uint8_t* seq, uint64_t bytes)
     if (ctx->stream_goff.empty()) { set_error("fpm_sketch_stream_begin was not called"); return FPM_ERR_ARG; }
     if (bytes == 0) return FPM_OK;
     FPM_CUDA(cudaSetDevice(ctx->device));
-    if (ctx->stream_used + bytes + 64 > ctx->stream_buf.cap) {
-        // grow by doubling, keeping what is already resident
-        size_t want = std::max<size_t>(ctx->stream_buf.cap * 2, ctx->stream_used + bytes + 64);
-        want = std::max<size_t>(want, (size_t)256 << 20);
-        void* np = nullptr;
-        cudaError_t e = cudaMalloc(&np, want);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(stream buffer)", __FILE__, __LINE__);
-        if (ctx->stream_used) FPM_CUDA(cudaMemcpyAsync(np, ctx->stream_buf.p, ctx->stream_used, cudaMemcpyDeviceToDevice, ctx->stream));
-        FPM_CUDA(cudaStreamSynchronize(ctx->stream));
-        if (ctx->stream_buf.p) cudaFree(ctx->stream_buf.p);
-        ctx->stream_buf.p = np;
-        ctx->stream_buf.cap = want;
-    }
+    int rc = fpm::stream_reserve(ctx, bytes);
+    if (rc) return rc;
     FPM_CUDA(cudaMemcpyAsync((uint8_t*)ctx->stream_buf.p + ctx->stream_used, seq, bytes, cudaMemcpyHostToDevice, ctx->stream));
     FPM_CUDA(cudaStreamSynchronize(ctx->stream));   // the caller may reuse its staging buffer right away
     ctx->stream_used += bytes;

@@ -101,6 +101,8 @@ lib.fpm_distance.restype = C.c_double
 lib.fpm_distance.argtypes = [C.c_uint64, C.c_uint64, C.c_int]
 lib.fpm_measure_int32_peak.argtypes = [_VP, C.POINTER(C.c_double)]
 lib.fpm_get_int32_peaks.argtypes = [_VP, C.POINTER(C.c_double)]
+lib.fpm_fastq_stream_append.argtypes = [_VP, _VP, C.c_uint64, C.c_uint32, C.POINTER(C.c_int), u64p]
+lib.fpm_fastq_line_ends.argtypes = [_VP, C.c_uint64, C.c_uint64, _VP]
 lib.fpm_fasta_parse.argtypes = [_VP, _VP, C.c_uint64, u64p, u64p, C.POINTER(C.c_int)]
 lib.fpm_fasta_records.argtypes = [_VP, _VP]
 lib.fpm_fasta_sequence.argtypes = [_VP, _VP]
@@ -118,7 +120,8 @@ EXPORTED = ["fpm_abi_version", "fpm_device_count", "fpm_ctx_create", "fpm_ctx_de
             "fpm_sketch_stream_begin", "fpm_sketch_stream_append", "fpm_sketch_stream_end_group", "fpm_sketch_stream_finish",
             "fpm_fp_hash_batch", "fpm_cfl_fingerprint_batch", "fpm_fingerprint_batch", "fpm_dist_tile", "fpm_dist_tile_dev", "fpm_fp_positional_tile", "fpm_pvalue", "fpm_distance",
             "fpm_measure_int32_peak", "fpm_get_int32_peaks", "fpm_ctx_set_timing", "fpm_ctx_get_timing", "fpm_ctx_set_dist_mode",
-            "fpm_fasta_parse", "fpm_fasta_records", "fpm_fasta_sequence", "fpm_sketch_parsed"]
+            "fpm_fasta_parse", "fpm_fasta_records", "fpm_fasta_sequence", "fpm_sketch_parsed",
+            "fpm_fastq_stream_append", "fpm_fastq_line_ends"]
 
 
 def _check(rc):
@@ -311,6 +314,36 @@ class Context:
         _check(lib.fpm_sketch_stream_finish(self._h, C.byref(params), hashes.ctypes.data,
                                             counts.ctypes.data if params.want_counts else None, n.ctypes.data, None))
         return [dict(hashes=hashes[g, :n[g]].copy(), counts=counts[g, :n[g]].copy()) for g in range(ng)]
+
+    def sketch_fastq_pieces(self, pieces, **kw):
+        """One read set given as raw four-line FASTQ pieces (each starting at a record boundary and ending with a newline):
+        parsed on the GPU, sketched as ONE group.  Returns None if a piece is not clean FASTQ, else
+        (dict(hashes, counts), infos) with infos[i] = (reads, reads >= k, bytes appended, first read >= k) of piece i."""
+        params = make_sketch_params(**kw)
+        _check(lib.fpm_sketch_stream_begin(self._h))
+        infos = []
+        for pc in pieces:
+            buf = np.frombuffer(bytes(pc), dtype=np.uint8).copy()
+            status = C.c_int(0)
+            info = (C.c_uint64 * 6)()
+            _check(lib.fpm_fastq_stream_append(self._h, buf.ctypes.data, buf.size, params.kmer_size, C.byref(status), info))
+            if status.value != 0:
+                _check(lib.fpm_sketch_stream_end_group(self._h))
+                return None
+            infos.append(tuple(int(x) for x in info[:4]))
+        _check(lib.fpm_sketch_stream_end_group(self._h))
+        s = params.sketch_size
+        hashes = np.zeros((1, s), dtype=np.uint64)
+        counts = np.zeros((1, s), dtype=np.uint32)
+        n = np.zeros(1, dtype=np.uint32)
+        _check(lib.fpm_sketch_stream_finish(self._h, C.byref(params), hashes.ctypes.data,
+                                            counts.ctypes.data if params.want_counts else None, n.ctypes.data, None))
+        return dict(hashes=hashes[0, :n[0]].copy(), counts=counts[0, :n[0]].copy()), infos
+
+    def fastq_line_ends(self, first_line, n_lines):
+        out = np.zeros(max(n_lines, 1), dtype=np.uint64)
+        _check(lib.fpm_fastq_line_ends(self._h, first_line, n_lines, out.ctypes.data))
+        return out[:n_lines]
 
     def kmer_hashes(self, record: bytes, **kw):
         """Hash of every valid window of one record, in order (getHash parity)."""

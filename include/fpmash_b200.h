@@ -168,6 +168,19 @@ typedef struct fpm_fasta_record {
 int fpm_fasta_parse(fpm_ctx* ctx, const uint8_t* raw, uint64_t n_bytes, uint64_t* out_n_records, uint64_t* out_seq_bytes, int* out_status);
 int fpm_fasta_records(fpm_ctx* ctx, fpm_fasta_record* out /* [n_records] */);
 int fpm_fasta_sequence(fpm_ctx* ctx, uint8_t* out /* [seq_bytes], tests */);
+/* Four-line FASTQ (one read set -> one sketch, `mash sketch -r`): a piece of a file -- starting at a record
+ * boundary, ending with '\n' -- is parsed on the device and its reads are appended to the HBM-resident stream
+ * of fpm_sketch_stream_begin / _end_group / _finish, each read followed by 0x00, exactly as
+ * fpm_sketch_stream_append would have received them from the host reader.  Anything the reference's reader
+ * (kseq.h:170-208) would treat differently from "header, sequence, '+' line, quality of equal length" is reported
+ * as *out_status = FPM_FASTA_NOT_PLAIN and nothing is appended: restart the read set with the host reader.
+ * out_info: [0] reads in the piece, [1] reads of at least min_len bases (sketchFile skips the others,
+ * Sketch.cpp:1374-1378), [2] bytes appended, [3] index of the first read of at least min_len bases (= [0] if none).
+ * fpm_fastq_line_ends returns offsets (in the piece) of the '\n' ending lines first_line .. first_line+n_lines-1 of the
+ * last piece: read r's header is the text between line 4r-1's end (or the piece start) and line 4r's end.      */
+#define FPM_FASTQ_INFO_WORDS 6
+int fpm_fastq_stream_append(fpm_ctx* ctx, const uint8_t* raw, uint64_t n_bytes, uint32_t min_len, int* out_status, uint64_t* out_info /* [6] */);
+int fpm_fastq_line_ends(fpm_ctx* ctx, uint64_t first_line, uint64_t n_lines, uint64_t* out);
 /* fpm_sketch_batch over the sequence the last fpm_fasta_parse left on the device (group_offsets in compacted
  * coordinates, from 0 to seq_bytes).                                                                        */
 int fpm_sketch_parsed(fpm_ctx* ctx, const fpm_sketch_params* p, const uint64_t* group_offsets, uint32_t n_groups, uint64_t* out_hashes,

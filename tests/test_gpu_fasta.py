@@ -150,3 +150,67 @@ def test_cli_gpu_parser_route_equals_host_reader_route(tmp_path, individual):
         b = subprocess.run([MASH, "sketch"] + opts + ["-o", "host_all"] + files, cwd=tmp_path, capture_output=True, text=True, env=env0)
         assert a.returncode == 0 and b.returncode == 0, (a.stderr, b.stderr)
         assert (tmp_path / "gpu_all.msh").read_bytes() == (tmp_path / "host_all.msh").read_bytes()
+
+
+def _fastq(rng, n, lens=(150, 150), n_rate=0.002):
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    recs, text = [], []
+    for i in range(n):
+        l = int(rng.integers(lens[0], lens[1] + 1))
+        r = bytearray(lut[rng.integers(0, 4, size=l)].tobytes())
+        for p in np.nonzero(rng.random(l) < n_rate)[0]:
+            r[p] = ord("N")
+        q = bytes(rng.integers(33, 75, size=l, dtype=np.uint8))      # quality bytes incl. '@' '+' '>' at line starts
+        if i % 7 == 0 and l:
+            q = b"@" + q[1:]
+        if i % 11 == 0 and l:
+            q = b"+" + q[1:]
+        recs.append(bytes(r))
+        text.append(b"@read%d some comment %d\n" % (i, i) + bytes(r) + b"\n+" + (b"read%d" % i if i % 3 == 0 else b"") + b"\n" + q + b"\n")
+    return recs, text
+
+
+def test_fastq_gpu_stream_equals_host_records(ctx):
+    """Clean four-line FASTQ parsed on the GPU = the same reads streamed from the host (sketch with -m 2 and counts, whose
+    largest element's count depends on the order of the reads)."""
+    rng = np.random.default_rng(8)
+    genome_reads, text = _fastq(rng, 3000, lens=(10, 180))
+    genome_reads = genome_reads + genome_reads[:1500]                 # repeated reads: counts >= 2
+    text = text + text[:1500]
+    kw = dict(k=21, s=300, min_cov=2, want_counts=True)
+    want = ctx.sketch_stream([genome_reads], **kw)[0]
+    # one piece, then uneven pieces cut at record boundaries
+    for cuts in ([0, len(text)], [0, 1, 2, 700, 701, 2999, len(text)]):
+        pieces = [b"".join(text[a:b]) for a, b in zip(cuts[:-1], cuts[1:])]
+        got, infos = ctx.sketch_fastq_pieces(pieces, **kw)
+        assert np.array_equal(got["hashes"], want["hashes"]) and np.array_equal(got["counts"], want["counts"])
+        assert sum(i[0] for i in infos) == len(text)
+        assert sum(i[1] for i in infos) == sum(len(r) >= 21 for r in genome_reads)
+        a0 = cuts[0]
+        first = next(i for i, r in enumerate(genome_reads[a0:cuts[1]]) if len(r) >= 21)
+        assert infos[0][3] == first
+    # the line table: header text of the first read of the last piece
+    ends = ctx.fastq_line_ends(0, 4)
+    piece = pieces[-1]
+    assert piece[:int(ends[0])].startswith(b"@read") and piece[int(ends[1]) + 1:int(ends[1]) + 2] == b"+"
+
+
+def test_fastq_gpu_rejects_what_the_general_reader_treats_differently(ctx):
+    ok = b"@r1 c\nACGTACGTACGTACGTACGTACGTAC\n+\nIIIIIIIIIIIIIIIIIIIIIIIIII\n"
+    assert ctx.sketch_fastq_pieces([ok], k=21, s=10) is not None
+    bad = {
+        "crlf": ok.replace(b"\n", b"\r\n"),
+        "fasta": b">r1\nACGT\n>r2\nACGT\n",
+        "short_quality": b"@r1\nACGTACGT\n+\nIIII\n",
+        "long_quality": b"@r1\nACGT\n+\nIIIIII\n",
+        "multi_line_sequence": b"@r1\nACGT\nACGT\n+\nIIIIIIII\n",
+        "no_plus": b"@r1\nACGT\n-\nIIII\n",
+        "no_at": b"r1\nACGT\n+\nIIII\n",
+        "blank_in_sequence": b"@r1\nAC GT\n+\nIIIII\n",
+        "plus_in_sequence": b"@r1\nAC+GT\n+\nIIIII\n",
+        "three_lines": b"@r1\nACGT\n+\n",
+        "empty_header": b"\nACGT\n+\nIIII\n",
+        "second_record_broken": ok + b"@r2\nACGT\n+\nII\n",
+    }
+    for nm, data in bad.items():
+        assert ctx.sketch_fastq_pieces([data], k=21, s=10) is None, nm
