@@ -686,6 +686,94 @@ void Sketch::initFromFingerprints(const vector<string>& files, const Parameters&
     cout << "Initialization complete." << endl;
 }
 
+// `mash sketch -r reads.fastq` without the host reader: pieces of ~256 MB, each cut at a record boundary, go to
+// fpm_fastq_stream_append.  Returns false (nothing usable was produced) if the file is not clean four-line FASTQ.
+// Metadata as sketchFile keeps it (Sketch.cpp:1380-1393,1436-1444): comment from the first read of at least k bases
+// (with kseq's stale-comment quirk, so the headers before it are walked too), count of such reads.
+static bool readsViaGpu(const string& file, const Sketch::Parameters& parameters, Sketch::Reference& reference, uint64_t& count, bool& skipped)
+{
+    FILE* f = fopen(file.c_str(), "rb");
+    if (!f) return false;
+    struct stat st;
+    if (fstat(fileno(f), &st) != 0 || !S_ISREG(st.st_mode)) { fclose(f); return false; }
+    const char* pieceEnv = getenv("FPMASH_FASTQ_PIECE");                                  // tests: small pieces exercise the boundary search
+    const uint64_t kPiece = pieceEnv && atoll(pieceEnv) >= 4096 ? (uint64_t)atoll(pieceEnv) : 256ull << 20;
+    void* pinned = nullptr;
+    gpuCheck(fpm_host_alloc(kPiece + 64, &pinned));
+    uint8_t* buf = (uint8_t*)pinned;
+    uint64_t used = 0;
+    bool eof = false, ok = true, first = true, haveComment = false;
+    string name, comment, commentCstr;
+    reference.name = file;
+    reference.length = 0;
+    count = 0;
+    skipped = false;
+    vector<uint64_t> ends;
+    while (ok && !(eof && used == 0)) {
+        if (!eof) {
+            const uint64_t got = fread(buf + used, 1, kPiece - used, f);
+            used += got;
+            if (used < kPiece) eof = true;
+        }
+        if (first && used >= 2 && buf[0] == 0x1f && buf[1] == 0x8b) { ok = false; break; }     // gzip behind a plain name
+        first = false;
+        uint64_t cut = used;
+        if (eof) {
+            if (used && buf[used - 1] != '\n') buf[used++] = '\n';                            // a last line without newline parses the same
+            cut = used;
+        } else {
+            // the last header line that is followed by a complete record: line starts s with buf[s] == '@' whose line
+            // two further down starts with '+' (a quality line starting with '@' is followed, two lines down, by a
+            // sequence line, and clean sequence lines never start with '+')
+            uint64_t starts[12];
+            int ns = 0;
+            for (uint64_t p = used; p > 0 && ns < 12; p--)
+                if (buf[p - 1] == '\n') starts[ns++] = p;                                      // starts[0] is the latest line start
+            cut = 0;
+            for (int i = 4; i < ns; i++)
+                if (starts[i] < used && buf[starts[i]] == '@' && buf[starts[i - 2]] == '+') { cut = starts[i]; break; }
+            if (cut == 0) { ok = false; break; }                                              // no record boundary in sight
+        }
+        if (cut == 0) break;
+        int status = 0;
+        uint64_t info[FPM_FASTQ_INFO_WORDS];
+        gpuCheck(fpm_fastq_stream_append(gpuContext(), buf, cut, (uint32_t)parameters.kmerSize, &status, info));
+        if (status != FPM_FASTA_OK) { ok = false; break; }
+        const uint64_t nReads = info[0], nValid = info[1], firstValid = info[3];
+        if (!haveComment && nReads) {
+            // walk the headers up to the first read that counts (all of them if none does: the stale comment carries on)
+            const uint64_t upto = nValid ? firstValid : nReads - 1;
+            ends.resize(4 * upto + 1);
+            gpuCheck(fpm_fastq_line_ends(gpuContext(), 0, 4 * upto + 1, ends.data()));
+            for (uint64_t r = 0; r <= upto; r++) {
+                const uint64_t b = r ? ends[4 * r - 1] + 1 : 0, e = ends[4 * r];
+                parseHeader(buf + b + 1, buf + e, false, name, comment, commentCstr);
+            }
+            if (nValid) {
+                reference.comment = name;
+                reference.comment.append(" ");
+                reference.comment.append(commentCstr.c_str());
+                haveComment = true;
+            }
+        }
+        count += nValid;
+        skipped |= nReads > nValid;
+        memmove(buf, buf + cut, used - cut);
+        used -= cut;
+    }
+    fclose(f);
+    fpm_host_free(pinned);
+    if (!ok) return false;
+    fpmTick("reads parsed on the GPU");
+    if (count > 1) {                                                                          // Sketch.cpp:1436-1444
+        reference.comment.insert(0, " seqs] ");
+        reference.comment.insert(0, to_string(count));
+        reference.comment.insert(0, "[");
+        reference.comment.append(" [...]");
+    }
+    return true;
+}
+
 void Sketch::initFromReads(const vector<string>& files, const Parameters& parametersNew)   // Sketch.cpp:203-210
 {
     parameters = parametersNew;
@@ -714,9 +802,22 @@ void Sketch::initFromReads(const vector<string>& files, const Parameters& parame
         void closeGroup(const Sketch::Reference&) override { push(); gpuCheck(fpm_sketch_stream_end_group(gpuContext())); }
     } sink;
     Reference reference;
-    uint64_t count;
-    bool skipped;
-    readGroup(files, parameters, reference, count, skipped, sink);
+    uint64_t count = 0;
+    bool skipped = false;
+    // One plain FASTQ file: its four-line records are parsed on the GPU, piece by piece, straight into the HBM
+    // stream (csrc/fasta_parse.cu).  Anything else -- several files feeding one sketch (their records interleave,
+    // Sketch.cpp:1352-1422), gzip, stdin, FASTA reads, FASTQ that is not four clean lines per record -- takes the
+    // host reader; if the GPU route gives up half way the stream is restarted from scratch.
+    const char* gpuParseEnv = getenv("FPMASH_GPU_PARSE");
+    bool viaGpu = !(gpuParseEnv && gpuParseEnv[0] == '0') && files.size() == 1 && files[0] != "-" && !hasSuffix(files[0], ".gz");
+    if (viaGpu) {
+        viaGpu = readsViaGpu(files[0], parameters, reference, count, skipped);
+        if (!viaGpu) {
+            gpuCheck(fpm_sketch_stream_begin(gpuContext()));
+            reference = Reference();
+        }
+    }
+    if (!viaGpu) readGroup(files, parameters, reference, count, skipped, sink);
     sink.closeGroup(reference);
     {
         const uint64_t s = parameters.minHashesPerWindow;

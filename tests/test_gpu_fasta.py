@@ -214,3 +214,40 @@ def test_fastq_gpu_rejects_what_the_general_reader_treats_differently(ctx):
     }
     for nm, data in bad.items():
         assert ctx.sketch_fastq_pieces([data], k=21, s=10) is None, nm
+
+
+def test_cli_read_mode_gpu_fastq_route_equals_host_reader_route(tmp_path):
+    """`mash sketch -r -m 2` on one plain FASTQ file: GPU route (pieces parsed on the device) and host reader write the
+    same .msh, byte for byte -- hashes, counts (order-dependent top count), comment with [N seqs], estimated length.
+    Also inputs the GPU route must hand back: FASTA reads, CRLF FASTQ."""
+    import gzip
+    from conftest import GOLDEN
+    data = gzip.open(os.path.join(GOLDEN, "reads1.fastq.gz"), "rb").read()
+    (tmp_path / "reads1.fastq").write_bytes(data)
+    (tmp_path / "no_final_newline.fastq").write_bytes(data.rstrip(b"\n"))
+    (tmp_path / "crlf.fastq").write_bytes(data[:200000].rsplit(b"\n@", 1)[0].replace(b"\n", b"\r\n") + b"\r\n")
+    rng = np.random.default_rng(9)
+    recs, text = _fastq(rng, 400, lens=(5, 160))                      # some reads shorter than k, incl. the first ones
+    (tmp_path / "short_first.fastq").write_bytes(b"@tiny first comment\nACGT\n+\nIIII\n@tiny2\nAC\n+\nII\n" + b"".join(text) * 2)   # every read twice: -m 2
+    (tmp_path / "reads.fa").write_bytes(b"".join(b">r%d\n%s\n" % (i, r) for i, r in enumerate(recs)) * 2)
+    env0 = dict(os.environ, FPMASH_GPU_PARSE="0")
+    for nm in ("reads1.fastq", "no_final_newline.fastq", "crlf.fastq", "short_first.fastq", "reads.fa"):
+        a = subprocess.run([MASH, "sketch", "-r", "-m", "2", "-k", "21", "-s", "500", "-o", "gpu_" + nm, nm], cwd=tmp_path, capture_output=True, text=True)
+        b = subprocess.run([MASH, "sketch", "-r", "-m", "2", "-k", "21", "-s", "500", "-o", "host_" + nm, nm], cwd=tmp_path, capture_output=True, text=True, env=env0)
+        assert a.returncode == b.returncode == 0, (nm, a.stderr, b.stderr)
+        assert (tmp_path / ("gpu_%s.msh" % nm)).read_bytes() == (tmp_path / ("host_%s.msh" % nm)).read_bytes(), nm
+        assert a.stderr.replace("gpu_", "") == b.stderr.replace("host_", ""), nm
+    # the same file in 64 KB pieces: every piece boundary goes through the record-boundary search
+    envp = dict(os.environ, FPMASH_FASTQ_PIECE="65536")
+    c = subprocess.run([MASH, "sketch", "-r", "-m", "2", "-k", "21", "-s", "500", "-o", "pieces", "reads1.fastq"], cwd=tmp_path, capture_output=True, text=True, env=envp)
+    assert c.returncode == 0, c.stderr
+    assert (tmp_path / "pieces.msh").read_bytes() == (tmp_path / "host_reads1.fastq.msh").read_bytes().replace(b"host_reads1.fastq", b"reads1.fastq") or \
+        (tmp_path / "pieces.msh").read_bytes() == (tmp_path / "gpu_reads1.fastq.msh").read_bytes()
+    # and the routes are the ones claimed: the timing trace names them
+    envt = dict(os.environ, FPMASH_TIMING="1")
+    t = subprocess.run([MASH, "sketch", "-r", "-m", "2", "-k", "21", "-s", "500", "-o", "trace", "reads1.fastq"], cwd=tmp_path, capture_output=True, text=True, env=envt)
+    assert "reads parsed on the GPU" in t.stderr
+    t = subprocess.run([MASH, "sketch", "-r", "-m", "2", "-k", "21", "-s", "500", "-o", "trace", "crlf.fastq"], cwd=tmp_path, capture_output=True, text=True, env=envt)
+    assert "reads parsed on the GPU" not in t.stderr
+    t = subprocess.run([MASH, "sketch", "-k", "21", "-s", "500", "-o", "trace2", "reads.fa"], cwd=tmp_path, capture_output=True, text=True, env=envt)
+    assert "fasta parsed on the GPU" in t.stderr
