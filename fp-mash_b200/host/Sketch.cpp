@@ -696,12 +696,15 @@ static bool readsViaGpu(const string& file, const Sketch::Parameters& parameters
     if (!f) return false;
     struct stat st;
     if (fstat(fileno(f), &st) != 0 || !S_ISREG(st.st_mode)) { fclose(f); return false; }
+    const uint64_t fileSize = (uint64_t)st.st_size;
+    const int fd = fileno(f);
     const char* pieceEnv = getenv("FPMASH_FASTQ_PIECE");                                  // tests: small pieces exercise the boundary search
-    const uint64_t kPiece = pieceEnv && atoll(pieceEnv) >= 4096 ? (uint64_t)atoll(pieceEnv) : 256ull << 20;
+    // 64 MB pieces: page-locking the staging buffer costs ~0.2 ms per MB, a piece takes a few ms on the device
+    const uint64_t kPiece = pieceEnv && atoll(pieceEnv) >= 4096 ? (uint64_t)atoll(pieceEnv) : 64ull << 20;
     void* pinned = nullptr;
     gpuCheck(fpm_host_alloc(kPiece + 64, &pinned));
     uint8_t* buf = (uint8_t*)pinned;
-    uint64_t used = 0;
+    uint64_t used = 0, fileOff = 0;
     bool eof = false, ok = true, first = true, haveComment = false;
     string name, comment, commentCstr;
     reference.name = file;
@@ -711,9 +714,28 @@ static bool readsViaGpu(const string& file, const Sketch::Parameters& parameters
     vector<uint64_t> ends;
     while (ok && !(eof && used == 0)) {
         if (!eof) {
-            const uint64_t got = fread(buf + used, 1, kPiece - used, f);
-            used += got;
-            if (used < kPiece) eof = true;
+            // the next stretch of the file, read by the -p threads straight into the pinned piece
+            const uint64_t want = min<uint64_t>(kPiece - used, fileSize - fileOff);
+            const int nt = (int)max<uint64_t>(1, min<uint64_t>((uint64_t)max(parameters.parallelism, 1), want >> 20));
+            atomic<bool> readOk(true);
+            auto readPart = [&](int t) {
+                uint64_t a = want * t / nt, b = want * (t + 1) / nt;
+                while (a < b) {
+                    const ssize_t r = pread(fd, buf + used + a, b - a, (off_t)(fileOff + a));
+                    if (r <= 0) { readOk = false; return; }
+                    a += (uint64_t)r;
+                }
+            };
+            if (nt == 1) readPart(0);
+            else {
+                vector<thread> pool;
+                for (int t = 0; t < nt; t++) pool.emplace_back(readPart, t);
+                for (auto& t : pool) t.join();
+            }
+            if (!readOk) { ok = false; break; }
+            used += want;
+            fileOff += want;
+            if (fileOff >= fileSize) eof = true;
         }
         if (first && used >= 2 && buf[0] == 0x1f && buf[1] == 0x8b) { ok = false; break; }     // gzip behind a plain name
         first = false;
@@ -784,11 +806,12 @@ void Sketch::initFromReads(const vector<string>& files, const Parameters& parame
         uint8_t* stage = nullptr;
         uint64_t used = 0;
         const uint64_t kStage = 64ull << 20;
-        StreamSink() { void* p = nullptr; gpuCheck(fpm_host_alloc(kStage, &p)); stage = (uint8_t*)p; gpuCheck(fpm_sketch_stream_begin(gpuContext())); }
-        ~StreamSink() { fpm_host_free(stage); }
+        StreamSink() { gpuCheck(fpm_sketch_stream_begin(gpuContext())); }
+        ~StreamSink() { if (stage) fpm_host_free(stage); }
         void push() { if (used) gpuCheck(fpm_sketch_stream_append(gpuContext(), stage, used)); used = 0; }
         void addRecord(const char* s, uint64_t l) override
         {
+            if (!stage) { void* p = nullptr; gpuCheck(fpm_host_alloc(kStage, &p)); stage = (uint8_t*)p; }   // only the host-reader route needs it
             uint64_t done = 0;                                // records longer than the stage go through in pieces
             while (done < l) {
                 if (used == kStage) push();
