@@ -458,7 +458,10 @@ def main():
                          "note": "algorithmic bytes = 1 B per base read once; this kernel is integer-ALU bound, see roofline_int"},
             "roofline_int": {"bound": "int32-alu", "achieved": int_achieved / 1e12, "peak": int_peak / 1e12, "unit": "Tint32-op/s",
                              "frac": int_achieved / int_peak,
-                             "note": "algorithmic ops = %d int32-op equivalents per k-mer (Murmur only, SURVEY.md 8d); peak = best of three inline-PTX microbenchmarks run live (alternating IMAD/LOP3, i.e. both integer pipes busy)" % W_INT32_OPS[K],
+                             "note": "algorithmic ops = %d int32-op equivalents per k-mer (Murmur only, SURVEY.md 8d); peak = best of three inline-PTX microbenchmarks run live (strictly alternating IMAD/LOP3 with 16 independent chains: both integer pipes busy, ~0.94 warp instructions per clock and SM sub-partition)" % W_INT32_OPS[K],
+                             "pipe_bound": {"note": "the same roofline per pipe: 30 of the 74 algorithmic ops are IMADs (FMA pipe), 44 run on the ALU pipe; each pipe alone has the measured single-pipe peak",
+                                            "alu_pipe_ceiling_gkmers": int_peaks[0] / 44 / 1e9, "fma_pipe_ceiling_gkmers": int_peaks[1] / 30 / 1e9,
+                                            "frac_of_tighter_ceiling": (windows_per_step / (hash_ms_avg * 1e-3) / 1e9) / min(int_peaks[0] / 44 / 1e9, int_peaks[1] / 30 / 1e9)} if K == 21 else None,
                              "peaks_measured": {"alu_pipe_lop3": int_peaks[0] / 1e12, "fma_pipe_imad": int_peaks[1] / 1e12, "alternating": int_peaks[2] / 1e12}},
             "kernel_ms": {"sketch_hash": hash_ms_avg, "sketch_select": sel_ms / max(sel_n, 1)},
             "cpu_baseline": cpu,

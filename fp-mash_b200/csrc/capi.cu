@@ -47,22 +47,26 @@ void DevBuf::release()
     cap = 0;
 }
 
-// Integer-pipe microbenchmark.  Eight independent register chains per thread, instructions pinned
-// with inline PTX so ptxas keeps them 1:1.  MODE 0: ALU pipe only (LOP3 / SHF / IADD3-class),
-// MODE 1: FMA pipe only (IMAD), MODE 2: alternating.  Every asm statement is one counted op.
+// Integer-pipe microbenchmark.  Sixteen independent register chains per thread, instructions pinned with inline
+// PTX so ptxas keeps them 1:1.  MODE 0: ALU pipe only (LOP3 / SHF / IADD3-class), MODE 1: FMA pipe only (IMAD),
+// MODE 2: strictly alternating.  Every asm statement is one counted op.  (profiles/ubench/int_mix.cu explores the
+// patterns: each pipe alone issues 0.48-0.50 warp instructions per clock and SM sub-partition; alternating reaches
+// 0.94 with sixteen chains at 32 warps per SM but only 0.78-0.80 with eight -- the first version of this kernel
+// used eight and under-reported the dual-pipe peak as 27 T/s instead of 35 T/s.)
+constexpr int PEAK_CHAINS = 16;
 template <int MODE>
 __global__ void __launch_bounds__(256) int32_peak_kernel(uint32_t iters, uint32_t seed, uint32_t* sink)
 {
-    uint32_t r[8];
+    uint32_t r[PEAK_CHAINS];
 #pragma unroll
-    for (int c = 0; c < 8; c++) r[c] = seed * (2 * c + 1) + threadIdx.x + blockIdx.x;
+    for (int c = 0; c < PEAK_CHAINS; c++) r[c] = seed * (2 * c + 1) + threadIdx.x + blockIdx.x;
     const uint32_t k1 = seed | 0x9e3779b1u, k2 = seed ^ 0x7f4a7c15u;
 #pragma unroll 1
     for (uint32_t i = 0; i < iters; i++) {
 #pragma unroll
         for (int u = 0; u < 4; u++) {
 #pragma unroll
-            for (int c = 0; c < 8; c++) {
+            for (int c = 0; c < PEAK_CHAINS; c++) {
                 if (MODE == 0 || (MODE == 2 && ((c + u) & 1)))
                     asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(r[c]) : "r"(k1), "r"(k2));
                 else
@@ -72,7 +76,7 @@ __global__ void __launch_bounds__(256) int32_peak_kernel(uint32_t iters, uint32_
     }
     uint32_t x = 0;
 #pragma unroll
-    for (int c = 0; c < 8; c++) x ^= r[c];
+    for (int c = 0; c < PEAK_CHAINS; c++) x ^= r[c];
     if (x == 0x12345u) sink[0] = x;   // practically never; keeps the chains alive
 }
 
@@ -287,7 +291,7 @@ int fpm_measure_int32_peak(fpm_ctx* c, double* out_ops_per_s)
     int rc = c->d_misc.ensure(64);
     if (rc) return rc;
     const uint32_t iters = 1 << 11;
-    const uint32_t grid = (uint32_t)c->sm_count * 8;
+    const uint32_t grid = (uint32_t)c->sm_count * 4;          // 32 warps per SM
     cudaEvent_t e0, e1;
     FPM_CUDA(cudaEventCreate(&e0));
     FPM_CUDA(cudaEventCreate(&e1));
@@ -304,7 +308,7 @@ int fpm_measure_int32_peak(fpm_ctx* c, double* out_ops_per_s)
             FPM_CUDA(cudaEventSynchronize(e1));
             float ms = 0;
             FPM_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-            double ops = (double)grid * 256.0 * iters * 32.0;   // 4 x 8 counted instructions per iteration
+            double ops = (double)grid * 256.0 * iters * 4.0 * PEAK_CHAINS;   // counted instructions per iteration
             if (rep > 0 && ms > 0) best_mode = std::max(best_mode, ops / (ms * 1e-3));
         }
         c->int_peak[mode] = best_mode;
