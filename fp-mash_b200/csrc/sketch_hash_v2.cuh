@@ -175,35 +175,48 @@ __global__ void __launch_bounds__(SK_THREADS, FPM_SK_MIN_CTAS) sketch_hash_kerne
             uint32_t fw0 = q0, fw1 = q1, fw2 = q2;
             uint32_t x[5];
             if (CANON) { x[0] = revcomp16(fw2); x[1] = revcomp16(fw1); x[2] = revcomp16(fw0); x[3] = 0; x[4] = 0; }
+#ifndef FPM_WIN
+#define FPM_WIN 4       // windows in flight per lane (unrolled); 16 / FPM_WIN sub-blocks per 16-window block
+#endif
 #pragma unroll 1
-            for (int sub = 0; sub < 4; sub++) {
+            for (int sub = 0; sub < 16 / FPM_WIN; sub++) {
+                // FPM_WIN windows in flight; ONE filter branch for all of them (a branch per window cost ~16 % of the
+                // stall samples: ISETP waiting for the end of the Murmur chain, then branch resolution)
+                uint64_t hh[FPM_WIN];
+                bool any_below = false;
+                if (live) {
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    if (!live) break;
-                    uint32_t fhi = j ? __funnelshift_l(fw1, fw0, 2 * j) : fw0;
-                    uint32_t flo = j ? __funnelshift_l(fw2, fw1, 2 * j) : fw1;
-                    uint32_t chi = fhi, clo = flo;
-                    if (CANON) {
-                        const int start = 48 - K - j;                 // constant: the rc registers move instead
-                        const int ia = start >> 4, sh = 2 * (start & 15);
-                        uint32_t rhi = sh ? __funnelshift_l(x[ia + 1], x[ia], sh) : x[ia];
-                        uint32_t rlo = sh ? __funnelshift_l(x[ia + 2], x[ia + 1], sh) : x[ia + 1];
-                        // bits below the k-mer only matter for palindromes, where both strands hash alike
-                        bool use_r = (((uint64_t)rhi << 32) | rlo) < (((uint64_t)fhi << 32) | flo);
-                        chi = use_r ? rhi : fhi;
-                        clo = use_r ? rlo : flo;
+                    for (int j = 0; j < FPM_WIN; j++) {
+                        uint32_t fhi = j ? __funnelshift_l(fw1, fw0, 2 * j) : fw0;
+                        uint32_t flo = j ? __funnelshift_l(fw2, fw1, 2 * j) : fw1;
+                        uint32_t chi = fhi, clo = flo;
+                        if (CANON) {
+                            const int start = 48 - K - j;                 // constant: the rc registers move instead
+                            const int ia = start >> 4, sh = 2 * (start & 15);
+                            uint32_t rhi = sh ? __funnelshift_l(x[ia + 1], x[ia], sh) : x[ia];
+                            uint32_t rlo = sh ? __funnelshift_l(x[ia + 2], x[ia + 1], sh) : x[ia + 1];
+                            // bits below the k-mer only matter for palindromes, where both strands hash alike
+                            bool use_r = (((uint64_t)rhi << 32) | rlo) < (((uint64_t)fhi << 32) | flo);
+                            chi = use_r ? rhi : fhi;
+                            clo = use_r ? rlo : flo;
+                        }
+                        uint64_t w[4];
+                        expand_lut<K>(chi, clo, w, lut_addr);
+                        uint64_t h = murmur3_h1_fixed<K>(w, seed, add1, add2);
+                        if (hash32) h &= 0xffffffffULL;
+                        hh[j] = h;
+                        // one-instruction reject on the deciding word; the exact 64-bit test only for the survivors
+                        any_below |= (hash32 ? (uint32_t)h : (uint32_t)(h >> 32)) <= tcut;
                     }
-                    uint64_t w[4];
-                    expand_lut<K>(chi, clo, w, lut_addr);
-                    uint64_t h = murmur3_h1_fixed<K>(w, seed, add1, add2);
-                    if (hash32) h &= 0xffffffffULL;
-                    // one-instruction reject on the deciding word; the exact 64-bit test only for the survivors
-                    const uint32_t hcut = hash32 ? (uint32_t)h : (uint32_t)(h >> 32);
-                    if (hcut <= tcut) {
+                }
+                if (any_below) {
+#pragma unroll
+                    for (int j = 0; j < FPM_WIN; j++) {
+                        const uint64_t h = hh[j];
                         // the exact 64-bit test reads its bound back through a volatile shared load, which the compiler
-                        // cannot speculate above the branch: the per-window path keeps ONE compare
+                        // cannot speculate above the branch
                         if (h > *(volatile uint64_t*)&s_tm[wid]) continue;
-                        const int b = 16 * blk + 4 * sub + j;                    // window index within the lane's 64
+                        const int b = 16 * blk + FPM_WIN * sub + j;              // window index within the lane's 64
                         const uint64_t vlo = ((uint64_t)v1 << 32) | v0;
                         const uint64_t vw = b ? ((vlo >> b) | ((uint64_t)v2 << (64 - b))) : vlo;
                         constexpr uint64_t km = (1ULL << K) - 1;
@@ -219,8 +232,8 @@ __global__ void __launch_bounds__(SK_THREADS, FPM_SK_MIN_CTAS) sketch_hash_kerne
                     }
                 }
                 // next four windows: forward registers one byte left, reverse-complement one byte right
-                fw0 = __funnelshift_l(fw1, fw0, 8); fw1 = __funnelshift_l(fw2, fw1, 8); fw2 <<= 8;
-                if (CANON) { x[2] = __funnelshift_r(x[2], x[1], 8); x[1] = __funnelshift_r(x[1], x[0], 8); x[0] >>= 8; }
+                fw0 = __funnelshift_l(fw1, fw0, 2 * FPM_WIN); fw1 = __funnelshift_l(fw2, fw1, 2 * FPM_WIN); fw2 <<= 2 * FPM_WIN;
+                if (CANON) { x[2] = __funnelshift_r(x[2], x[1], 2 * FPM_WIN); x[1] = __funnelshift_r(x[1], x[0], 2 * FPM_WIN); x[0] >>= 2 * FPM_WIN; }
                 // dense survivors (accept-all sketches of short records): insert as soon as a warp-load is waiting
                 // the queue can only have grown if some lane queued a survivor in these four windows (~5 % of the time)
                 if (__any_sync(0xffffffffu, queued)) {
