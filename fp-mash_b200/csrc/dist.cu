@@ -333,8 +333,14 @@ dist_tile_kernel(const uint64_t* __restrict__ pref, const uint64_t* __restrict__
 //   * 432 rows per phase at two CTAs per SM (was 288); phase 0 is staged with 16-byte vectors.
 // ---------------------------------------------------------------------------------------------------------
 constexpr uint32_t D4_INF = 0xffffffffu;
-constexpr int D4_ROWS = 432;          // rows resident per phase
-constexpr int D4_UNROLL = 8;          // unchecked steps per fast block
+#ifndef FPM_D4_ROWS
+#define FPM_D4_ROWS 432
+#endif
+#ifndef FPM_D4_UNROLL
+#define FPM_D4_UNROLL 2      // measured: 1 -> 2.63, 2 -> 2.66, 4 -> 2.62, 8 -> 2.55, 16 -> 2.40 G pairs/s (the compiler unrolls the counted loop itself)
+#endif
+constexpr int D4_ROWS = FPM_D4_ROWS;      // rows resident per phase
+constexpr int D4_UNROLL = FPM_D4_UNROLL;  // unchecked steps per fast block
 constexpr int D4_PAD = 1;             // one +inf row after them (a pointer rests at most on row R)
 constexpr int D4_COLROWS = D4_ROWS + D4_PAD;   // 433 rows x (32 + 32) columns x 4 B = 108.25 KB: two CTAs per SM
 constexpr int D4_COLS = 64;           // 32 query + 32 reference columns
