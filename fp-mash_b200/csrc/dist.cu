@@ -395,7 +395,7 @@ dist_tile32_kernel(const uint32_t* __restrict__ pref, const uint32_t* __restrict
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* colQ = reinterpret_cast<uint32_t*>(smem_raw);               // [D4_COLROWS][32] query columns
     uint32_t* colR = colQ + D4_COLROWS * 32;                              // [D4_COLROWS][32] reference columns
-    __shared__ uint32_t s_cursor[D4_COLS], s_end[D4_COLS], s_exh[D4_COLS];
+    __shared__ uint32_t s_cursor[D4_COLS], s_end[D4_COLS], s_exh[D4_COLS], s_lo[4], s_span[4];
     __shared__ uint32_t s_V;
     __shared__ uint32_t s_need;
 
@@ -449,14 +449,37 @@ dist_tile32_kernel(const uint32_t* __restrict__ pref, const uint32_t* __restrict
                 *reinterpret_cast<uint4*>((isq ? colQ : colR) + r * 32 + c4) = v;
             }
         } else {
-            for (int idx = t; idx < R * 64; idx += DT_THREADS) {
-                const int c = idx & 63, r = idx >> 6, pl = (c & 31) >> 4;
-                const bool isq = c < 32;
+            // later phases: every column has its own cursor.  Per 16-column plane, load the union of the row ranges
+            // [min cursor, max cursor + R) as whole 64-byte lines (16-byte vectors, coalesced) and drop every element
+            // into its column's slot; cells fed from beyond the list's end get +inf.  (Per-element loads at the
+            // columns' own rows touched a 32-byte sector per 4-byte element.)
+            if (t < 4) {
+                uint32_t lo = 0xffffffffu, hi = 0;
+                for (int c = 0; c < 16; c++) { const uint32_t cu = s_cursor[16 * t + c]; lo = min(lo, cu); hi = max(hi, cu); }
+                s_lo[t] = lo;
+                s_span[t] = hi - lo + (uint32_t)R;
+            }
+            __syncthreads();
+#pragma unroll 1
+            for (int pl4 = 0; pl4 < 4; pl4++) {                       // planes: Q0, Q1, R0, R1
+                const bool isq = pl4 < 2;
+                const int pl = pl4 & 1;
                 const uint64_t rows = isq ? rows_qry : rows_ref;
-                const uint64_t row = (uint64_t)s_cursor[c] + r;
-                uint32_t v = D4_INF;
-                if ((pl == 0 || (isq ? q1_exists : r1_exists)) && row < rows) v = (isq ? gQ0 : gR0)[((uint64_t)pl * rows + row) * 16 + (c & 15)];
-                (isq ? colQ : colR)[r * 32 + (c & 31)] = v < V ? v : D4_INF;
+                const bool exists = pl == 0 || (isq ? q1_exists : r1_exists);
+                const uint32_t* src = (isq ? gQ0 : gR0) + (uint64_t)pl * rows * 16;
+                uint32_t* dst = (isq ? colQ : colR) + 16 * pl;
+                const uint32_t lo = s_lo[pl4], span = s_span[pl4];
+                for (uint32_t idx = t; idx < span * 4; idx += DT_THREADS) {
+                    const uint32_t row = lo + (idx >> 2), c4 = (idx & 3) * 4;
+                    uint4 v = make_uint4(D4_INF, D4_INF, D4_INF, D4_INF);
+                    if (exists && (uint64_t)row < rows) v = *reinterpret_cast<const uint4*>(src + (uint64_t)row * 16 + c4);
+                    const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const uint32_t r = row - s_cursor[16 * pl4 + c4 + e];       // wraps for rows before the column's cursor
+                        if (r < (uint32_t)R) dst[r * 32 + c4 + e] = vv[e] < V ? vv[e] : D4_INF;
+                    }
+                }
             }
         }
         for (int idx = t; idx < D4_PAD * 64; idx += DT_THREADS) (idx < D4_PAD * 32 ? colQ + R * 32 : colR + R * 32 - D4_PAD * 32)[idx] = D4_INF;
