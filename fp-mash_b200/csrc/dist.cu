@@ -330,7 +330,8 @@ dist_tile_kernel(const uint64_t* __restrict__ pref, const uint64_t* __restrict__
 //     columns apart) in one interleaved instruction stream: twice the loads in flight per warp;
 //   * the first +inf row of every column is found once per phase, so a thread knows how many steps it can run
 //     without an end test; a list that is through lets the other one jump to its end in O(1);
-//   * 432 rows per phase at two CTAs per SM (was 288); phase 0 is staged with 16-byte vectors.
+//   * 432 rows per phase at two CTAs per SM (was 288); all phases are staged with 16-byte vector loads (phase 0
+//     row-aligned, later phases as the union of the columns' row ranges per 16-column plane).
 // ---------------------------------------------------------------------------------------------------------
 constexpr uint32_t D4_INF = 0xffffffffu;
 #ifndef FPM_D4_ROWS
