@@ -36,8 +36,8 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 K = 21
 S = 1000
 W_INT32_OPS = {21: 74, 32: 96, 16: 64}   # int32-op equivalents of Murmur per k-mer
-NCU_SKETCH_TRAFFIC_RATIO = (315.18 + 17.10) / 300.0   # DRAM bytes per algorithmic byte, ncu capture of sketch_hash_kernel_v2 (profiles/r01_sketch_hash_v3.txt)
-NCU_DIST_TRAFFIC_RATIO = (25.92 + 194.43) / (3200 * 3200 * 24 / 1e6 + 2 * 3200 * 1001 * 4 / 1e6)   # same for dist_tile32_kernel (profiles/r01_dist_tile32_v3.txt)
+NCU_SKETCH_TRAFFIC_RATIO = (315.19 + 16.98) / 300.0   # DRAM bytes per algorithmic byte, ncu capture of sketch_hash_kernel_v2 (profiles/r01_sketch_hash_v4.txt)
+NCU_DIST_TRAFFIC_RATIO = (27.22 + 193.05) / (3200 * 3200 * 24 / 1e6 + 2 * 3200 * 1001 * 4 / 1e6)   # same for dist_tile32_kernel (profiles/r01_dist_tile32_v4.txt)
 SMEM_BYTES_PER_CLK_PER_SM = 128        # one 32-lane x 4-byte wavefront per clock (B300_MICROARCH.md / measured LSU pipe limit)
 
 
@@ -393,12 +393,12 @@ def main():
                          "peak": hbm_peak, "unit": "GB/s",
                          "frac": ((q1 - q0) * nd * 24 + 2 * nd * S * 8) / (tile_avg * 1e-3) / 1e9 / hbm_peak if tile_n else None,
                          "traffic": ((q1 - q0) * nd * 24 + 2 * nd * (S + 1) * 4) * NCU_DIST_TRAFFIC_RATIO,
-                         "traffic_note": "dram bytes of one ncu --set full capture of dist_tile32_kernel (profiles/r01_dist_tile32_v3.txt) scaled to this launch; below the algorithmic bytes because part of the output was still in L2 when the capture ended"},
+                         "traffic_note": "dram bytes of one ncu --set full capture of dist_tile32_kernel (profiles/r01_dist_tile32_v4.txt) scaled to this launch; below the algorithmic bytes because part of the output was still in L2 when the capture ended"},
             "roofline_smem": {"bound": "shared-memory bandwidth", "achieved": merge_steps * 8 / (tile_avg * 1e-3) / 1e12 if tile_n else None,
                               "peak": torch.cuda.get_device_properties(device).multi_processor_count * SMEM_BYTES_PER_CLK_PER_SM * 1.965e9 / 1e12,
                               "unit": "TB/s",
                               "frac": (merge_steps * 8 / (tile_avg * 1e-3)) / (torch.cuda.get_device_properties(device).multi_processor_count * SMEM_BYTES_PER_CLK_PER_SM * 1.965e9) if tile_n else None,
-                              "note": "what bounds the rank kernel: every merge step is two 4-byte shared-memory loads per pair (one LDS.32 wavefront per list per warp); peak = SMs x 128 B/clk x 1965 MHz; ncu: shared-memory pipe 80 % busy incl. staging"},
+                              "note": "what bounds the rank kernel: every merge step is two 4-byte shared-memory loads per pair (one LDS.32 wavefront per list per warp); peak = SMs x 128 B/clk x 1965 MHz; ncu: shared-memory pipe 87 % busy incl. staging"},
         }
         # e2e on a stated sample of query rows (host panels in, 24-byte records out)
         if rank == 0:
@@ -452,7 +452,7 @@ def main():
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
                          "traffic": alg_bytes * NCU_SKETCH_TRAFFIC_RATIO, "kernel": "sketch_hash_kernel_v2<21,true>", "launch_ms": hash_ms_avg,
-                         "traffic_note": "dram__bytes_read+write of one ncu --set full capture (profiles/r01_sketch_hash_v3.txt: 332.3 MB for a 300.0 MB launch) scaled to this launch size",
+                         "traffic_note": "dram__bytes_read+write of one ncu --set full capture (profiles/r01_sketch_hash_v4.txt: 332.2 MB for a 300.0 MB launch) scaled to this launch size",
                          "share_of_step": hash_ms / ms_total if ms_total else None,
                          "peak_source": hbm_src,
                          "note": "algorithmic bytes = 1 B per base read once; this kernel is integer-ALU bound, see roofline_int"},
