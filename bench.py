@@ -38,6 +38,7 @@ S = 1000
 W_INT32_OPS = {21: 74, 32: 96, 16: 64}   # int32-op equivalents of Murmur per k-mer
 NCU_SKETCH_TRAFFIC_RATIO = (315.19 + 16.98) / 300.0   # DRAM bytes per algorithmic byte, ncu capture of sketch_hash_kernel_v2 (profiles/r01_sketch_hash_v4.txt)
 NCU_DIST_TRAFFIC_RATIO = (27.22 + 193.05) / (3200 * 3200 * 24 / 1e6 + 2 * 3200 * 1001 * 4 / 1e6)   # same for dist_tile32_kernel (profiles/r01_dist_tile32_v4.txt)
+IMAD_WIDE_RATE = 8.99 / 18.45         # IMAD.WIDE issue rate relative to IMAD, measured (profiles/ubench/int_mix.cu: 8.99 vs 18.45 T/s)
 SMEM_BYTES_PER_CLK_PER_SM = 128        # one 32-lane x 4-byte wavefront per clock (B300_MICROARCH.md / measured LSU pipe limit)
 
 
@@ -459,9 +460,10 @@ def main():
             "roofline_int": {"bound": "int32-alu", "achieved": int_achieved / 1e12, "peak": int_peak / 1e12, "unit": "Tint32-op/s",
                              "frac": int_achieved / int_peak,
                              "note": "algorithmic ops = %d int32-op equivalents per k-mer (Murmur only, SURVEY.md 8d); peak = best of three inline-PTX microbenchmarks run live (strictly alternating IMAD/LOP3 with 16 independent chains: both integer pipes busy, ~0.94 warp instructions per clock and SM sub-partition)" % W_INT32_OPS[K],
-                             "pipe_bound": {"note": "the same roofline per pipe: 30 of the 74 algorithmic ops are IMADs (FMA pipe), 44 run on the ALU pipe; each pipe alone has the measured single-pipe peak",
-                                            "alu_pipe_ceiling_gkmers": int_peaks[0] / 44 / 1e9, "fma_pipe_ceiling_gkmers": int_peaks[1] / 30 / 1e9,
-                                            "frac_of_tighter_ceiling": (windows_per_step / (hash_ms_avg * 1e-3) / 1e9) / min(int_peaks[0] / 44 / 1e9, int_peaks[1] / 30 / 1e9)} if K == 21 else None,
+                             "pipe_bound": {"note": "the same roofline per pipe, k=21: the ALU pipe carries 44 of the 74 algorithmic ops; the FMA pipe carries the ten 64-bit multiplies and two x*5+c = 12 wide multiplies (IMAD.WIDE: 0.487 x the IMAD rate, profiles/ubench/int_mix.cu) + 24 IMADs; each pipe at its measured single-pipe peak",
+                                            "alu_pipe_ceiling_gkmers": int_peaks[0] / 44 / 1e9,
+                                            "fma_pipe_ceiling_gkmers": 1.0 / (12 / (IMAD_WIDE_RATE * int_peaks[1]) + 24 / int_peaks[1]) / 1e9,
+                                            "frac_of_tighter_ceiling": (windows_per_step / (hash_ms_avg * 1e-3) / 1e9) / min(int_peaks[0] / 44 / 1e9, 1.0 / (12 / (IMAD_WIDE_RATE * int_peaks[1]) + 24 / int_peaks[1]) / 1e9)} if K == 21 else None,
                              "peaks_measured": {"alu_pipe_lop3": int_peaks[0] / 1e12, "fma_pipe_imad": int_peaks[1] / 1e12, "alternating": int_peaks[2] / 1e12}},
             "kernel_ms": {"sketch_hash": hash_ms_avg, "sketch_select": sel_ms / max(sel_n, 1)},
             "cpu_baseline": cpu,

@@ -37,6 +37,55 @@ __global__ void __launch_bounds__(256) k(uint32_t iters, uint32_t seed, uint32_t
     if (x == 0x12345u) sink[0] = x;
 }
 
+__global__ void __launch_bounds__(256) kw(uint32_t iters, uint32_t seed, uint32_t* sink)
+{
+    unsigned long long r[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) r[c] = seed * (2 * c + 1) + threadIdx.x + blockIdx.x;
+    const uint32_t k1 = seed | 0x9e3779b1u;
+#pragma unroll 1
+    for (uint32_t i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                uint32_t lo = (uint32_t)r[c];
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(r[c]) : "r"(lo), "r"(k1));
+            }
+        }
+    }
+    unsigned long long x = 0;
+#pragma unroll
+    for (int c = 0; c < 8; c++) x ^= r[c];
+    if (x == 0x12345u) sink[0] = (uint32_t)x;
+}
+
+__global__ void __launch_bounds__(256) kw2(uint32_t iters, uint32_t seed, uint32_t* sink)
+{
+    uint32_t r[16];
+#pragma unroll
+    for (int c = 0; c < 16; c++) r[c] = seed * (2 * c + 1) + threadIdx.x + blockIdx.x;
+    const uint32_t k1 = seed | 0x9e3779b1u;
+    unsigned long long acc = 0;
+#pragma unroll 1
+    for (uint32_t i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+#pragma unroll
+            for (int c = 0; c < 16; c++) {
+                unsigned long long w;
+                asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(w) : "r"(r[c]), "r"(k1));
+                r[c] = (uint32_t)w;                  // chain through the low word; the high word is kept alive below
+                acc ^= w >> 32;
+            }
+        }
+    }
+    uint32_t x = (uint32_t)acc;
+#pragma unroll
+    for (int c = 0; c < 16; c++) x ^= r[c];
+    if (x == 0x12345u) sink[0] = x;
+}
+
 template <int P, int C>
 double run(int ctas_per_sm, int sms, uint32_t* sink)
 {
@@ -73,5 +122,32 @@ int main()
     CELL(8, 16) CELL(8, 32) CELL(8, 64) printf("\n");
     CELL(16, 8) CELL(16, 16) CELL(16, 32) printf("\n");
     CELL(32, 8) CELL(32, 16) CELL(32, 32) printf("\n");
+    // IMAD.WIDE alone (64-bit result in a register pair): how many per clock?
+    {
+        double best = 0;
+        cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+        for (int rep = 0; rep < 4; rep++) {
+            cudaEventRecord(e0);
+            kw<<<sms * 4, 256>>>(1 << 11, rep + 3, sink);
+            cudaEventRecord(e1); cudaEventSynchronize(e1);
+            float ms; cudaEventElapsedTime(&ms, e0, e1);
+            double ops = (double)sms * 4 * 256.0 * (1 << 11) * 4.0 * 8;
+            if (rep && ops / (ms * 1e-3) > best) best = ops / (ms * 1e-3);
+        }
+        printf("IMAD.WIDE only      8ch x32w %6.2f T/s (%.3f warp-instructions/clk/SMSP)\n", best / 1e12, best / 32 / (sms * 4 * clk));
+    }
+    {
+        double best = 0;
+        cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+        for (int rep = 0; rep < 4; rep++) {
+            cudaEventRecord(e0);
+            kw2<<<sms * 4, 256>>>(1 << 11, rep + 3, sink);
+            cudaEventRecord(e1); cudaEventSynchronize(e1);
+            float ms; cudaEventElapsedTime(&ms, e0, e1);
+            double ops = (double)sms * 4 * 256.0 * (1 << 11) * 4.0 * 16;
+            if (rep && ops / (ms * 1e-3) > best) best = ops / (ms * 1e-3);
+        }
+        printf("mul.wide + xor      16ch x32w %6.2f T wide-multiplies/s (each followed by one LOP3 on the ALU pipe)\n", best / 1e12);
+    }
     return 0;
 }
