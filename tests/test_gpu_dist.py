@@ -196,3 +196,33 @@ def test_dist_structured_edge_cases(dctx, oracle):
     for s_cmp in (s, s - 1, 1, 3 * s):
         got, passed = dctx.dist_tile((h, sz, ln), (h, sz, ln), s_cmp, 21, 4.0 ** 21)
         _compare(got, passed, _oracle_matrix(oracle, (h, sz, ln), (h, sz, ln), s_cmp, 21, 4.0 ** 21))
+
+
+def test_dist_small_universe_many_ties(ctx, oracle):
+    """Sketches drawn from a universe of only 4000 hash values: most steps of most merges are ties (both lists advance),
+    columns run out at very different rows, many pairs end by exhaustion instead of reaching s."""
+    rng = np.random.default_rng(13)
+    universe = np.sort(rng.choice(1 << 62, size=4000, replace=False).astype(np.uint64))
+    n, width = 230, 1800
+    h = np.zeros((n, width), dtype=np.uint64)
+    sz = np.zeros(n, dtype=np.uint32)
+    for i in range(n):
+        m = int(rng.integers(0, width + 1)) if i % 5 else width
+        pick = np.sort(rng.choice(4000, size=m, replace=False))
+        h[i, :m] = universe[pick]
+        sz[i] = m
+    ln = rng.integers(10_000, 9_000_000, size=n).astype(np.uint64)
+    for s_cmp in (1000, 1800, 3000):
+        got32, pass32 = ctx.dist_tile((h, sz, ln), (h[:70], sz[:70], ln[:70]), s_cmp, 21, 4.0 ** 21)
+        ctx.set_dist_mode(force64=True)
+        try:
+            got64, pass64 = ctx.dist_tile((h, sz, ln), (h[:70], sz[:70], ln[:70]), s_cmp, 21, 4.0 ** 21)
+        finally:
+            ctx.set_dist_mode(force64=False)
+        assert np.array_equal(got32, got64) and np.array_equal(pass32, pass64)
+        # a sample of pairs against the oracle's literal loop
+        for q, r in [(0, 0), (1, 5), (7, 229), (33, 100), (69, 64), (12, 13), (5, 1)]:
+            w = oracle.compare(h[r, :sz[r]], h[q, :sz[q]], int(ln[r]), int(ln[q]), s_cmp, 21, 4.0 ** 21, 1.0, 1.0)
+            g = got32[q, r]
+            assert int(g["numer"]) == w["numer"] and int(g["denom"]) == w["denom"], (s_cmp, q, r, g, w)
+            assert g["distance"] == pytest.approx(w["distance"], rel=RTOL, abs=0)
