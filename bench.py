@@ -375,6 +375,7 @@ def main():
         d_ms = max_over_ranks(e0.elapsed_time(e1)) / dsteps
         tile_ms, tile_n = ctx.get_timing(fpm.KERNEL_DIST_TILE)
         lit_ms, lit_n = ctx.get_timing(fpm.KERNEL_DIST_LITERAL)
+        pack_ms, pack_n = ctx.get_timing(fpm.KERNEL_DIST_PACK)
         ctx.set_timing(False)
         merge_steps = int(steps_ctr.item()) / dsteps
         pairs = nd * nd
@@ -386,6 +387,8 @@ def main():
                        "sketch_size": S, "k": K, "sharding": "query rows over ranks, NCCL all-gather of the reference panel" if world > 1 else "single GPU"},
             "gpu_launches": ctx.launch_count() - dl0, "fast_path_launches": tile_n, "literal_launches": lit_n,
             "merge_steps_per_pair": merge_steps / ((q1 - q0) * nd),
+            "kernel_ms": {"dist_tile32": tile_avg, "rank_compress_and_mark": pack_ms / max(pack_n, 1)},
+            "pruning": "pairs whose sketches share no hash (known from the sorted hashes of the rank pre-pass) are answered without a merge; merge_steps_per_pair counts executed steps only",
             "roofline_int": {"bound": "int32-alu", "achieved": merge_steps * 3 / (tile_avg * 1e-3) / 1e12 if tile_n else None,
                              "peak": int_peak / 1e12, "unit": "Tint32-op/s",
                              "frac": (merge_steps * 3 / (tile_avg * 1e-3)) / int_peak if tile_n else None,

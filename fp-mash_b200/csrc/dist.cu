@@ -391,7 +391,8 @@ __device__ __noinline__ Merge32 merge32_alone(Merge32 m)
 __global__ void __launch_bounds__(DT_THREADS, 2)
 dist_tile32_kernel(const uint32_t* __restrict__ pref, const uint32_t* __restrict__ pqry, uint64_t rows_ref, uint64_t rows_qry,
                    uint64_t n_ref, uint64_t n_qry, const uint64_t* __restrict__ len_ref, const uint64_t* __restrict__ len_qry,
-                   DistArgs a, fpm_pair* __restrict__ out, unsigned long long* steps, uint32_t q_tile0)
+                   DistArgs a, fpm_pair* __restrict__ out, unsigned long long* steps, uint32_t q_tile0,
+                   const uint32_t* __restrict__ marks, uint32_t mark_words, const uint32_t* __restrict__ size_ref, const uint32_t* __restrict__ size_qry)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* colQ = reinterpret_cast<uint32_t*>(smem_raw);               // [D4_COLROWS][32] query columns
@@ -420,12 +421,52 @@ dist_tile32_kernel(const uint32_t* __restrict__ pref, const uint32_t* __restrict
         }
         s_cursor[t] = 0;
     }
+    // ---- which pairs need a merge at all?  (marks: bit r of query q's row = the two lists share a hash; a pair
+    // without any shared hash has common = 0 and denom = min(s, |A| + |B|), no merge needed) -----------------------
+    __shared__ uint32_t s_mask[32];
+    __shared__ uint16_t s_list[1024];
+    __shared__ uint32_t s_npairs;
+    if (t < 32) {
+        const uint64_t qg = q_tile2 * 32 + t;
+        uint32_t mk = 0;
+        if (qg < n_qry) {
+            mk = marks ? marks[qg * mark_words + r_tile2] : 0xffffffffu;
+            const uint64_t left = n_ref - r_tile2 * 32;                  // references in this tile
+            if (left < 32) mk &= (1u << left) - 1u;
+        }
+        s_mask[t] = mk;
+        const uint32_t c = __popc(mk);
+        uint32_t inc = c;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, inc, o);
+            if (t >= o) inc += up;
+        }
+        uint32_t pos = inc - c;
+        for (uint32_t m = mk; m; m &= m - 1) s_list[pos++] = (uint16_t)((t << 5) | (__ffs(m) - 1));
+        if (t == 31) s_npairs = inc;
+    }
+    __syncthreads();
+    const uint32_t npairs = s_npairs;
+    // many pairs: the fixed conflict-free assignment (query l, references (l+w) and (l+w+16) mod 32), unmarked pairs idle;
+    // few pairs: the list is dealt out two per thread, so that whole warps have nothing to do
+    const bool dense = npairs > 256;
+    int qc0 = l, qc1 = l, rcm0 = rc0, rcm1 = rc1;
+    bool act0, act1;
+    if (dense) {
+        act0 = (s_mask[l] >> rc0) & 1u;
+        act1 = (s_mask[l] >> rc1) & 1u;
+    } else {
+        act0 = 2u * t < npairs;
+        act1 = 2u * t + 1 < npairs;
+        if (act0) { const uint32_t e = s_list[2 * t]; qc0 = e >> 5; rcm0 = e & 31; }
+        if (act1) { const uint32_t e = s_list[2 * t + 1]; qc1 = e >> 5; rcm1 = e & 31; }
+    }
     uint32_t common0 = 0, common1 = 0, denom0 = 0, denom1 = 0;
-    bool done0 = false, done1 = false;
+    bool done0 = !act0, done1 = !act1;
     int R = (int)(a.s < (uint32_t)D4_ROWS ? (a.s < 32u ? 32u : a.s) : (uint32_t)D4_ROWS);
     __syncthreads();
 
-    for (int phase = 0;; phase++) {
+    for (int phase = 0; npairs != 0; phase++) {
         // ---- V = smallest element that does not fit this phase ------------------------
         __syncthreads();
         if (t == 0) { s_V = D4_INF; s_need = 0; }
@@ -499,14 +540,14 @@ dist_tile32_kernel(const uint32_t* __restrict__ pref, const uint32_t* __restrict
         // the reference loop (CommandDistance.cpp:376-400): an exhausted or phase-masked list reads +inf; matches
         // are recovered from the pointer advances: advances(a) + advances(b) = steps + matches
         {
-            const uint32_t pa0 = (uint32_t)__cvta_generic_to_shared(colQ + l);
-            const uint32_t pb00 = (uint32_t)__cvta_generic_to_shared(colR + rc0), pb01 = (uint32_t)__cvta_generic_to_shared(colR + rc1);
-            const uint32_t ea = pa0 + s_end[l] * 128;
+            const uint32_t pa00 = (uint32_t)__cvta_generic_to_shared(colQ + qc0), pa01 = (uint32_t)__cvta_generic_to_shared(colQ + qc1);
+            const uint32_t pb00 = (uint32_t)__cvta_generic_to_shared(colR + rcm0), pb01 = (uint32_t)__cvta_generic_to_shared(colR + rcm1);
             Merge32 m0, m1;
-            m0.pa = pa0; m0.pb = pb00; m0.ea = ea; m0.eb = pb00 + s_end[32 + rc0] * 128; m0.rem = done0 ? 0u : a.s - denom0;
-            m1.pa = pa0; m1.pb = pb01; m1.ea = ea; m1.eb = pb01 + s_end[32 + rc1] * 128; m1.rem = done1 ? 0u : a.s - denom1;
+            m0.pa = pa00; m0.pb = pb00; m0.ea = pa00 + s_end[qc0] * 128; m0.eb = pb00 + s_end[32 + rcm0] * 128; m0.rem = done0 ? 0u : a.s - denom0;
+            m1.pa = pa01; m1.pb = pb01; m1.ea = pa01 + s_end[qc1] * 128; m1.eb = pb01 + s_end[32 + rcm1] * 128; m1.rem = done1 ? 0u : a.s - denom1;
             const uint32_t budget0 = m0.rem, budget1 = m1.rem;
-            lds32(pa0, m0.av); m1.av = m0.av;
+            lds32(pa00, m0.av);
+            lds32(pa01, m1.av);
             lds32(pb00, m0.bv);
             lds32(pb01, m1.bv);
             // both pairs together while both have unchecked steps left; then each one alone
@@ -523,19 +564,19 @@ dist_tile32_kernel(const uint32_t* __restrict__ pref, const uint32_t* __restrict
             m1 = merge32_alone(m1);
             // a pair is finished when its union reached s, or when both lists are through for good (nothing at or
             // beyond V either); everything else goes on in the next phase with the rows it can still need
-            const uint32_t exh_a = s_exh[l], exh_b0 = s_exh[32 + rc0], exh_b1 = s_exh[32 + rc1];
+            const uint32_t exh_a0 = s_exh[qc0], exh_a1 = s_exh[qc1], exh_b0 = s_exh[32 + rcm0], exh_b1 = s_exh[32 + rcm1];
             {
                 const uint32_t n = budget0 - m0.rem;
                 denom0 += n;
-                common0 += ((m0.pa - pa0) >> 7) + ((m0.pb - pb00) >> 7) - n;
-                const bool through = (exh_a & exh_b0) != 0 & (m0.pa == m0.ea) & (m0.pb == m0.eb);
+                common0 += ((m0.pa - pa00) >> 7) + ((m0.pb - pb00) >> 7) - n;
+                const bool through = (exh_a0 & exh_b0) != 0 & (m0.pa == m0.ea) & (m0.pb == m0.eb);
                 done0 = done0 | (denom0 >= a.s) | through;
             }
             {
                 const uint32_t n = budget1 - m1.rem;
                 denom1 += n;
-                common1 += ((m1.pa - pa0) >> 7) + ((m1.pb - pb01) >> 7) - n;
-                const bool through = (exh_a & exh_b1) != 0 & (m1.pa == m1.ea) & (m1.pb == m1.eb);
+                common1 += ((m1.pa - pa01) >> 7) + ((m1.pb - pb01) >> 7) - n;
+                const bool through = (exh_a1 & exh_b1) != 0 & (m1.pa == m1.ea) & (m1.pb == m1.eb);
                 done1 = done1 | (denom1 >= a.s) | through;
             }
             const uint32_t need = max(done0 ? 0u : a.s - denom0, done1 ? 0u : a.s - denom1);
@@ -554,13 +595,26 @@ dist_tile32_kernel(const uint32_t* __restrict__ pref, const uint32_t* __restrict
     // ---- results: stage in shared memory, then coalesced row writes ---------------------
     __syncthreads();
     fpm_pair* res = reinterpret_cast<fpm_pair*>(smem_raw);                  // [32][32]
-    const uint64_t qg = q_tile2 * 32 + l;
-    unsigned long long my_steps = 0;       // union steps of real pairs only (tile padding merges against empty lists)
-    if (qg < n_qry) {
-        const uint64_t lq = len_qry[qg];
-        const uint64_t rg0 = r_tile2 * 32 + rc0, rg1 = r_tile2 * 32 + rc1;
-        if (rg0 < n_ref) { finish_pair(a, common0, denom0, len_ref[rg0], lq, &res[l * 32 + rc0]); my_steps += denom0; }
-        if (rg1 < n_ref) { finish_pair(a, common1, denom1, len_ref[rg1], lq, &res[l * 32 + rc1]); my_steps += denom1; }
+    unsigned long long my_steps = 0;       // union steps actually merged
+    {
+        // pairs that were not merged (by the fixed assignment: query l, references rc0 and rc1): no shared hash
+        const uint64_t qg = q_tile2 * 32 + l;
+        if (qg < n_qry) {
+            const uint64_t lq = len_qry[qg];
+            const uint32_t sq = size_qry[qg], mk = s_mask[l];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int rc = h ? rc1 : rc0;
+                const uint64_t rg = r_tile2 * 32 + rc;
+                if (rg < n_ref && !((mk >> rc) & 1u)) {
+                    const uint64_t un = (uint64_t)sq + size_ref[rg];
+                    finish_pair(a, 0, un < a.s ? un : a.s, len_ref[rg], lq, &res[l * 32 + rc]);
+                }
+            }
+        }
+        // the merged ones, by whoever merged them (marked pairs are always real pairs)
+        if (act0) { const uint64_t q = q_tile2 * 32 + qc0, r = r_tile2 * 32 + rcm0; finish_pair(a, common0, denom0, len_ref[r], len_qry[q], &res[qc0 * 32 + rcm0]); my_steps += denom0; }
+        if (act1) { const uint64_t q = q_tile2 * 32 + qc1, r = r_tile2 * 32 + rcm1; finish_pair(a, common1, denom1, len_ref[r], len_qry[q], &res[qc1 * 32 + rcm1]); my_steps += denom1; }
     }
     __syncthreads();
     {
@@ -598,7 +652,8 @@ static int run_dist(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* d_r
         // preferred: 32-bit dense ranks (dist_rank.cu); panels too large for 32-bit indices keep the 64-bit kernel
         uint32_t *p32r = nullptr, *p32q = nullptr;
         int mode = DIST_RANK_TOO_BIG;
-        if (!ctx->force_dist64 && (rc = dist_rank_panels(ctx, d_ref, d_qry, max_size_ref, max_size_qry, rows_r, rows_q, &p32r, &p32q, &mode))) return rc;
+        uint32_t* marks = nullptr;
+        if (!ctx->force_dist64 && (rc = dist_rank_panels(ctx, d_ref, d_qry, max_size_ref, max_size_qry, rows_r, rows_q, a.s, &p32r, &p32q, &mode, &marks))) return rc;
         if (mode == DIST_RANK_UNSORTED) fast = false;
         if (mode == DIST_RANK_TOO_BIG) {
             if ((rc = ctx->d_ref.ensure(nr16 * 16 * rows_r * 8))) return rc;
@@ -639,7 +694,7 @@ static int run_dist(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* d_r
                 ctx->time_begin(FPM_KERNEL_DIST_TILE);
                 if (k32)
                     dist_tile32_kernel<<<grid, DT_THREADS, smem, st>>>(p32r, p32q, rows_r, rows_q, d_ref->n, d_qry->n, d_ref->lengths, d_qry->lengths, a,
-                                                                       d_out, (unsigned long long*)d_steps, (uint32_t)t0);
+                                                                       d_out, (unsigned long long*)d_steps, (uint32_t)t0, marks, (uint32_t)((d_ref->n + 31) / 32), d_ref->sizes, d_qry->sizes);
                 else
                     dist_tile_kernel<<<grid, DT_THREADS, smem, st>>>(ctx->d_ref.as<uint64_t>(), ctx->d_qry.as<uint64_t>(), rows_r, rows_q, d_ref->n,
                                                                      d_qry->n, d_ref->lengths, d_qry->lengths, a, d_out, (unsigned long long*)d_steps, (uint32_t)t0);

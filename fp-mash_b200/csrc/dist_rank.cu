@@ -49,9 +49,81 @@ __global__ void __launch_bounds__(256) dist_scatter_kernel(const uint64_t* __res
     if (keys[i] != ~0ULL) packed[dst[i]] = rank[i];
 }
 
-int dist_rank_panels(fpm_ctx* ctx, const fpm_panel* d_ref, const fpm_panel* d_qry, uint32_t max_size_ref, uint32_t max_size_qry,
-                     uint64_t rows_r, uint64_t rows_q, uint32_t** packed_ref, uint32_t** packed_qry, int* mode)
+// ---------------------------------------------------------------------------------------------------------
+// Pruning support.  The sorted (hash, destination) array puts equal hashes next to each other, so it is also an
+// inverted index: rank -> the reference sketches that contain that hash.  A (query, reference) pair whose lists
+// share no hash at all needs no merge: common = 0 and denom = min(s, |A| + |B|) (CommandDistance.cpp:376-400 with no
+// equal elements).  dist_mark_kernel sets, per query, one bit per reference that shares at least one hash with it.
+// ---------------------------------------------------------------------------------------------------------
+struct RefFlag {
+    const uint64_t* keys;
+    const uint32_t* dst;
+    uint32_t pr;
+    __host__ __device__ uint32_t operator()(uint64_t i) const { return keys[i] != ~0ULL && dst[i] < pr ? 1u : 0u; }
+};
+
+// per sorted element: references go to the compact posting array; the head of every run records where its postings start
+__global__ void __launch_bounds__(256) dist_post_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ dst, const uint32_t* __restrict__ rank,
+                                                        const uint32_t* __restrict__ ref_pos, uint64_t m, uint32_t pr, uint32_t rows_r,
+                                                        uint32_t* __restrict__ post, uint32_t* __restrict__ run_ref_start)
 {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const uint64_t k = keys[i];
+    if (i == 0 || keys[i - 1] != k) run_ref_start[rank[i]] = ref_pos[i];
+    if (k != ~0ULL && dst[i] < pr) {
+        const uint32_t d = dst[i];
+        post[ref_pos[i]] = ((d >> 4) / rows_r) * 16 + (d & 15);           // sketch index from the tile-layout destination
+    }
+}
+
+// the slot after the last run: total number of reference postings
+__global__ void dist_post_tail_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ dst, const uint32_t* __restrict__ rank,
+                                      const uint32_t* __restrict__ ref_pos, uint64_t m, uint32_t pr, uint32_t* __restrict__ run_ref_start)
+{
+    const uint64_t i = m - 1;
+    run_ref_start[rank[i] + 1] = ref_pos[i] + ((keys[i] != ~0ULL && dst[i] < pr) ? 1u : 0u);
+}
+
+// number of postings the marking pass would walk: for every query element, the references sharing its hash
+__global__ void __launch_bounds__(256) dist_post_count_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ dst, const uint32_t* __restrict__ rank,
+                                                              const uint32_t* __restrict__ run_ref_start, uint64_t m, uint32_t pr, unsigned long long* total)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long c = 0;
+    if (i < m && keys[i] != ~0ULL && dst[i] >= pr) c = run_ref_start[rank[i] + 1] - run_ref_start[rank[i]];
+    for (int o = 16; o; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(total, c);
+}
+
+// one CTA per query sketch: bit r of its row = reference r shares a hash with it
+__global__ void __launch_bounds__(256) dist_mark_kernel(const uint32_t* __restrict__ p32q, uint64_t rows_q, const uint32_t* __restrict__ sizes_q,
+                                                        const uint32_t* __restrict__ run_ref_start, const uint32_t* __restrict__ post, uint32_t words,
+                                                        uint32_t* __restrict__ marks)
+{
+    extern __shared__ uint32_t s_bits[];
+    const uint32_t q = blockIdx.x;
+    for (uint32_t w = threadIdx.x; w < words; w += blockDim.x) s_bits[w] = 0;
+    __syncthreads();
+    const uint32_t n = sizes_q[q];
+    const uint32_t* col = p32q + ((uint64_t)(q >> 4) * rows_q) * 16 + (q & 15);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (uint32_t e = wid; e < n; e += nw) {                              // a warp per element, lanes over its postings
+        const uint32_t r = col[(uint64_t)e * 16];
+        const uint32_t lo = run_ref_start[r], hi = run_ref_start[r + 1];
+        for (uint32_t j = lo + lane; j < hi; j += 32) {
+            const uint32_t sk = post[j];
+            atomicOr(&s_bits[sk >> 5], 1u << (sk & 31));
+        }
+    }
+    __syncthreads();
+    for (uint32_t w = threadIdx.x; w < words; w += blockDim.x) marks[(uint64_t)q * words + w] = s_bits[w];
+}
+
+int dist_rank_panels(fpm_ctx* ctx, const fpm_panel* d_ref, const fpm_panel* d_qry, uint32_t max_size_ref, uint32_t max_size_qry,
+                     uint64_t rows_r, uint64_t rows_q, uint32_t sketch_size, uint32_t** packed_ref, uint32_t** packed_qry, int* mode, uint32_t** marks)
+{
+    *marks = nullptr;
     cudaStream_t st = ctx->stream;
     *mode = DIST_RANK_TOO_BIG;
     const uint64_t nr16 = (d_ref->n + 15) / 16, nq16 = (d_qry->n + 15) / 16;
@@ -98,13 +170,52 @@ int dist_rank_panels(fpm_ctx* ctx, const fpm_panel* d_ref, const fpm_panel* d_qr
     cub::TransformInputIterator<uint32_t, HeadFlag, cub::CountingInputIterator<uint64_t>> it(cnt, hf);
     FPM_CUDA(cub::DeviceScan::InclusiveSum(d_tmp, scan_tmp, it, rank, (int64_t)m, st));
     dist_scatter_kernel<<<(uint32_t)((m + 255) / 256), 256, 0, st>>>(ks, vb.Current(), rank, m, packed);
-    ctx->time_end();
     ctx->launches += 3 + (mr ? 1 : 0) + (mq ? 1 : 0);
     FPM_CUDA(cudaGetLastError());
-    uint32_t flag = 0;
-    FPM_CUDA(cudaMemcpyAsync(&flag, ctx->d_misc.p, 4, cudaMemcpyDeviceToHost, st));
+
+    // ---- inverted index for pruning (optional: skipped for huge reference panels or when switched off) ----------
+    const uint32_t words = (uint32_t)((d_ref->n + 31) / 32);
+    const bool want_prune = !ctx->no_dist_prune && d_ref->n <= 1000000 && mr > 0 && mq > 0;
+    uint32_t *ref_pos = nullptr, *post = nullptr, *run_ref_start = nullptr;
+    unsigned long long* d_total = (unsigned long long*)(ctx->d_misc.as<uint64_t>() + 1);
+    if (want_prune) {
+        size_t scan2_tmp = 0;
+        RefFlag rf{ks, vb.Current(), (uint32_t)pr};
+        cub::TransformInputIterator<uint32_t, RefFlag, cub::CountingInputIterator<uint64_t>> rit(cnt, rf);
+        FPM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan2_tmp, rit, (uint32_t*)nullptr, (int64_t)m, st));
+        const size_t a4 = (m * 4 + 4 + 255) & ~(size_t)255;
+        if ((rc = ctx->d_post.ensure(3 * a4 + scan2_tmp + 256))) return rc;
+        unsigned char* pb = ctx->d_post.as<unsigned char>();
+        ref_pos = (uint32_t*)pb; post = (uint32_t*)(pb + a4); run_ref_start = (uint32_t*)(pb + 2 * a4);
+        void* d_tmp2 = pb + 3 * a4;
+        FPM_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp2, scan2_tmp, rit, ref_pos, (int64_t)m, st));
+        // every rank up to the last one gets its start; the slot after the last run = number of reference postings
+        FPM_CUDA(cudaMemsetAsync(run_ref_start, 0xff, (m + 1) * 4, st));
+        dist_post_kernel<<<(uint32_t)((m + 255) / 256), 256, 0, st>>>(ks, vb.Current(), rank, ref_pos, m, (uint32_t)pr, (uint32_t)rows_r, post, run_ref_start);
+        dist_post_tail_kernel<<<1, 1, 0, st>>>(ks, vb.Current(), rank, ref_pos, m, (uint32_t)pr, run_ref_start);
+        dist_post_count_kernel<<<(uint32_t)((m + 255) / 256), 256, 0, st>>>(ks, vb.Current(), rank, run_ref_start, m, (uint32_t)pr, d_total);
+        ctx->launches += 4;
+        FPM_CUDA(cudaGetLastError());
+    }
+    uint64_t h2[2] = {0, 0};
+    FPM_CUDA(cudaMemcpyAsync(h2, ctx->d_misc.p, 16, cudaMemcpyDeviceToHost, st));
     FPM_CUDA(cudaStreamSynchronize(st));
+    const uint32_t flag = (uint32_t)h2[0];
     *mode = flag == 0 ? DIST_RANK_OK : DIST_RANK_UNSORTED;     // unsorted input or a hash equal to 2^64-1: the literal kernel defines the result
+    if (*mode == DIST_RANK_OK && want_prune) {
+        // walk the postings only if that costs well below the merges it can save: a posting is ~4 bytes of L2 traffic and
+        // one shared-memory atomic, a pair's merge up to sketch_size steps
+        const double postings = (double)h2[1], full = (double)d_ref->n * (double)d_qry->n * (double)std::max<uint32_t>(sketch_size, 1);
+        if (postings <= 0.05 * full && (size_t)words * 4 <= 200 * 1024) {
+            if ((rc = ctx->d_marks.ensure((size_t)d_qry->n * words * 4 + 64))) return rc;
+            FPM_CUDA(cudaFuncSetAttribute(dist_mark_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(words * 4)));
+            dist_mark_kernel<<<(uint32_t)d_qry->n, 256, words * 4, st>>>(*packed_qry, rows_q, d_qry->sizes, run_ref_start, post, words, ctx->d_marks.as<uint32_t>());
+            ctx->launches++;
+            FPM_CUDA(cudaGetLastError());
+            *marks = ctx->d_marks.as<uint32_t>();
+        }
+    }
+    ctx->time_end();
     return FPM_OK;
 }
 

@@ -9,6 +9,8 @@ namespace fpm {
 // caller then runs the 64-bit tile kernel) or with input that is not strictly ascending (literal kernel).
 enum { DIST_RANK_OK = 0, DIST_RANK_TOO_BIG = 1, DIST_RANK_UNSORTED = 2 };
 int dist_rank_panels(fpm_ctx* ctx, const fpm_panel* d_ref, const fpm_panel* d_qry, uint32_t max_size_ref, uint32_t max_size_qry,
-                     uint64_t rows_r, uint64_t rows_q, uint32_t** packed_ref, uint32_t** packed_qry, int* mode);
+                     uint64_t rows_r, uint64_t rows_q, uint32_t sketch_size, uint32_t** packed_ref, uint32_t** packed_qry, int* mode, uint32_t** marks);
+// *marks (nullable result): per query one row of ceil(n_ref / 32) words, bit r set iff reference r shares at least one hash
+// with the query; nullptr when pruning is off or would not pay.
 
 }  // namespace fpm

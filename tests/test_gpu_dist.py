@@ -10,12 +10,13 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-12
 
 
-@pytest.fixture(params=["rank32", "u64"])
+@pytest.fixture(params=["rank32", "rank32_noprune", "u64"])
 def dctx(ctx, request):
-    """The context with the tile kernel pinned: 32-bit dense ranks (default) or the 64-bit kernel."""
-    ctx.set_dist_mode(force64=request.param == "u64")
+    """The context with the tile kernel pinned: 32-bit dense ranks with pruning of pairs that share no hash (default),
+    the same merging every pair, or the 64-bit kernel."""
+    ctx.set_dist_mode(force64=request.param == "u64", no_prune=request.param == "rank32_noprune")
     yield ctx
-    ctx.set_dist_mode(force64=False)
+    ctx.set_dist_mode()
 
 
 def _oracle_matrix(oracle, ref, qry, s, k, kmer_space, max_d=1.0, max_p=1.0):
