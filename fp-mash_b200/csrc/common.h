@@ -55,8 +55,9 @@ struct fpm_ctx {
     // FASTA ingestion (fpm_fasta_parse): raw bytes, compacted sequence, per-chunk scan arrays, record table
     fpm::DevBuf fa_raw, fa_seq, fa_chunk, fa_recs;
     uint64_t fa_records = 0, fa_seq_bytes = 0;
-    fpm::DevBuf d_post, d_marks;                 // dist pruning: posting lists, per-query reference bitmaps
+    fpm::DevBuf d_post, d_marks, d_group;        // dist pruning: posting lists, per-query reference bitmaps, grouped copies
     bool no_dist_prune = false;                  // tests: merge every pair
+    bool no_dist_group = false;                  // tests: prune, but leave the panels in their own order
     bool force_dist64 = false;                   // tests: run the 64-bit tile kernel although the 32-bit rank path applies
     // optional per-kernel event timing (bench roofline): pairs of events around each launch
     bool timing = false;

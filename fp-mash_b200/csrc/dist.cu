@@ -392,7 +392,8 @@ __global__ void __launch_bounds__(DT_THREADS, 2)
 dist_tile32_kernel(const uint32_t* __restrict__ pref, const uint32_t* __restrict__ pqry, uint64_t rows_ref, uint64_t rows_qry,
                    uint64_t n_ref, uint64_t n_qry, const uint64_t* __restrict__ len_ref, const uint64_t* __restrict__ len_qry,
                    DistArgs a, fpm_pair* __restrict__ out, unsigned long long* steps, uint32_t q_tile0,
-                   const uint32_t* __restrict__ marks, uint32_t mark_words, const uint32_t* __restrict__ size_ref, const uint32_t* __restrict__ size_qry)
+                   const uint32_t* __restrict__ marks, uint32_t mark_words, const uint32_t* __restrict__ size_ref, const uint32_t* __restrict__ size_qry,
+                   const uint32_t* __restrict__ perm_q, const uint32_t* __restrict__ perm_r)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* colQ = reinterpret_cast<uint32_t*>(smem_raw);               // [D4_COLROWS][32] query columns
@@ -426,6 +427,14 @@ dist_tile32_kernel(const uint32_t* __restrict__ pref, const uint32_t* __restrict
     __shared__ uint32_t s_mask[32];
     __shared__ uint16_t s_list[1024];
     __shared__ uint32_t s_npairs;
+    __shared__ uint32_t s_orig[64];          // original sketch index of my 32 queries / 32 references (panels may be grouped, dist_rank.cu)
+    if (t >= 64 && t < 128) {
+        const int c = t - 64;
+        const bool isq = c < 32;
+        const uint64_t g = (isq ? q_tile2 : r_tile2) * 32 + (c & 31), n = isq ? n_qry : n_ref;
+        const uint32_t* perm = isq ? perm_q : perm_r;
+        s_orig[c] = g < n ? (perm ? perm[g] : (uint32_t)g) : 0xffffffffu;
+    }
     if (t < 32) {
         const uint64_t qg = q_tile2 * 32 + t;
         uint32_t mk = 0;
@@ -598,33 +607,34 @@ dist_tile32_kernel(const uint32_t* __restrict__ pref, const uint32_t* __restrict
     unsigned long long my_steps = 0;       // union steps actually merged
     {
         // pairs that were not merged (by the fixed assignment: query l, references rc0 and rc1): no shared hash
-        const uint64_t qg = q_tile2 * 32 + l;
-        if (qg < n_qry) {
-            const uint64_t lq = len_qry[qg];
-            const uint32_t sq = size_qry[qg], mk = s_mask[l];
+        const uint32_t qo = s_orig[l];
+        if (qo != 0xffffffffu) {
+            const uint64_t lq = len_qry[qo];
+            const uint32_t sq = size_qry[qo], mk = s_mask[l];
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const int rc = h ? rc1 : rc0;
-                const uint64_t rg = r_tile2 * 32 + rc;
-                if (rg < n_ref && !((mk >> rc) & 1u)) {
-                    const uint64_t un = (uint64_t)sq + size_ref[rg];
-                    finish_pair(a, 0, un < a.s ? un : a.s, len_ref[rg], lq, &res[l * 32 + rc]);
+                const uint32_t ro = s_orig[32 + rc];
+                if (ro != 0xffffffffu && !((mk >> rc) & 1u)) {
+                    const uint64_t un = (uint64_t)sq + size_ref[ro];
+                    finish_pair(a, 0, un < a.s ? un : a.s, len_ref[ro], lq, &res[l * 32 + rc]);
                 }
             }
         }
         // the merged ones, by whoever merged them (marked pairs are always real pairs)
-        if (act0) { const uint64_t q = q_tile2 * 32 + qc0, r = r_tile2 * 32 + rcm0; finish_pair(a, common0, denom0, len_ref[r], len_qry[q], &res[qc0 * 32 + rcm0]); my_steps += denom0; }
-        if (act1) { const uint64_t q = q_tile2 * 32 + qc1, r = r_tile2 * 32 + rcm1; finish_pair(a, common1, denom1, len_ref[r], len_qry[q], &res[qc1 * 32 + rcm1]); my_steps += denom1; }
+        if (act0) { finish_pair(a, common0, denom0, len_ref[s_orig[32 + rcm0]], len_qry[s_orig[qc0]], &res[qc0 * 32 + rcm0]); my_steps += denom0; }
+        if (act1) { finish_pair(a, common1, denom1, len_ref[s_orig[32 + rcm1]], len_qry[s_orig[qc1]], &res[qc1 * 32 + rcm1]); my_steps += denom1; }
     }
     __syncthreads();
     {
-        // 32 rows of 32 pairs = 768 bytes each, written as 8-byte words
+        // 32 rows of 32 pairs, written as 8-byte words to out[original query][original reference]: 768-byte rows when the
+        // panels are in their own order, 24-byte records when they were grouped
         const uint64_t* src = reinterpret_cast<const uint64_t*>(res);
         for (int idx = t; idx < 32 * 32 * 3; idx += DT_THREADS) {
             int row = idx / 96, wd = idx % 96, pr = wd / 3;
-            uint64_t qg2 = q_tile2 * 32 + row, rg2 = r_tile2 * 32 + pr;
-            if (qg2 < n_qry && rg2 < n_ref)
-                reinterpret_cast<uint64_t*>(out + qg2 * n_ref + rg2)[wd % 3] = src[idx];
+            const uint32_t qo = s_orig[row], ro = s_orig[32 + pr];
+            if (qo != 0xffffffffu && ro != 0xffffffffu)
+                reinterpret_cast<uint64_t*>(out + (uint64_t)qo * n_ref + ro)[wd % 3] = src[idx];
         }
     }
     if (steps) {
@@ -655,6 +665,11 @@ static int run_dist(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* d_r
         uint32_t* marks = nullptr;
         if (!ctx->force_dist64 && (rc = dist_rank_panels(ctx, d_ref, d_qry, max_size_ref, max_size_qry, rows_r, rows_q, a.s, &p32r, &p32q, &mode, &marks))) return rc;
         if (mode == DIST_RANK_UNSORTED) fast = false;
+        uint32_t *perm_q = nullptr, *perm_r = nullptr;
+        // grouping related sketches pays when results stay on the device (a grouped query order would break the row-chunked
+        // copy-out of the host path) and the panels are large enough to have many tiles
+        if (mode == DIST_RANK_OK && marks && !h_out && !ctx->no_dist_group && d_ref->n >= 256 && d_qry->n >= 256)
+            if ((rc = dist_group_panels(ctx, d_qry->n, d_ref->n, rows_q, rows_r, &p32r, &p32q, &marks, &perm_q, &perm_r))) return rc;
         if (mode == DIST_RANK_TOO_BIG) {
             if ((rc = ctx->d_ref.ensure(nr16 * 16 * rows_r * 8))) return rc;
             if ((rc = ctx->d_qry.ensure(nq16 * 16 * rows_q * 8))) return rc;
@@ -694,7 +709,7 @@ static int run_dist(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* d_r
                 ctx->time_begin(FPM_KERNEL_DIST_TILE);
                 if (k32)
                     dist_tile32_kernel<<<grid, DT_THREADS, smem, st>>>(p32r, p32q, rows_r, rows_q, d_ref->n, d_qry->n, d_ref->lengths, d_qry->lengths, a,
-                                                                       d_out, (unsigned long long*)d_steps, (uint32_t)t0, marks, (uint32_t)((d_ref->n + 31) / 32), d_ref->sizes, d_qry->sizes);
+                                                                       d_out, (unsigned long long*)d_steps, (uint32_t)t0, marks, (uint32_t)((d_ref->n + 31) / 32), d_ref->sizes, d_qry->sizes, perm_q, perm_r);
                 else
                     dist_tile_kernel<<<grid, DT_THREADS, smem, st>>>(ctx->d_ref.as<uint64_t>(), ctx->d_qry.as<uint64_t>(), rows_r, rows_q, d_ref->n,
                                                                      d_qry->n, d_ref->lengths, d_qry->lengths, a, d_out, (unsigned long long*)d_steps, (uint32_t)t0);

@@ -120,6 +120,100 @@ __global__ void __launch_bounds__(256) dist_mark_kernel(const uint32_t* __restri
     for (uint32_t w = threadIdx.x; w < words; w += blockDim.x) marks[(uint64_t)q * words + w] = s_bits[w];
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Grouping.  A 32 x 32 tile is either skipped (no marked pair), merged at full efficiency (many marked pairs) or
+// merged by a nearly idle CTA (a few).  Related sketches that sit next to each other make tiles of the first two
+// kinds, so both panels are put in an order in which they do: queries by their first marked reference, references
+// by the first query that marks them (stable sorts).  A heuristic -- results never depend on it.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dist_group_key_kernel(const uint32_t* __restrict__ marks, uint32_t n_q, uint32_t n_r, uint32_t words,
+                                                             uint32_t* __restrict__ key_q, uint32_t* __restrict__ key_r)
+{
+    const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (q >= n_q) return;
+    uint32_t first = n_r;
+    for (uint32_t w = lane; w < words; w += 32) {
+        uint32_t m = marks[(uint64_t)q * words + w];
+        if (m && first == n_r) first = w * 32 + (__ffs(m) - 1);
+        for (; m; m &= m - 1) atomicMin(&key_r[w * 32 + (__ffs(m) - 1)], q);
+    }
+    for (int o = 16; o; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+    if (lane == 0) key_q[q] = first;
+}
+
+__global__ void __launch_bounds__(256) dist_iota_kernel(uint32_t* v, uint32_t n)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = i;
+}
+
+// column tiles in the new order: sketch sk' of the output is sketch perm[sk'] of the input
+__global__ void __launch_bounds__(256) dist_repack_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, const uint32_t* __restrict__ perm,
+                                                          uint64_t n, uint64_t rows)
+{
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;     // over n16*16 x rows, column fastest
+    const uint64_t n16 = (n + 15) / 16;
+    if (idx >= n16 * 16 * rows) return;
+    const uint64_t c = idx & 15, row = (idx >> 4) % rows, tile = (idx >> 4) / rows, sk = tile * 16 + c;
+    uint32_t v = 0xffffffffu;
+    if (sk < n) { const uint64_t o = perm[sk]; v = src[(((o >> 4) * rows + row) << 4) + (o & 15)]; }
+    dst[idx] = v;
+}
+
+__global__ void __launch_bounds__(256) dist_marks_permute_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, const uint32_t* __restrict__ perm_q,
+                                                                 const uint32_t* __restrict__ perm_r, uint32_t n_q, uint32_t n_r, uint32_t words)
+{
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (uint64_t)n_q * words) return;
+    const uint32_t q2 = (uint32_t)(idx / words), w2 = (uint32_t)(idx % words);
+    const uint32_t* row = src + (uint64_t)perm_q[q2] * words;
+    uint32_t out = 0;
+    for (uint32_t b = 0; b < 32 && w2 * 32 + b < n_r; b++) {
+        const uint32_t r = perm_r[w2 * 32 + b];
+        out |= ((row[r >> 5] >> (r & 31)) & 1u) << b;
+    }
+    dst[idx] = out;
+}
+
+int dist_group_panels(fpm_ctx* ctx, uint64_t n_q, uint64_t n_r, uint64_t rows_q, uint64_t rows_r, uint32_t** p32r, uint32_t** p32q, uint32_t** marks,
+                      uint32_t** perm_q, uint32_t** perm_r)
+{
+    cudaStream_t st = ctx->stream;
+    const uint32_t words = (uint32_t)((n_r + 31) / 32);
+    const uint64_t nr16 = (n_r + 15) / 16, nq16 = (n_q + 15) / 16;
+    const uint64_t pr = nr16 * 16 * rows_r, pq = nq16 * 16 * rows_q;
+    size_t tmp_q = 0, tmp_r = 0;
+    FPM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_q, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (int64_t)n_q, 0, 32, st));
+    FPM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_r, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (int64_t)n_r, 0, 32, st));
+    const size_t tmp = std::max(tmp_q, tmp_r);
+    const size_t aq = (n_q * 4 + 255) & ~(size_t)255, ar = (n_r * 4 + 255) & ~(size_t)255, am = ((size_t)n_q * words * 4 + 255) & ~(size_t)255;
+    const size_t ap = ((pr + pq) * 4 + 255) & ~(size_t)255;
+    int rc;
+    if ((rc = ctx->d_group.ensure(4 * aq + 4 * ar + am + ap + tmp + 256))) return rc;
+    unsigned char* b = ctx->d_group.as<unsigned char>();
+    uint32_t* key_q = (uint32_t*)b; uint32_t* key_q2 = (uint32_t*)(b + aq); uint32_t* idx_q = (uint32_t*)(b + 2 * aq); uint32_t* pq_out = (uint32_t*)(b + 3 * aq);
+    b += 4 * aq;
+    uint32_t* key_r = (uint32_t*)b; uint32_t* key_r2 = (uint32_t*)(b + ar); uint32_t* idx_r = (uint32_t*)(b + 2 * ar); uint32_t* pr_out = (uint32_t*)(b + 3 * ar);
+    b += 4 * ar;
+    uint32_t* marks2 = (uint32_t*)b; b += am;
+    uint32_t* packed2 = (uint32_t*)b; b += ap;
+    void* d_tmp = b;
+    FPM_CUDA(cudaMemsetAsync(key_r, 0xff, n_r * 4, st));
+    dist_group_key_kernel<<<(uint32_t)((n_q * 32 + 255) / 256), 256, 0, st>>>(*marks, (uint32_t)n_q, (uint32_t)n_r, words, key_q, key_r);
+    dist_iota_kernel<<<(uint32_t)((n_q + 255) / 256), 256, 0, st>>>(idx_q, (uint32_t)n_q);
+    dist_iota_kernel<<<(uint32_t)((n_r + 255) / 256), 256, 0, st>>>(idx_r, (uint32_t)n_r);
+    FPM_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_q, key_q, key_q2, idx_q, pq_out, (int64_t)n_q, 0, 32, st));
+    FPM_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_r, key_r, key_r2, idx_r, pr_out, (int64_t)n_r, 0, 32, st));
+    dist_repack_kernel<<<(uint32_t)((pr + 255) / 256), 256, 0, st>>>(*p32r, packed2, pr_out, n_r, rows_r);
+    dist_repack_kernel<<<(uint32_t)((pq + 255) / 256), 256, 0, st>>>(*p32q, packed2 + pr, pq_out, n_q, rows_q);
+    dist_marks_permute_kernel<<<(uint32_t)(((uint64_t)n_q * words + 255) / 256), 256, 0, st>>>(*marks, marks2, pq_out, pr_out, (uint32_t)n_q, (uint32_t)n_r, words);
+    ctx->launches += 8;
+    FPM_CUDA(cudaGetLastError());
+    *p32r = packed2; *p32q = packed2 + pr; *marks = marks2; *perm_q = pq_out; *perm_r = pr_out;
+    return FPM_OK;
+}
+
 int dist_rank_panels(fpm_ctx* ctx, const fpm_panel* d_ref, const fpm_panel* d_qry, uint32_t max_size_ref, uint32_t max_size_qry,
                      uint64_t rows_r, uint64_t rows_q, uint32_t sketch_size, uint32_t** packed_ref, uint32_t** packed_qry, int* mode, uint32_t** marks)
 {

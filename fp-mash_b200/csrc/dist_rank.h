@@ -13,4 +13,9 @@ int dist_rank_panels(fpm_ctx* ctx, const fpm_panel* d_ref, const fpm_panel* d_qr
 // *marks (nullable result): per query one row of ceil(n_ref / 32) words, bit r set iff reference r shares at least one hash
 // with the query; nullptr when pruning is off or would not pay.
 
+// Reorders both panels so that related sketches are neighbours (see dist_rank.cu): replaces *p32r / *p32q / *marks by
+// their permuted versions and returns the permutations (new index -> original sketch index, device arrays).
+int dist_group_panels(fpm_ctx* ctx, uint64_t n_q, uint64_t n_r, uint64_t rows_q, uint64_t rows_r, uint32_t** p32r, uint32_t** p32q, uint32_t** marks,
+                      uint32_t** perm_q, uint32_t** perm_r);
+
 }  // namespace fpm

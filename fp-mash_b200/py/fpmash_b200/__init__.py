@@ -231,10 +231,10 @@ class Context:
     def launch_count(self):
         return int(lib.fpm_ctx_launch_count(self._h))
 
-    def set_dist_mode(self, force64=False, no_prune=False):
+    def set_dist_mode(self, force64=False, no_prune=False, no_group=False):
         """force64=True: run the 64-bit tile kernel even where the 32-bit rank kernel applies; no_prune=True: the rank
         kernel merges every pair (no skipping of pairs that share no hash)."""
-        _check(lib.fpm_ctx_set_dist_mode(self._h, 1 if force64 else (2 if no_prune else 0)))
+        _check(lib.fpm_ctx_set_dist_mode(self._h, 1 if force64 else (2 if no_prune else (3 if no_group else 0))))
 
     def set_timing(self, enable=True):
         _check(lib.fpm_ctx_set_timing(self._h, int(enable)))

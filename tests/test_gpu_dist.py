@@ -227,3 +227,36 @@ def test_dist_small_universe_many_ties(ctx, oracle):
             g = got32[q, r]
             assert int(g["numer"]) == w["numer"] and int(g["denom"]) == w["denom"], (s_cmp, q, r, g, w)
             assert g["distance"] == pytest.approx(w["distance"], rel=RTOL, abs=0)
+
+
+def test_dist_device_path_grouped_equals_ungrouped(ctx):
+    """The device entry point (results stay in HBM) reorders both panels so that related sketches share tiles; the output
+    must not depend on it: grouped+pruned = pruned = every pair merged = host path, byte for byte."""
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(14)
+    s = 500
+    n_r, n_q = 700, 333
+    rh, rs = sorted_sketch_panel(rng, n_r, s, n_clusters=9, shared=0.6)
+    qh, qs = sorted_sketch_panel(rng, n_q, s, n_clusters=9, shared=0.6)
+    qh[:50] = rh[200:250]; qs[:50] = rs[200:250]
+    qh[60:80] = 0; qs[60:80] = 0                                   # empty query sketches in the middle
+    rl = rng.integers(1000, 6_000_000, size=n_r).astype(np.uint64)
+    ql = rng.integers(1000, 6_000_000, size=n_q).astype(np.uint64)
+    want, _ = ctx.dist_tile((rh, rs, rl), (qh, qs, ql), s, 21, 4.0 ** 21, raw=True)
+    dev = torch.device("cuda", 0)
+    t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a).view(dt)).to(dev)
+    d_rh, d_rs, d_rl = t(rh, np.int64), t(rs.astype(np.uint32), np.int32), t(rl, np.int64)
+    d_qh, d_qs, d_ql = t(qh, np.int64), t(qs.astype(np.uint32), np.int32), t(ql, np.int64)
+    outs = []
+    for kw in (dict(), dict(no_group=True), dict(no_prune=True)):
+        ctx.set_dist_mode(**kw)
+        try:
+            out = torch.zeros(n_q * n_r * 24, dtype=torch.uint8, device=dev)
+            ctx.dist_tile_dev((d_rh.data_ptr(), d_rs.data_ptr(), d_rl.data_ptr(), n_r, s), (d_qh.data_ptr(), d_qs.data_ptr(), d_ql.data_ptr(), n_q, s),
+                              s, 21, 4.0 ** 21, out.data_ptr())
+            torch.cuda.synchronize()
+            outs.append(out.cpu().numpy().tobytes())
+        finally:
+            ctx.set_dist_mode()
+    assert outs[0] == outs[1] == outs[2]
+    assert outs[0] == np.ascontiguousarray(want).tobytes()
