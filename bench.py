@@ -361,48 +361,64 @@ def main():
                               S, K, kspace, out_pairs.data_ptr(), steps_ctr.data_ptr())
 
         dsteps = max(2, min(args.steps, 3))
-        for _ in range(2):
-            step_dist()
-        barrier()
-        steps_ctr.zero_()
-        ctx.set_timing(True)
-        dl0 = ctx.launch_count()
-        e0.record()
-        for _ in range(dsteps):
-            step_dist()
-        e1.record()
-        barrier()
-        d_ms = max_over_ranks(e0.elapsed_time(e1)) / dsteps
-        tile_ms, tile_n = ctx.get_timing(fpm.KERNEL_DIST_TILE)
-        lit_ms, lit_n = ctx.get_timing(fpm.KERNEL_DIST_LITERAL)
-        pack_ms, pack_n = ctx.get_timing(fpm.KERNEL_DIST_PACK)
-        ctx.set_timing(False)
-        merge_steps = int(steps_ctr.item()) / dsteps
         pairs = nd * nd
-        tile_avg = tile_ms / max(tile_n, 1)
+        n_sm = torch.cuda.get_device_properties(device).multi_processor_count
+
+        def timed_dist(**mode):
+            """dsteps timed passes of the sharded all-vs-all dist in the given kernel mode."""
+            ctx.set_dist_mode(**mode)
+            try:
+                for _ in range(2):
+                    step_dist()
+                barrier()
+                steps_ctr.zero_()
+                ctx.set_timing(True)
+                l0 = ctx.launch_count()
+                e0.record()
+                for _ in range(dsteps):
+                    step_dist()
+                e1.record()
+                barrier()
+                ms = max_over_ranks(e0.elapsed_time(e1)) / dsteps
+                tile_ms, tile_n = ctx.get_timing(fpm.KERNEL_DIST_TILE)
+                lit_ms, lit_n = ctx.get_timing(fpm.KERNEL_DIST_LITERAL)
+                pack_ms, pack_n = ctx.get_timing(fpm.KERNEL_DIST_PACK)
+                ctx.set_timing(False)
+                return {"ms": ms, "tile_avg": tile_ms / max(tile_n, 1), "tile_n": tile_n, "lit_n": lit_n, "pack_avg": pack_ms / max(pack_n, 1),
+                        "merge_steps": int(steps_ctr.item()) / dsteps, "launches": ctx.launch_count() - l0}
+            finally:
+                ctx.set_dist_mode()
+
+        full = timed_dist(no_prune=True)        # every pair merged: the merge kernel's own throughput and rooflines
+        run = timed_dist()                      # the product path: pairs without a shared hash are answered without a merge
+        d_ms, tile_avg, merge_steps = run["ms"], run["tile_avg"], run["merge_steps"]
+        out_bytes = (q1 - q0) * nd * 24 + 2 * nd * (S + 1) * 4
         dist_obj = {
             "metric": "sketch-pairs/sec dist (all-vs-all, k=21 s=1000)", "value": pairs / (d_ms * 1e-3), "unit": "pairs/s",
             "ms_per_step": d_ms, "steps": dsteps, "scaling": "strong",
             "config": {"workload": "all-vs-all mash dist of %d sketches (BASELINE configs[2])" % nd, "sketches": nd,
                        "sketch_size": S, "k": K, "sharding": "query rows over ranks, NCCL all-gather of the reference panel" if world > 1 else "single GPU"},
-            "gpu_launches": ctx.launch_count() - dl0, "fast_path_launches": tile_n, "literal_launches": lit_n,
+            "gpu_launches": run["launches"], "fast_path_launches": run["tile_n"], "literal_launches": run["lit_n"],
             "merge_steps_per_pair": merge_steps / ((q1 - q0) * nd),
-            "kernel_ms": {"dist_tile32": tile_avg, "rank_compress_and_mark": pack_ms / max(pack_n, 1)},
-            "pruning": "pairs whose sketches share no hash (known from the sorted hashes of the rank pre-pass) are answered without a merge; merge_steps_per_pair counts executed steps only",
-            "roofline_int": {"bound": "int32-alu", "achieved": merge_steps * 3 / (tile_avg * 1e-3) / 1e12 if tile_n else None,
-                             "peak": int_peak / 1e12, "unit": "Tint32-op/s",
-                             "frac": (merge_steps * 3 / (tile_avg * 1e-3)) / int_peak if tile_n else None,
-                             "note": "algorithmic ops = merge steps x 3 (SURVEY.md 8d) / dist_tile_kernel time; peak measured by fpm_measure_int32_peak"},
-            "roofline": {"bound": "hbm", "achieved": ((q1 - q0) * nd * 24 + 2 * nd * S * 8) / (tile_avg * 1e-3) / 1e9 if tile_n else None,
-                         "peak": hbm_peak, "unit": "GB/s",
-                         "frac": ((q1 - q0) * nd * 24 + 2 * nd * S * 8) / (tile_avg * 1e-3) / 1e9 / hbm_peak if tile_n else None,
-                         "traffic": ((q1 - q0) * nd * 24 + 2 * nd * (S + 1) * 4) * NCU_DIST_TRAFFIC_RATIO,
-                         "traffic_note": "dram bytes of one ncu --set full capture of dist_tile32_kernel (profiles/r01_dist_tile32_v4.txt) scaled to this launch; below the algorithmic bytes because part of the output was still in L2 when the capture ended"},
-            "roofline_smem": {"bound": "shared-memory bandwidth", "achieved": merge_steps * 8 / (tile_avg * 1e-3) / 1e12 if tile_n else None,
-                              "peak": torch.cuda.get_device_properties(device).multi_processor_count * SMEM_BYTES_PER_CLK_PER_SM * 1.965e9 / 1e12,
-                              "unit": "TB/s",
-                              "frac": (merge_steps * 8 / (tile_avg * 1e-3)) / (torch.cuda.get_device_properties(device).multi_processor_count * SMEM_BYTES_PER_CLK_PER_SM * 1.965e9) if tile_n else None,
-                              "note": "what bounds the rank kernel: every merge step is two 4-byte shared-memory loads per pair (one LDS.32 wavefront per list per warp); peak = SMs x 128 B/clk x 1965 MHz; ncu: shared-memory pipe 87 % busy incl. staging"},
+            "kernel_ms": {"dist_tile32": tile_avg, "rank_compress_index_mark": run["pack_avg"]},
+            "pruning": "exact: the rank pre-pass sorts every hash of both panels, which is also an inverted index; a pair whose sketches share no hash has common = 0 and denom = min(s, |A|+|B|) and is answered without a merge; related sketches are grouped into the same tiles; merge_steps_per_pair counts executed steps only; merge_all_pairs below is the same call with every pair merged",
+            "roofline": {"bound": "hbm", "achieved": out_bytes / (tile_avg * 1e-3) / 1e9 if run["tile_n"] else None, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": out_bytes / (tile_avg * 1e-3) / 1e9 / hbm_peak if run["tile_n"] else None, "traffic": None,
+                         "note": "dist_tile32_kernel of the pruned run: rank panels read once + 24 B per pair written (to the pairs' original positions, i.e. as 24-byte records when the panels were grouped)"},
+            "merge_all_pairs": {
+                "value": pairs / (full["ms"] * 1e-3), "unit": "pairs/s", "ms_per_step": full["ms"], "merge_steps_per_pair": full["merge_steps"] / ((q1 - q0) * nd),
+                "kernel_ms": {"dist_tile32": full["tile_avg"], "rank_compress": full["pack_avg"]},
+                "roofline_int": {"bound": "int32-alu", "achieved": full["merge_steps"] * 3 / (full["tile_avg"] * 1e-3) / 1e12, "peak": int_peak / 1e12, "unit": "Tint32-op/s",
+                                 "frac": (full["merge_steps"] * 3 / (full["tile_avg"] * 1e-3)) / int_peak,
+                                 "note": "algorithmic ops = merge steps x 3 (SURVEY.md 8d) / dist_tile32_kernel time; peak measured by fpm_measure_int32_peak"},
+                "roofline_smem": {"bound": "shared-memory bandwidth", "achieved": full["merge_steps"] * 8 / (full["tile_avg"] * 1e-3) / 1e12,
+                                  "peak": n_sm * SMEM_BYTES_PER_CLK_PER_SM * 1.965e9 / 1e12, "unit": "TB/s",
+                                  "frac": (full["merge_steps"] * 8 / (full["tile_avg"] * 1e-3)) / (n_sm * SMEM_BYTES_PER_CLK_PER_SM * 1.965e9),
+                                  "note": "what bounds the merge: every step is two 4-byte shared-memory loads per pair (one LDS.32 wavefront per list per warp); peak = SMs x 128 B/clk x 1965 MHz; ncu: shared-memory pipe 87 % busy incl. staging"},
+                "roofline": {"bound": "hbm", "achieved": out_bytes / (full["tile_avg"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": out_bytes / (full["tile_avg"] * 1e-3) / 1e9 / hbm_peak,
+                             "traffic": out_bytes * NCU_DIST_TRAFFIC_RATIO,
+                             "traffic_note": "dram bytes of one ncu --set full capture of dist_tile32_kernel (profiles/r01_dist_tile32_v4.txt) scaled to this launch; below the algorithmic bytes because part of the output was still in L2 when the capture ended"},
+            },
         }
         # e2e on a stated sample of query rows (host panels in, 24-byte records out)
         if rank == 0:
