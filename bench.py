@@ -250,7 +250,7 @@ def main():
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("FPM_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version banner / debug lines stay off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=device)
 
     def barrier():

@@ -91,6 +91,44 @@ __device__ __forceinline__ void finish_pair(const DistArgs& a, uint64_t common, 
     *out = o;
 }
 
+// fpm_dist_hits: passing pairs are appended to a list instead of written to an n x n matrix.
+struct HitSink {
+    fpm_hit* buf = nullptr;              // nullptr: matrix mode
+    unsigned long long* count = nullptr; // all passing pairs, also those beyond cap (the caller retries with room for them)
+    unsigned long long cap = 0;
+    int skip_unmarked = 0;               // the filters exclude distance 1: a pair without a shared hash cannot pass
+};
+
+// Called by whole converged warps: one atomicAdd per warp, the lanes with a hit write 32-byte records behind each other.
+__device__ __forceinline__ void append_hit(const HitSink& hs, bool pass, uint32_t q, uint32_t r, const fpm_pair& o)
+{
+    const uint32_t m = __ballot_sync(0xffffffffu, pass);
+    if (!m) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(hs.count, (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    const unsigned long long at = base + __popc(m & ((1u << lane) - 1u));
+    if (pass && at < hs.cap) {
+        uint4* dst = reinterpret_cast<uint4*>(hs.buf + at);
+        dst[0] = make_uint4(q, r, o.numer, o.denom);
+        dst[1] = make_uint4((uint32_t)__double_as_longlong(o.distance), (uint32_t)(__double_as_longlong(o.distance) >> 32),
+                            (uint32_t)__double_as_longlong(o.pvalue), (uint32_t)(__double_as_longlong(o.pvalue) >> 32));
+    }
+}
+
+// hits mode of the paths that produce a matrix (64-bit tile kernel, literal kernel): scan it for passing pairs
+__global__ void __launch_bounds__(256) dist_collect_kernel(const fpm_pair* __restrict__ mat, uint64_t total, uint64_t n_ref, HitSink hs)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * 256;
+    for (uint64_t base = (uint64_t)blockIdx.x * 256; base < total; base += stride) {   // uniform per CTA: warps stay converged
+        const uint64_t p = base + threadIdx.x;
+        fpm_pair o = {0, 0, 0., 0.};
+        if (p < total && (mat[p].denom & FPM_PAIR_PASS)) o = mat[p];
+        append_hit(hs, (o.denom & FPM_PAIR_PASS) != 0, (uint32_t)(p / n_ref), (uint32_t)(p % n_ref), o);
+    }
+}
+
 __global__ void __launch_bounds__(256) dist_literal_kernel(fpm_panel ref, fpm_panel qry, DistArgs a, fpm_pair* out, unsigned long long* steps)
 {
     uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -393,7 +431,7 @@ dist_tile32_kernel(const uint32_t* __restrict__ pref, const uint32_t* __restrict
                    uint64_t n_ref, uint64_t n_qry, const uint64_t* __restrict__ len_ref, const uint64_t* __restrict__ len_qry,
                    DistArgs a, fpm_pair* __restrict__ out, unsigned long long* steps, uint32_t q_tile0,
                    const uint32_t* __restrict__ marks, uint32_t mark_words, const uint32_t* __restrict__ size_ref, const uint32_t* __restrict__ size_qry,
-                   const uint32_t* __restrict__ perm_q, const uint32_t* __restrict__ perm_r)
+                   const uint32_t* __restrict__ perm_q, const uint32_t* __restrict__ perm_r, HitSink hs)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* colQ = reinterpret_cast<uint32_t*>(smem_raw);               // [D4_COLROWS][32] query columns
@@ -601,40 +639,67 @@ dist_tile32_kernel(const uint32_t* __restrict__ pref, const uint32_t* __restrict
         R = (int)min((uint32_t)D4_ROWS, max(32u, need_all));
     }
 
-    // ---- results: stage in shared memory, then coalesced row writes ---------------------
+    // ---- results -------------------------------------------------------------------------
     __syncthreads();
-    fpm_pair* res = reinterpret_cast<fpm_pair*>(smem_raw);                  // [32][32]
     unsigned long long my_steps = 0;       // union steps actually merged
-    {
-        // pairs that were not merged (by the fixed assignment: query l, references rc0 and rc1): no shared hash
-        const uint32_t qo = s_orig[l];
-        if (qo != 0xffffffffu) {
-            const uint64_t lq = len_qry[qo];
-            const uint32_t sq = size_qry[qo], mk = s_mask[l];
+    if (hs.buf) {
+        // hits mode: nothing is written for a pair that fails the -d / -v filters
+        fpm_pair o = {0, 0, 0., 0.};
+        if (!hs.skip_unmarked) {
+            const uint32_t qo = s_orig[l], mk = s_mask[l];
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const int rc = h ? rc1 : rc0;
                 const uint32_t ro = s_orig[32 + rc];
-                if (ro != 0xffffffffu && !((mk >> rc) & 1u)) {
-                    const uint64_t un = (uint64_t)sq + size_ref[ro];
-                    finish_pair(a, 0, un < a.s ? un : a.s, len_ref[ro], lq, &res[l * 32 + rc]);
+                bool pass = false;
+                if (qo != 0xffffffffu && ro != 0xffffffffu && !((mk >> rc) & 1u)) {
+                    const uint64_t un = (uint64_t)size_qry[qo] + size_ref[ro];
+                    finish_pair(a, 0, un < a.s ? un : a.s, len_ref[ro], len_qry[qo], &o);
+                    pass = (o.denom & FPM_PAIR_PASS) != 0;
                 }
+                append_hit(hs, pass, qo, ro, o);
             }
         }
-        // the merged ones, by whoever merged them (marked pairs are always real pairs)
-        if (act0) { finish_pair(a, common0, denom0, len_ref[s_orig[32 + rcm0]], len_qry[s_orig[qc0]], &res[qc0 * 32 + rcm0]); my_steps += denom0; }
-        if (act1) { finish_pair(a, common1, denom1, len_ref[s_orig[32 + rcm1]], len_qry[s_orig[qc1]], &res[qc1 * 32 + rcm1]); my_steps += denom1; }
-    }
-    __syncthreads();
-    {
-        // 32 rows of 32 pairs, written as 8-byte words to out[original query][original reference]: 768-byte rows when the
-        // panels are in their own order, 24-byte records when they were grouped
-        const uint64_t* src = reinterpret_cast<const uint64_t*>(res);
-        for (int idx = t; idx < 32 * 32 * 3; idx += DT_THREADS) {
-            int row = idx / 96, wd = idx % 96, pr = wd / 3;
-            const uint32_t qo = s_orig[row], ro = s_orig[32 + pr];
-            if (qo != 0xffffffffu && ro != 0xffffffffu)
-                reinterpret_cast<uint64_t*>(out + (uint64_t)qo * n_ref + ro)[wd % 3] = src[idx];
+        bool pass = false;
+        if (act0) { finish_pair(a, common0, denom0, len_ref[s_orig[32 + rcm0]], len_qry[s_orig[qc0]], &o); my_steps += denom0; pass = (o.denom & FPM_PAIR_PASS) != 0; }
+        append_hit(hs, pass, s_orig[qc0], s_orig[32 + rcm0], o);
+        pass = false;
+        if (act1) { finish_pair(a, common1, denom1, len_ref[s_orig[32 + rcm1]], len_qry[s_orig[qc1]], &o); my_steps += denom1; pass = (o.denom & FPM_PAIR_PASS) != 0; }
+        append_hit(hs, pass, s_orig[qc1], s_orig[32 + rcm1], o);
+    } else {
+        // matrix mode: stage in shared memory, then coalesced row writes
+        fpm_pair* res = reinterpret_cast<fpm_pair*>(smem_raw);                  // [32][32]
+        {
+            // pairs that were not merged (by the fixed assignment: query l, references rc0 and rc1): no shared hash
+            const uint32_t qo = s_orig[l];
+            if (qo != 0xffffffffu) {
+                const uint64_t lq = len_qry[qo];
+                const uint32_t sq = size_qry[qo], mk = s_mask[l];
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int rc = h ? rc1 : rc0;
+                    const uint32_t ro = s_orig[32 + rc];
+                    if (ro != 0xffffffffu && !((mk >> rc) & 1u)) {
+                        const uint64_t un = (uint64_t)sq + size_ref[ro];
+                        finish_pair(a, 0, un < a.s ? un : a.s, len_ref[ro], lq, &res[l * 32 + rc]);
+                    }
+                }
+            }
+            // the merged ones, by whoever merged them (marked pairs are always real pairs)
+            if (act0) { finish_pair(a, common0, denom0, len_ref[s_orig[32 + rcm0]], len_qry[s_orig[qc0]], &res[qc0 * 32 + rcm0]); my_steps += denom0; }
+            if (act1) { finish_pair(a, common1, denom1, len_ref[s_orig[32 + rcm1]], len_qry[s_orig[qc1]], &res[qc1 * 32 + rcm1]); my_steps += denom1; }
+        }
+        __syncthreads();
+        {
+            // 32 rows of 32 pairs, written as 8-byte words to out[original query][original reference]: 768-byte rows when the
+            // panels are in their own order, 24-byte records when they were grouped
+            const uint64_t* src = reinterpret_cast<const uint64_t*>(res);
+            for (int idx = t; idx < 32 * 32 * 3; idx += DT_THREADS) {
+                int row = idx / 96, wd = idx % 96, pr = wd / 3;
+                const uint32_t qo = s_orig[row], ro = s_orig[32 + pr];
+                if (qo != 0xffffffffu && ro != 0xffffffffu)
+                    reinterpret_cast<uint64_t*>(out + (uint64_t)qo * n_ref + ro)[wd % 3] = src[idx];
+            }
         }
     }
     if (steps) {
@@ -646,8 +711,28 @@ dist_tile32_kernel(const uint32_t* __restrict__ pref, const uint32_t* __restrict
 // h_out (nullable): host destination.  When given, the fast path runs in query-row chunks and copies chunk c
 // back on a second stream while chunk c+1 is being compared, then waits for all copies.
 static int run_dist(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* d_ref, const fpm_panel* d_qry, fpm_pair* d_out,
-                    uint64_t* d_steps, uint32_t max_size_ref, uint32_t max_size_qry, fpm_pair* h_out = nullptr)
+                    uint64_t* d_steps, uint32_t max_size_ref, uint32_t max_size_qry, fpm_pair* h_out = nullptr, const HitSink* hits = nullptr)
 {
+    // hits mode (fpm_dist_hits): d_out and h_out are null.  The 32-bit rank kernel appends passing pairs itself; the other
+    // paths need a result matrix, which then lives in ctx->d_out and is scanned by dist_collect_kernel.
+    const HitSink no_hits{};
+    auto matrix_for_hits = [&]() -> int {
+        const uint64_t bytes = d_ref->n * d_qry->n * sizeof(fpm_pair);
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = 0;
+        if (bytes > ctx->d_out.cap && bytes > free_b) { set_error("fpm_dist_hits: these panels need a %llu-byte result matrix on this path; pass fewer queries per call", (unsigned long long)bytes); return FPM_ERR_NOMEM; }
+        int rc = ctx->d_out.ensure(bytes);
+        if (rc) return rc;
+        d_out = ctx->d_out.as<fpm_pair>();
+        return FPM_OK;
+    };
+    auto collect = [&]() -> int {
+        const uint64_t total = d_ref->n * d_qry->n;
+        dist_collect_kernel<<<(uint32_t)std::min<uint64_t>((total + 255) / 256, (uint64_t)ctx->sm_count * 16), 256, 0, ctx->stream>>>(d_out, total, d_ref->n, *hits);
+        ctx->launches++;
+        FPM_CUDA(cudaGetLastError());
+        return FPM_OK;
+    };
     DistArgs a;
     a.s = p->sketch_size; a.kmer_size = p->kmer_size; a.kmer_space = p->kmer_space;
     a.max_distance = p->max_distance; a.max_pvalue = p->max_pvalue;
@@ -689,6 +774,7 @@ static int run_dist(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* d_r
         }
         if (fast) {
             const bool k32 = mode == DIST_RANK_OK;
+            if (hits && !k32 && (rc = matrix_for_hits())) return rc;
             const size_t smem = k32 ? (size_t)D4_COLS * D4_COLROWS * 4 : (size_t)DT_COLS * DT_COLROWS * 8;
             if (k32) FPM_CUDA(cudaFuncSetAttribute(dist_tile32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             else FPM_CUDA(cudaFuncSetAttribute(dist_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -709,7 +795,7 @@ static int run_dist(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* d_r
                 ctx->time_begin(FPM_KERNEL_DIST_TILE);
                 if (k32)
                     dist_tile32_kernel<<<grid, DT_THREADS, smem, st>>>(p32r, p32q, rows_r, rows_q, d_ref->n, d_qry->n, d_ref->lengths, d_qry->lengths, a,
-                                                                       d_out, (unsigned long long*)d_steps, (uint32_t)t0, marks, (uint32_t)((d_ref->n + 31) / 32), d_ref->sizes, d_qry->sizes, perm_q, perm_r);
+                                                                       d_out, (unsigned long long*)d_steps, (uint32_t)t0, marks, (uint32_t)((d_ref->n + 31) / 32), d_ref->sizes, d_qry->sizes, perm_q, perm_r, hits ? *hits : no_hits);
                 else
                     dist_tile_kernel<<<grid, DT_THREADS, smem, st>>>(ctx->d_ref.as<uint64_t>(), ctx->d_qry.as<uint64_t>(), rows_r, rows_q, d_ref->n,
                                                                      d_qry->n, d_ref->lengths, d_qry->lengths, a, d_out, (unsigned long long*)d_steps, (uint32_t)t0);
@@ -725,9 +811,12 @@ static int run_dist(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* d_r
                 }
             }
             if (h_out) FPM_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+            if (hits && !k32 && (rc = collect())) return rc;
         }
     }
     if (!fast) {
+        int rc;
+        if (hits && (rc = matrix_for_hits())) return rc;
         uint64_t blocks = (total + 255) / 256;
         if (blocks > 0x7fffffffull) { set_error("too many pairs for one launch"); return FPM_ERR_ARG; }
         ctx->time_begin(FPM_KERNEL_DIST_LITERAL);
@@ -739,6 +828,7 @@ static int run_dist(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* d_r
             FPM_CUDA(cudaMemcpyAsync(h_out, d_out, total * sizeof(fpm_pair), cudaMemcpyDeviceToHost, st));
             FPM_CUDA(cudaStreamSynchronize(st));
         }
+        if (hits && (rc = collect())) return rc;
     }
     return FPM_OK;
 }
@@ -783,6 +873,32 @@ int fpm_dist_tile_dev(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* d
     return run_dist(ctx, p, d_ref, d_qry, d_out, d_merge_steps, mr, mq);
 }
 
+// host panels -> device copies in ctx->d_rs / d_qs (hashes | lengths | sizes); also the largest sketch of each
+static int upload_panels(fpm_ctx* ctx, const fpm_panel* ref, const fpm_panel* qry, fpm_panel* dr, fpm_panel* dq, uint32_t* mr, uint32_t* mq)
+{
+    int rc;
+    *mr = *mq = 0;
+    for (uint64_t i = 0; i < ref->n; i++) *mr = std::max(*mr, ref->sizes[i]);
+    for (uint64_t i = 0; i < qry->n; i++) *mq = std::max(*mq, qry->sizes[i]);
+    if (*mr > ref->stride || *mq > qry->stride) { set_error("a sketch size exceeds the panel stride"); return FPM_ERR_ARG; }
+    cudaStream_t st = ctx->stream;
+    size_t rh = ref->n * ref->stride * 8, qh = qry->n * qry->stride * 8;
+    if ((rc = ctx->d_rs.ensure(rh + ref->n * 12 + 64))) return rc;
+    if ((rc = ctx->d_qs.ensure(qh + qry->n * 12 + 64))) return rc;
+    unsigned char* br = ctx->d_rs.as<unsigned char>();
+    unsigned char* bq = ctx->d_qs.as<unsigned char>();
+    *dr = *ref; *dq = *qry;
+    dr->hashes = (const uint64_t*)br; dr->lengths = (const uint64_t*)(br + rh); dr->sizes = (const uint32_t*)(br + rh + ref->n * 8);
+    dq->hashes = (const uint64_t*)bq; dq->lengths = (const uint64_t*)(bq + qh); dq->sizes = (const uint32_t*)(bq + qh + qry->n * 8);
+    if (rh) FPM_CUDA(cudaMemcpyAsync((void*)dr->hashes, ref->hashes, rh, cudaMemcpyHostToDevice, st));
+    FPM_CUDA(cudaMemcpyAsync((void*)dr->lengths, ref->lengths, ref->n * 8, cudaMemcpyHostToDevice, st));
+    FPM_CUDA(cudaMemcpyAsync((void*)dr->sizes, ref->sizes, ref->n * 4, cudaMemcpyHostToDevice, st));
+    if (qh) FPM_CUDA(cudaMemcpyAsync((void*)dq->hashes, qry->hashes, qh, cudaMemcpyHostToDevice, st));
+    FPM_CUDA(cudaMemcpyAsync((void*)dq->lengths, qry->lengths, qry->n * 8, cudaMemcpyHostToDevice, st));
+    FPM_CUDA(cudaMemcpyAsync((void*)dq->sizes, qry->sizes, qry->n * 4, cudaMemcpyHostToDevice, st));
+    return FPM_OK;
+}
+
 static int dist_tile_host(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* ref, const fpm_panel* qry, fpm_pair* out, bool positional)
 {
     if (!ctx) { set_error("ctx is NULL"); return FPM_ERR_ARG; }
@@ -791,26 +907,10 @@ static int dist_tile_host(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_pane
     if (ref->n == 0 || qry->n == 0) return FPM_OK;
     FPM_CUDA(cudaSetDevice(ctx->device));
     uint32_t mr = 0, mq = 0;
-    for (uint64_t i = 0; i < ref->n; i++) mr = std::max(mr, ref->sizes[i]);
-    for (uint64_t i = 0; i < qry->n; i++) mq = std::max(mq, qry->sizes[i]);
-    if (mr > ref->stride || mq > qry->stride) { set_error("a sketch size exceeds the panel stride"); return FPM_ERR_ARG; }
-    cudaStream_t st = ctx->stream;
-    // inputs: hashes | sizes | lengths for both panels
-    size_t rh = ref->n * ref->stride * 8, qh = qry->n * qry->stride * 8;
-    if ((rc = ctx->d_rs.ensure(rh + ref->n * 12 + 64))) return rc;
-    if ((rc = ctx->d_qs.ensure(qh + qry->n * 12 + 64))) return rc;
+    fpm_panel dr, dq;
+    if ((rc = upload_panels(ctx, ref, qry, &dr, &dq, &mr, &mq))) return rc;
     if ((rc = ctx->d_out.ensure(ref->n * qry->n * sizeof(fpm_pair)))) return rc;
-    unsigned char* br = ctx->d_rs.as<unsigned char>();
-    unsigned char* bq = ctx->d_qs.as<unsigned char>();
-    fpm_panel dr = *ref, dq = *qry;
-    dr.hashes = (const uint64_t*)br; dr.lengths = (const uint64_t*)(br + rh); dr.sizes = (const uint32_t*)(br + rh + ref->n * 8);
-    dq.hashes = (const uint64_t*)bq; dq.lengths = (const uint64_t*)(bq + qh); dq.sizes = (const uint32_t*)(bq + qh + qry->n * 8);
-    if (rh) FPM_CUDA(cudaMemcpyAsync((void*)dr.hashes, ref->hashes, rh, cudaMemcpyHostToDevice, st));
-    FPM_CUDA(cudaMemcpyAsync((void*)dr.lengths, ref->lengths, ref->n * 8, cudaMemcpyHostToDevice, st));
-    FPM_CUDA(cudaMemcpyAsync((void*)dr.sizes, ref->sizes, ref->n * 4, cudaMemcpyHostToDevice, st));
-    if (qh) FPM_CUDA(cudaMemcpyAsync((void*)dq.hashes, qry->hashes, qh, cudaMemcpyHostToDevice, st));
-    FPM_CUDA(cudaMemcpyAsync((void*)dq.lengths, qry->lengths, qry->n * 8, cudaMemcpyHostToDevice, st));
-    FPM_CUDA(cudaMemcpyAsync((void*)dq.sizes, qry->sizes, qry->n * 4, cudaMemcpyHostToDevice, st));
+    cudaStream_t st = ctx->stream;
     if (positional) {
         uint64_t total = ref->n * qry->n;
         fp_positional_kernel<<<(uint32_t)((total + 255) / 256), 256, 0, st>>>(dr, dq, p->max_distance, p->max_pvalue, ctx->d_out.as<fpm_pair>());
@@ -822,9 +922,73 @@ static int dist_tile_host(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_pane
     return FPM_OK;
 }
 
+// Both fpm_dist_hits entry points: device panels in, sorted hits at d_sorted (room for `capacity`), *n_hits on the host.
+static int dist_hits_run(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* d_ref, const fpm_panel* d_qry, uint32_t mr, uint32_t mq,
+                         fpm_hit* d_sorted, uint64_t capacity, uint64_t* n_hits, uint64_t* d_steps)
+{
+    int rc;
+    *n_hits = 0;
+    if (d_ref->n == 0 || d_qry->n == 0) return FPM_OK;
+    if (d_ref->n > 0xfffffffeull || d_qry->n > 0xfffffffeull) { set_error("panel too large for 32-bit hit indices"); return FPM_ERR_ARG; }
+    if ((rc = ctx->d_hits.ensure(capacity * sizeof(fpm_hit) + 64))) return rc;
+    cudaStream_t st = ctx->stream;
+    HitSink hs;
+    hs.count = ctx->d_hits.as<unsigned long long>();            // first 32 bytes: the counter; records follow
+    hs.buf = reinterpret_cast<fpm_hit*>(ctx->d_hits.as<unsigned char>() + 32);
+    hs.cap = capacity;
+    // a pair without a shared hash has distance 1 and p-value 1 (dist_math.h): it passes only when neither filter excludes 1
+    hs.skip_unmarked = (p->max_distance >= 0 && p->max_distance < 1.) || (p->max_pvalue >= 0 && p->max_pvalue < 1.);
+    FPM_CUDA(cudaMemsetAsync(hs.count, 0, 32, st));
+    if ((rc = run_dist(ctx, p, d_ref, d_qry, nullptr, d_steps, mr, mq, nullptr, &hs))) return rc;
+    unsigned long long n = 0;
+    FPM_CUDA(cudaMemcpyAsync(&n, hs.count, 8, cudaMemcpyDeviceToHost, st));
+    FPM_CUDA(cudaStreamSynchronize(st));
+    *n_hits = n;
+    if (n > capacity) { set_error("fpm_dist_hits: %llu pairs pass the filters, room for %llu", n, (unsigned long long)capacity); return FPM_ERR_CAPACITY; }
+    return dist_sort_hits(ctx, hs.buf, n, d_sorted);
+}
+
 int fpm_dist_tile(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* ref, const fpm_panel* qry, fpm_pair* out)
 {
     return dist_tile_host(ctx, p, ref, qry, out, false);
+}
+
+int fpm_dist_hits_dev(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* d_ref, const fpm_panel* d_qry, fpm_hit* d_out, uint64_t capacity,
+                      uint64_t* n_hits, uint64_t* d_merge_steps)
+{
+    if (!ctx) { set_error("ctx is NULL"); return FPM_ERR_ARG; }
+    if (!n_hits || (!d_out && capacity)) { set_error("NULL argument"); return FPM_ERR_ARG; }
+    int rc = check_dist(p, d_ref, d_qry);
+    if (rc) return rc;
+    FPM_CUDA(cudaSetDevice(ctx->device));
+    uint32_t mr = 0, mq = 0;
+    if ((rc = max_size_dev(ctx, d_ref, &mr))) return rc;
+    if ((rc = max_size_dev(ctx, d_qry, &mq))) return rc;
+    if (mr > d_ref->stride || mq > d_qry->stride) { set_error("a sketch size exceeds the panel stride"); return FPM_ERR_ARG; }
+    if ((rc = dist_hits_run(ctx, p, d_ref, d_qry, mr, mq, d_out, capacity, n_hits, d_merge_steps))) return rc;
+    FPM_CUDA(cudaStreamSynchronize(ctx->stream));
+    return FPM_OK;
+}
+
+int fpm_dist_hits(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* ref, const fpm_panel* qry, fpm_hit* out, uint64_t capacity, uint64_t* n_hits)
+{
+    if (!ctx) { set_error("ctx is NULL"); return FPM_ERR_ARG; }
+    if (!n_hits || (!out && capacity)) { set_error("NULL argument"); return FPM_ERR_ARG; }
+    int rc = check_dist(p, ref, qry);
+    if (rc) return rc;
+    *n_hits = 0;
+    if (ref->n == 0 || qry->n == 0) return FPM_OK;
+    FPM_CUDA(cudaSetDevice(ctx->device));
+    uint32_t mr = 0, mq = 0;
+    fpm_panel dr, dq;
+    if ((rc = upload_panels(ctx, ref, qry, &dr, &dq, &mr, &mq))) return rc;
+    // d_hits = counter | appended records | sorted records (dist_hits_run's own ensure() is then a no-op: the buffer only grows)
+    if ((rc = ctx->d_hits.ensure(2 * capacity * sizeof(fpm_hit) + 64))) return rc;
+    fpm_hit* d_sorted = reinterpret_cast<fpm_hit*>(ctx->d_hits.as<unsigned char>() + 32) + capacity;
+    if ((rc = dist_hits_run(ctx, p, &dr, &dq, mr, mq, d_sorted, capacity, n_hits, nullptr))) return rc;
+    if (*n_hits) FPM_CUDA(cudaMemcpyAsync(out, d_sorted, *n_hits * sizeof(fpm_hit), cudaMemcpyDeviceToHost, ctx->stream));
+    FPM_CUDA(cudaStreamSynchronize(ctx->stream));
+    return FPM_OK;
 }
 
 int fpm_fp_positional_tile(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* ref, const fpm_panel* qry, fpm_pair* out)

@@ -214,6 +214,48 @@ int dist_group_panels(fpm_ctx* ctx, uint64_t n_q, uint64_t n_r, uint64_t rows_q,
     return FPM_OK;
 }
 
+// ---- fpm_dist_hits: order the appended hits as the reference prints them (query-major, CommandDistance.cpp:303-333) ----
+__global__ void __launch_bounds__(256) hit_keys_kernel(const fpm_hit* __restrict__ hits, uint64_t n, uint64_t* __restrict__ keys, uint32_t* __restrict__ idx)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const uint2 qr = *reinterpret_cast<const uint2*>(hits + i);
+    keys[i] = ((uint64_t)qr.x << 32) | qr.y;
+    idx[i] = (uint32_t)i;
+}
+
+__global__ void __launch_bounds__(256) hit_gather_kernel(const fpm_hit* __restrict__ in, const uint32_t* __restrict__ idx, uint64_t n, fpm_hit* __restrict__ out)
+{
+    // two threads per 32-byte record, 16 bytes each
+    const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= 2 * n) return;
+    reinterpret_cast<uint4*>(out)[i] = reinterpret_cast<const uint4*>(in)[2ull * idx[i >> 1] + (i & 1)];
+}
+
+int dist_sort_hits(fpm_ctx* ctx, const fpm_hit* in, uint64_t n, fpm_hit* out)
+{
+    if (n == 0) return FPM_OK;
+    if (n >= 0xffffffffull) { set_error("more than 2^32 hits in one call"); return FPM_ERR_ARG; }
+    cudaStream_t st = ctx->stream;
+    size_t tmp = 0;
+    cub::DoubleBuffer<uint64_t> kb(nullptr, nullptr);
+    cub::DoubleBuffer<uint32_t> vb(nullptr, nullptr);
+    FPM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, kb, vb, (int64_t)n, 0, 64, st));
+    const size_t ak = (n * 8 + 255) & ~(size_t)255, av = (n * 4 + 255) & ~(size_t)255;
+    int rc;
+    if ((rc = ctx->d_hsort.ensure(2 * ak + 2 * av + tmp + 256))) return rc;
+    unsigned char* b = ctx->d_hsort.as<unsigned char>();
+    kb = cub::DoubleBuffer<uint64_t>((uint64_t*)b, (uint64_t*)(b + ak));
+    vb = cub::DoubleBuffer<uint32_t>((uint32_t*)(b + 2 * ak), (uint32_t*)(b + 2 * ak + av));
+    void* d_tmp = b + 2 * ak + 2 * av;
+    hit_keys_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, st>>>(in, n, kb.Current(), vb.Current());
+    FPM_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmp, kb, vb, (int64_t)n, 0, 64, st));
+    hit_gather_kernel<<<(uint32_t)((2 * n + 255) / 256), 256, 0, st>>>(in, vb.Current(), n, out);
+    ctx->launches += 3;
+    FPM_CUDA(cudaGetLastError());
+    return FPM_OK;
+}
+
 int dist_rank_panels(fpm_ctx* ctx, const fpm_panel* d_ref, const fpm_panel* d_qry, uint32_t max_size_ref, uint32_t max_size_qry,
                      uint64_t rows_r, uint64_t rows_q, uint32_t sketch_size, uint32_t** packed_ref, uint32_t** packed_qry, int* mode, uint32_t** marks)
 {

@@ -437,10 +437,37 @@ int CommandDistance::run() const
     dp.max_pvalue = pValueMax;
     dp.sorted_unique = fingerprint ? 0 : 1;   // fp lists are unsorted: the literal loop defines the result
 
+    // Filtered list output (-d / -v exclude some pairs, no table): only the passing pairs come back from the GPU, already
+    // in writeOutput's order (CommandDistance.cpp:303-333), from ONE call over all queries -- no n x n matrix anywhere.
+    const bool filtered = !table && ((distanceMax >= 0 && distanceMax < 1.) || (pValueMax >= 0 && pValueMax < 1.));
+    if (filtered && nRef && nQry) {
+        fpm_panel vr = pr.view(0, nRef), vq = pq.view(0, nQry);
+        vector<fpm_hit> hits(max<uint64_t>(1 << 16, 16 * (nRef + nQry)));
+        uint64_t nHits = 0;
+        int rc = fpm_dist_hits(gpuContext(), &dp, &vr, &vq, hits.data(), hits.size(), &nHits);
+        if (rc == FPM_ERR_CAPACITY) {
+            hits.resize(nHits);
+            rc = fpm_dist_hits(gpuContext(), &dp, &vr, &vq, hits.data(), hits.size(), &nHits);
+        }
+        if (rc != FPM_OK) {
+            cerr << "ERROR: " << fpm_last_error() << endl;
+            return 1;
+        }
+        for (uint64_t h = 0; h < nHits; h++) {
+            const fpm_hit& hit = hits[h];
+            const Sketch::Reference& rref = sketchRef.getReference(hit.ref);
+            const Sketch::Reference& qref = sketchQuery.getReference(hit.query);
+            cout << rref.name;
+            if (comment) cout << ':' << rref.comment;
+            cout << '\t' << qref.name;
+            if (comment) cout << ':' << qref.comment;
+            cout << '\t' << hit.distance << '\t' << hit.pvalue << '\t' << hit.numer << '/' << (hit.denom & 0x7fffffffu) << '\n';
+        }
+    }
     // query-major tiles of at most ~32M pairs (768 MB of results) per GPU call
     uint64_t rowsPerCall = nRef ? max<uint64_t>(1, (32ull << 20) / nRef) : 1;
     vector<fpm_pair> out;
-    for (uint64_t q0 = 0; q0 < nQry && nRef; q0 += rowsPerCall) {
+    for (uint64_t q0 = 0; q0 < nQry && nRef && !filtered; q0 += rowsPerCall) {
         uint64_t nq = min(rowsPerCall, nQry - q0);
         out.resize(nq * nRef);
         fpm_panel vr = pr.view(0, nRef), vq = pq.view(q0, nq);

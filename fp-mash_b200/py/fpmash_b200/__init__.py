@@ -108,6 +108,10 @@ lib.fpm_fasta_records.argtypes = [_VP, _VP]
 lib.fpm_fasta_sequence.argtypes = [_VP, _VP]
 lib.fpm_sketch_parsed.argtypes = [_VP, C.POINTER(SketchParams), _VP, C.c_uint32, _VP, _VP, _VP]
 FASTA_RECORD_DTYPE = np.dtype([("hdr_begin", "<u8"), ("hdr_end", "<u8"), ("seq_begin", "<u8")])
+lib.fpm_dist_hits.argtypes = [_VP, _VP, _VP, _VP, _VP, C.c_uint64, u64p]
+lib.fpm_dist_hits_dev.argtypes = [_VP, _VP, _VP, _VP, _VP, C.c_uint64, u64p, _VP]
+HIT_DTYPE = np.dtype([("query", "<u4"), ("ref", "<u4"), ("numer", "<u4"), ("denom", "<u4"), ("distance", "<f8"), ("pvalue", "<f8")])
+FPM_ERR_CAPACITY = -6
 lib.fpm_ctx_set_timing.argtypes = [_VP, C.c_int]
 lib.fpm_ctx_set_dist_mode.argtypes = [_VP, C.c_int]
 lib.fpm_ctx_get_timing.argtypes = [_VP, C.c_int, C.POINTER(C.c_double), u64p]
@@ -121,7 +125,7 @@ EXPORTED = ["fpm_abi_version", "fpm_device_count", "fpm_ctx_create", "fpm_ctx_de
             "fpm_fp_hash_batch", "fpm_cfl_fingerprint_batch", "fpm_fingerprint_batch", "fpm_dist_tile", "fpm_dist_tile_dev", "fpm_fp_positional_tile", "fpm_pvalue", "fpm_distance",
             "fpm_measure_int32_peak", "fpm_get_int32_peaks", "fpm_ctx_set_timing", "fpm_ctx_get_timing", "fpm_ctx_set_dist_mode",
             "fpm_fasta_parse", "fpm_fasta_records", "fpm_fasta_sequence", "fpm_sketch_parsed",
-            "fpm_fastq_stream_append", "fpm_fastq_line_ends"]
+            "fpm_fastq_stream_append", "fpm_fastq_line_ends", "fpm_dist_hits", "fpm_dist_hits_dev"]
 
 
 def _check(rc):
@@ -464,6 +468,42 @@ class Context:
         passed = (out["denom"] & FPM_PAIR_PASS) != 0
         out["denom"] &= 0x7fffffff
         return out, passed
+
+    def dist_hits(self, ref, qry, sketch_size, kmer_size, kmer_space, max_distance=1.0, max_pvalue=1.0, sorted_unique=True,
+                  capacity=None, out=None):
+        """`mash dist -d D -v P`: only the pairs that pass the filters, as HIT_DTYPE records sorted by (query, ref) (denom
+        without the pass flag).  The capacity is grown and the call repeated when more pairs pass than fit; `out` may be a
+        caller-owned (e.g. pinned) HIT_DTYPE array, which then fixes the capacity (FpmError FPM_ERR_CAPACITY if too small)."""
+        pr, keep_r = self._panel(*ref)
+        pq, keep_q = self._panel(*qry)
+        dp = DistParams(sketch_size, kmer_size, kmer_space, max_distance, max_pvalue, int(sorted_unique))
+        n = C.c_uint64(0)
+        if out is not None:
+            assert out.dtype == HIT_DTYPE and out.ndim == 1 and out.flags["C_CONTIGUOUS"]
+            _check(lib.fpm_dist_hits(self._h, C.byref(dp), C.byref(pr), C.byref(pq), out.ctypes.data, out.size, C.byref(n)))
+        else:
+            cap = int(capacity) if capacity is not None else max(1024, 8 * int(pq.n + pr.n))
+            while True:
+                out = np.zeros(cap, dtype=HIT_DTYPE)
+                rc = lib.fpm_dist_hits(self._h, C.byref(dp), C.byref(pr), C.byref(pq), out.ctypes.data, cap, C.byref(n))
+                if rc != FPM_ERR_CAPACITY:
+                    _check(rc)
+                    break
+                cap = int(n.value)
+        hits = out[:n.value]
+        hits["denom"] &= 0x7fffffff
+        return hits
+
+    def dist_hits_dev(self, ref_ptrs, qry_ptrs, sketch_size, kmer_size, kmer_space, d_out_ptr, capacity, d_steps_ptr=None,
+                      max_distance=1.0, max_pvalue=1.0, sorted_unique=True):
+        """Device panels in, sorted HIT_DTYPE records at d_out_ptr (room for `capacity`); returns the number of hits."""
+        pr = Panel(*ref_ptrs)
+        pq = Panel(*qry_ptrs)
+        dp = DistParams(sketch_size, kmer_size, kmer_space, max_distance, max_pvalue, int(sorted_unique))
+        n = C.c_uint64(0)
+        _check(lib.fpm_dist_hits_dev(self._h, C.byref(dp), C.byref(pr), C.byref(pq), _VP(d_out_ptr), int(capacity), C.byref(n),
+                                     _VP(d_steps_ptr) if d_steps_ptr else None))
+        return int(n.value)
 
     def fp_positional_tile(self, ref, qry, max_distance=1.0, max_pvalue=1.0):
         """compareFingerprints (mash triangle -fp): positional matches, chi-square p-value."""

@@ -225,6 +225,24 @@ int fpm_dist_tile(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* ref, 
 int fpm_dist_tile_dev(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* d_ref, const fpm_panel* d_qry,
                       fpm_pair* d_out, uint64_t* d_merge_steps /* nullable: += loop iterations */);
 
+/* The same comparison, but only the pairs that pass the -d / -v filters come back (what `mash dist -d D -v P`
+ * prints, CommandDistance.cpp:303-333 skips every other pair): records sorted by (query, ref), i.e. in the
+ * reference's output order.  No n x n result matrix exists anywhere: the tile kernel appends passing pairs to
+ * `out` directly, and when the filters exclude distance 1 (max_distance < 1 or max_pvalue < 1) pairs that share
+ * no hash are not even evaluated.  *n_hits = number of passing pairs; when it exceeds `capacity` the call
+ * returns FPM_ERR_CAPACITY, `out` holds nothing useful and the caller retries with room for *n_hits.          */
+typedef struct fpm_hit {
+    uint32_t query, ref;      /* indices into the two panels                                  */
+    uint32_t numer, denom;    /* as fpm_pair (denom carries FPM_PAIR_PASS)                    */
+    double distance;
+    double pvalue;
+} fpm_hit;
+#define FPM_ERR_CAPACITY (-6)
+int fpm_dist_hits(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* ref, const fpm_panel* qry, fpm_hit* out,
+                  uint64_t capacity, uint64_t* n_hits);
+int fpm_dist_hits_dev(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* d_ref, const fpm_panel* d_qry, fpm_hit* d_out,
+                      uint64_t capacity, uint64_t* n_hits, uint64_t* d_merge_steps /* nullable */);
+
 /* Replaces the fork's compareFingerprints (CommandTriangle.cpp:265-302, `mash triangle -fp`): positional
  * matches over the first min(|ref|,|qry|) hashes, distance = 1 - matches/min, p = chi-square(1 dof) upper
  * tail at `matches`.  Only max_distance / max_pvalue of *p are used.  Same output layout as fpm_dist_tile. */

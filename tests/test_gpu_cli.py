@@ -221,3 +221,28 @@ def test_parallel_parsing_keeps_submission_order(tmp_path):
     run(["sketch", "-i", "-o", "ind1"] + names, cwd=tmp_path)
     assert same_bytes(tmp_path / "ind1.msh", tmp_path / "ind4.msh")
     assert len(mshpy.load(tmp_path / "ind4.msh").refs) == sum(1 + i % 3 for i in range(23))
+
+
+def test_dist_filtered_output_is_the_filtered_full_output(tmp_path):
+    """`mash dist -d D -v P` (list output) takes the hits path -- one GPU call, only passing pairs come back; its rows must
+    be exactly the rows of the unfiltered run that satisfy the thresholds, in the same order (CommandDistance.cpp:303-333)."""
+    rng = np.random.default_rng(77)
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    roots = [lut[rng.integers(0, 4, size=30_000)] for _ in range(4)]
+    names = []
+    for i in range(36):
+        g = roots[i % 4].copy()
+        m = rng.random(g.size) < 0.002 * (1 + i // 4)
+        g[m] = lut[rng.integers(0, 4, size=int(m.sum()))]
+        names.append("g%02d.fa" % i)
+        with open(tmp_path / names[-1], "wb") as f:
+            f.write(b">g%d\n" % i + g.tobytes() + b"\n")
+    run(["sketch", "-s", "300", "-o", "all"] + names, cwd=tmp_path)
+    full = [l.split("\t") for l in run(["dist", "all.msh", "all.msh"], cwd=tmp_path).stdout.splitlines()]
+    assert len(full) == 36 * 36
+    for flags, keep in ((["-d", "0.02"], lambda r: float(r[2]) <= 0.02),
+                        (["-v", "1e-30"], lambda r: float(r[3]) <= 1e-30),
+                        (["-d", "0.05", "-v", "1e-10"], lambda r: float(r[2]) <= 0.05 and float(r[3]) <= 1e-10)):
+        got = [l.split("\t") for l in run(["dist"] + flags + ["all.msh", "all.msh"], cwd=tmp_path).stdout.splitlines()]
+        want = [r for r in full if keep(r)]
+        assert 36 <= len(want) < 36 * 36 and got == want, flags

@@ -260,3 +260,105 @@ def test_dist_device_path_grouped_equals_ungrouped(ctx):
             ctx.set_dist_mode()
     assert outs[0] == outs[1] == outs[2]
     assert outs[0] == np.ascontiguousarray(want).tobytes()
+
+
+# ---- fpm_dist_hits: only the pairs `mash dist -d D -v P` prints, in its output order ---------------------------------
+
+def _hits_from_matrix(mat_raw):
+    """What fpm_dist_hits must return, derived from the raw fpm_dist_tile matrix of the same call."""
+    q, r = np.nonzero((mat_raw["denom"] & 0x80000000) != 0)        # row-major: sorted by (query, ref)
+    sel = mat_raw[q, r]
+    return q, r, sel
+
+
+def _clustered_case(seed, n_r, n_q, s):
+    rng = np.random.default_rng(seed)
+    rh, rs = sorted_sketch_panel(rng, n_r, s, n_clusters=9, shared=0.6)
+    qh, qs = sorted_sketch_panel(rng, n_q, s, n_clusters=9, shared=0.6)
+    qh[:20] = rh[100:120]; qs[:20] = rs[100:120]
+    qh[30:35] = 0; qs[30:35] = 0
+    rl = rng.integers(1000, 6_000_000, size=n_r).astype(np.uint64)
+    ql = rng.integers(1000, 6_000_000, size=n_q).astype(np.uint64)
+    return (rh, rs, rl), (qh, qs, ql)
+
+
+@pytest.mark.parametrize("max_d,max_p", [(0.1, 1.0), (1.0, 1e-10), (0.05, 1e-3), (1.0, 1.0), (0.0, 1.0)])
+def test_dist_hits_equal_the_passing_pairs_of_the_matrix(dctx, max_d, max_p):
+    s = 400
+    ref, qry = _clustered_case(21, 300, 131, s)
+    mat, _ = dctx.dist_tile(ref, qry, s, 21, 4.0 ** 21, max_distance=max_d, max_pvalue=max_p, raw=True)
+    q, r, sel = _hits_from_matrix(mat)
+    hits = dctx.dist_hits(ref, qry, s, 21, 4.0 ** 21, max_distance=max_d, max_pvalue=max_p, capacity=7)   # forces the retry
+    assert len(hits) == len(q)
+    if max_d == 1.0 and max_p == 1.0:
+        assert len(hits) == 300 * 131                                 # no filter: every pair, unmarked ones included
+    assert np.array_equal(hits["query"], q) and np.array_equal(hits["ref"], r)
+    assert np.array_equal(hits["numer"], sel["numer"]) and np.array_equal(hits["denom"], sel["denom"] & 0x7fffffff)
+    assert hits["distance"].tobytes() == sel["distance"].tobytes() and hits["pvalue"].tobytes() == sel["pvalue"].tobytes()
+
+
+def test_dist_hits_against_the_oracle(ctx, oracle):
+    s = 200
+    ref, qry = _clustered_case(5, 40, 23, s)
+    hits = ctx.dist_hits(ref, qry, s, 21, 4.0 ** 21, max_distance=0.2, max_pvalue=1e-5)
+    want = _oracle_matrix(oracle, ref, qry, s, 21, 4.0 ** 21, 0.2, 1e-5)
+    exp = [(q, r, w) for q, row in enumerate(want) for r, w in enumerate(row) if w["passed"]]
+    assert len(exp) > 20 and len(hits) == len(exp)
+    for h, (q, r, w) in zip(hits, exp):
+        assert (int(h["query"]), int(h["ref"]), int(h["numer"]), int(h["denom"])) == (q, r, w["numer"], w["denom"])
+        assert h["distance"] == pytest.approx(w["distance"], rel=RTOL, abs=0)
+        assert h["pvalue"] == pytest.approx(w["pvalue"], rel=RTOL, abs=1e-300)
+
+
+def test_dist_hits_literal_path_and_capacity_error(ctx):
+    import fpmash_b200 as fpm
+    rng = np.random.default_rng(8)
+    n_r, n_q, s = 50, 31, 64
+    rh = rng.integers(0, 300, size=(n_r, s)).astype(np.uint64)        # unsorted, repeating: fp-mode lists
+    qh = rng.integers(0, 300, size=(n_q, s)).astype(np.uint64)
+    rs = np.full(n_r, s, dtype=np.uint32); qs = np.full(n_q, s, dtype=np.uint32)
+    rl = np.full(n_r, 5000, dtype=np.uint64); ql = np.full(n_q, 5000, dtype=np.uint64)
+    mat, _ = ctx.dist_tile((rh, rs, rl), (qh, qs, ql), s, 21, 4.0 ** 21, max_distance=0.3, sorted_unique=False, raw=True)
+    q, r, sel = _hits_from_matrix(mat)
+    hits = ctx.dist_hits((rh, rs, rl), (qh, qs, ql), s, 21, 4.0 ** 21, max_distance=0.3, sorted_unique=False)
+    assert len(q) > 0 and np.array_equal(hits["query"], q) and np.array_equal(hits["ref"], r)
+    assert hits["distance"].tobytes() == sel["distance"].tobytes()
+    small = np.zeros(max(1, len(q) // 2), dtype=fpm.HIT_DTYPE)
+    with pytest.raises(fpm.FpmError) as e:
+        ctx.dist_hits((rh, rs, rl), (qh, qs, ql), s, 21, 4.0 ** 21, max_distance=0.3, sorted_unique=False, out=small)
+    assert e.value.code == fpm.FPM_ERR_CAPACITY and str(len(q)) in str(e.value)
+    # nothing passes / empty panels
+    mat0, _ = ctx.dist_tile((rh, rs, rl), (qh, qs, ql), s, 21, 4.0 ** 21, max_distance=0.0, max_pvalue=0.0, sorted_unique=False, raw=True)
+    none = ctx.dist_hits((rh, rs, rl), (qh, qs, ql), s, 21, 4.0 ** 21, max_distance=0.0, max_pvalue=0.0, sorted_unique=False)
+    assert len(none) == len(_hits_from_matrix(mat0)[0]) == 0
+    empty = ctx.dist_hits((rh[:0], rs[:0], rl[:0]), (qh, qs, ql), s, 21, 4.0 ** 21, max_distance=0.3)
+    assert len(empty) == 0
+
+
+def test_dist_hits_device_entry_point(ctx):
+    torch = pytest.importorskip("torch")
+    import fpmash_b200 as fpm
+    s = 500
+    ref, qry = _clustered_case(33, 700, 333, s)
+    (rh, rs, rl), (qh, qs, ql) = ref, qry
+    mat, _ = ctx.dist_tile(ref, qry, s, 21, 4.0 ** 21, max_distance=0.15, raw=True)
+    q, r, sel = _hits_from_matrix(mat)
+    dev = torch.device("cuda", 0)
+    t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a).view(dt)).to(dev)
+    d_rh, d_rs, d_rl = t(rh, np.int64), t(rs.astype(np.uint32), np.int32), t(rl, np.int64)
+    d_qh, d_qs, d_ql = t(qh, np.int64), t(qs.astype(np.uint32), np.int32), t(ql, np.int64)
+    cap = len(q) + 5
+    steps = torch.zeros(1, dtype=torch.int64, device=dev)
+    for kw in (dict(), dict(no_group=True), dict(no_prune=True)):
+        ctx.set_dist_mode(**kw)
+        try:
+            out = torch.zeros(cap * 32, dtype=torch.uint8, device=dev)
+            n = ctx.dist_hits_dev((d_rh.data_ptr(), d_rs.data_ptr(), d_rl.data_ptr(), 700, s), (d_qh.data_ptr(), d_qs.data_ptr(), d_ql.data_ptr(), 333, s),
+                                  s, 21, 4.0 ** 21, out.data_ptr(), cap, d_steps_ptr=steps.data_ptr(), max_distance=0.15)
+        finally:
+            ctx.set_dist_mode()
+        hits = out.cpu().numpy().view(fpm.HIT_DTYPE)[:n]
+        assert n == len(q) and np.array_equal(hits["query"], q) and np.array_equal(hits["ref"], r)
+        assert np.array_equal(hits["numer"], sel["numer"]) and hits["distance"].tobytes() == sel["distance"].tobytes()
+        assert hits["pvalue"].tobytes() == sel["pvalue"].tobytes()
+    assert int(steps.item()) > 0
