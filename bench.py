@@ -433,6 +433,29 @@ def main():
             dt = time.perf_counter() - t0
             dist_obj["e2e"] = {"value": qs * nd / dt, "unit": "pairs/s", "sample": "%d query rows x %d refs, one GPU" % (qs, nd),
                                "h2d_bytes_per_step": int((nd + qs) * (S * 8 + 12)), "d2h_bytes_per_step": int(qs * nd * 24)}
+            # the same through `mash dist -d 0.25` semantics: every pair of the full all-vs-all is decided on the GPU, only the
+            # passing ones come back (fpm_dist_hits) -- host panels in, sorted hit records out
+            cap = 64 << 20
+            hit_buf = torch.empty(cap * 32, dtype=torch.uint8, pin_memory=True).numpy().view(fpm.HIT_DTYPE)
+            try:
+                php = panel.cpu().pin_memory().numpy().view(np.uint64)     # pinned host panels, as a caller that cares would hold them
+                ctx.dist_hits((php, hs, hl), (php, hs, hl), S, K, kspace, max_distance=0.25, out=hit_buf, raw=True)
+                ctx.set_timing(True)
+                t0 = time.perf_counter()
+                hits = ctx.dist_hits((php, hs, hl), (php, hs, hl), S, K, kspace, max_distance=0.25, out=hit_buf, raw=True)
+                dt = time.perf_counter() - t0
+                f_tile, f_pack = ctx.get_timing(fpm.KERNEL_DIST_TILE)[0], ctx.get_timing(fpm.KERNEL_DIST_PACK)[0]
+                ctx.set_timing(False)
+                sub = hits[hits["query"] < qs]
+                same = bool(np.array_equal(np.nonzero(got["distance"] <= 0.25)[1], sub["ref"]) and
+                            np.array_equal(got["numer"][got["distance"] <= 0.25], sub["numer"]))
+                dist_obj["e2e_filtered"] = {"value": nd * nd / dt, "unit": "pairs/s", "filter": "-d 0.25", "hits": int(len(hits)), "seconds": dt,
+                                            "kernel_ms": {"dist_tile32": f_tile, "rank_compress_index_mark": f_pack},
+                                            "sample": "all %d x %d pairs, one GPU, one call" % (nd, nd), "h2d_bytes_per_step": int(2 * nd * (S * 8 + 12)),
+                                            "d2h_bytes_per_step": int(len(hits) * 32), "agrees_with_matrix_rows": same}
+            except fpm.FpmError as e:
+                dist_obj["e2e_filtered"] = {"error": str(e)}
+            del hit_buf
             if not args.no_cpu and world == 1:
                 from oracle_py import RefLib
                 if RefLib.available():

@@ -465,13 +465,18 @@ dist_tile32_kernel(const uint32_t* __restrict__ pref, const uint32_t* __restrict
     __shared__ uint32_t s_mask[32];
     __shared__ uint16_t s_list[1024];
     __shared__ uint32_t s_npairs;
+    __shared__ uint32_t s_empty[2];          // bit c: query / reference c of the tile is an empty sketch
     __shared__ uint32_t s_orig[64];          // original sketch index of my 32 queries / 32 references (panels may be grouped, dist_rank.cu)
     if (t >= 64 && t < 128) {
         const int c = t - 64;
         const bool isq = c < 32;
         const uint64_t g = (isq ? q_tile2 : r_tile2) * 32 + (c & 31), n = isq ? n_qry : n_ref;
         const uint32_t* perm = isq ? perm_q : perm_r;
-        s_orig[c] = g < n ? (perm ? perm[g] : (uint32_t)g) : 0xffffffffu;
+        const uint32_t o = g < n ? (perm ? perm[g] : (uint32_t)g) : 0xffffffffu;
+        s_orig[c] = o;
+        // (threads 64..95 are one warp = the queries, 96..127 the references) which of them are empty sketches
+        const uint32_t em = __ballot_sync(0xffffffffu, o != 0xffffffffu && (isq ? size_qry : size_ref)[o] == 0);
+        if ((c & 31) == 0) s_empty[isq ? 0 : 1] = em;
     }
     if (t < 32) {
         const uint64_t qg = q_tile2 * 32 + t;
@@ -645,14 +650,17 @@ dist_tile32_kernel(const uint32_t* __restrict__ pref, const uint32_t* __restrict
     if (hs.buf) {
         // hits mode: nothing is written for a pair that fails the -d / -v filters
         fpm_pair o = {0, 0, 0., 0.};
-        if (!hs.skip_unmarked) {
+        // pairs without a shared hash have distance 1 -- except two EMPTY sketches (denom 0 = common: distance 0, dist_math.h),
+        // so even when the filters exclude distance 1 a tile holding empty sketches on both sides looks at those pairs
+        const uint32_t eq = s_empty[0], er = s_empty[1];
+        if (!hs.skip_unmarked || (eq && er)) {
             const uint32_t qo = s_orig[l], mk = s_mask[l];
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const int rc = h ? rc1 : rc0;
                 const uint32_t ro = s_orig[32 + rc];
                 bool pass = false;
-                if (qo != 0xffffffffu && ro != 0xffffffffu && !((mk >> rc) & 1u)) {
+                if (qo != 0xffffffffu && ro != 0xffffffffu && !((mk >> rc) & 1u) && (!hs.skip_unmarked || ((eq >> l) & (er >> rc) & 1u))) {
                     const uint64_t un = (uint64_t)size_qry[qo] + size_ref[ro];
                     finish_pair(a, 0, un < a.s ? un : a.s, len_ref[ro], len_qry[qo], &o);
                     pass = (o.denom & FPM_PAIR_PASS) != 0;
@@ -945,7 +953,7 @@ static int dist_hits_run(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel
     FPM_CUDA(cudaStreamSynchronize(st));
     *n_hits = n;
     if (n > capacity) { set_error("fpm_dist_hits: %llu pairs pass the filters, room for %llu", n, (unsigned long long)capacity); return FPM_ERR_CAPACITY; }
-    return dist_sort_hits(ctx, hs.buf, n, d_sorted);
+    return dist_sort_hits(ctx, hs.buf, n, d_qry->n, d_ref->n, d_sorted);
 }
 
 int fpm_dist_tile(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* ref, const fpm_panel* qry, fpm_pair* out)

@@ -96,7 +96,8 @@ __global__ void __launch_bounds__(256) dist_post_count_kernel(const uint64_t* __
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(total, c);
 }
 
-// one CTA per query sketch: bit r of its row = reference r shares a hash with it
+// one CTA per query sketch: bit r of its row = reference r shares a hash with it.  (Giving equal posting lists one identity
+// and walking each distinct list once per query was tried: lists of independently mutated relatives are all different.)
 __global__ void __launch_bounds__(256) dist_mark_kernel(const uint32_t* __restrict__ p32q, uint64_t rows_q, const uint32_t* __restrict__ sizes_q,
                                                         const uint32_t* __restrict__ run_ref_start, const uint32_t* __restrict__ post, uint32_t words,
                                                         uint32_t* __restrict__ marks)
@@ -161,19 +162,23 @@ __global__ void __launch_bounds__(256) dist_repack_kernel(const uint32_t* __rest
     dst[idx] = v;
 }
 
+// one CTA per output row: the source row sits in shared memory, a warp builds one output word per ballot
 __global__ void __launch_bounds__(256) dist_marks_permute_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, const uint32_t* __restrict__ perm_q,
                                                                  const uint32_t* __restrict__ perm_r, uint32_t n_q, uint32_t n_r, uint32_t words)
 {
-    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (uint64_t)n_q * words) return;
-    const uint32_t q2 = (uint32_t)(idx / words), w2 = (uint32_t)(idx % words);
+    extern __shared__ uint32_t s_row[];
+    const uint32_t q2 = blockIdx.x;
     const uint32_t* row = src + (uint64_t)perm_q[q2] * words;
-    uint32_t out = 0;
-    for (uint32_t b = 0; b < 32 && w2 * 32 + b < n_r; b++) {
-        const uint32_t r = perm_r[w2 * 32 + b];
-        out |= ((row[r >> 5] >> (r & 31)) & 1u) << b;
+    for (uint32_t w = threadIdx.x; w < words; w += blockDim.x) s_row[w] = row[w];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    for (uint32_t w2 = threadIdx.x >> 5; w2 < words; w2 += blockDim.x >> 5) {
+        const uint32_t i = w2 * 32 + lane;
+        bool bit = false;
+        if (i < n_r) { const uint32_t r = perm_r[i]; bit = (s_row[r >> 5] >> (r & 31)) & 1u; }
+        const uint32_t out = __ballot_sync(0xffffffffu, bit);
+        if (lane == 0) dst[(uint64_t)q2 * words + w2] = out;
     }
-    dst[idx] = out;
 }
 
 int dist_group_panels(fpm_ctx* ctx, uint64_t n_q, uint64_t n_r, uint64_t rows_q, uint64_t rows_r, uint32_t** p32r, uint32_t** p32q, uint32_t** marks,
@@ -207,7 +212,8 @@ int dist_group_panels(fpm_ctx* ctx, uint64_t n_q, uint64_t n_r, uint64_t rows_q,
     FPM_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_r, key_r, key_r2, idx_r, pr_out, (int64_t)n_r, 0, 32, st));
     dist_repack_kernel<<<(uint32_t)((pr + 255) / 256), 256, 0, st>>>(*p32r, packed2, pr_out, n_r, rows_r);
     dist_repack_kernel<<<(uint32_t)((pq + 255) / 256), 256, 0, st>>>(*p32q, packed2 + pr, pq_out, n_q, rows_q);
-    dist_marks_permute_kernel<<<(uint32_t)(((uint64_t)n_q * words + 255) / 256), 256, 0, st>>>(*marks, marks2, pq_out, pr_out, (uint32_t)n_q, (uint32_t)n_r, words);
+    FPM_CUDA(cudaFuncSetAttribute(dist_marks_permute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(words * 4)));
+    dist_marks_permute_kernel<<<(uint32_t)n_q, 256, words * 4, st>>>(*marks, marks2, pq_out, pr_out, (uint32_t)n_q, (uint32_t)n_r, words);
     ctx->launches += 8;
     FPM_CUDA(cudaGetLastError());
     *p32r = packed2; *p32q = packed2 + pr; *marks = marks2; *perm_q = pq_out; *perm_r = pr_out;
@@ -215,12 +221,12 @@ int dist_group_panels(fpm_ctx* ctx, uint64_t n_q, uint64_t n_r, uint64_t rows_q,
 }
 
 // ---- fpm_dist_hits: order the appended hits as the reference prints them (query-major, CommandDistance.cpp:303-333) ----
-__global__ void __launch_bounds__(256) hit_keys_kernel(const fpm_hit* __restrict__ hits, uint64_t n, uint64_t* __restrict__ keys, uint32_t* __restrict__ idx)
+__global__ void __launch_bounds__(256) hit_keys_kernel(const fpm_hit* __restrict__ hits, uint64_t n, uint64_t n_ref, uint64_t* __restrict__ keys, uint32_t* __restrict__ idx)
 {
     const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;
     const uint2 qr = *reinterpret_cast<const uint2*>(hits + i);
-    keys[i] = ((uint64_t)qr.x << 32) | qr.y;
+    keys[i] = (uint64_t)qr.x * n_ref + qr.y;          // the pair's position in the reference's output order
     idx[i] = (uint32_t)i;
 }
 
@@ -232,15 +238,18 @@ __global__ void __launch_bounds__(256) hit_gather_kernel(const fpm_hit* __restri
     reinterpret_cast<uint4*>(out)[i] = reinterpret_cast<const uint4*>(in)[2ull * idx[i >> 1] + (i & 1)];
 }
 
-int dist_sort_hits(fpm_ctx* ctx, const fpm_hit* in, uint64_t n, fpm_hit* out)
+int dist_sort_hits(fpm_ctx* ctx, const fpm_hit* in, uint64_t n, uint64_t n_qry, uint64_t n_ref, fpm_hit* out)
 {
+    int bits = 1;
+    while (bits < 64 && ((n_qry * n_ref - 1) >> bits)) bits++;   // radix passes only over the bits a pair index can have
+
     if (n == 0) return FPM_OK;
     if (n >= 0xffffffffull) { set_error("more than 2^32 hits in one call"); return FPM_ERR_ARG; }
     cudaStream_t st = ctx->stream;
     size_t tmp = 0;
     cub::DoubleBuffer<uint64_t> kb(nullptr, nullptr);
     cub::DoubleBuffer<uint32_t> vb(nullptr, nullptr);
-    FPM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, kb, vb, (int64_t)n, 0, 64, st));
+    FPM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, kb, vb, (int64_t)n, 0, bits, st));
     const size_t ak = (n * 8 + 255) & ~(size_t)255, av = (n * 4 + 255) & ~(size_t)255;
     int rc;
     if ((rc = ctx->d_hsort.ensure(2 * ak + 2 * av + tmp + 256))) return rc;
@@ -248,8 +257,8 @@ int dist_sort_hits(fpm_ctx* ctx, const fpm_hit* in, uint64_t n, fpm_hit* out)
     kb = cub::DoubleBuffer<uint64_t>((uint64_t*)b, (uint64_t*)(b + ak));
     vb = cub::DoubleBuffer<uint32_t>((uint32_t*)(b + 2 * ak), (uint32_t*)(b + 2 * ak + av));
     void* d_tmp = b + 2 * ak + 2 * av;
-    hit_keys_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, st>>>(in, n, kb.Current(), vb.Current());
-    FPM_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmp, kb, vb, (int64_t)n, 0, 64, st));
+    hit_keys_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, st>>>(in, n, n_ref, kb.Current(), vb.Current());
+    FPM_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmp, kb, vb, (int64_t)n, 0, bits, st));
     hit_gather_kernel<<<(uint32_t)((2 * n + 255) / 256), 256, 0, st>>>(in, vb.Current(), n, out);
     ctx->launches += 3;
     FPM_CUDA(cudaGetLastError());

@@ -19,6 +19,6 @@ int dist_group_panels(fpm_ctx* ctx, uint64_t n_q, uint64_t n_r, uint64_t rows_q,
                       uint32_t** perm_q, uint32_t** perm_r);
 
 // fpm_dist_hits: `n` hits appended in arbitrary order at `in` -> `out` sorted by (query, ref).  in != out.
-int dist_sort_hits(fpm_ctx* ctx, const fpm_hit* in, uint64_t n, fpm_hit* out);
+int dist_sort_hits(fpm_ctx* ctx, const fpm_hit* in, uint64_t n, uint64_t n_qry, uint64_t n_ref, fpm_hit* out);
 
 }  // namespace fpm

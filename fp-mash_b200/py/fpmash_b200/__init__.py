@@ -470,7 +470,7 @@ class Context:
         return out, passed
 
     def dist_hits(self, ref, qry, sketch_size, kmer_size, kmer_space, max_distance=1.0, max_pvalue=1.0, sorted_unique=True,
-                  capacity=None, out=None):
+                  capacity=None, out=None, raw=False):
         """`mash dist -d D -v P`: only the pairs that pass the filters, as HIT_DTYPE records sorted by (query, ref) (denom
         without the pass flag).  The capacity is grown and the call repeated when more pairs pass than fit; `out` may be a
         caller-owned (e.g. pinned) HIT_DTYPE array, which then fixes the capacity (FpmError FPM_ERR_CAPACITY if too small)."""
@@ -491,7 +491,8 @@ class Context:
                     break
                 cap = int(n.value)
         hits = out[:n.value]
-        hits["denom"] &= 0x7fffffff
+        if not raw:   # raw: the records exactly as the C ABI wrote them (every hit carries the pass flag in bit 31 of denom)
+            hits["denom"] &= 0x7fffffff
         return hits
 
     def dist_hits_dev(self, ref_ptrs, qry_ptrs, sketch_size, kmer_size, kmer_space, d_out_ptr, capacity, d_steps_ptr=None,

@@ -64,8 +64,8 @@ def test_dist_thresholds_and_sketch_size_mismatch(dctx, oracle):
     rl = np.full(40, 4_600_000, dtype=np.uint64)
     ql = np.full(24, 5_100_000, dtype=np.uint64)
     # compare at s=400 although the lists hold up to 1000 hashes (CommandDistance.cpp:342-344)
-    got, passed = dctx.dist_tile((rh, rs, rl), (qh, qs, ql), 400, 21, 4.0 ** 21, max_distance=0.2, max_pvalue=1e-5)
-    _compare(got, passed, _oracle_matrix(oracle, (rh, rs, rl), (qh, qs, ql), 400, 21, 4.0 ** 21, 0.2, 1e-5))
+    got, passed = dctx.dist_tile((rh, rs, rl), (qh, qs, ql), 400, 21, 4.0 ** 21, max_distance=0.06, max_pvalue=1e-3)
+    _compare(got, passed, _oracle_matrix(oracle, (rh, rs, rl), (qh, qs, ql), 400, 21, 4.0 ** 21, 0.06, 1e-3))
 
 
 def test_dist_heterogeneous_densities_multi_phase(dctx, oracle):
@@ -273,10 +273,12 @@ def _hits_from_matrix(mat_raw):
 
 def _clustered_case(seed, n_r, n_q, s):
     rng = np.random.default_rng(seed)
-    rh, rs = sorted_sketch_panel(rng, n_r, s, n_clusters=9, shared=0.6)
-    qh, qs = sorted_sketch_panel(rng, n_q, s, n_clusters=9, shared=0.6)
-    qh[:20] = rh[100:120]; qs[:20] = rs[100:120]
-    qh[30:35] = 0; qs[30:35] = 0
+    h, sz = sorted_sketch_panel(rng, n_r + n_q, s, n_clusters=9, shared=0.6)     # one family tree, split into the two panels
+    rh, rs, qh, qs = h[:n_r].copy(), sz[:n_r].copy(), h[n_r:].copy(), sz[n_r:].copy()
+    c = min(n_q, n_r) // 4
+    qh[:c] = rh[c:2 * c]; qs[:c] = rs[c:2 * c]                    # identical pairs
+    qh[c + 2:c + 5] = 0; qs[c + 2:c + 5] = 0                        # empty query sketches
+    rh[1] = 0; rs[1] = 0; rh[n_r - 1] = 0; rs[n_r - 1] = 0          # and empty references: empty x empty has distance 0 without sharing a hash
     rl = rng.integers(1000, 6_000_000, size=n_r).astype(np.uint64)
     ql = rng.integers(1000, 6_000_000, size=n_q).astype(np.uint64)
     return (rh, rs, rl), (qh, qs, ql)
@@ -300,10 +302,10 @@ def test_dist_hits_equal_the_passing_pairs_of_the_matrix(dctx, max_d, max_p):
 def test_dist_hits_against_the_oracle(ctx, oracle):
     s = 200
     ref, qry = _clustered_case(5, 40, 23, s)
-    hits = ctx.dist_hits(ref, qry, s, 21, 4.0 ** 21, max_distance=0.2, max_pvalue=1e-5)
-    want = _oracle_matrix(oracle, ref, qry, s, 21, 4.0 ** 21, 0.2, 1e-5)
+    hits = ctx.dist_hits(ref, qry, s, 21, 4.0 ** 21, max_distance=0.06, max_pvalue=1e-3)
+    want = _oracle_matrix(oracle, ref, qry, s, 21, 4.0 ** 21, 0.06, 1e-3)
     exp = [(q, r, w) for q, row in enumerate(want) for r, w in enumerate(row) if w["passed"]]
-    assert len(exp) > 20 and len(hits) == len(exp)
+    assert 20 < len(exp) < 23 * 40 and len(hits) == len(exp)
     for h, (q, r, w) in zip(hits, exp):
         assert (int(h["query"]), int(h["ref"]), int(h["numer"]), int(h["denom"])) == (q, r, w["numer"], w["denom"])
         assert h["distance"] == pytest.approx(w["distance"], rel=RTOL, abs=0)
