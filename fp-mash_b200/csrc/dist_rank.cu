@@ -97,7 +97,8 @@ __global__ void __launch_bounds__(256) dist_post_count_kernel(const uint64_t* __
 }
 
 // one CTA per query sketch: bit r of its row = reference r shares a hash with it.  (Giving equal posting lists one identity
-// and walking each distinct list once per query was tried: lists of independently mutated relatives are all different.)
+// and walking each distinct list once per query was tried: lists of independently mutated relatives are all different.
+// Testing the bit with a plain load before the atomic was tried too: 0.7 ms slower.)
 __global__ void __launch_bounds__(256) dist_mark_kernel(const uint32_t* __restrict__ p32q, uint64_t rows_q, const uint32_t* __restrict__ sizes_q,
                                                         const uint32_t* __restrict__ run_ref_start, const uint32_t* __restrict__ post, uint32_t words,
                                                         uint32_t* __restrict__ marks)
