@@ -93,30 +93,115 @@ __global__ void __launch_bounds__(256) dist_post_count_kernel(const uint64_t* __
     unsigned long long c = 0;
     if (i < m && keys[i] != ~0ULL && dst[i] >= pr) c = run_ref_start[rank[i] + 1] - run_ref_start[rank[i]];
     for (int o = 16; o; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
-    if ((threadIdx.x & 31) == 0 && c) atomicAdd(total, c);
+    // one atomic per CTA: a million same-address atomics (one per warp) cost 0.6 ms
+    __shared__ unsigned long long s_part[8];
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int w = 0; w < 8; w++) t += s_part[w];
+        if (t) atomicAdd(total, t);
+    }
 }
 
-// one CTA per query sketch: bit r of its row = reference r shares a hash with it.  (Giving equal posting lists one identity
-// and walking each distinct list once per query was tried: lists of independently mutated relatives are all different.
-// Testing the bit with a plain load before the atomic was tried too: 0.7 ms slower.)
+// Saturation.  Relatives repeat each other's postings: a query from a family of 1000 mutually related genomes walks
+// ~600 posting lists of ~600 references each to set the same 1000 bits.  The walk may stop as soon as every reference
+// the query can possibly reach is marked, and that set is known cheaply: sketches (references and queries as nodes of one
+// graph) that hold a common hash are connected, so all references of all the query's posting lists lie in the query's
+// CONNECTED COMPONENT.  A lock-free union-find over neighbours in the sorted hash array gives the components and their
+// reference counts in one pass over the array; the marking pass stops a query once it has set that many bits.  Exact
+// (a stopped walk could not have set another bit); a query in a huge sparse component simply never stops early.
+// Parents only ever decrease (a root is hooked under a smaller node, halving moves to a grandparent), so ANY value a
+// parent entry held at some time is an ancestor-or-self: finds may read through L1 (FRESH = false; millions of threads
+// read the same few roots, and going to L2 for each of those reads was 2 ms) and only need current data when a hook failed.
+template <bool FRESH>
+__device__ __forceinline__ uint32_t uf_find(uint32_t* __restrict__ parent, uint32_t x)
+{
+    for (;;) {
+        const uint32_t p = FRESH ? reinterpret_cast<volatile uint32_t*>(parent)[x] : __ldca(parent + x);
+        if (p == x) return x;
+        const uint32_t g = FRESH ? reinterpret_cast<volatile uint32_t*>(parent)[p] : __ldca(parent + p);
+        if (g != p) parent[x] = g;                                        // path halving
+        x = p;
+    }
+}
+
+__global__ void __launch_bounds__(256) dist_uf_init_kernel(uint32_t* __restrict__ parent, uint32_t* __restrict__ ref_count, uint32_t n)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { parent[i] = i; ref_count[i] = 0; }
+}
+
+// node of a tile-layout destination: references 0..n_r-1, queries n_r..n_r+n_q-1
+__device__ __forceinline__ uint32_t uf_node(uint32_t d, uint32_t pr, uint32_t rows_r, uint32_t rows_q, uint32_t n_r)
+{
+    if (d < pr) return ((d >> 4) / rows_r) * 16 + (d & 15);
+    d -= pr;
+    return n_r + ((d >> 4) / rows_q) * 16 + (d & 15);
+}
+
+__global__ void __launch_bounds__(256) dist_uf_union_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ dst, uint64_t m, uint32_t pr,
+                                                            uint32_t rows_r, uint32_t rows_q, uint32_t n_r, uint32_t* __restrict__ parent)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x + 1;
+    if (i >= m) return;
+    const uint64_t k = keys[i];
+    if (k == ~0ULL || keys[i - 1] != k) return;
+    uint32_t a = uf_node(dst[i], pr, rows_r, rows_q, n_r), b = uf_node(dst[i - 1], pr, rows_r, rows_q, n_r);
+    a = uf_find<false>(parent, a);
+    b = uf_find<false>(parent, b);
+    for (;;) {                                                             // hook the larger root under the smaller node
+        if (a == b) return;
+        if (a < b) { const uint32_t t = a; a = b; b = t; }
+        if (atomicCAS(&parent[a], a, b) == a) return;
+        a = uf_find<true>(parent, a);
+        b = uf_find<true>(parent, b);
+    }
+}
+
+// parent[x] = root for every node; ref_count[root] = references in the component
+__global__ void __launch_bounds__(256) dist_uf_flatten_kernel(uint32_t* __restrict__ parent, uint32_t* __restrict__ ref_count, uint32_t n_r, uint32_t n)
+{
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= n) return;
+    const uint32_t r = uf_find<true>(parent, x);
+    if (x < n_r) atomicAdd(&ref_count[r], 1u);
+    if (x >= n_r) parent[x] = r;            // only the queries' entries are read afterwards; references keep valid ancestors for concurrent finds
+}
+
+// one CTA per query sketch: bit r of its row = reference r shares a hash with it.  (Also tried: one identity for equal posting
+// lists, each distinct list walked once per query -- lists of independently mutated relatives are all different; and testing
+// the bit with a plain load before the atomic -- 0.7 ms slower.)
 __global__ void __launch_bounds__(256) dist_mark_kernel(const uint32_t* __restrict__ p32q, uint64_t rows_q, const uint32_t* __restrict__ sizes_q,
                                                         const uint32_t* __restrict__ run_ref_start, const uint32_t* __restrict__ post, uint32_t words,
+                                                        const uint32_t* __restrict__ parent, const uint32_t* __restrict__ ref_count, uint32_t n_r,
                                                         uint32_t* __restrict__ marks)
 {
     extern __shared__ uint32_t s_bits[];
+    __shared__ uint32_t s_count;
     const uint32_t q = blockIdx.x;
     for (uint32_t w = threadIdx.x; w < words; w += blockDim.x) s_bits[w] = 0;
+    if (threadIdx.x == 0) s_count = 0;
     __syncthreads();
     const uint32_t n = sizes_q[q];
+    const uint32_t target = parent ? ref_count[parent[n_r + q]] : 0xffffffffu;   // references this query can reach at all
     const uint32_t* col = p32q + ((uint64_t)(q >> 4) * rows_q) * 16 + (q & 15);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     for (uint32_t e = wid; e < n; e += nw) {                              // a warp per element, lanes over its postings
+        if (*reinterpret_cast<volatile uint32_t*>(&s_count) >= target) break;
         const uint32_t r = col[(uint64_t)e * 16];
         const uint32_t lo = run_ref_start[r], hi = run_ref_start[r + 1];
-        for (uint32_t j = lo + lane; j < hi; j += 32) {
-            const uint32_t sk = post[j];
-            atomicOr(&s_bits[sk >> 5], 1u << (sk & 31));
+        uint32_t fresh = 0;
+        for (uint32_t j0 = lo; j0 < hi; j0 += 32) {
+            const uint32_t j = j0 + lane;
+            bool isnew = false;
+            if (j < hi) {
+                const uint32_t sk = post[j], bit = 1u << (sk & 31);
+                isnew = !(atomicOr(&s_bits[sk >> 5], bit) & bit);
+            }
+            fresh += __popc(__ballot_sync(0xffffffffu, isnew));
         }
+        if (lane == 0 && fresh) atomicAdd(&s_count, fresh);
     }
     __syncthreads();
     for (uint32_t w = threadIdx.x; w < words; w += blockDim.x) marks[(uint64_t)q * words + w] = s_bits[w];
@@ -353,10 +438,20 @@ int dist_rank_panels(fpm_ctx* ctx, const fpm_panel* d_ref, const fpm_panel* d_qr
         // one shared-memory atomic, a pair's merge up to sketch_size steps
         const double postings = (double)h2[1], full = (double)d_ref->n * (double)d_qry->n * (double)std::max<uint32_t>(sketch_size, 1);
         if (postings <= 0.05 * full && (size_t)words * 4 <= 200 * 1024) {
-            if ((rc = ctx->d_marks.ensure((size_t)d_qry->n * words * 4 + 64))) return rc;
+            // marks [n_q][words] | union-find parents [n_r + n_q] | references per component [n_r + n_q]
+            const size_t a_marks = ((size_t)d_qry->n * words * 4 + 255) & ~(size_t)255;
+            const uint32_t nodes = (uint32_t)(d_ref->n + d_qry->n);
+            const size_t a_nodes = ((size_t)nodes * 4 + 255) & ~(size_t)255;
+            if ((rc = ctx->d_marks.ensure(a_marks + 2 * a_nodes + 64))) return rc;
+            uint32_t* parent = (uint32_t*)(ctx->d_marks.as<unsigned char>() + a_marks);
+            uint32_t* ref_count = (uint32_t*)(ctx->d_marks.as<unsigned char>() + a_marks + a_nodes);
+            dist_uf_init_kernel<<<(nodes + 255) / 256, 256, 0, st>>>(parent, ref_count, nodes);
+            dist_uf_union_kernel<<<(uint32_t)((m + 255) / 256), 256, 0, st>>>(ks, vb.Current(), m, (uint32_t)pr, (uint32_t)rows_r, (uint32_t)rows_q, (uint32_t)d_ref->n, parent);
+            dist_uf_flatten_kernel<<<(nodes + 255) / 256, 256, 0, st>>>(parent, ref_count, (uint32_t)d_ref->n, nodes);
             FPM_CUDA(cudaFuncSetAttribute(dist_mark_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(words * 4)));
-            dist_mark_kernel<<<(uint32_t)d_qry->n, 256, words * 4, st>>>(*packed_qry, rows_q, d_qry->sizes, run_ref_start, post, words, ctx->d_marks.as<uint32_t>());
-            ctx->launches++;
+            dist_mark_kernel<<<(uint32_t)d_qry->n, 256, words * 4, st>>>(*packed_qry, rows_q, d_qry->sizes, run_ref_start, post, words, parent, ref_count,
+                                                                         (uint32_t)d_ref->n, ctx->d_marks.as<uint32_t>());
+            ctx->launches += 4;
             FPM_CUDA(cudaGetLastError());
             *marks = ctx->d_marks.as<uint32_t>();
         }

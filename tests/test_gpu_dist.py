@@ -364,3 +364,26 @@ def test_dist_hits_device_entry_point(ctx):
         assert np.array_equal(hits["numer"], sel["numer"]) and hits["distance"].tobytes() == sel["distance"].tobytes()
         assert hits["pvalue"].tobytes() == sel["pvalue"].tobytes()
     assert int(steps.item()) > 0
+
+
+def test_dist_pruning_chained_components(ctx, oracle):
+    """The marking pass stops a query once it has marked as many references as its connected component holds.  Chains
+    (q shares with r0 only, r0 with r1, r1 with r2 ...) put many references in the component that the query never
+    reaches: the walk must not stop early and must not mark them; cliques are the case where it does stop."""
+    rng = np.random.default_rng(99)
+    s, n = 64, 96
+    base = np.sort(rng.choice(1 << 40, size=(n + 1) * s, replace=False).astype(np.uint64)).reshape(n + 1, s)
+    rh = np.zeros((n, s), dtype=np.uint64)
+    for i in range(n):                                   # reference i = half of block i + half of block i+1: a chain
+        rh[i] = np.sort(np.concatenate([base[i, ::2], base[i + 1, 1::2]]))
+    rh[40:60] = np.sort(np.concatenate([np.tile(base[40, :8], (20, 1)), rng.integers(1 << 41, 1 << 42, size=(20, s - 8)).astype(np.uint64)], axis=1), axis=1)  # a clique
+    qh = np.zeros((n, s), dtype=np.uint64)
+    qh[:] = base[:n]                                     # query i = block i: shares with references i-1 and i only
+    qh[45] = rh[45]
+    rs = np.full(n, s, dtype=np.uint32); qs = np.full(n, s, dtype=np.uint32)
+    rl = np.full(n, 100_000, dtype=np.uint64); ql = np.full(n, 100_000, dtype=np.uint64)
+    got, passed = ctx.dist_tile((rh, rs, rl), (qh, qs, ql), s, 21, 4.0 ** 21)
+    _compare(got, passed, _oracle_matrix(oracle, (rh, rs, rl), (qh, qs, ql), s, 21, 4.0 ** 21))
+    assert int((got["numer"] > 0).sum()) > 2 * n - 40
+    hits = ctx.dist_hits((rh, rs, rl), (qh, qs, ql), s, 21, 4.0 ** 21, max_distance=0.9)
+    assert len(hits) == int((got["distance"] <= 0.9).sum())
