@@ -404,7 +404,7 @@ def main():
             "pruning": "exact: the rank pre-pass sorts every hash of both panels, which is also an inverted index; a pair whose sketches share no hash has common = 0 and denom = min(s, |A|+|B|) and is answered without a merge; related sketches are grouped into the same tiles; merge_steps_per_pair counts executed steps only; merge_all_pairs below is the same call with every pair merged",
             "roofline": {"bound": "hbm", "achieved": out_bytes / (tile_avg * 1e-3) / 1e9 if run["tile_n"] else None, "peak": hbm_peak, "unit": "GB/s",
                          "frac": out_bytes / (tile_avg * 1e-3) / 1e9 / hbm_peak if run["tile_n"] else None, "traffic": None,
-                         "note": "dist_tile32_kernel of the pruned run: rank panels read once + 24 B per pair written (to the pairs' original positions, i.e. as 24-byte records when the panels were grouped)"},
+                         "note": "dist_fill_unshared_kernel + dist_tile32_kernel of the pruned run (both inside kernel_ms.dist_tile32): 24 B per pair streamed in matrix order for the pairs without a shared hash, merged pairs overwritten at their original positions, rank panels read once"},
             "merge_all_pairs": {
                 "value": pairs / (full["ms"] * 1e-3), "unit": "pairs/s", "ms_per_step": full["ms"], "merge_steps_per_pair": full["merge_steps"] / ((q1 - q0) * nd),
                 "kernel_ms": {"dist_tile32": full["tile_avg"], "rank_compress": full["pack_avg"]},

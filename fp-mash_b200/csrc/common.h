@@ -56,6 +56,7 @@ struct fpm_ctx {
     fpm::DevBuf fa_raw, fa_seq, fa_chunk, fa_recs;
     uint64_t fa_records = 0, fa_seq_bytes = 0;
     fpm::DevBuf d_post, d_marks, d_group;        // dist pruning: posting lists, per-query reference bitmaps, grouped copies
+    fpm::DevBuf d_tiles;                         // dist: list of the tiles that hold work
     fpm::DevBuf d_hits, d_hsort;                 // fpm_dist_hits: appended hits, sort keys / sorted copy
     bool no_dist_prune = false;                  // tests: merge every pair
     bool no_dist_group = false;                  // tests: prune, but leave the panels in their own order

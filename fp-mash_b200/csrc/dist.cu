@@ -129,6 +129,33 @@ __global__ void __launch_bounds__(256) dist_collect_kernel(const fpm_pair* __res
     }
 }
 
+// Grouped panels scatter the tile kernel's 24-byte records over the matrix (partial sectors, written at different times),
+// and 19 of 20 records of a pruned all-vs-all are the closed-form ones of pairs without a shared hash.  So those are
+// written first, for ALL pairs, as one coalesced stream in the matrix's own order; the tile kernel then only overwrites
+// the pairs it merged.
+__global__ void __launch_bounds__(256) dist_fill_unshared_kernel(DistArgs a, uint64_t n_ref, uint64_t total, const uint32_t* __restrict__ size_ref,
+                                                                 const uint32_t* __restrict__ size_qry, const uint64_t* __restrict__ len_ref,
+                                                                 const uint64_t* __restrict__ len_qry, fpm_pair* __restrict__ out)
+{
+    // two records = 48 bytes = three 16-byte stores per thread
+    const uint64_t p = 2 * ((uint64_t)blockIdx.x * 256 + threadIdx.x);
+    if (p >= total) return;
+    fpm_pair rec[2];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const uint64_t pp = p + h < total ? p + h : p;
+        const uint64_t q = pp / n_ref, r = pp - q * n_ref;
+        const uint64_t un = (uint64_t)size_qry[q] + size_ref[r];
+        finish_pair(a, 0, un < a.s ? un : a.s, len_ref[r], len_qry[q], &rec[h]);
+    }
+    if (p + 1 < total) {
+        const uint4* src = reinterpret_cast<const uint4*>(rec);
+        uint4* dst = reinterpret_cast<uint4*>(out + p);                  // 48 * (p/2) bytes from a 16-byte aligned base
+        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+    } else
+        out[p] = rec[0];
+}
+
 __global__ void __launch_bounds__(256) dist_literal_kernel(fpm_panel ref, fpm_panel qry, DistArgs a, fpm_pair* out, unsigned long long* steps)
 {
     uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -431,7 +458,8 @@ dist_tile32_kernel(const uint32_t* __restrict__ pref, const uint32_t* __restrict
                    uint64_t n_ref, uint64_t n_qry, const uint64_t* __restrict__ len_ref, const uint64_t* __restrict__ len_qry,
                    DistArgs a, fpm_pair* __restrict__ out, unsigned long long* steps, uint32_t q_tile0,
                    const uint32_t* __restrict__ marks, uint32_t mark_words, const uint32_t* __restrict__ size_ref, const uint32_t* __restrict__ size_qry,
-                   const uint32_t* __restrict__ perm_q, const uint32_t* __restrict__ perm_r, HitSink hs)
+                   const uint32_t* __restrict__ perm_q, const uint32_t* __restrict__ perm_r, HitSink hs, int prefilled,
+                   const uint2* __restrict__ tile_list)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* colQ = reinterpret_cast<uint32_t*>(smem_raw);               // [D4_COLROWS][32] query columns
@@ -443,7 +471,8 @@ dist_tile32_kernel(const uint32_t* __restrict__ pref, const uint32_t* __restrict
     const int t = threadIdx.x;
     const int w = t >> 5, l = t & 31;
     const int rc0 = (l + w) & 31, rc1 = (l + w + 16) & 31;     // my two reference columns; my query column is l
-    const uint64_t q_tile2 = blockIdx.y + q_tile0, r_tile2 = blockIdx.x;   // both index pairs of 16-column tiles
+    // both index pairs of 16-column tiles; with a tile list (dist_rank.cu: only the tiles that hold work) the grid is 1-D over it
+    const uint64_t q_tile2 = tile_list ? tile_list[blockIdx.x].x : blockIdx.y + q_tile0, r_tile2 = tile_list ? tile_list[blockIdx.x].y : blockIdx.x;
     const uint32_t* gQ0 = pqry + (2 * q_tile2) * rows_qry * 16;           // plane 1 follows at + rows * 16
     const uint32_t* gR0 = pref + (2 * r_tile2) * rows_ref * 16;
     const bool q1_exists = 2 * q_tile2 + 1 < (n_qry + 15) / 16, r1_exists = 2 * r_tile2 + 1 < (n_ref + 15) / 16;
@@ -674,6 +703,10 @@ dist_tile32_kernel(const uint32_t* __restrict__ pref, const uint32_t* __restrict
         pass = false;
         if (act1) { finish_pair(a, common1, denom1, len_ref[s_orig[32 + rcm1]], len_qry[s_orig[qc1]], &o); my_steps += denom1; pass = (o.denom & FPM_PAIR_PASS) != 0; }
         append_hit(hs, pass, s_orig[qc1], s_orig[32 + rcm1], o);
+    } else if (prefilled) {
+        // matrix mode, records of pairs without a shared hash already in place (dist_fill_unshared_kernel): only the merged pairs
+        if (act0) { finish_pair(a, common0, denom0, len_ref[s_orig[32 + rcm0]], len_qry[s_orig[qc0]], out + (uint64_t)s_orig[qc0] * n_ref + s_orig[32 + rcm0]); my_steps += denom0; }
+        if (act1) { finish_pair(a, common1, denom1, len_ref[s_orig[32 + rcm1]], len_qry[s_orig[qc1]], out + (uint64_t)s_orig[qc1] * n_ref + s_orig[32 + rcm1]); my_steps += denom1; }
     } else {
         // matrix mode: stage in shared memory, then coalesced row writes
         fpm_pair* res = reinterpret_cast<fpm_pair*>(smem_raw);                  // [32][32]
@@ -796,14 +829,30 @@ static int run_dist(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* d_r
                 FPM_CUDA(cudaEventCreateWithFlags(&ctx->copy_done[0], cudaEventDisableTiming));
                 FPM_CUDA(cudaEventCreateWithFlags(&ctx->copy_done[1], cudaEventDisableTiming));
             }
+            const bool prefill = k32 && perm_q && !hits && ((uintptr_t)d_out & 15) == 0;   // grouped panels: see dist_fill_unshared_kernel
+            // nothing has to come out of a tile without a marked pair when its closed-form records are already in place (prefill)
+            // or cannot pass the filters (hits): such launches run over the list of tiles that hold work -- 19 of 20 tiles of
+            // configs[2] are empty, and an empty 512-thread CTA still costs its launch
+            const uint2* tile_list = nullptr;
+            uint32_t n_listed = 0;
+            if (k32 && perm_q && nqt <= tiles_per_chunk && (prefill || (hits && hits->skip_unmarked)))
+                if ((rc = dist_tile_list(ctx, marks, d_qry->n, d_ref->n, perm_q, perm_r, d_qry->sizes, d_ref->sizes, &tile_list, &n_listed))) return rc;
             uint64_t c = 0;
             for (uint64_t t0 = 0; t0 < nqt; t0 += tiles_per_chunk, c++) {
                 const uint64_t nt = std::min(tiles_per_chunk, nqt - t0);
                 dim3 grid((uint32_t)((d_ref->n + 31) / 32), (uint32_t)nt);
+                if (tile_list) grid = dim3(n_listed, 1);
                 ctx->time_begin(FPM_KERNEL_DIST_TILE);
-                if (k32)
+                if (prefill && t0 == 0) {                             // once, all rows: a chunk's grouped tiles write to any row
+                    dist_fill_unshared_kernel<<<(uint32_t)((total + 511) / 512), 256, 0, st>>>(a, d_ref->n, total, d_ref->sizes, d_qry->sizes,
+                                                                                                d_ref->lengths, d_qry->lengths, d_out);
+                    ctx->launches++;
+                }
+                if (k32 && tile_list && n_listed == 0)
+                    ;                                                 // no pair shares a hash
+                else if (k32)
                     dist_tile32_kernel<<<grid, DT_THREADS, smem, st>>>(p32r, p32q, rows_r, rows_q, d_ref->n, d_qry->n, d_ref->lengths, d_qry->lengths, a,
-                                                                       d_out, (unsigned long long*)d_steps, (uint32_t)t0, marks, (uint32_t)((d_ref->n + 31) / 32), d_ref->sizes, d_qry->sizes, perm_q, perm_r, hits ? *hits : no_hits);
+                                                                       d_out, (unsigned long long*)d_steps, (uint32_t)t0, marks, (uint32_t)((d_ref->n + 31) / 32), d_ref->sizes, d_qry->sizes, perm_q, perm_r, hits ? *hits : no_hits, prefill ? 1 : 0, tile_list);
                 else
                     dist_tile_kernel<<<grid, DT_THREADS, smem, st>>>(ctx->d_ref.as<uint64_t>(), ctx->d_qry.as<uint64_t>(), rows_r, rows_q, d_ref->n,
                                                                      d_qry->n, d_ref->lengths, d_qry->lengths, a, d_out, (unsigned long long*)d_steps, (uint32_t)t0);

@@ -306,6 +306,62 @@ int dist_group_panels(fpm_ctx* ctx, uint64_t n_q, uint64_t n_r, uint64_t rows_q,
     return FPM_OK;
 }
 
+// ---- tiles that hold work ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dist_tile_empty_kernel(const uint32_t* __restrict__ perm, const uint32_t* __restrict__ sizes, uint32_t n, uint32_t* __restrict__ has_empty)
+{
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;            // grouped position
+    if (g < n && sizes[perm[g]] == 0) has_empty[g >> 5] = 1;
+}
+
+// a thread per (query tile, reference tile = one word of the permuted bitmaps)
+__global__ void __launch_bounds__(256) dist_tile_list_kernel(const uint32_t* __restrict__ marks, uint32_t n_q, uint32_t words, const uint32_t* __restrict__ empty_q,
+                                                             const uint32_t* __restrict__ empty_r, uint2* __restrict__ list, uint32_t* __restrict__ count)
+{
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t q_tiles = (n_q + 31) / 32;
+    bool work = false;
+    uint32_t qt = 0, rt = 0;
+    if (idx < (uint64_t)q_tiles * words) {
+        qt = (uint32_t)(idx / words); rt = (uint32_t)(idx % words);
+        uint32_t any = 0;
+        for (uint32_t q = qt * 32; q < min(n_q, qt * 32 + 32); q++) any |= marks[(uint64_t)q * words + rt];
+        work = any != 0 || (empty_q[qt] && empty_r[rt]);
+    }
+    // warp-aggregated append: the list stays roughly in row-major tile order
+    const uint32_t m = __ballot_sync(0xffffffffu, work);
+    if (!m) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(count, (uint32_t)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (work) list[base + __popc(m & ((1u << lane) - 1u))] = make_uint2(qt, rt);
+}
+
+int dist_tile_list(fpm_ctx* ctx, const uint32_t* marks, uint64_t n_q, uint64_t n_r, const uint32_t* perm_q, const uint32_t* perm_r,
+                   const uint32_t* size_q, const uint32_t* size_r, const uint2** list, uint32_t* n_listed)
+{
+    cudaStream_t st = ctx->stream;
+    const uint32_t words = (uint32_t)((n_r + 31) / 32), q_tiles = (uint32_t)((n_q + 31) / 32);
+    const uint64_t tiles = (uint64_t)q_tiles * words;
+    const size_t a_e = (((size_t)q_tiles + words) * 4 + 255) & ~(size_t)255;
+    int rc;
+    if ((rc = ctx->d_tiles.ensure(256 + a_e + tiles * sizeof(uint2)))) return rc;
+    unsigned char* b = ctx->d_tiles.as<unsigned char>();
+    uint32_t* count = (uint32_t*)b;
+    uint32_t* empty_q = (uint32_t*)(b + 256); uint32_t* empty_r = empty_q + q_tiles;
+    uint2* out = (uint2*)(b + 256 + a_e);
+    FPM_CUDA(cudaMemsetAsync(b, 0, 256 + a_e, st));
+    dist_tile_empty_kernel<<<(uint32_t)((n_q + 255) / 256), 256, 0, st>>>(perm_q, size_q, (uint32_t)n_q, empty_q);
+    dist_tile_empty_kernel<<<(uint32_t)((n_r + 255) / 256), 256, 0, st>>>(perm_r, size_r, (uint32_t)n_r, empty_r);
+    dist_tile_list_kernel<<<(uint32_t)((tiles + 255) / 256), 256, 0, st>>>(marks, (uint32_t)n_q, words, empty_q, empty_r, out, count);
+    ctx->launches += 3;
+    FPM_CUDA(cudaGetLastError());
+    FPM_CUDA(cudaMemcpyAsync(n_listed, count, 4, cudaMemcpyDeviceToHost, st));
+    FPM_CUDA(cudaStreamSynchronize(st));
+    *list = out;
+    return FPM_OK;
+}
+
 // ---- fpm_dist_hits: order the appended hits as the reference prints them (query-major, CommandDistance.cpp:303-333) ----
 __global__ void __launch_bounds__(256) hit_keys_kernel(const fpm_hit* __restrict__ hits, uint64_t n, uint64_t n_ref, uint64_t* __restrict__ keys, uint32_t* __restrict__ idx)
 {

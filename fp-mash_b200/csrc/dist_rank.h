@@ -18,6 +18,11 @@ int dist_rank_panels(fpm_ctx* ctx, const fpm_panel* d_ref, const fpm_panel* d_qr
 int dist_group_panels(fpm_ctx* ctx, uint64_t n_q, uint64_t n_r, uint64_t rows_q, uint64_t rows_r, uint32_t** p32r, uint32_t** p32q, uint32_t** marks,
                       uint32_t** perm_q, uint32_t** perm_r);
 
+// After dist_group_panels: the 32 x 32 tiles (grouped order) that hold a marked pair, or an empty query together with an
+// empty reference (such a pair has distance 0 without sharing a hash), as (query tile, reference tile) in device memory.
+int dist_tile_list(fpm_ctx* ctx, const uint32_t* marks, uint64_t n_q, uint64_t n_r, const uint32_t* perm_q, const uint32_t* perm_r,
+                   const uint32_t* size_q, const uint32_t* size_r, const uint2** list, uint32_t* n_listed);
+
 // fpm_dist_hits: `n` hits appended in arbitrary order at `in` -> `out` sorted by (query, ref).  in != out.
 int dist_sort_hits(fpm_ctx* ctx, const fpm_hit* in, uint64_t n, uint64_t n_qry, uint64_t n_ref, fpm_hit* out);
 
