@@ -138,13 +138,21 @@ __global__ void __launch_bounds__(256) dist_fill_unshared_kernel(DistArgs a, uin
                                                                  const uint64_t* __restrict__ len_qry, fpm_pair* __restrict__ out)
 {
     // two records = 48 bytes = three 16-byte stores per thread
+    // (one 64-bit division per CTA, not two per thread: the divisions were what bounded this kernel)
+    __shared__ uint64_t s_q0, s_r0;
+    if (threadIdx.x == 0) { const uint64_t p0 = (uint64_t)blockIdx.x * 512; s_q0 = p0 / n_ref; s_r0 = p0 - s_q0 * n_ref; }
+    __syncthreads();
     const uint64_t p = 2 * ((uint64_t)blockIdx.x * 256 + threadIdx.x);
     if (p >= total) return;
     fpm_pair rec[2];
 #pragma unroll
     for (int h = 0; h < 2; h++) {
         const uint64_t pp = p + h < total ? p + h : p;
-        const uint64_t q = pp / n_ref, r = pp - q * n_ref;
+        uint64_t q = s_q0, r = s_r0 + (pp - (uint64_t)blockIdx.x * 512);
+        if (r >= n_ref) {
+            if (n_ref >= 512) { r -= n_ref; q++; }                        // a CTA's 512 pairs span at most two rows
+            else { q = pp / n_ref; r = pp - q * n_ref; }
+        }
         const uint64_t un = (uint64_t)size_qry[q] + size_ref[r];
         finish_pair(a, 0, un < a.s ? un : a.s, len_ref[r], len_qry[q], &rec[h]);
     }

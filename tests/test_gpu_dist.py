@@ -229,13 +229,13 @@ def test_dist_small_universe_many_ties(ctx, oracle):
             assert g["distance"] == pytest.approx(w["distance"], rel=RTOL, abs=0)
 
 
-def test_dist_device_path_grouped_equals_ungrouped(ctx):
+@pytest.mark.parametrize("n_r,n_q", [(700, 333), (300, 261), (1025, 513)])
+def test_dist_device_path_grouped_equals_ungrouped(ctx, n_r, n_q):
     """The device entry point (results stay in HBM) reorders both panels so that related sketches share tiles; the output
     must not depend on it: grouped+pruned = pruned = every pair merged = host path, byte for byte."""
     torch = pytest.importorskip("torch")
     rng = np.random.default_rng(14)
     s = 500
-    n_r, n_q = 700, 333
     rh, rs = sorted_sketch_panel(rng, n_r, s, n_clusters=9, shared=0.6)
     qh, qs = sorted_sketch_panel(rng, n_q, s, n_clusters=9, shared=0.6)
     qh[:50] = rh[200:250]; qs[:50] = rs[200:250]
