@@ -249,8 +249,12 @@ def main():
         raise SystemExit("bench.py: no CUDA device -- the fp-mash B200 path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    # stdout carries ONE JSON line: libraries (NCCL prints its version banner to fd 1) get stderr for the rest of the run
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version banner / debug lines stay off stdout: one JSON line only
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
 
     def barrier():
@@ -511,7 +515,8 @@ def main():
             "cpu_baseline": cpu,
             "dist": dist_obj,
         }
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
     return 0
