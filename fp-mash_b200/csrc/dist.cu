@@ -2,12 +2,15 @@
 //
 // Replaces compare() -> compareSketches() -> pValue() (CommandDistance.cpp:335-450).
 //
-// Two kernels:
-//   dist_literal_kernel   one thread per pair, the reference loop executed literally from
-//                         row-major panels in global memory.  Defines the result for ANY
-//                         input (fp-mode lists are unsorted and may repeat, SURVEY.md a9) and
-//                         is the fallback when the fast path's preconditions do not hold.
-//   dist_tile_kernel      the fast path for ascending duplicate-free lists.  One CTA owns a
+// Kernels:
+//   dist_tile32_kernel    the fast path for ascending duplicate-free lists: 32 queries x 32 references per CTA on the
+//                         32-bit dense ranks of dist_rank.cu, two interleaved merges per thread, value-bounded phases,
+//                         steps without end tests.  Merges only the pairs whose sketches share a hash (bitmaps from
+//                         dist_rank.cu); results as a matrix (dist_fill_unshared_kernel streams the closed-form records
+//                         of all other pairs first when the panels were grouped) or as a list of the pairs that pass
+//                         the -d / -v filters (HitSink, fpm_dist_hits).  DESIGN.md 4.3.
+//   dist_tile_kernel      the first fast path, kept for panels beyond 2^31 hashes and as the implementation the rank
+//                         kernel is compared against.  One CTA owns a
 //                         16-query x 32-reference tile (512 pairs, one thread each).  The 48
 //                         sketches are staged in shared memory as lane-private COLUMNS
 //                         (element p of sketch c at [p][c]), so the data-dependent reads of a
@@ -19,6 +22,12 @@
 //                         masked to the +inf sentinel, which makes "phase exhausted" and
 //                         "list exhausted" the same cheap test.  Pairs that reach denom == s
 //                         stop early (for unrelated same-size genomes one phase suffices).
+//   dist_literal_kernel   one thread per pair, the reference loop executed literally from
+//                         row-major panels in global memory.  Defines the result for ANY
+//                         input (fp-mode lists are unsorted and may repeat, SURVEY.md a9) and
+//                         is the fallback when the fast path's preconditions do not hold.
+//   dist_collect_kernel   hits mode of the two kernels above: scans their matrix for passing pairs.
+//   fp_positional_kernel  the fork's positional fingerprint comparison (mash triangle -fp).
 //
 // This is set intersection, not a contraction: no tensor cores.  The bound is integer
 // compare / shared-memory throughput.

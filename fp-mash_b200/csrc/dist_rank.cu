@@ -9,9 +9,15 @@
 // Steps (all on the caller's stream):
 //   dist_keys_kernel     every valid element -> (hash, destination index in the packed 32-bit tile layout);
 //                        also validates "strictly ascending" (the fast path's precondition)
-//   cub radix sort       by hash (library call, like the scan below: preprocessing, ~5 % of a dist step)
+//   cub radix sort       by hash (library call, like the scans below: 2.6 ms for 4*10^7 hashes)
 //   cub inclusive scan   of "differs from predecessor" = dense rank
 //   dist_scatter_kernel  rank -> packed[destination]
+// The sorted array is also an inverted index, which everything below the scatter uses:
+//   dist_post_* kernels  posting lists rank -> reference sketches, and how many postings a marking pass would walk
+//   dist_uf_* kernels    connected components of the "shares a hash" graph (bounds what a query can reach)
+//   dist_mark_kernel     per query, one bit per reference that shares a hash with it (pairs without one need no merge)
+//   dist_group_panels    both panels re-ordered so that related sketches share tiles; dist_tile_list: tiles with work
+//   dist_sort_hits       fpm_dist_hits: appended hits -> the reference's output order
 #include <cub/cub.cuh>
 #include "common.h"
 #include "dist_rank.h"
