@@ -499,7 +499,8 @@ int dist_rank_panels(fpm_ctx* ctx, const fpm_panel* d_ref, const fpm_panel* d_qr
         // walk the postings only if that costs well below the merges it can save: a posting is ~4 bytes of L2 traffic and
         // one shared-memory atomic, a pair's merge up to sketch_size steps
         const double postings = (double)h2[1], full = (double)d_ref->n * (double)d_qry->n * (double)std::max<uint32_t>(sketch_size, 1);
-        if (postings <= 0.05 * full && (size_t)words * 4 <= 200 * 1024) {
+        // (and only while the bitmaps stay small next to the panels: n_q x n_r bits, twice when grouped)
+        if (postings <= 0.05 * full && (size_t)words * 4 <= 200 * 1024 && (double)d_qry->n * words * 4 <= 8e9) {
             // marks [n_q][words] | union-find parents [n_r + n_q] | references per component [n_r + n_q]
             const size_t a_marks = ((size_t)d_qry->n * words * 4 + 255) & ~(size_t)255;
             const uint32_t nodes = (uint32_t)(d_ref->n + d_qry->n);
