@@ -265,3 +265,18 @@ def test_all_gather_rows_gloo_world2(tmp_path):
     for p in procs:
         out, err = p.communicate(timeout=240)
         assert p.returncode == 0 and "ok" in out, err[-2000:]
+
+
+def test_record_layouts_match_the_header(fpm, tmp_path):
+    """include/fpmash_b200.h is plain C; the numpy record types of the binding must have the C compiler's layout."""
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "%s"\n'
+                   'int main(void){printf("%%zu %%zu %%zu %%zu %%zu %%zu %%zu\\n", sizeof(fpm_pair), offsetof(fpm_pair, distance), offsetof(fpm_pair, pvalue),'
+                   ' sizeof(fpm_hit), offsetof(fpm_hit, numer), offsetof(fpm_hit, distance), offsetof(fpm_hit, pvalue)); return 0;}\n'
+                   % os.path.join(ROOT, "include", "fpmash_b200.h"))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-o", str(exe), str(src)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    p, h = fpm.PAIR_DTYPE, fpm.HIT_DTYPE
+    assert got == [p.itemsize, p.fields["distance"][1], p.fields["pvalue"][1], h.itemsize, h.fields["numer"][1], h.fields["distance"][1], h.fields["pvalue"][1]]
+    assert got[0] == 24 and got[3] == 32
