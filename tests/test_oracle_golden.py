@@ -170,6 +170,28 @@ def test_compare_closed_form(oracle):
         assert (out["numer"], out["denom"]) == (common, denom)
 
 
+def test_compare_without_a_shared_hash_is_closed_form(oracle):
+    """What the GPU path's pruning relies on: when the two lists share no hash the reference loop yields
+    common = 0, denom = min(s, |A| + |B|), distance 1 and p-value 1 -- except two empty lists: 0/0, distance 0."""
+    rng = np.random.default_rng(17)
+    for _ in range(300):
+        s = int(rng.integers(1, 60))
+        u = rng.permutation(200)[:int(rng.integers(0, 90))].astype(np.uint64)
+        cut = int(rng.integers(0, len(u) + 1))
+        a, b = np.sort(u[:cut]), np.sort(u[cut:])                    # disjoint by construction, any sizes incl. empty
+        for md, mp_ in ((1.0, 1.0), (0.3, 1.0), (1.0, 1e-3)):
+            out = oracle.compare(a, b, 5000, 7000, s, 21, 4.0 ** 21, md, mp_)
+            assert (out["numer"], out["denom"]) == (0, min(s, len(a) + len(b)))
+            if len(a) + len(b) == 0:
+                assert out["distance"] == 0.0 and out["passed"] == (mp_ >= 1.0)
+                if out["passed"]:
+                    assert out["pvalue"] == 1.0
+            else:
+                assert out["distance"] == 1.0 and out["passed"] == (md >= 1.0 and mp_ >= 1.0)
+                if md >= 1.0:
+                    assert out["pvalue"] == 1.0
+
+
 # ---- the oracle vs the reference's own code (only where oracle/_ref was built) ---------------
 def test_oracle_matches_reference_heap(oracle, reflib):
     rng = np.random.default_rng(11)
