@@ -58,6 +58,11 @@ struct fpm_ctx {
     fpm::DevBuf d_post, d_marks, d_group;        // dist pruning: posting lists, per-query reference bitmaps, grouped copies
     fpm::DevBuf d_tiles;                         // dist: list of the tiles that hold work
     fpm::DevBuf d_hits, d_hsort;                 // fpm_dist_hits: appended hits, sort keys / sorted copy
+    // several GPUs, one process each (dist_multi.cu): NCCL communicator handed in or created from a unique id
+    void* comm = nullptr;                        // ncclComm_t
+    int comm_rank = 0, comm_world = 0;
+    bool comm_owned = false;
+    fpm::DevBuf d_xq, d_xr;                      // this rank's query / reference block after the exchange step
     bool no_dist_prune = false;                  // tests: merge every pair
     bool no_dist_group = false;                  // tests: prune, but leave the panels in their own order
     bool force_dist64 = false;                   // tests: run the 64-bit tile kernel although the 32-bit rank path applies

@@ -36,6 +36,7 @@
 #include "common.h"
 #include "dist_math.h"
 #include "dist_rank.h"
+#include "dist_internal.h"
 
 namespace fpm {
 
@@ -100,14 +101,6 @@ __device__ __forceinline__ void finish_pair(const DistArgs& a, uint64_t common, 
     *out = o;
 }
 
-// fpm_dist_hits: passing pairs are appended to a list instead of written to an n x n matrix.
-struct HitSink {
-    fpm_hit* buf = nullptr;              // nullptr: matrix mode
-    unsigned long long* count = nullptr; // all passing pairs, also those beyond cap (the caller retries with room for them)
-    unsigned long long cap = 0;
-    int skip_unmarked = 0;               // the filters exclude distance 1: a pair without a shared hash cannot pass
-};
-
 // Called by whole converged warps: one atomicAdd per warp, the lanes with a hit write 32-byte records behind each other.
 __device__ __forceinline__ void append_hit(const HitSink& hs, bool pass, uint32_t q, uint32_t r, const fpm_pair& o)
 {
@@ -120,7 +113,7 @@ __device__ __forceinline__ void append_hit(const HitSink& hs, bool pass, uint32_
     const unsigned long long at = base + __popc(m & ((1u << lane) - 1u));
     if (pass && at < hs.cap) {
         uint4* dst = reinterpret_cast<uint4*>(hs.buf + at);
-        dst[0] = make_uint4(q, r, o.numer, o.denom);
+        dst[0] = make_uint4(q + hs.q_base, r + hs.r_base, o.numer, o.denom);   // indices in the caller's panels (a rank's block: dist_multi.cu)
         dst[1] = make_uint4((uint32_t)__double_as_longlong(o.distance), (uint32_t)(__double_as_longlong(o.distance) >> 32),
                             (uint32_t)__double_as_longlong(o.pvalue), (uint32_t)(__double_as_longlong(o.pvalue) >> 32));
     }
@@ -134,7 +127,7 @@ __global__ void __launch_bounds__(256) dist_collect_kernel(const fpm_pair* __res
         const uint64_t p = base + threadIdx.x;
         fpm_pair o = {0, 0, 0., 0.};
         if (p < total && (mat[p].denom & FPM_PAIR_PASS)) o = mat[p];
-        append_hit(hs, (o.denom & FPM_PAIR_PASS) != 0, (uint32_t)(p / n_ref), (uint32_t)(p % n_ref), o);
+        append_hit(hs, (o.denom & FPM_PAIR_PASS) != 0, (uint32_t)(p / n_ref), (uint32_t)(p % n_ref), o);   // (bases added inside)
     }
 }
 
@@ -768,8 +761,8 @@ dist_tile32_kernel(const uint32_t* __restrict__ pref, const uint32_t* __restrict
 
 // h_out (nullable): host destination.  When given, the fast path runs in query-row chunks and copies chunk c
 // back on a second stream while chunk c+1 is being compared, then waits for all copies.
-static int run_dist(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* d_ref, const fpm_panel* d_qry, fpm_pair* d_out,
-                    uint64_t* d_steps, uint32_t max_size_ref, uint32_t max_size_qry, fpm_pair* h_out = nullptr, const HitSink* hits = nullptr)
+int run_dist(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* d_ref, const fpm_panel* d_qry, fpm_pair* d_out,
+             uint64_t* d_steps, uint32_t max_size_ref, uint32_t max_size_qry, fpm_pair* h_out, const HitSink* hits, uint64_t h_ld)
 {
     // hits mode (fpm_dist_hits): d_out and h_out are null.  The 32-bit rank kernel appends passing pairs itself; the other
     // paths need a result matrix, which then lives in ctx->d_out and is scanned by dist_collect_kernel.
@@ -880,8 +873,12 @@ static int run_dist(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* d_r
                     const uint64_t q0 = t0 * qt, q1 = std::min<uint64_t>(d_qry->n, (t0 + nt) * qt);
                     FPM_CUDA(cudaEventRecord(ctx->copy_done[c & 1], st));
                     FPM_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_done[c & 1], 0));
-                    FPM_CUDA(cudaMemcpyAsync(h_out + q0 * d_ref->n, d_out + q0 * d_ref->n, (q1 - q0) * d_ref->n * sizeof(fpm_pair),
-                                             cudaMemcpyDeviceToHost, ctx->copy_stream));
+                    if (h_ld == 0 || h_ld == d_ref->n)
+                        FPM_CUDA(cudaMemcpyAsync(h_out + q0 * d_ref->n, d_out + q0 * d_ref->n, (q1 - q0) * d_ref->n * sizeof(fpm_pair),
+                                                 cudaMemcpyDeviceToHost, ctx->copy_stream));
+                    else   // this call's matrix is a block of a wider one on the host (h_ld records per row)
+                        FPM_CUDA(cudaMemcpy2DAsync(h_out + q0 * h_ld, h_ld * sizeof(fpm_pair), d_out + q0 * d_ref->n, d_ref->n * sizeof(fpm_pair),
+                                                   d_ref->n * sizeof(fpm_pair), q1 - q0, cudaMemcpyDeviceToHost, ctx->copy_stream));
                 }
             }
             if (h_out) FPM_CUDA(cudaStreamSynchronize(ctx->copy_stream));
@@ -899,7 +896,9 @@ static int run_dist(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* d_r
         ctx->launches++;
         FPM_CUDA(cudaGetLastError());
         if (h_out) {
-            FPM_CUDA(cudaMemcpyAsync(h_out, d_out, total * sizeof(fpm_pair), cudaMemcpyDeviceToHost, st));
+            if (h_ld == 0 || h_ld == d_ref->n) FPM_CUDA(cudaMemcpyAsync(h_out, d_out, total * sizeof(fpm_pair), cudaMemcpyDeviceToHost, st));
+            else FPM_CUDA(cudaMemcpy2DAsync(h_out, h_ld * sizeof(fpm_pair), d_out, d_ref->n * sizeof(fpm_pair), d_ref->n * sizeof(fpm_pair), d_qry->n,
+                                            cudaMemcpyDeviceToHost, st));
             FPM_CUDA(cudaStreamSynchronize(st));
         }
         if (hits && (rc = collect())) return rc;
@@ -907,7 +906,7 @@ static int run_dist(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* d_r
     return FPM_OK;
 }
 
-static int max_size_dev(fpm_ctx* ctx, const fpm_panel* d, uint32_t* out)
+int max_size_dev(fpm_ctx* ctx, const fpm_panel* d, uint32_t* out)
 {
     std::vector<uint32_t> h(d->n);
     if (d->n) {
@@ -920,13 +919,18 @@ static int max_size_dev(fpm_ctx* ctx, const fpm_panel* d, uint32_t* out)
     return FPM_OK;
 }
 
-static int check_dist(const fpm_dist_params* p, const fpm_panel* ref, const fpm_panel* qry)
+int check_dist(const fpm_dist_params* p, const fpm_panel* ref, const fpm_panel* qry)
 {
     if (!p || !ref || !qry) { set_error("NULL argument"); return FPM_ERR_ARG; }
     if (p->sketch_size >= 0x7fffffffu) { set_error("sketch size too large"); return FPM_ERR_ARG; }
     if (p->kmer_size < 1) { set_error("kmer size must be >= 1"); return FPM_ERR_ARG; }
     return FPM_OK;
 }
+
+// one block of a wider host matrix (dist_multi.cu): `out` points at the block's first record, rows are ld records apart
+int dist_tile_host_ld(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* ref, const fpm_panel* qry, fpm_pair* out, uint64_t ld);
+int dist_hits_host(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* ref, const fpm_panel* qry, fpm_hit* out, uint64_t capacity, uint64_t* n_hits,
+                   uint32_t q_base, uint32_t r_base);
 
 }  // namespace fpm
 
@@ -973,7 +977,7 @@ static int upload_panels(fpm_ctx* ctx, const fpm_panel* ref, const fpm_panel* qr
     return FPM_OK;
 }
 
-static int dist_tile_host(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* ref, const fpm_panel* qry, fpm_pair* out, bool positional)
+static int dist_tile_host(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* ref, const fpm_panel* qry, fpm_pair* out, bool positional, uint64_t h_ld = 0)
 {
     if (!ctx) { set_error("ctx is NULL"); return FPM_ERR_ARG; }
     int rc = check_dist(p, ref, qry);
@@ -991,14 +995,16 @@ static int dist_tile_host(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_pane
         ctx->launches++;
         FPM_CUDA(cudaGetLastError());
         FPM_CUDA(cudaMemcpyAsync(out, ctx->d_out.p, ref->n * qry->n * sizeof(fpm_pair), cudaMemcpyDeviceToHost, st));
-    } else if ((rc = run_dist(ctx, p, &dr, &dq, ctx->d_out.as<fpm_pair>(), nullptr, mr, mq, out))) return rc;
+    } else if ((rc = run_dist(ctx, p, &dr, &dq, ctx->d_out.as<fpm_pair>(), nullptr, mr, mq, out, nullptr, h_ld))) return rc;
     FPM_CUDA(cudaStreamSynchronize(st));
     return FPM_OK;
 }
 
+}  // extern "C"
+
 // Both fpm_dist_hits entry points: device panels in, sorted hits at d_sorted (room for `capacity`), *n_hits on the host.
-static int dist_hits_run(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* d_ref, const fpm_panel* d_qry, uint32_t mr, uint32_t mq,
-                         fpm_hit* d_sorted, uint64_t capacity, uint64_t* n_hits, uint64_t* d_steps)
+int fpm::dist_hits_run(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* d_ref, const fpm_panel* d_qry, uint32_t mr, uint32_t mq,
+                       fpm_hit* d_sorted, uint64_t capacity, uint64_t* n_hits, uint64_t* d_steps, uint32_t q_base, uint32_t r_base)
 {
     int rc;
     *n_hits = 0;
@@ -1010,6 +1016,7 @@ static int dist_hits_run(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel
     hs.count = ctx->d_hits.as<unsigned long long>();            // first 32 bytes: the counter; records follow
     hs.buf = reinterpret_cast<fpm_hit*>(ctx->d_hits.as<unsigned char>() + 32);
     hs.cap = capacity;
+    hs.q_base = q_base; hs.r_base = r_base;
     // a pair without a shared hash has distance 1 and p-value 1 (dist_math.h): it passes only when neither filter excludes 1
     hs.skip_unmarked = (p->max_distance >= 0 && p->max_distance < 1.) || (p->max_pvalue >= 0 && p->max_pvalue < 1.);
     FPM_CUDA(cudaMemsetAsync(hs.count, 0, 32, st));
@@ -1019,8 +1026,10 @@ static int dist_hits_run(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel
     FPM_CUDA(cudaStreamSynchronize(st));
     *n_hits = n;
     if (n > capacity) { set_error("fpm_dist_hits: %llu pairs pass the filters, room for %llu", n, (unsigned long long)capacity); return FPM_ERR_CAPACITY; }
-    return dist_sort_hits(ctx, hs.buf, n, d_qry->n, d_ref->n, d_sorted);
+    return dist_sort_hits(ctx, hs.buf, n, d_qry->n, d_ref->n, d_sorted, q_base, r_base);
 }
+
+extern "C" {
 
 int fpm_dist_tile(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* ref, const fpm_panel* qry, fpm_pair* out)
 {
@@ -1046,6 +1055,19 @@ int fpm_dist_hits_dev(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* d
 
 int fpm_dist_hits(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* ref, const fpm_panel* qry, fpm_hit* out, uint64_t capacity, uint64_t* n_hits)
 {
+    return dist_hits_host(ctx, p, ref, qry, out, capacity, n_hits, 0, 0);
+}
+
+}  // extern "C"
+
+int fpm::dist_tile_host_ld(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* ref, const fpm_panel* qry, fpm_pair* out, uint64_t ld)
+{
+    return dist_tile_host(ctx, p, ref, qry, out, false, ld);
+}
+
+int fpm::dist_hits_host(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* ref, const fpm_panel* qry, fpm_hit* out, uint64_t capacity, uint64_t* n_hits,
+                        uint32_t q_base, uint32_t r_base)
+{
     if (!ctx) { set_error("ctx is NULL"); return FPM_ERR_ARG; }
     if (!n_hits || (!out && capacity)) { set_error("NULL argument"); return FPM_ERR_ARG; }
     int rc = check_dist(p, ref, qry);
@@ -1059,11 +1081,13 @@ int fpm_dist_hits(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* ref, 
     // d_hits = counter | appended records | sorted records (dist_hits_run's own ensure() is then a no-op: the buffer only grows)
     if ((rc = ctx->d_hits.ensure(2 * capacity * sizeof(fpm_hit) + 64))) return rc;
     fpm_hit* d_sorted = reinterpret_cast<fpm_hit*>(ctx->d_hits.as<unsigned char>() + 32) + capacity;
-    if ((rc = dist_hits_run(ctx, p, &dr, &dq, mr, mq, d_sorted, capacity, n_hits, nullptr))) return rc;
+    if ((rc = dist_hits_run(ctx, p, &dr, &dq, mr, mq, d_sorted, capacity, n_hits, nullptr, q_base, r_base))) return rc;
     if (*n_hits) FPM_CUDA(cudaMemcpyAsync(out, d_sorted, *n_hits * sizeof(fpm_hit), cudaMemcpyDeviceToHost, ctx->stream));
     FPM_CUDA(cudaStreamSynchronize(ctx->stream));
     return FPM_OK;
 }
+
+extern "C" {
 
 int fpm_fp_positional_tile(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* ref, const fpm_panel* qry, fpm_pair* out)
 {

@@ -165,14 +165,27 @@ __global__ void __launch_bounds__(256) dist_uf_union_kernel(const uint64_t* __re
     }
 }
 
-// parent[x] = root for every node; ref_count[root] = references in the component
+// parent[x] = root for every query node; ref_count[root] = references in the component.  The find here must not
+// compress paths: this kernel publishes roots into the array other threads are still walking, and a path-halving
+// store of a (non-root) grandparent landing after the final "parent[x] = root" would leave the query pointing at a
+// node whose ref_count is 0 -- its marking pass would then stop before walking a single posting.  With a read-only
+// walk every value ever stored from here on is a root, and a walker that meets one early simply arrives sooner.
+__device__ __forceinline__ uint32_t uf_root_readonly(const uint32_t* parent, uint32_t x)
+{
+    for (;;) {
+        const uint32_t p = reinterpret_cast<const volatile uint32_t*>(parent)[x];
+        if (p == x) return x;
+        x = p;
+    }
+}
+
 __global__ void __launch_bounds__(256) dist_uf_flatten_kernel(uint32_t* __restrict__ parent, uint32_t* __restrict__ ref_count, uint32_t n_r, uint32_t n)
 {
     const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= n) return;
-    const uint32_t r = uf_find<true>(parent, x);
+    const uint32_t r = uf_root_readonly(parent, x);
     if (x < n_r) atomicAdd(&ref_count[r], 1u);
-    if (x >= n_r) parent[x] = r;            // only the queries' entries are read afterwards; references keep valid ancestors for concurrent finds
+    if (x >= n_r) parent[x] = r;            // only the queries' entries are read afterwards
 }
 
 // one CTA per query sketch: bit r of its row = reference r shares a hash with it.  (Also tried: one identity for equal posting
@@ -369,12 +382,13 @@ int dist_tile_list(fpm_ctx* ctx, const uint32_t* marks, uint64_t n_q, uint64_t n
 }
 
 // ---- fpm_dist_hits: order the appended hits as the reference prints them (query-major, CommandDistance.cpp:303-333) ----
-__global__ void __launch_bounds__(256) hit_keys_kernel(const fpm_hit* __restrict__ hits, uint64_t n, uint64_t n_ref, uint64_t* __restrict__ keys, uint32_t* __restrict__ idx)
+__global__ void __launch_bounds__(256) hit_keys_kernel(const fpm_hit* __restrict__ hits, uint64_t n, uint64_t n_ref, uint32_t q_base, uint32_t r_base,
+                                                       uint64_t* __restrict__ keys, uint32_t* __restrict__ idx)
 {
     const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;
     const uint2 qr = *reinterpret_cast<const uint2*>(hits + i);
-    keys[i] = (uint64_t)qr.x * n_ref + qr.y;          // the pair's position in the reference's output order
+    keys[i] = (uint64_t)(qr.x - q_base) * n_ref + (qr.y - r_base);          // the pair's position in the reference's output order
     idx[i] = (uint32_t)i;
 }
 
@@ -386,7 +400,7 @@ __global__ void __launch_bounds__(256) hit_gather_kernel(const fpm_hit* __restri
     reinterpret_cast<uint4*>(out)[i] = reinterpret_cast<const uint4*>(in)[2ull * idx[i >> 1] + (i & 1)];
 }
 
-int dist_sort_hits(fpm_ctx* ctx, const fpm_hit* in, uint64_t n, uint64_t n_qry, uint64_t n_ref, fpm_hit* out)
+int dist_sort_hits(fpm_ctx* ctx, const fpm_hit* in, uint64_t n, uint64_t n_qry, uint64_t n_ref, fpm_hit* out, uint32_t q_base, uint32_t r_base)
 {
     int bits = 1;
     while (bits < 64 && ((n_qry * n_ref - 1) >> bits)) bits++;   // radix passes only over the bits a pair index can have
@@ -405,7 +419,7 @@ int dist_sort_hits(fpm_ctx* ctx, const fpm_hit* in, uint64_t n, uint64_t n_qry, 
     kb = cub::DoubleBuffer<uint64_t>((uint64_t*)b, (uint64_t*)(b + ak));
     vb = cub::DoubleBuffer<uint32_t>((uint32_t*)(b + 2 * ak), (uint32_t*)(b + 2 * ak + av));
     void* d_tmp = b + 2 * ak + 2 * av;
-    hit_keys_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, st>>>(in, n, n_ref, kb.Current(), vb.Current());
+    hit_keys_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, st>>>(in, n, n_ref, q_base, r_base, kb.Current(), vb.Current());
     FPM_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmp, kb, vb, (int64_t)n, 0, bits, st));
     hit_gather_kernel<<<(uint32_t)((2 * n + 255) / 256), 256, 0, st>>>(in, vb.Current(), n, out);
     ctx->launches += 3;

@@ -24,6 +24,7 @@ int dist_tile_list(fpm_ctx* ctx, const uint32_t* marks, uint64_t n_q, uint64_t n
                    const uint32_t* size_q, const uint32_t* size_r, const uint2** list, uint32_t* n_listed);
 
 // fpm_dist_hits: `n` hits appended in arbitrary order at `in` -> `out` sorted by (query, ref).  in != out.
-int dist_sort_hits(fpm_ctx* ctx, const fpm_hit* in, uint64_t n, uint64_t n_qry, uint64_t n_ref, fpm_hit* out);
+int dist_sort_hits(fpm_ctx* ctx, const fpm_hit* in, uint64_t n, uint64_t n_qry, uint64_t n_ref, fpm_hit* out, uint32_t q_base = 0, uint32_t r_base = 0);
+// (hit records carry indices q_base + q, r_base + r when the call compares one block of larger panels)
 
 }  // namespace fpm

@@ -33,6 +33,19 @@ __device__ __forceinline__ uint64_t mul64c(uint64_t x)
     return ((uint64_t)hi << 32) | lo;
 }
 
+// high word of x * C mod 2^64 only (mul.hi + two IMADs): the low word costs nothing extra with mul64c, but the
+// 64-bit result of IMAD.WIDE occupies two destination registers and issues at half rate
+template <uint64_t C>
+__device__ __forceinline__ uint32_t mul64c_hi(uint64_t x)
+{
+    const uint32_t xl = (uint32_t)x, xh = (uint32_t)(x >> 32);
+    uint32_t hi;
+    asm("mul.hi.u32 %0, %1, %3;\n\tmad.lo.u32 %0, %2, %3, %0;\n\tmad.lo.u32 %0, %1, %4, %0;"
+        : "=&r"(hi)
+        : "r"(xl), "r"(xh), "n"((uint32_t)C), "n"((uint32_t)(C >> 32)));
+    return hi;
+}
+
 __device__ __forceinline__ uint64_t fmix64(uint64_t k)
 {
     k ^= k >> 33;

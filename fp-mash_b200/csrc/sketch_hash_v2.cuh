@@ -27,39 +27,46 @@
 // chunk is the halo of lane 30 and the first chunk of the next warp tile.
 #pragma once
 #include "sketch_kernels.cuh"
+#include "sketch_tables.cuh"
 
 namespace fpm {
 
 constexpr int WT_WINDOWS = 63 * 32;        // windows per warp tile
 constexpr int WT_TILES_PER_WARP = 12;      // contiguous warp tiles walked by one warp
 
-// 4 ASCII bytes -> 4 validity bits (bit j = byte j is one of ACGT after optional case fold).
-// valid  <=>  the byte equals the ASCII letter its own 2-bit code expands to.
-__device__ __forceinline__ uint32_t nt_valid4_simd(uint32_t x, uint32_t fold_mask)
+// 32 ASCII bases (8 words) -> two big-endian 2-bit code words.  Per word one multiply gathers the four codes into
+// the top byte; three PRMTs assemble four such bytes into a register.  (Validity is not tracked here: the hash of a
+// window holding a letter outside ACGT is garbage that passes the threshold with probability ~1e-4 like any other,
+// and the survivors' letters are re-read from memory -- window_is_valid below -- before anything is inserted.)
+__device__ __forceinline__ uint32_t nt_codes4_top(uint32_t x)     // codes of 4 bases in bits 31..24, first base highest
 {
-    const uint32_t TBL = 0x54474341u;                       // 'A','C','G','T'
-    uint32_t f = x & fold_mask;
-    uint32_t c = ((x >> 1) ^ (x >> 2)) & 0x03030303u;       // per-byte code
-    uint32_t t = c | (c >> 4);                              // byte0 = c0|c1<<4, byte2 = c2|c3<<4
-    uint32_t sel = prmt(t, 0u, 0x4420u);                    // selector nibbles c0,c1,c2,c3
-    uint32_t e = prmt(TBL, 0u, sel);                        // expected ASCII per byte
-    uint32_t d = e ^ f;                                     // zero byte <=> valid
-    uint32_t nz = (((d & 0x7f7f7f7fu) + 0x7f7f7f7fu) | d) & 0x80808080u;   // bit 7 of each non-zero byte
-    uint32_t ok = (nz ^ 0x80808080u) >> 7;                  // bits 0,8,16,24
-    return (ok * 0x00204081u) >> 21 & 0xfu;                 // gather to bits 0..3
+    const uint32_t c = ((x >> 1) ^ (x >> 2)) & 0x03030303u;
+    return c * 0x40100401u;
 }
 
-// 32 ASCII bases (8 words) -> two big-endian 2-bit code words + 32 validity bits
-__device__ __forceinline__ void convert32(const uint32_t (&w)[8], uint32_t fold_mask, uint32_t& c0, uint32_t& c1, uint32_t& v)
+__device__ __forceinline__ uint32_t gather_top_bytes(uint32_t t0, uint32_t t1, uint32_t t2, uint32_t t3)
 {
-    c0 = 0; c1 = 0; v = 0;
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        c0 |= nt_codes4(w[i]) << (24 - 8 * i);
-        c1 |= nt_codes4(w[i + 4]) << (24 - 8 * i);
-        v |= nt_valid4_simd(w[i], fold_mask) << (4 * i);
-        v |= nt_valid4_simd(w[i + 4], fold_mask) << (16 + 4 * i);
+    const uint32_t u = prmt(t1, t0, 0x0073u);      // byte1 = t0's top byte, byte0 = t1's
+    const uint32_t v = prmt(t3, t2, 0x0073u);
+    return prmt(v, u, 0x5410u);                    // t0.b3 : t1.b3 : t2.b3 : t3.b3
+}
+
+__device__ __forceinline__ void convert32(const uint32_t (&w)[8], uint32_t& c0, uint32_t& c1)
+{
+    c0 = gather_top_bytes(nt_codes4_top(w[0]), nt_codes4_top(w[1]), nt_codes4_top(w[2]), nt_codes4_top(w[3]));
+    c1 = gather_top_bytes(nt_codes4_top(w[4]), nt_codes4_top(w[5]), nt_codes4_top(w[6]), nt_codes4_top(w[7]));
+}
+
+// Do the K bytes at `pos` all belong to ACGT (after the optional case fold)?  Rare path: only windows whose hash passed
+// the sketch's threshold get here.  Reads the input again (L1/L2 hits: the tile was loaded moments ago).
+static __device__ __noinline__ bool window_is_valid(const uint8_t* __restrict__ seq, uint64_t pos, int k, uint64_t n_bytes, uint32_t fold_mask)
+{
+    if (pos + (uint64_t)k > n_bytes) return false;
+    for (int i = 0; i < k; i++) {
+        const uint32_t b = seq[pos + i] & (fold_mask & 0xffu);
+        if (b != 'A' && b != 'C' && b != 'G' && b != 'T') return false;
     }
+    return true;
 }
 
 constexpr uint32_t SQ_CAP = 128;     // per-warp survivor queue (hash, position)
@@ -78,7 +85,7 @@ __device__ __forceinline__ void flush_survivors(const SketchArgs& a, const uint6
 }
 
 #ifndef FPM_SK_MIN_CTAS
-#define FPM_SK_MIN_CTAS 4   // 64 registers: four 256-thread CTAs (32 warps) per SM; measured best (3 -> 79 regs, 1 -> 100 regs are slower)
+#define FPM_SK_MIN_CTAS 3   // 80 registers, no spills: round 2's table-driven body at k=21 runs 273 Gk-mers/s at 3 CTAs/SM, 263 at 4 (64 registers, spills), 262 at 2
 #endif
 template <int K, bool CANON>
 __global__ void __launch_bounds__(SK_THREADS, FPM_SK_MIN_CTAS) sketch_hash_kernel_v2(const SketchArgs* __restrict__ ga, uint64_t range_lo, uint64_t range_hi,
@@ -92,15 +99,14 @@ __global__ void __launch_bounds__(SK_THREADS, FPM_SK_MIN_CTAS) sketch_hash_kerne
     const uint32_t fold_mask = a.fold_case ? 0xdfdfdfdfu : 0xffffffffu;
     // constants kept in registers for the whole kernel: as immediates they cost moves per window
     // (read from the argument block so that ptxas cannot fold them back into immediates)
-    const uint32_t tbl = a.c_tbl;
-    const uint64_t add1 = a.c_add1, add2 = a.c_add2;
+    const uint64_t add1 = a.c_add1, add2 = a.c_add2, add1s = a.c_add1s;
     __shared__ uint64_t s_qh[SK_THREADS / 32][SQ_CAP], s_qp[SK_THREADS / 32][SQ_CAP];
     __shared__ uint32_t s_qn[SK_THREADS / 32];
     __shared__ uint64_t s_tm[SK_THREADS / 32];      // the warp's current threshold bound (see the filter below)
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    __shared__ uint32_t s_lut[512];
-    build_expand_lut(s_lut, K, threadIdx.x, SK_THREADS);
-    uint32_t lut_addr = (uint32_t)__cvta_generic_to_shared(s_lut);
+    __shared__ KmerTables<K> s_tab;                 // Murmur's first multiply per word / the tail lane as table entries (sketch_tables.cuh)
+    build_kmer_tables<K>(&s_tab, threadIdx.x, SK_THREADS);
+    uint32_t lut_addr = (uint32_t)__cvta_generic_to_shared(&s_tab);
     asm volatile("" : "+r"(lut_addr));     // keep the table address in a register: re-deriving it costs ~4 instructions per window
     __syncthreads();
     if (lane == 0) s_qn[wid] = 0;
@@ -148,23 +154,24 @@ __global__ void __launch_bounds__(SK_THREADS, FPM_SK_MIN_CTAS) sketch_hash_kerne
         if (idle_tile) continue;
 
         const uint32_t tcut = hash32 ? (uint32_t)tmax : (uint32_t)(tmax >> 32);
+        // lazy finish: hi(a1) + hi(a2) + 1 is the hash's high word or one above it (carry from the low words unknown)
+        const uint32_t tcut1 = tcut == 0xffffffffu ? tcut : tcut + 1u;
         if (lane == 0) s_tm[wid] = tmax;
         __syncwarp();
 
         // ---- load + convert 64 bases per lane -------------------------------------------------
         const uint64_t lane_pos = tile_base + 64ull * lane;
-        uint32_t q0, q1, q2, q3, q4, q5, v0, v1, v2;
+        uint32_t q0, q1, q2, q3, q4, q5;
         {
             uint4 l0 = load16_guarded(seq, lane_pos, n_bytes), l1 = load16_guarded(seq, lane_pos + 16, n_bytes);
             uint4 l2 = load16_guarded(seq, lane_pos + 32, n_bytes), l3 = load16_guarded(seq, lane_pos + 48, n_bytes);
             const uint32_t wa[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
             const uint32_t wb[8] = {l2.x, l2.y, l2.z, l2.w, l3.x, l3.y, l3.z, l3.w};
-            convert32(wa, fold_mask, q0, q1, v0);
-            convert32(wb, fold_mask, q2, q3, v1);
+            convert32(wa, q0, q1);
+            convert32(wb, q2, q3);
         }
         q4 = __shfl_down_sync(0xffffffffu, q0, 1);
         q5 = __shfl_down_sync(0xffffffffu, q1, 1);
-        v2 = __shfl_down_sync(0xffffffffu, v0, 1);
         // (no lane leaves the tile early: the survivor queue below is flushed by the whole warp)
         const int nblk = lane_pos >= n_bytes ? 0 : (lane == 31 ? 2 : 4);
 
@@ -182,7 +189,8 @@ __global__ void __launch_bounds__(SK_THREADS, FPM_SK_MIN_CTAS) sketch_hash_kerne
             for (int sub = 0; sub < 16 / FPM_WIN; sub++) {
                 // FPM_WIN windows in flight; ONE filter branch for all of them (a branch per window cost ~16 % of the
                 // stall samples: ISETP waiting for the end of the Murmur chain, then branch resolution)
-                uint64_t hh[FPM_WIN];
+                constexpr bool lazy = FPM_LAZYFIN && !hash32;
+                uint64_t hh[FPM_WIN], hb[lazy ? FPM_WIN : 1];
                 bool any_below = false;
                 if (live) {
 #pragma unroll
@@ -200,28 +208,30 @@ __global__ void __launch_bounds__(SK_THREADS, FPM_SK_MIN_CTAS) sketch_hash_kerne
                             chi = use_r ? rhi : fhi;
                             clo = use_r ? rlo : flo;
                         }
-                        uint64_t w[4];
-                        expand_lut<K>(chi, clo, w, lut_addr);
-                        uint64_t h = murmur3_h1_fixed<K>(w, seed, add1, add2);
-                        if (hash32) h &= 0xffffffffULL;
-                        hh[j] = h;
-                        // one-instruction reject on the deciding word; the exact 64-bit test only for the survivors
-                        any_below |= (hash32 ? (uint32_t)h : (uint32_t)(h >> 32)) <= tcut;
+                        if (lazy) {
+                            kmer_hash_parts<K>(chi, clo, lut_addr, seed, add1s, add1, add2, hh[j], hb[j]);
+                            any_below |= (uint32_t)(hh[j] >> 32) + (uint32_t)(hb[j] >> 32) + 1u <= tcut1;
+                        } else {
+                            uint64_t a1_, a2_;
+                            kmer_hash_parts<K>(chi, clo, lut_addr, seed, add1s, add1, add2, a1_, a2_);
+                            uint64_t h = kmer_hash_finish(a1_, a2_);
+                            if (hash32) h &= 0xffffffffULL;
+                            hh[j] = h;
+                            // one-instruction reject on the deciding word; the exact 64-bit test only for the survivors
+                            any_below |= (hash32 ? (uint32_t)h : (uint32_t)(h >> 32)) <= tcut;
+                        }
                     }
                 }
                 if (any_below) {
 #pragma unroll
                     for (int j = 0; j < FPM_WIN; j++) {
-                        const uint64_t h = hh[j];
+                        const uint64_t h = lazy ? kmer_hash_finish(hh[j], hb[lazy ? j : 0]) : hh[j];
                         // the exact 64-bit test reads its bound back through a volatile shared load, which the compiler
                         // cannot speculate above the branch
                         if (h > *(volatile uint64_t*)&s_tm[wid]) continue;
                         const int b = 16 * blk + FPM_WIN * sub + j;              // window index within the lane's 64
-                        const uint64_t vlo = ((uint64_t)v1 << 32) | v0;
-                        const uint64_t vw = b ? ((vlo >> b) | ((uint64_t)v2 << (64 - b))) : vlo;
-                        constexpr uint64_t km = (1ULL << K) - 1;
                         const uint64_t pos = lane_pos + b;
-                        if ((vw & km) == km && pos >= range_lo && pos < range_hi) {
+                        if (pos >= range_lo && pos < range_hi && window_is_valid(seq, pos, K, n_bytes, fold_mask)) {
                             // survivors are queued per warp and inserted 32 at a time: the table atomics cost a
                             // ~1 us round trip that would otherwise stall the whole warp for one lane's hash
                             queued = true;
@@ -234,12 +244,13 @@ __global__ void __launch_bounds__(SK_THREADS, FPM_SK_MIN_CTAS) sketch_hash_kerne
                 // next four windows: forward registers one byte left, reverse-complement one byte right
                 fw0 = __funnelshift_l(fw1, fw0, 2 * FPM_WIN); fw1 = __funnelshift_l(fw2, fw1, 2 * FPM_WIN); fw2 <<= 2 * FPM_WIN;
                 if (CANON) { x[2] = __funnelshift_r(x[2], x[1], 2 * FPM_WIN); x[1] = __funnelshift_r(x[1], x[0], 2 * FPM_WIN); x[0] >>= 2 * FPM_WIN; }
-                // dense survivors (accept-all sketches of short records): insert as soon as a warp-load is waiting
-                // the queue can only have grown if some lane queued a survivor in these four windows (~5 % of the time)
-                if (__any_sync(0xffffffffu, queued)) {
-                    queued = false;
-                    if (s_qn[wid] >= 32) flush_survivors(a, s_qh[wid], s_qp[wid], &s_qn[wid], lane, trace);
-                }
+            }
+            // dense survivors (accept-all sketches of short records): insert once a warp-load is waiting.  One vote per
+            // 16-window block; the queue can only have grown if some lane queued a survivor (entries beyond the queue's
+            // capacity were inserted directly).
+            if (__any_sync(0xffffffffu, queued)) {
+                queued = false;
+                if (s_qn[wid] >= 32) flush_survivors(a, s_qh[wid], s_qp[wid], &s_qn[wid], lane, trace);
             }
             q0 = q1; q1 = q2; q2 = q3; q3 = q4; q4 = q5;
         }

@@ -224,7 +224,7 @@ int sketch_batch_dev_impl(fpm_ctx* ctx, const fpm_sketch_params* p, const uint8_
         a.maxkey_cnt = ctx->maxcnt.as<uint32_t>(); a.maxkey_pos = ctx->maxpos.as<uint64_t>();
         a.overflow = ctx->overflow.as<uint32_t>();
         a.sketch_size = s; a.seed = p->seed; a.fold_case = !p->preserve_case; a.hash32 = !p->use64;
-            a.c_tbl = 0x54474341u; a.c_add1 = 0x52dce729ULL; a.c_add2 = 0x38495ab5ULL;
+            a.c_tbl = 0x54474341u; a.c_add1 = 0x52dce729ULL; a.c_add2 = 0x38495ab5ULL; a.c_add1s = a.c_add1 + 5ull * a.seed;
         FPM_CUDA(cudaMemcpyAsync(ctx->args.p, &a, sizeof a, cudaMemcpyHostToDevice, st));
         for (const auto& r : ranges) {
             ctx->time_begin(FPM_KERNEL_SKETCH_HASH);
@@ -324,7 +324,7 @@ int sketch_batch_dev_impl(fpm_ctx* ctx, const fpm_sketch_params* p, const uint8_
             a.fin_hashes = d_out_hashes; a.fin_n = d_out_n; a.tr_off = ctx->tr_off.as<uint64_t>(); a.tr_cap = d_out_counts;
             a.tr_cursor = ctx->tr_cursor.as<uint32_t>(); a.tr_pos = ctx->tr_pos.as<uint64_t>();
             a.sketch_size = s; a.seed = p->seed; a.fold_case = !p->preserve_case; a.hash32 = !p->use64;
-            a.c_tbl = 0x54474341u; a.c_add1 = 0x52dce729ULL; a.c_add2 = 0x38495ab5ULL;
+            a.c_tbl = 0x54474341u; a.c_add1 = 0x52dce729ULL; a.c_add2 = 0x38495ab5ULL; a.c_add1s = a.c_add1 + 5ull * a.seed;
             FPM_CUDA(cudaMemcpyAsync(ctx->args.p, &a, sizeof a, cudaMemcpyHostToDevice, st));
             for (const auto& r : ranges) {
                 ctx->time_begin(FPM_KERNEL_SKETCH_HASH);
@@ -418,21 +418,30 @@ int fpm_sketch_batch(fpm_ctx* ctx, const fpm_sketch_params* p, const uint8_t* se
         if (n_chunks > 1) FPM_CUDA(cudaEventRecord(ctx->copy_done[c & 1], cs));
         return FPM_OK;
     };
-    if ((rc = enqueue_copy(0))) return rc;
+    // Any exit below, failure included, first drains the copy stream: a copy of the caller's host buffer may still be in
+    // flight there, and the caller is free to release that buffer as soon as this function returns.
+    auto drained = [&](int code) -> int {
+        if (n_chunks > 1 && ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+        return code;
+    };
+    if ((rc = enqueue_copy(0))) return drained(rc);
     std::vector<uint64_t> goff;
     rc = FPM_OK;
     for (size_t c = 0; c < n_chunks && rc == FPM_OK; c++) {
         const uint32_t g0 = cut[c], ng = cut[c + 1] - cut[c];
-        if (n_chunks > 1) FPM_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->copy_done[c & 1], 0));
+        if (n_chunks > 1) {
+            cudaError_t e = cudaStreamWaitEvent(ctx->stream, ctx->copy_done[c & 1], 0);
+            if (e != cudaSuccess) return drained(cuda_fail(e, "cudaStreamWaitEvent(copy_done)", __FILE__, __LINE__));
+        }
         // the event of chunk c+1 reuses slot (c+1)&1, last used by chunk c-1 whose wait was already enqueued
-        if (c + 1 < n_chunks && (rc = enqueue_copy(c + 1))) return rc;
+        if (c + 1 < n_chunks && (rc = enqueue_copy(c + 1))) return drained(rc);
         goff.resize(ng + 1);
         for (uint32_t g = 0; g <= ng; g++) goff[g] = group_offsets[g0 + g] - group_offsets[g0];
         rc = sketch_batch_dev_impl(ctx, p, ctx->seq.as<uint8_t>() + dev_off[c], goff[ng], goff.data(), ng,
                                    ctx->outh.as<uint64_t>() + (uint64_t)g0 * s, counts ? ctx->outc.as<uint32_t>() + (uint64_t)g0 * s : nullptr,
                                    ctx->outn.as<uint32_t>() + g0, out_kmers ? ctx->outk.as<uint64_t>() + g0 : nullptr);
     }
-    if (rc) return rc;
+    if (rc) return drained(rc);
     FPM_CUDA(cudaMemcpyAsync(out_hashes, ctx->outh.p, sizeof(uint64_t) * n_groups * s, cudaMemcpyDeviceToHost, ctx->stream));
     if (counts) FPM_CUDA(cudaMemcpyAsync(out_counts, ctx->outc.p, sizeof(uint32_t) * n_groups * s, cudaMemcpyDeviceToHost, ctx->stream));
     FPM_CUDA(cudaMemcpyAsync(out_n, ctx->outn.p, sizeof(uint32_t) * n_groups, cudaMemcpyDeviceToHost, ctx->stream));

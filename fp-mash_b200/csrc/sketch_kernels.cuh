@@ -69,7 +69,7 @@ struct SketchArgs {
     int hash32;                  // !use64
     // hot-loop constants handed over as data ('ACGT' table for PRMT, Murmur block addends)
     uint32_t c_tbl;
-    uint64_t c_add1, c_add2;
+    uint64_t c_add1, c_add2, c_add1s;   // c_add1s = c_add1 + 5 * seed (first Murmur block, sketch_tables.cuh)
 };
 
 // ---------------------------------------------------------------------------------------
@@ -223,42 +223,6 @@ __device__ __forceinline__ void expand_lut(uint32_t hi, uint32_t lo, uint64_t (&
     for (int c = 0; c < 4; c++) w[c] = ((uint64_t)v[2 * c + 1] << 32) | v[2 * c];
 }
 
-// The 16 windows of one block.  fw0..2: 48 forward bases; window i starts at base i.
-// CANON: pick min(forward, reverse complement) (ties are palindromes: identical bytes).
-// F is called as F(i, hash) for every window, valid or not (validity is checked only for the
-// rare windows that pass the threshold).
-template <int K, bool CANON, typename Sink>
-__device__ __forceinline__ void hash_block16(uint32_t fw0, uint32_t fw1, uint32_t fw2, uint32_t seed, int hash32, Sink&& sink)
-{
-    uint32_t rc[5];
-    if (CANON) {
-        rc[0] = revcomp16(fw2); rc[1] = revcomp16(fw1); rc[2] = revcomp16(fw0); rc[3] = 0; rc[4] = 0;
-    }
-#pragma unroll
-    for (int i = 0; i < 16; i++) {
-        uint32_t fhi = i ? __funnelshift_l(fw1, fw0, 2 * i) : fw0;
-        uint32_t flo = i ? __funnelshift_l(fw2, fw1, 2 * i) : fw1;
-        uint32_t chi = fhi, clo = flo;
-        if (CANON) {
-            const int start = 48 - K - i;            // rc position of the window's first rc base
-            const int a = start >> 4, sh = 2 * (start & 15);
-            uint32_t rhi = sh ? __funnelshift_l(rc[a + 1], rc[a], sh) : rc[a];
-            uint32_t rlo = sh ? __funnelshift_l(rc[a + 2], rc[a + 1], sh) : rc[a + 1];
-            uint64_t f64 = ((uint64_t)fhi << 32) | flo, r64 = ((uint64_t)rhi << 32) | rlo;
-            // Bits below the k-mer (neighbouring bases) can only decide the comparison when the
-            // k-mer equals its own reverse complement, where both choices give the same bytes.
-            bool use_r = r64 < f64;
-            chi = use_r ? rhi : fhi;
-            clo = use_r ? rlo : flo;
-        }
-        uint64_t w[4];
-        expand_ascii<K>(chi, clo, w);
-        uint64_t h = murmur3_h1_fixed<K>(w, seed);
-        if (hash32) h &= 0xffffffffULL;
-        sink(i, h);
-    }
-}
-
 __device__ __forceinline__ uint32_t find_group(const uint64_t* group_off, uint32_t lo, uint32_t hi, uint64_t pos)
 {
     // largest g in [lo,hi] with group_off[g] <= pos
@@ -310,37 +274,6 @@ static __device__ __noinline__ void sketch_emit(const SketchArgs& a, uint64_t h,
     atomicExch(&a.overflow[g], 1u);
 }
 
-// ---------------------------------------------------------------------------------------
-// Every window's hash, in order (tests only; single record, no groups).
-// out[pos] = hash or SK_EMPTY-marked invalid via the parallel flag array.
-// ---------------------------------------------------------------------------------------
-template <int K, bool CANON>
-__global__ void __launch_bounds__(SK_THREADS) kmer_hash_stream_kernel(const uint8_t* seq, uint64_t n_bytes, uint32_t seed,
-                                                                      int fold_case, int hash32, uint64_t* out, uint8_t* out_valid)
-{
-    __shared__ uint32_t s_code[2 * SK_TILE_CHUNKS + 2];
-    __shared__ uint32_t s_valid[SK_TILE_CHUNKS + 1];
-    const uint64_t tile_base = (uint64_t)blockIdx.x * SK_TILE_WINDOWS;
-    convert_tile(seq, n_bytes, tile_base, fold_case, s_code, s_valid);
-    if (threadIdx.x == 0) { s_code[2 * SK_TILE_CHUNKS] = 0; s_code[2 * SK_TILE_CHUNKS + 1] = 0; s_valid[SK_TILE_CHUNKS] = 0; }
-    __syncthreads();
-    for (int it = 0; it < SK_BLOCKS_PER_THREAD; it++) {
-        const int b = it * SK_THREADS + threadIdx.x;
-        const uint64_t block_pos = tile_base + 16ull * b;
-        if (block_pos >= n_bytes) break;
-        hash_block16<K, CANON>(s_code[b], s_code[b + 1], s_code[b + 2], seed, hash32, [&](int i, uint64_t h) {
-            uint64_t pos = block_pos + i;
-            if (pos < n_bytes) {
-                uint64_t v = ((uint64_t)s_valid[(b >> 1) + 1] << 32) | s_valid[b >> 1];
-                v >>= (16 * (b & 1) + i);
-                constexpr uint64_t km = (1ULL << K) - 1;
-                out[pos] = h;
-                out_valid[pos] = ((v & km) == km) ? 1 : 0;
-            }
-        });
-    }
-}
-
 // Valid windows per group (the "k-mers sketched" unit).  One thread per 32-base chunk.
 template <int K>
 __global__ void __launch_bounds__(SK_THREADS) count_windows_kernel(const SketchArgs* __restrict__ ga, unsigned long long* out_kmers)
@@ -361,9 +294,10 @@ __global__ void __launch_bounds__(SK_THREADS) count_windows_kernel(const SketchA
     __syncthreads();
     const int c = threadIdx.x;                       // chunk of 32 windows
     const uint64_t chunk_pos = tile_base + 32ull * c;
-    if (chunk_pos >= a.n_bytes) return;
+    // (no early exit for chunks beyond the input: every lane takes part in the warp reduction below)
+    const bool in_range = chunk_pos < a.n_bytes;
     // window i valid iff valid bits [i, i+K) all set: AND-shift doubling on 64 bits
-    uint64_t v = ((uint64_t)s_valid[c + 1] << 32) | s_valid[c];
+    uint64_t v = in_range ? ((uint64_t)s_valid[c + 1] << 32) | s_valid[c] : 0;
     int have = 1;
     // build run-of-K mask by binary decomposition of K
     uint64_t acc = ~0ULL;

@@ -176,7 +176,11 @@ bool resolve(Msg& m, int s, size_t i, Obj& o)
         int ts = (int)hi;
         bool dbl = (lo >> 2) & 1;
         if (!m.in(ts, pad, dbl ? 2 : 1)) { m.err = "far pointer out of range"; return false; }
-        if (!dbl) return resolve(m, ts, pad, o);
+        if (!dbl) {
+            // the landing pad of a single-far pointer is an ordinary (near) pointer: exactly one hop, no recursion
+            if ((m.seg[ts][pad] & 3) == 2) { m.err = "far pointer landing pad is itself a far pointer"; return false; }
+            return resolve(m, ts, pad, o);
+        }
         uint64_t p0 = m.seg[ts][pad], tag = m.seg[ts][pad + 1];
         if (((uint32_t)p0 & 3) != 2) { m.err = "bad double-far landing pad"; return false; }
         o.kind = (uint32_t)tag & 3; o.seg = (int)(p0 >> 32); o.idx = (uint32_t)p0 >> 3; o.hi = (uint32_t)(tag >> 32);

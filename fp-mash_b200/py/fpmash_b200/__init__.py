@@ -25,6 +25,7 @@ FPM_ERR_CUDA = -2
 FPM_ERR_ARG = -3
 FPM_ERR_UNSUPPORTED = -4
 FPM_ERR_NOMEM = -5
+FPM_ERR_COMM = -7
 FPM_PAIR_PASS = 0x80000000
 
 u8p = C.POINTER(C.c_uint8)
@@ -116,7 +117,63 @@ lib.fpm_ctx_set_timing.argtypes = [_VP, C.c_int]
 lib.fpm_ctx_set_dist_mode.argtypes = [_VP, C.c_int]
 lib.fpm_ctx_get_timing.argtypes = [_VP, C.c_int, C.POINTER(C.c_double), u64p]
 
-KERNEL_SKETCH_HASH, KERNEL_SKETCH_SELECT, KERNEL_DIST_TILE, KERNEL_DIST_LITERAL, KERNEL_DIST_PACK = range(5)
+KERNEL_SKETCH_HASH, KERNEL_SKETCH_SELECT, KERNEL_DIST_TILE, KERNEL_DIST_LITERAL, KERNEL_DIST_PACK, KERNEL_DIST_EXCHANGE = range(6)
+
+
+class Block(C.Structure):
+    _fields_ = [("q_begin", C.c_uint64), ("q_end", C.c_uint64), ("r_begin", C.c_uint64), ("r_end", C.c_uint64)]
+
+
+COMM_ID_BYTES = 128
+lib.fpm_shard_range.restype = None
+lib.fpm_shard_range.argtypes = [C.c_uint64, C.c_int, C.c_int, u64p, u64p]
+lib.fpm_dist_grid_shape.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+lib.fpm_dist_block.argtypes = [C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.POINTER(Block)]
+lib.fpm_comm_get_unique_id.argtypes = [_VP]
+lib.fpm_comm_init_rank.argtypes = [_VP, _VP, C.c_int, C.c_int]
+lib.fpm_comm_adopt.argtypes = [_VP, _VP, C.c_int, C.c_int]
+lib.fpm_comm_destroy.argtypes = [_VP]
+lib.fpm_comm_rank.argtypes = [_VP]
+lib.fpm_comm_size.argtypes = [_VP]
+lib.fpm_dist_sharded_dev.argtypes = [_VP, C.POINTER(DistParams), C.POINTER(Panel), C.c_uint64, C.POINTER(Panel), C.c_uint64, _VP, C.c_uint64,
+                                     C.POINTER(Block), _VP]
+lib.fpm_dist_hits_sharded_dev.argtypes = [_VP, C.POINTER(DistParams), C.POINTER(Panel), C.c_uint64, C.POINTER(Panel), C.c_uint64, _VP, C.c_uint64,
+                                          u64p, C.POINTER(Block), _VP]
+lib.fpm_multi_create.argtypes = [_VP, C.c_int, C.POINTER(_VP)]
+lib.fpm_multi_destroy.argtypes = [_VP]
+lib.fpm_multi_destroy.restype = None
+lib.fpm_multi_size.argtypes = [_VP]
+lib.fpm_multi_ctx.argtypes = [_VP, C.c_int]
+lib.fpm_multi_ctx.restype = _VP
+lib.fpm_dist_tile_multi.argtypes = [_VP, C.POINTER(DistParams), C.POINTER(Panel), C.POINTER(Panel), _VP]
+lib.fpm_dist_hits_multi.argtypes = [_VP, C.POINTER(DistParams), C.POINTER(Panel), C.POINTER(Panel), _VP, C.c_uint64, u64p]
+lib.fpm_sketch_batch_multi.argtypes = [_VP, C.POINTER(SketchParams), _VP, C.c_uint64, _VP, C.c_uint32, _VP, _VP, _VP, _VP]
+
+
+def shard_range(n, part, parts):
+    """Rows [n*part/parts, n*(part+1)/parts) -- fpm_shard_range."""
+    a, b = C.c_uint64(0), C.c_uint64(0)
+    lib.fpm_shard_range(n, part, parts, C.byref(a), C.byref(b))
+    return int(a.value), int(b.value)
+
+
+def dist_grid_shape(world, n_qry, n_ref):
+    qp, rp = C.c_int(0), C.c_int(0)
+    _check(lib.fpm_dist_grid_shape(world, n_qry, n_ref, C.byref(qp), C.byref(rp)))
+    return qp.value, rp.value
+
+
+def dist_block(rank, world, n_qry, n_ref):
+    """(q_begin, q_end, r_begin, r_end) of the block `rank` compares -- fpm_dist_block."""
+    b = Block()
+    _check(lib.fpm_dist_block(rank, world, n_qry, n_ref, C.byref(b)))
+    return int(b.q_begin), int(b.q_end), int(b.r_begin), int(b.r_end)
+
+
+def comm_unique_id():
+    buf = (C.c_uint8 * COMM_ID_BYTES)()
+    _check(lib.fpm_comm_get_unique_id(buf))
+    return bytes(buf)
 
 EXPORTED = ["fpm_abi_version", "fpm_device_count", "fpm_ctx_create", "fpm_ctx_destroy", "fpm_last_error",
             "fpm_ctx_sync", "fpm_ctx_stream", "fpm_ctx_set_stream", "fpm_host_alloc", "fpm_host_free",
@@ -125,7 +182,11 @@ EXPORTED = ["fpm_abi_version", "fpm_device_count", "fpm_ctx_create", "fpm_ctx_de
             "fpm_fp_hash_batch", "fpm_cfl_fingerprint_batch", "fpm_fingerprint_batch", "fpm_dist_tile", "fpm_dist_tile_dev", "fpm_fp_positional_tile", "fpm_pvalue", "fpm_distance",
             "fpm_measure_int32_peak", "fpm_get_int32_peaks", "fpm_ctx_set_timing", "fpm_ctx_get_timing", "fpm_ctx_set_dist_mode",
             "fpm_fasta_parse", "fpm_fasta_records", "fpm_fasta_sequence", "fpm_sketch_parsed",
-            "fpm_fastq_stream_append", "fpm_fastq_line_ends", "fpm_dist_hits", "fpm_dist_hits_dev"]
+            "fpm_fastq_stream_append", "fpm_fastq_line_ends", "fpm_dist_hits", "fpm_dist_hits_dev",
+            "fpm_shard_range", "fpm_dist_grid_shape", "fpm_dist_block", "fpm_comm_get_unique_id", "fpm_comm_init_rank", "fpm_comm_adopt",
+            "fpm_comm_destroy", "fpm_comm_rank", "fpm_comm_size", "fpm_dist_sharded_dev", "fpm_dist_hits_sharded_dev",
+            "fpm_multi_create", "fpm_multi_destroy", "fpm_multi_size", "fpm_multi_ctx", "fpm_dist_tile_multi", "fpm_dist_hits_multi",
+            "fpm_sketch_batch_multi"]
 
 
 def _check(rc):
@@ -525,6 +586,112 @@ class Context:
         dp = DistParams(sketch_size, kmer_size, kmer_space, max_distance, max_pvalue, int(sorted_unique))
         _check(lib.fpm_dist_tile_dev(self._h, C.byref(dp), C.byref(pr), C.byref(pq), _VP(d_out_ptr),
                                      _VP(d_steps_ptr) if d_steps_ptr else None))
+
+
+    # -- several GPUs, one process each -------------------------------------------------------
+    def comm_init(self, unique_id, rank, world):
+        """Collective: create this context's NCCL communicator from the id rank 0 got from comm_unique_id()."""
+        buf = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(unique_id)
+        _check(lib.fpm_comm_init_rank(self._h, buf, rank, world))
+
+    def comm_destroy(self):
+        _check(lib.fpm_comm_destroy(self._h))
+
+    def dist_sharded_dev(self, ref_shard_ptrs, n_ref_total, qry_shard_ptrs, n_qry_total, sketch_size, kmer_size, kmer_space, d_out_ptr,
+                         out_capacity, d_steps_ptr=None, max_distance=1.0, max_pvalue=1.0, sorted_unique=True):
+        """Collective all-ranks comparison: this rank's row shards in, its block of the result matrix out (dense, at d_out_ptr).
+        Returns the block (q_begin, q_end, r_begin, r_end)."""
+        pr = Panel(*ref_shard_ptrs)
+        pq = Panel(*qry_shard_ptrs)
+        dp = DistParams(sketch_size, kmer_size, kmer_space, max_distance, max_pvalue, int(sorted_unique))
+        b = Block()
+        _check(lib.fpm_dist_sharded_dev(self._h, C.byref(dp), C.byref(pr), n_ref_total, C.byref(pq), n_qry_total, _VP(d_out_ptr), int(out_capacity),
+                                        C.byref(b), _VP(d_steps_ptr) if d_steps_ptr else None))
+        return int(b.q_begin), int(b.q_end), int(b.r_begin), int(b.r_end)
+
+    def dist_hits_sharded_dev(self, ref_shard_ptrs, n_ref_total, qry_shard_ptrs, n_qry_total, sketch_size, kmer_size, kmer_space, d_out_ptr,
+                              capacity, d_steps_ptr=None, max_distance=1.0, max_pvalue=1.0, sorted_unique=True):
+        pr = Panel(*ref_shard_ptrs)
+        pq = Panel(*qry_shard_ptrs)
+        dp = DistParams(sketch_size, kmer_size, kmer_space, max_distance, max_pvalue, int(sorted_unique))
+        b = Block()
+        n = C.c_uint64(0)
+        _check(lib.fpm_dist_hits_sharded_dev(self._h, C.byref(dp), C.byref(pr), n_ref_total, C.byref(pq), n_qry_total, _VP(d_out_ptr), int(capacity),
+                                             C.byref(n), C.byref(b), _VP(d_steps_ptr) if d_steps_ptr else None))
+        return int(n.value), (int(b.q_begin), int(b.q_end), int(b.r_begin), int(b.r_end))
+
+
+class Multi:
+    """All GPUs of the box driven from one process (fpm_multi_*): what `mash dist` / `mash sketch` use."""
+
+    def __init__(self, devices=None, n_devices=0):
+        h = _VP()
+        if devices is not None:
+            arr = (C.c_int * len(devices))(*devices)
+            _check(lib.fpm_multi_create(arr, len(devices), C.byref(h)))
+        else:
+            _check(lib.fpm_multi_create(None, n_devices, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if self._h:
+            lib.fpm_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def size(self):
+        return lib.fpm_multi_size(self._h)
+
+    def dist_tile(self, ref, qry, sketch_size, kmer_size, kmer_space, max_distance=1.0, max_pvalue=1.0, sorted_unique=True, out=None, raw=False):
+        pr, keep_r = Context._panel(*ref)
+        pq, keep_q = Context._panel(*qry)
+        dp = DistParams(sketch_size, kmer_size, kmer_space, max_distance, max_pvalue, int(sorted_unique))
+        if out is None:
+            out = np.zeros((pq.n, pr.n), dtype=PAIR_DTYPE)
+        assert out.dtype == PAIR_DTYPE and out.shape == (pq.n, pr.n) and out.flags["C_CONTIGUOUS"]
+        _check(lib.fpm_dist_tile_multi(self._h, C.byref(dp), C.byref(pr), C.byref(pq), out.ctypes.data))
+        if raw:
+            return out, None
+        passed = (out["denom"] & FPM_PAIR_PASS) != 0
+        out["denom"] &= 0x7fffffff
+        return out, passed
+
+    def dist_hits(self, ref, qry, sketch_size, kmer_size, kmer_space, max_distance=1.0, max_pvalue=1.0, sorted_unique=True, capacity=None, raw=False):
+        pr, keep_r = Context._panel(*ref)
+        pq, keep_q = Context._panel(*qry)
+        dp = DistParams(sketch_size, kmer_size, kmer_space, max_distance, max_pvalue, int(sorted_unique))
+        n = C.c_uint64(0)
+        cap = int(capacity) if capacity is not None else max(1024, 8 * int(pq.n + pr.n))
+        while True:
+            out = np.zeros(cap, dtype=HIT_DTYPE)
+            rc = lib.fpm_dist_hits_multi(self._h, C.byref(dp), C.byref(pr), C.byref(pq), out.ctypes.data, cap, C.byref(n))
+            if rc != FPM_ERR_CAPACITY:
+                _check(rc)
+                break
+            cap = int(n.value)
+        hits = out[:n.value]
+        if not raw:
+            hits["denom"] &= 0x7fffffff
+        return hits
+
+    def sketch_batch(self, seq, group_offsets, params, want_kmers=False):
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        goff = np.ascontiguousarray(group_offsets, dtype=np.uint64)
+        n = len(goff) - 1
+        s = params.sketch_size
+        hashes = np.zeros((n, s), dtype=np.uint64)
+        counts = np.zeros((n, s), dtype=np.uint32) if params.want_counts else None
+        out_n = np.zeros(n, dtype=np.uint32)
+        kmers = np.zeros(n, dtype=np.uint64) if want_kmers else None
+        _check(lib.fpm_sketch_batch_multi(self._h, C.byref(params), seq.ctypes.data, seq.size, goff.ctypes.data, n, hashes.ctypes.data,
+                                          counts.ctypes.data if counts is not None else None, out_n.ctypes.data,
+                                          kmers.ctypes.data if kmers is not None else None))
+        return {"hashes": hashes, "counts": counts, "n": out_n, "kmers": kmers}
 
 
 def pvalue(x, len_ref, len_qry, kmer_space, n):

@@ -1,23 +1,17 @@
-"""Multi-GPU partitioning of the hot path: one process per GPU.
+"""Host-side helpers for the one-process-per-GPU deployment of the hot path.
 
-* sketching shards by input file / sequence: no data-path collective (`assign_by_size`);
-* dist shards the QUERY rows over ranks; the reference panel is replicated with ONE exchange
-  step, an all-gather of each rank's panel shard (`all_gather_rows`, NCCL over NVLink on GPUs,
-  gloo in the CPU tests); results stay sharded by query row.
+The partitioning itself lives in the library (csrc/dist_multi.cu: fpm_shard_range, fpm_dist_grid_shape, fpm_dist_block,
+fpm_dist_sharded_dev); this module only does what the HOST program has to do around it:
 
-torch.distributed is plumbing here; it is imported lazily so the single-GPU path needs no torch.
+* sketching shards by input file / sequence, no data-path collective (`assign_by_size`);
+* `init_comm`: distribute the NCCL unique id of rank 0 over whatever process group the host already has
+  (torch.distributed here; MPI or a file work the same) and create the library's communicator;
+* `assemble_blocks`: put the ranks' result blocks back into the reference's query-major matrix
+  (CommandDistance.cpp:355-359) -- used by the tests and by rank 0 when it wants the whole table.
+
+torch.distributed is plumbing; it is imported lazily so the single-GPU path needs no torch.
 """
-
-
-def shard_range(n, rank, world):
-    """Contiguous [lo, hi) of n items owned by `rank`; sizes differ by at most one."""
-    base, extra = divmod(n, world)
-    lo = rank * base + min(rank, extra)
-    return lo, lo + base + (1 if rank < extra else 0)
-
-
-def shard_bounds(n, world):
-    return [shard_range(n, r, world) for r in range(world)]
+import numpy as np
 
 
 def assign_by_size(sizes, world):
@@ -33,21 +27,65 @@ def assign_by_size(sizes, world):
     return [[i for i in range(len(sizes)) if owner[i] == r] for r in range(world)]
 
 
-def all_gather_rows(local_rows, n_total, group=None):
-    """All-gather a row-sharded 2-D tensor whose shards follow shard_range(n_total, rank, world).
-    Uneven shards are padded to the largest shard for the collective and trimmed afterwards."""
+def shard_range(n, part, parts):
+    """Rows [n*part/parts, n*(part+1)/parts): the row shard `part` of `parts` (same rule as fpm_shard_range)."""
+    return n * part // parts, n * (part + 1) // parts
+
+
+def grid_shape(world, n_qry, n_ref):
+    """q_parts x r_parts = world minimising n_qry/q_parts + n_ref/r_parts (same rule as fpm_dist_grid_shape)."""
+    best, shape = None, (1, world)
+    for q in range(1, world + 1):
+        if world % q:
+            continue
+        cost = n_qry / q + n_ref / (world // q)
+        if best is None or cost < best * (1 - 1e-12):
+            best, shape = cost, (q, world // q)
+    return shape
+
+
+def block_of(rank, world, n_qry, n_ref):
+    """(q_begin, q_end, r_begin, r_end) of the block rank `rank` compares (same rule as fpm_dist_block)."""
+    qp, rp = grid_shape(world, n_qry, n_ref)
+    qi, rj = divmod(rank, rp)
+    return (shard_range(n_qry, qi * rp, world)[0], shard_range(n_qry, (qi + 1) * rp, world)[0],
+            shard_range(n_ref, rj * qp, world)[0], shard_range(n_ref, (rj + 1) * qp, world)[0])
+
+
+def senders_and_receivers(rank, world, n_qry, n_ref):
+    """The exchange step as fpm_dist_sharded_dev performs it.  Returns {"q_send": [...], "r_send": [...], "q_recv": [...],
+    "r_recv": [...]}: ranks this rank sends its query / reference row shard to, and ranks whose shards make up its blocks."""
+    qp, rp = grid_shape(world, n_qry, n_ref)
+    qi, rj = divmod(rank, rp)
+    return {"q_send": [(rank // rp) * rp + d for d in range(rp)], "r_send": [d * rp + rank // qp for d in range(qp)],
+            "q_recv": list(range(qi * rp, (qi + 1) * rp)), "r_recv": list(range(rj * qp, (rj + 1) * qp))}
+
+
+def assemble_blocks(blocks, n_qry, n_ref, dtype):
+    """blocks: iterable of ((q0, q1, r0, r1), array[q1-q0][r1-r0]) -> the full [n_qry][n_ref] query-major matrix."""
+    out = np.zeros((n_qry, n_ref), dtype=dtype)
+    seen = np.zeros((n_qry, n_ref), dtype=bool)
+    for (q0, q1, r0, r1), a in blocks:
+        assert not seen[q0:q1, r0:r1].any(), "blocks overlap"
+        out[q0:q1, r0:r1] = np.asarray(a).reshape(q1 - q0, r1 - r0)
+        seen[q0:q1, r0:r1] = True
+    assert seen.all(), "blocks do not cover the pair space"
+    return out
+
+
+def init_comm(ctx, group=None):
+    """Create ctx's NCCL communicator over the ranks of an initialised torch.distributed group: rank 0's unique id is
+    broadcast as 128 bytes, then every rank calls fpm_comm_init_rank."""
     import torch
     import torch.distributed as dist
+    import fpmash_b200 as fpm
 
-    world = dist.get_world_size(group)
-    bounds = shard_bounds(n_total, world)
-    width = max(hi - lo for lo, hi in bounds)
-    if all(hi - lo == width for lo, hi in bounds):
-        out = torch.empty((n_total,) + tuple(local_rows.shape[1:]), dtype=local_rows.dtype, device=local_rows.device)
-        dist.all_gather_into_tensor(out, local_rows.contiguous(), group=group)
-        return out
-    pad = torch.zeros((width,) + tuple(local_rows.shape[1:]), dtype=local_rows.dtype, device=local_rows.device)
-    pad[:local_rows.shape[0]] = local_rows
-    parts = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(parts, pad, group=group)
-    return torch.cat([p[:hi - lo] for p, (lo, hi) in zip(parts, bounds)], dim=0)
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    on_gpu = dist.get_backend(group) == "nccl"
+    dev = torch.device("cuda", torch.cuda.current_device()) if on_gpu else torch.device("cpu")
+    t = torch.zeros(fpm.COMM_ID_BYTES, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        t = torch.frombuffer(bytearray(fpm.comm_unique_id()), dtype=torch.uint8).to(dev)
+    dist.broadcast(t, src=0, group=group)
+    ctx.comm_init(bytes(t.cpu().numpy().tobytes()), rank, world)
+    return rank, world

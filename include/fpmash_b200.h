@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define FPM_ABI_VERSION 1
+#define FPM_ABI_VERSION 2
 
 typedef enum fpm_status {
     FPM_OK = 0,
@@ -34,7 +34,9 @@ typedef enum fpm_status {
     FPM_ERR_CUDA = -2,        /* a CUDA runtime call failed (message has the CUDA error)    */
     FPM_ERR_ARG = -3,         /* invalid argument                                            */
     FPM_ERR_UNSUPPORTED = -4, /* valid in the reference but outside the accelerated path     */
-    FPM_ERR_NOMEM = -5
+    FPM_ERR_NOMEM = -5,
+    /* -6 is FPM_ERR_CAPACITY (see fpm_dist_hits) */
+    FPM_ERR_COMM = -7         /* NCCL unavailable or a collective failed                      */
 } fpm_status;
 
 typedef struct fpm_ctx fpm_ctx;
@@ -243,6 +245,66 @@ int fpm_dist_hits(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* ref, 
 int fpm_dist_hits_dev(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* d_ref, const fpm_panel* d_qry, fpm_hit* d_out,
                       uint64_t capacity, uint64_t* n_hits, uint64_t* d_merge_steps /* nullable */);
 
+/* ---- several GPUs -------------------------------------------------------- */
+
+/* The reference spreads `mash dist` over its thread pool by cutting the query x reference pair space into chunks
+ * (CommandDistance.cpp:224-261: <= 4096 consecutive pairs each, results consumed in submission order) and `mash sketch`
+ * by handing whole files to pool threads (Sketch.cpp:353-355).  Here the pair space is cut into a q_parts x r_parts
+ * GRID OF BLOCKS, one per GPU (fpm_dist_grid_shape minimises the rows a GPU has to index: 8 GPUs -> 2 x 4), and whole
+ * sketches go to GPUs in contiguous byte-balanced ranges.  Row shard `part` of `parts` of an n-row panel is rows
+ * [n*part/parts, n*(part+1)/parts) (fpm_shard_range); rank = q_index * r_parts + r_index; a query block is the union of
+ * the row shards of its grid row, a reference block the union of q_parts consecutive row shards.                     */
+typedef struct fpm_block {
+    uint64_t q_begin, q_end;  /* query rows of the block                                    */
+    uint64_t r_begin, r_end;  /* reference rows of the block                                */
+} fpm_block;
+void fpm_shard_range(uint64_t n, int part, int parts, uint64_t* begin, uint64_t* end);
+int fpm_dist_grid_shape(int world, uint64_t n_qry, uint64_t n_ref, int* q_parts, int* r_parts);
+int fpm_dist_block(int rank, int world, uint64_t n_qry, uint64_t n_ref, fpm_block* out);
+
+/* One process per GPU: communicator hand-in.  Either adopt an ncclComm_t the host program already has
+ * (never destroyed by this library), or let the library create one: rank 0 obtains an id (ncclGetUniqueId), the host
+ * distributes its FPM_COMM_ID_BYTES bytes by whatever means it has (MPI, torch.distributed, a file), every rank calls
+ * fpm_comm_init_rank -- collectively.  NCCL is loaded with dlopen at that point; FPM_ERR_COMM when it is missing.    */
+#define FPM_COMM_ID_BYTES 128
+int fpm_comm_get_unique_id(void* out_id /* [FPM_COMM_ID_BYTES] */);
+int fpm_comm_init_rank(fpm_ctx* ctx, const void* id, int rank, int world);
+int fpm_comm_adopt(fpm_ctx* ctx, void* nccl_comm, int rank, int world);
+int fpm_comm_destroy(fpm_ctx* ctx);
+int fpm_comm_rank(const fpm_ctx* ctx);               /* -1 without a communicator                */
+int fpm_comm_size(const fpm_ctx* ctx);               /* 0 without a communicator                 */
+
+/* compare() over all ranks (collective; replaces the fan-out of CommandDistance.cpp:224-261).  Every rank passes ITS row
+ * shard of both panels, resident in HBM (d_*_shard->n must equal its fpm_shard_range of n_*_total; the row stride must be
+ * the same on all ranks).  The one exchange step of the path: each shard is sent to exactly the ranks whose block holds
+ * it (grouped ncclSend / ncclRecv over NVLink).  The rank then compares its block (fpm_dist_block) and leaves the result
+ * in d_out_block as a dense [q_end - q_begin][r_end - r_begin] matrix, query-major like fpm_dist_tile: record (q, r) of
+ * the whole comparison is d_out_block[(q - q_begin) * (r_end - r_begin) + (r - r_begin)] on the rank whose block holds
+ * it, bit-identical to the single-GPU result.  out_capacity: room in d_out_block, in records.                        */
+int fpm_dist_sharded_dev(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* d_ref_shard, uint64_t n_ref_total,
+                         const fpm_panel* d_qry_shard, uint64_t n_qry_total, fpm_pair* d_out_block, uint64_t out_capacity,
+                         fpm_block* block, uint64_t* d_merge_steps /* nullable */);
+/* The same in hits mode (fpm_dist_hits_dev): the block's passing pairs, sorted by (query, ref), indices global.        */
+int fpm_dist_hits_sharded_dev(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* d_ref_shard, uint64_t n_ref_total,
+                              const fpm_panel* d_qry_shard, uint64_t n_qry_total, fpm_hit* d_out, uint64_t capacity, uint64_t* n_hits,
+                              fpm_block* block, uint64_t* d_merge_steps /* nullable */);
+
+/* One process driving all GPUs of the box (what `mash dist` and `mash sketch` do): the panels are in host memory, so each
+ * GPU uploads its two blocks and no collective is needed.  One host thread per GPU inside the call; results arrive in
+ * `out` exactly as from the single-GPU entry point (full query-major matrix / hits in the reference's output order).  */
+typedef struct fpm_multi fpm_multi;
+int fpm_multi_create(const int* devices /* nullable: 0..n-1 */, int n_devices /* <= 0: all visible */, fpm_multi** out);
+void fpm_multi_destroy(fpm_multi* m);
+int fpm_multi_size(const fpm_multi* m);
+fpm_ctx* fpm_multi_ctx(fpm_multi* m, int i);
+int fpm_dist_tile_multi(fpm_multi* m, const fpm_dist_params* p, const fpm_panel* ref, const fpm_panel* qry, fpm_pair* out);
+int fpm_dist_hits_multi(fpm_multi* m, const fpm_dist_params* p, const fpm_panel* ref, const fpm_panel* qry, fpm_hit* out,
+                        uint64_t capacity, uint64_t* n_hits);
+/* fpm_sketch_batch with the sketches spread over the GPUs (whole sketches, contiguous ranges balanced by bytes).      */
+int fpm_sketch_batch_multi(fpm_multi* m, const fpm_sketch_params* p, const uint8_t* seq, uint64_t seq_bytes,
+                           const uint64_t* group_offsets, uint32_t n_groups, uint64_t* out_hashes, uint32_t* out_counts,
+                           uint32_t* out_n, uint64_t* out_kmers);
+
 /* Replaces the fork's compareFingerprints (CommandTriangle.cpp:265-302, `mash triangle -fp`): positional
  * matches over the first min(|ref|,|qry|) hashes, distance = 1 - matches/min, p = chi-square(1 dof) upper
  * tail at `matches`.  Only max_distance / max_pvalue of *p are used.  Same output layout as fpm_dist_tile. */
@@ -270,6 +332,7 @@ double fpm_distance(uint64_t common, uint64_t denom, int kmer_size);
 #define FPM_KERNEL_DIST_TILE 2     /* dist_tile32_kernel / dist_tile_kernel                        */
 #define FPM_KERNEL_DIST_LITERAL 3  /* dist_literal_kernel                                          */
 #define FPM_KERNEL_DIST_PACK 4     /* dist_pack_kernel, or the rank pre-pass (keys, sort, scan, scatter) */
+#define FPM_KERNEL_DIST_EXCHANGE 5 /* fpm_dist_sharded_dev: the grouped ncclSend / ncclRecv of the row shards      */
 int fpm_ctx_set_timing(fpm_ctx* ctx, int enable);
 int fpm_ctx_get_timing(fpm_ctx* ctx, int kernel_id, double* out_ms_total, uint64_t* out_launches);
 

@@ -19,6 +19,18 @@ def test_kmer_hash_stream_matches_getHash(ctx, oracle, k, noncanonical):
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("k", list(range(1, 33)))
+def test_production_kernel_hashes_every_window_like_getHash(ctx, oracle, k):
+    """The sketch kernel itself (table-driven Murmur, lazy finish, threshold filter) with a sketch larger than the
+    number of windows: the sketch then IS the set of all window hashes with their multiplicities."""
+    rng = np.random.default_rng(3000 + k)
+    recs = [dirty_dna(rng, 6000, n_rate=0.002), random_dna(rng, 2500)]
+    for noncanonical in (False, True):
+        got = ctx.sketch_records([recs], k=k, s=20000, noncanonical=noncanonical, want_counts=True)[0]
+        want = oracle.sketch(recs, k=k, s=20000, noncanonical=noncanonical)
+        assert np.array_equal(got["hashes"], want["hashes"]) and np.array_equal(got["counts"], want["counts"])
+
+
 def test_kmer_hash_preserve_case_and_seed(ctx, oracle):
     rng = np.random.default_rng(7)
     rec = dirty_dna(rng, 5000, lower_rate=0.3)

@@ -154,7 +154,7 @@ def test_c_abi_exports_every_declared_symbol(fpm):
     for sym in declared:
         assert hasattr(lib, sym), "declared in include/fpmash_b200.h but not exported: " + sym
     assert declared == set(fpm.EXPORTED)
-    assert fpm.lib.fpm_abi_version() == 1
+    assert fpm.lib.fpm_abi_version() == 2
 
 
 def test_no_gpu_fails_loudly(fpm):
@@ -216,52 +216,113 @@ def test_pvalue_and_distance_match_oracle(fpm, oracle):
         assert fpm.distance(c, d, 21) == pytest.approx(want, rel=1e-15, abs=0)
 
 
-# ---- multi-GPU plumbing on CPU: gloo, world_size 2 ---------------------------------------------
-def test_shard_helpers():
-    from fpmash_b200.sharding import assign_by_size, shard_bounds
-    for n in (0, 1, 7, 20000):
-        for w in (1, 2, 3, 8):
-            b = shard_bounds(n, w)
-            assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(w - 1))
-            assert max(h - l for l, h in b) - min(h - l for l, h in b) <= 1
-    parts = assign_by_size([5, 1, 9, 3, 3, 7], 2)
+# ---- multi-GPU plumbing on CPU: the grid rules of the library, and the exchange step under gloo -------------------------
+def test_grid_and_shard_rules_agree_with_the_library(fpm):
+    """fpm_shard_range / fpm_dist_grid_shape / fpm_dist_block (C, no GPU needed) == the host helpers; the blocks of a grid
+    tile the pair space exactly once; every row shard reaches exactly the ranks whose block contains it."""
+    from fpmash_b200 import sharding as sh
+    parts = sh.assign_by_size([5, 1, 9, 3, 3, 7], 2)
     assert sorted(sum(parts, [])) == list(range(6)) and all(p == sorted(p) for p in parts)
     loads = [sum([5, 1, 9, 3, 3, 7][i] for i in p) for p in parts]
     assert abs(loads[0] - loads[1]) <= 2
+    for world in (1, 2, 3, 4, 6, 8):
+        for n_q, n_r in ((20000, 20000), (100000, 10000), (7, 5), (1, 64), (0, 9), (1000, 3)):
+            assert fpm.dist_grid_shape(world, n_q, n_r) == sh.grid_shape(world, n_q, n_r)
+            qp, rp = sh.grid_shape(world, n_q, n_r)
+            assert qp * rp == world
+            cover = np.zeros((n_q, n_r), dtype=np.int32) if n_q * n_r <= 10**6 else None
+            for rank in range(world):
+                assert fpm.shard_range(n_q, rank, world) == sh.shard_range(n_q, rank, world)
+                blk = sh.block_of(rank, world, n_q, n_r)
+                assert fpm.dist_block(rank, world, n_q, n_r) == blk
+                if cover is not None:
+                    cover[blk[0]:blk[1], blk[2]:blk[3]] += 1
+                ex = sh.senders_and_receivers(rank, world, n_q, n_r)
+                # my block's rows are exactly the shards I receive
+                assert blk[0] == sh.shard_range(n_q, ex["q_recv"][0], world)[0] and blk[1] == sh.shard_range(n_q, ex["q_recv"][-1], world)[1]
+                assert blk[2] == sh.shard_range(n_r, ex["r_recv"][0], world)[0] and blk[3] == sh.shard_range(n_r, ex["r_recv"][-1], world)[1]
+                # and every rank I send to expects me
+                for d in ex["q_send"]:
+                    assert rank in sh.senders_and_receivers(d, world, n_q, n_r)["q_recv"]
+                for d in ex["r_send"]:
+                    assert rank in sh.senders_and_receivers(d, world, n_q, n_r)["r_recv"]
+            if cover is not None:
+                assert (cover == 1).all()
+    # 8 GPUs, all-vs-all: 2 x 4 -- a GPU indexes 3/4 of a panel's rows instead of 9/8 with row sharding
+    assert sh.grid_shape(8, 20000, 20000) in ((2, 4), (4, 2))
 
 
 WORKER = r"""
 import os, sys
 sys.path.insert(0, os.path.join(%(root)r, "fp-mash_b200", "py"))
+sys.path.insert(0, os.path.join(%(root)r, "oracle"))
 import numpy as np, torch, torch.distributed as dist
-from fpmash_b200.sharding import shard_range, all_gather_rows
-dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%(port)d", rank=int(sys.argv[1]), world_size=2)
+from fpmash_b200 import sharding as sh
+from oracle_py import Oracle
+world = %(world)d
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%(port)d", rank=int(sys.argv[1]), world_size=world)
 rank = dist.get_rank()
-for n in (10, 7):                       # even and uneven shards
-    full = torch.arange(n * 4, dtype=torch.int64).reshape(n, 4) * 3 + 1
-    lo, hi = shard_range(n, rank, 2)
-    got = all_gather_rows(full[lo:hi].clone(), n)
-    assert torch.equal(got, full), (rank, n)
-    # dist sharding: this rank compares its query rows against the gathered panel; the union of
-    # the ranks' rows must be the whole query-major matrix
-    mine = torch.full((n,), -1, dtype=torch.int64); mine[lo:hi] = rank
-    dist.all_reduce(mine, op=dist.ReduceOp.MAX)
-    assert (mine >= 0).all()
+orc = Oracle()
+rng = np.random.default_rng(5)
+n_q, n_r, s = 11, 9, 40
+pool = rng.choice(1 << 20, size=400, replace=False).astype(np.uint64)
+def panel(n):
+    return np.stack([np.sort(rng.choice(pool, size=s, replace=False)) for _ in range(n)])
+Q, R = panel(n_q), panel(n_r)                       # same seed on every rank: each rank then keeps only ITS row shard
+q0, q1 = sh.shard_range(n_q, rank, world); r0, r1 = sh.shard_range(n_r, rank, world)
+my_q, my_r = torch.from_numpy(Q[q0:q1].astype(np.int64)), torch.from_numpy(R[r0:r1].astype(np.int64))
+# the exchange step exactly as fpm_dist_sharded_dev performs it (grouped send/recv; gloo instead of NCCL)
+ex = sh.senders_and_receivers(rank, world, n_q, n_r)
+blk = sh.block_of(rank, world, n_q, n_r)
+bq = torch.zeros((blk[1] - blk[0], s), dtype=torch.int64); br = torch.zeros((blk[3] - blk[2], s), dtype=torch.int64)
+ops = []
+for role, mine, sends, recvs, out, base, n in (("q", my_q, ex["q_send"], ex["q_recv"], bq, blk[0], n_q), ("r", my_r, ex["r_send"], ex["r_recv"], br, blk[2], n_r)):
+    for d in sends:
+        if d != rank and mine.shape[0]:
+            ops.append(dist.P2POp(dist.isend, mine.contiguous(), d))
+    for src in recvs:
+        a, b = sh.shard_range(n, src, world)
+        if a == b:
+            continue
+        if src == rank:
+            out[a - base:b - base] = mine
+        else:
+            ops.append(dist.P2POp(dist.irecv, out[a - base:b - base], src))
+if ops:
+    for w in dist.batch_isend_irecv(ops):
+        w.wait()
+assert np.array_equal(bq.numpy().astype(np.uint64), Q[blk[0]:blk[1]]) and np.array_equal(br.numpy().astype(np.uint64), R[blk[2]:blk[3]])
+# each rank compares its block; gathered blocks == the reference's query-major table
+mine = np.zeros((blk[1] - blk[0], blk[3] - blk[2]), dtype=np.int64)
+for i in range(mine.shape[0]):
+    for j in range(mine.shape[1]):
+        c = orc.compare(br.numpy().astype(np.uint64)[j], bq.numpy().astype(np.uint64)[i], 1000, 1000, s, 21, 4.0 ** 21)
+        mine[i, j] = c["numer"] * 1000 + c["denom"]
+gathered = [None] * world
+dist.all_gather_object(gathered, (blk, mine))
+full = sh.assemble_blocks(gathered, n_q, n_r, np.int64)
+for q in range(n_q):
+    for r in range(n_r):
+        c = orc.compare(R[r], Q[q], 1000, 1000, s, 21, 4.0 ** 21)
+        assert full[q, r] == c["numer"] * 1000 + c["denom"], (q, r)
 dist.barrier()
 dist.destroy_process_group()
 print("ok", rank)
 """
 
 
-def test_all_gather_rows_gloo_world2(tmp_path):
+@pytest.mark.parametrize("world", [2, 4])
+def test_block_exchange_gloo(tmp_path, world):
+    """world_size 2 and 4 on CPU (gloo): row shards -> blocks by the library's send/receive lists, blocks compared by the
+    oracle, gathered blocks == the single-process query-major table."""
     import socket
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
     script = tmp_path / "w.py"
-    script.write_text(WORKER % {"root": ROOT, "port": port})
-    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for r in range(2)]
+    script.write_text(WORKER % {"root": ROOT, "port": port, "world": world})
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for r in range(world)]
     for p in procs:
         out, err = p.communicate(timeout=240)
         assert p.returncode == 0 and "ok" in out, err[-2000:]
