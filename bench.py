@@ -4,9 +4,13 @@
 Metric (BASELINE.json): Gk-mers/sec sketched; sketch-pairs/sec dist.
 Workload at N GPUs: configs[1] "mash sketch k=21 s=1000 canonical over 1,000 synthetic 5 Mbp
 bacterial-size genomes" PER GPU (sketching shards by input file, no collective: weak scaling),
-plus -- reported in the same JSON line under "dist" -- configs[2] "all-vs-all mash dist of
-20,000 sketches (k=21 s=1000)", queries row-sharded over the ranks with an NCCL all-gather of
-the reference panel (strong scaling: the 4e8 pairs are fixed).
+plus -- reported in the same JSON line under "dist" and, compactly, as the LAST key "dist_summary" --
+configs[2] "all-vs-all mash dist of 20,000 sketches (k=21 s=1000)" cut into query x reference blocks over
+the ranks by the library itself (fpm_dist_sharded_dev: grouped ncclSend/ncclRecv of the row shards, then
+every rank compares its block; strong scaling: the 4e8 pairs are fixed), and under "configs" the other
+BASELINE configs at their named sizes (C1 fp mode, C4 read set with -m 2, C5 k=32 s=10000).
+Parity is checked inside the run: CPU-reference sketches == GPU sketches, CPU-reference dist rows == the
+device-path output, pruned == merge-all, and several GPUs == one GPU (digests + rank 0's block byte for byte).
 
 A "step" = one pass of the hot path over one batch: fpm_sketch_batch_dev over all genomes of the
 rank (value, inputs resident in HBM) / fpm_sketch_batch with pinned HOST buffers (e2e, H2D and
@@ -36,7 +40,7 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 K = 21
 S = 1000
 W_INT32_OPS = {21: 74, 32: 96, 16: 64}   # int32-op equivalents of Murmur per k-mer
-NCU_SKETCH_TRAFFIC_RATIO = (315.19 + 16.98) / 300.0   # DRAM bytes per algorithmic byte, ncu capture of sketch_hash_kernel_v2 (profiles/r01_sketch_hash_v4.txt)
+NCU_SKETCH_TRAFFIC_RATIO = (525.96 + 32.02) / 500.0005   # DRAM bytes per algorithmic byte, ncu --set full capture of sketch_hash_kernel_v2<21,true> (profiles/r02_sketch_hash_v2.txt: 100 x 5 Mbp launch)
 NCU_DIST_TRAFFIC_RATIO = (27.22 + 193.05) / (3200 * 3200 * 24 / 1e6 + 2 * 3200 * 1001 * 4 / 1e6)   # same for dist_tile32_kernel (profiles/r01_dist_tile32_v4.txt)
 IMAD_WIDE_RATE = 8.99 / 18.45         # IMAD.WIDE issue rate relative to IMAD, measured (profiles/ubench/int_mix.cu: 8.99 vs 18.45 T/s)
 SMEM_BYTES_PER_CLK_PER_SM = 128        # one 32-lane x 4-byte wavefront per clock (B300_MICROARCH.md / measured LSU pipe limit)
@@ -54,6 +58,10 @@ def parse_args():
     ap.add_argument("--cpu-genomes", type=int, default=512, help="genomes in the CPU-baseline sample (512 x 5 Mbp = ~2.2 s on 16 cores per pass)")
     ap.add_argument("--cpu-dist-queries", type=int, default=256, help="query rows in the CPU dist sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-configs", action="store_true", help="skip the compact C1 / C4 / C5 measurements")
+    ap.add_argument("--c5-queries", type=int, default=100000, help="C5 dist: query sketches (config: 100000); 0 skips C5 dist")
+    ap.add_argument("--c5-refs", type=int, default=10000, help="C5 dist: reference sketches (config: 10000)")
+    ap.add_argument("--c5-merge-all", type=int, default=1, help="C5 dist: also time the same call with every pair merged (1e13 merge steps, a few seconds)")
     return ap.parse_args()
 
 
@@ -219,9 +227,11 @@ def run_reference(args):
         "unit": "Gk-mers/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total_t / len(vals), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic",
+        # the same config object as our arm prints (the bounded sample is described in cpu_baseline.sample)
         "config": {"workload": "mash sketch -k 21 -s 1000 canonical over %d synthetic %.1f Mbp genomes per GPU (BASELINE configs[1])" % (args.genomes, args.genome_len / 1e6),
                    "genomes_per_gpu": args.genomes, "genome_len": args.genome_len, "k": K, "sketch_size": S, "seed": 42,
-                   "cpu_sample_genomes_per_step": n},
+                   "l2": "inputs (%.1f GB per GPU) exceed the 126 MB L2; no flush needed" % (args.genomes * (args.genome_len + 1) / 1e9),
+                   "parallelism": "files sharded over %d GPU(s), no collective" % int(os.environ.get("WORLD_SIZE", "1"))},
         "cpu_baseline": {"value": value, "unit": "Gk-mers/s", "cores": threads, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": "Gk-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -232,6 +242,42 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------
+def gen_panel_rows(torch, row0, row1, s, device, seed, n_clusters, shared=0.6, chunk=500, core_seed=None):
+    """Rows [row0, row1) of a clustered panel of sorted duplicate-free u64 sketches (same construction as gen_sketch_panel),
+    generated chunk by chunk with per-chunk seeds so that every rank can produce exactly its own rows."""
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed if core_seed is None else core_seed)     # panels built on the same cores are related cluster by cluster
+    hi = int((1 << 64) * s / 4_999_980)
+    big = 1 << 62
+    cores = torch.randint(0, hi, (n_clusters, 2 * s), generator=gen, device=device, dtype=torch.int64)
+    out = torch.empty((row1 - row0, s), dtype=torch.int64, device=device)
+    for c in range(row0 // chunk, (row1 + chunk - 1) // chunk):
+        i0, i1 = c * chunk, (c + 1) * chunk
+        gen.manual_seed(seed * 1_000_003 + c)
+        m = i1 - i0
+        core = cores[torch.arange(i0, i1, device=device) % n_clusters]
+        keep = torch.rand((m, 2 * s), generator=gen, device=device) < shared
+        core = torch.where(keep, core, torch.full_like(core, big))
+        cand, _ = torch.sort(torch.cat([core, torch.randint(0, hi, (m, s), generator=gen, device=device, dtype=torch.int64)], dim=1), dim=1)
+        dup = torch.zeros_like(cand, dtype=torch.bool)
+        dup[:, 1:] = cand[:, 1:] == cand[:, :-1]
+        cand, _ = torch.sort(torch.where(dup, torch.full_like(cand, big), cand), dim=1)
+        lo, hi_r = max(i0, row0), min(i1, row1)
+        out[lo - row0:hi_r - row0] = cand[lo - i0:hi_r - i0, :s]
+        del core, keep, cand, dup
+    return out
+
+
+def pair_digest(torch, out_u8, n_pairs):
+    """Order-independent digest of fpm_pair records in HBM: wrap-around int64 sums of numer, denom (without the pass flag),
+    the distance bit patterns and the p-value bit patterns.  Sums over blocks add up to the sum over the whole matrix."""
+    if n_pairs == 0:
+        return torch.zeros(4, dtype=torch.int64, device=out_u8.device)
+    w = out_u8[:n_pairs * 24].view(torch.int32).view(n_pairs, 6)
+    d = out_u8[:n_pairs * 24].view(torch.int64).view(n_pairs, 3)
+    return torch.stack([w[:, 0].sum(dtype=torch.int64), (w[:, 1] & 0x7fffffff).sum(dtype=torch.int64), d[:, 1].sum(), d[:, 2].sum()])
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -241,6 +287,7 @@ def main():
     import torch
     import torch.distributed as dist
     import fpmash_b200 as fpm
+    from fpmash_b200 import sharding
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -269,9 +316,17 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def sum_over_ranks(t):
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t
+
     ctx = fpm.Context(local_rank)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    if world > 1:
+        sharding.init_comm(ctx)            # the library's own NCCL communicator (unique id of rank 0 broadcast over torch.distributed)
     params = fpm.make_sketch_params(k=K, s=S, seed=42)
+    threads = os.cpu_count() or 1
 
     # ---- sketch: value (HBM resident) --------------------------------------------------------
     n, L = args.genomes, args.genome_len
@@ -322,11 +377,12 @@ def main():
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * windows_per_step * args.steps / e2e_s / 1e9
     clocks = sampler.stop() if rank == 0 else None   # sampled across the resident and the end-to-end timed regions
-    assert np.array_equal(e2e_res["hashes"], out_h.cpu().numpy().view(np.uint64)), "e2e and resident sketches differ"
+    gpu_sketches = out_h.cpu().numpy().view(np.uint64)
+    assert np.array_equal(e2e_res["hashes"], gpu_sketches), "e2e and resident sketches differ"
     h2d = int(seq.numel() + offsets.nbytes)
     d2h = int(n * S * 8 + n * 4)
 
-    # ---- roofline of the dominant kernel -----------------------------------------------------
+    # ---- rooflines of the dominant kernel ------------------------------------------------------
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -334,7 +390,7 @@ def main():
     except OSError:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    hbm_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    hbm_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     hash_ms_avg = hash_ms / max(hash_n, 1)
     alg_bytes = float(seq.numel())                                    # 1 B per base read once
     achieved_gbs = alg_bytes / (hash_ms_avg * 1e-3) / 1e9
@@ -342,34 +398,56 @@ def main():
     int_peaks = ctx.int32_peaks()                     # ALU pipe only, FMA pipe (IMAD) only, alternating
     int_ops = windows_per_step * W_INT32_OPS[K]
     int_achieved = int_ops / (hash_ms_avg * 1e-3)
+    n_sm = torch.cuda.get_device_properties(device).multi_processor_count
 
-    # ---- dist (configs[2]) -------------------------------------------------------------------
-    dist_obj = None
+    # ---- CPU baseline (rank 0, N=1 only): the reference's own TUs on a bounded sample, outputs compared with the GPU's ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle_py import RefLib
+        cg = min(args.cpu_genomes, n)
+        if not RefLib.available():
+            from oracle_py import build
+            build(ref=True)
+        if RefLib.available():
+            stride = L + 1
+            sample = np.array(host_seq[:cg * stride], copy=True)          # the reference upper-cases in place
+            soff = np.arange(cg + 1, dtype=np.uint64) * np.uint64(stride)
+            t0 = time.perf_counter()
+            ch, _, cn = RefLib().sketch_batch(sample, soff, K, S, seed=42, use64=True, threads=threads)
+            dt = time.perf_counter() - t0
+            cpu = {"value": cg * (L - K + 1) / dt / 1e9, "unit": "Gk-mers/s", "cores": threads, "kind": "reference",
+                   "sample": "%d of %d genomes (%d Mbp), reference TUs hash.cpp/MurmurHash3.cpp/MinHashHeap.cpp + restated sketchFile loop, -p %d, %.1f s" % (cg, n, cg * L // 1_000_000, threads, dt),
+                   "matches_gpu": bool(np.array_equal(ch, gpu_sketches[:cg]) and (cn == S).all())}
+            del sample
+    del pinned_seq, host_seq, e2e_res
+
+    # ---- dist (configs[2]): all-vs-all of nd sketches, query x reference blocks over the ranks (library call) -------------
+    dist_obj, dist_summary = None, None
+    kspace = 4.0 ** K
     if args.dist_sketches > 0:
         nd = args.dist_sketches
         panel = gen_sketch_panel(torch, nd, S, device, seed=3)
         sizes = torch.full((nd,), S, dtype=torch.int32, device=device)
         lengths = torch.full((nd,), 5_000_000, dtype=torch.int64, device=device)
-        q0, q1 = rank * nd // world, (rank + 1) * nd // world
-        r0, r1 = q0, q1                                            # this rank's shard of the reference panel
-        ref_full = torch.empty_like(panel) if world > 1 else panel
-        out_pairs = torch.empty(((q1 - q0) * nd * 24,), dtype=torch.uint8, device=device)
+        s0, s1 = sharding.shard_range(nd, rank, world)                  # this rank's row shard of the panel (queries = references)
+        blk = sharding.block_of(rank, world, nd, nd)
+        blk_pairs = (blk[1] - blk[0]) * (blk[3] - blk[2])
+        out_pairs = torch.empty((max(blk_pairs, 1) * 24,), dtype=torch.uint8, device=device)
         steps_ctr = torch.zeros(1, dtype=torch.int64, device=device)
-        kspace = 4.0 ** K
+        shard = (panel[s0:s1].data_ptr(), sizes[s0:s1].data_ptr(), lengths[s0:s1].data_ptr(), s1 - s0, S)
+        full_ptrs = (panel.data_ptr(), sizes.data_ptr(), lengths.data_ptr(), nd, S)
 
         def step_dist():
-            if world > 1:   # the one exchange step of the path: all-gather the reference panel over NVLink
-                dist.all_gather_into_tensor(ref_full, panel[r0:r1].contiguous())
-            ctx.dist_tile_dev((ref_full.data_ptr(), sizes.data_ptr(), lengths.data_ptr(), nd, S),
-                              (panel[q0:q1].data_ptr(), sizes[q0:q1].data_ptr(), lengths[q0:q1].data_ptr(), q1 - q0, S),
-                              S, K, kspace, out_pairs.data_ptr(), steps_ctr.data_ptr())
+            if world > 1:   # exchange step (row shards -> blocks, grouped ncclSend/ncclRecv) + this rank's block, one library call
+                ctx.dist_sharded_dev(shard, nd, shard, nd, S, K, kspace, out_pairs.data_ptr(), blk_pairs, steps_ctr.data_ptr())
+            else:
+                ctx.dist_tile_dev(full_ptrs, full_ptrs, S, K, kspace, out_pairs.data_ptr(), steps_ctr.data_ptr())
 
-        dsteps = max(2, min(args.steps, 3))
+        dsteps = max(3, min(args.steps, 10))
         pairs = nd * nd
-        n_sm = torch.cuda.get_device_properties(device).multi_processor_count
 
         def timed_dist(**mode):
-            """dsteps timed passes of the sharded all-vs-all dist in the given kernel mode."""
+            """dsteps timed passes of the all-vs-all dist in the given kernel mode."""
             ctx.set_dist_mode(**mode)
             try:
                 for _ in range(2):
@@ -387,103 +465,98 @@ def main():
                 tile_ms, tile_n = ctx.get_timing(fpm.KERNEL_DIST_TILE)
                 lit_ms, lit_n = ctx.get_timing(fpm.KERNEL_DIST_LITERAL)
                 pack_ms, pack_n = ctx.get_timing(fpm.KERNEL_DIST_PACK)
+                ex_ms, ex_n = ctx.get_timing(fpm.KERNEL_DIST_EXCHANGE)
                 ctx.set_timing(False)
-                return {"ms": ms, "tile_avg": tile_ms / max(tile_n, 1), "tile_n": tile_n, "lit_n": lit_n, "pack_avg": pack_ms / max(pack_n, 1),
-                        "merge_steps": int(steps_ctr.item()) / dsteps, "launches": ctx.launch_count() - l0}
+                st = sum_over_ranks(steps_ctr.clone())
+                return {"ms": ms, "tile": max_over_ranks(tile_ms / dsteps), "tile_n": tile_n, "lit_n": lit_n, "pack": max_over_ranks(pack_ms / dsteps),
+                        "exchange": max_over_ranks(ex_ms / dsteps), "merge_steps": int(st.item()) / dsteps, "launches": ctx.launch_count() - l0,
+                        "digest": [int(x) for x in sum_over_ranks(pair_digest(torch, out_pairs, blk_pairs)).tolist()]}
             finally:
                 ctx.set_dist_mode()
 
         full = timed_dist(no_prune=True)        # every pair merged: the merge kernel's own throughput and rooflines
         run = timed_dist()                      # the product path: pairs without a shared hash are answered without a merge
-        d_ms, tile_avg, merge_steps = run["ms"], run["tile_avg"], run["merge_steps"]
-        out_bytes = (q1 - q0) * nd * 24 + 2 * nd * (S + 1) * 4
+        # parity inside the bench: (1) pruned == merge-all, (2) several GPUs == one GPU (rank 0 recomputes the whole matrix alone)
+        parity = {"pruned_equals_merge_all": run["digest"] == full["digest"]}
+        if world > 1:
+            ok = torch.ones(1, dtype=torch.int64, device=device)
+            if rank == 0:
+                alone = torch.empty((pairs * 24,), dtype=torch.uint8, device=device)
+                ctx.dist_tile_dev(full_ptrs, full_ptrs, S, K, kspace, alone.data_ptr(), None)
+                torch.cuda.synchronize()
+                ok[0] = int([int(x) for x in pair_digest(torch, alone, pairs).tolist()] == run["digest"])
+                # and record for record on this rank's own block
+                mine = alone.view(pairs, 24).view(nd, nd, 24)[blk[0]:blk[1], blk[2]:blk[3]].reshape(-1)
+                ok[0] &= int(torch.equal(mine, out_pairs[:blk_pairs * 24]))
+                del alone, mine
+            dist.broadcast(ok, src=0)
+            parity["sharded_equals_single_gpu"] = bool(ok.item())
+        d_ms = run["ms"]
+        smem_peak = n_sm * SMEM_BYTES_PER_CLK_PER_SM * 1.965e9
+        qp, rp = sharding.grid_shape(world, nd, nd)
         dist_obj = {
-            "metric": "sketch-pairs/sec dist (all-vs-all, k=21 s=1000)", "value": pairs / (d_ms * 1e-3), "unit": "pairs/s",
-            "ms_per_step": d_ms, "steps": dsteps, "scaling": "strong",
-            "config": {"workload": "all-vs-all mash dist of %d sketches (BASELINE configs[2])" % nd, "sketches": nd,
-                       "sketch_size": S, "k": K, "sharding": "query rows over ranks, NCCL all-gather of the reference panel" if world > 1 else "single GPU"},
-            "gpu_launches": run["launches"], "fast_path_launches": run["tile_n"], "literal_launches": run["lit_n"],
-            "merge_steps_per_pair": merge_steps / ((q1 - q0) * nd),
-            "kernel_ms": {"dist_tile32": tile_avg, "rank_compress_index_mark": run["pack_avg"]},
-            "pruning": "exact: the rank pre-pass sorts every hash of both panels, which is also an inverted index; a pair whose sketches share no hash has common = 0 and denom = min(s, |A|+|B|) and is answered without a merge; related sketches are grouped into the same tiles; merge_steps_per_pair counts executed steps only; merge_all_pairs below is the same call with every pair merged",
-            "roofline": {"bound": "hbm", "achieved": out_bytes / (tile_avg * 1e-3) / 1e9 if run["tile_n"] else None, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": out_bytes / (tile_avg * 1e-3) / 1e9 / hbm_peak if run["tile_n"] else None, "traffic": None,
-                         "note": "dist_fill_unshared_kernel + dist_tile32_kernel of the pruned run (both inside kernel_ms.dist_tile32): 24 B per pair streamed in matrix order for the pairs without a shared hash, merged pairs overwritten at their original positions, rank panels read once"},
-            "merge_all_pairs": {
-                "value": pairs / (full["ms"] * 1e-3), "unit": "pairs/s", "ms_per_step": full["ms"], "merge_steps_per_pair": full["merge_steps"] / ((q1 - q0) * nd),
-                "kernel_ms": {"dist_tile32": full["tile_avg"], "rank_compress": full["pack_avg"]},
-                "roofline_int": {"bound": "int32-alu", "achieved": full["merge_steps"] * 3 / (full["tile_avg"] * 1e-3) / 1e12, "peak": int_peak / 1e12, "unit": "Tint32-op/s",
-                                 "frac": (full["merge_steps"] * 3 / (full["tile_avg"] * 1e-3)) / int_peak,
-                                 "note": "algorithmic ops = merge steps x 3 (SURVEY.md 8d) / dist_tile32_kernel time; peak measured by fpm_measure_int32_peak"},
-                "roofline_smem": {"bound": "shared-memory bandwidth", "achieved": full["merge_steps"] * 8 / (full["tile_avg"] * 1e-3) / 1e12,
-                                  "peak": n_sm * SMEM_BYTES_PER_CLK_PER_SM * 1.965e9 / 1e12, "unit": "TB/s",
-                                  "frac": (full["merge_steps"] * 8 / (full["tile_avg"] * 1e-3)) / (n_sm * SMEM_BYTES_PER_CLK_PER_SM * 1.965e9),
-                                  "note": "what bounds the merge: every step is two 4-byte shared-memory loads per pair (one LDS.32 wavefront per list per warp); peak = SMs x 128 B/clk x 1965 MHz; ncu: shared-memory pipe 87 % busy incl. staging"},
-                "roofline": {"bound": "hbm", "achieved": out_bytes / (full["tile_avg"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": out_bytes / (full["tile_avg"] * 1e-3) / 1e9 / hbm_peak,
-                             "traffic": out_bytes * NCU_DIST_TRAFFIC_RATIO,
-                             "traffic_note": "dram bytes of one ncu --set full capture of dist_tile32_kernel (profiles/r01_dist_tile32_v4.txt) scaled to this launch; below the algorithmic bytes because part of the output was still in L2 when the capture ended"},
-            },
+            "metric": "sketch-pairs/sec dist (all-vs-all, k=21 s=1000)", "value": pairs / (d_ms * 1e-3), "unit": "pairs/s", "ms_per_step": d_ms, "steps": dsteps,
+            "scaling": "strong", "workload": "all-vs-all mash dist of %d sketches (BASELINE configs[2])" % nd,
+            "sharding": "%d x %d blocks of query x reference rows over the ranks (fpm_dist_sharded_dev)" % (qp, rp) if world > 1 else "single GPU",
+            "gpu_launches": run["launches"], "literal_launches": run["lit_n"], "merge_steps_per_pair": run["merge_steps"] / pairs,
+            "kernel_ms": {"exchange": run["exchange"], "prepass": run["pack"], "fill+tiles": run["tile"]},
+            "merge_all_pairs": {"value": pairs / (full["ms"] * 1e-3), "ms_per_step": full["ms"], "merge_steps_per_pair": full["merge_steps"] / pairs,
+                                "kernel_ms": {"exchange": full["exchange"], "prepass": full["pack"], "tiles": full["tile"]},
+                                "roofline_smem": {"achieved": full["merge_steps"] / world * 8 / (full["tile"] * 1e-3) / 1e12, "peak": smem_peak / 1e12, "unit": "TB/s",
+                                                  "frac": full["merge_steps"] / world * 8 / (full["tile"] * 1e-3) / smem_peak},
+                                "roofline_int": {"frac": full["merge_steps"] / world * 3 / (full["tile"] * 1e-3) / int_peak}},
+            "parity": parity, "digest": run["digest"],
         }
-        # e2e on a stated sample of query rows (host panels in, 24-byte records out)
-        if rank == 0:
-            qs = min(nd, 8192)
+        # e2e on a stated sample of query rows (host panels in, 24-byte records out), and the CPU reference on a sample of the DEVICE output
+        if rank == 0 and world == 1:
+            qs_n = min(nd, 8192)
             hp = panel.cpu().numpy().view(np.uint64)
             hs = np.full(nd, S, dtype=np.uint32)
             hl = np.full(nd, 5_000_000, dtype=np.uint64)
-            pinned = torch.empty(qs * nd * 24, dtype=torch.uint8, pin_memory=True).numpy().view(fpm.PAIR_DTYPE).reshape(qs, nd)
-            ctx.dist_tile((hp, hs, hl), (hp[:qs], hs[:qs], hl[:qs]), S, K, kspace, out=pinned, raw=True)
+            pinned = torch.empty(qs_n * nd * 24, dtype=torch.uint8, pin_memory=True).numpy().view(fpm.PAIR_DTYPE).reshape(qs_n, nd)
+            ctx.dist_tile((hp, hs, hl), (hp[:qs_n], hs[:qs_n], hl[:qs_n]), S, K, kspace, out=pinned, raw=True)
             t0 = time.perf_counter()
-            got, _ = ctx.dist_tile((hp, hs, hl), (hp[:qs], hs[:qs], hl[:qs]), S, K, kspace, out=pinned, raw=True)
+            got, _ = ctx.dist_tile((hp, hs, hl), (hp[:qs_n], hs[:qs_n], hl[:qs_n]), S, K, kspace, out=pinned, raw=True)
             dt = time.perf_counter() - t0
-            dist_obj["e2e"] = {"value": qs * nd / dt, "unit": "pairs/s", "sample": "%d query rows x %d refs, one GPU" % (qs, nd),
-                               "h2d_bytes_per_step": int((nd + qs) * (S * 8 + 12)), "d2h_bytes_per_step": int(qs * nd * 24)}
-            # the same through `mash dist -d 0.25` semantics: every pair of the full all-vs-all is decided on the GPU, only the
-            # passing ones come back (fpm_dist_hits) -- host panels in, sorted hit records out
+            dist_obj["e2e"] = {"value": qs_n * nd / dt, "unit": "pairs/s", "sample": "%d query rows x %d refs" % (qs_n, nd),
+                               "h2d_bytes_per_step": int((nd + qs_n) * (S * 8 + 12)), "d2h_bytes_per_step": int(qs_n * nd * 24)}
             cap = 64 << 20
             hit_buf = torch.empty(cap * 32, dtype=torch.uint8, pin_memory=True).numpy().view(fpm.HIT_DTYPE)
             try:
                 php = panel.cpu().pin_memory().numpy().view(np.uint64)     # pinned host panels, as a caller that cares would hold them
                 ctx.dist_hits((php, hs, hl), (php, hs, hl), S, K, kspace, max_distance=0.25, out=hit_buf, raw=True)
-                ctx.set_timing(True)
                 t0 = time.perf_counter()
                 hits = ctx.dist_hits((php, hs, hl), (php, hs, hl), S, K, kspace, max_distance=0.25, out=hit_buf, raw=True)
                 dt = time.perf_counter() - t0
-                f_tile, f_pack = ctx.get_timing(fpm.KERNEL_DIST_TILE)[0], ctx.get_timing(fpm.KERNEL_DIST_PACK)[0]
-                ctx.set_timing(False)
-                sub = hits[hits["query"] < qs]
-                same = bool(np.array_equal(np.nonzero(got["distance"] <= 0.25)[1], sub["ref"]) and
-                            np.array_equal(got["numer"][got["distance"] <= 0.25], sub["numer"]))
+                sub = hits[hits["query"] < qs_n]
+                same = bool(np.array_equal(np.nonzero(got["distance"] <= 0.25)[1], sub["ref"]) and np.array_equal(got["numer"][got["distance"] <= 0.25], sub["numer"]))
                 dist_obj["e2e_filtered"] = {"value": nd * nd / dt, "unit": "pairs/s", "filter": "-d 0.25", "hits": int(len(hits)), "seconds": dt,
-                                            "kernel_ms": {"dist_tile32": f_tile, "rank_compress_index_mark": f_pack},
-                                            "sample": "all %d x %d pairs, one GPU, one call" % (nd, nd), "h2d_bytes_per_step": int(2 * nd * (S * 8 + 12)),
                                             "d2h_bytes_per_step": int(len(hits) * 32), "agrees_with_matrix_rows": same}
             except fpm.FpmError as e:
                 dist_obj["e2e_filtered"] = {"error": str(e)}
             del hit_buf
-            if not args.no_cpu and world == 1:
+            if not args.no_cpu:
                 from oracle_py import RefLib
                 if RefLib.available():
                     cq = min(args.cpu_dist_queries, nd)
-                    threads = os.cpu_count() or 1
+                    rows = np.linspace(0, nd - 1, cq).astype(np.int64)          # spread over the clusters and the grouped tile order
                     t0 = time.perf_counter()
-                    cn, cd, cdist = RefLib().dist_batch(hp, hs, hp[:cq], hs[:cq], S, K, threads=threads)
+                    cn, cd, cdist = RefLib().dist_batch(hp, hs, hp[rows], hs[rows], S, K, threads=threads)
                     dt = time.perf_counter() - t0
-                    ok = (np.array_equal(cn.reshape(cq, nd), got["numer"][:cq]) and np.array_equal(cd.reshape(cq, nd), got["denom"][:cq] & 0x7fffffff)
-                          and np.allclose(cdist.reshape(cq, nd), got["distance"][:cq], rtol=1e-12, atol=0))
+                    # the DEVICE path's output (grouped panels, prefilled records, tile list): rows of out_pairs left by the last timed step
+                    devrows = out_pairs.view(nd, nd * 24)[torch.from_numpy(rows).to(device)].cpu().numpy().view(fpm.PAIR_DTYPE).reshape(cq, nd)
+                    ok = (np.array_equal(cn.reshape(cq, nd), devrows["numer"]) and np.array_equal(cd.reshape(cq, nd), devrows["denom"] & 0x7fffffff)
+                          and np.allclose(cdist.reshape(cq, nd), devrows["distance"], rtol=1e-12, atol=0))
                     dist_obj["cpu_baseline"] = {"value": cq * nd / dt, "unit": "pairs/s", "cores": threads, "kind": "reference",
-                                                "sample": "%d query rows x %d refs (compareSketches loop over the reference's HashList, <=4096-pair chunks, no p-value)" % (cq, nd),
+                                                "sample": "%d query rows x %d refs (compareSketches over the reference's HashList, <=4096-pair chunks, no p-value), compared with the device-path output" % (cq, nd),
                                                 "matches_gpu": bool(ok)}
+        dist_summary = {"pairs_per_s": dist_obj["value"], "ms": d_ms, "exchange_ms": run["exchange"], "prepass_ms": run["pack"], "fill_tiles_ms": run["tile"],
+                        "merge_all_pairs_per_s": pairs / (full["ms"] * 1e-3), "merge_all_ms": full["ms"], "roofline_smem": dist_obj["merge_all_pairs"]["roofline_smem"]["frac"],
+                        "grid": "%dx%d" % (qp, rp), "parity": parity}
+        del panel, out_pairs
 
-    # ---- CPU baseline (rank 0, N=1 only) -----------------------------------------------------
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        threads = os.cpu_count() or 1
-        cg = min(args.cpu_genomes, n)
-        r = cpu_sketch_baseline(host_seq, L, cg, threads)
-        if r is not None:
-            cpu = {"value": r[0], "unit": "Gk-mers/s", "cores": threads, "kind": "reference",
-                   "sample": "%d of %d genomes (%d Mbp), reference TUs hash.cpp/MurmurHash3.cpp/MinHashHeap.cpp + restated sketchFile loop, -p %d, %.1f s" % (
-                       cg, n, cg * L // 1_000_000, threads, r[1])}
+    # ---- the other BASELINE configs, compact (C1 fp mode, C4 read set -m 2, C5 k=32 s=10000) --------------------------------
+    configs = run_other_configs(args, torch, np, fpm, sharding, ctx, device, rank, world, seq, offsets, n, L, barrier, max_over_ranks, sum_over_ranks, threads) if not args.no_configs else None
 
     if rank == 0:
         line = {
@@ -497,29 +570,154 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Gk-mers/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
+            "roofline": {"bound": "int32-alu", "achieved": int_achieved / 1e12, "peak": int_peak / 1e12, "unit": "Tint32-op/s", "frac": int_achieved / int_peak,
                          "traffic": alg_bytes * NCU_SKETCH_TRAFFIC_RATIO, "kernel": "sketch_hash_kernel_v2<21,true>", "launch_ms": hash_ms_avg,
-                         "traffic_note": "dram__bytes_read+write of one ncu --set full capture (profiles/r01_sketch_hash_v4.txt: 332.2 MB for a 300.0 MB launch) scaled to this launch size",
                          "share_of_step": hash_ms / ms_total if ms_total else None,
-                         "peak_source": hbm_src,
-                         "note": "algorithmic bytes = 1 B per base read once; this kernel is integer-ALU bound, see roofline_int"},
-            "roofline_int": {"bound": "int32-alu", "achieved": int_achieved / 1e12, "peak": int_peak / 1e12, "unit": "Tint32-op/s",
-                             "frac": int_achieved / int_peak,
-                             "note": "algorithmic ops = %d int32-op equivalents per k-mer (Murmur only, SURVEY.md 8d); peak = best of three inline-PTX microbenchmarks run live (strictly alternating IMAD/LOP3 with 16 independent chains: both integer pipes busy, ~0.94 warp instructions per clock and SM sub-partition)" % W_INT32_OPS[K],
-                             "pipe_bound": {"note": "the same roofline per pipe, k=21: the ALU pipe carries 44 of the 74 algorithmic ops; the FMA pipe carries the ten 64-bit multiplies and two x*5+c = 12 wide multiplies (IMAD.WIDE: 0.487 x the IMAD rate, profiles/ubench/int_mix.cu) + 24 IMADs; each pipe at its measured single-pipe peak",
-                                            "alu_pipe_ceiling_gkmers": int_peaks[0] / 44 / 1e9,
-                                            "fma_pipe_ceiling_gkmers": 1.0 / (12 / (IMAD_WIDE_RATE * int_peaks[1]) + 24 / int_peaks[1]) / 1e9,
-                                            "frac_of_tighter_ceiling": (windows_per_step / (hash_ms_avg * 1e-3) / 1e9) / min(int_peaks[0] / 44 / 1e9, 1.0 / (12 / (IMAD_WIDE_RATE * int_peaks[1]) + 24 / int_peaks[1]) / 1e9)} if K == 21 else None,
-                             "peaks_measured": {"alu_pipe_lop3": int_peaks[0] / 1e12, "fma_pipe_imad": int_peaks[1] / 1e12, "alternating": int_peaks[2] / 1e12}},
+                         "ops_per_kmer": W_INT32_OPS[K],
+                         "peak_source": "measured live: alternating IMAD/LOP3, 16 chains (fpm_measure_int32_peak); SURVEY 8d: the sketch kernel is integer-ALU bound",
+                         "peaks": {"alu_lop3": int_peaks[0] / 1e12, "fma_imad": int_peaks[1] / 1e12, "alternating": int_peaks[2] / 1e12},
+                         "hbm": {"achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak, "peak_source": hbm_src,
+                                 "note": "1 B per base read once; dram traffic 1.12x (ncu profiles/r02_sketch_hash_v2.txt)"}},
             "kernel_ms": {"sketch_hash": hash_ms_avg, "sketch_select": sel_ms / max(sel_n, 1)},
             "cpu_baseline": cpu,
             "dist": dist_obj,
+            "configs": configs,
+            "dist_summary": dist_summary,
         }
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
+        ctx.comm_destroy()
         dist.destroy_process_group()
     return 0
+
+
+def run_other_configs(args, torch, np, fpm, sharding, ctx, device, rank, world, seq, offsets, n, L, barrier, max_over_ranks, sum_over_ranks, threads):
+    """BASELINE.json configs[0], [3], [4] at their named sizes (compact numbers; the headline stays configs[1])."""
+    out = {}
+    lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=device)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, reps):
+        fn()
+        barrier()
+        ev0.record()
+        for _ in range(reps):
+            fn()
+        ev1.record()
+        barrier()
+        return max_over_ranks(ev0.elapsed_time(ev1)) / reps
+
+    # -- C5 sketch shape: k=32 s=10000 over this rank's genomes (the same 1000 x 5 Mbp buffer; a rate, so the sample size does not matter)
+    g5 = min(n, 200)
+    p5 = fpm.make_sketch_params(k=32, s=10000)
+    oh5 = torch.zeros((g5, 10000), dtype=torch.int64, device=device)
+    on5 = torch.zeros(g5, dtype=torch.int32, device=device)
+    ms = timed(lambda: ctx.sketch_batch_dev(seq.data_ptr(), int(offsets[g5]), offsets[:g5 + 1], p5, oh5.data_ptr(), None, on5.data_ptr()), 3)
+    out["C5_sketch"] = {"Gkmers_per_s": world * g5 * (L - 31) / (ms * 1e-3) / 1e9, "ms": ms, "k": 32, "s": 10000, "genomes_per_gpu": g5, "full": bool((on5 == 10000).all().item())}
+    del oh5, on5
+
+    # -- C4: 1,000,000 reads x 150 bp (30x of a 5 Mbp genome), 1 % substitutions, 0.1 % N, both strands, -m 2 with counts: ONE sketch, one GPU
+    if rank == 0:
+        gen = torch.Generator(device=device)
+        gen.manual_seed(4)
+        GL, n_reads, rl = 5_000_000, 1_000_000, 150
+        genome = torch.randint(0, 4, (GL,), generator=gen, device=device, dtype=torch.uint8)
+        start = torch.randint(0, GL - rl, (n_reads,), generator=gen, device=device)
+        codes = genome[start[:, None] + torch.arange(rl, device=device)[None, :]]
+        rev = torch.rand(n_reads, generator=gen, device=device) < 0.5
+        codes = torch.where(rev[:, None], 3 - codes.flip(1), codes)
+        err = torch.rand((n_reads, rl), generator=gen, device=device) < 0.01
+        codes = torch.where(err, torch.randint(0, 4, (n_reads, rl), generator=gen, device=device, dtype=torch.uint8), codes)
+        reads = lut[codes.long()]
+        reads[torch.rand((n_reads, rl), generator=gen, device=device) < 0.001] = ord("N")
+        buf = torch.zeros((n_reads, rl + 1), dtype=torch.uint8, device=device)
+        buf[:, :rl] = reads
+        buf = buf.reshape(-1)
+        del reads, codes, err, rev, start
+        offs = np.array([0, buf.numel()], dtype=np.uint64)
+        p4 = fpm.make_sketch_params(k=21, s=1000, min_cov=2, want_counts=True)
+        oh = torch.zeros((1, 1000), dtype=torch.int64, device=device)
+        oc = torch.zeros((1, 1000), dtype=torch.int32, device=device)
+        on = torch.zeros(1, dtype=torch.int32, device=device)
+        ok = torch.zeros(1, dtype=torch.int64, device=device)
+        ctx.sketch_batch_dev(buf.data_ptr(), buf.numel(), offs, p4, oh.data_ptr(), oc.data_ptr(), on.data_ptr(), ok.data_ptr())
+        windows = int(ok.item())
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        reps = 5
+        for _ in range(reps):
+            ctx.sketch_batch_dev(buf.data_ptr(), buf.numel(), offs, p4, oh.data_ptr(), oc.data_ptr(), on.data_ptr())
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) / reps * 1e3
+        c4 = {"Gkmers_per_s": windows / (ms * 1e-3) / 1e9, "ms": ms, "reads": n_reads, "valid_windows": windows, "min_cov": 2, "gpus": 1, "full": int(on.item()) == 1000}
+        if world == 1 and not args.no_cpu:
+            from oracle_py import RefLib
+            if RefLib.available():
+                host = buf.cpu().numpy()
+                hoff = np.array([0, host.size], dtype=np.uint64)
+                t0 = time.perf_counter()
+                ch, cc, cn = RefLib().sketch_batch(host, hoff, 21, 1000, seed=42, use64=True, min_cov=2, threads=1, want_counts=True)
+                dt = time.perf_counter() - t0
+                c4["cpu_reference_Gkmers_per_s"] = windows / dt / 1e9           # read mode is single-threaded in the reference (Sketch.cpp:203-210)
+                c4["matches_cpu_reference"] = bool(np.array_equal(ch[0], oh.cpu().numpy().view(np.uint64)[0]) and np.array_equal(cc[0], oc.cpu().numpy().view(np.uint32)[0]))
+        out["C4_reads"] = c4
+        del buf
+
+        # -- C1: fp mode, 5 ids x 2000 fingerprint lines (1..20 tokens each), 32-bit hashes, literal comparison of the unsorted lists
+        rng = np.random.default_rng(1)
+        lines = [list(rng.integers(1, 101, size=int(rng.integers(1, 21)))) for _ in range(5 * 2000)]
+        t0 = time.perf_counter()
+        fh = ctx.fp_hash_batch(lines, seed=42, use64=False)
+        hp = np.ascontiguousarray(fh.reshape(5, 2000))
+        got, _ = ctx.dist_tile((hp, np.full(5, 2000, np.uint32), np.full(5, 10000, np.uint64)), (hp, np.full(5, 2000, np.uint32), np.full(5, 10000, np.uint64)),
+                               2000, 1, 10.0, sorted_unique=False)
+        c1 = {"ms": (time.perf_counter() - t0) * 1e3, "lines": len(lines), "pairs": 25, "self_pairs_distance_0": bool((np.diag(got["distance"]) == 0).all())}
+        out["C1_fp"] = c1
+
+    # -- C5 dist at full size: 100,000 queries x 10,000 references, s=10000, k=32 (1e9 pairs), blocks over the ranks
+    if args.c5_queries > 0:
+        nq, nr, s5 = args.c5_queries, args.c5_refs, 10000
+        q0, q1 = sharding.shard_range(nq, rank, world)
+        r0, r1 = sharding.shard_range(nr, rank, world)
+        qp_ = gen_panel_rows(torch, q0, q1, s5, device, 52, 100, core_seed=5)     # 100 clusters shared by both panels: a query is
+        rp_ = gen_panel_rows(torch, r0, r1, s5, device, 51, 100, core_seed=5)     # related to the 1 % of references of its cluster
+        qs = torch.full((q1 - q0,), s5, dtype=torch.int32, device=device); ql = torch.full((q1 - q0,), 5_000_000, dtype=torch.int64, device=device)
+        rs = torch.full((r1 - r0,), s5, dtype=torch.int32, device=device); rlen = torch.full((r1 - r0,), 5_000_000, dtype=torch.int64, device=device)
+        blk = sharding.block_of(rank, world, nq, nr)
+        bp = (blk[1] - blk[0]) * (blk[3] - blk[2])
+        o5 = torch.empty((max(bp, 1) * 24,), dtype=torch.uint8, device=device)
+        st5 = torch.zeros(1, dtype=torch.int64, device=device)
+        rptr = (rp_.data_ptr(), rs.data_ptr(), rlen.data_ptr(), r1 - r0, s5)
+        qptr = (qp_.data_ptr(), qs.data_ptr(), ql.data_ptr(), q1 - q0, s5)
+
+        def c5_step():
+            if world > 1:
+                ctx.dist_sharded_dev(rptr, nr, qptr, nq, s5, 32, 4.0 ** 32, o5.data_ptr(), bp, st5.data_ptr())
+            else:
+                ctx.dist_tile_dev(rptr, qptr, s5, 32, 4.0 ** 32, o5.data_ptr(), st5.data_ptr())
+
+        def c5_timed(**mode):
+            ctx.set_dist_mode(**mode)
+            try:
+                c5_step()
+                barrier()
+                st5.zero_()
+                ev0.record()
+                c5_step()
+                ev1.record()
+                barrier()
+                sec = max_over_ranks(ev0.elapsed_time(ev1)) * 1e-3
+                return sec, int(sum_over_ranks(st5.clone()).item()) / (nq * nr), [int(x) for x in sum_over_ranks(pair_digest(torch, o5, bp)).tolist()]
+            finally:
+                ctx.set_dist_mode()
+
+        sec, spp, dg = c5_timed()
+        out["C5_dist"] = {"pairs_per_s": nq * nr / sec, "seconds": sec, "queries": nq, "refs": nr, "s": s5, "k": 32, "merge_steps_per_pair": spp, "digest": dg}
+        if args.c5_merge_all:
+            sec_a, spp_a, dg_a = c5_timed(no_prune=True)
+            out["C5_dist"].update({"merge_all_seconds": sec_a, "merge_all_steps_per_s": spp_a * nq * nr / sec_a, "merge_all_equals_pruned": dg_a == dg})
+    return out
 
 
 if __name__ == "__main__":

@@ -444,10 +444,15 @@ int CommandDistance::run() const
         fpm_panel vr = pr.view(0, nRef), vq = pq.view(0, nQry);
         vector<fpm_hit> hits(max<uint64_t>(1 << 16, 16 * (nRef + nQry)));
         uint64_t nHits = 0;
-        int rc = fpm_dist_hits(gpuContext(), &dp, &vr, &vq, hits.data(), hits.size(), &nHits);
+        // large jobs: the pair space is cut into query x reference blocks over all GPUs (fpm_dist_hits_multi); the list comes
+        // back merged in the same order
+        fpm_multi* multi = fingerprint ? nullptr : gpuMulti(nRef * nQry, kMultiGpuPairs);
+        auto call = [&]() { return multi ? fpm_dist_hits_multi(multi, &dp, &vr, &vq, hits.data(), hits.size(), &nHits)
+                                         : fpm_dist_hits(gpuContext(), &dp, &vr, &vq, hits.data(), hits.size(), &nHits); };
+        int rc = call();
         if (rc == FPM_ERR_CAPACITY) {
             hits.resize(nHits);
-            rc = fpm_dist_hits(gpuContext(), &dp, &vr, &vq, hits.data(), hits.size(), &nHits);
+            rc = call();
         }
         if (rc != FPM_OK) {
             cerr << "ERROR: " << fpm_last_error() << endl;
@@ -465,13 +470,14 @@ int CommandDistance::run() const
         }
     }
     // query-major tiles of at most ~32M pairs (768 MB of results) per GPU call
-    uint64_t rowsPerCall = nRef ? max<uint64_t>(1, (32ull << 20) / nRef) : 1;
+    fpm_multi* multiTile = (filtered || fingerprint) ? nullptr : gpuMulti(nRef * nQry, kMultiGpuPairs);
+    uint64_t rowsPerCall = nRef ? max<uint64_t>(1, ((32ull << 20) * (multiTile ? fpm_multi_size(multiTile) : 1)) / nRef) : 1;
     vector<fpm_pair> out;
     for (uint64_t q0 = 0; q0 < nQry && nRef && !filtered; q0 += rowsPerCall) {
         uint64_t nq = min(rowsPerCall, nQry - q0);
         out.resize(nq * nRef);
         fpm_panel vr = pr.view(0, nRef), vq = pq.view(q0, nq);
-        if (fpm_dist_tile(gpuContext(), &dp, &vr, &vq, out.data()) != FPM_OK) {
+        if ((multiTile ? fpm_dist_tile_multi(multiTile, &dp, &vr, &vq, out.data()) : fpm_dist_tile(gpuContext(), &dp, &vr, &vq, out.data())) != FPM_OK) {
             cerr << "ERROR: " << fpm_last_error() << endl;
             return 1;
         }

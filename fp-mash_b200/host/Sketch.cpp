@@ -39,20 +39,59 @@ void fpmTick(const char* label)
     last = now;
 }
 
+// All GPUs this process may use, created on first use (context creation costs a few hundred ms per device on boxes without
+// persistence mode, so jobs below gpuMulti()'s thresholds only ever touch the first one).  FPMASH_DEVICE pins one
+// device; FPMASH_GPUS limits (or, beyond the number of devices present, repeats -- tests) the devices used.
+static std::vector<int> gpuDeviceList()
+{
+    std::vector<int> list;
+    const int have = fpm_device_count();
+    if (const char* dev = getenv("FPMASH_DEVICE")) { list.push_back(atoi(dev)); return list; }
+    int want = have;
+    if (const char* g = getenv("FPMASH_GPUS")) want = atoi(g);
+    if (want < 1) want = 1;
+    for (int i = 0; i < want; i++) list.push_back(have > 0 ? i % have : i);
+    return list;
+}
+
+static fpm_multi* g_multi = nullptr;
+static fpm_ctx* g_ctx = nullptr;
+
 fpm_ctx* gpuContext()
 {
-    static fpm_ctx* ctx = nullptr;
-    if (!ctx) {
-        const char* dev = getenv("FPMASH_DEVICE");
+    if (g_multi) return fpm_multi_ctx(g_multi, 0);
+    if (!g_ctx) {
+        const std::vector<int> devs = gpuDeviceList();
         fpmTick("before fpm_ctx_create");
-        int rc = fpm_ctx_create(dev ? atoi(dev) : 0, &ctx);
+        int rc = fpm_ctx_create(devs[0], &g_ctx);
         fpmTick("fpm_ctx_create done");
         if (rc != FPM_OK) {
             cerr << "ERROR: " << fpm_last_error() << endl;
             exit(1);
         }
     }
-    return ctx;
+    return g_ctx;
+}
+
+// The several-GPU handle (fpm_multi_*, csrc/dist_multi.cu), or nullptr when this process has one device / the job is too
+// small to be worth the other devices' start-up.  The reference spreads the same work over -p threads
+// (CommandDistance.cpp:224-261, Sketch.cpp:353-355).
+fpm_multi* gpuMulti(uint64_t work /* pairs, or sequence bytes */, uint64_t threshold)
+{
+    if (g_multi) return g_multi;
+    if (const char* e = getenv("FPMASH_MULTI_MIN")) threshold = strtoull(e, nullptr, 10);   // tests: small jobs on several GPUs
+    if (work < threshold) return nullptr;
+    const std::vector<int> devs = gpuDeviceList();
+    if (devs.size() < 2) return nullptr;
+    if (g_ctx) { fpm_ctx_destroy(g_ctx); g_ctx = nullptr; }          // its scratch memory would only compete with the handle's own context
+    fpmTick("before fpm_multi_create");
+    int rc = fpm_multi_create(devs.data(), (int)devs.size(), &g_multi);
+    fpmTick("fpm_multi_create done");
+    if (rc != FPM_OK) {
+        cerr << "ERROR: " << fpm_last_error() << endl;
+        exit(1);
+    }
+    return g_multi;
 }
 
 static void gpuCheck(int rc)
@@ -168,8 +207,12 @@ void Sketch::flushBatch(Batch& b)
     vector<uint32_t> counts(parameters.counts ? (size_t)n * s : 0);
     vector<uint32_t> outn(n);
     fpmTick("batch parsed");
-    gpuCheck(fpm_sketch_batch(gpuContext(), &sp, b.seq, b.used, b.goff.data(), n, hashes.data(),
-                              parameters.counts ? counts.data() : nullptr, outn.data(), nullptr));
+    // several sketches and enough bytes: whole sketches go to all GPUs (contiguous byte-balanced ranges), else one GPU
+    if (fpm_multi* multi = n >= 2 ? gpuMulti(b.used, 96ull << 20) : nullptr)
+        gpuCheck(fpm_sketch_batch_multi(multi, &sp, b.seq, b.used, b.goff.data(), n, hashes.data(), parameters.counts ? counts.data() : nullptr, outn.data(), nullptr));
+    else
+        gpuCheck(fpm_sketch_batch(gpuContext(), &sp, b.seq, b.used, b.goff.data(), n, hashes.data(),
+                                  parameters.counts ? counts.data() : nullptr, outn.data(), nullptr));
     fpmTick("fpm_sketch_batch done");
     for (uint32_t g = 0; g < n; g++) {
         Reference& r = b.metas[g];

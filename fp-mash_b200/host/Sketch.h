@@ -114,6 +114,10 @@ void setAlphabetFromString(Sketch::Parameters& parameters, const char* character
 
 // The process-wide CUDA context (created on first use; failure is fatal: no CPU fallback).
 struct fpm_ctx;
+struct fpm_multi;
 fpm_ctx* gpuContext();
+// all GPUs of the box for jobs of at least `threshold` units of `work` (pairs / sequence bytes); nullptr: use gpuContext()
+fpm_multi* gpuMulti(uint64_t work, uint64_t threshold);
+static const uint64_t kMultiGpuPairs = 64ull << 20;   // dist jobs below this many pairs stay on one GPU
 // FPMASH_TIMING=1: print elapsed wall-clock milestones to stderr (where does a CLI run spend its time?)
 void fpmTick(const char* label);

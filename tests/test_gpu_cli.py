@@ -246,3 +246,89 @@ def test_dist_filtered_output_is_the_filtered_full_output(tmp_path):
         got = [l.split("\t") for l in run(["dist"] + flags + ["all.msh", "all.msh"], cwd=tmp_path).stdout.splitlines()]
         want = [r for r in full if keep(r)]
         assert 36 <= len(want) < 36 * 36 and got == want, flags
+
+
+def test_thousand_reference_msh_layout(tmp_path, oracle):
+    """configs[1] writes ONE .msh with 1000 references: the reference list leaves segment 0, so every name, comment and
+    hash list sits behind a far pointer with its own landing pad (SURVEY.md Appendix D -- the layout the reference's
+    capnp arena produces, unpinned by its fixtures).  Written by the product, read back by the independent decoder."""
+    rng = np.random.default_rng(77)
+    recs = [bytes(np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=3000)]) for _ in range(1000)]
+    with open(tmp_path / "many.fa", "wb") as f:
+        for i, r in enumerate(recs):
+            f.write(b">seq%04d sample %d\n" % (i, i) + r + b"\n")
+    run(["sketch", "-i", "-o", "many", "many.fa"], cwd=tmp_path)
+    data = open(tmp_path / "many.msh", "rb").read()
+    m = mshpy.Msh(data)
+    assert len(m.refs) == 1000 and m.kmer_size == 21 and m.sketch_size == 1000
+    # step 2 of the walk-through: segment 1 is exactly the landing pad + tag + 1000 x 9 words, and it is full
+    assert m.segment_words[1] == 9002
+    # step 3: later segments have capacities 10026, 20052, 40104, ... (nextSize doubling from 1024 + 9002); all but the last are
+    # filled until the next object (plus its landing pad) no longer fits
+    caps, nxt = [], 1024 + 9002
+    for w in m.segment_words[2:]:
+        caps.append(nxt)
+        nxt += nxt
+        assert w <= caps[-1]
+    import struct
+    order = []
+    for i in range(1000):
+        e_idx = 2 + 9 * i                                              # element i of the composite list in segment 1
+        for slot, what in ((2, "name"), (3, "comment"), (5, "hashes64")):
+            w = struct.unpack_from("<Q", m.segs[1], 8 * (e_idx + 2 + slot))[0]
+            lo, hi = w & 0xffffffff, w >> 32
+            assert lo & 3 == 2 and not (lo >> 2) & 1, "reference %d %s: not a single-far pointer" % (i, what)
+            pad_seg, pad_idx = hi, lo >> 3
+            assert pad_seg >= 2
+            pad = struct.unpack_from("<Q", m.segs[pad_seg], 8 * pad_idx)[0]
+            assert pad & 3 == 1 and ((pad & 0xffffffff) >> 2) == 0, "landing pad is a list pointer with offset 0: the object follows it"
+            order.append((pad_seg, pad_idx))
+        assert m.refs[i]["name"] == "seq%04d" % i and m.refs[i]["comment"] == "sample %d" % i and m.refs[i]["length"] == 3000
+    assert order == sorted(order), "objects are allocated in call order name, comment, hashes per reference"
+    # a segment is left only when the next object did not fit into what was left of its capacity
+    for (sa, ia), (sb, ib) in zip(order, order[1:]):
+        if sb != sa:
+            assert sb == sa + 1 and ib == 0
+    for seg_i, cap in zip(range(2, len(m.segment_words) - 1), caps):
+        first_next = next(k for k, (s_, _) in enumerate(order) if s_ == seg_i + 1)
+        kind = first_next % 3
+        ref = m.refs[first_next // 3]
+        size = 1 + ((len(ref["name"]) + 1 + 7) // 8 if kind == 0 else (len(ref["comment"]) + 1 + 7) // 8 if kind == 1 else len(ref["hashes64"]))
+        assert m.segment_words[seg_i] + size > cap
+    for i in (0, 1, 499, 999):
+        want = oracle.sketch([recs[i]], k=21, s=1000)
+        assert m.refs[i]["hashes64"] == [int(x) for x in want["hashes"]]
+    # and the product's own reader agrees with what it wrote: paste reproduces the file
+    run(["paste", "again", "many.msh"], cwd=tmp_path)
+    assert same_bytes(tmp_path / "again.msh", tmp_path / "many.msh")
+
+
+def test_cli_on_several_gpus_prints_the_same(tmp_path):
+    """`mash sketch` / `mash dist` over all GPUs of the box (fpm_multi_*: query x reference blocks, whole sketches per GPU) must
+    write the same files and print the same rows as on one GPU.  FPMASH_GPUS beyond the devices present repeats them."""
+    rng = np.random.default_rng(5)
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    base = lut[rng.integers(0, 4, size=120000)]
+    names = []
+    for i in range(14):
+        g = base.copy() if i % 2 == 0 else lut[rng.integers(0, 4, size=90000)]
+        idx = rng.random(g.size) < 0.01 * (1 + i)
+        g[idx] = lut[rng.integers(0, 4, size=int(idx.sum()))]
+        with open(tmp_path / ("g%02d.fa" % i), "wb") as f:
+            f.write(b">g%d\n" % i + bytes(g) + b"\n")
+        names.append("g%02d.fa" % i)
+
+    def with_env(extra, args):
+        env = dict(os.environ, **extra)
+        r = subprocess.run([MASH] + args, capture_output=True, text=True, cwd=tmp_path, env=env)
+        assert r.returncode == 0, r.stderr
+        return r.stdout
+
+    one = {"FPMASH_GPUS": "1"}
+    many = {"FPMASH_GPUS": "3", "FPMASH_MULTI_MIN": "1"}
+    with_env(one, ["sketch", "-o", "one"] + names)
+    with_env(many, ["sketch", "-o", "many"] + names)
+    assert same_bytes(tmp_path / "one.msh", tmp_path / "many.msh")
+    for args in (["dist", "one.msh", "one.msh"], ["dist", "-d", "0.2", "one.msh", "one.msh"], ["dist", "-t", "one.msh", "one.msh"],
+                 ["dist", "-v", "1e-20", "one.msh", "g03.fa", "g04.fa"]):
+        assert with_env(one, args) == with_env(many, args), args
