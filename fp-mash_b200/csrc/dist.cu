@@ -53,6 +53,7 @@ struct DistArgs {
     uint32_t s;
     int kmer_size;
     double kmer_space, max_distance, max_pvalue;
+    uint32_t k128 = 128u, k1 = 1u;   // the row pitch and 1 as run-time values (FPM_D4_FMA_BUMP: a multiply-add ptxas cannot fold into an add)
 };
 
 // (the "memory" clobbers matter: these loads read what other threads staged, so they must stay behind the
@@ -70,8 +71,24 @@ __device__ __forceinline__ void lds32(uint32_t addr, uint32_t& v)
 // One step of the reference's merge loop (CommandDistance.cpp:378-386) on 32-bit ranks held in shared-memory
 // columns of 128-byte row pitch: the list(s) holding the smaller-or-equal head advance and reload.  Pinned as
 // six instructions (two compares, two predicated pointer bumps, two predicated LDS.32).
-__device__ __forceinline__ void merge_step32(uint32_t& pa, uint32_t& pb, uint32_t& av, uint32_t& bv)
+#ifndef FPM_D4_FMA_BUMP
+#define FPM_D4_FMA_BUMP 0     // pointer bumps as IMAD (FMA pipe) instead of IADD (ALU pipe, which also carries the two compares)
+#endif
+__device__ __forceinline__ void merge_step32(uint32_t& pa, uint32_t& pb, uint32_t& av, uint32_t& bv, uint32_t c128 = 128u, uint32_t c1 = 1u)
 {
+#if FPM_D4_FMA_BUMP
+    asm volatile("{\n\t.reg .pred pa_le, pb_le;\n\t"
+                 "setp.le.u32 pa_le, %2, %3;\n\t"
+                 "setp.ge.u32 pb_le, %2, %3;\n\t"
+                 "@pa_le mad.lo.u32 %0, %4, %5, %0;\n\t"
+                 "@pb_le mad.lo.u32 %1, %4, %5, %1;\n\t"
+                 "@pa_le ld.shared.u32 %2, [%0];\n\t"
+                 "@pb_le ld.shared.u32 %3, [%1];\n\t}"
+                 : "+r"(pa), "+r"(pb), "+r"(av), "+r"(bv)
+                 : "r"(c128), "r"(c1)
+                 : "memory");
+    return;
+#endif
     asm volatile("{\n\t.reg .pred pa_le, pb_le;\n\t"
                  "setp.le.u32 pa_le, %2, %3;\n\t"
                  "setp.ge.u32 pb_le, %2, %3;\n\t"
@@ -642,13 +659,14 @@ dist_tile32_kernel(const uint32_t* __restrict__ pref, const uint32_t* __restrict
             lds32(pb00, m0.bv);
             lds32(pb01, m1.bv);
             // both pairs together while both have unchecked steps left; then each one alone
+            const uint32_t k128 = a.k128, k1 = a.k1;
             for (;;) {
                 uint32_t blocks = min(m0.safe(), m1.safe()) / D4_UNROLL;
                 if (!blocks) break;
                 m0.rem -= blocks * D4_UNROLL; m1.rem -= blocks * D4_UNROLL;
                 do {
 #pragma unroll
-                    for (int u = 0; u < D4_UNROLL; u++) { merge_step32(m0.pa, m0.pb, m0.av, m0.bv); merge_step32(m1.pa, m1.pb, m1.av, m1.bv); }
+                    for (int u = 0; u < D4_UNROLL; u++) { merge_step32(m0.pa, m0.pb, m0.av, m0.bv, k128, k1); merge_step32(m1.pa, m1.pb, m1.av, m1.bv, k128, k1); }
                 } while (--blocks);
             }
             m0 = merge32_alone(m0);

@@ -21,7 +21,6 @@
 //   - ONE PROCESS, ALL GPUS (fpm_multi_*): what `mash dist` / `mash sketch` use.  Panels are in host memory, so every
 //     GPU simply uploads its two blocks: no collective.  One host thread per GPU.
 #include <dlfcn.h>
-#include <nccl.h>
 #include <string.h>
 #include <algorithm>
 #include <string>
@@ -29,24 +28,12 @@
 #include <vector>
 #include "common.h"
 #include "dist_internal.h"
+#include "nccl_dyn.h"
 
 namespace fpm {
 
-// ---- NCCL, bound at run time ------------------------------------------------------------------------------------
-struct NcclApi {
-    void* handle = nullptr;
-    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
-    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
-    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
-    ncclResult_t (*GroupStart)() = nullptr;
-    ncclResult_t (*GroupEnd)() = nullptr;
-    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
-    const char* (*GetErrorString)(ncclResult_t) = nullptr;
-};
-
-static NcclApi* nccl_api()
+// ---- NCCL, bound at run time (nccl_dyn.h) ------------------------------------------------------------------------
+NcclApi* nccl_api()
 {
     static NcclApi api;
     static bool tried = false;
@@ -70,17 +57,12 @@ static NcclApi* nccl_api()
     FPM_NCCL_SYM(Send, "ncclSend");
     FPM_NCCL_SYM(Recv, "ncclRecv");
     FPM_NCCL_SYM(AllGather, "ncclAllGather");
+    FPM_NCCL_SYM(AllReduce, "ncclAllReduce");
     FPM_NCCL_SYM(GetErrorString, "ncclGetErrorString");
 #undef FPM_NCCL_SYM
     if (!ok) { set_error("the NCCL library lacks a required symbol"); dlclose(api.handle); api.handle = nullptr; return nullptr; }
     return &api;
 }
-
-#define FPM_NCCL(api, call)                                                                                          \
-    do {                                                                                                             \
-        ncclResult_t r__ = (call);                                                                                   \
-        if (r__ != ncclSuccess) { set_error("NCCL error %d (%s): %s", (int)r__, (api)->GetErrorString(r__), #call); return FPM_ERR_COMM; } \
-    } while (0)
 
 // ---- the grid ---------------------------------------------------------------------------------------------------
 static uint64_t shard_begin(uint64_t n, uint64_t part, uint64_t parts) { return (uint64_t)((unsigned __int128)n * part / parts); }

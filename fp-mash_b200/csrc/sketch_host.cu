@@ -10,6 +10,7 @@
 #include "sketch_kernels.cuh"
 #include "sketch_launch.h"
 #include "sketch_select.h"
+#include "nccl_dyn.h"
 #include <math.h>
 
 namespace fpm {
@@ -356,6 +357,352 @@ int sketch_batch_dev_impl(fpm_ctx* ctx, const fpm_sketch_params* p, const uint8_
     return FPM_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// ONE read set spread over the GPUs of a communicator (SURVEY.md 8e, row "read sketch"): `mash sketch -r` turns all
+// reads into one sketch on a single thread in the reference (Sketch.cpp:203-210).  Every rank hashes a contiguous part
+// of the read stream into a counting table of its own; the candidates -- (hash, count, first position) of every entry
+// below the common bound -- are all-gathered and merged by key (counts add up, positions take the minimum), and every
+// rank selects the bottom-s of the merged table: the set formulation of MinHashHeap is order
+// independent.  The one order-DEPENDENT number, the multiplicity of the largest element of a full sketch, needs the
+// stream positions of the final hashes: each rank's trace pass writes its (global) positions into its own slice of
+// every hash's bucket, an all-reduce joins the slices, and sketch_topcount_kernel applies the rule as on one GPU.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) table_export_kernel(const uint64_t* __restrict__ tkeys, const uint32_t* __restrict__ tcnt, const uint64_t* __restrict__ tpos,
+                                                           uint32_t cap, uint64_t* __restrict__ out_keys, uint32_t* __restrict__ out_cnt, uint64_t* __restrict__ out_pos,
+                                                           uint32_t* counter)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool have = i < cap && tkeys[i] != SK_EMPTY;
+    const uint32_t m = __ballot_sync(0xffffffffu, have);
+    if (!m) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (have) {
+        const uint32_t o = base + __popc(m & ((1u << lane) - 1u));
+        out_keys[o] = tkeys[i]; out_cnt[o] = tcnt[i]; out_pos[o] = tpos[i];
+    }
+}
+
+// entries [rank][stride] of all ranks -> one table: counts add up, first positions take the minimum
+__global__ void __launch_bounds__(256) table_import_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ cnt, const uint64_t* __restrict__ pos,
+                                                           const uint32_t* __restrict__ n_of_rank, uint32_t stride, uint32_t world, uint64_t* tkeys, uint32_t* tcnt,
+                                                           uint64_t* tpos, uint32_t mask, uint32_t* overflow)
+{
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (uint64_t)world * stride) return;
+    const uint32_t r = (uint32_t)(idx / stride), i = (uint32_t)(idx % stride);
+    if (i >= n_of_rank[r]) return;
+    const uint64_t h = keys[idx];
+    uint32_t slot = table_slot(h, mask);
+    for (uint32_t probe = 0; probe <= mask; probe++) {
+        const unsigned long long prev = atomicCAS((unsigned long long*)&tkeys[slot], (unsigned long long)SK_EMPTY, (unsigned long long)h);
+        if (prev == SK_EMPTY || prev == h) {
+            atomicAdd(&tcnt[slot], cnt[idx]);
+            atomicMin((unsigned long long*)&tpos[slot], (unsigned long long)pos[idx]);
+            return;
+        }
+        slot = (slot + 1) & mask;
+    }
+    atomicExch(overflow, 1u);
+}
+
+// occurrences of each final hash in THIS rank's table
+__global__ void __launch_bounds__(256) table_lookup_counts_kernel(const uint64_t* __restrict__ fin, uint32_t n, const uint64_t* __restrict__ tkeys,
+                                                                  const uint32_t* __restrict__ tcnt, uint32_t mask, uint32_t maxkey_cnt, uint32_t* __restrict__ out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t h = fin[i];
+    uint32_t c = 0;
+    if (h == SK_EMPTY) c = maxkey_cnt;
+    else {
+        uint32_t slot = table_slot(h, mask);
+        for (uint32_t probe = 0; probe <= mask; probe++) {
+            const uint64_t k = tkeys[slot];
+            if (k == h) { c = tcnt[slot]; break; }
+            if (k == SK_EMPTY) break;
+            slot = (slot + 1) & mask;
+        }
+    }
+    out[i] = c;
+}
+
+int sketch_reads_sharded_impl(fpm_ctx* ctx, const fpm_sketch_params* p, const uint8_t* d_seq, uint64_t n_bytes, uint64_t* d_out_hashes,
+                              uint32_t* d_out_counts, uint32_t* d_out_n, uint64_t* d_out_kmers)
+{
+    int rc = check_params(p);
+    if (rc) return rc;
+    if (!ctx->comm || ctx->comm_world < 1) { set_error("no communicator: call fpm_comm_init_rank or fpm_comm_adopt first"); return FPM_ERR_ARG; }
+    if (!is_nucleotide(p)) { set_error("a read set spread over several GPUs needs the nucleotide alphabet"); return FPM_ERR_UNSUPPORTED; }
+    if (!d_out_hashes || !d_out_n || (!d_seq && n_bytes)) { set_error("NULL buffer"); return FPM_ERR_ARG; }
+    if (((uintptr_t)d_seq & 15) != 0) { set_error("d_seq must be 16-byte aligned"); return FPM_ERR_ARG; }
+    NcclApi* api = nccl_api();
+    if (!api) return FPM_ERR_COMM;
+    ncclComm_t comm = (ncclComm_t)ctx->comm;
+    const int W = ctx->comm_world, me = ctx->comm_rank;
+    cudaStream_t st = ctx->stream;
+    const int K = p->kmer_size;
+    const uint32_t s = p->sketch_size;
+    const bool canon = !p->noncanonical;
+    const uint64_t full = p->use64 ? kAll64 : 0xffffffffULL;
+    const uint64_t target = s <= 4096 ? 2ull * s + 64 : (uint64_t)s + s / 4 + 256;
+    const bool want_counts = p->want_counts && d_out_counts;
+
+    // small exchanges go through one scratch block: [W] x 4 u64 of per-rank metadata, sent from slot `me`
+    if ((rc = ctx->d_misc.ensure(64 + (size_t)W * 32))) return rc;
+    if ((rc = ctx->ensure_pinned((size_t)W * 32 + 64))) return rc;
+    uint64_t* d_meta = ctx->d_misc.as<uint64_t>() + 8;
+    uint64_t* h_meta = (uint64_t*)ctx->h_pinned;
+    auto gather_meta = [&](uint64_t a0, uint64_t a1, uint64_t a2, uint64_t a3) -> int {
+        const uint64_t mine[4] = {a0, a1, a2, a3};
+        FPM_CUDA(cudaMemcpyAsync(d_meta + 4 * me, mine, 32, cudaMemcpyHostToDevice, st));
+        FPM_NCCL(api, api->AllGather(d_meta + 4 * me, d_meta, 32, ncclUint8, comm, st));
+        FPM_CUDA(cudaMemcpyAsync(h_meta, d_meta, (size_t)W * 32, cudaMemcpyDeviceToHost, st));
+        FPM_CUDA(cudaStreamSynchronize(st));
+        return FPM_OK;
+    };
+    // ---- where this rank's part sits in the stream ---------------------------------------------------------------
+    if ((rc = gather_meta(n_bytes, 0, 0, 0))) return rc;
+    uint64_t n_total = 0, base = 0;
+    for (int r = 0; r < W; r++) { if (r < me) base += h_meta[4 * r]; n_total += h_meta[4 * r]; }
+    if (n_total == 0) {
+        FPM_CUDA(cudaMemsetAsync(d_out_n, 0, sizeof(uint32_t), st));
+        if (d_out_kmers) FPM_CUDA(cudaMemsetAsync(d_out_kmers, 0, sizeof(uint64_t), st));
+        return FPM_OK;
+    }
+    // ---- plan: as fpm_sketch_batch for one group of n_total bytes ------------------------------------------------
+    GroupPlan pl;
+    const uint64_t cov_guess = p->min_cov > 1 ? std::max<uint64_t>(1, std::min<uint64_t>(32, (64ull << 20) / (4 * target))) : 1;
+    if (n_total <= 2 * target * cov_guess) { pl.all = true; pl.thresh = full; pl.cap = pow2ceil(2 * n_total); }
+    else { pl.all = false; pl.thresh = scale_threshold(full, (double)(target * cov_guess) / (double)n_total); pl.cap = pow2ceil(4 * target * cov_guess); }
+
+    const uint64_t h_goff[2] = {0, n_bytes};
+    if ((rc = ctx->goff.ensure(16))) return rc;
+    if ((rc = ctx->thresh.ensure(8))) return rc;
+    if ((rc = ctx->active.ensure(1))) return rc;
+    if ((rc = ctx->toff.ensure(8))) return rc;
+    if ((rc = ctx->tmask.ensure(4))) return rc;
+    if ((rc = ctx->maxcnt.ensure(8))) return rc;
+    if ((rc = ctx->maxpos.ensure(16))) return rc;
+    if ((rc = ctx->overflow.ensure(8))) return rc;
+    if ((rc = ctx->stat.ensure(64))) return rc;
+    if ((rc = ctx->args.ensure(sizeof(SketchArgs)))) return rc;
+    FPM_CUDA(cudaMemcpyAsync(ctx->goff.p, h_goff, 16, cudaMemcpyHostToDevice, st));
+    const uint8_t one = 1;
+    const uint64_t zero64 = 0;
+    FPM_CUDA(cudaMemcpyAsync(ctx->active.p, &one, 1, cudaMemcpyHostToDevice, st));
+    FPM_CUDA(cudaMemcpyAsync(ctx->toff.p, &zero64, 8, cudaMemcpyHostToDevice, st));
+    int max_smem = 0;
+    FPM_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+    if (configure_sketch_select((size_t)SK_SORT_CAP * 8) != 0) { set_error("cudaFuncSetAttribute(select) failed"); return FPM_ERR_CUDA; }
+
+    auto fill_args = [&](SketchArgs& a) {
+        memset(&a, 0, sizeof a);
+        a.seq = d_seq; a.n_bytes = n_bytes; a.group_off = ctx->goff.as<uint64_t>(); a.n_groups = 1;
+        a.thresh = ctx->thresh.as<uint64_t>(); a.active = ctx->active.as<uint8_t>();
+        a.sketch_size = s; a.seed = p->seed; a.fold_case = !p->preserve_case; a.hash32 = !p->use64;
+        a.c_tbl = 0x54474341u; a.c_add1 = 0x52dce729ULL; a.c_add2 = 0x38495ab5ULL; a.c_add1s = a.c_add1 + 5ull * a.seed;
+        a.pos_base = base;
+    };
+    // the merged table lives in ctx->scratch: keys | counts | positions | maxkey count / position | overflow
+    uint32_t local_cap = 0, merged_cap = 0, h_outn = 0, h_topcnt = 0;
+    uint64_t *m_keys = nullptr, *m_pos = nullptr;
+    uint32_t *m_cnt = nullptr;
+    uint32_t h_local_maxcnt = 0;
+    for (int pass = 0; pass < 12; pass++) {
+        // ---- local pass ---------------------------------------------------------------------------------------------
+        local_cap = pl.cap;
+        if ((rc = ctx->tkeys.ensure((size_t)local_cap * 8))) return rc;
+        if ((rc = ctx->tcnt.ensure((size_t)local_cap * 4))) return rc;
+        if ((rc = ctx->tpos.ensure((size_t)local_cap * 8))) return rc;
+        FPM_CUDA(cudaMemsetAsync(ctx->tkeys.p, 0xff, (size_t)local_cap * 8, st));
+        FPM_CUDA(cudaMemsetAsync(ctx->tcnt.p, 0, (size_t)local_cap * 4, st));
+        FPM_CUDA(cudaMemsetAsync(ctx->tpos.p, 0xff, (size_t)local_cap * 8, st));
+        FPM_CUDA(cudaMemsetAsync(ctx->maxcnt.p, 0, 8, st));
+        FPM_CUDA(cudaMemsetAsync(ctx->maxpos.p, 0xff, 16, st));
+        FPM_CUDA(cudaMemsetAsync(ctx->overflow.p, 0, 8, st));
+        const uint32_t mask = local_cap - 1;
+        FPM_CUDA(cudaMemcpyAsync(ctx->thresh.p, &pl.thresh, 8, cudaMemcpyHostToDevice, st));
+        FPM_CUDA(cudaMemcpyAsync(ctx->tmask.p, &mask, 4, cudaMemcpyHostToDevice, st));
+        SketchArgs a;
+        fill_args(a);
+        a.tkeys = ctx->tkeys.as<uint64_t>(); a.tcnt = ctx->tcnt.as<uint32_t>(); a.tpos = ctx->tpos.as<uint64_t>();
+        a.toff = ctx->toff.as<uint64_t>(); a.tmask = ctx->tmask.as<uint32_t>();
+        a.maxkey_cnt = ctx->maxcnt.as<uint32_t>(); a.maxkey_pos = ctx->maxpos.as<uint64_t>(); a.overflow = ctx->overflow.as<uint32_t>();
+        FPM_CUDA(cudaMemcpyAsync(ctx->args.p, &a, sizeof a, cudaMemcpyHostToDevice, st));
+        if (n_bytes) {
+            ctx->time_begin(FPM_KERNEL_SKETCH_HASH);
+            g_hash_launch[K - 1](canon, st, ctx->args.as<SketchArgs>(), 0, n_bytes, 0);
+            ctx->time_end();
+            ctx->launches++;
+            FPM_CUDA(cudaGetLastError());
+        }
+        // ---- export the candidates, exchange, merge ---------------------------------------------------------------------
+        // export buffers: room for every rank's entries, this rank's at slot `me` (the in-place form of ncclAllGather)
+        const size_t ek = (size_t)local_cap * 8, ec = (size_t)local_cap * 4;
+        if ((rc = ctx->tr_pos.ensure((size_t)W * (2 * ek + ec) + 256))) return rc;
+        unsigned char* eb = ctx->tr_pos.as<unsigned char>();
+        uint64_t* x_keys = (uint64_t*)eb; uint64_t* x_pos = (uint64_t*)(eb + (size_t)W * ek); uint32_t* x_cnt = (uint32_t*)(eb + (size_t)W * 2 * ek);
+        uint32_t* d_counter = ctx->overflow.as<uint32_t>() + 1;
+        table_export_kernel<<<(local_cap + 255) / 256, 256, 0, st>>>(a.tkeys, a.tcnt, a.tpos, local_cap, x_keys + (size_t)me * local_cap, x_cnt + (size_t)me * local_cap,
+                                                                      x_pos + (size_t)me * local_cap, d_counter);
+        ctx->launches++;
+        FPM_CUDA(cudaGetLastError());
+        uint32_t h4[4] = {0, 0, 0, 0};     // overflow, exported entries, maxkey count
+        uint64_t h_maxpos = ~0ULL;
+        FPM_CUDA(cudaMemcpyAsync(h4, ctx->overflow.p, 8, cudaMemcpyDeviceToHost, st));
+        FPM_CUDA(cudaMemcpyAsync(h4 + 2, ctx->maxcnt.p, 4, cudaMemcpyDeviceToHost, st));
+        FPM_CUDA(cudaMemcpyAsync(&h_maxpos, ctx->maxpos.p, 8, cudaMemcpyDeviceToHost, st));
+        FPM_CUDA(cudaStreamSynchronize(st));
+        h_local_maxcnt = h4[2];
+        if ((rc = gather_meta(h4[1], h4[0], h4[2], h_maxpos))) return rc;
+        bool too_many = false;
+        uint64_t total_entries = 0, max_entries = 0, maxkey_cnt = 0, maxkey_pos = ~0ULL;
+        std::vector<uint32_t> n_of(W);
+        for (int r = 0; r < W; r++) {
+            n_of[r] = (uint32_t)h_meta[4 * r]; total_entries += n_of[r]; max_entries = std::max<uint64_t>(max_entries, n_of[r]);
+            too_many |= h_meta[4 * r + 1] != 0; maxkey_cnt += h_meta[4 * r + 2]; maxkey_pos = std::min(maxkey_pos, h_meta[4 * r + 3]);
+        }
+        uint32_t nq = 0, nd = 0;
+        if (!too_many) {
+            // all ranks send the same number of elements (the largest export); only the first n_of[r] of each slot count
+            FPM_NCCL(api, api->AllGather(x_keys + (size_t)me * local_cap, x_keys, ek, ncclUint8, comm, st));
+            FPM_NCCL(api, api->AllGather(x_pos + (size_t)me * local_cap, x_pos, ek, ncclUint8, comm, st));
+            FPM_NCCL(api, api->AllGather(x_cnt + (size_t)me * local_cap, x_cnt, ec, ncclUint8, comm, st));
+            merged_cap = std::max<uint32_t>(pow2ceil(2 * total_entries + 64), 64);
+            const size_t mk = (size_t)merged_cap * 8, mc = (size_t)merged_cap * 4;
+            if ((rc = ctx->scratch.ensure(2 * mk + mc + 256 + (size_t)merged_cap * 8))) return rc;
+            unsigned char* mb = ctx->scratch.as<unsigned char>();
+            m_keys = (uint64_t*)mb; m_pos = (uint64_t*)(mb + mk); m_cnt = (uint32_t*)(mb + 2 * mk);
+            uint32_t* m_extra = (uint32_t*)(mb + 2 * mk + mc);           // [0] merged mask, [1] overflow, [2] maxkey count, [4..5] maxkey position, [8..] n_of_rank
+            uint64_t* m_sort = (uint64_t*)(mb + 2 * mk + mc + 256);      // select's global sort scratch
+            FPM_CUDA(cudaMemsetAsync(m_keys, 0xff, mk, st));
+            FPM_CUDA(cudaMemsetAsync(m_pos, 0xff, mk, st));
+            FPM_CUDA(cudaMemsetAsync(m_cnt, 0, mc, st));
+            uint32_t ex[64];
+            memset(ex, 0, sizeof ex);
+            if (W > 48) { set_error("more than 48 ranks"); return FPM_ERR_UNSUPPORTED; }
+            ex[0] = merged_cap - 1; ex[2] = (uint32_t)maxkey_cnt; memcpy(ex + 4, &maxkey_pos, 8);
+            for (int r = 0; r < W; r++) ex[8 + r] = n_of[r];
+            FPM_CUDA(cudaMemcpyAsync(m_extra, ex, sizeof ex, cudaMemcpyHostToDevice, st));
+            table_import_kernel<<<(uint32_t)(((uint64_t)W * local_cap + 255) / 256), 256, 0, st>>>(x_keys, x_cnt, x_pos, m_extra + 8, local_cap, (uint32_t)W, m_keys, m_cnt, m_pos,
+                                                                                                 merged_cap - 1, m_extra + 1);
+            ctx->launches++;
+            FPM_CUDA(cudaGetLastError());
+            // ---- bottom-s of the merged table: the same kernel as on one GPU ----------------------------------------------
+            SelectArgs sa;
+            sa.tkeys = m_keys; sa.tcnt = m_cnt; sa.tpos = m_pos; sa.toff = ctx->toff.as<uint64_t>(); sa.tmask = m_extra;
+            sa.maxkey_cnt = m_extra + 2; sa.maxkey_pos = (const uint64_t*)(m_extra + 4); sa.active = ctx->active.as<uint8_t>();
+            sa.sketch_size = s; sa.min_cov = p->min_cov;
+            sa.sort_cap = std::min<uint32_t>(SK_SORT_CAP, merged_cap);
+            sa.scratch = merged_cap > SK_SORT_CAP ? m_sort : nullptr;
+            sa.out_hashes = d_out_hashes; sa.out_counts = want_counts ? d_out_counts : nullptr; sa.out_firstpos = nullptr;
+            sa.out_n = d_out_n;
+            uint32_t* d_stat = ctx->stat.as<uint32_t>();
+            sa.stat_nq = d_stat; sa.stat_nd = d_stat + 1; sa.stat_topcnt = d_stat + 2;
+            ctx->time_begin(FPM_KERNEL_SKETCH_SELECT);
+            launch_sketch_select(1, (size_t)sa.sort_cap * 8, st, sa);
+            ctx->time_end();
+            ctx->launches++;
+            FPM_CUDA(cudaGetLastError());
+            uint32_t h_stat[3] = {0, 0, 0};
+            FPM_CUDA(cudaMemcpyAsync(h_stat, d_stat, 12, cudaMemcpyDeviceToHost, st));
+            FPM_CUDA(cudaStreamSynchronize(st));
+            nq = h_stat[0]; nd = h_stat[1]; h_topcnt = h_stat[2];
+        }
+        // ---- decide: the same rule on every rank, from the same numbers -----------------------------------------------
+        const bool too_few = !too_many && !pl.all && nq < s;
+        if (!too_many && !too_few) { h_outn = std::min<uint32_t>(nq, s); break; }
+        if (pass == 11) { set_error("bottom-s selection did not converge"); return FPM_ERR_CUDA; }
+        const double cur = pl.all ? 1.0 : ((double)pl.thresh + 1.0) / ((double)full + 1.0);
+        double next;
+        if (too_many) next = cur / 4;
+        else next = nq >= 16 ? cur * 1.15 * (double)target / (double)nq : cur * 16;
+        if (next >= 1.0) { pl.all = true; pl.thresh = full; next = 1.0; }
+        else { pl.all = false; pl.thresh = scale_threshold(full, next); }
+        double nd_next = ((double)nd + 16) * (next / cur) * 1.3 + 256;
+        if (too_many) nd_next = (double)local_cap;
+        if (nd_next > (double)n_total) nd_next = (double)n_total;
+        pl.cap = std::max(pow2ceil((uint64_t)(2 * nd_next)), pow2ceil(4 * target));
+    }
+
+    // ---- order-dependent multiplicity of the largest element (full sketch only) ----------------------------------------
+    if (want_counts && h_outn == s && h_topcnt > p->min_cov) {
+        std::vector<uint32_t> tot(s);
+        FPM_CUDA(cudaMemcpyAsync(tot.data(), d_out_counts, sizeof(uint32_t) * s, cudaMemcpyDeviceToHost, st));
+        // this rank's occurrences of every final hash, then everybody's
+        if ((rc = ctx->tr_cursor.ensure(sizeof(uint32_t) * ((size_t)W + 2) * s))) return rc;
+        uint32_t* d_loc_all = ctx->tr_cursor.as<uint32_t>();               // [W][s]; cursors behind it
+        table_lookup_counts_kernel<<<(s + 255) / 256, 256, 0, st>>>(d_out_hashes, s, ctx->tkeys.as<uint64_t>(), ctx->tcnt.as<uint32_t>(), local_cap - 1, h_local_maxcnt,
+                                                                    d_loc_all + (size_t)me * s);
+        ctx->launches++;
+        FPM_CUDA(cudaGetLastError());
+        FPM_NCCL(api, api->AllGather(d_loc_all + (size_t)me * s, d_loc_all, (size_t)s * 4, ncclUint8, comm, st));
+        std::vector<uint32_t> loc((size_t)W * s);
+        FPM_CUDA(cudaMemcpyAsync(loc.data(), d_loc_all, sizeof(uint32_t) * (size_t)W * s, cudaMemcpyDeviceToHost, st));
+        FPM_CUDA(cudaStreamSynchronize(st));
+        std::vector<uint64_t> off_all(s), off_mine(s);
+        std::vector<uint32_t> cap_mine(s);
+        uint64_t total = 0;
+        for (uint32_t b = 0; b < s; b++) {
+            off_all[b] = total;
+            uint64_t before = 0, sum = 0;
+            for (int r = 0; r < W; r++) { if (r < me) before += loc[(size_t)r * s + b]; sum += loc[(size_t)r * s + b]; }
+            if (sum != tot[b]) { set_error("internal: per-rank counts of a sketch hash do not add up"); return FPM_ERR_CUDA; }
+            off_mine[b] = total + before; cap_mine[b] = loc[(size_t)me * s + b];
+            total += tot[b];
+        }
+        // buckets: [total] positions (zero = not mine), joined by an all-reduce; offsets of both views; capacities of mine
+        if ((rc = ctx->tr_off.ensure(sizeof(uint64_t) * 2 * s + sizeof(uint32_t) * s + 64))) return rc;
+        uint64_t* d_off_all = ctx->tr_off.as<uint64_t>(); uint64_t* d_off_mine = d_off_all + s; uint32_t* d_cap_mine = (uint32_t*)(d_off_mine + s);
+        if ((rc = ctx->glist.ensure(sizeof(uint64_t) * std::max<uint64_t>(total, 1) + 64))) return rc;
+        uint64_t* d_pos = ctx->glist.as<uint64_t>();
+        uint32_t* d_cursor = d_loc_all + (size_t)W * s;
+        FPM_CUDA(cudaMemcpyAsync(d_off_all, off_all.data(), sizeof(uint64_t) * s, cudaMemcpyHostToDevice, st));
+        FPM_CUDA(cudaMemcpyAsync(d_off_mine, off_mine.data(), sizeof(uint64_t) * s, cudaMemcpyHostToDevice, st));
+        FPM_CUDA(cudaMemcpyAsync(d_cap_mine, cap_mine.data(), sizeof(uint32_t) * s, cudaMemcpyHostToDevice, st));
+        FPM_CUDA(cudaMemsetAsync(d_pos, 0, sizeof(uint64_t) * std::max<uint64_t>(total, 1), st));
+        FPM_CUDA(cudaMemsetAsync(d_cursor, 0, sizeof(uint32_t) * s, st));
+        FPM_CUDA(cudaMemcpyAsync(ctx->thresh.p, &pl.thresh, 8, cudaMemcpyHostToDevice, st));
+        SketchArgs a;
+        fill_args(a);
+        a.fin_hashes = d_out_hashes; a.fin_n = d_out_n; a.tr_off = d_off_mine; a.tr_cap = d_cap_mine; a.tr_cursor = d_cursor; a.tr_pos = d_pos;
+        FPM_CUDA(cudaMemcpyAsync(ctx->args.p, &a, sizeof a, cudaMemcpyHostToDevice, st));
+        if (n_bytes) {
+            ctx->time_begin(FPM_KERNEL_SKETCH_HASH);
+            g_hash_launch[K - 1](canon, st, ctx->args.as<SketchArgs>(), 0, n_bytes, 1);
+            ctx->time_end();
+            ctx->launches++;
+            FPM_CUDA(cudaGetLastError());
+        }
+        FPM_NCCL(api, api->AllReduce(d_pos, d_pos, total, ncclUint64, ncclSum, comm, st));
+        const uint32_t zero = 0;
+        uint32_t* d_g0 = ctx->overflow.as<uint32_t>();
+        FPM_CUDA(cudaMemcpyAsync(d_g0, &zero, 4, cudaMemcpyHostToDevice, st));
+        launch_sketch_topcount(1, st, d_g0, s, p->min_cov, d_off_all, d_out_counts, d_pos, d_out_counts);
+        ctx->launches++;
+        FPM_CUDA(cudaGetLastError());
+    }
+    if (d_out_kmers) {
+        FPM_CUDA(cudaMemsetAsync(d_out_kmers, 0, sizeof(uint64_t), st));
+        if (n_bytes) {
+            SketchArgs a;
+            memset(&a, 0, sizeof a);
+            a.seq = d_seq; a.n_bytes = n_bytes; a.group_off = ctx->goff.as<uint64_t>(); a.n_groups = 1;
+            a.fold_case = !p->preserve_case;
+            FPM_CUDA(cudaMemcpyAsync(ctx->args.p, &a, sizeof a, cudaMemcpyHostToDevice, st));
+            g_count_launch[K - 1]((uint32_t)((n_bytes + SK_TILE_WINDOWS - 1) / SK_TILE_WINDOWS), st, ctx->args.as<SketchArgs>(), (unsigned long long*)d_out_kmers);
+            ctx->launches++;
+            FPM_CUDA(cudaGetLastError());
+        }
+        FPM_NCCL(api, api->AllReduce(d_out_kmers, d_out_kmers, 1, ncclUint64, ncclSum, comm, st));
+    }
+    FPM_CUDA(cudaStreamSynchronize(st));
+    return FPM_OK;
+}
+
 }  // namespace fpm
 
 using namespace fpm;
@@ -369,6 +716,14 @@ int fpm_sketch_batch_dev(fpm_ctx* ctx, const fpm_sketch_params* p, const uint8_t
     if (!ctx) { set_error("ctx is NULL"); return FPM_ERR_ARG; }
     FPM_CUDA(cudaSetDevice(ctx->device));
     return sketch_batch_dev_impl(ctx, p, d_seq, seq_bytes, h_group_offsets, n_groups, d_out_hashes, d_out_counts, d_out_n, d_out_kmers);
+}
+
+int fpm_sketch_reads_sharded_dev(fpm_ctx* ctx, const fpm_sketch_params* p, const uint8_t* d_seq, uint64_t seq_bytes, uint64_t* d_out_hashes,
+                                 uint32_t* d_out_counts, uint32_t* d_out_n, uint64_t* d_out_kmers)
+{
+    if (!ctx) { set_error("ctx is NULL"); return FPM_ERR_ARG; }
+    FPM_CUDA(cudaSetDevice(ctx->device));
+    return sketch_reads_sharded_impl(ctx, p, d_seq, seq_bytes, d_out_hashes, d_out_counts, d_out_n, d_out_kmers);
 }
 
 int fpm_sketch_batch(fpm_ctx* ctx, const fpm_sketch_params* p, const uint8_t* seq, uint64_t seq_bytes,

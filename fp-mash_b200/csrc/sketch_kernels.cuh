@@ -70,6 +70,7 @@ struct SketchArgs {
     // hot-loop constants handed over as data ('ACGT' table for PRMT, Murmur block addends)
     uint32_t c_tbl;
     uint64_t c_add1, c_add2, c_add1s;   // c_add1s = c_add1 + 5 * seed (first Murmur block, sketch_tables.cuh)
+    uint64_t pos_base;           // added to every stream position stored (a rank's part of one read set spread over GPUs)
 };
 
 // ---------------------------------------------------------------------------------------
@@ -250,13 +251,13 @@ static __device__ __noinline__ void sketch_emit(const SketchArgs& a, uint64_t h,
         if (lo < n && fin[lo] == h) {
             uint64_t b = (uint64_t)g * a.sketch_size + lo;
             uint32_t idx = atomicAdd(&a.tr_cursor[b], 1u);
-            if (idx < a.tr_cap[b]) a.tr_pos[a.tr_off[b] + idx] = pos;
+            if (idx < a.tr_cap[b]) a.tr_pos[a.tr_off[b] + idx] = pos + a.pos_base;
         }
         return;
     }
     if (h == SK_EMPTY) {   // the one value that cannot be a table key
         atomicAdd(&a.maxkey_cnt[g], 1u);
-        atomicMin((unsigned long long*)&a.maxkey_pos[g], (unsigned long long)pos);
+        atomicMin((unsigned long long*)&a.maxkey_pos[g], (unsigned long long)(pos + a.pos_base));
         return;
     }
     const uint64_t base = a.toff[g];
@@ -266,7 +267,7 @@ static __device__ __noinline__ void sketch_emit(const SketchArgs& a, uint64_t h,
         unsigned long long prev = atomicCAS((unsigned long long*)&a.tkeys[base + slot], (unsigned long long)SK_EMPTY, (unsigned long long)h);
         if (prev == SK_EMPTY || prev == h) {
             atomicAdd(&a.tcnt[base + slot], 1u);
-            atomicMin((unsigned long long*)&a.tpos[base + slot], (unsigned long long)pos);
+            atomicMin((unsigned long long*)&a.tpos[base + slot], (unsigned long long)(pos + a.pos_base));
             return;
         }
         slot = (slot + 1) & mask;

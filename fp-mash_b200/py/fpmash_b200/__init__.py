@@ -139,6 +139,7 @@ lib.fpm_dist_sharded_dev.argtypes = [_VP, C.POINTER(DistParams), C.POINTER(Panel
                                      C.POINTER(Block), _VP]
 lib.fpm_dist_hits_sharded_dev.argtypes = [_VP, C.POINTER(DistParams), C.POINTER(Panel), C.c_uint64, C.POINTER(Panel), C.c_uint64, _VP, C.c_uint64,
                                           u64p, C.POINTER(Block), _VP]
+lib.fpm_sketch_reads_sharded_dev.argtypes = [_VP, C.POINTER(SketchParams), _VP, C.c_uint64, _VP, _VP, _VP, _VP]
 lib.fpm_multi_create.argtypes = [_VP, C.c_int, C.POINTER(_VP)]
 lib.fpm_multi_destroy.argtypes = [_VP]
 lib.fpm_multi_destroy.restype = None
@@ -186,7 +187,7 @@ EXPORTED = ["fpm_abi_version", "fpm_device_count", "fpm_ctx_create", "fpm_ctx_de
             "fpm_shard_range", "fpm_dist_grid_shape", "fpm_dist_block", "fpm_comm_get_unique_id", "fpm_comm_init_rank", "fpm_comm_adopt",
             "fpm_comm_destroy", "fpm_comm_rank", "fpm_comm_size", "fpm_dist_sharded_dev", "fpm_dist_hits_sharded_dev",
             "fpm_multi_create", "fpm_multi_destroy", "fpm_multi_size", "fpm_multi_ctx", "fpm_dist_tile_multi", "fpm_dist_hits_multi",
-            "fpm_sketch_batch_multi"]
+            "fpm_sketch_batch_multi", "fpm_sketch_reads_sharded_dev"]
 
 
 def _check(rc):
@@ -596,6 +597,11 @@ class Context:
 
     def comm_destroy(self):
         _check(lib.fpm_comm_destroy(self._h))
+
+    def sketch_reads_sharded_dev(self, d_seq_ptr, seq_bytes, params, d_hashes_ptr, d_counts_ptr, d_n_ptr, d_kmers_ptr=None):
+        """Collective: this rank's contiguous part of ONE read set in, the complete sketch out on every rank."""
+        _check(lib.fpm_sketch_reads_sharded_dev(self._h, C.byref(params), _VP(d_seq_ptr), int(seq_bytes), _VP(d_hashes_ptr),
+                                                _VP(d_counts_ptr) if d_counts_ptr else None, _VP(d_n_ptr), _VP(d_kmers_ptr) if d_kmers_ptr else None))
 
     def dist_sharded_dev(self, ref_shard_ptrs, n_ref_total, qry_shard_ptrs, n_qry_total, sketch_size, kmer_size, kmer_space, d_out_ptr,
                          out_capacity, d_steps_ptr=None, max_distance=1.0, max_pvalue=1.0, sorted_unique=True):

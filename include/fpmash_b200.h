@@ -289,6 +289,18 @@ int fpm_dist_hits_sharded_dev(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_
                               const fpm_panel* d_qry_shard, uint64_t n_qry_total, fpm_hit* d_out, uint64_t capacity, uint64_t* n_hits,
                               fpm_block* block, uint64_t* d_merge_steps /* nullable */);
 
+/* ONE read set spread over the ranks (`mash sketch -r`: initFromReads + sketchFile turn a whole read set into a single
+ * sketch on one thread, Sketch.cpp:203-210).  Collective.  Every rank passes a contiguous part of the read stream, whole
+ * records in fpm_sketch_batch's layout, rank order = stream order.  Each rank hashes its part into a counting table of
+ * its own; the candidates (hash, count, first position) are all-gathered and merged by key, and the bottom-s with
+ * multiplicity >= min_cov is selected from the merged table (MinHashHeap's final set is order independent).
+ * The one order-dependent number -- HashSet's count of the largest element of a full sketch -- is settled from the global
+ * stream positions of the final hashes (an all-reduce over their position buckets).  Every rank receives the complete
+ * result: d_out_hashes [sketch_size], d_out_counts [sketch_size] or NULL, d_out_n [1], d_out_kmers [1] or NULL --
+ * bit-identical to fpm_sketch_batch_dev over the concatenated stream.  Nucleotide alphabet only.                      */
+int fpm_sketch_reads_sharded_dev(fpm_ctx* ctx, const fpm_sketch_params* p, const uint8_t* d_seq, uint64_t seq_bytes,
+                                 uint64_t* d_out_hashes, uint32_t* d_out_counts, uint32_t* d_out_n, uint64_t* d_out_kmers);
+
 /* One process driving all GPUs of the box (what `mash dist` and `mash sketch` do): the panels are in host memory, so each
  * GPU uploads its two blocks and no collective is needed.  One host thread per GPU inside the call; results arrive in
  * `out` exactly as from the single-GPU entry point (full query-major matrix / hits in the reference's output order).  */

@@ -143,3 +143,76 @@ def test_sharded_dist_over_nccl_equals_single_gpu(fpm, tmp_path, world):
     for p in procs:
         out, err = p.communicate(timeout=600)
         assert p.returncode == 0 and "ok" in out, err[-3000:]
+
+
+READS_WORKER = r"""
+import os, sys
+root = %(root)r
+for p in (os.path.join(root, "fp-mash_b200", "py"), os.path.join(root, "tests")):
+    sys.path.insert(0, p)
+import numpy as np, torch, torch.distributed as dist
+import fpmash_b200 as fpm
+from fpmash_b200 import sharding as sh
+from util import mutate, random_dna
+rank, world = int(sys.argv[1]), %(world)d
+torch.cuda.set_device(rank)
+dev = torch.device("cuda", rank)
+dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%(port)d", rank=rank, world_size=world, device_id=dev)
+ctx = fpm.Context(rank)
+ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+sh.init_comm(ctx)
+rng = np.random.default_rng(12)                      # the same read set on every rank; each keeps a contiguous part
+genome = random_dna(rng, 60000)
+reads = []
+for _ in range(14000):                               # ~35x of 150 bp reads with errors, both strands, a few N
+    p = int(rng.integers(0, len(genome) - 150))
+    r = mutate(rng, genome[p:p + 150], 0.01)
+    if rng.random() < 0.5:
+        r = r[::-1].translate(bytes.maketrans(b"ACGT", b"TGCA"))
+    if rng.random() < 0.02:
+        r = r[:70] + b"N" + r[71:]
+    reads.append(r)
+tiny = [random_dna(rng, 400)]                        # fewer windows than sketch slots: the accept-all path
+for case, (recs, k, s, m) in enumerate([(reads, 21, 1000, 2), (reads, 21, 100, 2), (reads, 21, 100, 1), (reads, 21, 300, 3), (reads, 16, 200, 2), (tiny, 21, 1000, 1),
+                                        (reads[:3], 21, 1000, 2)]):
+    cut = [len(recs) * r // world for r in range(world + 1)]
+    if case == 6:
+        cut = [0] + [len(recs)] * world                # everything on rank 0, the other ranks hold nothing
+    mine = b"".join(x + b"\0" for x in recs[cut[rank]:cut[rank + 1]])
+    buf = torch.zeros(max(len(mine), 16) + 64, dtype=torch.uint8, device=dev)
+    if mine:
+        buf[:len(mine)] = torch.frombuffer(bytearray(mine), dtype=torch.uint8).to(dev)
+    prm = fpm.make_sketch_params(k=k, s=s, min_cov=m, want_counts=True)
+    oh = torch.zeros(s, dtype=torch.int64, device=dev); oc = torch.zeros(s, dtype=torch.int32, device=dev)
+    on = torch.zeros(1, dtype=torch.int32, device=dev); ok = torch.zeros(1, dtype=torch.int64, device=dev)
+    ctx.sketch_reads_sharded_dev(buf.data_ptr(), len(mine), prm, oh.data_ptr(), oc.data_ptr(), on.data_ptr(), ok.data_ptr())
+    torch.cuda.synchronize()
+    n = int(on.item())
+    want = ctx.sketch_records([recs], k=k, s=s, min_cov=m, want_counts=True, want_kmers=True)[0]      # the whole read set on this GPU alone
+    assert n == len(want["hashes"]), (case, rank, n, len(want["hashes"]))
+    assert np.array_equal(oh.cpu().numpy().view(np.uint64)[:n], want["hashes"]), (case, rank, "hashes")
+    assert np.array_equal(oc.cpu().numpy().view(np.uint32)[:n], want["counts"]), (case, rank, "counts")
+    assert int(ok.item()) == want["kmers"], (case, rank, "windows")
+    dist.barrier()
+ctx.comm_destroy()
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_read_set_over_several_gpus_equals_single_gpu(fpm, tmp_path, world):
+    """One read set (mash sketch -r, -m 1..3, counts with the reference's order-dependent top count) spread over the ranks:
+    hashes, multiplicities and window count identical to the single-GPU sketch of the whole stream."""
+    if fpm.device_count() < world:
+        pytest.skip("needs %d GPUs; run under gpurun --gpus %d" % (world, world))
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / "w.py"
+    script.write_text(READS_WORKER % {"root": ROOT, "port": port, "world": world})
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for r in range(world)]
+    for p in procs:
+        out, err = p.communicate(timeout=600)
+        assert p.returncode == 0 and "ok" in out, err[-3000:]
