@@ -63,8 +63,21 @@ struct fpm_ctx {
     int comm_rank = 0, comm_world = 0;
     bool comm_owned = false;
     fpm::DevBuf d_xq, d_xr;                      // this rank's query / reference block after the exchange step
+    // resident reference panel (fpm_dist_set_reference): its device copy and its index survive across query chunks
+    bool ref_set = false;
+    fpm_panel ref_dev = {nullptr, nullptr, nullptr, 0, 0};
+    uint32_t ref_max = 0;
+    struct RefIndexState {                       // what dist_rank_panels built for the reference panel (dist_rank.cu)
+        bool valid = false, unsorted = false, uf_valid = false;
+        const void* hashes = nullptr;            // identity of the panel it was built for
+        uint64_t n_r = 0, rows_r = 0, m = 0, pr = 0;
+        const uint64_t* ks = nullptr;            // sorted keys
+        uint32_t n_buckets = 0;
+    } rix;
+    fpm::DevBuf d_p32q, d_uf;                    // packed query tiles; union-find parents / component sizes of the references
     bool no_dist_prune = false;                  // tests: merge every pair
     bool no_dist_group = false;                  // tests: prune, but leave the panels in their own order
+    bool force_dist_saturate = false;            // tests: always bound the marking walks by the components' sizes
     bool force_dist64 = false;                   // tests: run the 64-bit tile kernel although the 32-bit rank path applies
     // optional per-kernel event timing (bench roofline): pairs of events around each launch
     bool timing = false;

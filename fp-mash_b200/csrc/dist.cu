@@ -970,41 +970,52 @@ int fpm_dist_tile_dev(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* d
 }
 
 // host panels -> device copies in ctx->d_rs / d_qs (hashes | lengths | sizes); also the largest sketch of each
+// host panel -> device copy in `buf` (hashes | lengths | sizes); also the largest sketch
+static int upload_panel(fpm_ctx* ctx, const fpm_panel* h, DevBuf& buf, fpm_panel* d, uint32_t* max_size)
+{
+    int rc;
+    *max_size = 0;
+    for (uint64_t i = 0; i < h->n; i++) *max_size = std::max(*max_size, h->sizes[i]);
+    if (*max_size > h->stride) { set_error("a sketch size exceeds the panel stride"); return FPM_ERR_ARG; }
+    cudaStream_t st = ctx->stream;
+    const size_t hb = h->n * h->stride * 8;
+    if ((rc = buf.ensure(hb + h->n * 12 + 64))) return rc;
+    unsigned char* b = buf.as<unsigned char>();
+    *d = *h;
+    d->hashes = (const uint64_t*)b; d->lengths = (const uint64_t*)(b + hb); d->sizes = (const uint32_t*)(b + hb + h->n * 8);
+    if (hb) FPM_CUDA(cudaMemcpyAsync((void*)d->hashes, h->hashes, hb, cudaMemcpyHostToDevice, st));
+    FPM_CUDA(cudaMemcpyAsync((void*)d->lengths, h->lengths, h->n * 8, cudaMemcpyHostToDevice, st));
+    FPM_CUDA(cudaMemcpyAsync((void*)d->sizes, h->sizes, h->n * 4, cudaMemcpyHostToDevice, st));
+    return FPM_OK;
+}
+
+// ref == nullptr: the resident reference panel of fpm_dist_set_reference
 static int upload_panels(fpm_ctx* ctx, const fpm_panel* ref, const fpm_panel* qry, fpm_panel* dr, fpm_panel* dq, uint32_t* mr, uint32_t* mq)
 {
     int rc;
-    *mr = *mq = 0;
-    for (uint64_t i = 0; i < ref->n; i++) *mr = std::max(*mr, ref->sizes[i]);
-    for (uint64_t i = 0; i < qry->n; i++) *mq = std::max(*mq, qry->sizes[i]);
-    if (*mr > ref->stride || *mq > qry->stride) { set_error("a sketch size exceeds the panel stride"); return FPM_ERR_ARG; }
-    cudaStream_t st = ctx->stream;
-    size_t rh = ref->n * ref->stride * 8, qh = qry->n * qry->stride * 8;
-    if ((rc = ctx->d_rs.ensure(rh + ref->n * 12 + 64))) return rc;
-    if ((rc = ctx->d_qs.ensure(qh + qry->n * 12 + 64))) return rc;
-    unsigned char* br = ctx->d_rs.as<unsigned char>();
-    unsigned char* bq = ctx->d_qs.as<unsigned char>();
-    *dr = *ref; *dq = *qry;
-    dr->hashes = (const uint64_t*)br; dr->lengths = (const uint64_t*)(br + rh); dr->sizes = (const uint32_t*)(br + rh + ref->n * 8);
-    dq->hashes = (const uint64_t*)bq; dq->lengths = (const uint64_t*)(bq + qh); dq->sizes = (const uint32_t*)(bq + qh + qry->n * 8);
-    if (rh) FPM_CUDA(cudaMemcpyAsync((void*)dr->hashes, ref->hashes, rh, cudaMemcpyHostToDevice, st));
-    FPM_CUDA(cudaMemcpyAsync((void*)dr->lengths, ref->lengths, ref->n * 8, cudaMemcpyHostToDevice, st));
-    FPM_CUDA(cudaMemcpyAsync((void*)dr->sizes, ref->sizes, ref->n * 4, cudaMemcpyHostToDevice, st));
-    if (qh) FPM_CUDA(cudaMemcpyAsync((void*)dq->hashes, qry->hashes, qh, cudaMemcpyHostToDevice, st));
-    FPM_CUDA(cudaMemcpyAsync((void*)dq->lengths, qry->lengths, qry->n * 8, cudaMemcpyHostToDevice, st));
-    FPM_CUDA(cudaMemcpyAsync((void*)dq->sizes, qry->sizes, qry->n * 4, cudaMemcpyHostToDevice, st));
-    return FPM_OK;
+    if (ref) {
+        ctx->ref_set = false;                                            // an explicit reference panel replaces the resident one
+        ctx->rix.valid = false;
+        if ((rc = upload_panel(ctx, ref, ctx->d_rs, dr, mr))) return rc;
+    } else {
+        if (!ctx->ref_set) { set_error("no reference panel: pass one, or call fpm_dist_set_reference first"); return FPM_ERR_ARG; }
+        *dr = ctx->ref_dev; *mr = ctx->ref_max;
+    }
+    return upload_panel(ctx, qry, ctx->d_qs, dq, mq);
 }
 
 static int dist_tile_host(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* ref, const fpm_panel* qry, fpm_pair* out, bool positional, uint64_t h_ld = 0)
 {
     if (!ctx) { set_error("ctx is NULL"); return FPM_ERR_ARG; }
+    if (!ref && ctx->ref_set) ref = &ctx->ref_dev;                       // resident reference panel (only n / stride are read on the host)
+    const bool resident = ref == &ctx->ref_dev;
     int rc = check_dist(p, ref, qry);
     if (rc) return rc;
     if (ref->n == 0 || qry->n == 0) return FPM_OK;
     FPM_CUDA(cudaSetDevice(ctx->device));
     uint32_t mr = 0, mq = 0;
     fpm_panel dr, dq;
-    if ((rc = upload_panels(ctx, ref, qry, &dr, &dq, &mr, &mq))) return rc;
+    if ((rc = upload_panels(ctx, resident ? nullptr : ref, qry, &dr, &dq, &mr, &mq))) return rc;
     if ((rc = ctx->d_out.ensure(ref->n * qry->n * sizeof(fpm_pair)))) return rc;
     cudaStream_t st = ctx->stream;
     if (positional) {
@@ -1088,6 +1099,8 @@ int fpm::dist_hits_host(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel*
 {
     if (!ctx) { set_error("ctx is NULL"); return FPM_ERR_ARG; }
     if (!n_hits || (!out && capacity)) { set_error("NULL argument"); return FPM_ERR_ARG; }
+    if (!ref && ctx->ref_set) ref = &ctx->ref_dev;
+    const bool resident = ref == &ctx->ref_dev;
     int rc = check_dist(p, ref, qry);
     if (rc) return rc;
     *n_hits = 0;
@@ -1095,7 +1108,7 @@ int fpm::dist_hits_host(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel*
     FPM_CUDA(cudaSetDevice(ctx->device));
     uint32_t mr = 0, mq = 0;
     fpm_panel dr, dq;
-    if ((rc = upload_panels(ctx, ref, qry, &dr, &dq, &mr, &mq))) return rc;
+    if ((rc = upload_panels(ctx, resident ? nullptr : ref, qry, &dr, &dq, &mr, &mq))) return rc;
     // d_hits = counter | appended records | sorted records (dist_hits_run's own ensure() is then a no-op: the buffer only grows)
     if ((rc = ctx->d_hits.ensure(2 * capacity * sizeof(fpm_hit) + 64))) return rc;
     fpm_hit* d_sorted = reinterpret_cast<fpm_hit*>(ctx->d_hits.as<unsigned char>() + 32) + capacity;
@@ -1106,6 +1119,21 @@ int fpm::dist_hits_host(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel*
 }
 
 extern "C" {
+
+int fpm_dist_set_reference(fpm_ctx* ctx, const fpm_panel* ref)
+{
+    if (!ctx) { set_error("ctx is NULL"); return FPM_ERR_ARG; }
+    ctx->ref_set = false;
+    ctx->rix.valid = false;
+    if (!ref) return FPM_OK;
+    if (!ref->sizes || !ref->lengths || (!ref->hashes && ref->n * ref->stride)) { set_error("NULL panel array"); return FPM_ERR_ARG; }
+    FPM_CUDA(cudaSetDevice(ctx->device));
+    int rc = upload_panel(ctx, ref, ctx->d_rs, &ctx->ref_dev, &ctx->ref_max);
+    if (rc) return rc;
+    FPM_CUDA(cudaStreamSynchronize(ctx->stream));                        // the caller may release its host panel now
+    ctx->ref_set = true;
+    return FPM_OK;
+}
 
 int fpm_fp_positional_tile(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* ref, const fpm_panel* qry, fpm_pair* out)
 {

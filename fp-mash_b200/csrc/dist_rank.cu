@@ -1,19 +1,26 @@
-// dist_rank.cu -- order-preserving 32-bit compression of the sketch panels for dist_tile32_kernel.
+// dist_rank.cu -- order-preserving 32-bit codes for the sketch panels of dist_tile32_kernel, and the inverted index.
 //
-// compareSketches (CommandDistance.cpp:365-400) looks only at the ORDER and EQUALITY of the hashes of the two
-// lists, never at their values.  So the 64-bit hashes of both panels are replaced by their dense rank in the
-// sorted set of all distinct hashes of the call (equal hashes -> equal rank, h1 < h2 -> rank1 < rank2): exact,
-// and a merge step then costs one 32-bit shared-memory load and one 32-bit compare per list instead of a 64-bit
-// load (two shared-memory wavefronts) and a two-instruction compare.  0xffffffff is the +inf sentinel.
+// compareSketches (CommandDistance.cpp:365-400) only ever compares a hash of the REFERENCE list with a hash of the QUERY
+// list, and only for order and equality.  So the 64-bit hashes are replaced by 32-bit codes that keep exactly those
+// relations (a merge step then costs one 32-bit shared-memory load and one 32-bit compare per list):
+//   * the reference panel alone is sorted (radix sort of (hash, destination) pairs, a library call) and every distinct
+//     reference hash gets its dense rank r:      code = 2 r + 1;
+//   * a query hash is looked up among the distinct reference hashes (a bucket table over the value range narrows the
+//     binary search to a handful of entries): equal to reference hash r -> code 2 r + 1, otherwise 2 * (number of distinct
+//     reference hashes below it) -- an even code that sits strictly between its neighbours' odd ones.  Two different
+//     query hashes between the same two reference hashes share a code; they are never compared with each other.
+//   0xffffffff is the +inf sentinel.
+// Round 1 sorted both panels together (dense ranks over the union): twice the sort for an all-vs-all, and a reference
+// index that had to be rebuilt for every query chunk.  Now the index is a property of the reference panel alone.
 //
 // Steps (all on the caller's stream):
-//   dist_keys_kernel     every valid element -> (hash, destination index in the packed 32-bit tile layout);
-//                        also validates "strictly ascending" (the fast path's precondition)
-//   cub radix sort       by hash (library call, like the scans below: 2.6 ms for 4*10^7 hashes)
-//   cub inclusive scan   of "differs from predecessor" = dense rank
-//   dist_scatter_kernel  rank -> packed[destination]
-// The sorted array is also an inverted index, which everything below the scatter uses:
-//   dist_post_* kernels  posting lists rank -> reference sketches, and how many postings a marking pass would walk
+//   dist_keys_kernel      every valid reference element -> (hash, destination in the packed tile layout); validates "strictly ascending"
+//   cub radix sort        by hash (library call, like the scans below)
+//   cub inclusive scan    of "differs from predecessor" = dense rank
+//   dist_index_kernel     codes -> packed reference tiles; distinct hashes dk[]; posting lists post[] / run_start[]
+//   dist_bucket_* kernels bucket table start[] over dk[] (heads, suffix-min scan)
+//   dist_qcode_kernel     every query element: lookup -> code -> packed query tiles; validates; counts the postings a marking pass would walk
+// The sorted reference array is the inverted index everything below uses:
 //   dist_uf_* kernels    connected components of the "shares a hash" graph (bounds what a query can reach)
 //   dist_mark_kernel     per query, one bit per reference that shares a hash with it (pairs without one need no merge)
 //   dist_group_panels    both panels re-ordered so that related sketches share tiles; dist_tile_list: tiles with work
@@ -47,57 +54,94 @@ struct HeadFlag {
     __host__ __device__ uint32_t operator()(uint64_t i) const { return i > 0 && keys[i] != keys[i - 1] ? 1u : 0u; }
 };
 
-__global__ void __launch_bounds__(256) dist_scatter_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ dst,
-                                                           const uint32_t* __restrict__ rank, uint64_t m, uint32_t* __restrict__ packed)
-{
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m) return;
-    if (keys[i] != ~0ULL) packed[dst[i]] = rank[i];
-}
-
 // ---------------------------------------------------------------------------------------------------------
-// Pruning support.  The sorted (hash, destination) array puts equal hashes next to each other, so it is also an
-// inverted index: rank -> the reference sketches that contain that hash.  A (query, reference) pair whose lists
-// share no hash at all needs no merge: common = 0 and denom = min(s, |A| + |B|) (CommandDistance.cpp:376-400 with no
-// equal elements).  dist_mark_kernel sets, per query, one bit per reference that shares at least one hash with it.
+// Index of the reference panel.  scal[]: [0] D = number of distinct hashes, [1] number of valid elements, [2] shift of the
+// bucket table, [3] the largest hash (two words), [5] flags.
 // ---------------------------------------------------------------------------------------------------------
-struct RefFlag {
-    const uint64_t* keys;
-    const uint32_t* dst;
-    uint32_t pr;
-    __host__ __device__ uint32_t operator()(uint64_t i) const { return keys[i] != ~0ULL && dst[i] < pr ? 1u : 0u; }
-};
-
-// per sorted element: references go to the compact posting array; the head of every run records where its postings start
-__global__ void __launch_bounds__(256) dist_post_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ dst, const uint32_t* __restrict__ rank,
-                                                        const uint32_t* __restrict__ ref_pos, uint64_t m, uint32_t pr, uint32_t rows_r,
-                                                        uint32_t* __restrict__ post, uint32_t* __restrict__ run_ref_start)
+__global__ void __launch_bounds__(256) dist_index_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ dst, const uint32_t* __restrict__ rank,
+                                                         uint64_t m, uint32_t rows_r, uint32_t* __restrict__ packed, uint64_t* __restrict__ dk,
+                                                         uint32_t* __restrict__ post, uint32_t* __restrict__ run_start, uint32_t* __restrict__ scal)
 {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
     const uint64_t k = keys[i];
-    if (i == 0 || keys[i - 1] != k) run_ref_start[rank[i]] = ref_pos[i];
-    if (k != ~0ULL && dst[i] < pr) {
-        const uint32_t d = dst[i];
-        post[ref_pos[i]] = ((d >> 4) / rows_r) * 16 + (d & 15);           // sketch index from the tile-layout destination
+    if (k == ~0ULL) return;                                                 // the invalid slots sort behind every hash
+    const uint32_t r = rank[i], d = dst[i];
+    packed[d] = 2u * r + 1u;
+    post[i] = ((d >> 4) / rows_r) * 16 + (d & 15);                          // sketch index from the tile-layout destination
+    if (i == 0 || keys[i - 1] != k) { dk[r] = k; run_start[r] = (uint32_t)i; }
+    if (i + 1 == m || keys[i + 1] == ~0ULL) {                              // the last valid element
+        scal[0] = r + 1; scal[1] = (uint32_t)(i + 1);
+        run_start[r + 1] = (uint32_t)(i + 1);
+        scal[3] = (uint32_t)k; scal[4] = (uint32_t)(k >> 32);
     }
 }
 
-// the slot after the last run: total number of reference postings
-__global__ void dist_post_tail_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ dst, const uint32_t* __restrict__ rank,
-                                      const uint32_t* __restrict__ ref_pos, uint64_t m, uint32_t pr, uint32_t* __restrict__ run_ref_start)
+// bucket b of the table holds the distinct hashes h with (h >> shift) == b; shift makes the largest hash land in the last of B
+// buckets.  cum[b] = number of distinct hashes in buckets 0..b: written by the last hash of every bucket, completed by a prefix maximum.
+__global__ void dist_bucket_setup_kernel(uint32_t* __restrict__ scal, uint32_t log2_buckets)
 {
-    const uint64_t i = m - 1;
-    run_ref_start[rank[i] + 1] = ref_pos[i] + ((keys[i] != ~0ULL && dst[i] < pr) ? 1u : 0u);
+    const uint64_t maxkey = ((uint64_t)scal[4] << 32) | scal[3];
+    const int bits = 64 - __clzll((long long)maxkey);
+    scal[2] = bits > (int)log2_buckets ? (uint32_t)(bits - (int)log2_buckets) : 0u;
 }
 
-// number of postings the marking pass would walk: for every query element, the references sharing its hash
-__global__ void __launch_bounds__(256) dist_post_count_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ dst, const uint32_t* __restrict__ rank,
-                                                              const uint32_t* __restrict__ run_ref_start, uint64_t m, uint32_t pr, unsigned long long* total)
+__global__ void __launch_bounds__(256) dist_bucket_tails_kernel(const uint64_t* __restrict__ dk, const uint32_t* __restrict__ scal, uint32_t* __restrict__ cum)
 {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x, D = scal[0];
+    if (r >= D) return;
+    const uint32_t shift = scal[2];
+    const uint64_t b = dk[r] >> shift;
+    if (r + 1 == D || (dk[r + 1] >> shift) != b) cum[b] = r + 1;
+}
+
+struct MaxOp {
+    __host__ __device__ uint32_t operator()(uint32_t a, uint32_t b) const { return a > b ? a : b; }
+};
+
+struct RefIndex {
+    const uint64_t* dk;          // distinct reference hashes, ascending
+    const uint32_t* cum;         // [n_buckets] distinct hashes in buckets 0..b
+    const uint32_t* scal;
+};
+
+// number of distinct reference hashes below h, and whether h is one of them
+__device__ __forceinline__ uint32_t ref_lower_bound(const RefIndex& ix, uint64_t h, uint32_t D, uint32_t shift, uint64_t maxkey, bool* found)
+{
+    *found = false;
+    if (D == 0 || h > maxkey) return D;
+    const uint64_t b = h >> shift;
+    uint32_t lo = b ? ix.cum[b - 1] : 0u, hi = ix.cum[b];
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (ix.dk[mid] < h) lo = mid + 1; else hi = mid;
+    }
+    *found = lo < D && ix.dk[lo] == h;
+    return lo;
+}
+
+// Every query element: its code into the packed query tiles; flags |= 1 for a row that is not strictly ascending or holds
+// the reserved value; *total += postings a marking pass would walk for it (references sharing its hash).
+__global__ void __launch_bounds__(256) dist_qcode_kernel(fpm_panel pn, uint32_t max_size, uint64_t rows, RefIndex ix, const uint32_t* __restrict__ run_start,
+                                                         uint32_t* __restrict__ packed, uint32_t* flags, unsigned long long* total)
+{
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long c = 0;
-    if (i < m && keys[i] != ~0ULL && dst[i] >= pr) c = run_ref_start[rank[i] + 1] - run_ref_start[rank[i]];
+    if (idx < pn.n * max_size) {
+        const uint64_t sk = idx / max_size, row = idx % max_size;
+        if (row < pn.sizes[sk]) {
+            const uint64_t v = pn.hashes[sk * pn.stride + row];
+            bool bad = v == ~0ULL;
+            if (row > 0 && pn.hashes[sk * pn.stride + row - 1] >= v) bad = true;
+            if (bad) atomicOr(flags, 1u);
+            const uint32_t D = ix.scal[0], shift = ix.scal[2];
+            const uint64_t maxkey = ((uint64_t)ix.scal[4] << 32) | ix.scal[3];
+            bool found;
+            const uint32_t lb = ref_lower_bound(ix, v, D, shift, maxkey, &found);
+            packed[((sk >> 4) * rows + row) * 16 + (sk & 15)] = 2u * lb + (found ? 1u : 0u);
+            if (found) c = run_start[lb + 1] - run_start[lb];
+        }
+    }
     for (int o = 16; o; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
     // one atomic per CTA: a million same-address atomics (one per warp) cost 0.6 ms
     __shared__ unsigned long long s_part[8];
@@ -112,10 +156,11 @@ __global__ void __launch_bounds__(256) dist_post_count_kernel(const uint64_t* __
 
 // Saturation.  Relatives repeat each other's postings: a query from a family of 1000 mutually related genomes walks
 // ~600 posting lists of ~600 references each to set the same 1000 bits.  The walk may stop as soon as every reference
-// the query can possibly reach is marked, and that set is known cheaply: sketches (references and queries as nodes of one
-// graph) that hold a common hash are connected, so all references of all the query's posting lists lie in the query's
-// CONNECTED COMPONENT.  A lock-free union-find over neighbours in the sorted hash array gives the components and their
-// reference counts in one pass over the array; the marking pass stops a query once it has set that many bits.  Exact
+// the query can possibly reach is marked, and that set is known cheaply: references that hold a common hash are connected,
+// so all references of one posting list lie in one CONNECTED COMPONENT of the "shares a hash" graph over the references,
+// and everything a query can reach lies in the components its posting lists start in.  A lock-free union-find over
+// neighbours in the sorted reference array gives the components and their sizes in one pass; a query's marking pass first
+// adds up the sizes of the (usually one or two) components it touches and stops once it has set that many bits.  Exact
 // (a stopped walk could not have set another bit); a query in a huge sparse component simply never stops early.
 // Parents only ever decrease (a root is hooked under a smaller node, halving moves to a grandparent), so ANY value a
 // parent entry held at some time is an ancestor-or-self: finds may read through L1 (FRESH = false; millions of threads
@@ -138,22 +183,8 @@ __global__ void __launch_bounds__(256) dist_uf_init_kernel(uint32_t* __restrict_
     if (i < n) { parent[i] = i; ref_count[i] = 0; }
 }
 
-// node of a tile-layout destination: references 0..n_r-1, queries n_r..n_r+n_q-1
-__device__ __forceinline__ uint32_t uf_node(uint32_t d, uint32_t pr, uint32_t rows_r, uint32_t rows_q, uint32_t n_r)
+__device__ __forceinline__ void uf_union(uint32_t* __restrict__ parent, uint32_t a, uint32_t b)
 {
-    if (d < pr) return ((d >> 4) / rows_r) * 16 + (d & 15);
-    d -= pr;
-    return n_r + ((d >> 4) / rows_q) * 16 + (d & 15);
-}
-
-__global__ void __launch_bounds__(256) dist_uf_union_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ dst, uint64_t m, uint32_t pr,
-                                                            uint32_t rows_r, uint32_t rows_q, uint32_t n_r, uint32_t* __restrict__ parent)
-{
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x + 1;
-    if (i >= m) return;
-    const uint64_t k = keys[i];
-    if (k == ~0ULL || keys[i - 1] != k) return;
-    uint32_t a = uf_node(dst[i], pr, rows_r, rows_q, n_r), b = uf_node(dst[i - 1], pr, rows_r, rows_q, n_r);
     a = uf_find<false>(parent, a);
     b = uf_find<false>(parent, b);
     for (;;) {                                                             // hook the larger root under the smaller node
@@ -165,11 +196,21 @@ __global__ void __launch_bounds__(256) dist_uf_union_kernel(const uint64_t* __re
     }
 }
 
-// parent[x] = root for every query node; ref_count[root] = references in the component.  The find here must not
-// compress paths: this kernel publishes roots into the array other threads are still walking, and a path-halving
-// store of a (non-root) grandparent landing after the final "parent[x] = root" would leave the query pointing at a
-// node whose ref_count is 0 -- its marking pass would then stop before walking a single posting.  With a read-only
-// walk every value ever stored from here on is a root, and a walker that meets one early simply arrives sooner.
+// nodes: references 0..n_r-1, queries n_r..n_r+n_q-1.  References holding the same hash are neighbours in the sorted array.
+__global__ void __launch_bounds__(256) dist_uf_union_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ post, uint64_t m, uint32_t* __restrict__ parent)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x + 1;
+    if (i >= m) return;
+    const uint64_t k = keys[i];
+    if (k == ~0ULL || keys[i - 1] != k) return;
+    uf_union(parent, post[i], post[i - 1]);
+}
+
+// parent[x] = root for every reference; ref_count[root] = references in the component.  The find here must not compress
+// paths: this kernel publishes roots into the array other threads are still walking, and a path-halving store of a
+// (non-root) grandparent landing after the final "parent[x] = root" would leave a node pointing at a non-root whose
+// ref_count is 0.  With a read-only walk every value ever stored from here on is a root, and a walker that meets one
+// early simply arrives sooner.
 __device__ __forceinline__ uint32_t uf_root_readonly(const uint32_t* parent, uint32_t x)
 {
     for (;;) {
@@ -179,36 +220,74 @@ __device__ __forceinline__ uint32_t uf_root_readonly(const uint32_t* parent, uin
     }
 }
 
-__global__ void __launch_bounds__(256) dist_uf_flatten_kernel(uint32_t* __restrict__ parent, uint32_t* __restrict__ ref_count, uint32_t n_r, uint32_t n)
+__global__ void __launch_bounds__(256) dist_uf_flatten_kernel(uint32_t* __restrict__ parent, uint32_t* __restrict__ ref_count, uint32_t n_r)
 {
     const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= n) return;
+    if (x >= n_r) return;
     const uint32_t r = uf_root_readonly(parent, x);
-    if (x < n_r) atomicAdd(&ref_count[r], 1u);
-    if (x >= n_r) parent[x] = r;            // only the queries' entries are read afterwards
+    atomicAdd(&ref_count[r], 1u);
+    parent[x] = r;
 }
 
 // one CTA per query sketch: bit r of its row = reference r shares a hash with it.  (Also tried: one identity for equal posting
 // lists, each distinct list walked once per query -- lists of independently mutated relatives are all different; and testing
 // the bit with a plain load before the atomic -- 0.7 ms slower.)
+constexpr int MARK_ROOTS = 32;       // components a query may touch before the early stop is given up for it
 __global__ void __launch_bounds__(256) dist_mark_kernel(const uint32_t* __restrict__ p32q, uint64_t rows_q, const uint32_t* __restrict__ sizes_q,
                                                         const uint32_t* __restrict__ run_ref_start, const uint32_t* __restrict__ post, uint32_t words,
                                                         const uint32_t* __restrict__ parent, const uint32_t* __restrict__ ref_count, uint32_t n_r,
                                                         uint32_t* __restrict__ marks)
 {
     extern __shared__ uint32_t s_bits[];
-    __shared__ uint32_t s_count;
+    __shared__ uint32_t s_count, s_nroots, s_roots[MARK_ROOTS], s_target;
     const uint32_t q = blockIdx.x;
     for (uint32_t w = threadIdx.x; w < words; w += blockDim.x) s_bits[w] = 0;
-    if (threadIdx.x == 0) s_count = 0;
+    if (threadIdx.x == 0) { s_count = 0; s_nroots = 0; s_target = 0xffffffffu; }
     __syncthreads();
     const uint32_t n = sizes_q[q];
-    const uint32_t target = parent ? ref_count[parent[n_r + q]] : 0xffffffffu;   // references this query can reach at all
     const uint32_t* col = p32q + ((uint64_t)(q >> 4) * rows_q) * 16 + (q & 15);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (parent) {
+        // references this query can reach at all: the sizes of the components its posting lists start in.  A component listed
+        // twice (two warps racing) only makes the bound larger, which keeps it a bound.
+        for (uint32_t e0 = 0; e0 < n; e0 += blockDim.x) {                   // (uniform trip count: the warp votes below)
+            const uint32_t e = e0 + threadIdx.x;
+            uint32_t root = 0xffffffffu;
+            if (e < n) {
+                const uint32_t code = col[(uint64_t)e * 16];
+                if (code & 1u) root = parent[post[run_ref_start[code >> 1]]];
+            }
+            // one lane per distinct component of the warp looks it up in the list and appends it if it is new
+            const uint32_t peers = __match_any_sync(0xffffffffu, root);
+            if (root != 0xffffffffu && __ffs(peers) - 1 == lane) {
+                bool seen = false;
+                const uint32_t have = min(*reinterpret_cast<volatile uint32_t*>(&s_nroots), (uint32_t)MARK_ROOTS);
+                for (uint32_t i = 0; i < have; i++) seen |= reinterpret_cast<volatile uint32_t*>(s_roots)[i] == root;
+                if (!seen) {
+                    const uint32_t slot = atomicAdd(&s_nroots, 1u);
+                    if (slot < MARK_ROOTS) s_roots[slot] = root;
+                }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && s_nroots <= MARK_ROOTS) {
+            // (duplicates from races are dropped here: the list is tiny)
+            uint32_t t = 0;
+            for (uint32_t i = 0; i < s_nroots; i++) {
+                bool dup = false;
+                for (uint32_t j = 0; j < i; j++) dup |= s_roots[j] == s_roots[i];
+                if (!dup) t += ref_count[s_roots[i]];
+            }
+            s_target = t;
+        }
+        __syncthreads();
+    }
+    const uint32_t target = s_target;
     for (uint32_t e = wid; e < n; e += nw) {                              // a warp per element, lanes over its postings
         if (*reinterpret_cast<volatile uint32_t*>(&s_count) >= target) break;
-        const uint32_t r = col[(uint64_t)e * 16];
+        const uint32_t code = col[(uint64_t)e * 16];
+        if (!(code & 1u)) continue;                                       // even code: no reference holds this hash
+        const uint32_t r = code >> 1;
         const uint32_t lo = run_ref_start[r], hi = run_ref_start[r + 1];
         uint32_t fresh = 0;
         for (uint32_t j0 = lo; j0 < hi; j0 += 32) {
@@ -435,100 +514,131 @@ int dist_rank_panels(fpm_ctx* ctx, const fpm_panel* d_ref, const fpm_panel* d_qr
     *mode = DIST_RANK_TOO_BIG;
     const uint64_t nr16 = (d_ref->n + 15) / 16, nq16 = (d_qry->n + 15) / 16;
     const uint64_t pr = nr16 * 16 * rows_r, pq = nq16 * 16 * rows_q;      // packed elements
-    const uint64_t mr = d_ref->n * (uint64_t)max_size_ref, mq = d_qry->n * (uint64_t)max_size_qry, m = mr + mq;
-    if (pr + pq >= 0xffffffffull || m >= 0x7fffffffull) return FPM_OK;    // ranks / indices would not fit: 64-bit path
+    const uint64_t mr = d_ref->n * (uint64_t)max_size_ref, mq = d_qry->n * (uint64_t)max_size_qry, m = mr;
+    if (pr >= 0xffffffffull || pq >= 0xffffffffull || mr >= 0x7fffffffull) { ctx->rix.valid = false; return FPM_OK; }   // codes / indices would not fit: 64-bit path
     int rc;
-    if ((rc = ctx->d_p32.ensure((pr + pq) * 4))) return rc;
     if ((rc = ctx->d_misc.ensure(64))) return rc;
-    uint32_t* packed = ctx->d_p32.as<uint32_t>();
-    *packed_ref = packed;
-    *packed_qry = packed + pr;
-    FPM_CUDA(cudaMemsetAsync(packed, 0xff, (pr + pq) * 4, st));
     FPM_CUDA(cudaMemsetAsync(ctx->d_misc.p, 0, 64, st));
-    if (m == 0) { *mode = DIST_RANK_OK; return FPM_OK; }
-
-    size_t sort_tmp = 0, scan_tmp = 0;
-    cub::DoubleBuffer<uint64_t> kb(nullptr, nullptr);
-    cub::DoubleBuffer<uint32_t> vb(nullptr, nullptr);
-    FPM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, kb, vb, (int64_t)m, 0, 64, st));
-    HeadFlag hf{nullptr};
-    cub::CountingInputIterator<uint64_t> cnt(0);
-    cub::TransformInputIterator<uint32_t, HeadFlag, cub::CountingInputIterator<uint64_t>> it0(cnt, hf);
-    FPM_CUDA(cub::DeviceScan::InclusiveSum(nullptr, scan_tmp, it0, (uint32_t*)nullptr, (int64_t)m, st));
-    const size_t tmp = std::max(sort_tmp, scan_tmp);
-    // one scratch block: keys x2 | dst x2 | cub temp (the rank array reuses the spare key buffer)
-    const size_t ka = (m * 8 + 255) & ~(size_t)255, va = (m * 4 + 255) & ~(size_t)255;
-    if ((rc = ctx->d_rank.ensure(2 * ka + 2 * va + tmp + 256))) return rc;
-    unsigned char* base = ctx->d_rank.as<unsigned char>();
-    uint64_t* k0 = (uint64_t*)base; uint64_t* k1 = (uint64_t*)(base + ka);
-    uint32_t* v0 = (uint32_t*)(base + 2 * ka); uint32_t* v1 = (uint32_t*)(base + 2 * ka + va);
-    void* d_tmp = base + 2 * ka + 2 * va;
-
-    ctx->time_begin(FPM_KERNEL_DIST_PACK);
-    if (mr) dist_keys_kernel<<<(uint32_t)((mr + 255) / 256), 256, 0, st>>>(*d_ref, max_size_ref, rows_r, 0u, 0, k0, v0, ctx->d_misc.as<uint32_t>());
-    if (mq) dist_keys_kernel<<<(uint32_t)((mq + 255) / 256), 256, 0, st>>>(*d_qry, max_size_qry, rows_q, (uint32_t)pr, mr, k0, v0, ctx->d_misc.as<uint32_t>());
-    FPM_CUDA(cudaGetLastError());
-    kb = cub::DoubleBuffer<uint64_t>(k0, k1);
-    vb = cub::DoubleBuffer<uint32_t>(v0, v1);
-    FPM_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, sort_tmp, kb, vb, (int64_t)m, 0, 64, st));
-    const uint64_t* ks = kb.Current();
-    uint32_t* rank = (uint32_t*)kb.Alternate();
-    hf.keys = ks;
-    cub::TransformInputIterator<uint32_t, HeadFlag, cub::CountingInputIterator<uint64_t>> it(cnt, hf);
-    FPM_CUDA(cub::DeviceScan::InclusiveSum(d_tmp, scan_tmp, it, rank, (int64_t)m, st));
-    dist_scatter_kernel<<<(uint32_t)((m + 255) / 256), 256, 0, st>>>(ks, vb.Current(), rank, m, packed);
-    ctx->launches += 3 + (mr ? 1 : 0) + (mq ? 1 : 0);
-    FPM_CUDA(cudaGetLastError());
-
-    // ---- inverted index for pruning (optional: skipped for huge reference panels or when switched off) ----------
-    const uint32_t words = (uint32_t)((d_ref->n + 31) / 32);
-    const bool want_prune = !ctx->no_dist_prune && d_ref->n <= 1000000 && mr > 0 && mq > 0;
-    uint32_t *ref_pos = nullptr, *post = nullptr, *run_ref_start = nullptr;
+    uint32_t* d_flag_r = ctx->d_misc.as<uint32_t>();
+    uint32_t* d_flag_q = d_flag_r + 1;
     unsigned long long* d_total = (unsigned long long*)(ctx->d_misc.as<uint64_t>() + 1);
-    if (want_prune) {
-        size_t scan2_tmp = 0;
-        RefFlag rf{ks, vb.Current(), (uint32_t)pr};
-        cub::TransformInputIterator<uint32_t, RefFlag, cub::CountingInputIterator<uint64_t>> rit(cnt, rf);
-        FPM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan2_tmp, rit, (uint32_t*)nullptr, (int64_t)m, st));
-        const size_t a4 = (m * 4 + 4 + 255) & ~(size_t)255;
-        if ((rc = ctx->d_post.ensure(3 * a4 + scan2_tmp + 256))) return rc;
+
+    // bucket table over the distinct reference hashes: about four elements per bucket
+    uint32_t log2b = 10;
+    while ((1ull << log2b) < mr / 4 && log2b < 27) log2b++;
+    const uint32_t n_buckets = 1u << log2b;
+    // the index: post [m] | run_start [m + 1] | dk [m] | cum [n_buckets] | scalars
+    const size_t a4 = (m * 4 + 4 + 255) & ~(size_t)255, a8 = (m * 8 + 255) & ~(size_t)255, ab = (((size_t)n_buckets + 1) * 4 + 255) & ~(size_t)255;
+
+    // A resident reference panel (fpm_dist_set_reference) keeps its packed tiles and its index from one query chunk to the next
+    fpm_ctx::RefIndexState& rix = ctx->rix;
+    const bool reuse = ctx->ref_set && rix.valid && rix.hashes == (const void*)d_ref->hashes && rix.n_r == d_ref->n && rix.rows_r == rows_r && rix.m == m;
+    ctx->time_begin(FPM_KERNEL_DIST_PACK);
+    if (!reuse) {
+        rix = fpm_ctx::RefIndexState();
+        if ((rc = ctx->d_p32.ensure(pr * 4 + 64))) return rc;
+        FPM_CUDA(cudaMemsetAsync(ctx->d_p32.p, 0xff, pr * 4, st));
+        size_t sort_tmp = 0, scan_tmp = 0, scan2_tmp = 0;
+        cub::DoubleBuffer<uint64_t> kb(nullptr, nullptr);
+        cub::DoubleBuffer<uint32_t> vb(nullptr, nullptr);
+        HeadFlag hf{nullptr};
+        cub::CountingInputIterator<uint64_t> cnt(0);
+        cub::TransformInputIterator<uint32_t, HeadFlag, cub::CountingInputIterator<uint64_t>> it0(cnt, hf);
+        if (m) {
+            FPM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, kb, vb, (int64_t)m, 0, 64, st));
+            FPM_CUDA(cub::DeviceScan::InclusiveSum(nullptr, scan_tmp, it0, (uint32_t*)nullptr, (int64_t)m, st));
+        }
+        FPM_CUDA(cub::DeviceScan::InclusiveScan(nullptr, scan2_tmp, (uint32_t*)nullptr, (uint32_t*)nullptr, MaxOp(), (int64_t)n_buckets, st));
+        const size_t tmp = std::max(std::max(sort_tmp, scan_tmp), scan2_tmp);
+        // one scratch block: keys x2 | dst x2 | cub temp (the rank array reuses the spare key buffer)
+        const size_t ka = (m * 8 + 255) & ~(size_t)255, va = (m * 4 + 255) & ~(size_t)255;
+        if ((rc = ctx->d_rank.ensure(2 * ka + 2 * va + tmp + 256))) return rc;
+        unsigned char* base = ctx->d_rank.as<unsigned char>();
+        uint64_t* k0 = (uint64_t*)base; uint64_t* k1 = (uint64_t*)(base + ka);
+        uint32_t* v0 = (uint32_t*)(base + 2 * ka); uint32_t* v1 = (uint32_t*)(base + 2 * ka + va);
+        void* d_tmp = base + 2 * ka + 2 * va;
+        if ((rc = ctx->d_post.ensure(2 * a4 + a8 + ab + 256))) return rc;
         unsigned char* pb = ctx->d_post.as<unsigned char>();
-        ref_pos = (uint32_t*)pb; post = (uint32_t*)(pb + a4); run_ref_start = (uint32_t*)(pb + 2 * a4);
-        void* d_tmp2 = pb + 3 * a4;
-        FPM_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp2, scan2_tmp, rit, ref_pos, (int64_t)m, st));
-        // every rank up to the last one gets its start; the slot after the last run = number of reference postings
-        FPM_CUDA(cudaMemsetAsync(run_ref_start, 0xff, (m + 1) * 4, st));
-        dist_post_kernel<<<(uint32_t)((m + 255) / 256), 256, 0, st>>>(ks, vb.Current(), rank, ref_pos, m, (uint32_t)pr, (uint32_t)rows_r, post, run_ref_start);
-        dist_post_tail_kernel<<<1, 1, 0, st>>>(ks, vb.Current(), rank, ref_pos, m, (uint32_t)pr, run_ref_start);
-        dist_post_count_kernel<<<(uint32_t)((m + 255) / 256), 256, 0, st>>>(ks, vb.Current(), rank, run_ref_start, m, (uint32_t)pr, d_total);
-        ctx->launches += 4;
+        uint32_t* post = (uint32_t*)pb; uint32_t* run_start = (uint32_t*)(pb + a4); uint64_t* dk = (uint64_t*)(pb + 2 * a4);
+        uint32_t* cum = (uint32_t*)(pb + 2 * a4 + a8); uint32_t* scal = (uint32_t*)(pb + 2 * a4 + a8 + ab);
+        FPM_CUDA(cudaMemsetAsync(scal, 0, 64, st));
+        FPM_CUDA(cudaMemsetAsync(cum, 0, ((size_t)n_buckets + 1) * 4, st));
+        FPM_CUDA(cudaMemsetAsync(run_start, 0, 4, st));
+        const uint64_t* ks = k0;
+        if (m) {
+            dist_keys_kernel<<<(uint32_t)((mr + 255) / 256), 256, 0, st>>>(*d_ref, max_size_ref, rows_r, 0u, 0, k0, v0, d_flag_r);
+            FPM_CUDA(cudaGetLastError());
+            kb = cub::DoubleBuffer<uint64_t>(k0, k1);
+            vb = cub::DoubleBuffer<uint32_t>(v0, v1);
+            FPM_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, sort_tmp, kb, vb, (int64_t)m, 0, 64, st));
+            ks = kb.Current();
+            uint32_t* rank = (uint32_t*)kb.Alternate();
+            hf.keys = ks;
+            cub::TransformInputIterator<uint32_t, HeadFlag, cub::CountingInputIterator<uint64_t>> it(cnt, hf);
+            FPM_CUDA(cub::DeviceScan::InclusiveSum(d_tmp, scan_tmp, it, rank, (int64_t)m, st));
+            dist_index_kernel<<<(uint32_t)((m + 255) / 256), 256, 0, st>>>(ks, vb.Current(), rank, m, (uint32_t)rows_r, ctx->d_p32.as<uint32_t>(), dk, post, run_start, scal);
+            ctx->launches += 2;
+        }
+        dist_bucket_setup_kernel<<<1, 1, 0, st>>>(scal, log2b);
+        if (m) dist_bucket_tails_kernel<<<(uint32_t)((m + 255) / 256), 256, 0, st>>>(dk, scal, cum);
+        FPM_CUDA(cub::DeviceScan::InclusiveScan(d_tmp, scan2_tmp, cum, cum, MaxOp(), (int64_t)n_buckets, st));
+        ctx->launches += 1 + (m ? 1 : 0);
+        FPM_CUDA(cudaGetLastError());
+        rix.valid = true; rix.hashes = d_ref->hashes; rix.n_r = d_ref->n; rix.rows_r = rows_r; rix.m = m; rix.pr = pr; rix.ks = ks; rix.n_buckets = n_buckets;
+    }
+    unsigned char* pb = ctx->d_post.as<unsigned char>();
+    uint32_t* post = (uint32_t*)pb; uint32_t* run_start = (uint32_t*)(pb + a4); uint64_t* dk = (uint64_t*)(pb + 2 * a4);
+    uint32_t* cum = (uint32_t*)(pb + 2 * a4 + a8); uint32_t* scal = (uint32_t*)(pb + 2 * a4 + a8 + ab);
+    const uint64_t* ks = rix.ks;
+    *packed_ref = ctx->d_p32.as<uint32_t>();
+
+    // ---- the query panel: codes by lookup ------------------------------------------------------------------------
+    if ((rc = ctx->d_p32q.ensure(pq * 4 + 64))) return rc;
+    *packed_qry = ctx->d_p32q.as<uint32_t>();
+    FPM_CUDA(cudaMemsetAsync(*packed_qry, 0xff, pq * 4, st));
+    RefIndex ix{dk, cum, scal};
+    if (mq) {
+        dist_qcode_kernel<<<(uint32_t)((mq + 255) / 256), 256, 0, st>>>(*d_qry, max_size_qry, rows_q, ix, run_start, *packed_qry, d_flag_q, d_total);
+        ctx->launches++;
         FPM_CUDA(cudaGetLastError());
     }
+
+    // ---- pruning (optional: skipped for huge reference panels or when switched off) ------------------------------
+    const uint32_t words = (uint32_t)((d_ref->n + 31) / 32);
+    const bool want_prune = !ctx->no_dist_prune && d_ref->n <= 1000000 && mr > 0 && mq > 0;
     uint64_t h2[2] = {0, 0};
     FPM_CUDA(cudaMemcpyAsync(h2, ctx->d_misc.p, 16, cudaMemcpyDeviceToHost, st));
     FPM_CUDA(cudaStreamSynchronize(st));
-    const uint32_t flag = (uint32_t)h2[0];
-    *mode = flag == 0 ? DIST_RANK_OK : DIST_RANK_UNSORTED;     // unsorted input or a hash equal to 2^64-1: the literal kernel defines the result
+    if (!reuse) rix.unsorted = (uint32_t)h2[0] != 0;
+    const bool bad = rix.unsorted || (uint32_t)(h2[0] >> 32) != 0;
+    *mode = bad ? DIST_RANK_UNSORTED : DIST_RANK_OK;           // unsorted input or a hash equal to 2^64-1: the literal kernel defines the result
     if (*mode == DIST_RANK_OK && want_prune) {
         // walk the postings only if that costs well below the merges it can save: a posting is ~4 bytes of L2 traffic and
         // one shared-memory atomic, a pair's merge up to sketch_size steps
         const double postings = (double)h2[1], full = (double)d_ref->n * (double)d_qry->n * (double)std::max<uint32_t>(sketch_size, 1);
         // (and only while the bitmaps stay small next to the panels: n_q x n_r bits, twice when grouped)
         if (postings <= 0.05 * full && (size_t)words * 4 <= 200 * 1024 && (double)d_qry->n * words * 4 <= 8e9) {
-            // marks [n_q][words] | union-find parents [n_r + n_q] | references per component [n_r + n_q]
-            const size_t a_marks = ((size_t)d_qry->n * words * 4 + 255) & ~(size_t)255;
-            const uint32_t nodes = (uint32_t)(d_ref->n + d_qry->n);
+            if ((rc = ctx->d_marks.ensure((size_t)d_qry->n * words * 4 + 64))) return rc;
+            const uint32_t nodes = (uint32_t)d_ref->n;
             const size_t a_nodes = ((size_t)nodes * 4 + 255) & ~(size_t)255;
-            if ((rc = ctx->d_marks.ensure(a_marks + 2 * a_nodes + 64))) return rc;
-            uint32_t* parent = (uint32_t*)(ctx->d_marks.as<unsigned char>() + a_marks);
-            uint32_t* ref_count = (uint32_t*)(ctx->d_marks.as<unsigned char>() + a_marks + a_nodes);
-            dist_uf_init_kernel<<<(nodes + 255) / 256, 256, 0, st>>>(parent, ref_count, nodes);
-            dist_uf_union_kernel<<<(uint32_t)((m + 255) / 256), 256, 0, st>>>(ks, vb.Current(), m, (uint32_t)pr, (uint32_t)rows_r, (uint32_t)rows_q, (uint32_t)d_ref->n, parent);
-            dist_uf_flatten_kernel<<<(nodes + 255) / 256, 256, 0, st>>>(parent, ref_count, (uint32_t)d_ref->n, nodes);
+            if ((rc = ctx->d_uf.ensure(2 * a_nodes + 64))) return rc;
+            uint32_t* parent = ctx->d_uf.as<uint32_t>();
+            uint32_t* ref_count = (uint32_t*)(ctx->d_uf.as<unsigned char>() + a_nodes);
+            // The components cost a fixed ~0.5 ms (a few long chains of dependent L2 round trips while the trees form, whatever
+            // the panel size), a posting costs ~1 ps of marking (measured: 9e8 postings of a 10000 x 5000 block, 1.0 ms without
+            // the early stop against 0.11 ms + 0.54 ms with it): the early stop pays from about 5e8 postings on.
+            const bool saturate = postings > 4e8 || ctx->force_dist_saturate;
+            if (saturate && !rix.uf_valid) {
+                dist_uf_init_kernel<<<(nodes + 255) / 256, 256, 0, st>>>(parent, ref_count, nodes);
+                dist_uf_union_kernel<<<(uint32_t)((m + 255) / 256), 256, 0, st>>>(ks, post, m, parent);
+                dist_uf_flatten_kernel<<<(nodes + 255) / 256, 256, 0, st>>>(parent, ref_count, nodes);
+                ctx->launches += 3;
+                rix.uf_valid = true;
+            }
             FPM_CUDA(cudaFuncSetAttribute(dist_mark_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(words * 4)));
-            dist_mark_kernel<<<(uint32_t)d_qry->n, 256, words * 4, st>>>(*packed_qry, rows_q, d_qry->sizes, run_ref_start, post, words, parent, ref_count,
-                                                                         (uint32_t)d_ref->n, ctx->d_marks.as<uint32_t>());
-            ctx->launches += 4;
+            dist_mark_kernel<<<(uint32_t)d_qry->n, 256, words * 4, st>>>(*packed_qry, rows_q, d_qry->sizes, run_start, post, words, saturate ? parent : nullptr,
+                                                                         ref_count, (uint32_t)d_ref->n, ctx->d_marks.as<uint32_t>());
+            ctx->launches += 1;
             FPM_CUDA(cudaGetLastError());
             *marks = ctx->d_marks.as<uint32_t>();
         }

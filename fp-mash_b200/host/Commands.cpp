@@ -473,11 +473,21 @@ int CommandDistance::run() const
     fpm_multi* multiTile = (filtered || fingerprint) ? nullptr : gpuMulti(nRef * nQry, kMultiGpuPairs);
     uint64_t rowsPerCall = nRef ? max<uint64_t>(1, ((32ull << 20) * (multiTile ? fpm_multi_size(multiTile) : 1)) / nRef) : 1;
     vector<fpm_pair> out;
+    // one GPU, several query chunks: the reference panel is uploaded and indexed once and stays resident (the reference keeps
+    // its whole sketch file loaded while the queries stream past, CommandDistance.cpp:163-266)
+    const bool residentRef = !multiTile && !filtered && nRef && nQry > rowsPerCall;
+    if (residentRef) {
+        fpm_panel vr = pr.view(0, nRef);
+        if (fpm_dist_set_reference(gpuContext(), &vr) != FPM_OK) {
+            cerr << "ERROR: " << fpm_last_error() << endl;
+            return 1;
+        }
+    }
     for (uint64_t q0 = 0; q0 < nQry && nRef && !filtered; q0 += rowsPerCall) {
         uint64_t nq = min(rowsPerCall, nQry - q0);
         out.resize(nq * nRef);
         fpm_panel vr = pr.view(0, nRef), vq = pq.view(q0, nq);
-        if ((multiTile ? fpm_dist_tile_multi(multiTile, &dp, &vr, &vq, out.data()) : fpm_dist_tile(gpuContext(), &dp, &vr, &vq, out.data())) != FPM_OK) {
+        if ((multiTile ? fpm_dist_tile_multi(multiTile, &dp, &vr, &vq, out.data()) : fpm_dist_tile(gpuContext(), &dp, residentRef ? nullptr : &vr, &vq, out.data())) != FPM_OK) {
             cerr << "ERROR: " << fpm_last_error() << endl;
             return 1;
         }

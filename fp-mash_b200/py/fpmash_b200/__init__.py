@@ -140,6 +140,7 @@ lib.fpm_dist_sharded_dev.argtypes = [_VP, C.POINTER(DistParams), C.POINTER(Panel
 lib.fpm_dist_hits_sharded_dev.argtypes = [_VP, C.POINTER(DistParams), C.POINTER(Panel), C.c_uint64, C.POINTER(Panel), C.c_uint64, _VP, C.c_uint64,
                                           u64p, C.POINTER(Block), _VP]
 lib.fpm_sketch_reads_sharded_dev.argtypes = [_VP, C.POINTER(SketchParams), _VP, C.c_uint64, _VP, _VP, _VP, _VP]
+lib.fpm_dist_set_reference.argtypes = [_VP, C.POINTER(Panel)]
 lib.fpm_multi_create.argtypes = [_VP, C.c_int, C.POINTER(_VP)]
 lib.fpm_multi_destroy.argtypes = [_VP]
 lib.fpm_multi_destroy.restype = None
@@ -187,7 +188,7 @@ EXPORTED = ["fpm_abi_version", "fpm_device_count", "fpm_ctx_create", "fpm_ctx_de
             "fpm_shard_range", "fpm_dist_grid_shape", "fpm_dist_block", "fpm_comm_get_unique_id", "fpm_comm_init_rank", "fpm_comm_adopt",
             "fpm_comm_destroy", "fpm_comm_rank", "fpm_comm_size", "fpm_dist_sharded_dev", "fpm_dist_hits_sharded_dev",
             "fpm_multi_create", "fpm_multi_destroy", "fpm_multi_size", "fpm_multi_ctx", "fpm_dist_tile_multi", "fpm_dist_hits_multi",
-            "fpm_sketch_batch_multi", "fpm_sketch_reads_sharded_dev"]
+            "fpm_sketch_batch_multi", "fpm_sketch_reads_sharded_dev", "fpm_dist_set_reference"]
 
 
 def _check(rc):
@@ -297,10 +298,11 @@ class Context:
     def launch_count(self):
         return int(lib.fpm_ctx_launch_count(self._h))
 
-    def set_dist_mode(self, force64=False, no_prune=False, no_group=False):
+    def set_dist_mode(self, force64=False, no_prune=False, no_group=False, saturate=False):
         """force64=True: run the 64-bit tile kernel even where the 32-bit rank kernel applies; no_prune=True: the rank
-        kernel merges every pair (no skipping of pairs that share no hash)."""
-        _check(lib.fpm_ctx_set_dist_mode(self._h, 1 if force64 else (2 if no_prune else (3 if no_group else 0))))
+        kernel merges every pair (no skipping of pairs that share no hash); saturate=True: always bound the marking walks
+        by the sizes of the reference components (by default only when the panels are large enough for that to pay)."""
+        _check(lib.fpm_ctx_set_dist_mode(self._h, 1 if force64 else (2 if no_prune else (3 if no_group else (4 if saturate else 0)))))
 
     def set_timing(self, enable=True):
         _check(lib.fpm_ctx_set_timing(self._h, int(enable)))
@@ -513,11 +515,33 @@ class Context:
         p = Panel(h.ctypes.data, sz.ctypes.data, ln.ctypes.data, h.shape[0], h.shape[1])
         return p, (h, sz, ln)
 
+    def dist_set_reference(self, ref):
+        """Upload and keep a reference panel (hashes, sizes, lengths), or drop it with None; afterwards pass ref=None to
+        dist_tile / dist_hits."""
+        if ref is None:
+            _check(lib.fpm_dist_set_reference(self._h, None))
+            self._ref_n = None
+            return
+        pr, keep = self._panel(*ref)
+        _check(lib.fpm_dist_set_reference(self._h, C.byref(pr)))
+        self._ref_n = int(pr.n)
+
     def dist_tile(self, ref, qry, sketch_size, kmer_size, kmer_space, max_distance=1.0, max_pvalue=1.0,
                   sorted_unique=True, out=None, raw=False):
         """ref / qry: (hashes [n][stride], sizes [n], lengths [n]).  Returns a structured array
         [n_qry][n_ref] of (numer, denom, distance, pvalue) plus a bool `pass` matrix.  `out` may be a
-        caller-owned (e.g. pinned) PAIR_DTYPE array of that shape."""
+        caller-owned (e.g. pinned) PAIR_DTYPE array of that shape.  ref=None: the resident reference panel."""
+        if ref is None:
+            pq, keep_q = self._panel(*qry)
+            dp = DistParams(sketch_size, kmer_size, kmer_space, max_distance, max_pvalue, int(sorted_unique))
+            if out is None:
+                out = np.zeros((pq.n, self._ref_n), dtype=PAIR_DTYPE)
+            _check(lib.fpm_dist_tile(self._h, C.byref(dp), None, C.byref(pq), out.ctypes.data))
+            if raw:
+                return out, None
+            passed = (out["denom"] & FPM_PAIR_PASS) != 0
+            out["denom"] &= 0x7fffffff
+            return out, passed
         pr, keep_r = self._panel(*ref)
         pq, keep_q = self._panel(*qry)
         dp = DistParams(sketch_size, kmer_size, kmer_space, max_distance, max_pvalue, int(sorted_unique))

@@ -227,6 +227,14 @@ int fpm_dist_tile(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* ref, 
 int fpm_dist_tile_dev(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* d_ref, const fpm_panel* d_qry,
                       fpm_pair* d_out, uint64_t* d_merge_steps /* nullable: += loop iterations */);
 
+/* A reference panel that stays resident: uploaded, sorted and indexed ONCE, then compared with any number of query panels
+ * (chunks of a query set too large for one call, or the rows of a .msh file as they are read).  The reference keeps its
+ * whole sketch file loaded while queries stream past, CommandDistance.cpp:163-266; here the index (codes, posting lists)
+ * is a property of the reference panel alone, so a query chunk costs only its own lookups.  After this call pass
+ * ref = NULL to fpm_dist_tile / fpm_dist_hits; passing a panel again (or NULL here) drops the resident one.  The host
+ * arrays may be released when the call returns.                                                                      */
+int fpm_dist_set_reference(fpm_ctx* ctx, const fpm_panel* ref /* host; NULL: drop */);
+
 /* The same comparison, but only the pairs that pass the -d / -v filters come back (what `mash dist -d D -v P`
  * prints, CommandDistance.cpp:303-333 skips every other pair): records sorted by (query, ref), i.e. in the
  * reference's output order.  No n x n result matrix exists anywhere: the tile kernel appends passing pairs to
@@ -329,6 +337,7 @@ int fpm_fp_positional_tile(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_pan
 #define FPM_DIST_FORCE64 1
 #define FPM_DIST_NO_PRUNE 2   /* 32-bit rank kernel, but merge every pair (no disjoint-pair pruning)           */
 #define FPM_DIST_NO_GROUP 3   /* prune, but do not reorder the panels so that related sketches share tiles     */
+#define FPM_DIST_SATURATE 4   /* prune, and always bound the marking walks by component sizes (default: only when it pays) */
 int fpm_ctx_set_dist_mode(fpm_ctx* ctx, int mode);
 
 /* Scalar helpers exported for host code and tests (same code the kernels run).             */

@@ -10,11 +10,12 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-12
 
 
-@pytest.fixture(params=["rank32", "rank32_noprune", "u64"])
+@pytest.fixture(params=["rank32", "rank32_saturate", "rank32_noprune", "u64"])
 def dctx(ctx, request):
-    """The context with the tile kernel pinned: 32-bit dense ranks with pruning of pairs that share no hash (default),
-    the same merging every pair, or the 64-bit kernel."""
-    ctx.set_dist_mode(force64=request.param == "u64", no_prune=request.param == "rank32_noprune")
+    """The context with the tile kernel pinned: 32-bit codes with pruning of pairs that share no hash (default), the same with
+    the marking walks bounded by the reference components (what large panels get), the same merging every pair, or the
+    64-bit kernel."""
+    ctx.set_dist_mode(force64=request.param == "u64", no_prune=request.param == "rank32_noprune", saturate=request.param == "rank32_saturate")
     yield ctx
     ctx.set_dist_mode()
 
@@ -382,8 +383,37 @@ def test_dist_pruning_chained_components(ctx, oracle):
     qh[45] = rh[45]
     rs = np.full(n, s, dtype=np.uint32); qs = np.full(n, s, dtype=np.uint32)
     rl = np.full(n, 100_000, dtype=np.uint64); ql = np.full(n, 100_000, dtype=np.uint64)
-    got, passed = ctx.dist_tile((rh, rs, rl), (qh, qs, ql), s, 21, 4.0 ** 21)
-    _compare(got, passed, _oracle_matrix(oracle, (rh, rs, rl), (qh, qs, ql), s, 21, 4.0 ** 21))
-    assert int((got["numer"] > 0).sum()) > 2 * n - 40
-    hits = ctx.dist_hits((rh, rs, rl), (qh, qs, ql), s, 21, 4.0 ** 21, max_distance=0.9)
+    ctx.set_dist_mode(saturate=True)                     # (small panels would otherwise skip the component bound)
+    try:
+        got, passed = ctx.dist_tile((rh, rs, rl), (qh, qs, ql), s, 21, 4.0 ** 21)
+        _compare(got, passed, _oracle_matrix(oracle, (rh, rs, rl), (qh, qs, ql), s, 21, 4.0 ** 21))
+        assert int((got["numer"] > 0).sum()) > 2 * n - 40
+        hits = ctx.dist_hits((rh, rs, rl), (qh, qs, ql), s, 21, 4.0 ** 21, max_distance=0.9)
+    finally:
+        ctx.set_dist_mode()
     assert len(hits) == int((got["distance"] <= 0.9).sum())
+
+
+def test_resident_reference_panel_equals_one_call(dctx, fpm):
+    """fpm_dist_set_reference: the reference panel is uploaded and indexed once; query chunks of any size, in any order, give
+    the rows of the single full call (and an explicit panel afterwards replaces the resident one)."""
+    rng = np.random.default_rng(321)
+    s, n_ref, n_qry = 128, 300, 517
+    rh, rs = sorted_sketch_panel(rng, n_ref, s, n_clusters=5)
+    qh, qs = sorted_sketch_panel(rng, n_qry, s, n_clusters=5)
+    qh[:4] = rh[:4]; qs[:4] = rs[:4]
+    rl = rng.integers(1000, 6_000_000, size=n_ref).astype(np.uint64)
+    ql = rng.integers(1000, 6_000_000, size=n_qry).astype(np.uint64)
+    want, _ = dctx.dist_tile((rh, rs, rl), (qh, qs, ql), s, 21, 4.0 ** 21, raw=True)
+    dctx.dist_set_reference((rh, rs, rl))
+    try:
+        for lo, hi in ((400, 517), (0, 1), (1, 257), (257, 400), (0, 517)):
+            got, _ = dctx.dist_tile(None, (qh[lo:hi], qs[lo:hi], ql[lo:hi]), s, 21, 4.0 ** 21, raw=True)
+            assert got.tobytes() == want[lo:hi].tobytes(), (lo, hi)
+        # another reference panel through the ordinary call, then the resident one is gone
+        other, _ = dctx.dist_tile((qh[:50], qs[:50], ql[:50]), (qh[:20], qs[:20], ql[:20]), s, 21, 4.0 ** 21, raw=True)
+        assert other.shape == (20, 50)
+        with pytest.raises(fpm.FpmError):
+            dctx.dist_tile(None, (qh[:5], qs[:5], ql[:5]), s, 21, 4.0 ** 21)
+    finally:
+        dctx.dist_set_reference(None)
