@@ -12,6 +12,7 @@
 #include <iostream>
 
 #include "Sketch.h"
+#include "msh.h"
 #include "fpmash_b200.h"
 
 using namespace std;
@@ -335,6 +336,117 @@ static void buildPanel(const Sketch& sk, HostPanel& p)
     }
 }
 
+// `mash dist ref.msh query1.msh query2.msh ...` without materialising the queries: chunks of rows from the mapped files ->
+// pinned panel -> fpm_dist_tile / fpm_dist_hits against the resident reference panel -> writeOutput (CommandDistance.cpp:276-333).
+static int streamQueries(const Sketch& sketchRef, const vector<string>& queryFiles, const Sketch::Parameters& parameters, bool table, bool comment,
+                         double distanceMax, double pValueMax)
+{
+    const uint64_t nRef = sketchRef.getReferenceCount();
+    HostPanel pr;
+    buildPanel(sketchRef, pr);
+    fpm_dist_params dp;
+    // compare(): sketchSize = min of the two getMinHashesPerWindow(); the query side's is `parameters` (enforced on its files)
+    dp.sketch_size = (uint32_t)min<uint64_t>(parameters.minHashesPerWindow, sketchRef.getMinHashesPerWindow());
+    dp.kmer_size = sketchRef.getKmerSize();
+    dp.kmer_space = sketchRef.getKmerSpace();
+    dp.max_distance = distanceMax;
+    dp.max_pvalue = pValueMax;
+    dp.sorted_unique = 1;
+    {
+        fpm_panel vr = pr.view(0, nRef);
+        if (fpm_dist_set_reference(gpuContext(), &vr) != FPM_OK) {
+            cerr << "ERROR: " << fpm_last_error() << endl;
+            return 1;
+        }
+    }
+    const bool filtered = !table && ((distanceMax >= 0 && distanceMax < 1.) || (pValueMax >= 0 && pValueMax < 1.));
+    void* pinned = nullptr;
+    size_t pinnedCap = 0;
+    vector<fpm_pair> out;
+    vector<fpm_hit> hits;
+    vector<string> names, comments;
+    for (const string& file : queryFiles) {
+        if (!Sketch::sketchFileCompatible(parameters, file, false)) continue;
+        msh::PanelReader reader;
+        string err;
+        uint64_t stride = 0;
+        if (!reader.open(file, err) || !reader.max_list(parameters.use64, parameters.minHashesPerWindow, stride, err)) {
+            cerr << "ERROR: " << file << " is not a valid sketch file (" << err << ")." << endl;
+            return 1;
+        }
+        stride = max<uint64_t>(stride, 1);
+        const uint64_t nQry = reader.count();
+        // rows per chunk: ~64 MB of hashes in the staging panel, and at most ~32M pairs of results
+        uint64_t rows = max<uint64_t>(1, min<uint64_t>((64ull << 20) / (stride * 8), (32ull << 20) / nRef));
+        const size_t need = rows * (stride * 8 + 12) + 64;
+        if (need > pinnedCap) {
+            if (pinned) fpm_host_free(pinned);
+            if (fpm_host_alloc(need, &pinned) != FPM_OK) { cerr << "ERROR: " << fpm_last_error() << endl; return 1; }
+            pinnedCap = need;
+        }
+        uint64_t* ph = (uint64_t*)pinned;
+        uint64_t* pl = ph + rows * stride;
+        uint32_t* ps = (uint32_t*)(pl + rows);
+        for (uint64_t q0 = 0; q0 < nQry; q0 += rows) {
+            const uint64_t nq = min(rows, nQry - q0);
+            if (!reader.fill(q0, q0 + nq, parameters.use64, parameters.minHashesPerWindow, ph, stride, ps, pl, err)) {
+                cerr << "ERROR: " << file << " is not a valid sketch file (" << err << ")." << endl;
+                return 1;
+            }
+            names.resize(nq); comments.resize(nq);
+            for (uint64_t i = 0; i < nq; i++)
+                if (!reader.meta(q0 + i, names[i], comments[i], err)) { cerr << "ERROR: " << file << " is not a valid sketch file (" << err << ")." << endl; return 1; }
+            fpm_panel vq;
+            vq.hashes = ph; vq.sizes = ps; vq.lengths = pl; vq.n = nq; vq.stride = stride;
+            if (filtered) {
+                if (hits.size() < (1u << 16)) hits.resize(max<uint64_t>(1 << 16, 16 * (nRef + nq)));
+                uint64_t nHits = 0;
+                int rc = fpm_dist_hits(gpuContext(), &dp, nullptr, &vq, hits.data(), hits.size(), &nHits);
+                if (rc == FPM_ERR_CAPACITY) {
+                    hits.resize(nHits);
+                    rc = fpm_dist_hits(gpuContext(), &dp, nullptr, &vq, hits.data(), hits.size(), &nHits);
+                }
+                if (rc != FPM_OK) { cerr << "ERROR: " << fpm_last_error() << endl; return 1; }
+                for (uint64_t h = 0; h < nHits; h++) {
+                    const fpm_hit& hit = hits[h];
+                    const Sketch::Reference& rref = sketchRef.getReference(hit.ref);
+                    cout << rref.name;
+                    if (comment) cout << ':' << rref.comment;
+                    cout << '\t' << names[hit.query];
+                    if (comment) cout << ':' << comments[hit.query];
+                    cout << '\t' << hit.distance << '\t' << hit.pvalue << '\t' << hit.numer << '/' << (hit.denom & 0x7fffffffu) << '\n';
+                }
+                continue;
+            }
+            out.resize(nq * nRef);
+            if (fpm_dist_tile(gpuContext(), &dp, nullptr, &vq, out.data()) != FPM_OK) { cerr << "ERROR: " << fpm_last_error() << endl; return 1; }
+            for (uint64_t i = 0; i < nq; i++) {
+                if (table) cout << names[i];
+                for (uint64_t j = 0; j < nRef; j++) {
+                    const fpm_pair& pair = out[i * nRef + j];
+                    const bool pass = (pair.denom & FPM_PAIR_PASS) != 0;
+                    if (table) {
+                        cout << '\t';
+                        if (pass) cout << pair.distance;
+                    } else if (pass) {
+                        const Sketch::Reference& rref = sketchRef.getReference(j);
+                        cout << rref.name;
+                        if (comment) cout << ':' << rref.comment;
+                        cout << '\t' << names[i];
+                        if (comment) cout << ':' << comments[i];
+                        cout << '\t' << pair.distance << '\t' << pair.pvalue << '\t' << pair.numer << '/' << FPM_PAIR_DENOM(pair) << '\n';
+                    }
+                }
+                if (table) cout << endl;
+            }
+        }
+    }
+    if (pinned) fpm_host_free(pinned);
+    fpm_dist_set_reference(gpuContext(), nullptr);
+    cout.flush();
+    return 0;
+}
+
 int CommandDistance::run() const
 {
     if (arguments.size() < 2 || options.at("help").active) {
@@ -416,6 +528,19 @@ int CommandDistance::run() const
     for (size_t i = 1; i < arguments.size(); i++) {
         if (list) splitFile(arguments[i], queryFiles);
         else queryFiles.push_back(arguments[i]);
+    }
+    // Query side given as sketch files only: stream them.  The files are mapped, rows of sketches go from
+    // the mapping into a pinned panel chunk and on to the GPU, where the reference panel and its index stay resident; no
+    // Reference objects, no second copy of a multi-gigabyte query set.  FPMASH_MSH_STREAM=0 keeps the loading path.
+    {
+        bool allSketches = !queryFiles.empty() && !fingerprint;
+        for (const string& f : queryFiles) allSketches &= hasSuffix(f, suffixSketch);
+        const char* e = getenv("FPMASH_MSH_STREAM");
+        if (allSketches && !(e && e[0] == '0') && sketchRef.getReferenceCount() > 0) {
+            const int rc = streamQueries(sketchRef, queryFiles, parameters, table, comment, distanceMax, pValueMax);
+            if (rc == 0 && warningCount > 0 && !parameters.reads) warnKmerSize(parameters, *this, lengthMax, lengthMaxName, randomChance, kMin, warningCount);
+            return rc;
+        }
     }
     Sketch sketchQuery;
     if (fingerprint && tagMSH) sketchQuery.initFromFiles(queryFiles, parameters);

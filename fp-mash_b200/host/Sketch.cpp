@@ -973,6 +973,43 @@ uint64_t Sketch::initParametersFromCapnp(const char* file)   // Sketch.cpp:401-4
 }
 
 
+// The checks initFromFiles applies to a sketch file among its inputs (Sketch.cpp:266-313): false = the file is skipped, with
+// the reference's warning.
+bool Sketch::sketchFileCompatible(const Parameters& parameters, const string& file, bool contain)
+{
+    Sketch sketchTest;
+    sketchTest.initParametersFromCapnp(file.c_str());
+    Sketch current;
+    current.parameters = parameters;
+    string alphabet, alphabetTest;
+    current.getAlphabetAsString(alphabet);
+    sketchTest.getAlphabetAsString(alphabetTest);
+    if (alphabet != alphabetTest) {
+        cerr << "\nWARNING: The sketch file " << file << " has different alphabet (" << alphabetTest << ") than the current alphabet (" << alphabet << "). This file will be skipped." << endl << endl;
+        return false;
+    }
+    if (sketchTest.getHashSeed() != parameters.seed) {
+        cerr << "\nWARNING: The sketch " << file << " has a seed size (" << sketchTest.getHashSeed() << ") that does not match the current seed (" << parameters.seed << "). This file will be skipped." << endl << endl;
+        return false;
+    }
+    if (sketchTest.getKmerSize() != parameters.kmerSize) {
+        cerr << "\nWARNING: The sketch " << file << " has a kmer size (" << sketchTest.getKmerSize() << ") that does not match the current kmer size (" << parameters.kmerSize << "). This file will be skipped." << endl << endl;
+        return false;
+    }
+    if (!contain && sketchTest.getMinHashesPerWindow() < parameters.minHashesPerWindow) {
+        cerr << "\nWARNING: The sketch file " << file << " has a target sketch size (" << sketchTest.getMinHashesPerWindow() << ") that is smaller than the current sketch size (" << parameters.minHashesPerWindow << "). This file will be skipped." << endl << endl;
+        return false;
+    }
+    if (sketchTest.getNoncanonical() != parameters.noncanonical) {
+        cerr << "\nWARNING: The sketch file " << file << " is " << (sketchTest.getNoncanonical() ? "noncanonical" : "canonical") << ", which is incompatible with the current setting. This file will be skipped." << endl << endl;
+        return false;
+    }
+    if (sketchTest.getMinHashesPerWindow() > parameters.minHashesPerWindow) {
+        cerr << "\nWARNING: The sketch file " << file << " has a target sketch size (" << sketchTest.getMinHashesPerWindow() << ") that is larger than the current sketch size (" << parameters.minHashesPerWindow << "). Its sketches will be reduced." << endl << endl;
+    }
+    return true;
+}
+
 int Sketch::initFromFiles(const vector<string>& files, const Parameters& parametersNew, int verbosity, bool enforceParameters, bool contain)
 {
     parameters = parametersNew;
@@ -1017,35 +1054,8 @@ int Sketch::initFromFiles(const vector<string>& files, const Parameters& paramet
         if (isSketch) {
             flushRawBatch(rawBatch, batch);
             flushBatch(batch);                                   // keep submission order (ThreadPool output queue)
-            Sketch sketchTest;
-            sketchTest.initParametersFromCapnp(files[i].c_str());
             if (i == 0 && !enforceParameters) initParametersFromCapnp(files[i].c_str());
-            string alphabet, alphabetTest;
-            getAlphabetAsString(alphabet);
-            sketchTest.getAlphabetAsString(alphabetTest);
-            if (alphabet != alphabetTest) {
-                cerr << "\nWARNING: The sketch file " << files[i] << " has different alphabet (" << alphabetTest << ") than the current alphabet (" << alphabet << "). This file will be skipped." << endl << endl;
-                continue;
-            }
-            if (sketchTest.getHashSeed() != parameters.seed) {
-                cerr << "\nWARNING: The sketch " << files[i] << " has a seed size (" << sketchTest.getHashSeed() << ") that does not match the current seed (" << parameters.seed << "). This file will be skipped." << endl << endl;
-                continue;
-            }
-            if (sketchTest.getKmerSize() != parameters.kmerSize) {
-                cerr << "\nWARNING: The sketch " << files[i] << " has a kmer size (" << sketchTest.getKmerSize() << ") that does not match the current kmer size (" << parameters.kmerSize << "). This file will be skipped." << endl << endl;
-                continue;
-            }
-            if (!contain && sketchTest.getMinHashesPerWindow() < parameters.minHashesPerWindow) {
-                cerr << "\nWARNING: The sketch file " << files[i] << " has a target sketch size (" << sketchTest.getMinHashesPerWindow() << ") that is smaller than the current sketch size (" << parameters.minHashesPerWindow << "). This file will be skipped." << endl << endl;
-                continue;
-            }
-            if (sketchTest.getNoncanonical() != parameters.noncanonical) {
-                cerr << "\nWARNING: The sketch file " << files[i] << " is " << (sketchTest.getNoncanonical() ? "noncanonical" : "canonical") << ", which is incompatible with the current setting. This file will be skipped." << endl << endl;
-                continue;
-            }
-            if (sketchTest.getMinHashesPerWindow() > parameters.minHashesPerWindow) {
-                cerr << "\nWARNING: The sketch file " << files[i] << " has a target sketch size (" << sketchTest.getMinHashesPerWindow() << ") that is larger than the current sketch size (" << parameters.minHashesPerWindow << "). Its sketches will be reduced." << endl << endl;
-            }
+            if (!sketchFileCompatible(parameters, files[i], contain)) continue;
             loadSketchFile(files[i]);
             continue;
         }

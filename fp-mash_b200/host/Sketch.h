@@ -66,6 +66,7 @@ public:
     };
 
     void initFromFingerprints(const std::vector<std::string>& files, const Parameters& parametersNew);
+    static bool sketchFileCompatible(const Parameters& parameters, const std::string& file, bool contain);
     int initFromFiles(const std::vector<std::string>& files, const Parameters& parametersNew, int verbosity = 0,
                       bool enforceParameters = false, bool contain = false);
     void initFromReads(const std::vector<std::string>& files, const Parameters& parametersNew);

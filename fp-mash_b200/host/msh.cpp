@@ -1,4 +1,8 @@
 // msh.cpp -- see msh.h.  Wire layout and allocator behaviour: SURVEY.md section 5.1 / Appendix D.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include "msh.h"
 
 #include <stdio.h>
@@ -355,6 +359,110 @@ bool decode(const uint8_t* data, size_t size, bool use64, uint64_t max_hashes, F
             for (size_t j = 0; j < hn; j++) r.counts[j] = j < cn ? p[j] : 0;
         }
     }
+    return true;
+}
+
+// ---- PanelReader -------------------------------------------------------------------------------------------------
+namespace {
+struct ReaderState { Msg m; RootView rv; };
+}  // namespace
+
+PanelReader::~PanelReader()
+{
+    delete (ReaderState*)state_;
+    if (map_) munmap((void*)map_, size_);
+}
+
+bool PanelReader::open(const std::string& path, std::string& err)
+{
+    int fd = ::open(path.c_str(), O_RDONLY);
+    if (fd < 0) { err = "could not open the file"; return false; }
+    struct stat st;
+    if (fstat(fd, &st) != 0 || st.st_size <= 0) { ::close(fd); err = "empty or unreadable file"; return false; }
+    size_ = (size_t)st.st_size;
+    void* p = mmap(nullptr, size_, PROT_READ, MAP_PRIVATE, fd, 0);
+    ::close(fd);
+    if (p == MAP_FAILED) { map_ = nullptr; err = "mmap failed"; return false; }
+    map_ = (const uint8_t*)p;
+    madvise(p, size_, MADV_SEQUENTIAL);
+    ReaderState* stt = new ReaderState();
+    state_ = stt;
+    if (!msh::open(map_, size_, stt->m) || !open_root(stt->m, stt->rv)) { err = stt->m.err; return false; }
+    fill_header(stt->m, stt->rv.root, header_);
+    Obj a;
+    if (!ptr_field(stt->m, stt->rv.root, 2, a) || !read_text(stt->m, a, header_.alphabet)) { err = stt->m.err; return false; }
+    header_.has_alphabet = a.kind != -1;
+    n_refs_ = stt->rv.n_refs;
+    return true;
+}
+
+static bool hash_list_of(Msg& m, const RootView& rv, uint64_t i, bool use64, Obj& o, size_t& n, std::string& err)
+{
+    const size_t esz = rv.elem_nd + rv.elem_np;
+    StructView e{rv.refs.seg, rv.refs.idx + 1 + i * esz, (uint32_t)rv.elem_nd, (uint32_t)rv.elem_np};
+    if (!ptr_field(m, e, use64 ? 5 : 4, o)) { err = m.err; return false; }
+    n = 0;
+    if (o.kind == 1) {
+        n = o.hi >> 3;
+        if ((o.hi & 7) != (use64 ? 5u : 4u)) { err = "hash list has the wrong element size"; return false; }
+        if (!m.in(o.seg, o.idx, use64 ? n : (n + 1) / 2)) { err = "hash list out of range"; return false; }
+    }
+    return true;
+}
+
+bool PanelReader::max_list(bool use64, uint64_t max_hashes, uint64_t& out, std::string& err) const
+{
+    ReaderState* stt = (ReaderState*)state_;
+    out = 0;
+    for (uint64_t i = 0; i < n_refs_; i++) {
+        Obj o;
+        size_t n;
+        if (!hash_list_of(stt->m, stt->rv, i, use64, o, n, err)) return false;
+        if (max_hashes && n > max_hashes) n = max_hashes;
+        if (n > out) out = n;
+    }
+    return true;
+}
+
+bool PanelReader::fill(uint64_t i0, uint64_t i1, bool use64, uint64_t max_hashes, uint64_t* hashes, uint64_t stride, uint32_t* sizes, uint64_t* lengths,
+                       std::string& err) const
+{
+    ReaderState* stt = (ReaderState*)state_;
+    Msg& m = stt->m;
+    const RootView& rv = stt->rv;
+    const size_t esz = rv.elem_nd + rv.elem_np;
+    if (i1 > n_refs_ || i0 > i1) { err = "row range outside the file"; return false; }
+    for (uint64_t i = i0; i < i1; i++) {
+        StructView e{rv.refs.seg, rv.refs.idx + 1 + i * esz, (uint32_t)rv.elem_nd, (uint32_t)rv.elem_np};
+        const uint64_t d0 = data_word(m, e, 0), len64 = data_word(m, e, 1);
+        lengths[i - i0] = len64 ? len64 : (uint32_t)d0;                      // Sketch.cpp:1099-1106
+        Obj o;
+        size_t n;
+        if (!hash_list_of(m, rv, i, use64, o, n, err)) return false;
+        if (max_hashes && n > max_hashes) n = max_hashes;                     // Sketch.cpp:1117-1120
+        if (n > stride) { err = "a sketch is longer than the panel stride"; return false; }
+        uint64_t* dst = hashes + (i - i0) * stride;
+        if (use64) memcpy(dst, m.seg[o.seg] + o.idx, n * 8);
+        else {
+            const uint32_t* p = n ? (const uint32_t*)(m.seg[o.seg] + o.idx) : nullptr;
+            for (size_t j = 0; j < n; j++) dst[j] = p[j];
+        }
+        sizes[i - i0] = (uint32_t)n;
+    }
+    return true;
+}
+
+bool PanelReader::meta(uint64_t i, std::string& name, std::string& comment, std::string& err) const
+{
+    ReaderState* stt = (ReaderState*)state_;
+    Msg& m = stt->m;
+    const RootView& rv = stt->rv;
+    if (i >= n_refs_) { err = "row outside the file"; return false; }
+    const size_t esz = rv.elem_nd + rv.elem_np;
+    StructView e{rv.refs.seg, rv.refs.idx + 1 + i * esz, (uint32_t)rv.elem_nd, (uint32_t)rv.elem_np};
+    Obj o;
+    if (!ptr_field(m, e, 2, o) || !read_text(m, o, name)) { err = m.err; return false; }
+    if (!ptr_field(m, e, 3, o) || !read_text(m, o, comment)) { err = m.err; return false; }
     return true;
 }
 

@@ -42,6 +42,35 @@ std::vector<uint8_t> encode(const File& f, bool write_counts);
 bool decode(const uint8_t* data, size_t size, bool use64, uint64_t max_hashes, File& out, std::string& err);
 bool decode_header(const uint8_t* data, size_t size, Header& h, uint64_t& ref_count, bool& first_has_counts, std::string& err);
 
+// Streaming reader for `mash dist` on large sketch files: the file is mapped, nothing is materialised as
+// Reference objects; rows of sketches are copied straight from the mapping into a dense panel (the layout fpm_dist_tile
+// takes: [rows][stride] u64 + sizes + lengths), e.g. a pinned staging buffer, chunk by chunk.  Same rules as loadCapnp
+// (Sketch.cpp:1059-1219): referenceList else referenceListOld, hashes64 / hashes32 by use64, lists truncated to
+// max_hashes, length64 else length.
+class PanelReader {
+public:
+    PanelReader() = default;
+    ~PanelReader();
+    PanelReader(const PanelReader&) = delete;
+    PanelReader& operator=(const PanelReader&) = delete;
+    bool open(const std::string& path, std::string& err);
+    const Header& header() const { return header_; }
+    uint64_t count() const { return n_refs_; }
+    // largest list length over all references after truncation to max_hashes (0 = no truncation): the panel stride
+    bool max_list(bool use64, uint64_t max_hashes, uint64_t& out, std::string& err) const;
+    // rows [i0, i1) -> hashes[(i - i0) * stride + j], sizes[i - i0], lengths[i - i0]; unused slots are left untouched
+    bool fill(uint64_t i0, uint64_t i1, bool use64, uint64_t max_hashes, uint64_t* hashes, uint64_t stride, uint32_t* sizes, uint64_t* lengths,
+              std::string& err) const;
+    bool meta(uint64_t i, std::string& name, std::string& comment, std::string& err) const;
+
+private:
+    const uint8_t* map_ = nullptr;
+    size_t size_ = 0;
+    Header header_;
+    uint64_t n_refs_ = 0;
+    void* state_ = nullptr;          // parsed segment table + reference list position
+};
+
 bool read_file(const std::string& path, std::vector<uint8_t>& bytes);
 bool write_file(const std::string& path, const std::vector<uint8_t>& bytes);
 

@@ -325,10 +325,43 @@ def test_cli_on_several_gpus_prints_the_same(tmp_path):
         return r.stdout
 
     one = {"FPMASH_GPUS": "1"}
-    many = {"FPMASH_GPUS": "3", "FPMASH_MULTI_MIN": "1"}
+    many = {"FPMASH_GPUS": "3", "FPMASH_MULTI_MIN": "1", "FPMASH_MSH_STREAM": "0"}      # (sketch-file queries would otherwise be streamed on one GPU)
+    loaded = {"FPMASH_GPUS": "1", "FPMASH_MSH_STREAM": "0"}
     with_env(one, ["sketch", "-o", "one"] + names)
     with_env(many, ["sketch", "-o", "many"] + names)
     assert same_bytes(tmp_path / "one.msh", tmp_path / "many.msh")
     for args in (["dist", "one.msh", "one.msh"], ["dist", "-d", "0.2", "one.msh", "one.msh"], ["dist", "-t", "one.msh", "one.msh"],
                  ["dist", "-v", "1e-20", "one.msh", "g03.fa", "g04.fa"]):
-        assert with_env(one, args) == with_env(many, args), args
+        want = with_env(one, args)                      # sketch-file queries streamed from the mapped file, resident reference panel
+        assert want == with_env(many, args), args       # all GPUs, queries loaded
+        assert want == with_env(loaded, args), args     # one GPU, queries loaded
+        assert len(want) > 100
+
+
+def test_streamed_queries_in_small_chunks(tmp_path):
+    """`mash dist ref.msh q1.msh q2.msh`: the query files are mapped and streamed chunk by chunk against the resident reference
+    panel.  Two query files, differing sketch sizes (the larger is reduced like loadCapnp does), names and comments kept."""
+    rng = np.random.default_rng(8)
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    base = lut[rng.integers(0, 4, size=60000)]
+    for name, n in (("a", 40), ("b", 25), ("r", 12)):
+        with open(tmp_path / (name + ".fa"), "wb") as f:
+            for i in range(n):
+                g = base.copy()
+                idx = rng.random(g.size) < 0.002 * (1 + i % 7)
+                g[idx] = lut[rng.integers(0, 4, size=int(idx.sum()))]
+                f.write(b">%s%d the %dth of %s\n" % (name.encode(), i, i, name.encode()) + bytes(g) + b"\n")
+    run(["sketch", "-i", "-s", "400", "-o", "r", "r.fa"], cwd=tmp_path)
+    run(["sketch", "-i", "-s", "400", "-o", "a", "a.fa"], cwd=tmp_path)
+    run(["sketch", "-i", "-s", "700", "-o", "b", "b.fa"], cwd=tmp_path)
+
+    def out(env, args):
+        r = subprocess.run([MASH] + args, capture_output=True, text=True, cwd=tmp_path, env=dict(os.environ, **env))
+        assert r.returncode == 0, r.stderr
+        return r.stdout, r.stderr
+
+    for args in (["dist", "r.msh", "a.msh", "b.msh"], ["dist", "-C", "-d", "0.05", "r.msh", "a.msh", "b.msh"], ["dist", "-t", "r.msh", "b.msh", "a.msh"]):
+        s_out, s_err = out({}, args)
+        l_out, l_err = out({"FPMASH_MSH_STREAM": "0"}, args)
+        assert s_out == l_out and len(s_out) > 1000, args
+        assert ("will be reduced" in s_err) == ("will be reduced" in l_err)
