@@ -49,6 +49,7 @@ struct fpm_ctx {
     // streaming sketch input (fpm_sketch_stream_*): sequence accumulated in HBM + group ends
     fpm::DevBuf stream_buf;
     uint64_t stream_used = 0;
+    uint64_t stream_tickets = 0;                 // fpm_sketch_stream_append_async: copies queued so far (event = ticket & 1)
     std::vector<uint64_t> stream_goff;
     // dist scratch
     fpm::DevBuf d_ref, d_qry, d_rs, d_qs, d_rl, d_ql, d_out, d_misc, d_p32, d_rank;

@@ -184,7 +184,26 @@ int sketch_batch_dev_impl(fpm_ctx* ctx, const fpm_sketch_params* p, const uint8_
     if ((size_t)max_smem < (size_t)SK_SORT_CAP * 8) { set_error("device offers only %d bytes of opt-in shared memory", max_smem); return FPM_ERR_UNSUPPORTED; }
     if (configure_sketch_select((size_t)SK_SORT_CAP * 8) != 0) { set_error("cudaFuncSetAttribute(select) failed"); return FPM_ERR_CUDA; }
 
+    // survivor log (only when multiplicities are wanted): everything the first pass inserts, so that the order-dependent top
+    // count needs no second pass over the input.  Sized for the planned number of insertions; an overflow, or a sketch that
+    // needed a re-run, falls back to the trace pass.
+    uint64_t log_cap = 0;
+    if (want_counts && nucleotide) {
+        for (uint32_t g = 0; g < n_groups; g++) {
+            const uint64_t n = h_goff[g + 1] - h_goff[g];
+            const uint64_t cov_guess = p->min_cov > 1 ? std::max<uint64_t>(1, std::min<uint64_t>(32, (64ull << 20) / (4 * target * n_groups))) : 1;
+            log_cap += std::min<uint64_t>(n, 4 * target * cov_guess);
+        }
+        log_cap = std::min<uint64_t>(log_cap + 1024, (uint64_t)1 << 28);
+        if ((rc = ctx->firstpos.ensure(log_cap * 16 + 64))) return rc;
+    }
+    uint64_t* d_log_h = ctx->firstpos.as<uint64_t>() + 8;
+    uint64_t* d_log_p = d_log_h + log_cap;
+    unsigned long long* d_log_count = ctx->firstpos.as<unsigned long long>();
+    int passes_run = 0;
+
     for (int pass = 0; pass < 12; pass++) {
+        passes_run = pass + 1;
         // tables for the active groups
         uint64_t slots = 0;
         uint32_t max_cap = 64;
@@ -226,6 +245,10 @@ int sketch_batch_dev_impl(fpm_ctx* ctx, const fpm_sketch_params* p, const uint8_
         a.overflow = ctx->overflow.as<uint32_t>();
         a.sketch_size = s; a.seed = p->seed; a.fold_case = !p->preserve_case; a.hash32 = !p->use64;
             a.c_tbl = 0x54474341u; a.c_add1 = 0x52dce729ULL; a.c_add2 = 0x38495ab5ULL; a.c_add1s = a.c_add1 + 5ull * a.seed;
+        if (log_cap && pass == 0) {
+            a.log_h = d_log_h; a.log_p = d_log_p; a.log_count = d_log_count; a.log_cap = log_cap;
+            FPM_CUDA(cudaMemsetAsync(d_log_count, 0, 8, st));
+        }
         FPM_CUDA(cudaMemcpyAsync(ctx->args.p, &a, sizeof a, cudaMemcpyHostToDevice, st));
         for (const auto& r : ranges) {
             ctx->time_begin(FPM_KERNEL_SKETCH_HASH);
@@ -241,6 +264,7 @@ int sketch_batch_dev_impl(fpm_ctx* ctx, const fpm_sketch_params* p, const uint8_
         sa.maxkey_cnt = a.maxkey_cnt; sa.maxkey_pos = a.maxkey_pos; sa.active = a.active;
         sa.sketch_size = s; sa.min_cov = p->min_cov;
         sa.sort_cap = std::min<uint32_t>(SK_SORT_CAP, max_cap);
+        sa.thresh = a.thresh;
         sa.scratch = nullptr;
         if (max_cap > SK_SORT_CAP) {   // large sketches: sort qualifying keys in global memory
             if ((rc = ctx->scratch.ensure(slots * 8))) return rc;
@@ -295,15 +319,20 @@ int sketch_batch_dev_impl(fpm_ctx* ctx, const fpm_sketch_params* p, const uint8_
         for (uint32_t g = 0; g < n_groups; g++)
             if (h_outn[g] == s && h_topcnt[g] > p->min_cov) tg.push_back(g);
         if (!tg.empty()) {
-            // bucket layout from the counts just written
-            std::vector<uint32_t> row(s);
+            // bucket layout from the counts just written (one copy and one wait, whole rows of all sketches when many need it)
             std::vector<uint64_t> h_troff((size_t)n_groups * s, 0);
             uint64_t total = 0;
-            for (uint32_t g : tg) {
-                FPM_CUDA(cudaMemcpyAsync(row.data(), d_out_counts + (uint64_t)g * s, sizeof(uint32_t) * s, cudaMemcpyDeviceToHost, st));
+            unsigned long long h_logged = ~0ULL;
+            {
+                const uint32_t g_first = tg.front(), g_last = tg.back();
+                std::vector<uint32_t> rows((size_t)(g_last - g_first + 1) * s);
+                FPM_CUDA(cudaMemcpyAsync(rows.data(), d_out_counts + (uint64_t)g_first * s, sizeof(uint32_t) * rows.size(), cudaMemcpyDeviceToHost, st));
+                if (log_cap) FPM_CUDA(cudaMemcpyAsync(&h_logged, d_log_count, 8, cudaMemcpyDeviceToHost, st));
                 FPM_CUDA(cudaStreamSynchronize(st));
-                for (uint32_t r = 0; r < s; r++) { h_troff[(uint64_t)g * s + r] = total; total += row[r]; }
+                for (uint32_t g : tg)
+                    for (uint32_t r = 0; r < s; r++) { h_troff[(uint64_t)g * s + r] = total; total += rows[(size_t)(g - g_first) * s + r]; }
             }
+            const bool from_log = log_cap && passes_run == 1 && h_logged <= log_cap;
             if ((rc = ctx->tr_off.ensure(sizeof(uint64_t) * (uint64_t)n_groups * s))) return rc;
             if ((rc = ctx->tr_cursor.ensure(sizeof(uint32_t) * (uint64_t)n_groups * s))) return rc;
             if ((rc = ctx->tr_pos.ensure(sizeof(uint64_t) * std::max<uint64_t>(total, 1)))) return rc;
@@ -326,6 +355,15 @@ int sketch_batch_dev_impl(fpm_ctx* ctx, const fpm_sketch_params* p, const uint8_
             a.tr_cursor = ctx->tr_cursor.as<uint32_t>(); a.tr_pos = ctx->tr_pos.as<uint64_t>();
             a.sketch_size = s; a.seed = p->seed; a.fold_case = !p->preserve_case; a.hash32 = !p->use64;
             a.c_tbl = 0x54474341u; a.c_add1 = 0x52dce729ULL; a.c_add2 = 0x38495ab5ULL; a.c_add1s = a.c_add1 + 5ull * a.seed;
+            if (from_log) {
+                // positions of the sketches' hashes straight from what the first pass logged
+                SketchArgs al = a;
+                al.log_h = d_log_h; al.log_p = d_log_p; al.log_count = nullptr; al.log_cap = log_cap;
+                FPM_CUDA(cudaMemcpyAsync(ctx->args.p, &al, sizeof al, cudaMemcpyHostToDevice, st));
+                launch_sketch_trace_log(h_logged, st, ctx->args.as<SketchArgs>());
+                ctx->launches++;
+                FPM_CUDA(cudaGetLastError());
+            } else {
             FPM_CUDA(cudaMemcpyAsync(ctx->args.p, &a, sizeof a, cudaMemcpyHostToDevice, st));
             for (const auto& r : ranges) {
                 ctx->time_begin(FPM_KERNEL_SKETCH_HASH);
@@ -334,6 +372,7 @@ int sketch_batch_dev_impl(fpm_ctx* ctx, const fpm_sketch_params* p, const uint8_
                 ctx->time_end();
                 ctx->launches++;
                 FPM_CUDA(cudaGetLastError());
+            }
             }
             launch_sketch_topcount((uint32_t)tg.size(), st, ctx->glist.as<uint32_t>(), s, p->min_cov, a.tr_off, a.tr_cap, a.tr_pos, d_out_counts);
             ctx->launches++;
@@ -596,6 +635,7 @@ int sketch_reads_sharded_impl(fpm_ctx* ctx, const fpm_sketch_params* p, const ui
             sa.tkeys = m_keys; sa.tcnt = m_cnt; sa.tpos = m_pos; sa.toff = ctx->toff.as<uint64_t>(); sa.tmask = m_extra;
             sa.maxkey_cnt = m_extra + 2; sa.maxkey_pos = (const uint64_t*)(m_extra + 4); sa.active = ctx->active.as<uint8_t>();
             sa.sketch_size = s; sa.min_cov = p->min_cov;
+            sa.thresh = ctx->thresh.as<uint64_t>();
             sa.sort_cap = std::min<uint32_t>(SK_SORT_CAP, merged_cap);
             sa.scratch = merged_cap > SK_SORT_CAP ? m_sort : nullptr;
             sa.out_hashes = d_out_hashes; sa.out_counts = want_counts ? d_out_counts : nullptr; sa.out_firstpos = nullptr;
@@ -854,6 +894,36 @@ int fpm_sketch_stream_append(fpm_ctx* ctx, const uint8_t* seq, uint64_t bytes)
     FPM_CUDA(cudaMemcpyAsync((uint8_t*)ctx->stream_buf.p + ctx->stream_used, seq, bytes, cudaMemcpyHostToDevice, ctx->stream));
     FPM_CUDA(cudaStreamSynchronize(ctx->stream));   // the caller may reuse its staging buffer right away
     ctx->stream_used += bytes;
+    return FPM_OK;
+}
+
+// The same without waiting for the copy: the piece must stay untouched until fpm_sketch_stream_wait(ticket).  With two staging
+// buffers the host reads the next piece of the file while this one crosses PCIe.
+int fpm_sketch_stream_append_async(fpm_ctx* ctx, const uint8_t* seq, uint64_t bytes, uint64_t* ticket)
+{
+    if (!ctx || !ticket) { set_error("NULL argument"); return FPM_ERR_ARG; }
+    if (ctx->stream_goff.empty()) { set_error("fpm_sketch_stream_begin was not called"); return FPM_ERR_ARG; }
+    FPM_CUDA(cudaSetDevice(ctx->device));
+    if (!ctx->copy_done[0]) {
+        if (!ctx->copy_stream) FPM_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        FPM_CUDA(cudaEventCreateWithFlags(&ctx->copy_done[0], cudaEventDisableTiming));
+        FPM_CUDA(cudaEventCreateWithFlags(&ctx->copy_done[1], cudaEventDisableTiming));
+    }
+    int rc = fpm::stream_reserve(ctx, bytes);      // (growing the HBM buffer waits for the copies in flight: same stream)
+    if (rc) return rc;
+    if (bytes) FPM_CUDA(cudaMemcpyAsync((uint8_t*)ctx->stream_buf.p + ctx->stream_used, seq, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->stream_used += bytes;
+    *ticket = ctx->stream_tickets++;
+    FPM_CUDA(cudaEventRecord(ctx->copy_done[*ticket & 1], ctx->stream));
+    return FPM_OK;
+}
+
+int fpm_sketch_stream_wait(fpm_ctx* ctx, uint64_t ticket)
+{
+    if (!ctx) { set_error("ctx is NULL"); return FPM_ERR_ARG; }
+    if (ticket >= ctx->stream_tickets) { set_error("unknown ticket"); return FPM_ERR_ARG; }
+    if (ticket + 2 < ctx->stream_tickets) return FPM_OK;                  // two newer copies were queued behind it on the same stream
+    FPM_CUDA(cudaEventSynchronize(ctx->copy_done[ticket & 1]));
     return FPM_OK;
 }
 

@@ -71,6 +71,12 @@ struct SketchArgs {
     uint32_t c_tbl;
     uint64_t c_add1, c_add2, c_add1s;   // c_add1s = c_add1 + 5 * seed (first Murmur block, sketch_tables.cuh)
     uint64_t pos_base;           // added to every stream position stored (a rank's part of one read set spread over GPUs)
+    // survivor log (nullable): every (hash, position) that reached a table, so that the order-dependent top count can be
+    // settled from the first pass instead of hashing the input a second time
+    uint64_t* log_h;
+    uint64_t* log_p;
+    unsigned long long* log_count;
+    uint64_t log_cap;
 };
 
 // ---------------------------------------------------------------------------------------
@@ -254,6 +260,15 @@ static __device__ __noinline__ void sketch_emit(const SketchArgs& a, uint64_t h,
             if (idx < a.tr_cap[b]) a.tr_pos[a.tr_off[b] + idx] = pos + a.pos_base;
         }
         return;
+    }
+    if (a.log_h) {
+        // warp-aggregated append: one atomic per group of converged lanes
+        const unsigned m = __activemask();
+        const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+        unsigned long long at = 0;
+        if (lane == leader) at = atomicAdd(a.log_count, (unsigned long long)__popc(m));
+        at = __shfl_sync(m, at, leader) + __popc(m & ((1u << lane) - 1u));
+        if (at < a.log_cap) { a.log_h[at] = h; a.log_p[at] = pos; }
     }
     if (h == SK_EMPTY) {   // the one value that cannot be a table key
         atomicAdd(&a.maxkey_cnt[g], 1u);

@@ -8,6 +8,26 @@ namespace fpm {
 // Selection: one CTA per sketch.
 // ---------------------------------------------------------------------------------------
 
+// One CTA walks a whole table: with one dependent load per iteration that is latency bound (256 iterations x ~0.6 us for a
+// 262144-slot table: 0.15 ms per walk, three walks per sketch).  So eight slots are fetched before any is looked at.
+template <typename F>
+__device__ __forceinline__ void for_each_slot(const uint64_t* __restrict__ tkeys, const uint32_t* __restrict__ tcnt, uint64_t base, uint32_t mask, F&& f)
+{
+    for (uint32_t i0 = threadIdx.x; i0 <= mask; i0 += blockDim.x * 8) {
+        uint64_t k[8];
+        uint32_t c[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const uint32_t i = i0 + u * blockDim.x;
+            const bool in = i <= mask && i >= i0;                      // (i >= i0: no wrap-around at 2^32)
+            k[u] = in ? tkeys[base + i] : SK_EMPTY;
+            c[u] = in ? tcnt[base + i] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) f(k[u], c[u]);
+    }
+}
+
 __global__ void __launch_bounds__(1024) sketch_select_kernel(const SelectArgs a)
 {
     extern __shared__ uint64_t s_keys[];
@@ -21,28 +41,45 @@ __global__ void __launch_bounds__(1024) sketch_select_kernel(const SelectArgs a)
     __syncthreads();
     {
         uint32_t nd = 0, nq1 = 0;
-        for (uint32_t i = threadIdx.x; i <= mask; i += blockDim.x) {
-            if (a.tkeys[base + i] != SK_EMPTY) { nd++; nq1 += a.tcnt[base + i] >= a.min_cov; }
-        }
+        for_each_slot(a.tkeys, a.tcnt, base, mask, [&](uint64_t key, uint32_t cnt) {
+            if (key != SK_EMPTY) { nd++; nq1 += cnt >= a.min_cov; }
+        });
         if (threadIdx.x == 0 && a.maxkey_cnt[g]) { nd++; nq1 += a.maxkey_cnt[g] >= a.min_cov; }
         if (nd) atomicAdd(&s_nd, nd);
         if (nq1) atomicAdd(&s_nq, nq1);
     }
     __syncthreads();
-    const uint32_t nq = s_nq;
+    uint32_t nq = s_nq;
     if (threadIdx.x == 0) { a.stat_nq[g] = nq; a.stat_nd[g] = s_nd; a.stat_topcnt[g] = 0; }
     __syncthreads();
+    // Many more qualifying hashes than sketch slots (a read set at 30x under a bound guessed for 32x): the hashes are uniform
+    // below the bound, so about 2 s of them lie below cut = bound * 2 s / nq.  If at least s do, the bottom-s is among them and
+    // only they are sorted -- in shared memory instead of a one-CTA bitonic sort of all nq keys in global memory.
+    uint64_t cut = ~0ULL;
+    if (a.thresh && nq > 4 * a.sketch_size && a.thresh[g] != ~0ULL) {
+        const uint64_t c = (uint64_t)((double)a.thresh[g] * (2.0 * (double)a.sketch_size / (double)nq));
+        if (threadIdx.x == 0) s_nq = 0;
+        __syncthreads();
+        uint32_t below = 0;
+        for_each_slot(a.tkeys, a.tcnt, base, mask, [&](uint64_t key, uint32_t cnt) {
+            below += key <= c && cnt >= a.min_cov;                       // (SK_EMPTY is above every cut)
+        });
+        if (below) atomicAdd(&s_nq, below);
+        __syncthreads();
+        const uint32_t nb = s_nq;
+        __syncthreads();
+        if (nb >= a.sketch_size) { cut = c; nq = nb; }
+    }
     // keys are sorted in shared memory when they fit, else in this sketch's slice of the global scratch
     // (same capacity as its table, so P = pow2ceil(nq) always fits)
     uint64_t* keys = nq <= a.sort_cap ? s_keys : (a.scratch ? a.scratch + base : nullptr);
     if (!keys) { if (threadIdx.x == 0) a.out_n[g] = 0; return; }
     if (threadIdx.x == 0) s_nq = 0;
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i <= mask; i += blockDim.x) {
-        uint64_t key = a.tkeys[base + i];
-        if (key != SK_EMPTY && a.tcnt[base + i] >= a.min_cov) keys[atomicAdd(&s_nq, 1u)] = key;
-    }
-    if (threadIdx.x == 0 && a.maxkey_cnt[g] >= a.min_cov && a.maxkey_cnt[g]) keys[atomicAdd(&s_nq, 1u)] = SK_EMPTY;
+    for_each_slot(a.tkeys, a.tcnt, base, mask, [&](uint64_t key, uint32_t cnt) {
+        if (key != SK_EMPTY && key <= cut && cnt >= a.min_cov) keys[atomicAdd(&s_nq, 1u)] = key;
+    });
+    if (threadIdx.x == 0 && cut == ~0ULL && a.maxkey_cnt[g] >= a.min_cov && a.maxkey_cnt[g]) keys[atomicAdd(&s_nq, 1u)] = SK_EMPTY;
     uint32_t P = 1;
     while (P < nq) P <<= 1;
     for (uint32_t i = nq + threadIdx.x; i < P; i += blockDim.x) keys[i] = SK_EMPTY;
@@ -123,6 +160,20 @@ __global__ void __launch_bounds__(256) sketch_topcount_kernel(const uint32_t* gr
     atomicAdd(&s_cnt, c);
     __syncthreads();
     if (threadIdx.x == 0) out_counts[b] = s_cnt;
+}
+
+// The trace pass without a second pass over the input: the first pass logged every (hash, position) it inserted.
+__global__ void __launch_bounds__(256) sketch_trace_log_kernel(const SketchArgs* __restrict__ ga, uint64_t n_log)
+{
+    const SketchArgs& a = *ga;
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_log) return;
+    sketch_emit(a, a.log_h[i], a.log_p[i], 0, a.n_groups - 1, 1);
+}
+
+void launch_sketch_trace_log(uint64_t n_log, cudaStream_t st, const SketchArgs* d_args)
+{
+    if (n_log) sketch_trace_log_kernel<<<(uint32_t)((n_log + 255) / 256), 256, 0, st>>>(d_args, n_log);
 }
 
 // -fp mode: one thread per fingerprint line.

@@ -17,6 +17,8 @@ struct SelectArgs {
     uint32_t sketch_size;
     uint32_t min_cov;
     uint32_t sort_cap;       // u64 keys that fit the dynamic shared memory of this launch
+    const uint64_t* thresh;  // [n_groups] the bound the pass admitted hashes under (nullable): lets a sketch with many more
+                             // qualifying hashes than slots sort only those below a cut instead of all of them
     uint64_t* scratch;       // table-shaped global scratch for sketches with more qualifying keys (nullable)
     uint64_t* out_hashes;    // [n_groups][s]
     uint32_t* out_counts;    // [n_groups][s] (nullable)
@@ -32,6 +34,8 @@ int configure_sketch_select(size_t max_smem_bytes);
 void launch_sketch_topcount(uint32_t n_list, cudaStream_t st, const uint32_t* d_groups, uint32_t sketch_size, uint32_t min_cov,
                             const uint64_t* tr_off, const uint32_t* tr_cap, const uint64_t* tr_pos, uint32_t* out_counts);
 struct SketchArgs;
+// the trace pass from the survivor log: every logged (hash, position) of the listed sketches goes through sketch_emit's trace branch
+void launch_sketch_trace_log(uint64_t n_log, cudaStream_t st, const SketchArgs* d_args);
 void launch_sketch_generic(cudaStream_t st, const SketchArgs* d_args, const uint8_t* d_alphabet, int K, uint64_t range_lo,
                            uint64_t range_hi, int mode, unsigned long long* out_kmers);
 void launch_fp_hash(uint64_t n_lines, cudaStream_t st, const uint64_t* tokens, const uint64_t* line_off, uint32_t seed, int use64, uint64_t* out);

@@ -846,15 +846,36 @@ void Sketch::initFromReads(const vector<string>& files, const Parameters& parame
     // A read set becomes ONE sketch and can be far larger than a staging buffer: records are streamed to the
     // GPU in pinned pieces (fpm_sketch_stream_*), accumulate in HBM and are sketched once at the end.
     struct StreamSink : SeqSink {
+        // two pinned staging buffers filled in turn: while one crosses PCIe (fpm_sketch_stream_append_async) the reader fills the other
+        uint8_t* stages[2] = {nullptr, nullptr};
+        uint64_t tickets[2] = {0, 0};
+        bool inFlight[2] = {false, false};
+        int cur = 0;
         uint8_t* stage = nullptr;
         uint64_t used = 0;
-        const uint64_t kStage = 64ull << 20;
+        const uint64_t kStage = 32ull << 20;
         StreamSink() { gpuCheck(fpm_sketch_stream_begin(gpuContext())); }
-        ~StreamSink() { if (stage) fpm_host_free(stage); }
-        void push() { if (used) gpuCheck(fpm_sketch_stream_append(gpuContext(), stage, used)); used = 0; }
+        ~StreamSink()
+        {
+            for (int i = 0; i < 2; i++) {
+                if (inFlight[i]) fpm_sketch_stream_wait(gpuContext(), tickets[i]);
+                if (stages[i]) fpm_host_free(stages[i]);
+            }
+        }
+        void push()
+        {
+            if (!used) return;
+            gpuCheck(fpm_sketch_stream_append_async(gpuContext(), stage, used, &tickets[cur]));
+            inFlight[cur] = true;
+            used = 0;
+            cur ^= 1;                                                       // go on in the other buffer, once its last copy is through
+            if (inFlight[cur]) { gpuCheck(fpm_sketch_stream_wait(gpuContext(), tickets[cur])); inFlight[cur] = false; }
+            if (!stages[cur]) { void* p = nullptr; gpuCheck(fpm_host_alloc(kStage, &p)); stages[cur] = (uint8_t*)p; }
+            stage = stages[cur];
+        }
         void addRecord(const char* s, uint64_t l) override
         {
-            if (!stage) { void* p = nullptr; gpuCheck(fpm_host_alloc(kStage, &p)); stage = (uint8_t*)p; }   // only the host-reader route needs it
+            if (!stage) { void* p = nullptr; gpuCheck(fpm_host_alloc(kStage, &p)); stages[cur] = stage = (uint8_t*)p; }   // only the host-reader route needs it
             uint64_t done = 0;                                // records longer than the stage go through in pieces
             while (done < l) {
                 if (used == kStage) push();

@@ -87,6 +87,8 @@ lib.fpm_sketch_batch_dev.argtypes = [_VP, C.POINTER(SketchParams), _VP, C.c_uint
 lib.fpm_sketch_stream_begin.argtypes = [_VP]
 lib.fpm_sketch_stream_append.argtypes = [_VP, _VP, C.c_uint64]
 lib.fpm_sketch_stream_end_group.argtypes = [_VP]
+lib.fpm_sketch_stream_append_async.argtypes = [_VP, _VP, C.c_uint64, u64p]
+lib.fpm_sketch_stream_wait.argtypes = [_VP, C.c_uint64]
 lib.fpm_sketch_stream_finish.argtypes = [_VP, C.POINTER(SketchParams), _VP, _VP, _VP, _VP]
 lib.fpm_kmer_hashes.argtypes = [_VP, C.POINTER(SketchParams), _VP, C.c_uint64, _VP, u64p]
 lib.fpm_fp_hash_batch.argtypes = [_VP, _VP, _VP, C.c_uint64, C.c_uint32, C.c_int, _VP]
@@ -188,7 +190,7 @@ EXPORTED = ["fpm_abi_version", "fpm_device_count", "fpm_ctx_create", "fpm_ctx_de
             "fpm_shard_range", "fpm_dist_grid_shape", "fpm_dist_block", "fpm_comm_get_unique_id", "fpm_comm_init_rank", "fpm_comm_adopt",
             "fpm_comm_destroy", "fpm_comm_rank", "fpm_comm_size", "fpm_dist_sharded_dev", "fpm_dist_hits_sharded_dev",
             "fpm_multi_create", "fpm_multi_destroy", "fpm_multi_size", "fpm_multi_ctx", "fpm_dist_tile_multi", "fpm_dist_hits_multi",
-            "fpm_sketch_batch_multi", "fpm_sketch_reads_sharded_dev", "fpm_dist_set_reference"]
+            "fpm_sketch_batch_multi", "fpm_sketch_reads_sharded_dev", "fpm_dist_set_reference", "fpm_sketch_stream_append_async", "fpm_sketch_stream_wait"]
 
 
 def _check(rc):
@@ -366,16 +368,32 @@ class Context:
             out.append(d)
         return out
 
-    def sketch_stream(self, groups, piece=1 << 16, **kw):
-        """Like sketch_records but through the streaming entry points, in pieces of `piece` bytes."""
+    def sketch_stream(self, groups, piece=1 << 16, double_buffered=False, **kw):
+        """Like sketch_records but through the streaming entry points, in pieces of `piece` bytes.  double_buffered: the pieces go
+        through two pinned staging buffers with fpm_sketch_stream_append_async / _wait, as the CLI's reader does."""
         params = make_sketch_params(**kw)
         _check(lib.fpm_sketch_stream_begin(self._h))
+        stages = [PinnedBuffer(piece), PinnedBuffer(piece)] if double_buffered else None
+        tickets, cur = [None, None], 0
         for g in groups:
             buf = np.frombuffer(b"".join(bytes(r) + b"\0" for r in g), dtype=np.uint8).copy() if g else np.zeros(0, dtype=np.uint8)
             for p0 in range(0, buf.size, piece):
                 chunk = np.ascontiguousarray(buf[p0:p0 + piece])
-                _check(lib.fpm_sketch_stream_append(self._h, chunk.ctypes.data, chunk.size))
+                if not double_buffered:
+                    _check(lib.fpm_sketch_stream_append(self._h, chunk.ctypes.data, chunk.size))
+                    continue
+                if tickets[cur] is not None:
+                    _check(lib.fpm_sketch_stream_wait(self._h, tickets[cur]))
+                stages[cur].array[:chunk.size] = chunk
+                t = C.c_uint64(0)
+                _check(lib.fpm_sketch_stream_append_async(self._h, stages[cur].array.ctypes.data, chunk.size, C.byref(t)))
+                tickets[cur] = t.value
+                cur ^= 1
             _check(lib.fpm_sketch_stream_end_group(self._h))
+        if double_buffered:
+            for t in tickets:
+                if t is not None:
+                    _check(lib.fpm_sketch_stream_wait(self._h, t))
         ng, s = len(groups), params.sketch_size
         hashes = np.zeros((ng, s), dtype=np.uint64)
         counts = np.zeros((ng, s), dtype=np.uint32)

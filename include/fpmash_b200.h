@@ -109,6 +109,11 @@ int fpm_sketch_batch_dev(fpm_ctx* ctx, const fpm_sketch_params* p,
  * finish() sketches all groups exactly like fpm_sketch_batch.  append() returns after its copy completed. */
 int fpm_sketch_stream_begin(fpm_ctx* ctx);
 int fpm_sketch_stream_append(fpm_ctx* ctx, const uint8_t* seq, uint64_t bytes);
+/* append() without the wait: returns a ticket at once; the piece must not be modified before fpm_sketch_stream_wait(ticket)
+ * returned.  Tickets complete in order, and waiting is only ever needed for the two most recent ones -- enough for the
+ * intended use, two staging buffers filled in turn while the other one's copy is in flight.                              */
+int fpm_sketch_stream_append_async(fpm_ctx* ctx, const uint8_t* seq, uint64_t bytes, uint64_t* ticket);
+int fpm_sketch_stream_wait(fpm_ctx* ctx, uint64_t ticket);
 int fpm_sketch_stream_end_group(fpm_ctx* ctx);
 int fpm_sketch_stream_finish(fpm_ctx* ctx, const fpm_sketch_params* p, uint64_t* out_hashes, uint32_t* out_counts,
                              uint32_t* out_n, uint64_t* out_kmers);

@@ -176,8 +176,8 @@ def test_streaming_entry_points_match_batch(ctx, oracle):
     genome = random_dna(rng, 30000)
     reads = [mutate(rng, genome[p:p + 150], 0.01) for p in rng.integers(0, len(genome) - 150, size=5000)]
     groups = [reads, [dirty_dna(rng, 200000)], [b"ACGT"], []]
-    for piece in (1000, 1 << 16, 1 << 22):
-        got = ctx.sketch_stream(groups, piece=piece, k=21, s=500, min_cov=2, want_counts=True)
+    for piece, double_buffered in ((1000, False), (1 << 16, False), (1 << 22, False), (4096, True), (1 << 18, True)):
+        got = ctx.sketch_stream(groups, piece=piece, double_buffered=double_buffered, k=21, s=500, min_cov=2, want_counts=True)
         for g, recs in zip(got, groups):
             want = oracle.sketch(recs, k=21, s=500, min_cov=2)
             assert np.array_equal(g["hashes"], want["hashes"]) and np.array_equal(g["counts"], want["counts"])
