@@ -63,7 +63,7 @@ struct fpm_ctx {
     void* comm = nullptr;                        // ncclComm_t
     int comm_rank = 0, comm_world = 0;
     bool comm_owned = false;
-    fpm::DevBuf d_xq, d_xr;                      // this rank's query / reference block after the exchange step
+    fpm::DevBuf d_xq, d_xr, d_xg;                // this rank's query / reference block after the exchange step; all-gather staging
     // resident reference panel (fpm_dist_set_reference): its device copy and its index survive across query chunks
     bool ref_set = false;
     fpm_panel ref_dev = {nullptr, nullptr, nullptr, 0, 0};
@@ -73,6 +73,7 @@ struct fpm_ctx {
         const void* hashes = nullptr;            // identity of the panel it was built for
         uint64_t n_r = 0, rows_r = 0, m = 0, pr = 0;
         const uint64_t* ks = nullptr;            // sorted keys
+        const uint32_t* rank = nullptr;          // dense rank of every sorted element
         uint32_t n_buckets = 0;
     } rix;
     fpm::DevBuf d_p32q, d_uf;                    // packed query tiles; union-find parents / component sizes of the references

@@ -108,6 +108,61 @@ static int block_panel(DevBuf& buf, uint64_t rows, uint64_t stride, fpm_panel* o
     return FPM_OK;
 }
 
+// The exchange step for panels of moderate size: ONE all-gather per panel (NCCL's best-tuned collective: rings over all
+// NVLink channels / NVLS through the switch), then every rank keeps the shards of its block.  Measured at 8 GPUs on
+// configs[2] (2 x 20 000 x 8 KB rows): 0.57 ms for the grouped send/recv below against the all-gather's time in
+// profiles/r02_bench_8gpu_*.json.  A panel used in both roles (all-vs-all) is gathered once.
+static int exchange_blocks_allgather(fpm_ctx* ctx, NcclApi* api, const fpm_panel* d_ref_shard, uint64_t n_ref, const fpm_panel* d_qry_shard, uint64_t n_qry,
+                                     const Block& b, fpm_panel* blk_ref, fpm_panel* blk_qry)
+{
+    const int W = ctx->comm_world, me = ctx->comm_rank;
+    ncclComm_t comm = (ncclComm_t)ctx->comm;
+    cudaStream_t st = ctx->stream;
+    const bool same = d_qry_shard->hashes == d_ref_shard->hashes && d_qry_shard->sizes == d_ref_shard->sizes && d_qry_shard->lengths == d_ref_shard->lengths &&
+                      n_qry == n_ref && d_qry_shard->stride == d_ref_shard->stride;
+    int rc;
+    ctx->time_begin(FPM_KERNEL_DIST_EXCHANGE);
+    for (int role = 0; role < 2; role++) {                                // 0: query panel, 1: reference panel
+        const fpm_panel* mine = role == 0 ? d_qry_shard : d_ref_shard;
+        const uint64_t n = role == 0 ? n_qry : n_ref;
+        const uint64_t my0 = shard_begin(n, me, W), my1 = shard_begin(n, me + 1, W);
+        if (mine->n != my1 - my0) { set_error("rank %d holds %llu %s rows, its shard of %llu rows over %d ranks has %llu", me, (unsigned long long)mine->n,
+                                              role ? "reference" : "query", (unsigned long long)n, W, (unsigned long long)(my1 - my0)); return FPM_ERR_ARG; }
+        const uint64_t max_rows = (n + W - 1) / W, stride = mine->stride;
+        const size_t hb = max_rows * stride * 8, lb = max_rows * 8, sb = max_rows * 4;
+        if (!(role == 1 && same)) {
+            if ((rc = ctx->d_xg.ensure((size_t)W * (hb + lb + sb) + 256))) return rc;
+            unsigned char* g = ctx->d_xg.as<unsigned char>();
+            unsigned char* gh = g; unsigned char* gl = g + (size_t)W * hb; unsigned char* gs = gl + (size_t)W * lb;
+            if (my1 > my0) {
+                FPM_CUDA(cudaMemcpyAsync(gh + (size_t)me * hb, mine->hashes, (my1 - my0) * stride * 8, cudaMemcpyDeviceToDevice, st));
+                FPM_CUDA(cudaMemcpyAsync(gl + (size_t)me * lb, mine->lengths, (my1 - my0) * 8, cudaMemcpyDeviceToDevice, st));
+                FPM_CUDA(cudaMemcpyAsync(gs + (size_t)me * sb, mine->sizes, (my1 - my0) * 4, cudaMemcpyDeviceToDevice, st));
+            }
+            if (hb) FPM_NCCL(api, api->AllGather(gh + (size_t)me * hb, gh, hb, ncclUint8, comm, st));
+            if (lb) FPM_NCCL(api, api->AllGather(gl + (size_t)me * lb, gl, lb, ncclUint8, comm, st));
+            if (sb) FPM_NCCL(api, api->AllGather(gs + (size_t)me * sb, gs, sb, ncclUint8, comm, st));
+        }
+        unsigned char* g = ctx->d_xg.as<unsigned char>();
+        unsigned char* gh = g; unsigned char* gl = g + (size_t)W * hb; unsigned char* gs = gl + (size_t)W * lb;
+        // keep the shards of this rank's block
+        for (int keep = (role == 1 && same) ? 1 : role; keep <= ((role == 0 && same) ? 0 : role); keep++) {
+            const fpm_panel* blk = keep == 0 ? blk_qry : blk_ref;
+            const int first = keep == 0 ? b.qi * b.rp : b.rj * b.qp, cnt = keep == 0 ? b.rp : b.qp;
+            const uint64_t blk0 = keep == 0 ? b.q0 : b.r0;
+            for (int sh = first; sh < first + cnt; sh++) {
+                const uint64_t s0 = shard_begin(n, sh, W), s1 = shard_begin(n, sh + 1, W);
+                if (s1 == s0) continue;
+                FPM_CUDA(cudaMemcpyAsync((void*)(blk->hashes + (s0 - blk0) * stride), gh + (size_t)sh * hb, (s1 - s0) * stride * 8, cudaMemcpyDeviceToDevice, st));
+                FPM_CUDA(cudaMemcpyAsync((void*)(blk->lengths + (s0 - blk0)), gl + (size_t)sh * lb, (s1 - s0) * 8, cudaMemcpyDeviceToDevice, st));
+                FPM_CUDA(cudaMemcpyAsync((void*)(blk->sizes + (s0 - blk0)), gs + (size_t)sh * sb, (s1 - s0) * 4, cudaMemcpyDeviceToDevice, st));
+            }
+        }
+    }
+    ctx->time_end();
+    return FPM_OK;
+}
+
 // The exchange step: every rank's row shard of a panel goes to the ranks whose block holds it.
 static int exchange_blocks(fpm_ctx* ctx, const fpm_panel* d_ref_shard, uint64_t n_ref, const fpm_panel* d_qry_shard, uint64_t n_qry, const Block& b,
                            fpm_panel* blk_ref, fpm_panel* blk_qry)
@@ -120,6 +175,13 @@ static int exchange_blocks(fpm_ctx* ctx, const fpm_panel* d_ref_shard, uint64_t 
     int rc;
     if ((rc = block_panel(ctx->d_xq, b.q1 - b.q0, d_qry_shard->stride, blk_qry))) return rc;
     if ((rc = block_panel(ctx->d_xr, b.r1 - b.r0, d_ref_shard->stride, blk_ref))) return rc;
+    // panels that fit a few GB whole: all-gather, keep the block; larger ones (the 8 GB query panel of configs[4]): only the
+    // shards of the block travel, by grouped send / receive
+    const uint64_t kAllGatherBytes = 4ull << 30;
+    const char* xenv = getenv("FPMASH_EXCHANGE");                            // tests: "p2p" / "allgather" pin the method
+    const bool small = n_qry * d_qry_shard->stride * 8 <= kAllGatherBytes && n_ref * d_ref_shard->stride * 8 <= kAllGatherBytes;
+    if ((small && !(xenv && xenv[0] == 'p')) || (xenv && xenv[0] == 'a'))
+        return exchange_blocks_allgather(ctx, api, d_ref_shard, n_ref, d_qry_shard, n_qry, b, blk_ref, blk_qry);
 
     struct Msg { const void* src; void* dst; size_t bytes; };
     auto three = [](const fpm_panel* from, uint64_t from_row, const fpm_panel* to, uint64_t to_row, uint64_t rows, Msg* m) {

@@ -196,14 +196,18 @@ __device__ __forceinline__ void uf_union(uint32_t* __restrict__ parent, uint32_t
     }
 }
 
-// nodes: references 0..n_r-1, queries n_r..n_r+n_q-1.  References holding the same hash are neighbours in the sorted array.
-__global__ void __launch_bounds__(256) dist_uf_union_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ post, uint64_t m, uint32_t* __restrict__ parent)
+// nodes: the references.  References holding the same hash are neighbours in the sorted array, in ascending sketch order (the
+// radix sort is stable and the keys were generated sketch by sketch): every member of a posting list is joined with the
+// list's FIRST member, its smallest.  (Joining neighbours instead builds chains that the hooks then have to walk: a few
+// hundred dependent L2 round trips, 0.5 ms whatever the panel size.)
+__global__ void __launch_bounds__(256) dist_uf_union_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ post, const uint32_t* __restrict__ rank,
+                                                            const uint32_t* __restrict__ run_start, uint64_t m, uint32_t* __restrict__ parent)
 {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x + 1;
     if (i >= m) return;
     const uint64_t k = keys[i];
     if (k == ~0ULL || keys[i - 1] != k) return;
-    uf_union(parent, post[i], post[i - 1]);
+    uf_union(parent, post[i], post[run_start[rank[i]]]);
 }
 
 // parent[x] = root for every reference; ref_count[root] = references in the component.  The find here must not compress
@@ -585,6 +589,7 @@ int dist_rank_panels(fpm_ctx* ctx, const fpm_panel* d_ref, const fpm_panel* d_qr
         ctx->launches += 1 + (m ? 1 : 0);
         FPM_CUDA(cudaGetLastError());
         rix.valid = true; rix.hashes = d_ref->hashes; rix.n_r = d_ref->n; rix.rows_r = rows_r; rix.m = m; rix.pr = pr; rix.ks = ks; rix.n_buckets = n_buckets;
+        rix.rank = m ? (const uint32_t*)kb.Alternate() : nullptr;
     }
     unsigned char* pb = ctx->d_post.as<unsigned char>();
     uint32_t* post = (uint32_t*)pb; uint32_t* run_start = (uint32_t*)(pb + a4); uint64_t* dk = (uint64_t*)(pb + 2 * a4);
@@ -630,7 +635,7 @@ int dist_rank_panels(fpm_ctx* ctx, const fpm_panel* d_ref, const fpm_panel* d_qr
             const bool saturate = postings > 4e8 || ctx->force_dist_saturate;
             if (saturate && !rix.uf_valid) {
                 dist_uf_init_kernel<<<(nodes + 255) / 256, 256, 0, st>>>(parent, ref_count, nodes);
-                dist_uf_union_kernel<<<(uint32_t)((m + 255) / 256), 256, 0, st>>>(ks, post, m, parent);
+                dist_uf_union_kernel<<<(uint32_t)((m + 255) / 256), 256, 0, st>>>(ks, post, rix.rank, run_start, m, parent);
                 dist_uf_flatten_kernel<<<(nodes + 255) / 256, 256, 0, st>>>(parent, ref_count, nodes);
                 ctx->launches += 3;
                 rix.uf_valid = true;

@@ -86,8 +86,11 @@ dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%(port)d", rank=ran
 ctx = fpm.Context(rank)
 ctx.set_stream(torch.cuda.current_stream().cuda_stream)
 sh.init_comm(ctx)
-for case, (n_r, n_q, s, mode) in enumerate([(1500, 1500, 200, {}), (333, 2047, 96, {}), (1500, 1500, 200, {"no_prune": True}), (5, 3, 50, {})]):
-    rng = np.random.default_rng(100 + case)                  # same panels on every rank; each keeps only its row shards
+for case, (n_r, n_q, s, mode) in enumerate([(1500, 1500, 200, {}), (333, 2047, 96, {}), (1500, 1500, 200, {"no_prune": True}), (5, 3, 50, {}),
+                                            (1500, 1500, 200, {"p2p": 1}), (333, 2047, 96, {"p2p": 1})]):
+    # the exchange step: all-gather + keep the block (default for panels of this size) or grouped send/receive of just the block's shards
+    os.environ["FPMASH_EXCHANGE"] = "p2p" if mode.pop("p2p", 0) else "allgather"
+    rng = np.random.default_rng(100 + case %% 4)             # same panels on every rank; each keeps only its row shards
     rh, rs = sorted_sketch_panel(rng, n_r, s, n_clusters=8)
     qh, qs = sorted_sketch_panel(rng, n_q, s, n_clusters=8)
     rs[n_r - 1] = 0; qs[0] = 0
