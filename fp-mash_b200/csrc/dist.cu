@@ -148,6 +148,23 @@ __global__ void __launch_bounds__(256) dist_collect_kernel(const fpm_pair* __res
     }
 }
 
+// The record of a pair whose sketches share no hash, without going through finish_pair: common = 0, denom = min(s, |A| + |B|)
+// (CommandDistance.cpp:376-400 with no equal elements); distance 1, or 0 when both sketches are empty (common == denom);
+// pValue(0, ...) = 1 (CommandDistance.cpp:435); the -d / -v tests of :416-428.  Needs no lengths and no logarithm.
+__device__ __forceinline__ fpm_pair unshared_record(const DistArgs& a, uint32_t size_qry, uint32_t size_ref)
+{
+    const uint64_t un = (uint64_t)size_qry + size_ref;
+    fpm_pair o;
+    o.numer = 0;
+    o.denom = (uint32_t)(un < a.s ? un : a.s);
+    o.distance = o.denom == 0 ? 0. : 1.;
+    bool pass = !(a.max_distance >= 0 && o.distance > a.max_distance);
+    o.pvalue = pass ? 1. : 0.;
+    if (pass && a.max_pvalue >= 0 && 1. > a.max_pvalue) pass = false;
+    if (pass) o.denom |= FPM_PAIR_PASS;
+    return o;
+}
+
 // Grouped panels scatter the tile kernel's 24-byte records over the matrix (partial sectors, written at different times),
 // and 19 of 20 records of a pruned all-vs-all are the closed-form ones of pairs without a shared hash.  So those are
 // written first, for ALL pairs, as one coalesced stream in the matrix's own order; the tile kernel then only overwrites
@@ -172,8 +189,7 @@ __global__ void __launch_bounds__(256) dist_fill_unshared_kernel(DistArgs a, uin
             if (n_ref >= 512) { r -= n_ref; q++; }                        // a CTA's 512 pairs span at most two rows
             else { q = pp / n_ref; r = pp - q * n_ref; }
         }
-        const uint64_t un = (uint64_t)size_qry[q] + size_ref[r];
-        finish_pair(a, 0, un < a.s ? un : a.s, len_ref[r], len_qry[q], &rec[h]);
+        rec[h] = unshared_record(a, size_qry[q], size_ref[r]);
     }
     if (p + 1 < total) {
         const uint4* src = reinterpret_cast<const uint4*>(rec);
