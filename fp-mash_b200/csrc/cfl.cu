@@ -1,11 +1,13 @@
 // cfl.cu -- lyn2vec's "basic" fingerprints on the GPU (the producer of `-fp` inputs):
-// --type_factorization CFL, ICFL and CFL_ICFL-<C>.
+// --type_factorization CFL, ICFL, CFL_ICFL-<C> and their *_COMB forms (CFL_COMB, ICFL_COMB, CFL_ICFL_COMB-<C>).
 //
 // Replaces, for --type basic --shift shift (the README recipe, README.md:34-52, uses CFL):
 //   shift_string      (lyn2vec/fingerprint_utils.py:95-110)  every circular window of `window` (=100) characters
 //   CFL               (lyn2vec/factorizations.py:102-126)    Duval's Lyndon factorisation of each window
 //   ICFL_recursive    (factorizations.py:143-248)            the inverse Lyndon factorisation
 //   CFL_icfl          (factorizations.py:265-300)            CFL with long factors sub-factorised by ICFL
+//   d_duval_          (lyn2vec/factorizations_comb.py:213-245) the *_COMB forms: the factorisation of the window refined by the
+//                                                            (mirrored) factorisation of its reverse complement
 //   the line writer   (fingerprint_utils.py:443-476)         one row of factor LENGTHS per window
 // and fuses getHashFingerPrint (hash.cpp:45-73) over each row, so a FASTA record can go straight to the
 // `-fp` sketch (one 32-bit hash per window) without the text file -- which can still be written from
@@ -39,6 +41,22 @@ struct RowSink {
     }
 };
 
+// *_COMB: the factor boundaries of a word as a bit set (bit p = a factor ends after p characters), either as emitted or
+// mirrored (the factorisation of the reverse complement, read backwards: a boundary after c characters of the reverse
+// complement is a boundary after len - c characters of the word).
+struct CutSink {
+    uint32_t bits[CFL_MAX_WINDOW / 32 + 1];
+    uint32_t pos, len;
+    bool mirror;
+    __device__ __forceinline__ void mark(uint32_t p) { bits[p >> 5] |= 1u << (p & 31); }
+    __device__ __forceinline__ void emit(uint32_t flen)
+    {
+        if (mirror) mark(len - pos);
+        pos += flen;
+        if (!mirror) mark(pos);
+    }
+};
+
 // ICFL, the inverse Lyndon factorisation (lyn2vec/factorizations.py:143-248, ICFL_recursive), without recursion.
 // The reference recurses on a suffix: find_pre (:172-189) scans the longest prefix x[0..j) on which
 // x[j'] <= x[i'] keeps holding (a non-increasing "anti-Lyndon" run) up to the first character x[j] that breaks
@@ -48,7 +66,8 @@ struct RowSink {
 // longer than `last`, else it is glued to it.  Here: a forward pass records (|p|, last) per level, a backward
 // pass decides the cuts, a second forward pass emits the lengths in order.
 // scratch: plen/aux/f hold n bytes each (n <= 256, so every value fits a byte: |p| <= j <= 255).
-__device__ void icfl_lengths(const uint8_t* w, int n, uint8_t* plen, uint8_t* aux, uint8_t* f, RowSink& sink)
+template <typename Sink>
+__device__ void icfl_lengths(const uint8_t* w, int n, uint8_t* plen, uint8_t* aux, uint8_t* f, Sink& sink)
 {
     int pos = 0, levels = 0, tail_len = 0;
     for (;;) {
@@ -91,6 +110,30 @@ __device__ void icfl_lengths(const uint8_t* w, int n, uint8_t* plen, uint8_t* au
     sink.emit(acc + tail_len);
 }
 
+// One word through CFL (Duval, factorizations.py:102-126), ICFL or CFL_ICFL; factor lengths go to `sink` in order.
+template <typename Sink>
+__device__ void factorise(const uint8_t* word, uint32_t len, int mode, uint32_t sub_len, uint8_t* s_plen, uint8_t* s_aux, uint8_t* s_f, Sink& sink)
+{
+    if (mode == FPM_FACT_ICFL) {
+        icfl_lengths(word, (int)len, s_plen, s_aux, s_f, sink);
+        return;
+    }
+    uint32_t i = 0;
+    while (i < len) {
+        uint32_t j = i + 1, k = i;
+        while (j < len && word[k] <= word[j]) {
+            k = word[k] < word[j] ? i : k + 1;
+            j++;
+        }
+        const uint32_t flen = j - k;
+        while (i <= k) {
+            if (mode == FPM_FACT_CFL_ICFL && flen > sub_len) icfl_lengths(word + i, (int)flen, s_plen, s_aux, s_f, sink);
+            else sink.emit(flen);
+            i += flen;
+        }
+    }
+}
+
 // mode: FPM_FACT_CFL, FPM_FACT_ICFL, FPM_FACT_CFL_ICFL (CFL factors longer than `sub_len` are sub-factorised with
 // ICFL, CFL_icfl, factorizations.py:265-300; the "<<" ">>" markers are dropped from the rows, fingerprint_utils.py:459-463)
 __global__ void __launch_bounds__(128) cfl_window_kernel(const uint8_t* __restrict__ seq, const uint64_t* __restrict__ rec_off,
@@ -114,24 +157,28 @@ __global__ void __launch_bounds__(128) cfl_window_kernel(const uint8_t* __restri
     RowSink sink;
     sink.h1 = seed; sink.h2 = seed; sink.pending = 0; sink.ntok = 0;
     sink.row = out_tok ? out_tok + w * window : nullptr;
-    if (mode == FPM_FACT_ICFL) {
-        icfl_lengths(word, (int)len, s_plen, s_aux, s_f, sink);
+    if (mode < FPM_FACT_CFL_COMB) {
+        factorise(word, len, mode, sub_len, s_plen, s_aux, s_f, sink);
     } else {
-        // Duval (factorizations.py:102-126)
-        uint32_t i = 0;
-        while (i < len) {
-            uint32_t j = i + 1, k = i;
-            while (j < len && word[k] <= word[j]) {
-                k = word[k] < word[j] ? i : k + 1;
-                j++;
-            }
-            const uint32_t flen = j - k;
-            while (i <= k) {
-                if (mode == FPM_FACT_CFL_ICFL && flen > sub_len) icfl_lengths(word + i, (int)flen, s_plen, s_aux, s_f, sink);
-                else sink.emit(flen);
-                i += flen;
-            }
+        // d_duval_ (factorizations_comb.py:213-245): the boundaries of alg(word) together with the mirrored boundaries of
+        // alg(reverse complement).  Its quirk is kept: the reverse complement of CFL_ICFL_COMB-<C> is factorised with the
+        // default threshold 30 whatever C is (:221 calls alg(complement) without k).
+        const int base = mode - FPM_FACT_CFL_COMB;
+        CutSink cuts;
+        for (uint32_t i = 0; i < sizeof cuts.bits / 4; i++) cuts.bits[i] = 0;
+        cuts.len = len;
+        cuts.pos = 0; cuts.mirror = false;
+        factorise(word, len, base, sub_len, s_plen, s_aux, s_f, cuts);
+        uint8_t rc[CFL_MAX_WINDOW];
+        for (uint32_t j = 0; j < len; j++) {                // reverse_complement (:8-10): A<->T, C<->G, N stays (other letters make the reference raise)
+            const uint8_t c = word[len - 1 - j];
+            rc[j] = c == 'A' ? 'T' : c == 'T' ? 'A' : c == 'C' ? 'G' : c == 'G' ? 'C' : c;
         }
+        cuts.pos = 0; cuts.mirror = true;
+        factorise(rc, len, base, 30u, s_plen, s_aux, s_f, cuts);
+        uint32_t last = 0;
+        for (uint32_t p = 1; p <= len; p++)
+            if ((cuts.bits[p >> 5] >> (p & 31)) & 1u) { sink.emit(p - last); last = p; }
     }
     const uint64_t h = sink.finish();
     if (out_hash) out_hash[w] = use64 ? h : (h & 0xffffffffULL);
@@ -147,7 +194,7 @@ extern "C" int fpm_fingerprint_batch(fpm_ctx* ctx, const uint8_t* seq, const uin
                                      uint16_t* out_tokens, uint16_t* out_ntokens, uint64_t* out_window_offsets)
 {
     if (!ctx) { set_error("ctx is NULL"); return FPM_ERR_ARG; }
-    if (factorization != FPM_FACT_CFL && factorization != FPM_FACT_ICFL && factorization != FPM_FACT_CFL_ICFL) {
+    if (factorization < FPM_FACT_CFL || factorization > FPM_FACT_CFL_ICFL_COMB) {
         set_error("unknown factorization %d", factorization);
         return FPM_ERR_ARG;
     }

@@ -944,11 +944,11 @@ CommandFingerprint::CommandFingerprint() : Command()
 {
     name = "fingerprint";
     summary = "Lyndon (CFL / ICFL) fingerprints of sequences, the input of `sketch -fp` (lyn2vec basic mode).";
-    description = "For every record of each FASTA input, factorise every circular window of -w characters (-t CFL: Duval's algorithm; ICFL: inverse Lyndon factorisation; CFL_ICFL-<C>: CFL with factors longer than C sub-factorised by ICFL) and write one line of factor lengths per window, in the format of lyn2vec's fingerprint_<type>.txt. The row id is the second word of the record header followed by _0, as lyn2vec writes it with --rev_comb true.";
+    description = "For every record of each FASTA input, factorise every circular window of -w characters (-t CFL: Duval's algorithm; ICFL: inverse Lyndon factorisation; CFL_ICFL-<C>: CFL with factors longer than C sub-factorised by ICFL; CFL_COMB, ICFL_COMB, CFL_ICFL_COMB-<C>: the same refined by the factorisation of the window's reverse complement) and write one line of factor lengths per window, in the format of lyn2vec's fingerprint_<type>.txt. The row id is the second word of the record header followed by _0, as lyn2vec writes it with --rev_comb true.";
     argumentString = "<fasta> [<fasta>] ...";
     useOption("help");
     addOption("window", Option(Option::Integer, "w", "", "Window length of the circular shifts.", "100", 1, 256));
-    addOption("type", Option(Option::File, "t", "", "Factorisation (lyn2vec --type_factorization): CFL, ICFL or CFL_ICFL-<C> (lyn2vec offers C = 10, 20, 30).", "CFL"));
+    addOption("type", Option(Option::File, "t", "", "Factorisation (lyn2vec --type_factorization): CFL, ICFL, CFL_ICFL-<C>, CFL_COMB, ICFL_COMB or CFL_ICFL_COMB-<C> (lyn2vec offers C = 10, 20, 30).", "CFL"));
     addOption("prefix", Option(Option::File, "o", "Output", "Output file (default: fingerprint_<type>.txt).", ""));
 }
 
@@ -967,8 +967,13 @@ int CommandFingerprint::run() const
     else if (type.compare(0, 9, "CFL_ICFL-") == 0 && type.size() > 9 && type.find_first_not_of("0123456789", 9) == string::npos) {
         factorization = FPM_FACT_CFL_ICFL;
         subLen = (uint32_t)atoi(type.c_str() + 9);
+    } else if (type == "CFL_COMB") factorization = FPM_FACT_CFL_COMB;
+    else if (type == "ICFL_COMB") factorization = FPM_FACT_ICFL_COMB;
+    else if (type.compare(0, 14, "CFL_ICFL_COMB-") == 0 && type.size() > 14 && type.find_first_not_of("0123456789", 14) == string::npos) {
+        factorization = FPM_FACT_CFL_ICFL_COMB;
+        subLen = (uint32_t)atoi(type.c_str() + 14);
     } else {
-        cerr << "ERROR: unknown factorisation \"" << type << "\" (CFL, ICFL, CFL_ICFL-<C>)." << endl;
+        cerr << "ERROR: unknown factorisation \"" << type << "\" (CFL, ICFL, CFL_ICFL-<C>, CFL_COMB, ICFL_COMB, CFL_ICFL_COMB-<C>)." << endl;
         return 1;
     }
     vector<string> ids;

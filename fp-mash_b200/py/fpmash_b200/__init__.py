@@ -94,7 +94,7 @@ lib.fpm_kmer_hashes.argtypes = [_VP, C.POINTER(SketchParams), _VP, C.c_uint64, _
 lib.fpm_fp_hash_batch.argtypes = [_VP, _VP, _VP, C.c_uint64, C.c_uint32, C.c_int, _VP]
 lib.fpm_cfl_fingerprint_batch.argtypes = [_VP, _VP, _VP, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, _VP, _VP, _VP, _VP]
 lib.fpm_fingerprint_batch.argtypes = [_VP, _VP, _VP, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, C.c_int, _VP, _VP, _VP, _VP]
-FACT_CFL, FACT_ICFL, FACT_CFL_ICFL = 0, 1, 2
+FACT_CFL, FACT_ICFL, FACT_CFL_ICFL, FACT_CFL_COMB, FACT_ICFL_COMB, FACT_CFL_ICFL_COMB = 0, 1, 2, 3, 4, 5
 lib.fpm_dist_tile.argtypes = [_VP, C.POINTER(DistParams), C.POINTER(Panel), C.POINTER(Panel), _VP]
 lib.fpm_fp_positional_tile.argtypes = [_VP, C.POINTER(DistParams), C.POINTER(Panel), C.POINTER(Panel), _VP]
 lib.fpm_dist_tile_dev.argtypes = [_VP, C.POINTER(DistParams), C.POINTER(Panel), C.POINTER(Panel), _VP, _VP]
@@ -457,7 +457,7 @@ class Context:
         return out
 
     def fingerprint_batch(self, records, window=100, factorization="CFL", seed=42, use64=False):
-        """lyn2vec basic/shift on the GPU: records = list of bytes; factorization = "CFL", "ICFL" or "CFL_ICFL-<C>"
+        """lyn2vec basic/shift on the GPU: records = list of bytes; factorization = "CFL", "ICFL", "CFL_ICFL-<C>", "CFL_COMB", "ICFL_COMB" or "CFL_ICFL_COMB-<C>"
         (lyn2vec's --type_factorization).  Returns (rows, hashes, window_offsets): rows[w] = list of factor lengths
         of window w, hashes[w] = getHashFingerPrint(rows[w])."""
         if factorization == "CFL":
@@ -466,6 +466,12 @@ class Context:
             mode, sub = FACT_ICFL, 0
         elif factorization.startswith("CFL_ICFL-"):
             mode, sub = FACT_CFL_ICFL, int(factorization.split("-")[1])
+        elif factorization == "CFL_COMB":
+            mode, sub = FACT_CFL_COMB, 0
+        elif factorization == "ICFL_COMB":
+            mode, sub = FACT_ICFL_COMB, 0
+        elif factorization.startswith("CFL_ICFL_COMB-"):
+            mode, sub = FACT_CFL_ICFL_COMB, int(factorization.split("-")[1])
         else:
             raise ValueError("unknown factorization " + factorization)
         off = np.zeros(len(records) + 1, dtype=np.uint64)

@@ -151,6 +151,11 @@ int fpm_cfl_fingerprint_batch(fpm_ctx* ctx, const uint8_t* seq, const uint64_t* 
 #define FPM_FACT_CFL 0
 #define FPM_FACT_ICFL 1
 #define FPM_FACT_CFL_ICFL 2
+/* lyn2vec's *_COMB forms (d_cfl / d_icfl / d_cfl_icfl -> d_duval_, lyn2vec/factorizations_comb.py:178-245): the factor
+ * boundaries of the window together with the mirrored boundaries of the factorisation of its reverse complement.        */
+#define FPM_FACT_CFL_COMB 3
+#define FPM_FACT_ICFL_COMB 4
+#define FPM_FACT_CFL_ICFL_COMB 5
 int fpm_fingerprint_batch(fpm_ctx* ctx, const uint8_t* seq, const uint64_t* rec_offsets, uint32_t n_records, uint32_t window,
                           int factorization, uint32_t sub_len, uint32_t seed, int use64, uint64_t* out_hashes,
                           uint16_t* out_tokens, uint16_t* out_ntokens, uint64_t* out_window_offsets);

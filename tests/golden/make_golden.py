@@ -6,8 +6,8 @@
    large text inputs are gzipped with mtime 0 so the bytes are reproducible;
 2. generates known-answer vectors by calling the reference's own hash.cpp / MinHashHeap.cpp
    (oracle/_ref/libmashref.so) on seeded inputs -> ref_vectors.json;
-3. runs the reference's own lyn2vec (README.md:34-52 recipe) on DNA1.fasta with --type_factorization ICFL and
-   CFL_ICFL-30 -> DNA1-ICFL.txt.gz, DNA1-CFL_ICFL-30.txt.gz (the CFL run reproduces the shipped DNA1-CFL.txt
+3. runs the reference's own lyn2vec (README.md:34-52 recipe) on DNA1.fasta with --type_factorization ICFL,
+   CFL_ICFL-30, CFL_COMB, ICFL_COMB and CFL_ICFL_COMB-10 -> DNA1-ICFL.txt.gz, DNA1-CFL_ICFL-30.txt.gz, DNA1-CFL_COMB.txt.gz ... (the CFL run reproduces the shipped DNA1-CFL.txt
    byte for byte, which is checked here).
 """
 import gzip
@@ -63,7 +63,7 @@ def main():
     # lyn2vec, run as the README runs it (it writes fingerprint_<type>.txt next to the FASTA file)
     with tempfile.TemporaryDirectory() as d:
         shutil.copyfile(os.path.join(REF, "training/Umberto/CFL/DNA1.fasta"), os.path.join(d, "DNA1.fasta"))
-        for fact in ("CFL", "ICFL", "CFL_ICFL-30"):
+        for fact in ("CFL", "ICFL", "CFL_ICFL-30", "CFL_COMB", "ICFL_COMB", "CFL_ICFL_COMB-10"):
             subprocess.run([sys.executable, "lyn2vec.py", "--type", "basic", "--path", d + "/", "--fasta", "DNA1.fasta", "--type_factorization", fact,
                             "--rev_comb", "true", "-n", "4"], cwd=os.path.join(REF, "lyn2vec"), check=True, stdout=subprocess.DEVNULL)
             data = open(os.path.join(d, "fingerprint_%s.txt" % fact), "rb").read()

@@ -112,7 +112,7 @@ def cfl_icfl(word, c):
     return out
 
 
-@pytest.mark.parametrize("fact", ["ICFL", "CFL_ICFL-30"])
+@pytest.mark.parametrize("fact", ["ICFL", "CFL_ICFL-30", "CFL_COMB", "ICFL_COMB", "CFL_ICFL_COMB-10"])
 def test_fingerprint_cli_icfl_reproduces_lyn2vec_file(tmp_path, fact):
     shutil.copy(os.path.join(GOLDEN, "DNA1.fasta"), tmp_path / "DNA1.fasta")
     r = subprocess.run([MASH, "fingerprint", "-t", fact, "DNA1.fasta"], cwd=tmp_path, capture_output=True, text=True)
@@ -141,3 +141,45 @@ def test_icfl_rows_and_fused_hashes(ctx, oracle):
         assert w == int(woff[-1]) == len(rows)
     rows, _, _ = ctx.fingerprint_batch(recs[-1:], window=256, factorization="ICFL")
     assert rows[3] == icfl(shifts(recs[-1], 256)[3])
+
+
+def comb(word, alg, alg_rc):
+    """d_duval_ (lyn2vec/factorizations_comb.py:213-245): the boundaries of alg(word) and the mirrored boundaries of
+    alg_rc(reverse complement of word)."""
+    cuts, pos = set(), 0
+    for f in alg(word):
+        pos += f
+        cuts.add(pos)
+    rc = bytes(word[::-1]).translate(bytes.maketrans(b"ACGT", b"TGCA"))
+    pos = 0
+    for f in alg_rc(rc):
+        cuts.add(len(word) - pos)
+        pos += f
+    out, last = [], 0
+    for p in sorted(cuts):
+        out.append(p - last)
+        last = p
+    return out
+
+
+def test_comb_rows_and_fused_hashes(ctx, oracle):
+    """CFL_COMB / ICFL_COMB / CFL_ICFL_COMB-<C>, windows with N, short records; the reverse complement of CFL_ICFL_COMB-<C>
+    is factorised with threshold 30 whatever C is, as the reference does (factorizations_comb.py:221)."""
+    rng = np.random.default_rng(16)
+    alpha = np.frombuffer(b"ACGT", dtype=np.uint8)
+    alpha_n = np.frombuffer(b"ACGTN", dtype=np.uint8)
+    recs = [alpha[rng.integers(0, 4, size=n)].tobytes() for n in (350, 100, 99, 1, 2, 7, 180)]
+    recs += [alpha_n[rng.integers(0, 5, size=220)].tobytes(), b"A" * 150, b"TGCA" * 40, b"T" * 60 + b"A" * 60, b"ACGT" * 30 + b"T"]
+    recs.append(bytes(rng.integers(65, 67, size=256, dtype=np.uint8)).replace(b"B", b"C"))    # two letters: long borders
+    cases = (("CFL_COMB", duval, duval), ("ICFL_COMB", icfl, icfl), ("CFL_ICFL_COMB-10", lambda w: cfl_icfl(w, 10), lambda w: cfl_icfl(w, 30)),
+             ("CFL_ICFL_COMB-30", lambda w: cfl_icfl(w, 30), lambda w: cfl_icfl(w, 30)))
+    for fact, fn, fn_rc in cases:
+        rows, hashes, woff = ctx.fingerprint_batch(recs, window=100, factorization=fact)
+        w = 0
+        for r, rec in enumerate(recs):
+            for word in shifts(rec):
+                assert rows[w] == comb(word, fn, fn_rc), (fact, r, w, word)
+                assert sum(rows[w]) == len(word)
+                assert int(hashes[w]) == oracle.fp_hash(rows[w], 42, False)
+                w += 1
+        assert w == int(woff[-1]) == len(rows)
