@@ -63,7 +63,7 @@ struct fpm_ctx {
     void* comm = nullptr;                        // ncclComm_t
     int comm_rank = 0, comm_world = 0;
     bool comm_owned = false;
-    fpm::DevBuf d_xq, d_xr, d_xg;                // this rank's query / reference block after the exchange step; all-gather staging
+    fpm::DevBuf d_xq, d_xr, d_xg, d_xg2;              // this rank's query / reference block after the exchange step; all-gather staging
     // resident reference panel (fpm_dist_set_reference): its device copy and its index survive across query chunks
     bool ref_set = false;
     fpm_panel ref_dev = {nullptr, nullptr, nullptr, 0, 0};

@@ -130,9 +130,10 @@ static int exchange_blocks_allgather(fpm_ctx* ctx, NcclApi* api, const fpm_panel
                                               role ? "reference" : "query", (unsigned long long)n, W, (unsigned long long)(my1 - my0)); return FPM_ERR_ARG; }
         const uint64_t max_rows = (n + W - 1) / W, stride = mine->stride;
         const size_t hb = max_rows * stride * 8, lb = max_rows * 8, sb = max_rows * 4;
+        DevBuf& gbuf = (role == 1 && !same) ? ctx->d_xg2 : ctx->d_xg;      // (a block may keep pointing into its panel's gather buffer)
         if (!(role == 1 && same)) {
-            if ((rc = ctx->d_xg.ensure((size_t)W * (hb + lb + sb) + 256))) return rc;
-            unsigned char* g = ctx->d_xg.as<unsigned char>();
+            if ((rc = gbuf.ensure((size_t)W * (hb + lb + sb) + 256))) return rc;
+            unsigned char* g = gbuf.as<unsigned char>();
             unsigned char* gh = g; unsigned char* gl = g + (size_t)W * hb; unsigned char* gs = gl + (size_t)W * lb;
             if (my1 > my0) {
                 FPM_CUDA(cudaMemcpyAsync(gh + (size_t)me * hb, mine->hashes, (my1 - my0) * stride * 8, cudaMemcpyDeviceToDevice, st));
@@ -143,13 +144,20 @@ static int exchange_blocks_allgather(fpm_ctx* ctx, NcclApi* api, const fpm_panel
             if (lb) FPM_NCCL(api, api->AllGather(gl + (size_t)me * lb, gl, lb, ncclUint8, comm, st));
             if (sb) FPM_NCCL(api, api->AllGather(gs + (size_t)me * sb, gs, sb, ncclUint8, comm, st));
         }
-        unsigned char* g = ctx->d_xg.as<unsigned char>();
+        unsigned char* g = gbuf.as<unsigned char>();
         unsigned char* gh = g; unsigned char* gl = g + (size_t)W * hb; unsigned char* gs = gl + (size_t)W * lb;
         // keep the shards of this rank's block
         for (int keep = (role == 1 && same) ? 1 : role; keep <= ((role == 0 && same) ? 0 : role); keep++) {
-            const fpm_panel* blk = keep == 0 ? blk_qry : blk_ref;
+            fpm_panel* blk = keep == 0 ? blk_qry : blk_ref;
             const int first = keep == 0 ? b.qi * b.rp : b.rj * b.qp, cnt = keep == 0 ? b.rp : b.qp;
             const uint64_t blk0 = keep == 0 ? b.q0 : b.r0;
+            if (n % W == 0) {
+                // equal shards: consecutive slots of the gather buffer ARE the block, nothing to copy
+                blk->hashes = (const uint64_t*)(gh + (size_t)first * hb);
+                blk->lengths = (const uint64_t*)(gl + (size_t)first * lb);
+                blk->sizes = (const uint32_t*)(gs + (size_t)first * sb);
+                continue;
+            }
             for (int sh = first; sh < first + cnt; sh++) {
                 const uint64_t s0 = shard_begin(n, sh, W), s1 = shard_begin(n, sh + 1, W);
                 if (s1 == s0) continue;

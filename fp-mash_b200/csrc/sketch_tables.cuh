@@ -21,6 +21,9 @@
 #ifndef FPM_T0TAB
 #define FPM_T0TAB 1
 #endif
+#ifndef FPM_T0MASK
+#define FPM_T0MASK 0xf   // which key words (bit c = word c) take the T0 table; the others expand + multiply
+#endif
 #ifndef FPM_LAZYFIN
 #define FPM_LAZYFIN 1
 #endif
@@ -94,7 +97,7 @@ __device__ __forceinline__ uint64_t word_times(uint32_t chi, uint32_t clo, uint3
         asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(a1) : "r"(i1), "r"(tb));
         asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(xh) : "r"(a1), "n"(off_lut + (nb < 8 ? 1024u : 0u)));
     }
-    if (FPM_T0TAB && nb >= 4) {
+    if (FPM_T0TAB && ((FPM_T0MASK >> C) & 1) && nb >= 4) {
         uint32_t a0, lo, hi;
         asm("mad.lo.u32 %0, %1, 8, %2;" : "=r"(a0) : "r"(i0), "r"(tb));
         asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+%3];" : "=r"(lo), "=r"(hi) : "r"(a0), "n"((uint32_t)(MUL == FPM_MC1 ? offsetof(T, t0c1) : offsetof(T, t0c2))));
