@@ -12,7 +12,7 @@ for g in range(ng):
     gen.manual_seed(500 + g)
     seq[g * (L + 1):g * (L + 1) + L] = lut[torch.randint(0, 4, (L,), generator=gen, device=dev, dtype=torch.uint8).long()]
 offs = np.arange(ng + 1, dtype=np.uint64) * np.uint64(L + 1)
-for k, s in ((21, 1000),) + (((32, 1000), (16, 1000)) if "--all" in sys.argv else ()):
+for k, s in ((21, 1000),) + (((32, 1000), (16, 1000)) if "--all" in sys.argv else ()) + (((32, 10000), (21, 10000)) if "--large" in sys.argv else ()):
     p = fpm.make_sketch_params(k=k, s=s)
     oh = torch.zeros((ng, s), dtype=torch.int64, device=dev); on = torch.zeros(ng, dtype=torch.int32, device=dev)
     f = lambda: ctx.sketch_batch_dev(seq.data_ptr(), seq.numel(), offs, p, oh.data_ptr(), None, on.data_ptr())
