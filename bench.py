@@ -40,7 +40,7 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 K = 21
 S = 1000
 W_INT32_OPS = {21: 74, 32: 96, 16: 64}   # int32-op equivalents of Murmur per k-mer
-NCU_SKETCH_TRAFFIC_RATIO = (524.81 + 22.97) / 500.0005   # DRAM bytes per algorithmic byte, ncu --set full capture of sketch_hash_kernel_v2<21,true> (profiles/r02_sketch_hash_v3.txt: 100 x 5 Mbp launch)
+NCU_SKETCH_TRAFFIC_RATIO = (526.58 + 23.66) / 500.0005   # DRAM bytes per algorithmic byte, ncu --set full capture of sketch_hash_kernel_v2<21,true> (profiles/r02_sketch_hash_v4.txt: 100 x 5 Mbp launch)
 NCU_DIST_TRAFFIC_RATIO = (27.22 + 193.05) / (3200 * 3200 * 24 / 1e6 + 2 * 3200 * 1001 * 4 / 1e6)   # same for dist_tile32_kernel (profiles/r01_dist_tile32_v4.txt)
 IMAD_WIDE_RATE = 8.99 / 18.45         # IMAD.WIDE issue rate relative to IMAD, measured (profiles/ubench/int_mix.cu: 8.99 vs 18.45 T/s)
 SMEM_BYTES_PER_CLK_PER_SM = 128        # one 32-lane x 4-byte wavefront per clock (B300_MICROARCH.md / measured LSU pipe limit)
@@ -577,7 +577,7 @@ def main():
                          "peak_source": "measured live: alternating IMAD/LOP3, 16 chains (fpm_measure_int32_peak); SURVEY 8d: the sketch kernel is integer-ALU bound",
                          "peaks": {"alu_lop3": int_peaks[0] / 1e12, "fma_imad": int_peaks[1] / 1e12, "alternating": int_peaks[2] / 1e12},
                          "hbm": {"achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak, "peak_source": hbm_src,
-                                 "note": "1 B per base read once; dram traffic 1.10x (ncu profiles/r02_sketch_hash_v3.txt)"}},
+                                 "note": "1 B per base read once; dram traffic 1.10x (ncu profiles/r02_sketch_hash_v4.txt)"}},
             "kernel_ms": {"sketch_hash": hash_ms_avg, "sketch_select": sel_ms / max(sel_n, 1)},
             "cpu_baseline": cpu,
             "dist": dist_obj,
