@@ -417,3 +417,35 @@ def test_resident_reference_panel_equals_one_call(dctx, fpm):
             dctx.dist_tile(None, (qh[:5], qs[:5], ql[:5]), s, 21, 4.0 ** 21)
     finally:
         dctx.dist_set_reference(None)
+
+
+def test_dist_long_reference_chains_same_in_every_mode(ctx, fpm):
+    """the component pass must never make a query stop marking early.  Long chains of references (reference i shares
+    a few hashes with i+1 only: trees 3000 deep while the union-find forms) plus queries hanging off them at random places;
+    the result with the component bound forced on must equal the result without it, without grouping and without pruning."""
+    rng = np.random.default_rng(4242)
+    s, n_r, n_q = 48, 3000, 700
+    link = np.sort(rng.choice(1 << 44, size=(n_r + 1) * 6, replace=False).astype(np.uint64)).reshape(n_r + 1, 6)
+    priv = rng.integers(1 << 45, 1 << 46, size=(n_r, s - 12)).astype(np.uint64)
+    rh = np.sort(np.concatenate([link[:-1], link[1:], priv], axis=1), axis=1)           # reference i: links i and i+1
+    qh = np.zeros((n_q, s), dtype=np.uint64)
+    at = rng.integers(0, n_r, size=n_q)
+    for q in range(n_q):
+        own = rng.integers(1 << 47, 1 << 48, size=s - 6).astype(np.uint64)
+        qh[q] = np.sort(np.concatenate([link[at[q]], own]))                             # touches references at[q]-1 and at[q]
+    for a in (rh, qh):
+        assert (np.diff(a.astype(np.float64), axis=1) > 0).all()
+    rs = np.full(n_r, s, dtype=np.uint32); qs = np.full(n_q, s, dtype=np.uint32)
+    rl = np.full(n_r, 1_000_000, dtype=np.uint64); ql = np.full(n_q, 1_000_000, dtype=np.uint64)
+    outs = []
+    for mode in ({"saturate": True}, {}, {"no_group": True}, {"no_prune": True}):
+        ctx.set_dist_mode(**mode)
+        try:
+            for _ in range(3 if mode.get("saturate") else 1):                            # the race was rare: repeat
+                got, _ = ctx.dist_tile((rh, rs, rl), (qh, qs, ql), s, 21, 4.0 ** 21, raw=True)
+                outs.append(got.tobytes())
+        finally:
+            ctx.set_dist_mode()
+    assert all(o == outs[0] for o in outs)
+    got = np.frombuffer(outs[0], dtype=fpm.PAIR_DTYPE).reshape(n_q, n_r)
+    assert int((got["numer"] == 6).sum()) >= n_q                                          # every query found its neighbours
