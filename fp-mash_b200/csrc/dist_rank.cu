@@ -122,30 +122,58 @@ __device__ __forceinline__ uint32_t ref_lower_bound(const RefIndex& ix, uint64_t
 
 // Every query element: its code into the packed query tiles; flags |= 1 for a row that is not strictly ascending or holds
 // the reserved value; *total += postings a marking pass would walk for it (references sharing its hash).
+// A CTA owns a tile of 32 sketches x 32 rows.  The hashes come in row-major (one sketch's consecutive rows: 256 contiguous
+// bytes per warp load) and go through shared memory so that a warp then works on ONE row of 32 sketches:
+//   * row r of every sorted sketch is the same quantile of the hash range, so the warp's 32 lookups -- and those of the CTAs
+//     running beside it, the grid walks sketch tiles fastest -- fall into one narrow band of the bucket table and of dk[],
+//     which the L2 holds; with one sketch per warp the lookups were scattered over the whole index (0.8 GB for configs[4]),
+//   * the codes of 16 neighbouring sketches at one row are 64 contiguous bytes of the column-tile layout (a thread per
+//     (sketch, row) in sketch-major order wrote 4 bytes per 32-byte sector).
+// configs[4] (10^9 lookups into 10^8 reference hashes): 48 ms before (profiles/r02_c5_launches.csv).
+constexpr int QC_TILE = 32;
 __global__ void __launch_bounds__(256) dist_qcode_kernel(fpm_panel pn, uint32_t max_size, uint64_t rows, RefIndex ix, const uint32_t* __restrict__ run_start,
                                                          uint32_t* __restrict__ packed, uint32_t* flags, unsigned long long* total)
 {
-    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ uint64_t s_h[QC_TILE][QC_TILE + 1];          // [sketch][row], padded: the transposed reads are conflict free
+    const uint64_t sk0 = (uint64_t)blockIdx.x * QC_TILE, row0 = (uint64_t)blockIdx.y * QC_TILE;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     unsigned long long c = 0;
-    if (idx < pn.n * max_size) {
-        const uint64_t sk = idx / max_size, row = idx % max_size;
-        if (row < pn.sizes[sk]) {
-            const uint64_t v = pn.hashes[sk * pn.stride + row];
-            bool bad = v == ~0ULL;
-            if (row > 0 && pn.hashes[sk * pn.stride + row - 1] >= v) bad = true;
-            if (bad) atomicOr(flags, 1u);
-            const uint32_t D = ix.scal[0], shift = ix.scal[2];
-            const uint64_t maxkey = ((uint64_t)ix.scal[4] << 32) | ix.scal[3];
+    // ---- load: warp w takes sketches 4w .. 4w+3, lane = row --------------------------------------------------------------
+#pragma unroll
+    for (int i = 0; i < QC_TILE / 8; i++) {
+        const int s = wid * (QC_TILE / 8) + i;
+        const uint64_t sk = sk0 + s, row = row0 + lane;
+        const bool in = sk < pn.n && row < pn.sizes[sk];
+        const uint64_t v = in ? pn.hashes[sk * pn.stride + row] : ~0ULL;
+        uint64_t prev = __shfl_up_sync(0xffffffffu, v, 1);      // (a row inside the sketch has its predecessor inside it too)
+        bool bad = false;
+        if (in) {
+            if (lane == 0 && row > 0) prev = pn.hashes[sk * pn.stride + row - 1];
+            bad = v == ~0ULL || (row > 0 && prev >= v);
+        }
+        s_h[s][lane] = v;
+        if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(flags, 1u);
+    }
+    __syncthreads();
+    // ---- look up: warp w takes rows 4w .. 4w+3, lane = sketch ------------------------------------------------------------
+    const uint32_t D = ix.scal[0], shift = ix.scal[2];
+    const uint64_t maxkey = ((uint64_t)ix.scal[4] << 32) | ix.scal[3];
+#pragma unroll
+    for (int i = 0; i < QC_TILE / 8; i++) {
+        const int r = wid * (QC_TILE / 8) + i;
+        const uint64_t sk = sk0 + lane, row = row0 + r;
+        const uint64_t v = s_h[lane][r];
+        if (sk < pn.n && row < max_size && row < pn.sizes[sk]) {
             bool found;
             const uint32_t lb = ref_lower_bound(ix, v, D, shift, maxkey, &found);
             packed[((sk >> 4) * rows + row) * 16 + (sk & 15)] = 2u * lb + (found ? 1u : 0u);
-            if (found) c = run_start[lb + 1] - run_start[lb];
+            if (found) c += run_start[lb + 1] - run_start[lb];
         }
     }
     for (int o = 16; o; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
     // one atomic per CTA: a million same-address atomics (one per warp) cost 0.6 ms
     __shared__ unsigned long long s_part[8];
-    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = c;
+    if (lane == 0) s_part[wid] = c;
     __syncthreads();
     if (threadIdx.x == 0) {
         unsigned long long t = 0;
@@ -603,7 +631,10 @@ int dist_rank_panels(fpm_ctx* ctx, const fpm_panel* d_ref, const fpm_panel* d_qr
     FPM_CUDA(cudaMemsetAsync(*packed_qry, 0xff, pq * 4, st));
     RefIndex ix{dk, cum, scal};
     if (mq) {
-        dist_qcode_kernel<<<(uint32_t)((mq + 255) / 256), 256, 0, st>>>(*d_qry, max_size_qry, rows_q, ix, run_start, *packed_qry, d_flag_q, d_total);
+        // sketch tiles fastest, row tiles slowest: the CTAs in flight at any time work on the same rows (= the same band of the index)
+        const dim3 qgrid((uint32_t)((d_qry->n + QC_TILE - 1) / QC_TILE), (uint32_t)((max_size_qry + QC_TILE - 1) / QC_TILE));
+        if (qgrid.y > 65535) { set_error("sketches of more than %u hashes are not supported", 65535u * QC_TILE); return FPM_ERR_UNSUPPORTED; }
+        dist_qcode_kernel<<<qgrid, 256, 0, st>>>(*d_qry, max_size_qry, rows_q, ix, run_start, *packed_qry, d_flag_q, d_total);
         ctx->launches++;
         FPM_CUDA(cudaGetLastError());
     }
