@@ -76,6 +76,8 @@ struct fpm_ctx {
         const uint32_t* rank = nullptr;          // dense rank of every sorted element
         uint32_t n_buckets = 0;
     } rix;
+    fpm::DevBuf d_codes;                         // query codes, row-major [n_q][code_stride] (dist_rank.cu)
+    uint64_t code_stride = 0;
     fpm::DevBuf d_p32q, d_uf;                    // packed query tiles; union-find parents / component sizes of the references
     bool no_dist_prune = false;                  // tests: merge every pair
     bool no_dist_group = false;                  // tests: prune, but leave the panels in their own order

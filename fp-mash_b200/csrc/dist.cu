@@ -839,7 +839,8 @@ int run_dist(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* d_ref, con
         // grouping related sketches pays when results stay on the device (a grouped query order would break the row-chunked
         // copy-out of the host path) and the panels are large enough to have many tiles
         if (mode == DIST_RANK_OK && marks && !h_out && !ctx->no_dist_group && d_ref->n >= 256 && d_qry->n >= 256)
-            if ((rc = dist_group_panels(ctx, d_qry->n, d_ref->n, rows_q, rows_r, &p32r, &p32q, &marks, &perm_q, &perm_r))) return rc;
+            if ((rc = dist_group_panels(ctx, d_qry->n, d_ref->n, rows_q, rows_r, d_qry->sizes, &p32r, &p32q, &marks, &perm_q, &perm_r))) return rc;
+        if (mode == DIST_RANK_OK && !p32q && (rc = dist_pack_queries(ctx, d_qry->sizes, d_qry->n, rows_q, &p32q))) return rc;   // no grouping: natural order
         if (mode == DIST_RANK_TOO_BIG) {
             if ((rc = ctx->d_ref.ensure(nr16 * 16 * rows_r * 8))) return rc;
             if ((rc = ctx->d_qry.ensure(nq16 * 16 * rows_q * 8))) return rc;

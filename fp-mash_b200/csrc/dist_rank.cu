@@ -127,14 +127,17 @@ __device__ __forceinline__ uint32_t ref_lower_bound(const RefIndex& ix, uint64_t
 //   * row r of every sorted sketch is the same quantile of the hash range, so the warp's 32 lookups -- and those of the CTAs
 //     running beside it, the grid walks sketch tiles fastest -- fall into one narrow band of the bucket table and of dk[],
 //     which the L2 holds; with one sketch per warp the lookups were scattered over the whole index (0.8 GB for configs[4]),
-//   * the codes of 16 neighbouring sketches at one row are 64 contiguous bytes of the column-tile layout (a thread per
-//     (sketch, row) in sketch-major order wrote 4 bytes per 32-byte sector).
+//   * the codes go back through shared memory into a ROW-MAJOR array codes[sketch][row] (128 contiguous bytes per warp store).
+//     The column tiles the tile kernel reads are written later by dist_pack_queries_kernel, in natural or in grouped order:
+//     packing first and regrouping afterwards gathered single columns out of column tiles, 4 useful bytes per 32-byte sector
+//     (10 ms for configs[4]); the marking kernel reads a query's codes contiguously instead of 64 bytes apart.
 // configs[4] (10^9 lookups into 10^8 reference hashes): 48 ms before (profiles/r02_c5_launches.csv).
 constexpr int QC_TILE = 32;
-__global__ void __launch_bounds__(256) dist_qcode_kernel(fpm_panel pn, uint32_t max_size, uint64_t rows, RefIndex ix, const uint32_t* __restrict__ run_start,
-                                                         uint32_t* __restrict__ packed, uint32_t* flags, unsigned long long* total)
+__global__ void __launch_bounds__(256) dist_qcode_kernel(fpm_panel pn, uint32_t max_size, RefIndex ix, const uint32_t* __restrict__ run_start,
+                                                         uint32_t* __restrict__ codes, uint32_t* flags, unsigned long long* total)
 {
     __shared__ uint64_t s_h[QC_TILE][QC_TILE + 1];          // [sketch][row], padded: the transposed reads are conflict free
+    __shared__ uint32_t s_c[QC_TILE][QC_TILE + 1];          // the codes on their way back
     const uint64_t sk0 = (uint64_t)blockIdx.x * QC_TILE, row0 = (uint64_t)blockIdx.y * QC_TILE;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     unsigned long long c = 0;
@@ -163,12 +166,22 @@ __global__ void __launch_bounds__(256) dist_qcode_kernel(fpm_panel pn, uint32_t 
         const int r = wid * (QC_TILE / 8) + i;
         const uint64_t sk = sk0 + lane, row = row0 + r;
         const uint64_t v = s_h[lane][r];
+        uint32_t code = 0xffffffffu;
         if (sk < pn.n && row < max_size && row < pn.sizes[sk]) {
             bool found;
             const uint32_t lb = ref_lower_bound(ix, v, D, shift, maxkey, &found);
-            packed[((sk >> 4) * rows + row) * 16 + (sk & 15)] = 2u * lb + (found ? 1u : 0u);
+            code = 2u * lb + (found ? 1u : 0u);
             if (found) c += run_start[lb + 1] - run_start[lb];
         }
+        s_c[lane][r] = code;
+    }
+    __syncthreads();
+    // ---- store: warp w takes sketches 4w .. 4w+3 again, lane = row: 128 contiguous bytes of the row-major code array ------
+#pragma unroll
+    for (int i = 0; i < QC_TILE / 8; i++) {
+        const int s = wid * (QC_TILE / 8) + i;
+        const uint64_t sk = sk0 + s, row = row0 + lane;
+        if (sk < pn.n && row < max_size) codes[sk * max_size + row] = s_c[s][lane];
     }
     for (int o = 16; o; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
     // one atomic per CTA: a million same-address atomics (one per warp) cost 0.6 ms
@@ -265,7 +278,7 @@ __global__ void __launch_bounds__(256) dist_uf_flatten_kernel(uint32_t* __restri
 // lists, each distinct list walked once per query -- lists of independently mutated relatives are all different; and testing
 // the bit with a plain load before the atomic -- 0.7 ms slower.)
 constexpr int MARK_ROOTS = 32;       // components a query may touch before the early stop is given up for it
-__global__ void __launch_bounds__(256) dist_mark_kernel(const uint32_t* __restrict__ p32q, uint64_t rows_q, const uint32_t* __restrict__ sizes_q,
+__global__ void __launch_bounds__(256) dist_mark_kernel(const uint32_t* __restrict__ codes, uint64_t code_stride, const uint32_t* __restrict__ sizes_q,
                                                         const uint32_t* __restrict__ run_ref_start, const uint32_t* __restrict__ post, uint32_t words,
                                                         const uint32_t* __restrict__ parent, const uint32_t* __restrict__ ref_count, uint32_t n_r,
                                                         uint32_t* __restrict__ marks)
@@ -277,7 +290,7 @@ __global__ void __launch_bounds__(256) dist_mark_kernel(const uint32_t* __restri
     if (threadIdx.x == 0) { s_count = 0; s_nroots = 0; s_target = 0xffffffffu; }
     __syncthreads();
     const uint32_t n = sizes_q[q];
-    const uint32_t* col = p32q + ((uint64_t)(q >> 4) * rows_q) * 16 + (q & 15);
+    const uint32_t* col = codes + (uint64_t)q * code_stride;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     if (parent) {
         // references this query can reach at all: the sizes of the components its posting lists start in.  A component listed
@@ -286,7 +299,7 @@ __global__ void __launch_bounds__(256) dist_mark_kernel(const uint32_t* __restri
             const uint32_t e = e0 + threadIdx.x;
             uint32_t root = 0xffffffffu;
             if (e < n) {
-                const uint32_t code = col[(uint64_t)e * 16];
+                const uint32_t code = col[e];
                 if (code & 1u) root = parent[post[run_ref_start[code >> 1]]];
             }
             // one lane per distinct component of the warp looks it up in the list and appends it if it is new
@@ -317,7 +330,7 @@ __global__ void __launch_bounds__(256) dist_mark_kernel(const uint32_t* __restri
     const uint32_t target = s_target;
     for (uint32_t e = wid; e < n; e += nw) {                              // a warp per element, lanes over its postings
         if (*reinterpret_cast<volatile uint32_t*>(&s_count) >= target) break;
-        const uint32_t code = col[(uint64_t)e * 16];
+        const uint32_t code = col[e];
         if (!(code & 1u)) continue;                                       // even code: no reference holds this hash
         const uint32_t r = code >> 1;
         const uint32_t lo = run_ref_start[r], hi = run_ref_start[r + 1];
@@ -397,8 +410,57 @@ __global__ void __launch_bounds__(256) dist_marks_permute_kernel(const uint32_t*
     }
 }
 
-int dist_group_panels(fpm_ctx* ctx, uint64_t n_q, uint64_t n_r, uint64_t rows_q, uint64_t rows_r, uint32_t** p32r, uint32_t** p32q, uint32_t** marks,
-                      uint32_t** perm_q, uint32_t** perm_r)
+// Row-major query codes -> column tiles [n/16][rows][16], sketch sk' of the output = sketch perm[sk'] of the input (perm null:
+// natural order); +inf beyond each sketch's size.  A CTA builds 16 columns x 32 rows: coalesced row-major reads (a warp reads
+// 32 consecutive codes of one sketch), transposed in shared memory, written as 64-byte row segments.
+__global__ void __launch_bounds__(256) dist_pack_queries_kernel(const uint32_t* __restrict__ codes, uint64_t code_stride, const uint32_t* __restrict__ sizes,
+                                                                const uint32_t* __restrict__ perm, uint64_t n, uint64_t rows, uint32_t* __restrict__ dst)
+{
+    __shared__ uint32_t s_t[16][33];
+    const uint64_t tile = blockIdx.x, row0 = (uint64_t)blockIdx.y * 32;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const int c = wid * 2 + i;
+        const uint64_t sk = tile * 16 + c, row = row0 + lane;
+        uint32_t v = 0xffffffffu;
+        if (sk < n) {
+            const uint64_t o = perm ? perm[sk] : sk;
+            if (row < sizes[o]) v = codes[o * code_stride + row];
+        }
+        s_t[c][lane] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const int r = (threadIdx.x >> 4) + 16 * i, c = threadIdx.x & 15;
+        const uint64_t row = row0 + r;
+        if (row < rows) dst[(tile * rows + row) * 16 + c] = s_t[c][r];
+    }
+}
+
+static void launch_pack_queries(cudaStream_t st, const uint32_t* codes, uint64_t code_stride, const uint32_t* sizes, const uint32_t* perm, uint64_t n, uint64_t rows,
+                                uint32_t* dst)
+{
+    const dim3 grid((uint32_t)((n + 15) / 16), (uint32_t)((rows + 31) / 32));
+    if (n && rows) dist_pack_queries_kernel<<<grid, 256, 0, st>>>(codes, code_stride, sizes, perm, n, rows, dst);
+}
+
+// natural order (no grouping): into ctx->d_p32q
+int dist_pack_queries(fpm_ctx* ctx, const uint32_t* d_sizes_q, uint64_t n_q, uint64_t rows_q, uint32_t** p32q)
+{
+    const uint64_t pq = ((n_q + 15) / 16) * 16 * rows_q;
+    int rc;
+    if ((rc = ctx->d_p32q.ensure(pq * 4 + 64))) return rc;
+    *p32q = ctx->d_p32q.as<uint32_t>();
+    launch_pack_queries(ctx->stream, ctx->d_codes.as<uint32_t>(), ctx->code_stride, d_sizes_q, nullptr, n_q, rows_q, *p32q);
+    ctx->launches++;
+    FPM_CUDA(cudaGetLastError());
+    return FPM_OK;
+}
+
+int dist_group_panels(fpm_ctx* ctx, uint64_t n_q, uint64_t n_r, uint64_t rows_q, uint64_t rows_r, const uint32_t* d_sizes_q, uint32_t** p32r, uint32_t** p32q,
+                      uint32_t** marks, uint32_t** perm_q, uint32_t** perm_r)
 {
     cudaStream_t st = ctx->stream;
     const uint32_t words = (uint32_t)((n_r + 31) / 32);
@@ -427,7 +489,7 @@ int dist_group_panels(fpm_ctx* ctx, uint64_t n_q, uint64_t n_r, uint64_t rows_q,
     FPM_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_q, key_q, key_q2, idx_q, pq_out, (int64_t)n_q, 0, 32, st));
     FPM_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_r, key_r, key_r2, idx_r, pr_out, (int64_t)n_r, 0, 32, st));
     dist_repack_kernel<<<(uint32_t)((pr + 255) / 256), 256, 0, st>>>(*p32r, packed2, pr_out, n_r, rows_r);
-    dist_repack_kernel<<<(uint32_t)((pq + 255) / 256), 256, 0, st>>>(*p32q, packed2 + pr, pq_out, n_q, rows_q);
+    launch_pack_queries(st, ctx->d_codes.as<uint32_t>(), ctx->code_stride, d_sizes_q, pq_out, n_q, rows_q, packed2 + pr);   // the queries go straight from their row-major codes into grouped tiles
     FPM_CUDA(cudaFuncSetAttribute(dist_marks_permute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(words * 4)));
     dist_marks_permute_kernel<<<(uint32_t)n_q, 256, words * 4, st>>>(*marks, marks2, pq_out, pr_out, (uint32_t)n_q, (uint32_t)n_r, words);
     ctx->launches += 8;
@@ -625,16 +687,17 @@ int dist_rank_panels(fpm_ctx* ctx, const fpm_panel* d_ref, const fpm_panel* d_qr
     const uint64_t* ks = rix.ks;
     *packed_ref = ctx->d_p32.as<uint32_t>();
 
-    // ---- the query panel: codes by lookup ------------------------------------------------------------------------
-    if ((rc = ctx->d_p32q.ensure(pq * 4 + 64))) return rc;
-    *packed_qry = ctx->d_p32q.as<uint32_t>();
-    FPM_CUDA(cudaMemsetAsync(*packed_qry, 0xff, pq * 4, st));
+    // ---- the query panel: codes by lookup, row-major; the caller packs them (dist_pack_queries / dist_group_panels) ---------
+    (void)pq;
+    *packed_qry = nullptr;
+    if ((rc = ctx->d_codes.ensure(std::max<uint64_t>(mq, 1) * 4 + 64))) return rc;
+    ctx->code_stride = max_size_qry;
     RefIndex ix{dk, cum, scal};
     if (mq) {
         // sketch tiles fastest, row tiles slowest: the CTAs in flight at any time work on the same rows (= the same band of the index)
         const dim3 qgrid((uint32_t)((d_qry->n + QC_TILE - 1) / QC_TILE), (uint32_t)((max_size_qry + QC_TILE - 1) / QC_TILE));
         if (qgrid.y > 65535) { set_error("sketches of more than %u hashes are not supported", 65535u * QC_TILE); return FPM_ERR_UNSUPPORTED; }
-        dist_qcode_kernel<<<qgrid, 256, 0, st>>>(*d_qry, max_size_qry, rows_q, ix, run_start, *packed_qry, d_flag_q, d_total);
+        dist_qcode_kernel<<<qgrid, 256, 0, st>>>(*d_qry, max_size_qry, ix, run_start, ctx->d_codes.as<uint32_t>(), d_flag_q, d_total);
         ctx->launches++;
         FPM_CUDA(cudaGetLastError());
     }
@@ -672,7 +735,7 @@ int dist_rank_panels(fpm_ctx* ctx, const fpm_panel* d_ref, const fpm_panel* d_qr
                 rix.uf_valid = true;
             }
             FPM_CUDA(cudaFuncSetAttribute(dist_mark_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(words * 4)));
-            dist_mark_kernel<<<(uint32_t)d_qry->n, 256, words * 4, st>>>(*packed_qry, rows_q, d_qry->sizes, run_start, post, words, saturate ? parent : nullptr,
+            dist_mark_kernel<<<(uint32_t)d_qry->n, 256, words * 4, st>>>(ctx->d_codes.as<uint32_t>(), ctx->code_stride, d_qry->sizes, run_start, post, words, saturate ? parent : nullptr,
                                                                          ref_count, (uint32_t)d_ref->n, ctx->d_marks.as<uint32_t>());
             ctx->launches += 1;
             FPM_CUDA(cudaGetLastError());

@@ -15,8 +15,11 @@ int dist_rank_panels(fpm_ctx* ctx, const fpm_panel* d_ref, const fpm_panel* d_qr
 
 // Reorders both panels so that related sketches are neighbours (see dist_rank.cu): replaces *p32r / *p32q / *marks by
 // their permuted versions and returns the permutations (new index -> original sketch index, device arrays).
-int dist_group_panels(fpm_ctx* ctx, uint64_t n_q, uint64_t n_r, uint64_t rows_q, uint64_t rows_r, uint32_t** p32r, uint32_t** p32q, uint32_t** marks,
-                      uint32_t** perm_q, uint32_t** perm_r);
+int dist_group_panels(fpm_ctx* ctx, uint64_t n_q, uint64_t n_r, uint64_t rows_q, uint64_t rows_r, const uint32_t* d_sizes_q, uint32_t** p32r, uint32_t** p32q,
+                      uint32_t** marks, uint32_t** perm_q, uint32_t** perm_r);
+// dist_rank_panels leaves the query codes row-major (ctx->d_codes); this writes their column tiles in natural order.  (Grouping
+// writes them in grouped order itself.)
+int dist_pack_queries(fpm_ctx* ctx, const uint32_t* d_sizes_q, uint64_t n_q, uint64_t rows_q, uint32_t** p32q);
 
 // After dist_group_panels: the 32 x 32 tiles (grouped order) that hold a marked pair, or an empty query together with an
 // empty reference (such a pair has distance 0 without sharing a hash), as (query tile, reference tile) in device memory.
