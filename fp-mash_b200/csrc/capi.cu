@@ -196,7 +196,7 @@ void fpm_ctx_destroy(fpm_ctx* c)
     fpm::DevBuf* bufs[] = {&c->seq, &c->goff, &c->thresh, &c->active, &c->toff, &c->tmask, &c->tkeys, &c->tcnt, &c->tpos, &c->maxcnt,
                            &c->maxpos, &c->overflow, &c->stat, &c->tiles, &c->args, &c->alpha, &c->scratch, &c->stream_buf, &c->outh, &c->outc, &c->outn, &c->outk, &c->firstpos,
                            &c->tr_off, &c->tr_cursor, &c->tr_pos, &c->glist, &c->d_ref, &c->d_qry, &c->d_rs, &c->d_qs, &c->d_rl, &c->d_ql,
-                           &c->d_out, &c->d_misc, &c->d_p32, &c->d_rank, &c->fa_raw, &c->fa_seq, &c->fa_chunk, &c->fa_recs, &c->d_post, &c->d_marks, &c->d_group, &c->d_hits, &c->d_hsort, &c->d_tiles, &c->d_xq, &c->d_xr, &c->d_xg, &c->d_xg2, &c->d_p32q, &c->d_uf, &c->d_codes};
+                           &c->d_out, &c->d_misc, &c->d_p32, &c->d_rank, &c->fa_raw, &c->fa_seq, &c->fa_chunk, &c->fa_recs, &c->d_post, &c->d_marks, &c->d_group, &c->d_hits, &c->d_hsort, &c->d_tiles, &c->d_xq, &c->d_xr, &c->d_xg, &c->d_xg2, &c->d_p32q, &c->d_uf, &c->d_codes, &c->gz_in, &c->gz_meta};
     fpm_comm_destroy(c);
     for (auto* b : bufs) b->release();
     if (c->h_pinned) cudaFreeHost(c->h_pinned);

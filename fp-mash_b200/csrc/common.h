@@ -56,6 +56,8 @@ struct fpm_ctx {
     // FASTA ingestion (fpm_fasta_parse): raw bytes, compacted sequence, per-chunk scan arrays, record table
     fpm::DevBuf fa_raw, fa_seq, fa_chunk, fa_recs;
     uint64_t fa_records = 0, fa_seq_bytes = 0;
+    uint64_t fa_resident = 0;                    // bytes of the raw batch in fa_raw (uploaded by fpm_fasta_parse or inflated by fpm_gunzip_batch)
+    fpm::DevBuf gz_in, gz_meta;                  // gunzip.cu: compressed bytes; offsets / sizes / status per file
     fpm::DevBuf d_post, d_marks, d_group;        // dist pruning: posting lists, per-query reference bitmaps, grouped copies
     fpm::DevBuf d_tiles;                         // dist: list of the tiles that hold work
     fpm::DevBuf d_hits, d_hsort;                 // fpm_dist_hits: appended hits, sort keys / sorted copy

@@ -381,6 +381,19 @@ __global__ void __launch_bounds__(256) fastq_check_kernel(const uint64_t* __rest
     }
 }
 
+
+// header text of every record -> out[off[i] .. off[i+1]) (at most hdr_end - hdr_begin bytes), one warp per record
+__global__ void __launch_bounds__(256) fasta_headers_kernel(const uint8_t* __restrict__ raw, uint64_t n_bytes, const fpm_fasta_record* __restrict__ recs, uint64_t n,
+                                                            const uint64_t* __restrict__ off, uint8_t* __restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    for (uint64_t r = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < n; r += (uint64_t)gridDim.x * 8) {
+        const uint64_t b = recs[r].hdr_begin, e = recs[r].hdr_end < n_bytes ? recs[r].hdr_end : n_bytes;
+        const uint64_t len = e > b ? e - b : 0, room = off[r + 1] - off[r];
+        for (uint64_t j = lane; j < len && j < room; j += 32) out[off[r] + j] = raw[b + j];
+    }
+}
+
 }  // namespace fpm
 
 using namespace fpm;
@@ -391,10 +404,11 @@ int fpm_fasta_parse(fpm_ctx* ctx, const uint8_t* raw, uint64_t n_bytes, uint64_t
 {
     if (!ctx) { set_error("ctx is NULL"); return FPM_ERR_ARG; }
     if (!out_n_records || !out_seq_bytes || !out_status) { set_error("NULL output"); return FPM_ERR_ARG; }
-    if (!raw && n_bytes) { set_error("raw is NULL"); return FPM_ERR_ARG; }
+    // raw == NULL: the batch fpm_gunzip_batch inflated into fa_raw
+    if (!raw && n_bytes && ctx->fa_resident != n_bytes) { set_error("raw is NULL and no resident batch of %llu bytes", (unsigned long long)n_bytes); return FPM_ERR_ARG; }
     *out_n_records = 0; *out_seq_bytes = 0; *out_status = FPM_FASTA_OK;
     ctx->fa_records = 0; ctx->fa_seq_bytes = 0;
-    if (n_bytes == 0) return FPM_OK;
+    if (n_bytes == 0) { ctx->fa_resident = 0; return FPM_OK; }
     FPM_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const uint64_t n_chunks = (n_bytes + FA_CHUNK - 1) / FA_CHUNK;
@@ -413,7 +427,8 @@ int fpm_fasta_parse(fpm_ctx* ctx, const uint8_t* raw, uint64_t n_bytes, uint64_t
     uint8_t* start_state = chunk_fn + n_chunks;
     uint64_t* totals = ctx->d_misc.as<uint64_t>() + 2;               // d_misc: [flags | pad | totals[2]]
     FPM_CUDA(cudaMemsetAsync(ctx->d_misc.p, 0, 64, st));
-    FPM_CUDA(cudaMemcpyAsync(ctx->fa_raw.p, raw, n_bytes, cudaMemcpyHostToDevice, st));
+    if (raw) FPM_CUDA(cudaMemcpyAsync(ctx->fa_raw.p, raw, n_bytes, cudaMemcpyHostToDevice, st));
+    ctx->fa_resident = n_bytes;
     const uint32_t grid = (uint32_t)((n_chunks * 32 + 255) / 256);
     const uint8_t* d_raw = ctx->fa_raw.as<uint8_t>();
     fasta_chunk_fn_kernel<<<grid, 256, 0, st>>>(d_raw, n_bytes, n_chunks, chunk_fn);
@@ -437,6 +452,30 @@ int fpm_fasta_parse(fpm_ctx* ctx, const uint8_t* raw, uint64_t n_bytes, uint64_t
     ctx->fa_seq_bytes = seq_bytes;
     *out_n_records = n_rec;
     *out_seq_bytes = seq_bytes;
+    return FPM_OK;
+}
+
+int fpm_fasta_headers(fpm_ctx* ctx, const uint64_t* offsets, uint8_t* out)
+{
+    if (!ctx || !offsets) { set_error("NULL argument"); return FPM_ERR_ARG; }
+    const uint64_t n = ctx->fa_records;
+    if (n == 0) return FPM_OK;
+    const uint64_t total = offsets[n] - offsets[0];
+    if (offsets[0] != 0) { set_error("offsets must start at 0"); return FPM_ERR_ARG; }
+    if (total && !out) { set_error("out is NULL"); return FPM_ERR_ARG; }
+    FPM_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    int rc;
+    if ((rc = ctx->fa_chunk.ensure((n + 1) * 8 + total + 64))) return rc;
+    uint64_t* d_off = ctx->fa_chunk.as<uint64_t>();
+    uint8_t* d_out = (uint8_t*)(d_off + n + 1);
+    FPM_CUDA(cudaMemcpyAsync(d_off, offsets, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    fasta_headers_kernel<<<(uint32_t)std::min<uint64_t>((n + 7) / 8, 65535), 256, 0, st>>>(ctx->fa_raw.as<uint8_t>(), ctx->fa_resident, ctx->fa_recs.as<fpm_fasta_record>(), n, d_off,
+                                                                                          d_out);
+    ctx->launches++;
+    FPM_CUDA(cudaGetLastError());
+    if (total) FPM_CUDA(cudaMemcpyAsync(out, d_out, total, cudaMemcpyDeviceToHost, st));
+    FPM_CUDA(cudaStreamSynchronize(st));
     return FPM_OK;
 }
 

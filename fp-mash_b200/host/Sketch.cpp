@@ -26,6 +26,9 @@ using namespace std;
 
 static const uint64_t kLimitReadFingerprint = 1000000;   // LIMIT_READ_FINGERPRINT, Sketch.cpp:37
 static const uint64_t kFlushBytes = 256ull << 20;        // sequence bytes per GPU batch (the pinned staging buffer is sized for it)
+static const uint64_t kGzFlushBytes = 4096ull << 20;     // COMPRESSED bytes per batch of .gz files inflated on the GPU: the parallelism there is
+                                                         // one warp per file and a stream's rate is fixed, so a batch should hold thousands of
+                                                         // files when there are that many (~14 GB inflated, in HBM only)
 
 void fpmTick(const char* label)
 {
@@ -233,10 +236,11 @@ static void parseSequenceFile(const string& file, const Sketch::Parameters& para
 // comes back.  The metadata rules of sketchFile (Sketch.cpp:1318-1422,1436-1444) are applied to that table.
 // ------------------------------------------------------------------------------------------
 struct Sketch::RawBatch {
-    uint8_t* raw = nullptr;      // pinned: file bytes, each file followed by one 0x00
+    uint8_t* raw = nullptr;      // pinned: file bytes, each file followed by one 0x00 -- or, gz: the compressed files back to back
     uint64_t used = 0, cap = 0;
+    bool gz = false;             // the files are gzip streams, inflated on the device (csrc/gunzip.cu); set while the batch is empty
     vector<string> files;
-    vector<uint64_t> fileEnd;    // offset of each file's 0x00
+    vector<uint64_t> fileEnd;    // offset of each file's 0x00 (gz: end of its compressed bytes)
 
     ~RawBatch() { if (raw) fpm_host_free(raw); }
     void reserve(uint64_t extra)
@@ -265,7 +269,7 @@ struct Sketch::RawBatch {
             if (stat(names[i].c_str(), &st) != 0 || !S_ISREG(st.st_mode)) { ok[i] = 0; continue; }
             size[i] = (uint64_t)st.st_size;
             off[i] = used + total;
-            total += size[i] + 1;
+            total += size[i] + (gz ? 0 : 1);
         }
         reserve(total);
         auto readOne = [&](size_t i) {
@@ -277,7 +281,9 @@ struct Sketch::RawBatch {
             const bool more = fgetc(f) != EOF;
             fclose(f);
             if (got != size[i] || more) { ok[i] = 0; return; }
-            if (size[i] >= 2 && dst[0] == 0x1f && dst[1] == 0x8b) { ok[i] = 0; return; }       // gzip
+            const bool magic = size[i] >= 2 && dst[0] == 0x1f && dst[1] == 0x8b;
+            if (gz) { if (!magic) ok[i] = 0; return; }                                          // zlib reads anything else through unchanged: host reader
+            if (magic) { ok[i] = 0; return; }                                                  // gzip behind a plain name
             if (size[i] && memchr(dst, 0, size[i]) != nullptr) { ok[i] = 0; return; }
             dst[size[i]] = 0;
         };
@@ -296,7 +302,7 @@ struct Sketch::RawBatch {
         for (size_t i = 0; i < good; i++) {
             files.push_back(names[i]);
             fileEnd.push_back(off[i] + size[i]);
-            used = off[i] + size[i] + 1;
+            used = off[i] + size[i] + (gz ? 0 : 1);
         }
         return good;
     }
@@ -327,7 +333,18 @@ void Sketch::flushRawBatch(RawBatch& rb, Batch& hostBatch)
     fpmTick("raw batch read");
     uint64_t nRec = 0, seqBytes = 0;
     int status = 0;
-    gpuCheck(fpm_fasta_parse(gpuContext(), rb.raw, rb.used, &nRec, &seqBytes, &status));
+    if (rb.gz) {
+        // gzip streams: inflated on the device (one warp per file); the raw batch never exists on the host
+        vector<uint64_t> gzOff{0};
+        gzOff.insert(gzOff.end(), rb.fileEnd.begin(), rb.fileEnd.end());
+        uint64_t total = 0;
+        gpuCheck(fpm_gunzip_batch(gpuContext(), rb.raw, gzOff.data(), (uint32_t)rb.files.size(), rb.fileEnd.data(), &total, &status));
+        fpmTick("gzip batch inflated on the GPU");
+        if (status == FPM_GUNZIP_OK) gpuCheck(fpm_fasta_parse(gpuContext(), nullptr, total, &nRec, &seqBytes, &status));
+        else status = FPM_FASTA_NOT_PLAIN;                 // a damaged or unusual stream: zlib (the host reader) defines what the reference reads
+    } else {
+        gpuCheck(fpm_fasta_parse(gpuContext(), rb.raw, rb.used, &nRec, &seqBytes, &status));
+    }
     if (status != FPM_FASTA_OK) {
         // not plain FASTA somewhere in this batch (FASTQ records): the host reader defines the result
         for (const string& f : rb.files) parseSequenceFile(f, parameters, hostBatch);
@@ -337,6 +354,15 @@ void Sketch::flushRawBatch(RawBatch& rb, Batch& hostBatch)
     }
     vector<fpm_fasta_record> recs(nRec);
     if (nRec) gpuCheck(fpm_fasta_records(gpuContext(), recs.data()));
+    // header text: in the pinned batch, or (gz) gathered from the device
+    vector<uint8_t> hdrBytes;
+    vector<uint64_t> hdrOff;
+    if (rb.gz) {
+        hdrOff.assign(nRec + 1, 0);
+        for (uint64_t i = 0; i < nRec; i++) hdrOff[i + 1] = hdrOff[i] + (recs[i].hdr_end - recs[i].hdr_begin);
+        hdrBytes.resize(hdrOff[nRec] + 1);
+        if (nRec) gpuCheck(fpm_fasta_headers(gpuContext(), hdrOff.data(), hdrBytes.data()));
+    }
     fpmTick("fasta parsed on the GPU");
     vector<uint64_t> goff{0};
     vector<Reference> metas;
@@ -359,7 +385,8 @@ void Sketch::flushRawBatch(RawBatch& rb, Batch& hostBatch)
                 if (!parameters.concatenated) { goff.push_back(seqEnd); keep.push_back(0); metas.emplace_back(); }
                 continue;
             }
-            parseHeader(rb.raw + recs[r].hdr_begin + 1, rb.raw + recs[r].hdr_end, atEof, name, comment, commentCstr);
+            if (rb.gz) parseHeader(hdrBytes.data() + hdrOff[r] + 1, hdrBytes.data() + hdrOff[r + 1], atEof, name, comment, commentCstr);
+            else parseHeader(rb.raw + recs[r].hdr_begin + 1, rb.raw + recs[r].hdr_end, atEof, name, comment, commentCstr);
             if (parameters.concatenated) {
                 if (l < (uint64_t)parameters.kmerSize) { skipped = true; continue; }
                 if (count == 0) {
@@ -1045,6 +1072,28 @@ int Sketch::initFromFiles(const vector<string>& files, const Parameters& paramet
     size_t rawDone = 0;                                          // candidates below this index are already in rawBatch
     for (size_t i = 0; i < files.size(); i++)
         rawCandidate[i] = gpuParse && !hasSuffix(files[i], suffixSketch) && files[i] != "-" && !hasSuffix(files[i], ".gz");
+    // .gz files are inflated on the GPU (csrc/gunzip.cu: one warp per file) when a run of them keeps the device busier than
+    // the -p host threads would be: one stream inflates at ~19 MB/s there (a host core's zlib: ~240 MB/s), thousands run at
+    // once, and the batch takes as long as its largest file.  So: at least 32 files in a row, and
+    // largest / 19 MB/s < total / (240 MB/s x p).  FPMASH_GPU_GUNZIP=0 turns the route off, =1 takes it for any run.
+    const char* gunzipEnv = getenv("FPMASH_GPU_GUNZIP");
+    const bool gunzipOff = gunzipEnv && gunzipEnv[0] == '0', gunzipForce = gunzipEnv && gunzipEnv[0] == '1';
+    vector<char> gzCandidate(files.size(), 0);
+    for (size_t i = 0; i < files.size() && gpuParse && !gunzipOff;) {
+        size_t j = i;
+        uint64_t sumBytes = 0, maxBytes = 0;
+        while (j < files.size() && hasSuffix(files[j], ".gz") && files[j] != "-") {
+            struct stat st;
+            const uint64_t sz = stat(files[j].c_str(), &st) == 0 ? (uint64_t)st.st_size : 0;
+            sumBytes += sz;
+            maxBytes = max(maxBytes, sz);
+            j++;
+        }
+        const double hostThreads = (double)max(parametersNew.parallelism, 1);
+        if (j > i && (gunzipForce || (j - i >= 32 && (double)maxBytes * 12.6 * hostThreads < (double)sumBytes)))
+            for (size_t t = i; t < j; t++) gzCandidate[t] = rawCandidate[t] = 1;
+        i = max(j, i + 1);
+    }
 
     // the other sequence files (not sketches, not stdin) can be parsed ahead by -p threads
     vector<string> jobFiles;
@@ -1097,16 +1146,19 @@ int Sketch::initFromFiles(const vector<string>& files, const Parameters& paramet
             flushBatch(batch);                                   // references keep the order of the inputs
             if (rawDone > i) continue;                           // already read with an earlier file of its run
             // the run of GPU-parse candidates starting here, up to one batch of bytes, read by the -p threads
+            const bool gz = gzCandidate[i] != 0;
+            if (rawBatch.gz != gz) { flushRawBatch(rawBatch, batch); rawBatch.gz = gz; }
+            const uint64_t flushAt = gz ? kGzFlushBytes : kFlushBytes;
             vector<string> run;
             uint64_t runBytes = 0;
-            for (size_t j = i; j < files.size() && rawCandidate[j] && (run.empty() || rawBatch.used + runBytes < kFlushBytes); j++) {
+            for (size_t j = i; j < files.size() && rawCandidate[j] && (gzCandidate[j] != 0) == gz && (run.empty() || rawBatch.used + runBytes < flushAt); j++) {
                 struct stat st;
                 run.push_back(files[j]);
                 runBytes += stat(files[j].c_str(), &st) == 0 ? (uint64_t)st.st_size + 1 : 1;
             }
             const size_t good = rawBatch.addFiles(run, parameters.parallelism);
             rawDone = i + good;
-            if (rawBatch.used >= kFlushBytes) flushRawBatch(rawBatch, batch);
+            if (rawBatch.used >= flushAt) flushRawBatch(rawBatch, batch);
             if (good > 0) continue;
             flushRawBatch(rawBatch, batch);                      // gzip behind a plain name, 0x00 inside, ...: host reader
             parseSequenceFile(files[i], parameters, batch);

@@ -109,6 +109,9 @@ lib.fpm_fastq_line_ends.argtypes = [_VP, C.c_uint64, C.c_uint64, _VP]
 lib.fpm_fasta_parse.argtypes = [_VP, _VP, C.c_uint64, u64p, u64p, C.POINTER(C.c_int)]
 lib.fpm_fasta_records.argtypes = [_VP, _VP]
 lib.fpm_fasta_sequence.argtypes = [_VP, _VP]
+lib.fpm_gunzip_batch.argtypes = [_VP, _VP, _VP, C.c_uint32, _VP, u64p, C.POINTER(C.c_int)]
+lib.fpm_gunzip_output.argtypes = [_VP, _VP]
+lib.fpm_fasta_headers.argtypes = [_VP, _VP, _VP]
 lib.fpm_sketch_parsed.argtypes = [_VP, C.POINTER(SketchParams), _VP, C.c_uint32, _VP, _VP, _VP]
 FASTA_RECORD_DTYPE = np.dtype([("hdr_begin", "<u8"), ("hdr_end", "<u8"), ("seq_begin", "<u8")])
 lib.fpm_dist_hits.argtypes = [_VP, _VP, _VP, _VP, _VP, C.c_uint64, u64p]
@@ -190,7 +193,8 @@ EXPORTED = ["fpm_abi_version", "fpm_device_count", "fpm_ctx_create", "fpm_ctx_de
             "fpm_shard_range", "fpm_dist_grid_shape", "fpm_dist_block", "fpm_comm_get_unique_id", "fpm_comm_init_rank", "fpm_comm_adopt",
             "fpm_comm_destroy", "fpm_comm_rank", "fpm_comm_size", "fpm_dist_sharded_dev", "fpm_dist_hits_sharded_dev",
             "fpm_multi_create", "fpm_multi_destroy", "fpm_multi_size", "fpm_multi_ctx", "fpm_dist_tile_multi", "fpm_dist_hits_multi",
-            "fpm_sketch_batch_multi", "fpm_sketch_reads_sharded_dev", "fpm_dist_set_reference", "fpm_sketch_stream_append_async", "fpm_sketch_stream_wait"]
+            "fpm_sketch_batch_multi", "fpm_sketch_reads_sharded_dev", "fpm_dist_set_reference", "fpm_sketch_stream_append_async", "fpm_sketch_stream_wait",
+            "fpm_gunzip_batch", "fpm_gunzip_output", "fpm_fasta_headers"]
 
 
 def _check(rc):
@@ -515,6 +519,53 @@ class Context:
                 _check(lib.fpm_fasta_sequence(self._h, seq.ctypes.data))
             seq = seq[:nseq.value]
         return recs, lengths, seq
+
+    def gunzip_batch(self, gz_files, fetch=True):
+        """gz_files: list of bytes (gzip files).  Inflates them on the device into the raw batch of fasta_parse (each file
+        followed by 0x00).  Returns (status, file_end, raw): status 0 = all clean; file_end[i] = offset of file i's 0x00;
+        raw = the batch copied back (fetch=True) or None."""
+        sizes = np.array([0] + [len(g) for g in gz_files], dtype=np.uint64)
+        off = np.cumsum(sizes).astype(np.uint64)
+        blob = np.frombuffer(b"".join(bytes(g) for g in gz_files) + b"\0", dtype=np.uint8).copy()
+        ends = np.zeros(max(len(gz_files), 1), dtype=np.uint64)
+        total, status = C.c_uint64(0), C.c_int(0)
+        _check(lib.fpm_gunzip_batch(self._h, blob.ctypes.data, off.ctypes.data, len(gz_files), ends.ctypes.data, C.byref(total), C.byref(status)))
+        if status.value != 0:
+            return status.value, None, None
+        raw = None
+        if fetch:
+            raw = np.zeros(max(total.value, 1), dtype=np.uint8)
+            _check(lib.fpm_gunzip_output(self._h, raw.ctypes.data))
+            raw = raw[:total.value]
+        return 0, ends[:len(gz_files)], raw
+
+    def fasta_parse_resident(self, n_bytes, fetch_sequence=True, fetch_headers=True):
+        """fasta_parse over the batch gunzip_batch left on the device.  Returns None when it is not plain FASTA, else
+        (records, lengths, sequence, headers): headers[i] = bytes [hdr_begin, hdr_end) of record i."""
+        nrec, nseq, status = C.c_uint64(0), C.c_uint64(0), C.c_int(0)
+        _check(lib.fpm_fasta_parse(self._h, None, n_bytes, C.byref(nrec), C.byref(nseq), C.byref(status)))
+        if status.value != 0:
+            return None
+        recs = np.zeros(nrec.value, dtype=FASTA_RECORD_DTYPE)
+        if nrec.value:
+            _check(lib.fpm_fasta_records(self._h, recs.ctypes.data))
+        nxt = np.append(recs["seq_begin"][1:], np.uint64(nseq.value)) if nrec.value else np.zeros(0, dtype=np.uint64)
+        lengths = (nxt - recs["seq_begin"] - np.uint64(1)).astype(np.uint64) if nrec.value else nxt
+        seq = None
+        if fetch_sequence:
+            seq = np.zeros(max(nseq.value, 1), dtype=np.uint8)
+            if nseq.value:
+                _check(lib.fpm_fasta_sequence(self._h, seq.ctypes.data))
+            seq = seq[:nseq.value]
+        headers = None
+        if fetch_headers:
+            hoff = np.zeros(nrec.value + 1, dtype=np.uint64)
+            hoff[1:] = np.cumsum(recs["hdr_end"] - recs["hdr_begin"])
+            hb = np.zeros(max(int(hoff[-1]), 1), dtype=np.uint8)
+            if nrec.value:
+                _check(lib.fpm_fasta_headers(self._h, hoff.ctypes.data, hb.ctypes.data))
+            headers = [hb[int(hoff[i]):int(hoff[i + 1])].tobytes() for i in range(nrec.value)]
+        return recs, lengths, seq, headers
 
     def sketch_parsed(self, group_offsets, params):
         """Sketch the sequence the last fasta_parse left on the device."""

@@ -177,9 +177,28 @@ typedef struct fpm_fasta_record {
 } fpm_fasta_record;
 #define FPM_FASTA_OK 0
 #define FPM_FASTA_NOT_PLAIN 1
-int fpm_fasta_parse(fpm_ctx* ctx, const uint8_t* raw, uint64_t n_bytes, uint64_t* out_n_records, uint64_t* out_seq_bytes, int* out_status);
+int fpm_fasta_parse(fpm_ctx* ctx, const uint8_t* raw /* NULL: the batch fpm_gunzip_batch left on the device */, uint64_t n_bytes, uint64_t* out_n_records,
+                    uint64_t* out_seq_bytes, int* out_status);
 int fpm_fasta_records(fpm_ctx* ctx, fpm_fasta_record* out /* [n_records] */);
 int fpm_fasta_sequence(fpm_ctx* ctx, uint8_t* out /* [seq_bytes], tests */);
+/* gzip'ed FASTA files inflated on the device (the reference reads every input through zlib's gzopen / gzread,
+ * Sketch.cpp:1340-1346, kseq.h:60-75).  `gz` holds the COMPRESSED bytes of n_files files back to back, file i at
+ * [gz_offsets[i], gz_offsets[i+1]).  One warp per file inflates it (all members of a multi-member file) into the raw
+ * batch of fpm_fasta_parse -- every file followed by one 0x00 -- which stays resident in the context:
+ * out_file_end[i] = offset of file i's 0x00, *out_total = bytes of the batch.  Follow with
+ * fpm_fasta_parse(ctx, NULL, *out_total, ...) (raw == NULL: parse the resident batch) and fpm_fasta_headers.
+ * The trailer of every member is checked like zlib does (CRC-32, ISIZE).  *out_status != FPM_GUNZIP_OK: some file is
+ * not a clean gzip stream (or holds a 0x00 byte) and nothing is resident -- read the batch with the host reader.   */
+#define FPM_GUNZIP_OK 0
+#define FPM_GUNZIP_BAD_STREAM 1
+#define FPM_GUNZIP_HAS_NUL 2
+int fpm_gunzip_batch(fpm_ctx* ctx, const uint8_t* gz, const uint64_t* gz_offsets /* [n_files+1] */, uint32_t n_files,
+                     uint64_t* out_file_end /* [n_files] */, uint64_t* out_total, int* out_status);
+int fpm_gunzip_output(fpm_ctx* ctx, uint8_t* out /* [*out_total], tests */);
+/* Header text of the records of the last fpm_fasta_parse, from the raw batch on the device (the host has no copy of it
+ * after fpm_gunzip_batch): bytes [hdr_begin, hdr_end) of record i go to out[offsets[i] .. offsets[i+1]); the caller
+ * computes offsets from the record table (offsets[i+1] - offsets[i] = hdr_end - hdr_begin).                        */
+int fpm_fasta_headers(fpm_ctx* ctx, const uint64_t* offsets /* [n_records+1] */, uint8_t* out);
 /* Four-line FASTQ (one read set -> one sketch, `mash sketch -r`): a piece of a file -- starting at a record
  * boundary, ending with '\n' -- is parsed on the device and its reads are appended to the HBM-resident stream
  * of fpm_sketch_stream_begin / _end_group / _finish, each read followed by 0x00, exactly as
@@ -364,6 +383,7 @@ double fpm_distance(uint64_t common, uint64_t denom, int kmer_size);
 #define FPM_KERNEL_DIST_LITERAL 3  /* dist_literal_kernel                                          */
 #define FPM_KERNEL_DIST_PACK 4     /* dist_pack_kernel, or the rank pre-pass (keys, sort, scan, scatter) */
 #define FPM_KERNEL_DIST_EXCHANGE 5 /* fpm_dist_sharded_dev: the grouped ncclSend / ncclRecv of the row shards      */
+#define FPM_KERNEL_GUNZIP 6        /* gunzip_kernel (fpm_gunzip_batch)                             */
 int fpm_ctx_set_timing(fpm_ctx* ctx, int enable);
 int fpm_ctx_get_timing(fpm_ctx* ctx, int kernel_id, double* out_ms_total, uint64_t* out_launches);
 

@@ -341,3 +341,20 @@ def test_record_layouts_match_the_header(fpm, tmp_path):
     p, h = fpm.PAIR_DTYPE, fpm.HIT_DTYPE
     assert got == [p.itemsize, p.fields["distance"][1], p.fields["pvalue"][1], h.itemsize, h.fields["numer"][1], h.fields["distance"][1], h.fields["pvalue"][1]]
     assert got[0] == 24 and got[3] == 32
+
+
+def test_gunzip_core_on_the_cpu_equals_zlib(tmp_path):
+    """The sequential half of the GPU inflate (csrc/gunzip_core.cuh: bit reader, Huffman codes, block and member headers,
+    CRC arithmetic) is plain C++; tests/native/gunzip_sim.cpp runs it on the CPU the way lane 0 of the kernel does."""
+    import gz_cases
+    exe = str(tmp_path / "gunzip_sim")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-x", "c++", os.path.join(ROOT, "tests", "native", "gunzip_sim.cpp"), "-o", exe], check=True)
+    for name, (gz, want) in gz_cases.good_cases(big=True).items():
+        (tmp_path / "in.gz").write_bytes(gz)
+        r = subprocess.run([exe, str(tmp_path / "in.gz"), str(tmp_path / "out")], timeout=120)
+        assert r.returncode == 0, name
+        assert (tmp_path / "out").read_bytes() == want, name
+    for name, gz in gz_cases.bad_cases().items():
+        (tmp_path / "in.gz").write_bytes(gz)
+        r = subprocess.run([exe, str(tmp_path / "in.gz"), str(tmp_path / "out")], timeout=120)
+        assert r.returncode == 2, name
