@@ -311,34 +311,112 @@ GZ_HD inline int gz_read_block(GzStream& s, GzShared& sh)
     return GZ_S_CODES;
 }
 
-// up to 32 tokens of a Huffman block into sh.tok: literal = its byte; match = 1 << 31 | length << 16 | (distance - 1).
-// Returns the next state (GZ_S_CODES: block goes on); *ntok = tokens written.  A token is at most 48 bits long and the
-// caller's top-up left more than 1.5 KB in the ring: no refill inside.  Code and extra bits of a symbol (<= 15 + 13) come out
-// of ONE 32-bit window.
-GZ_HD inline int gz_decode_batch(GzStream& s, GzShared& sh, uint32_t* ntok)
+// ---- the token loop ---------------------------------------------------------------------------------------------
+// Shared-memory words by byte offset.  On the device these are ld.shared / st.shared on 32-bit shared-space addresses
+// computed once per batch: through the generic pointers of GzShared the compiler re-derived the shared window base
+// (S2R SR_CgaCtaId ...) at every access of the loop.
+#ifdef __CUDA_ARCH__
+typedef uint32_t gz_smem_t;
+__device__ __forceinline__ gz_smem_t gz_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t gz_ld(gz_smem_t base, uint32_t byte_off)
+{
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(base + byte_off));
+    return v;
+}
+__device__ __forceinline__ void gz_st(gz_smem_t base, uint32_t byte_off, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(base + byte_off), "r"(v)); }
+#else
+typedef uint8_t* gz_smem_t;
+inline gz_smem_t gz_smem(const void* p) { return (uint8_t*)p; }
+inline uint32_t gz_ld(gz_smem_t base, uint32_t byte_off) { return *reinterpret_cast<const uint32_t*>(base + byte_off); }
+inline void gz_st(gz_smem_t base, uint32_t byte_off, uint32_t v) { *reinterpret_cast<uint32_t*>(base + byte_off) = v; }
+#endif
+
+// One token the careful way (codes longer than the first-level tables, end of block, invalid symbols): the reader is at the
+// token's first bit.  Returns the next state; a token was written to sh.tok[*n] (and *n advanced) unless the block ended.
+GZ_HD inline int gz_decode_one(GzStream& s, GzShared& sh, uint32_t* n)
 {
     GzBits& b = s.b;
+    uint32_t cur = b.window();
+    uint32_t e = s.lit.tab[cur & ((1u << GZ_LIT_BITS) - 1u)];
+    if (!(e & 15u)) e = gz_decode_slow(cur, s.lit);
+    const uint32_t kind = e & GZ_K_MASK, cl = e & 15u;
+    if (!cl || kind == GZ_K_BAD) return GZ_S_BAD;
+    if (kind == GZ_K_LIT) { b.bp += cl; sh.tok[(*n)++] = e >> 16; return GZ_S_CODES; }
+    if (kind == GZ_K_EOB) { b.bp += cl; return s.last_block ? GZ_S_TRAILER : GZ_S_BLOCK; }
+    const uint32_t xl = (e >> 4) & 15u;
+    const uint32_t len = (e >> 16) + ((cur >> cl) & ((1u << xl) - 1u));
+    b.bp += cl + xl;
+    cur = b.window();
+    uint32_t d = s.dist.tab[cur & ((1u << GZ_DIST_BITS) - 1u)];
+    if (!(d & 15u)) d = gz_decode_slow(cur, s.dist);
+    const uint32_t dl = d & 15u, xd = (d >> 4) & 15u;
+    if (!dl || (d & GZ_K_MASK) == GZ_K_BAD) return GZ_S_BAD;
+    const uint32_t dd = (d >> 16) + ((cur >> dl) & ((1u << xd) - 1u));
+    b.bp += dl + xd;
+    sh.tok[(*n)++] = 0x80000000u | (len << 16) | (dd - 1);
+    return GZ_S_CODES;
+}
+
+// Up to 32 tokens of a Huffman block into sh.tok: literal = its byte; match = 1 << 31 | length << 16 | (distance - 1).
+// Returns the next state (GZ_S_CODES: block goes on); *ntok = tokens written.  A token is at most 48 bits long and the
+// caller's top-up left more than 1.5 KB in the ring: no ring refill inside.
+// This loop bounds a stream's rate -- one thread, one dependent chain (profiles/r02_gunzip_kernel.txt: an instruction every
+// six cycles, and every branch on a fresh predicate costs as much as a shared-memory load).  So the common case is straight
+// line code: the next bits wait in a 64-bit register pair (refilled without a branch from a ring word fetched one refill
+// ahead), a literal runs through the distance half with zero widths instead of branching around it, and everything rare
+// -- a code longer than the first-level table, end of block, an invalid symbol -- leaves the loop through ONE test per
+// token, is handled by gz_decode_one from the token's first bit, and the loop is entered again.
+GZ_HD inline int gz_decode_batch(GzStream& s, GzShared& sh, uint32_t* ntok)
+{
+    const gz_smem_t ring = gz_smem(sh.ring), lit_tab = gz_smem(sh.lit_tab), dist_tab = gz_smem(sh.dist_tab), tok = gz_smem(sh.tok);
+    constexpr uint32_t RING_MASK = 4u * (GZ_RING_WORDS - 1);
     int next = GZ_S_CODES;
     uint32_t n = 0;
-    while (n < 32) {
-        uint32_t cur = b.window();
-        uint32_t e = s.lit.tab[cur & ((1u << GZ_LIT_BITS) - 1u)];
-        if (!(e & 15u)) e = gz_decode_slow(cur, s.lit);
-        const uint32_t kind = e & GZ_K_MASK, cl = e & 15u;
-        if (!cl || kind == GZ_K_BAD) { next = GZ_S_BAD; break; }
-        if (kind == GZ_K_LIT) { b.bp += cl; sh.tok[n++] = e >> 16; continue; }
-        if (kind == GZ_K_EOB) { b.bp += cl; next = s.last_block ? GZ_S_TRAILER : GZ_S_BLOCK; break; }
-        const uint32_t xl = (e >> 4) & 15u;
-        const uint32_t len = (e >> 16) + ((cur >> cl) & ((1u << xl) - 1u));
-        b.bp += cl + xl;
-        cur = b.window();
-        uint32_t d = s.dist.tab[cur & ((1u << GZ_DIST_BITS) - 1u)];
-        if (!(d & 15u)) d = gz_decode_slow(cur, s.dist);
-        const uint32_t dl = d & 15u, xd = (d >> 4) & 15u;
-        if (!dl || (d & GZ_K_MASK) == GZ_K_BAD) { next = GZ_S_BAD; break; }
-        const uint32_t dd = (d >> 16) + ((cur >> dl) & ((1u << xd) - 1u));
-        b.bp += dl + xd;
-        sh.tok[n++] = 0x80000000u | (len << 16) | (dd - 1);
+    while (n < 32 && next == GZ_S_CODES) {
+        uint32_t w4 = (s.b.bp >> 5) * 4u;                          // byte offset (unwrapped) of the next ring word to load
+        uint64_t bb = (((uint64_t)gz_ld(ring, (w4 + 4u) & RING_MASK) << 32) | gz_ld(ring, w4 & RING_MASK)) >> (s.b.bp & 31u);
+        uint32_t nb = 64u - (s.b.bp & 31u);                        // valid bits in bb
+        w4 += 8u;
+        uint32_t nxt = gz_ld(ring, w4 & RING_MASK);
+        for (;;) {
+            // (state at the token's first bit, for the careful path)
+            const uint32_t nb_t = nb, w4_t = w4;
+            uint32_t fill = nb <= 32u ? 1u : 0u;
+            bb |= fill ? (uint64_t)nxt << nb : 0ull;
+            nb += fill * 32u;
+            w4 += fill * 4u;
+            nxt = gz_ld(ring, w4 & RING_MASK);
+            uint32_t cur = (uint32_t)bb;
+            const uint32_t e = gz_ld(lit_tab, (cur & ((1u << GZ_LIT_BITS) - 1u)) * 4u);
+            const uint32_t cl = e & 15u, xl = (e >> 4) & 15u;
+            const bool is_len = (e & GZ_K_MASK) == GZ_K_LEN;
+            const uint32_t val = (e >> 16) + ((cur >> cl) & ((1u << xl) - 1u));         // literal byte (xl = 0) or match length
+            bb >>= cl + xl;
+            nb -= cl + xl;
+            fill = nb <= 32u ? 1u : 0u;
+            bb |= fill ? (uint64_t)nxt << nb : 0ull;
+            nb += fill * 32u;
+            w4 += fill * 4u;
+            nxt = gz_ld(ring, w4 & RING_MASK);
+            cur = (uint32_t)bb;
+            const uint32_t d = gz_ld(dist_tab, (cur & ((1u << GZ_DIST_BITS) - 1u)) * 4u);
+            const uint32_t dl = is_len ? d & 15u : 0u, xd = is_len ? (d >> 4) & 15u : 0u;
+            const uint32_t dd = (d >> 16) + ((cur >> dl) & ((1u << xd) - 1u));
+            // one test: anything but a literal or a length with short codes and valid symbols
+            const bool rare = cl == 0u || (e & GZ_K_MASK) >= GZ_K_EOB || (is_len && ((d & 15u) == 0u || (d & GZ_K_MASK) == GZ_K_BAD));
+            if (rare) {
+                // back to the token's first bit: bits consumed so far = loaded - left, with the values the token started with
+                s.b.bp = 8u * w4_t - nb_t;
+                break;
+            }
+            bb >>= dl + xd;
+            nb -= dl + xd;
+            gz_st(tok, n * 4u, is_len ? (0x80000000u | (val << 16) | (dd - 1u)) : val);
+            n++;
+            if (n == 32) { s.b.bp = 8u * w4 - nb; break; }
+        }
+        if (n < 32) next = gz_decode_one(s, sh, &n);
     }
     // reading beyond the file's end means a truncated stream (zeros or the next file follow there)
     if (s.in_pos() > s.in_end + 8) next = GZ_S_BAD;
