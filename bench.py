@@ -698,6 +698,62 @@ def run_other_configs(args, torch, np, fpm, sharding, ctx, device, rank, world, 
         c1 = {"ms": (time.perf_counter() - t0) * 1e3, "lines": len(lines), "pairs": 25, "self_pairs_distance_0": bool((np.diag(got["distance"]) == 0).all())}
         out["C1_fp"] = c1
 
+        # -- ingestion of a gzip'ed collection (every input of the reference goes through zlib, Sketch.cpp:1340-1346): the headline
+        # genomes as 1000 .fna.gz files, inflated by fpm_gunzip_batch (one warp per file) and parsed + sketched without the inflated bytes
+        # visiting the host, next to zlib on the host threads.  (the first 32 genomes, compressed here, repeated: a stream's rate is what it is.)
+        try:
+            import ctypes as C
+            import gzip
+            import zlib
+            from concurrent.futures import ThreadPoolExecutor
+            n_gz = 1000
+            m_gz = min(32, n)
+            host_seq = seq[:int(offsets[m_gz])].cpu().numpy()
+            plain = []
+            for i in range(m_gz):
+                g = host_seq[int(offsets[i]):int(offsets[i + 1]) - 1].tobytes()
+                plain.append(b">genome%d\n" % i + b"\n".join(g[j:j + 80] for j in range(0, len(g), 80)) + b"\n")
+            with ThreadPoolExecutor(threads) as ex:
+                gz_m = list(ex.map(lambda b: gzip.compress(b, 6), plain))
+            gz = [gz_m[i % m_gz] for i in range(n_gz)]
+            raw_bytes = sum(len(plain[i % m_gz]) for i in range(n_gz))
+            t0 = time.perf_counter()
+            with ThreadPoolExecutor(threads) as ex:
+                inflated = sum(ex.map(lambda b: len(zlib.decompress(b, 31)), gz[:256]))
+            host_gbs = inflated / (time.perf_counter() - t0) / 1e9
+            goff = np.cumsum(np.array([0] + [len(b) for b in gz], dtype=np.uint64)).astype(np.uint64)
+            blob = torch.frombuffer(bytearray(b"".join(gz)), dtype=torch.uint8).pin_memory()
+            ends = np.zeros(n_gz, dtype=np.uint64)
+            total, status = C.c_uint64(0), C.c_int(0)
+            ctx.set_timing(True)
+            t0 = time.perf_counter()
+            fpm._check(fpm.lib.fpm_gunzip_batch(ctx._h, blob.data_ptr(), goff.ctypes.data, n_gz, ends.ctypes.data, C.byref(total), C.byref(status)))
+            t_inflate = time.perf_counter() - t0
+            k_ms, k_n = ctx.get_timing(6)
+            ctx.set_timing(False)
+            parsed = ctx.fasta_parse_resident(total.value, fetch_sequence=False, fetch_headers=True) if status.value == 0 else None
+            same = False
+            t_all = None
+            if parsed is not None:
+                recs, lengths, _, headers = parsed
+                goffs = np.append(recs["seq_begin"], np.uint64(int(recs["seq_begin"][-1]) + int(lengths[-1]) + 1)).astype(np.uint64)
+                res = ctx.sketch_parsed(goffs, fpm.make_sketch_params(k=K, s=S))
+                t_all = time.perf_counter() - t0
+                # the same genomes sketched from the resident buffer of the headline run
+                oh = torch.zeros((m_gz, S), dtype=torch.int64, device=device)
+                on = torch.zeros(m_gz, dtype=torch.int32, device=device)
+                ctx.sketch_batch_dev(seq.data_ptr(), int(offsets[m_gz]), offsets[:m_gz + 1], fpm.make_sketch_params(k=K, s=S), oh.data_ptr(), None, on.data_ptr())
+                want = oh.cpu().numpy().view(np.uint64)
+                same = bool(len(headers) == n_gz and headers[m_gz + 1] == b">genome1" and all(np.array_equal(res["hashes"][i], want[i % m_gz]) for i in range(0, n_gz, 37)))
+            out["gz_ingest"] = {"files": n_gz, "compressed_GB": float(goff[-1]) / 1e9, "inflated_GB": raw_bytes / 1e9, "status": status.value,
+                                "gunzip_kernel_ms": k_ms, "kernel_launches": k_n, "inflate_GBps": raw_bytes / (k_ms * 1e-3) / 1e9 if k_ms else None,
+                                "upload_plus_inflate_s": t_inflate, "upload_inflate_parse_sketch_s": t_all,
+                                "Gkmers_per_s_from_gz_files": (n_gz * (L - K + 1) / t_all / 1e9) if t_all else None,
+                                "host_zlib_GBps": host_gbs, "host_threads": threads, "sketches_equal_plain_input": same}
+            del blob
+        except Exception as e:                                        # a side measurement: never takes the bench line down
+            out["gz_ingest"] = {"error": repr(e)[:200]}
+
     # -- C5 dist at full size: 100,000 queries x 10,000 references, s=10000, k=32 (1e9 pairs), blocks over the ranks
     if args.c5_queries > 0:
         nq, nr, s5 = args.c5_queries, args.c5_refs, 10000
