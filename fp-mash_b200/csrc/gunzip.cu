@@ -249,7 +249,7 @@ int fpm_gunzip_batch(fpm_ctx* ctx, const uint8_t* gz, const uint64_t* gz_offsets
     FPM_CUDA(cudaMemcpyAsync(ctx->gz_in.p, gz, in_bytes, cudaMemcpyHostToDevice, st));
     FPM_CUDA(cudaMemsetAsync(ctx->gz_in.as<uint8_t>() + in_bytes, 0, PAD, st));
     FPM_CUDA(cudaMemcpyAsync(d_in_off, gz_offsets, sizeof(uint64_t) * (n_files + 1), cudaMemcpyHostToDevice, st));
-    // first layout: the size each file's trailer claims (RFC 1952 ISIZE; a DEFLATE stream cannot expand beyond 1032 : 1)
+    // first layout: the size each file's trailer claims (RFC 1952 ISIZE)
     std::vector<uint64_t> off(n_files + 1), size(n_files);
     std::vector<uint32_t> status(n_files);
     off[0] = 0;
@@ -257,7 +257,8 @@ int fpm_gunzip_batch(fpm_ctx* ctx, const uint8_t* gz, const uint64_t* gz_offsets
         const uint64_t b = gz_offsets[i], e = gz_offsets[i + 1];
         uint64_t claim = 0;
         if (e - b >= 18) claim = (uint64_t)gz[e - 4] | ((uint64_t)gz[e - 3] << 8) | ((uint64_t)gz[e - 2] << 16) | ((uint64_t)gz[e - 1] << 24);
-        claim = std::min<uint64_t>(claim, (e - b) * 1032 + 64);
+        // (a trailer can claim anything: beyond 16 : 1 -- FASTA compresses 3 to 6 : 1 -- the first pass only measures, see below)
+        claim = std::min<uint64_t>(claim, (e - b) * 16 + 65536);
         off[i + 1] = off[i] + claim + 1;
     }
     for (int pass = 0; pass < 2; pass++) {

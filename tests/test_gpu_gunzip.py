@@ -34,6 +34,12 @@ def test_gunzip_batch_equals_zlib(ctx):
     assert bytes(raw) == b"".join(w + b"\0" for _, w in files)
     assert [int(e) for e in ends] == list(np.cumsum([len(w) + 1 for _, w in files]) - 1)
     assert ctx.gunzip_batch([])[0] == 0
+    # a stream that expands far beyond the first layout's guess (16 : 1), and one whose trailer is followed by padding that
+    # reads as an absurd size claim: the measuring pass settles both
+    runs = b">n\n" + b"N" * 3_000_000 + b"\n"
+    padded = gzip.compress(cases["dna_l6"][1][:50000]) + b"\0" * 7 + b"\xff\xff\xff\x7f"
+    status, ends, raw = ctx.gunzip_batch([gzip.compress(runs, 9), padded])
+    assert status == 0 and bytes(raw) == runs + b"\0" + cases["dna_l6"][1][:50000] + b"\0"
 
 
 def test_gunzip_batch_refuses_what_zlib_refuses(ctx):
