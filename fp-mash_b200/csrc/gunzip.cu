@@ -106,20 +106,22 @@ __global__ void __launch_bounds__(32) gunzip_kernel(const uint8_t* __restrict__ 
             __syncwarp();
         }
         // ---- lane 0: one step of the stream ---------------------------------------------------------------------------
-        uint32_t ntok = 0;
+        uint32_t ntok = 0, ready = 0;
         int next_state = state;
         if (lane == 0) {
             if (state == GZ_S_HEADER) next_state = gz_read_header(s);
             else if (state == GZ_S_BLOCK) next_state = gz_read_block(s, sh);
-            else if (state == GZ_S_CODES) next_state = gz_decode_batch(s, sh, &ntok);
+            else if (state == GZ_S_CODES) next_state = gz_decode_batch(s, sh, &ntok, &ready);
         }
         ntok = __shfl_sync(0xffffffffu, ntok, 0);
+        ready = __shfl_sync(0xffffffffu, ready, 0);
         next_state = __shfl_sync(0xffffffffu, next_state, 0);
         __syncwarp();
 
         if (state == GZ_S_CODES && ntok) {
-            // ---- place the tokens ---------------------------------------------------------------------------------
-            const uint32_t tok = lane < (int)ntok ? sh.tok[lane] : 0;
+            // ---- every lane decodes the token whose first bit lane 0 found, then the tokens are placed -------------------
+            uint32_t tok = lane < (int)ntok ? sh.tok[lane] : 0;
+            if (lane < (int)ntok && !((ready >> lane) & 1u)) tok = gz_token_at(sh, tok);
             const bool is_match = lane < (int)ntok && (tok >> 31);
             const uint32_t len = lane < (int)ntok ? (is_match ? (tok >> 16) & 0x1ffu : 1u) : 0u;
             const uint32_t dst = (tok & 0xffffu) + 1u;

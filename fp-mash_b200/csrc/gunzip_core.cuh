@@ -46,9 +46,11 @@ GZ_TABLE uint8_t c_clorder[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3
 // One canonical Huffman code: a first-level table indexed by the next tab_bits bits of the stream, and the (count per
 // length, symbols in canonical order) form for the codes that do not fit it.  Table entries carry everything the
 // decoder needs for the symbol, so that a token costs two shared-memory lookups and no constant-table reads:
-//   bits 0-3 code length (0: not a short code -> canonical decode), 4-7 number of extra bits, 8-9 kind, 16-31 value
-//   (the literal byte; the base of a length or distance symbol).
+//   bits 0-3 code length (0: not a short code -> canonical decode), 4-7 number of extra bits, 8-9 kind, 10-14 code length +
+//   extra bits (what the symbol advances the stream by), 15 "not for the fast loop" (no short code here, end of block,
+//   invalid symbol), 16-31 value (the literal byte; the base of a length or distance symbol).
 constexpr uint32_t GZ_K_LIT = 0u << 8, GZ_K_LEN = 1u << 8, GZ_K_EOB = 2u << 8, GZ_K_BAD = 3u << 8, GZ_K_MASK = 3u << 8;
+constexpr uint32_t GZ_RARE = 1u << 15;
 struct GzCode {
     uint16_t* count;           // [16]
     uint16_t* syms;
@@ -69,20 +71,20 @@ struct GzShared {
     uint32_t crc_tab[256];
 };
 
-// what the decoder needs to know about symbol `sym` of a code of the given kind (without the code length)
-GZ_HD inline uint32_t gz_symbol_entry(int kind, int sym)
+// what the decoder needs to know about symbol `sym` of a code of the given kind, coded with `len` bits
+GZ_HD inline uint32_t gz_symbol_entry(int kind, int sym, int len)
 {
+    uint32_t e, x = 0;
     if (kind == 0) {
-        if (sym < 256) return GZ_K_LIT | ((uint32_t)sym << 16);
-        if (sym == 256) return GZ_K_EOB;
-        if (sym >= 286) return GZ_K_BAD;
-        return GZ_K_LEN | ((uint32_t)c_lext[sym - 257] << 4) | ((uint32_t)c_lbase[sym - 257] << 16);
-    }
-    if (kind == 1) {
-        if (sym >= 30) return GZ_K_BAD;
-        return ((uint32_t)c_dext[sym] << 4) | ((uint32_t)c_dbase[sym] << 16);
-    }
-    return (uint32_t)sym << 16;
+        if (sym < 256) e = GZ_K_LIT | ((uint32_t)sym << 16);
+        else if (sym == 256) e = GZ_K_EOB | GZ_RARE;
+        else if (sym >= 286) e = GZ_K_BAD | GZ_RARE;
+        else { x = c_lext[sym - 257]; e = GZ_K_LEN | ((uint32_t)c_lbase[sym - 257] << 16); }
+    } else if (kind == 1) {
+        if (sym >= 30) e = GZ_K_BAD | GZ_RARE;
+        else { x = c_dext[sym]; e = (uint32_t)c_dbase[sym] << 16; }
+    } else e = (uint32_t)sym << 16;
+    return e | (uint32_t)len | (x << 4) | (((uint32_t)len + x) << 10);
 }
 
 // ---- lane 0's bit reader: a bit position over a ring of 32-bit words ---------------------------------------------------
@@ -124,7 +126,7 @@ GZ_HD inline uint32_t gz_decode_slow(uint32_t cur, const GzCode& h)
     for (int len = 1; len <= 15; len++) {
         code |= (int)((cur >> (len - 1)) & 1u);
         const int c = h.count[len];
-        if (code - c < first) return gz_symbol_entry(h.kind, h.syms[index + (code - first)]) | (uint32_t)len;
+        if (code - c < first) return gz_symbol_entry(h.kind, h.syms[index + (code - first)], len);
         index += c;
         first += c;
         first <<= 1;
@@ -139,7 +141,7 @@ GZ_HD inline int gz_build(GzCode& h, const uint8_t* lens, int n)
     for (int l = 0; l <= 15; l++) h.count[l] = 0;
     for (int s = 0; s < n; s++) h.count[lens[s]]++;
     const int tab_n = h.tab ? 1 << h.tab_bits : 0;
-    for (int i = 0; i < tab_n; i++) h.tab[i] = 0;
+    for (int i = 0; i < tab_n; i++) h.tab[i] = GZ_RARE;               // no short code ends here
     if (h.count[0] == n) return 0;                         // no codes: complete, every use fails
     int left = 1;
     for (int l = 1; l <= 15; l++) {
@@ -159,7 +161,7 @@ GZ_HD inline int gz_build(GzCode& h, const uint8_t* lens, int n)
         const uint32_t c = next[l]++;
         if (h.tab && l <= h.tab_bits) {
             const uint32_t r = gz_brev(c) >> (32 - l);          // codes enter the stream most significant bit first
-            const uint32_t e = gz_symbol_entry(h.kind, s) | (uint32_t)l;
+            const uint32_t e = gz_symbol_entry(h.kind, s, l);
             for (uint32_t i = r; i < (uint32_t)tab_n; i += 1u << l) h.tab[i] = e;
         }
     }
@@ -358,69 +360,106 @@ GZ_HD inline int gz_decode_one(GzStream& s, GzShared& sh, uint32_t* n)
     return GZ_S_CODES;
 }
 
-// Up to 32 tokens of a Huffman block into sh.tok: literal = its byte; match = 1 << 31 | length << 16 | (distance - 1).
-// Returns the next state (GZ_S_CODES: block goes on); *ntok = tokens written.  A token is at most 48 bits long and the
+// The token that starts at bit `pos` of the stream, decoded through the first-level tables only (the serial loop below has
+// checked that they suffice): literal = its byte; match = 1 << 31 | length << 16 | (distance - 1).  Any lane can do this for
+// any token of the round once the token's first bit is known -- which is the only thing that is sequential about DEFLATE.
+GZ_HD __forceinline__ uint32_t gz_token_at(const GzShared& sh, uint32_t pos)
+{
+    uint32_t w = pos >> 5;
+    uint32_t w0 = sh.ring[w & (GZ_RING_WORDS - 1)], w1 = sh.ring[(w + 1) & (GZ_RING_WORDS - 1)];
+#ifdef __CUDA_ARCH__
+    uint32_t cur = __funnelshift_r(w0, w1, pos & 31u);
+#else
+    uint32_t cur = (uint32_t)((((uint64_t)w1 << 32) | w0) >> (pos & 31));
+#endif
+    const uint32_t e = sh.lit_tab[cur & ((1u << GZ_LIT_BITS) - 1u)];
+    const uint32_t cl = e & 15u, xl = (e >> 4) & 15u;
+    const uint32_t val = (e >> 16) + ((cur >> cl) & ((1u << xl) - 1u));
+    if ((e & GZ_K_MASK) != GZ_K_LEN) return val;
+    pos += cl + xl;
+    w = pos >> 5;
+    w0 = sh.ring[w & (GZ_RING_WORDS - 1)]; w1 = sh.ring[(w + 1) & (GZ_RING_WORDS - 1)];
+#ifdef __CUDA_ARCH__
+    cur = __funnelshift_r(w0, w1, pos & 31u);
+#else
+    cur = (uint32_t)((((uint64_t)w1 << 32) | w0) >> (pos & 31));
+#endif
+    const uint32_t d = sh.dist_tab[cur & ((1u << GZ_DIST_BITS) - 1u)];
+    const uint32_t dl = d & 15u, xd = (d >> 4) & 15u;
+    const uint32_t dd = (d >> 16) + ((cur >> dl) & ((1u << xd) - 1u));
+    return 0x80000000u | (val << 16) | (dd - 1u);
+}
+
+// One round of a Huffman block: where up to 32 tokens START.  sh.tok[i] = bit position of token i, for the lanes to decode
+// with gz_token_at -- except where bit i of *ready is set: that token needed the careful path and sh.tok[i] is the token.
+// Returns the next state (GZ_S_CODES: block goes on); *ntok = entries written.  A token is at most 48 bits long and the
 // caller's top-up left more than 1.5 KB in the ring: no ring refill inside.
 // This loop bounds a stream's rate -- one thread, one dependent chain (profiles/r02_gunzip_kernel.txt: an instruction every
-// six cycles, and every branch on a fresh predicate costs as much as a shared-memory load).  So the common case is straight
-// line code: the next bits wait in a 64-bit register pair (refilled without a branch from a ring word fetched one refill
-// ahead), a literal runs through the distance half with zero widths instead of branching around it, and everything rare
-// -- a code longer than the first-level table, end of block, an invalid symbol -- leaves the loop through ONE test per
-// token, is handled by gz_decode_one from the token's first bit, and the loop is entered again.
-GZ_HD inline int gz_decode_batch(GzStream& s, GzShared& sh, uint32_t* ntok)
+// 4 to 6 cycles, every branch on a fresh predicate as expensive as a shared-memory load).  So it does nothing but find the
+// starts: per token two table lookups whose entries say by how many bits the symbol (code + extra bits) advances the
+// stream, on a 64-bit register pair refilled by select from a ring word fetched one refill ahead; a literal runs through
+// the distance half with a zero advance instead of branching around it; and everything rare -- a code longer than the
+// first-level table, end of block, an invalid symbol: one flag bit in the entries -- leaves through ONE test per token,
+// is handled by gz_decode_one from the token's first bit, and the loop is entered again.
+GZ_HD inline int gz_decode_batch(GzStream& s, GzShared& sh, uint32_t* ntok, uint32_t* ready)
 {
     const gz_smem_t ring = gz_smem(sh.ring), lit_tab = gz_smem(sh.lit_tab), dist_tab = gz_smem(sh.dist_tab), tok = gz_smem(sh.tok);
     constexpr uint32_t RING_MASK = 4u * (GZ_RING_WORDS - 1);
     int next = GZ_S_CODES;
-    uint32_t n = 0;
+    uint32_t n = 0, rdy = 0;
     while (n < 32 && next == GZ_S_CODES) {
         uint32_t w4 = (s.b.bp >> 5) * 4u;                          // byte offset (unwrapped) of the next ring word to load
         uint64_t bb = (((uint64_t)gz_ld(ring, (w4 + 4u) & RING_MASK) << 32) | gz_ld(ring, w4 & RING_MASK)) >> (s.b.bp & 31u);
         uint32_t nb = 64u - (s.b.bp & 31u);                        // valid bits in bb
         w4 += 8u;
         uint32_t nxt = gz_ld(ring, w4 & RING_MASK);
+        // invariant at a token's first bit: nb >= 33.  Both lookups index with bits that are already there (10 of >= 33; 8 of
+        // the >= 13 left behind a length symbol), so the two refills wait for nobody: they overlap the lookups' latency, and
+        // the chain per token is lookup, shift, lookup, shift.
+        {
+            const uint32_t fill = nb <= 32u ? 1u : 0u;
+            bb |= fill ? (uint64_t)nxt << nb : 0ull;
+            nb += fill * 32u;
+            w4 += fill * 4u;
+            nxt = gz_ld(ring, w4 & RING_MASK);
+        }
         for (;;) {
-            // (state at the token's first bit, for the careful path)
-            const uint32_t nb_t = nb, w4_t = w4;
+            const uint32_t pos = 8u * w4 - nb;                     // the token's first bit
+            const uint32_t e = gz_ld(lit_tab, ((uint32_t)bb & ((1u << GZ_LIT_BITS) - 1u)) * 4u);
+            const uint32_t a1 = (e >> 10) & 31u;                   // <= 20
+            bb >>= a1;
+            nb -= a1;                                              // >= 13
+            const uint32_t d = gz_ld(dist_tab, ((uint32_t)bb & ((1u << GZ_DIST_BITS) - 1u)) * 4u);
             uint32_t fill = nb <= 32u ? 1u : 0u;
             bb |= fill ? (uint64_t)nxt << nb : 0ull;
-            nb += fill * 32u;
+            nb += fill * 32u;                                      // >= 45
             w4 += fill * 4u;
             nxt = gz_ld(ring, w4 & RING_MASK);
-            uint32_t cur = (uint32_t)bb;
-            const uint32_t e = gz_ld(lit_tab, (cur & ((1u << GZ_LIT_BITS) - 1u)) * 4u);
-            const uint32_t cl = e & 15u, xl = (e >> 4) & 15u;
-            const bool is_len = (e & GZ_K_MASK) == GZ_K_LEN;
-            const uint32_t val = (e >> 16) + ((cur >> cl) & ((1u << xl) - 1u));         // literal byte (xl = 0) or match length
-            bb >>= cl + xl;
-            nb -= cl + xl;
+            const uint32_t is_len = 0u - ((e >> 8) & 1u);          // all ones for a length symbol (kind bit 0; EOB / BAD carry GZ_RARE)
+            const uint32_t dm = d & is_len;
+            if ((e | dm) & GZ_RARE) { s.b.bp = pos; break; }       // back to the token's first bit
+            const uint32_t a2 = (dm >> 10) & 31u;                  // <= 28
+            bb >>= a2;
+            nb -= a2;                                              // >= 17
             fill = nb <= 32u ? 1u : 0u;
             bb |= fill ? (uint64_t)nxt << nb : 0ull;
-            nb += fill * 32u;
+            nb += fill * 32u;                                      // >= 33 again
             w4 += fill * 4u;
             nxt = gz_ld(ring, w4 & RING_MASK);
-            cur = (uint32_t)bb;
-            const uint32_t d = gz_ld(dist_tab, (cur & ((1u << GZ_DIST_BITS) - 1u)) * 4u);
-            const uint32_t dl = is_len ? d & 15u : 0u, xd = is_len ? (d >> 4) & 15u : 0u;
-            const uint32_t dd = (d >> 16) + ((cur >> dl) & ((1u << xd) - 1u));
-            // one test: anything but a literal or a length with short codes and valid symbols
-            const bool rare = cl == 0u || (e & GZ_K_MASK) >= GZ_K_EOB || (is_len && ((d & 15u) == 0u || (d & GZ_K_MASK) == GZ_K_BAD));
-            if (rare) {
-                // back to the token's first bit: bits consumed so far = loaded - left, with the values the token started with
-                s.b.bp = 8u * w4_t - nb_t;
-                break;
-            }
-            bb >>= dl + xd;
-            nb -= dl + xd;
-            gz_st(tok, n * 4u, is_len ? (0x80000000u | (val << 16) | (dd - 1u)) : val);
+            gz_st(tok, n * 4u, pos);
             n++;
             if (n == 32) { s.b.bp = 8u * w4 - nb; break; }
         }
-        if (n < 32) next = gz_decode_one(s, sh, &n);
+        if (n < 32) {
+            const uint32_t before = n;
+            next = gz_decode_one(s, sh, &n);
+            if (n != before) rdy |= 1u << before;
+        }
     }
     // reading beyond the file's end means a truncated stream (zeros or the next file follow there)
     if (s.in_pos() > s.in_end + 8) next = GZ_S_BAD;
     *ntok = n;
+    *ready = rdy;
     return next;
 }
 

@@ -47,13 +47,13 @@ int main(int argc, char** argv)
             }
             s.b.whi += 128;
         }
-        uint32_t ntok = 0;
+        uint32_t ntok = 0, ready = 0;
         int next = state;
         if (state == GZ_S_HEADER) next = gz_read_header(s);
         else if (state == GZ_S_BLOCK) next = gz_read_block(s, sh);
-        else if (state == GZ_S_CODES) next = gz_decode_batch(s, sh, &ntok);
+        else if (state == GZ_S_CODES) next = gz_decode_batch(s, sh, &ntok, &ready);
         for (uint32_t t = 0; t < ntok && next != GZ_S_BAD; t++) {
-            const uint32_t tok = sh.tok[t];
+            const uint32_t tok = ((ready >> t) & 1u) ? sh.tok[t] : gz_token_at(sh, sh.tok[t]);       // what lane t does
             if (!(tok >> 31)) { out.push_back((uint8_t)tok); continue; }
             const uint32_t len = (tok >> 16) & 0x1ffu, d = (tok & 0xffffu) + 1u;
             if (d > out.size() - member_begin) { next = GZ_S_BAD; break; }
