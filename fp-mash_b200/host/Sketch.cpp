@@ -1073,9 +1073,9 @@ int Sketch::initFromFiles(const vector<string>& files, const Parameters& paramet
     for (size_t i = 0; i < files.size(); i++)
         rawCandidate[i] = gpuParse && !hasSuffix(files[i], suffixSketch) && files[i] != "-" && !hasSuffix(files[i], ".gz");
     // .gz files are inflated on the GPU (csrc/gunzip.cu: one warp per file) when a run of them keeps the device busier than
-    // the -p host threads would be: one stream inflates at ~19 MB/s there (a host core's zlib: ~240 MB/s), thousands run at
+    // the -p host threads would be: one stream inflates at ~28 MB/s there (a host core's zlib: ~240 MB/s), thousands run at
     // once, and the batch takes as long as its largest file.  So: at least 32 files in a row, and
-    // largest / 19 MB/s < total / (240 MB/s x p).  FPMASH_GPU_GUNZIP=0 turns the route off, =1 takes it for any run.
+    // largest / 28 MB/s < total / (240 MB/s x p).  FPMASH_GPU_GUNZIP=0 turns the route off, =1 takes it for any run.
     const char* gunzipEnv = getenv("FPMASH_GPU_GUNZIP");
     const bool gunzipOff = gunzipEnv && gunzipEnv[0] == '0', gunzipForce = gunzipEnv && gunzipEnv[0] == '1';
     vector<char> gzCandidate(files.size(), 0);
@@ -1090,7 +1090,7 @@ int Sketch::initFromFiles(const vector<string>& files, const Parameters& paramet
             j++;
         }
         const double hostThreads = (double)max(parametersNew.parallelism, 1);
-        if (j > i && (gunzipForce || (j - i >= 32 && (double)maxBytes * 12.6 * hostThreads < (double)sumBytes)))
+        if (j > i && (gunzipForce || (j - i >= 32 && (double)maxBytes * 8.6 * hostThreads < (double)sumBytes)))
             for (size_t t = i; t < j; t++) gzCandidate[t] = rawCandidate[t] = 1;
         i = max(j, i + 1);
     }
