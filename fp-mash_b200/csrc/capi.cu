@@ -139,11 +139,12 @@ int fpm_ctx_set_timing(fpm_ctx* c, int enable)
 int fpm_ctx_set_dist_mode(fpm_ctx* c, int mode)
 {
     if (!c) { set_error("ctx is NULL"); return FPM_ERR_ARG; }
-    if (mode != FPM_DIST_AUTO && mode != FPM_DIST_FORCE64 && mode != FPM_DIST_NO_PRUNE && mode != FPM_DIST_NO_GROUP && mode != FPM_DIST_SATURATE) { set_error("unknown dist mode %d", mode); return FPM_ERR_ARG; }
+    if (mode != FPM_DIST_AUTO && mode != FPM_DIST_FORCE64 && mode != FPM_DIST_NO_PRUNE && mode != FPM_DIST_NO_GROUP && mode != FPM_DIST_SATURATE && mode != FPM_DIST_GROUP) { set_error("unknown dist mode %d", mode); return FPM_ERR_ARG; }
     c->force_dist64 = mode == FPM_DIST_FORCE64;
     c->no_dist_prune = mode == FPM_DIST_NO_PRUNE;
     c->no_dist_group = mode == FPM_DIST_NO_GROUP;
     c->force_dist_saturate = mode == FPM_DIST_SATURATE;
+    c->force_dist_group = mode == FPM_DIST_GROUP;
     return FPM_OK;
 }
 

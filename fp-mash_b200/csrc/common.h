@@ -83,6 +83,7 @@ struct fpm_ctx {
     fpm::DevBuf d_p32q, d_uf;                    // packed query tiles; union-find parents / component sizes of the references
     bool no_dist_prune = false;                  // tests: merge every pair
     bool no_dist_group = false;                  // tests: prune, but leave the panels in their own order
+    bool force_dist_group = false;               // tests: always reorder the panels (default: only when the marked pairs are scattered)
     bool force_dist_saturate = false;            // tests: always bound the marking walks by the components' sizes
     bool force_dist64 = false;                   // tests: run the 64-bit tile kernel although the 32-bit rank path applies
     // optional per-kernel event timing (bench roofline): pairs of events around each launch

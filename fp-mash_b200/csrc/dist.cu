@@ -836,10 +836,24 @@ int run_dist(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* d_ref, con
         if (!ctx->force_dist64 && (rc = dist_rank_panels(ctx, d_ref, d_qry, max_size_ref, max_size_qry, rows_r, rows_q, a.s, &p32r, &p32q, &mode, &marks))) return rc;
         if (mode == DIST_RANK_UNSORTED) fast = false;
         uint32_t *perm_q = nullptr, *perm_r = nullptr;
-        // grouping related sketches pays when results stay on the device (a grouped query order would break the row-chunked
-        // copy-out of the host path) and the panels are large enough to have many tiles
-        if (mode == DIST_RANK_OK && marks && !h_out && !ctx->no_dist_group && d_ref->n >= 256 && d_qry->n >= 256)
-            if ((rc = dist_group_panels(ctx, d_qry->n, d_ref->n, rows_q, rows_r, d_qry->sizes, &p32r, &p32q, &marks, &perm_q, &perm_r))) return rc;
+        // When results stay on the device (a grouped query order would break the row-chunked copy-out of the host path) and the
+        // panels are large enough to have many tiles, only the tiles that hold a marked pair are launched, over records filled in
+        // beforehand (`listed`).  And the panels are regrouped so that related sketches share tiles -- if the marked pairs are
+        // scattered: a collection that is already ordered by relatedness (families side by side: 20 465 tiles for 2*10^7 marked
+        // pairs at configs[2], 5 % above the minimum) gains nothing from the 1.1 ms that regrouping costs there.
+        bool listed = false;
+        const uint2* tile_list = nullptr;
+        uint32_t n_listed = 0;
+        if (mode == DIST_RANK_OK && marks && !h_out && !ctx->no_dist_group && d_ref->n >= 256 && d_qry->n >= 256) {
+            uint64_t n_marked = 0;
+            listed = true;
+            if ((rc = dist_tile_list(ctx, marks, d_qry->n, d_ref->n, nullptr, nullptr, d_qry->sizes, d_ref->sizes, &tile_list, &n_listed, &n_marked))) return rc;
+            const bool scattered = (uint64_t)n_listed * 1024 > 2 * n_marked + 64 * 1024;         // tiles less than half full on average
+            if (scattered || ctx->force_dist_group) {
+                if ((rc = dist_group_panels(ctx, d_qry->n, d_ref->n, rows_q, rows_r, d_qry->sizes, &p32r, &p32q, &marks, &perm_q, &perm_r))) return rc;
+                tile_list = nullptr;                                  // listed again in the new order, below
+            }
+        }
         if (mode == DIST_RANK_OK && !p32q && (rc = dist_pack_queries(ctx, d_qry->sizes, d_qry->n, rows_q, &p32q))) return rc;   // no grouping: natural order
         if (mode == DIST_RANK_TOO_BIG) {
             if ((rc = ctx->d_ref.ensure(nr16 * 16 * rows_r * 8))) return rc;
@@ -874,14 +888,13 @@ int run_dist(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_panel* d_ref, con
                 FPM_CUDA(cudaEventCreateWithFlags(&ctx->copy_done[0], cudaEventDisableTiming));
                 FPM_CUDA(cudaEventCreateWithFlags(&ctx->copy_done[1], cudaEventDisableTiming));
             }
-            const bool prefill = k32 && perm_q && !hits && ((uintptr_t)d_out & 15) == 0;   // grouped panels: see dist_fill_unshared_kernel
+            const bool prefill = k32 && listed && !hits && ((uintptr_t)d_out & 15) == 0;   // see dist_fill_unshared_kernel
             // nothing has to come out of a tile without a marked pair when its closed-form records are already in place (prefill)
             // or cannot pass the filters (hits): such launches run over the list of tiles that hold work -- 19 of 20 tiles of
             // configs[2] are empty, and an empty 512-thread CTA still costs its launch
-            const uint2* tile_list = nullptr;
-            uint32_t n_listed = 0;
-            if (k32 && perm_q && nqt <= tiles_per_chunk && (prefill || (hits && hits->skip_unmarked)))
-                if ((rc = dist_tile_list(ctx, marks, d_qry->n, d_ref->n, perm_q, perm_r, d_qry->sizes, d_ref->sizes, &tile_list, &n_listed))) return rc;
+            if (k32 && listed && nqt <= tiles_per_chunk && (prefill || (hits && hits->skip_unmarked))) {
+                if (!tile_list && (rc = dist_tile_list(ctx, marks, d_qry->n, d_ref->n, perm_q, perm_r, d_qry->sizes, d_ref->sizes, &tile_list, &n_listed, nullptr))) return rc;
+            } else tile_list = nullptr;
             uint64_t c = 0;
             for (uint64_t t0 = 0; t0 < nqt; t0 += tiles_per_chunk, c++) {
                 const uint64_t nt = std::min(tiles_per_chunk, nqt - t0);

@@ -502,23 +502,27 @@ int dist_group_panels(fpm_ctx* ctx, uint64_t n_q, uint64_t n_r, uint64_t rows_q,
 __global__ void __launch_bounds__(256) dist_tile_empty_kernel(const uint32_t* __restrict__ perm, const uint32_t* __restrict__ sizes, uint32_t n, uint32_t* __restrict__ has_empty)
 {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;            // grouped position
-    if (g < n && sizes[perm[g]] == 0) has_empty[g >> 5] = 1;
+    if (g < n && sizes[perm ? perm[g] : g] == 0) has_empty[g >> 5] = 1;
 }
 
 // a thread per (query tile, reference tile = one word of the permuted bitmaps)
 __global__ void __launch_bounds__(256) dist_tile_list_kernel(const uint32_t* __restrict__ marks, uint32_t n_q, uint32_t words, const uint32_t* __restrict__ empty_q,
-                                                             const uint32_t* __restrict__ empty_r, uint2* __restrict__ list, uint32_t* __restrict__ count)
+                                                             const uint32_t* __restrict__ empty_r, uint2* __restrict__ list, uint32_t* __restrict__ count, unsigned long long* __restrict__ n_pairs)
 {
     const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t q_tiles = (n_q + 31) / 32;
     bool work = false;
-    uint32_t qt = 0, rt = 0;
+    uint32_t qt = 0, rt = 0, my_pairs = 0;
     if (idx < (uint64_t)q_tiles * words) {
         qt = (uint32_t)(idx / words); rt = (uint32_t)(idx % words);
-        uint32_t any = 0;
-        for (uint32_t q = qt * 32; q < min(n_q, qt * 32 + 32); q++) any |= marks[(uint64_t)q * words + rt];
+        uint32_t any = 0, pairs = 0;
+        for (uint32_t q = qt * 32; q < min(n_q, qt * 32 + 32); q++) { const uint32_t mk = marks[(uint64_t)q * words + rt]; any |= mk; pairs += __popc(mk); }
         work = any != 0 || (empty_q[qt] && empty_r[rt]);
+        my_pairs = pairs;
     }
+    // marked pairs in all: one atomic per warp (in natural order every tile of an unordered collection holds some)
+    for (int o = 16; o; o >>= 1) my_pairs += __shfl_down_sync(0xffffffffu, my_pairs, o);
+    if ((threadIdx.x & 31) == 0 && my_pairs) atomicAdd(n_pairs, (unsigned long long)my_pairs);
     // warp-aggregated append: the list stays roughly in row-major tile order
     const uint32_t m = __ballot_sync(0xffffffffu, work);
     if (!m) return;
@@ -530,7 +534,7 @@ __global__ void __launch_bounds__(256) dist_tile_list_kernel(const uint32_t* __r
 }
 
 int dist_tile_list(fpm_ctx* ctx, const uint32_t* marks, uint64_t n_q, uint64_t n_r, const uint32_t* perm_q, const uint32_t* perm_r,
-                   const uint32_t* size_q, const uint32_t* size_r, const uint2** list, uint32_t* n_listed)
+                   const uint32_t* size_q, const uint32_t* size_r, const uint2** list, uint32_t* n_listed, uint64_t* n_pairs)
 {
     cudaStream_t st = ctx->stream;
     const uint32_t words = (uint32_t)((n_r + 31) / 32), q_tiles = (uint32_t)((n_q + 31) / 32);
@@ -545,11 +549,14 @@ int dist_tile_list(fpm_ctx* ctx, const uint32_t* marks, uint64_t n_q, uint64_t n
     FPM_CUDA(cudaMemsetAsync(b, 0, 256 + a_e, st));
     dist_tile_empty_kernel<<<(uint32_t)((n_q + 255) / 256), 256, 0, st>>>(perm_q, size_q, (uint32_t)n_q, empty_q);
     dist_tile_empty_kernel<<<(uint32_t)((n_r + 255) / 256), 256, 0, st>>>(perm_r, size_r, (uint32_t)n_r, empty_r);
-    dist_tile_list_kernel<<<(uint32_t)((tiles + 255) / 256), 256, 0, st>>>(marks, (uint32_t)n_q, words, empty_q, empty_r, out, count);
+    dist_tile_list_kernel<<<(uint32_t)((tiles + 255) / 256), 256, 0, st>>>(marks, (uint32_t)n_q, words, empty_q, empty_r, out, count, (unsigned long long*)(b + 8));
     ctx->launches += 3;
     FPM_CUDA(cudaGetLastError());
-    FPM_CUDA(cudaMemcpyAsync(n_listed, count, 4, cudaMemcpyDeviceToHost, st));
+    uint64_t h[2] = {0, 0};
+    FPM_CUDA(cudaMemcpyAsync(h, b, 16, cudaMemcpyDeviceToHost, st));
     FPM_CUDA(cudaStreamSynchronize(st));
+    *n_listed = (uint32_t)h[0];
+    if (n_pairs) *n_pairs = h[1];
     *list = out;
     return FPM_OK;
 }

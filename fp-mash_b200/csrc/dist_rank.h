@@ -21,10 +21,12 @@ int dist_group_panels(fpm_ctx* ctx, uint64_t n_q, uint64_t n_r, uint64_t rows_q,
 // writes them in grouped order itself.)
 int dist_pack_queries(fpm_ctx* ctx, const uint32_t* d_sizes_q, uint64_t n_q, uint64_t rows_q, uint32_t** p32q);
 
-// After dist_group_panels: the 32 x 32 tiles (grouped order) that hold a marked pair, or an empty query together with an
-// empty reference (such a pair has distance 0 without sharing a hash), as (query tile, reference tile) in device memory.
+// The 32 x 32 tiles (in the panels' current order: perm_q / perm_r after dist_group_panels, null = natural order) that hold a
+// marked pair, or an empty query together with an empty reference (such a pair has distance 0 without sharing a hash), as
+// (query tile, reference tile) in device memory; *n_pairs (nullable) = marked pairs in all.  n_listed * 1024 against n_pairs
+// says how scattered the marked pairs are: run_dist regroups the panels only when that pays.
 int dist_tile_list(fpm_ctx* ctx, const uint32_t* marks, uint64_t n_q, uint64_t n_r, const uint32_t* perm_q, const uint32_t* perm_r,
-                   const uint32_t* size_q, const uint32_t* size_r, const uint2** list, uint32_t* n_listed);
+                   const uint32_t* size_q, const uint32_t* size_r, const uint2** list, uint32_t* n_listed, uint64_t* n_pairs);
 
 // fpm_dist_hits: `n` hits appended in arbitrary order at `in` -> `out` sorted by (query, ref).  in != out.
 int dist_sort_hits(fpm_ctx* ctx, const fpm_hit* in, uint64_t n, uint64_t n_qry, uint64_t n_ref, fpm_hit* out, uint32_t q_base = 0, uint32_t r_base = 0);

@@ -304,11 +304,12 @@ class Context:
     def launch_count(self):
         return int(lib.fpm_ctx_launch_count(self._h))
 
-    def set_dist_mode(self, force64=False, no_prune=False, no_group=False, saturate=False):
+    def set_dist_mode(self, force64=False, no_prune=False, no_group=False, saturate=False, group=False):
         """force64=True: run the 64-bit tile kernel even where the 32-bit rank kernel applies; no_prune=True: the rank
         kernel merges every pair (no skipping of pairs that share no hash); saturate=True: always bound the marking walks
-        by the sizes of the reference components (by default only when the panels are large enough for that to pay)."""
-        _check(lib.fpm_ctx_set_dist_mode(self._h, 1 if force64 else (2 if no_prune else (3 if no_group else (4 if saturate else 0)))))
+        by the sizes of the reference components (by default only when the panels are large enough for that to pay); group=True:
+        always reorder the panels so that related sketches share tiles (by default only when the marked pairs are scattered)."""
+        _check(lib.fpm_ctx_set_dist_mode(self._h, 1 if force64 else (2 if no_prune else (3 if no_group else (4 if saturate else (5 if group else 0))))))
 
     def set_timing(self, enable=True):
         _check(lib.fpm_ctx_set_timing(self._h, int(enable)))

@@ -367,6 +367,7 @@ int fpm_fp_positional_tile(fpm_ctx* ctx, const fpm_dist_params* p, const fpm_pan
 #define FPM_DIST_NO_PRUNE 2   /* 32-bit rank kernel, but merge every pair (no disjoint-pair pruning)           */
 #define FPM_DIST_NO_GROUP 3   /* prune, but do not reorder the panels so that related sketches share tiles     */
 #define FPM_DIST_SATURATE 4   /* prune, and always bound the marking walks by component sizes (default: only when it pays) */
+#define FPM_DIST_GROUP 5      /* prune, and always reorder the panels (default: only when the marked pairs are scattered over the tiles) */
 int fpm_ctx_set_dist_mode(fpm_ctx* ctx, int mode);
 
 /* Scalar helpers exported for host code and tests (same code the kernels run).             */

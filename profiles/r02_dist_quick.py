@@ -32,3 +32,19 @@ for name, mode in (("merge_all", {"no_prune": True}), ("pruned", {})):
     print("%-9s step %.3f ms (min of 5)  tiles %.3f  prepass %.3f  digest %s" % (name, min(ts), tile[0] / 5, pack[0] / 5,
           [int(x) for x in bench.pair_digest(torch, out, nd * nd).tolist()]))
 ctx.set_dist_mode()
+# the same collection with relatives next to each other (rows sorted by family), as a taxonomy-ordered sketch file would have them:
+# the default leaves such panels in their own order; group=True regroups them anyway
+order = torch.argsort(torch.arange(nd, device=dev) % 20, stable=True)
+panel_o = panel[order].contiguous()
+ptrs_o = (panel_o.data_ptr(), sizes.data_ptr(), lengths.data_ptr(), nd, S)
+for name, mode in (("ordered", {}), ("ordered, regrouped anyway", {"group": True})):
+    ctx.set_dist_mode(**mode)
+    for _ in range(2):
+        ctx.dist_tile_dev(ptrs_o, ptrs_o, S, K, 4.0 ** K, out.data_ptr())
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(5):
+        e0.record(); ctx.dist_tile_dev(ptrs_o, ptrs_o, S, K, 4.0 ** K, out.data_ptr()); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    print("%-26s step %.3f ms (min of 5)  digest %s" % (name, min(ts), [int(x) for x in bench.pair_digest(torch, out, nd * nd).tolist()]))
+ctx.set_dist_mode()

@@ -249,7 +249,8 @@ def test_dist_device_path_grouped_equals_ungrouped(ctx, n_r, n_q):
     d_rh, d_rs, d_rl = t(rh, np.int64), t(rs.astype(np.uint32), np.int32), t(rl, np.int64)
     d_qh, d_qs, d_ql = t(qh, np.int64), t(qs.astype(np.uint32), np.int32), t(ql, np.int64)
     outs = []
-    for kw in (dict(), dict(no_group=True), dict(no_prune=True)):
+    # default = regroup only when the marked pairs are scattered; group=True always; no_group: neither regrouping nor the tile list
+    for kw in (dict(), dict(group=True), dict(no_group=True), dict(no_prune=True)):
         ctx.set_dist_mode(**kw)
         try:
             out = torch.zeros(n_q * n_r * 24, dtype=torch.uint8, device=dev)
@@ -259,7 +260,7 @@ def test_dist_device_path_grouped_equals_ungrouped(ctx, n_r, n_q):
             outs.append(out.cpu().numpy().tobytes())
         finally:
             ctx.set_dist_mode()
-    assert outs[0] == outs[1] == outs[2]
+    assert outs[0] == outs[1] == outs[2] == outs[3]
     assert outs[0] == np.ascontiguousarray(want).tobytes()
 
 
@@ -352,7 +353,7 @@ def test_dist_hits_device_entry_point(ctx):
     d_qh, d_qs, d_ql = t(qh, np.int64), t(qs.astype(np.uint32), np.int32), t(ql, np.int64)
     cap = len(q) + 5
     steps = torch.zeros(1, dtype=torch.int64, device=dev)
-    for kw in (dict(), dict(no_group=True), dict(no_prune=True)):
+    for kw in (dict(), dict(group=True), dict(no_group=True), dict(no_prune=True)):
         ctx.set_dist_mode(**kw)
         try:
             out = torch.zeros(cap * 32, dtype=torch.uint8, device=dev)
@@ -438,7 +439,7 @@ def test_dist_long_reference_chains_same_in_every_mode(ctx, fpm):
     rs = np.full(n_r, s, dtype=np.uint32); qs = np.full(n_q, s, dtype=np.uint32)
     rl = np.full(n_r, 1_000_000, dtype=np.uint64); ql = np.full(n_q, 1_000_000, dtype=np.uint64)
     outs = []
-    for mode in ({"saturate": True}, {}, {"no_group": True}, {"no_prune": True}):
+    for mode in ({"saturate": True}, {}, {"group": True}, {"no_group": True}, {"no_prune": True}):
         ctx.set_dist_mode(**mode)
         try:
             for _ in range(3 if mode.get("saturate") else 1):                            # the race was rare: repeat

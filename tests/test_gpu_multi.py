@@ -87,7 +87,7 @@ ctx = fpm.Context(rank)
 ctx.set_stream(torch.cuda.current_stream().cuda_stream)
 sh.init_comm(ctx)
 for case, (n_r, n_q, s, mode) in enumerate([(1500, 1500, 200, {}), (333, 2047, 96, {}), (1500, 1500, 200, {"no_prune": True}), (5, 3, 50, {}),
-                                            (1500, 1500, 200, {"p2p": 1}), (333, 2047, 96, {"p2p": 1})]):
+                                            (1500, 1500, 200, {"p2p": 1}), (333, 2047, 96, {"p2p": 1}), (1500, 1500, 200, {"group": True})]):
     # the exchange step: all-gather + keep the block (default for panels of this size) or grouped send/receive of just the block's shards
     os.environ["FPMASH_EXCHANGE"] = "p2p" if mode.pop("p2p", 0) else "allgather"
     rng = np.random.default_rng(100 + case %% 4)             # same panels on every rank; each keeps only its row shards
