@@ -358,3 +358,42 @@ def test_gunzip_core_on_the_cpu_equals_zlib(tmp_path):
         (tmp_path / "in.gz").write_bytes(gz)
         r = subprocess.run([exe, str(tmp_path / "in.gz"), str(tmp_path / "out")], timeout=120)
         assert r.returncode == 2, name
+
+
+def test_gunzip_core_random_streams(tmp_path):
+    """Randomised: inputs from incompressible to highly repetitive, every zlib level / strategy / window size / memLevel
+    (memLevel changes how often a block ends), through the CPU run of the decoder core."""
+    import random
+    import zlib
+    exe = str(tmp_path / "gunzip_sim")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-x", "c++", os.path.join(ROOT, "tests", "native", "gunzip_sim.cpp"), "-o", exe], check=True)
+    rnd = random.Random(20260)
+    strategies = [zlib.Z_DEFAULT_STRATEGY, zlib.Z_FILTERED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FIXED]
+    for case in range(120):
+        n = rnd.choice([0, 1, 2, 31, 257, 4096, 65535, 65536, 70000, 300000])
+        kind = case % 4
+        if kind == 0:
+            data = bytes(rnd.getrandbits(8) for _ in range(n))
+        elif kind == 1:
+            data = "".join(rnd.choice("ACGT") for _ in range(n)).encode()
+        elif kind == 2:
+            unit = bytes(rnd.getrandbits(8) for _ in range(rnd.choice([1, 2, 3, 7, 100, 5000])))
+            data = (unit * (n // len(unit) + 1))[:n]
+        else:
+            words = [bytes(rnd.getrandbits(8) for _ in range(rnd.randint(1, 12))) for _ in range(50)]
+            data = b"".join(rnd.choice(words) for _ in range(n // 6 + 1))[:n]
+        co = zlib.compressobj(rnd.randint(0, 9), zlib.DEFLATED, 16 + rnd.randint(9, 15), rnd.randint(1, 9), rnd.choice(strategies))
+        gz = co.compress(data) + co.flush()
+        (tmp_path / "in.gz").write_bytes(gz)
+        r = subprocess.run([exe, str(tmp_path / "in.gz"), str(tmp_path / "out")], timeout=120)
+        assert r.returncode == 0, case
+        assert (tmp_path / "out").read_bytes() == data, case
+        # one flipped bit somewhere: refused (CRC) or, if the flip hit a don't-care header byte, still the same data
+        if len(gz) > 30 and case % 3 == 0:
+            g = bytearray(gz)
+            g[rnd.randrange(10, len(g))] ^= 1 << rnd.randrange(8)
+            (tmp_path / "in.gz").write_bytes(bytes(g))
+            r = subprocess.run([exe, str(tmp_path / "in.gz"), str(tmp_path / "out")], timeout=120)
+            assert r.returncode in (0, 2), case
+            if r.returncode == 0:
+                assert (tmp_path / "out").read_bytes() == data, case
