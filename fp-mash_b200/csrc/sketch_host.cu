@@ -111,7 +111,7 @@ int sketch_batch_dev_impl(fpm_ctx* ctx, const fpm_sketch_params* p, const uint8_
     int rc = check_params(p);
     if (rc) return rc;
     if (n_groups == 0) return FPM_OK;
-    if (!d_seq || !h_goff || !d_out_hashes || !d_out_n) { set_error("NULL buffer"); return FPM_ERR_ARG; }
+    if ((!d_seq && n_bytes) || !h_goff || !d_out_hashes || !d_out_n) { set_error("NULL buffer"); return FPM_ERR_ARG; }   // (an empty batch has no buffer: a read set whose reads are all shorter than k)
     if (h_goff[0] != 0 || h_goff[n_groups] != n_bytes) { set_error("group_offsets must start at 0 and end at seq_bytes"); return FPM_ERR_ARG; }
     for (uint32_t g = 0; g < n_groups; g++)
         if (h_goff[g + 1] < h_goff[g]) { set_error("group_offsets not ascending at %u", g); return FPM_ERR_ARG; }
@@ -893,6 +893,22 @@ int fpm_sketch_stream_append(fpm_ctx* ctx, const uint8_t* seq, uint64_t bytes)
     if (rc) return rc;
     FPM_CUDA(cudaMemcpyAsync((uint8_t*)ctx->stream_buf.p + ctx->stream_used, seq, bytes, cudaMemcpyHostToDevice, ctx->stream));
     FPM_CUDA(cudaStreamSynchronize(ctx->stream));   // the caller may reuse its staging buffer right away
+    ctx->stream_used += bytes;
+    return FPM_OK;
+}
+
+// The compacted sequence the last fpm_fasta_parse left on the device (records back to back, each followed by 0x00 -- the
+// stream's own layout) goes to the end of the stream: FASTA read sets never cross PCIe twice.
+int fpm_sketch_stream_append_parsed(fpm_ctx* ctx)
+{
+    if (!ctx) { set_error("ctx is NULL"); return FPM_ERR_ARG; }
+    if (ctx->stream_goff.empty()) { set_error("fpm_sketch_stream_begin was not called"); return FPM_ERR_ARG; }
+    const uint64_t bytes = ctx->fa_seq_bytes;
+    if (bytes == 0) return FPM_OK;
+    FPM_CUDA(cudaSetDevice(ctx->device));
+    int rc = fpm::stream_reserve(ctx, bytes);
+    if (rc) return rc;
+    FPM_CUDA(cudaMemcpyAsync((uint8_t*)ctx->stream_buf.p + ctx->stream_used, ctx->fa_seq.p, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     ctx->stream_used += bytes;
     return FPM_OK;
 }

@@ -756,8 +756,9 @@ void Sketch::initFromFingerprints(const vector<string>& files, const Parameters&
     cout << "Initialization complete." << endl;
 }
 
-// `mash sketch -r reads.fastq` without the host reader: pieces of ~256 MB, each cut at a record boundary, go to
-// fpm_fastq_stream_append.  Returns false (nothing usable was produced) if the file is not clean four-line FASTQ.
+// `mash sketch -r reads.fastq` (or reads.fa) without the host reader: pieces, each cut at a record boundary, go to
+// fpm_fastq_stream_append (four-line FASTQ) or to fpm_fasta_parse + fpm_sketch_stream_append_parsed (FASTA reads).
+// Returns false (nothing usable was produced) if the file is neither clean four-line FASTQ nor plain FASTA.
 // Metadata as sketchFile keeps it (Sketch.cpp:1380-1393,1436-1444): comment from the first read of at least k bases
 // (with kseq's stale-comment quirk, so the headers before it are walked too), count of such reads.
 static bool readsViaGpu(const string& file, const Sketch::Parameters& parameters, Sketch::Reference& reference, uint64_t& count, bool& skipped)
@@ -775,7 +776,8 @@ static bool readsViaGpu(const string& file, const Sketch::Parameters& parameters
     gpuCheck(fpm_host_alloc(kPiece + 64, &pinned));
     uint8_t* buf = (uint8_t*)pinned;
     uint64_t used = 0, fileOff = 0;
-    bool eof = false, ok = true, first = true, haveComment = false;
+    bool eof = false, ok = true, first = true, haveComment = false, fasta = false;
+    vector<fpm_fasta_record> recs;
     string name, comment, commentCstr;
     reference.name = file;
     reference.length = 0;
@@ -808,7 +810,53 @@ static bool readsViaGpu(const string& file, const Sketch::Parameters& parameters
             if (fileOff >= fileSize) eof = true;
         }
         if (first && used >= 2 && buf[0] == 0x1f && buf[1] == 0x8b) { ok = false; break; }     // gzip behind a plain name
+        if (first) {
+            // kseq looks for the first '>' or '@' (kseq.h:172): that byte decides which parser takes the file
+            const uint8_t* gt = (const uint8_t*)memchr(buf, '>', used);
+            const uint8_t* at = (const uint8_t*)memchr(buf, '@', used);
+            fasta = gt && (!at || gt < at);
+        }
         first = false;
+        if (fasta) {
+            // ---- FASTA reads: pieces cut at "\n>" (always a record start), parsed by fpm_fasta_parse, appended device to device ----
+            uint64_t cut = used;
+            if (!eof) {
+                cut = 0;
+                for (uint64_t p = used; p > 1; p--)
+                    if (buf[p - 1] == '>' && buf[p - 2] == '\n') { cut = p - 1; break; }
+                if (cut == 0) { ok = false; break; }                                          // one record larger than a piece: host reader
+            }
+            if (cut == 0) break;
+            if (memchr(buf, 0, cut) != nullptr) { ok = false; break; }                        // 0x00 separates files for the device parser
+            const uint8_t saved = buf[cut];
+            buf[cut] = 0;
+            uint64_t nRec = 0, seqBytes = 0;
+            int status = 0;
+            gpuCheck(fpm_fasta_parse(gpuContext(), buf, cut + 1, &nRec, &seqBytes, &status));
+            buf[cut] = saved;
+            if (status != FPM_FASTA_OK) { ok = false; break; }
+            recs.resize(nRec);
+            if (nRec) gpuCheck(fpm_fasta_records(gpuContext(), recs.data()));
+            gpuCheck(fpm_sketch_stream_append_parsed(gpuContext()));
+            for (uint64_t r = 0; r < nRec; r++) {
+                const uint64_t seqEnd = r + 1 < nRec ? recs[r + 1].seq_begin : seqBytes;
+                const uint64_t l = seqEnd - recs[r].seq_begin - 1;
+                const bool atEof = recs[r].hdr_end == cut;                                    // header ended by the end of the file, not by '\n'
+                if (atEof && recs[r].hdr_end == recs[r].hdr_begin + 1) continue;              // a lone '>' as the last byte: no record for kseq
+                if (!haveComment) parseHeader(buf + recs[r].hdr_begin + 1, buf + recs[r].hdr_end, atEof, name, comment, commentCstr);
+                if (l < (uint64_t)parameters.kmerSize) { skipped = true; continue; }
+                if (!haveComment) {
+                    reference.comment = name;
+                    reference.comment.append(" ");
+                    reference.comment.append(commentCstr.c_str());
+                    haveComment = true;
+                }
+                count++;
+            }
+            memmove(buf, buf + cut, used - cut);
+            used -= cut;
+            continue;
+        }
         uint64_t cut = used;
         if (eof) {
             if (used && buf[used - 1] != '\n') buf[used++] = '\n';                            // a last line without newline parses the same
@@ -920,8 +968,8 @@ void Sketch::initFromReads(const vector<string>& files, const Parameters& parame
     bool skipped = false;
     // One plain FASTQ file: its four-line records are parsed on the GPU, piece by piece, straight into the HBM
     // stream (csrc/fasta_parse.cu).  Anything else -- several files feeding one sketch (their records interleave,
-    // Sketch.cpp:1352-1422), gzip, stdin, FASTA reads, FASTQ that is not four clean lines per record -- takes the
-    // host reader; if the GPU route gives up half way the stream is restarted from scratch.
+    // Sketch.cpp:1352-1422), gzip, stdin, FASTQ that is not four clean lines per record -- takes the host reader; if the
+    // GPU route gives up half way the stream is restarted from scratch.  (FASTA reads: the FASTA parser, piece by piece.)
     const char* gpuParseEnv = getenv("FPMASH_GPU_PARSE");
     bool viaGpu = !(gpuParseEnv && gpuParseEnv[0] == '0') && files.size() == 1 && files[0] != "-" && !hasSuffix(files[0], ".gz");
     if (viaGpu) {

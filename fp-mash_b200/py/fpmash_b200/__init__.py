@@ -112,6 +112,7 @@ lib.fpm_fasta_sequence.argtypes = [_VP, _VP]
 lib.fpm_gunzip_batch.argtypes = [_VP, _VP, _VP, C.c_uint32, _VP, u64p, C.POINTER(C.c_int)]
 lib.fpm_gunzip_output.argtypes = [_VP, _VP]
 lib.fpm_fasta_headers.argtypes = [_VP, _VP, _VP]
+lib.fpm_sketch_stream_append_parsed.argtypes = [_VP]
 lib.fpm_sketch_parsed.argtypes = [_VP, C.POINTER(SketchParams), _VP, C.c_uint32, _VP, _VP, _VP]
 FASTA_RECORD_DTYPE = np.dtype([("hdr_begin", "<u8"), ("hdr_end", "<u8"), ("seq_begin", "<u8")])
 lib.fpm_dist_hits.argtypes = [_VP, _VP, _VP, _VP, _VP, C.c_uint64, u64p]
@@ -194,7 +195,7 @@ EXPORTED = ["fpm_abi_version", "fpm_device_count", "fpm_ctx_create", "fpm_ctx_de
             "fpm_comm_destroy", "fpm_comm_rank", "fpm_comm_size", "fpm_dist_sharded_dev", "fpm_dist_hits_sharded_dev",
             "fpm_multi_create", "fpm_multi_destroy", "fpm_multi_size", "fpm_multi_ctx", "fpm_dist_tile_multi", "fpm_dist_hits_multi",
             "fpm_sketch_batch_multi", "fpm_sketch_reads_sharded_dev", "fpm_dist_set_reference", "fpm_sketch_stream_append_async", "fpm_sketch_stream_wait",
-            "fpm_gunzip_batch", "fpm_gunzip_output", "fpm_fasta_headers"]
+            "fpm_gunzip_batch", "fpm_gunzip_output", "fpm_fasta_headers", "fpm_sketch_stream_append_parsed"]
 
 
 def _check(rc):
@@ -431,6 +432,29 @@ class Context:
         _check(lib.fpm_sketch_stream_finish(self._h, C.byref(params), hashes.ctypes.data,
                                             counts.ctypes.data if params.want_counts else None, n.ctypes.data, None))
         return dict(hashes=hashes[0, :n[0]].copy(), counts=counts[0, :n[0]].copy()), infos
+
+    def sketch_fasta_pieces(self, pieces, **kw):
+        """One read set given as raw FASTA pieces (each starting at a record boundary): every piece is parsed on the GPU
+        (fpm_fasta_parse) and its compacted sequence appended to the read stream device to device; sketched as ONE group.
+        Returns None if a piece is not plain FASTA, else dict(hashes, counts)."""
+        params = make_sketch_params(**kw)
+        _check(lib.fpm_sketch_stream_begin(self._h))
+        for pc in pieces:
+            raw = np.frombuffer(bytes(pc) + b"\0", dtype=np.uint8).copy()
+            nrec, nseq, status = C.c_uint64(0), C.c_uint64(0), C.c_int(0)
+            _check(lib.fpm_fasta_parse(self._h, raw.ctypes.data, raw.size, C.byref(nrec), C.byref(nseq), C.byref(status)))
+            if status.value != 0:
+                _check(lib.fpm_sketch_stream_end_group(self._h))
+                return None
+            _check(lib.fpm_sketch_stream_append_parsed(self._h))
+        _check(lib.fpm_sketch_stream_end_group(self._h))
+        s = params.sketch_size
+        hashes = np.zeros((1, s), dtype=np.uint64)
+        counts = np.zeros((1, s), dtype=np.uint32)
+        n = np.zeros(1, dtype=np.uint32)
+        _check(lib.fpm_sketch_stream_finish(self._h, C.byref(params), hashes.ctypes.data,
+                                            counts.ctypes.data if params.want_counts else None, n.ctypes.data, None))
+        return dict(hashes=hashes[0, :n[0]].copy(), counts=counts[0, :n[0]].copy())
 
     def fastq_line_ends(self, first_line, n_lines):
         out = np.zeros(max(n_lines, 1), dtype=np.uint64)

@@ -212,6 +212,10 @@ int fpm_fasta_headers(fpm_ctx* ctx, const uint64_t* offsets /* [n_records+1] */,
 #define FPM_FASTQ_INFO_WORDS 6
 int fpm_fastq_stream_append(fpm_ctx* ctx, const uint8_t* raw, uint64_t n_bytes, uint32_t min_len, int* out_status, uint64_t* out_info /* [6] */);
 int fpm_fastq_line_ends(fpm_ctx* ctx, uint64_t first_line, uint64_t n_lines, uint64_t* out);
+/* FASTA read sets (`mash sketch -r reads.fa`): the compacted sequence of the last fpm_fasta_parse (records back to back,
+ * each followed by 0x00 = the stream's layout) is appended to the HBM read stream of fpm_sketch_stream_begin, device to
+ * device.  The caller cuts the file into pieces at record boundaries ("\n>") and parses piece after piece.              */
+int fpm_sketch_stream_append_parsed(fpm_ctx* ctx);
 /* fpm_sketch_batch over the sequence the last fpm_fasta_parse left on the device (group_offsets in compacted
  * coordinates, from 0 to seq_bytes).                                                                        */
 int fpm_sketch_parsed(fpm_ctx* ctx, const fpm_sketch_params* p, const uint64_t* group_offsets, uint32_t n_groups, uint64_t* out_hashes,

@@ -251,3 +251,58 @@ def test_cli_read_mode_gpu_fastq_route_equals_host_reader_route(tmp_path):
     assert "reads parsed on the GPU" not in t.stderr
     t = subprocess.run([MASH, "sketch", "-k", "21", "-s", "500", "-o", "trace2", "reads.fa"], cwd=tmp_path, capture_output=True, text=True, env=envt)
     assert "fasta parsed on the GPU" in t.stderr
+
+
+def test_fasta_read_set_pieces_equal_streamed_reads(ctx):
+    """FASTA reads parsed on the GPU piece by piece and appended device to device = the same reads streamed from the host."""
+    rng = np.random.default_rng(21)
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    reads = [lut[rng.integers(0, 4, size=int(rng.integers(5, 400)))].tobytes() for _ in range(3000)]
+    reads = reads + reads[:1500]                                       # repeated reads: counts >= 2
+    text = [b">r%d c%d\n" % (i, i) + b"\n".join(r[j:j + 70] for j in range(0, len(r), 70)) + b"\n" for i, r in enumerate(reads)]
+    kw = dict(k=21, s=300, min_cov=2, want_counts=True)
+    want = ctx.sketch_stream([reads], **kw)[0]
+    for cuts in ([0, len(text)], [0, 1, 2, 900, 901, 4499, len(text)]):
+        got = ctx.sketch_fasta_pieces([b"".join(text[a:b]) for a, b in zip(cuts[:-1], cuts[1:])], **kw)
+        assert got is not None
+        assert np.array_equal(got["hashes"], want["hashes"]) and np.array_equal(got["counts"], want["counts"])
+    assert ctx.sketch_fasta_pieces([b">r\nACGT\n+\nIIII\n"], **kw) is None
+
+
+def test_cli_read_mode_fasta_reads_gpu_route_equals_host_reader_route(tmp_path):
+    """`mash sketch -r -m 2` on FASTA reads (wrapped lines, comments, short first reads, CRLF, no final newline, a lone '>' at
+    the end): the GPU route in small pieces and the host reader write the same .msh; the timing trace names the route."""
+    rng = np.random.default_rng(22)
+    lut = np.frombuffer(b"ACGTN", dtype=np.uint8)
+    reads = [lut[rng.integers(0, 5 if i % 50 == 0 else 4, size=int(rng.integers(3, 500)))].tobytes() for i in range(4000)]
+    def fasta(rs, eol=b"\n", width=60):
+        return b"".join(b">read%d some comment %d" % (i, i) * (i % 3 != 0) + b">r%d" % i * (i % 3 == 0) + eol +
+                        eol.join(r[j:j + width] for j in range(0, len(r), width)) + eol for i, r in enumerate(rs))
+    base = fasta(reads) * 2
+    files = {
+        "reads.fa": base,
+        "short_first.fa": b">tiny first comment\nACGT\n>tiny2\nAC\n" + base,
+        "no_final_newline.fa": base.rstrip(b"\n"),
+        "lone_gt.fa": base + b">",
+        "crlf.fa": fasta(reads[:800], eol=b"\r\n") * 2,
+        "junk_first.fa": b"junk before the first record\n" + base,
+        "all_short.fa": b">a c\nACGT\n>b\nACG\n",
+    }
+    for nm, data in files.items():
+        (tmp_path / nm).write_bytes(data)
+    env0 = dict(os.environ, FPMASH_GPU_PARSE="0")
+    envp = dict(os.environ, FPMASH_FASTQ_PIECE="65536")
+    for nm in files:
+        opts = ["sketch", "-r", "-m", "2", "-k", "21", "-s", "400"]
+        a = subprocess.run([MASH] + opts + ["-o", "gpu_" + nm, nm], cwd=tmp_path, capture_output=True, text=True)
+        c = subprocess.run([MASH] + opts + ["-o", "pcs_" + nm, nm], cwd=tmp_path, capture_output=True, text=True, env=envp)
+        b = subprocess.run([MASH] + opts + ["-o", "host_" + nm, nm], cwd=tmp_path, capture_output=True, text=True, env=env0)
+        assert a.returncode == b.returncode == c.returncode, (nm, a.stderr, b.stderr, c.stderr)
+        assert a.stderr.replace("gpu_", "") == b.stderr.replace("host_", "") == c.stderr.replace("pcs_", ""), nm
+        if a.returncode == 0:
+            want = (tmp_path / ("host_%s.msh" % nm)).read_bytes()
+            assert (tmp_path / ("gpu_%s.msh" % nm)).read_bytes() == want, nm
+            assert (tmp_path / ("pcs_%s.msh" % nm)).read_bytes() == want, nm
+    envt = dict(os.environ, FPMASH_TIMING="1")
+    t = subprocess.run([MASH, "sketch", "-r", "-k", "21", "-s", "400", "-o", "trace", "reads.fa"], cwd=tmp_path, capture_output=True, text=True, env=envt)
+    assert "reads parsed on the GPU" in t.stderr
