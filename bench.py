@@ -510,7 +510,7 @@ def main():
         # e2e on a stated sample of query rows (host panels in, 24-byte records out), and the CPU reference on a sample of the DEVICE output
         if rank == 0 and world == 1:
             qs_n = min(nd, 8192)
-            hp = panel.cpu().numpy().view(np.uint64)
+            hp = panel.cpu().pin_memory().numpy().view(np.uint64)            # pinned host panels (the contract's "inputs from pinned host memory")
             hs = np.full(nd, S, dtype=np.uint32)
             hl = np.full(nd, 5_000_000, dtype=np.uint64)
             pinned = torch.empty(qs_n * nd * 24, dtype=torch.uint8, pin_memory=True).numpy().view(fpm.PAIR_DTYPE).reshape(qs_n, nd)
@@ -523,7 +523,7 @@ def main():
             cap = 64 << 20
             hit_buf = torch.empty(cap * 32, dtype=torch.uint8, pin_memory=True).numpy().view(fpm.HIT_DTYPE)
             try:
-                php = panel.cpu().pin_memory().numpy().view(np.uint64)     # pinned host panels, as a caller that cares would hold them
+                php = hp
                 ctx.dist_hits((php, hs, hl), (php, hs, hl), S, K, kspace, max_distance=0.25, out=hit_buf, raw=True)
                 t0 = time.perf_counter()
                 hits = ctx.dist_hits((php, hs, hl), (php, hs, hl), S, K, kspace, max_distance=0.25, out=hit_buf, raw=True)
