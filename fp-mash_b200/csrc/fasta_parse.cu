@@ -255,7 +255,9 @@ __global__ void __launch_bounds__(256) fasta_emit_kernel(const uint8_t* __restri
 // line number is a prefix sum of newlines.  Everything the general reader would treat differently is detected and
 // reported as FPM_FASTA_NOT_PLAIN (the caller restarts with the host reader): a header not starting with '@', a
 // third line not starting with '+', a sequence byte outside 33..126 or one of '>' '+' '@', a quality byte outside
-// 33..127, '\r' or 0x00 anywhere, sequence and quality of different lengths, a line count not divisible by four.
+// 33..127, 0x00 anywhere, a '\r' in a sequence or quality line that is not the last byte before the '\n' (CRLF files: the reader
+// drops that '\r' from sequence and quality and keeps it in the header's comment, and so does this parser), sequence and quality
+// lines of different lengths, a line count not divisible by four.
 // The buffer must start at a record boundary and end with '\n'.
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) fastq_newline_kernel(const uint8_t* __restrict__ raw, uint64_t n, uint64_t n_chunks, uint32_t* __restrict__ cnt_nl,
@@ -273,7 +275,7 @@ __global__ void __launch_bounds__(256) fastq_newline_kernel(const uint8_t* __res
         for (int j = 0; j < 4; j++) {
             const uint32_t b = (w >> (8 * j)) & 0xffu;
             c += b == '\n';
-            bad |= (b == '\r') | (b == 0);
+            bad |= (b == 0);
         }
     }
     for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
@@ -312,15 +314,20 @@ __global__ void __launch_bounds__(256) fastq_emit_kernel(const uint8_t* __restri
         uint64_t my_line = line + (inc - nl);
         uint32_t before = __shfl_up_sync(0xffffffffu, w >> 24, 1);  // last byte of the previous lane
         if (lane == 0) before = prev_last;
+        uint32_t after = __shfl_down_sync(0xffffffffu, w & 0xffu, 1);   // first byte of the next lane
+        if (lane == 31) after = pos + 4 < n ? raw[pos + 4] : '\n';
         uint8_t ob[4];
         uint32_t nb = 0;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const uint32_t b = (w >> (8 * j)) & 0xffu;
+            const uint32_t next = j < 3 ? (w >> (8 * (j + 1))) & 0xffu : after;
             if (pos + j < n) {
                 const uint32_t role = (uint32_t)my_line & 3u;
                 const bool first = before == '\n';
-                if (b == '\n') {
+                if (b == '\r' && (role == 1 || role == 3)) {
+                    if (!(pos + j + 1 < n && next == '\n')) bad = 1;     // CRLF only: kseq drops the '\r' of a sequence / quality line
+                } else if (b == '\n') {
                     if (role == 1) ob[nb++] = 0;                    // end of a read
                     if (first && role != 1 && role != 3) bad = 1;   // empty header or '+' line
                     if (WRITE) nlpos[my_line] = pos + j;
@@ -363,13 +370,16 @@ __global__ void __launch_bounds__(256) fastq_emit_kernel(const uint8_t* __restri
 }
 
 // per record: sequence and quality lengths must agree; count the reads of at least min_len bases and find the first one
-__global__ void __launch_bounds__(256) fastq_check_kernel(const uint64_t* __restrict__ nlpos, uint64_t n_reads, uint32_t min_len, uint32_t* __restrict__ flags,
-                                                          unsigned long long* __restrict__ n_valid, unsigned long long* __restrict__ first_valid)
+__global__ void __launch_bounds__(256) fastq_check_kernel(const uint8_t* __restrict__ raw, const uint64_t* __restrict__ nlpos, uint64_t n_reads, uint32_t min_len,
+                                                          uint32_t* __restrict__ flags, unsigned long long* __restrict__ n_valid, unsigned long long* __restrict__ first_valid)
 {
     const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool valid = false, bad = false;
     if (r < n_reads) {
-        const uint64_t len1 = nlpos[4 * r + 1] - nlpos[4 * r] - 1, len3 = nlpos[4 * r + 3] - nlpos[4 * r + 2] - 1;
+        // bases / quality bytes of the record: the line without its '\r' (CRLF files)
+        uint64_t len1 = nlpos[4 * r + 1] - nlpos[4 * r] - 1, len3 = nlpos[4 * r + 3] - nlpos[4 * r + 2] - 1;
+        if (len1 && raw[nlpos[4 * r + 1] - 1] == '\r') len1--;
+        if (len3 && raw[nlpos[4 * r + 3] - 1] == '\r') len3--;
         bad = len1 != len3;
         valid = len1 >= min_len;
     }
@@ -544,7 +554,7 @@ int fpm_fastq_stream_append(fpm_ctx* ctx, const uint8_t* raw, uint64_t n_bytes, 
     uint8_t* dst = (uint8_t*)ctx->stream_buf.p + ctx->stream_used;
     fasta_scan_kernel<<<1, 1024, 0, st>>>(1, n_chunks, nullptr, nullptr, cnt_bytes, cnt_bytes, out_off, scratch, totals);
     fastq_emit_kernel<true><<<grid, 256, 0, st>>>(d_raw, n_bytes, n_chunks, line_base, nullptr, out_off, dst, nlpos, nullptr);
-    if (n_reads) fastq_check_kernel<<<(uint32_t)((n_reads + 255) / 256), 256, 0, st>>>(nlpos, n_reads, min_len, d_flags, d_valid, d_first);
+    if (n_reads) fastq_check_kernel<<<(uint32_t)((n_reads + 255) / 256), 256, 0, st>>>(d_raw, nlpos, n_reads, min_len, d_flags, d_valid, d_first);
     ctx->launches += 3;
     FPM_CUDA(cudaGetLastError());
     FPM_CUDA(cudaMemcpyAsync(h, ctx->d_misc.p, 48, cudaMemcpyDeviceToHost, st));

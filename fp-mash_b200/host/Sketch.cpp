@@ -968,7 +968,7 @@ void Sketch::initFromReads(const vector<string>& files, const Parameters& parame
     bool skipped = false;
     // One plain FASTQ file: its four-line records are parsed on the GPU, piece by piece, straight into the HBM
     // stream (csrc/fasta_parse.cu).  Anything else -- several files feeding one sketch (their records interleave,
-    // Sketch.cpp:1352-1422), gzip, stdin, FASTQ that is not four clean lines per record -- takes the host reader; if the
+    // Sketch.cpp:1352-1422), gzip, stdin, FASTQ that is not four lines per record (LF or CRLF) -- takes the host reader; if the
     // GPU route gives up half way the stream is restarted from scratch.  (FASTA reads: the FASTA parser, piece by piece.)
     const char* gpuParseEnv = getenv("FPMASH_GPU_PARSE");
     bool viaGpu = !(gpuParseEnv && gpuParseEnv[0] == '0') && files.size() == 1 && files[0] != "-" && !hasSuffix(files[0], ".gz");

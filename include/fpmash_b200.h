@@ -204,7 +204,8 @@ int fpm_fasta_headers(fpm_ctx* ctx, const uint64_t* offsets /* [n_records+1] */,
  * of fpm_sketch_stream_begin / _end_group / _finish, each read followed by 0x00, exactly as
  * fpm_sketch_stream_append would have received them from the host reader.  Anything the reference's reader
  * (kseq.h:170-208) would treat differently from "header, sequence, '+' line, quality of equal length" is reported
- * as *out_status = FPM_FASTA_NOT_PLAIN and nothing is appended: restart the read set with the host reader.
+ * as *out_status = FPM_FASTA_NOT_PLAIN and nothing is appended: restart the read set with the host reader.  (CRLF line
+ * ends are fine: the '\r' of a sequence or quality line is dropped, as the reader drops it.)
  * out_info: [0] reads in the piece, [1] reads of at least min_len bases (sketchFile skips the others,
  * Sketch.cpp:1374-1378), [2] bytes appended, [3] index of the first read of at least min_len bases (= [0] if none).
  * fpm_fastq_line_ends returns offsets (in the piece) of the '\n' ending lines first_line .. first_line+n_lines-1 of the

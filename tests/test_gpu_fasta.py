@@ -198,8 +198,15 @@ def test_fastq_gpu_stream_equals_host_records(ctx):
 def test_fastq_gpu_rejects_what_the_general_reader_treats_differently(ctx):
     ok = b"@r1 c\nACGTACGTACGTACGTACGTACGTAC\n+\nIIIIIIIIIIIIIIIIIIIIIIIIII\n"
     assert ctx.sketch_fastq_pieces([ok], k=21, s=10) is not None
+    # CRLF files: the reader drops the '\r' of sequence and quality lines; so does the device parser
+    crlf = ctx.sketch_fastq_pieces([ok.replace(b"\n", b"\r\n") * 3], k=21, s=10)
+    lf = ctx.sketch_fastq_pieces([ok * 3], k=21, s=10)
+    assert crlf is not None and np.array_equal(crlf[0]["hashes"], lf[0]["hashes"]) and crlf[1][0][:2] == lf[1][0][:2] == (3, 3)
+    short = b"@r1\r\nACGTACGTACGTACGTACGT\r\n+\r\nIIIIIIIIIIIIIIIIIIII\r\n"       # 20 bases + '\r': not a read of 21
+    assert ctx.sketch_fastq_pieces([short], k=21, s=10)[1][0][:2] == (1, 0)
     bad = {
-        "crlf": ok.replace(b"\n", b"\r\n"),
+        "cr_inside_sequence": b"@r1\nAC\rGT\n+\nIIII\n",
+        "cr_only_on_the_sequence_line": b"@r1\nACGT\r\n+\nIIIII\n",
         "fasta": b">r1\nACGT\n>r2\nACGT\n",
         "short_quality": b"@r1\nACGTACGT\n+\nIIII\n",
         "long_quality": b"@r1\nACGT\n+\nIIIIII\n",
@@ -219,7 +226,7 @@ def test_fastq_gpu_rejects_what_the_general_reader_treats_differently(ctx):
 def test_cli_read_mode_gpu_fastq_route_equals_host_reader_route(tmp_path):
     """`mash sketch -r -m 2` on one plain FASTQ file: GPU route (pieces parsed on the device) and host reader write the
     same .msh, byte for byte -- hashes, counts (order-dependent top count), comment with [N seqs], estimated length.
-    Also inputs the GPU route must hand back: FASTA reads, CRLF FASTQ."""
+    Also CRLF FASTQ (GPU route as well) and FASTA reads (the FASTA parser's route)."""
     import gzip
     from conftest import GOLDEN
     data = gzip.open(os.path.join(GOLDEN, "reads1.fastq.gz"), "rb").read()
@@ -248,7 +255,10 @@ def test_cli_read_mode_gpu_fastq_route_equals_host_reader_route(tmp_path):
     t = subprocess.run([MASH, "sketch", "-r", "-m", "2", "-k", "21", "-s", "500", "-o", "trace", "reads1.fastq"], cwd=tmp_path, capture_output=True, text=True, env=envt)
     assert "reads parsed on the GPU" in t.stderr
     t = subprocess.run([MASH, "sketch", "-r", "-m", "2", "-k", "21", "-s", "500", "-o", "trace", "crlf.fastq"], cwd=tmp_path, capture_output=True, text=True, env=envt)
-    assert "reads parsed on the GPU" not in t.stderr
+    assert "reads parsed on the GPU" in t.stderr                       # CRLF FASTQ too
+    (tmp_path / "wrapped.fastq").write_bytes(b"@r1\nACGTACGTACGTACGTACGTACGT\nACGTACGT\n+\nIIIIIIIIIIIIIIIIIIIIIIII\nIIIIIIII\n" * 4)
+    t = subprocess.run([MASH, "sketch", "-r", "-k", "21", "-s", "500", "-o", "trace", "wrapped.fastq"], cwd=tmp_path, capture_output=True, text=True, env=envt)
+    assert t.returncode == 0 and "reads parsed on the GPU" not in t.stderr      # wrapped lines: the host reader
     t = subprocess.run([MASH, "sketch", "-k", "21", "-s", "500", "-o", "trace2", "reads.fa"], cwd=tmp_path, capture_output=True, text=True, env=envt)
     assert "fasta parsed on the GPU" in t.stderr
 
